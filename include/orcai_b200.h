@@ -1,0 +1,147 @@
+/* liborcai_b200 - C ABI of the B200-native orcAI prediction hot path.
+ *
+ * The reference (ethz-tb/orcAI v1.0.3) is pure Python and has no FFI; its boundary for this
+ * path is the Python function surface of src/orcAI/spectrogram.py and src/orcAI/predict.py.
+ * Each entry point below is what a ctypes binding placed under one of those functions calls
+ * (INTEGRATION.md shows the stubs).  Conventions: plain pointers and sizes, `int` status
+ * (0 = ok, negative = error, text via orcai_last_error), caller-allocated outputs, no C++
+ * exceptions cross the ABI, one context per (process, device); calls on one context are not
+ * thread-safe, distinct contexts are independent.  There is no CPU fallback: every entry
+ * point that computes needs a CUDA device (sm_100a build).
+ */
+#ifndef ORCAI_B200_H
+#define ORCAI_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ORCAI_OK 0
+#define ORCAI_ERR_ARG (-1)         /* bad argument / unsupported parameter set */
+#define ORCAI_ERR_CUDA (-2)        /* CUDA runtime error, see orcai_last_error */
+#define ORCAI_ERR_STATE (-3)       /* call order (no recording loaded, no weights, ...) */
+#define ORCAI_ERR_CAPACITY (-4)    /* caller buffer too small; required size reported */
+#define ORCAI_ERR_TOO_SHORT (-5)   /* recording shorter than one snippet (reference: Keras raises on empty batch) */
+
+#define ORCAI_PCM_I16 0            /* raw PCM16; the kernel applies x/32768 (libsndfile/librosa.load semantics) */
+#define ORCAI_PCM_F32 1            /* float32 in [-1,1], what librosa.load hands to stft (spectrogram.py:23-35) */
+
+typedef struct orcai_ctx orcai_ctx;
+
+/* Parameter block = the fields of orcai_parameter.json / model_shape.json the path consumes
+ * (reference: models/orcai-V1/orcai_parameter.json, model_shape.json). */
+typedef struct {
+  int32_t sampling_rate;  /* 48000 */
+  int32_t n_fft;          /* 512  (kernel K1 is specialised to 512) */
+  int32_t hop;            /* 256  ("n_overlap" in the JSON, used as hop length: spectrogram.py:37) */
+  int32_t band_lo;        /* first kept rFFT bin  (0)   spectrogram.py:62-68 */
+  int32_t band_hi;        /* one past last kept   (171) */
+  double q_lo;            /* quantiles as np.percentile sees them: true_divide(100*q, 100) */
+  double q_hi;
+  int32_t snippet_len;    /* 736  model_shape.json input_shape[0] */
+  int32_t n_freq;         /* 171  model_shape.json input_shape[1] == band_hi - band_lo */
+  int32_t n_labels;       /* 7 */
+  int32_t n_blocks;       /* len(filters) = 4 */
+  int32_t filters[8];     /* 30,40,50,60 */
+  int32_t kernel_size;    /* 3 */
+  int32_t lstm_units;     /* 128 */
+  int32_t reserved[8];
+} orcai_params;
+
+typedef struct {
+  int64_t n_frames;       /* T = 1 + n_samples / hop */
+  float ref_power;        /* max |S|^2 over all 257 bins and all frames (amplitude_to_db ref=np.max, squared) */
+  float db_ref;           /* 10*log10(max(1e-10, ref_power)) */
+  float lo;               /* nearest-rank q_lo percentile of the cropped, shifted, floored dB array */
+  float hi;               /* nearest-rank q_hi percentile */
+  int64_t rank_lo;        /* the two ranks (indices into the sorted flattened array) */
+  int64_t rank_hi;
+} orcai_spec_stats;
+
+/* Device times (CUDA events on the context's stream) of the stages of the last call, in ms,
+ * and the number of kernels this library launched since the context was created. */
+typedef struct {
+  float h2d_ms;
+  float stft_ms;
+  float select_ms;
+  float normalise_ms;
+  float network_ms;
+  float post_ms;
+  float d2h_ms;
+  float total_ms;
+  uint64_t kernel_launches;
+  float net_stage_ms[16]; /* per network stage of the last forward chunk sequence */
+} orcai_timings;
+
+/* ---- context ------------------------------------------------------------------------------ */
+int orcai_create(int device, const orcai_params* params, orcai_ctx** out);
+void orcai_destroy(orcai_ctx* ctx);
+const char* orcai_last_error(const orcai_ctx* ctx);   /* ctx may be NULL: error of the last failed orcai_create */
+int orcai_get_timings(const orcai_ctx* ctx, orcai_timings* out);
+int orcai_version(void);
+
+/* ---- weights: replaces keras.saving.load_model inside load_orcai_model (io.py:386-392) ----- */
+/* n named float32 tensors in Keras variable layouts (names: orcai_b200/weights.py). BatchNorm
+ * folding and the device layouts are produced inside. */
+int orcai_load_weights(orcai_ctx* ctx, const char* const* names, const float* const* data,
+                       const int64_t* sizes, int32_t n);
+
+/* ---- spectrogram stage: replaces calculate_spectrogram + preprocess_spectrogram
+ *      (spectrogram.py:15-87; librosa.stft / amplitude_to_db / np.percentile call sites) ------ */
+int64_t orcai_num_frames(int64_t n_samples, int32_t hop);
+/* Upload mono PCM (host memory) and keep it resident as the context's current recording. */
+int orcai_upload_pcm(orcai_ctx* ctx, const void* pcm_host, int32_t dtype, int64_t n_samples);
+/* STFT -> dB -> crop -> global max -> exact percentiles on the resident recording.  With
+ * `normalise` != 0 also materialises the normalised (T, n_freq) float32 spectrogram on the device. */
+int orcai_spectrogram_resident(orcai_ctx* ctx, int32_t normalise, orcai_spec_stats* stats);
+/* One call = upload + orcai_spectrogram_resident(normalise=1) + copy-out of the (T, n_freq) result. */
+int orcai_spectrogram(orcai_ctx* ctx, const void* pcm_host, int32_t dtype, int64_t n_samples,
+                      float* spec_out_host, orcai_spec_stats* stats);
+/* Copy rows [row0, row0+nrows) of the normalised spectrogram / of the cropped dB array to host. */
+int orcai_read_spectrogram(orcai_ctx* ctx, int64_t row0, int64_t nrows, float* out_host);
+int orcai_read_db(orcai_ctx* ctx, int64_t row0, int64_t nrows, float* out_host);
+
+/* ---- snippet batcher + orcai-V1 forward: replaces the snippet copy and model.predict
+ *      (predict.py:252-268; architectures.py:120-241) ----------------------------------------- */
+int64_t orcai_num_snippets(int64_t n_frames, int32_t snippet_len);
+/* model.predict boundary: x (n, snippet_len, n_freq) float32 host -> (n, snippet_len/2^n_blocks, n_labels). */
+int orcai_forward_host(orcai_ctx* ctx, const float* snippets_host, int64_t n, float* preds_out_host);
+/* Snippets [first, first+n) cut as strided windows from the resident recording (no copy). */
+int orcai_forward_resident(orcai_ctx* ctx, int64_t first, int64_t n, float* preds_out_host);
+
+/* ---- post-processing: replaces predict.py:276-340 and auxiliary.py:420-440 ----------------- */
+/* preds (n_snippets, P, L) float32 host -> overlap-averaged float64 (T/2^n_blocks, L) + counts,
+ * thresholded at threshold/max(count) (strict >), run-length segments in label-major order
+ * (label index, first step, inclusive last step).  agg_out / cnt_out may be NULL. */
+int orcai_postprocess(orcai_ctx* ctx, const float* preds_host, int64_t n_snippets, int64_t n_frames,
+                      double threshold, double* agg_out, double* cnt_out, int32_t* seg_label,
+                      int64_t* seg_start, int64_t* seg_stop, int64_t seg_capacity, int64_t* n_segments);
+/* compute_binary_predictions boundary (predict.py:298-317) on caller-supplied aggregates. */
+int orcai_threshold_segments(orcai_ctx* ctx, const double* agg_host, const double* cnt_host,
+                             int64_t n_steps, int32_t n_labels, double threshold, int32_t* seg_label,
+                             int64_t* seg_start, int64_t* seg_stop, int64_t seg_capacity,
+                             int64_t* n_segments);
+
+/* ---- fused, device-resident predict_wav core (predict.py:426-451) --------------------------- */
+/* Runs spectrogram -> snippets -> forward -> overlap-average -> threshold -> segments on the
+ * resident recording without leaving the device; only segments (and optionally the aggregates)
+ * are copied back. */
+int orcai_predict_resident(orcai_ctx* ctx, double threshold, orcai_spec_stats* stats,
+                           double* agg_out, double* cnt_out, int32_t* seg_label, int64_t* seg_start,
+                           int64_t* seg_stop, int64_t seg_capacity, int64_t* n_segments);
+/* upload + orcai_predict_resident. */
+int orcai_predict_pcm(orcai_ctx* ctx, const void* pcm_host, int32_t dtype, int64_t n_samples,
+                      double threshold, orcai_spec_stats* stats, double* agg_out, double* cnt_out,
+                      int32_t* seg_label, int64_t* seg_start, int64_t* seg_stop,
+                      int64_t seg_capacity, int64_t* n_segments);
+
+/* ---- knobs ---------------------------------------------------------------------------------- */
+/* Network path: 0 = fp32 CUDA-core reference path, 1 = bf16 tensor-core path (when built). */
+int orcai_set_option(orcai_ctx* ctx, const char* key, int64_t value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ORCAI_B200_H */

@@ -1,0 +1,348 @@
+"""ctypes binding of liborcai_b200.so (C ABI declared in include/orcai_b200.h).
+
+There is no CPU fallback: if the shared library is missing, or no sm_100 device is
+present, every compute entry point raises.  ``load_library()`` alone needs no GPU
+(it only dlopens and resolves symbols), which is what the CPU test-suite checks.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+PKG = Path(__file__).resolve().parent
+LIB_PATH = PKG / "liborcai_b200.so"
+
+ORCAI_OK = 0
+ORCAI_ERR_ARG = -1
+ORCAI_ERR_CUDA = -2
+ORCAI_ERR_STATE = -3
+ORCAI_ERR_CAPACITY = -4
+ORCAI_ERR_TOO_SHORT = -5
+PCM_I16 = 0
+PCM_F32 = 1
+
+
+class OrcaiError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"liborcai_b200 error {code}: {message}")
+        self.code = code
+        self.message = message
+
+
+class Params(C.Structure):
+    _fields_ = [
+        ("sampling_rate", C.c_int32),
+        ("n_fft", C.c_int32),
+        ("hop", C.c_int32),
+        ("band_lo", C.c_int32),
+        ("band_hi", C.c_int32),
+        ("q_lo", C.c_double),
+        ("q_hi", C.c_double),
+        ("snippet_len", C.c_int32),
+        ("n_freq", C.c_int32),
+        ("n_labels", C.c_int32),
+        ("n_blocks", C.c_int32),
+        ("filters", C.c_int32 * 8),
+        ("kernel_size", C.c_int32),
+        ("lstm_units", C.c_int32),
+        ("reserved", C.c_int32 * 8),
+    ]
+
+
+class SpecStats(C.Structure):
+    _fields_ = [
+        ("n_frames", C.c_int64),
+        ("ref_power", C.c_float),
+        ("db_ref", C.c_float),
+        ("lo", C.c_float),
+        ("hi", C.c_float),
+        ("rank_lo", C.c_int64),
+        ("rank_hi", C.c_int64),
+    ]
+
+
+class Timings(C.Structure):
+    _fields_ = [
+        ("h2d_ms", C.c_float),
+        ("stft_ms", C.c_float),
+        ("select_ms", C.c_float),
+        ("normalise_ms", C.c_float),
+        ("network_ms", C.c_float),
+        ("post_ms", C.c_float),
+        ("d2h_ms", C.c_float),
+        ("total_ms", C.c_float),
+        ("kernel_launches", C.c_uint64),
+        ("net_stage_ms", C.c_float * 16),
+    ]
+
+    def as_dict(self) -> dict:
+        d = {k: getattr(self, k) for k, _ in self._fields_ if k != "net_stage_ms"}
+        d["net_stage_ms"] = list(self.net_stage_ms)
+        return d
+
+
+_P = C.c_void_p
+_SIGNATURES = {
+    # name: (restype, argtypes)  -- must list every symbol declared in include/orcai_b200.h
+    "orcai_create": (C.c_int, [C.c_int, C.POINTER(Params), C.POINTER(_P)]),
+    "orcai_destroy": (None, [_P]),
+    "orcai_last_error": (C.c_char_p, [_P]),
+    "orcai_get_timings": (C.c_int, [_P, C.POINTER(Timings)]),
+    "orcai_version": (C.c_int, []),
+    "orcai_load_weights": (C.c_int, [_P, C.POINTER(C.c_char_p), C.POINTER(_P), C.POINTER(C.c_int64), C.c_int32]),
+    "orcai_num_frames": (C.c_int64, [C.c_int64, C.c_int32]),
+    "orcai_upload_pcm": (C.c_int, [_P, _P, C.c_int32, C.c_int64]),
+    "orcai_spectrogram_resident": (C.c_int, [_P, C.c_int32, C.POINTER(SpecStats)]),
+    "orcai_spectrogram": (C.c_int, [_P, _P, C.c_int32, C.c_int64, _P, C.POINTER(SpecStats)]),
+    "orcai_read_spectrogram": (C.c_int, [_P, C.c_int64, C.c_int64, _P]),
+    "orcai_read_db": (C.c_int, [_P, C.c_int64, C.c_int64, _P]),
+    "orcai_num_snippets": (C.c_int64, [C.c_int64, C.c_int32]),
+    "orcai_forward_host": (C.c_int, [_P, _P, C.c_int64, _P]),
+    "orcai_forward_resident": (C.c_int, [_P, C.c_int64, C.c_int64, _P]),
+    "orcai_postprocess": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_double, _P, _P, _P, _P, _P, C.c_int64, C.POINTER(C.c_int64)]),
+    "orcai_threshold_segments": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_double, _P, _P, _P, C.c_int64, C.POINTER(C.c_int64)]),
+    "orcai_predict_resident": (C.c_int, [_P, C.c_double, C.POINTER(SpecStats), _P, _P, _P, _P, _P, C.c_int64, C.POINTER(C.c_int64)]),
+    "orcai_predict_pcm": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_double, C.POINTER(SpecStats), _P, _P, _P, _P, _P, C.c_int64, C.POINTER(C.c_int64)]),
+    "orcai_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),
+}
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """dlopen liborcai_b200.so and bind every exported entry point (no GPU needed)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise OrcaiError(
+            ORCAI_ERR_STATE,
+            f"{LIB_PATH} is missing - build it with `python -m orcai_b200.build` (sm_100a, nvcc). "
+            "orcai_b200 has no CPU fallback.",
+        )
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def exported_symbols() -> list[str]:
+    return list(_SIGNATURES)
+
+
+def _ptr(a: np.ndarray | None):
+    return None if a is None else a.ctypes.data_as(_P)
+
+
+def params_from_dicts(orcai_parameter: dict, shape: dict) -> Params:
+    """Fill the C parameter block from orcai_parameter.json / model_shape.json contents."""
+    sp = orcai_parameter["spectrogram"]
+    sr, n_fft = int(sp["sampling_rate"]), int(sp["nfft"])
+    freqs = np.fft.rfftfreq(n=n_fft, d=1.0 / sr)
+    # band selection rule of preprocess_spectrogram (reference spectrogram.py:62-68)
+    band_lo = int(np.argwhere(freqs <= sp["freq_range"][0])[0][0])
+    band_hi = int(np.argwhere(freqs >= sp["freq_range"][1])[0][0])
+    p = Params()
+    p.sampling_rate = sr
+    p.n_fft = n_fft
+    p.hop = int(sp["n_overlap"])
+    p.band_lo, p.band_hi = band_lo, band_hi
+    # np.percentile(x, 100*q) divides by 100 again before computing the nearest rank
+    p.q_lo = float(np.true_divide(100 * sp["quantiles"][0], 100))
+    p.q_hi = float(np.true_divide(100 * sp["quantiles"][1], 100))
+    p.snippet_len = int(shape["input_shape"][0])
+    p.n_freq = int(shape["input_shape"][1])
+    p.n_labels = int(shape["num_labels"])
+    filters = list(orcai_parameter["model"]["filters"])
+    p.n_blocks = len(filters)
+    for i, f in enumerate(filters[:8]):
+        p.filters[i] = int(f)
+    p.kernel_size = int(orcai_parameter["model"]["kernel_size"])
+    p.lstm_units = int(orcai_parameter["model"]["lstm_units"])
+    return p
+
+
+class Context:
+    """One liborcai_b200 context = one device, one stream, one resident recording."""
+
+    def __init__(self, orcai_parameter: dict, shape: dict, device: int = 0):
+        self.lib = load_library()
+        self.params = params_from_dicts(orcai_parameter, shape)
+        self.orcai_parameter = orcai_parameter
+        self.shape = shape
+        h = _P()
+        rc = self.lib.orcai_create(int(device), C.byref(self.params), C.byref(h))
+        if rc != ORCAI_OK:
+            raise OrcaiError(rc, (self.lib.orcai_last_error(None) or b"").decode())
+        self._h = h
+        self.device = device
+        self.pred_len = self.params.snippet_len >> self.params.n_blocks
+        self.weights_loaded = False
+
+    # -- plumbing ------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.orcai_destroy(self._h)
+            self._h = None
+
+    def __del__(self):  # pragma: no cover
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int):
+        if rc != ORCAI_OK:
+            raise OrcaiError(rc, (self.lib.orcai_last_error(self._h) or b"").decode())
+
+    def timings(self) -> dict:
+        t = Timings()
+        self._check(self.lib.orcai_get_timings(self._h, C.byref(t)))
+        return t.as_dict()
+
+    def set_option(self, key: str, value: int):
+        self._check(self.lib.orcai_set_option(self._h, key.encode(), int(value)))
+
+    # -- weights -------------------------------------------------------------------------------
+    def load_weights(self, W: dict):
+        names = list(W)
+        arrs = [np.ascontiguousarray(W[k], dtype=np.float32) for k in names]
+        n = len(names)
+        c_names = (C.c_char_p * n)(*[k.encode() for k in names])
+        c_data = (_P * n)(*[a.ctypes.data for a in arrs])
+        c_sizes = (C.c_int64 * n)(*[a.size for a in arrs])
+        self._check(self.lib.orcai_load_weights(self._h, c_names, c_data, c_sizes, n))
+        self.weights_loaded = True
+
+    # -- spectrogram ---------------------------------------------------------------------------
+    @staticmethod
+    def _pcm(pcm: np.ndarray):
+        pcm = np.ascontiguousarray(pcm)
+        if pcm.ndim != 1:
+            raise ValueError("pcm must be mono (1-D)")
+        if pcm.dtype == np.int16:
+            return pcm, PCM_I16
+        if pcm.dtype == np.float32:
+            return pcm, PCM_F32
+        raise ValueError(f"pcm dtype {pcm.dtype} not supported (int16 or float32)")
+
+    def upload_pcm(self, pcm: np.ndarray):
+        pcm, dt = self._pcm(pcm)
+        self._check(self.lib.orcai_upload_pcm(self._h, _ptr(pcm), dt, pcm.size))
+
+    def spectrogram_resident(self, normalise: bool = True) -> SpecStats:
+        st = SpecStats()
+        self._check(self.lib.orcai_spectrogram_resident(self._h, int(normalise), C.byref(st)))
+        return st
+
+    def spectrogram(self, pcm: np.ndarray):
+        """(normalised (T, n_freq) float32, stats) through the one-call entry point."""
+        pcm, dt = self._pcm(pcm)
+        T = self.lib.orcai_num_frames(pcm.size, self.params.hop)
+        out = np.empty((T, self.params.n_freq), dtype=np.float32)
+        st = SpecStats()
+        self._check(self.lib.orcai_spectrogram(self._h, _ptr(pcm), dt, pcm.size, _ptr(out), C.byref(st)))
+        return out, st
+
+    def read_spectrogram(self, row0: int, nrows: int) -> np.ndarray:
+        out = np.empty((nrows, self.params.n_freq), dtype=np.float32)
+        self._check(self.lib.orcai_read_spectrogram(self._h, row0, nrows, _ptr(out)))
+        return out
+
+    def read_db(self, row0: int, nrows: int) -> np.ndarray:
+        out = np.empty((nrows, self.params.n_freq), dtype=np.float32)
+        self._check(self.lib.orcai_read_db(self._h, row0, nrows, _ptr(out)))
+        return out
+
+    # -- network -------------------------------------------------------------------------------
+    def forward_host(self, snippets: np.ndarray) -> np.ndarray:
+        x = np.ascontiguousarray(snippets, dtype=np.float32)
+        if x.ndim == 4 and x.shape[-1] == 1:
+            x = x[..., 0]
+        if x.ndim != 3 or x.shape[1] != self.params.snippet_len or x.shape[2] != self.params.n_freq:
+            raise ValueError(
+                f"expected snippets of shape (N, {self.params.snippet_len}, {self.params.n_freq}[, 1]), got {snippets.shape}"
+            )
+        x = np.ascontiguousarray(x)
+        out = np.empty((x.shape[0], self.pred_len, self.params.n_labels), dtype=np.float32)
+        self._check(self.lib.orcai_forward_host(self._h, _ptr(x), x.shape[0], _ptr(out)))
+        return out
+
+    def forward_resident(self, first: int, n: int) -> np.ndarray:
+        out = np.empty((n, self.pred_len, self.params.n_labels), dtype=np.float32)
+        self._check(self.lib.orcai_forward_resident(self._h, first, n, _ptr(out)))
+        return out
+
+    # -- post-processing -----------------------------------------------------------------------
+    def _segments_call(self, fn, S: int, L: int):
+        cap = max(1024, min(L * ((S + 1) // 2), 1 << 18))
+        while True:
+            lab = np.empty(cap, np.int32)
+            sta = np.empty(cap, np.int64)
+            sto = np.empty(cap, np.int64)
+            n = C.c_int64(0)
+            rc = fn(_ptr(lab), _ptr(sta), _ptr(sto), cap, C.byref(n))
+            if rc == ORCAI_ERR_CAPACITY and n.value > cap:
+                cap = int(n.value)
+                continue
+            self._check(rc)
+            k = int(n.value)
+            return lab[:k], sta[:k], sto[:k]
+
+    def postprocess(self, preds: np.ndarray, n_frames: int, threshold: float = 0.5, want_agg: bool = True):
+        p = np.ascontiguousarray(preds, dtype=np.float32)
+        N = p.shape[0]
+        ds = 1 << self.params.n_blocks
+        S, L = n_frames // ds, self.params.n_labels
+        agg = np.zeros((S, L), np.float64) if want_agg else None
+        cnt = np.zeros(S, np.float64) if want_agg else None
+        lab, sta, sto = self._segments_call(
+            lambda a, b, c, cap, n: self.lib.orcai_postprocess(
+                self._h, _ptr(p), N, n_frames, float(threshold), _ptr(agg), _ptr(cnt), a, b, c, cap, n
+            ),
+            S,
+            L,
+        )
+        return agg, cnt, lab, sta, sto
+
+    def threshold_segments(self, agg: np.ndarray, cnt: np.ndarray, threshold: float = 0.5):
+        a = np.ascontiguousarray(agg, dtype=np.float64)
+        k = np.ascontiguousarray(cnt, dtype=np.float64)
+        S, L = a.shape
+        return self._segments_call(
+            lambda x, y, z, cap, n: self.lib.orcai_threshold_segments(
+                self._h, _ptr(a), _ptr(k), S, L, float(threshold), x, y, z, cap, n
+            ),
+            S,
+            L,
+        )
+
+    # -- fused ---------------------------------------------------------------------------------
+    def predict_pcm(self, pcm: np.ndarray, threshold: float = 0.5, want_agg: bool = True, resident: bool = False):
+        """WAV samples -> (stats, agg, cnt, label_idx, start_step, stop_step) without leaving the device.
+
+        resident=True reuses the recording already uploaded with upload_pcm (pcm is only used for its length).
+        """
+        pcm, dt = self._pcm(pcm)
+        T = self.lib.orcai_num_frames(pcm.size, self.params.hop)
+        ds = 1 << self.params.n_blocks
+        S, L = T // ds, self.params.n_labels
+        agg = np.zeros((S, L), np.float64) if want_agg else None
+        cnt = np.zeros(S, np.float64) if want_agg else None
+        st = SpecStats()
+        if resident:
+            call = lambda a, b, c, cap, n: self.lib.orcai_predict_resident(  # noqa: E731
+                self._h, float(threshold), C.byref(st), _ptr(agg), _ptr(cnt), a, b, c, cap, n
+            )
+        else:
+            call = lambda a, b, c, cap, n: self.lib.orcai_predict_pcm(  # noqa: E731
+                self._h, _ptr(pcm), dt, pcm.size, float(threshold), C.byref(st), _ptr(agg), _ptr(cnt), a, b, c, cap, n
+            )
+        lab, sta, sto = self._segments_call(call, S, L)
+        return st, agg, cnt, lab, sta, sto

@@ -1,0 +1,105 @@
+// Shared declarations of liborcai_b200: context, error handling, stage launchers.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/orcai_b200.h"
+
+namespace orcai {
+
+constexpr int kRawLd = 176;          // row pitch (floats) of the raw dB buffer: 704 B rows, 32 B-sector aligned
+constexpr int kMaxBlocks = 8;
+
+struct SelectState {                 // device-resident scratch of the exact two-rank radix select
+  unsigned long long hist[2][2048];  // per-rank digit histograms of the current pass
+  unsigned long long rank[2];        // rank still to be located inside the current prefix
+  unsigned int prefix[2];            // key bits decided so far (high bits)
+  unsigned int pmax_bits;            // max |S|^2 over all bins and frames (float bits, non-negative)
+  float db_ref;                      // 10*log10(max(1e-10, pmax))
+  float lo, hi;                      // selected percentiles (shifted + floored dB)
+  unsigned int tile_counter;         // scan kernel dynamic tile id
+  unsigned int pad;
+};
+
+struct NetWeights;                   // net.cu
+
+struct Ctx {
+  int device = 0;
+  orcai_params p{};
+  cudaStream_t stream = nullptr;
+  std::string err;
+  // STFT tables on device: [0]=float input scale, [1]=int16 input scale ; each 768 float2
+  float* d_tables[2] = {nullptr, nullptr};
+  SelectState* d_sel = nullptr;
+  // current recording
+  void* d_pcm = nullptr;  size_t pcm_cap = 0;  int pcm_dtype = 0;  int64_t n_samples = 0;
+  float* d_raw = nullptr; size_t raw_cap = 0;  int64_t T = 0;      // raw dB (T, kRawLd)
+  float* d_spec = nullptr; size_t spec_cap = 0;                    // normalised (T, n_freq) compact
+  bool have_stats = false;
+  // network
+  NetWeights* net = nullptr;
+  float* d_preds = nullptr; size_t preds_cap = 0;                  // (N, pred_len, n_labels)
+  // post-processing scratch
+  void* d_post = nullptr; size_t post_cap = 0;
+  // pinned staging
+  void* h_pin = nullptr; size_t pin_cap = 0;
+  // timing / accounting of the last call
+  orcai_timings tm{};
+  cudaEvent_t ev[16] = {};
+  uint64_t launches = 0;
+  int sm_count = 148;
+};
+
+#define ORCAI_CUDA(ctx, call)                                                            \
+  do {                                                                                   \
+    cudaError_t e__ = (call);                                                            \
+    if (e__ != cudaSuccess) {                                                            \
+      char b__[512];                                                                     \
+      snprintf(b__, sizeof b__, "%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+      (ctx)->err = b__;                                                                  \
+      return ORCAI_ERR_CUDA;                                                             \
+    }                                                                                    \
+  } while (0)
+
+#define ORCAI_FAIL(ctx, code, ...)                       \
+  do {                                                   \
+    char b__[512];                                       \
+    snprintf(b__, sizeof b__, __VA_ARGS__);              \
+    (ctx)->err = b__;                                    \
+    return (code);                                       \
+  } while (0)
+
+#define ORCAI_CHECK(expr)                                \
+  do {                                                   \
+    int rc__ = (expr);                                   \
+    if (rc__ != ORCAI_OK) return rc__;                   \
+  } while (0)
+
+int ensure_device_buffer(Ctx* c, void** p, size_t* cap, size_t bytes);
+
+// ---- stage launchers (all asynchronous on c->stream) -------------------------------------------
+// K1: fused window + rFFT512 + |.|^2 + 10log10 + crop ; also the global power max.   (stft.cu)
+int launch_stft(Ctx* c, const void* d_pcm, int dtype, int64_t n_samples, int64_t T, float* d_raw);
+// exact percentiles (radix select on shifted/floored dB) and K2 normalise.          (select.cu)
+int launch_select(Ctx* c, const float* d_raw, int64_t T);
+int launch_normalise(Ctx* c, const float* d_raw, int64_t T, float* d_spec);
+int launch_read_db(Ctx* c, const float* d_raw, int64_t T, float* d_out);             // shifted + floored dB, compact
+// network forward                                                                    (net.cu)
+int net_create(Ctx* c);
+void net_destroy(Ctx* c);
+int net_set_chunk(Ctx* c, int chunk);
+int net_load_weights(Ctx* c, const char* const* names, const float* const* data, const int64_t* sizes, int n);
+// input_mode 0: raw dB buffer (pitch kRawLd, normalise on load with c->d_sel stats), snippet i starts at row
+//               (first + i) * shift ; input_mode 1: normalised compact snippets (pitch n_freq), snippet stride = snippet_len rows
+int net_forward(Ctx* c, const float* d_in, int input_mode, int64_t first, int64_t n, float* d_preds);
+// post-processing: overlap-average + threshold + run-length segments                 (post.cu)
+int launch_postprocess(Ctx* c, const float* d_preds, int64_t n_snippets, int64_t T, double threshold,
+                       double* h_agg, double* h_cnt, int32_t* h_label, int64_t* h_start, int64_t* h_stop,
+                       int64_t cap, int64_t* n_seg);
+int launch_threshold_segments(Ctx* c, const double* h_agg, const double* h_cnt, int64_t S, int L, double threshold,
+                              int32_t* h_label, int64_t* h_start, int64_t* h_stop, int64_t cap, int64_t* n_seg);
+
+}  // namespace orcai

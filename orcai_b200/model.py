@@ -1,0 +1,40 @@
+"""The model object boundary: ``model.predict(x (N,736,171,1) f32) -> (N,46,7) f32``.
+
+Stands in for the ``keras.Model`` that the reference's ``load_orcai_model`` returns
+(``src/orcAI/io.py:357-410``) and that ``compute_aggregated_predictions`` calls
+(``src/orcAI/predict.py:266-268``).  The forward pass runs in liborcai_b200.
+"""
+
+from __future__ import annotations
+
+import numpy as np
+
+from orcai_b200.runtime import get_context
+from orcai_b200.weights import check_weights
+
+
+class OrcaiModel:
+    def __init__(self, orcai_parameter: dict, shape: dict, weights: dict, device: int | None = None):
+        if orcai_parameter.get("architecture", "ResNetLSTM") != "ResNetLSTM":
+            raise ValueError(f"Unknown model architecture: {orcai_parameter.get('architecture')}")
+        check_weights(weights, orcai_parameter, shape)
+        self.orcai_parameter = orcai_parameter
+        self.shape = shape
+        self.weights = weights
+        self.ctx = get_context(orcai_parameter, shape, device)
+        self.ctx.load_weights(weights)
+        n_blocks = len(orcai_parameter["model"]["filters"])
+        self.input_shape = (None, *shape["input_shape"])
+        self.output_shape = (None, shape["input_shape"][0] // 2**n_blocks, shape["num_labels"])
+
+    def predict(self, x, batch_size: int | None = None, verbose: int = 0, **_unused) -> np.ndarray:
+        """Keras-style predict; ``batch_size`` bounds the snippets staged on the device per call."""
+        x = np.asarray(x, dtype=np.float32)
+        if x.shape[0] == 0:
+            raise ValueError("Expected input data to be non-empty.")
+        step = int(batch_size) if batch_size else 1024
+        step = max(step, 256)
+        outs = [self.ctx.forward_host(x[i : i + step]) for i in range(0, x.shape[0], step)]
+        return outs[0] if len(outs) == 1 else np.concatenate(outs, axis=0)
+
+    __call__ = predict

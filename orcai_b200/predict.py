@@ -1,0 +1,454 @@
+"""Prediction workflow with the reference's function surface (``src/orcAI/predict.py``).
+
+Signatures, output naming, error behaviour and file contents follow predict.py:235-757 of the
+reference; the arithmetic runs in liborcai_b200:
+
+* ``predict_wav`` uses the fused device-resident path (spectrogram -> strided snippets -> forward ->
+  overlap-average -> threshold -> run lengths); only segments and aggregates come back.
+* ``compute_aggregated_predictions`` / ``compute_binary_predictions`` keep the reference's staged
+  interfaces (host spectrogram in, numpy out) on top of the same kernels.
+* The label file is written without pandas' ``.loc`` float-into-int assignment, which raises on
+  pandas >= 3 (predict.py:362-363); the bytes are what pandas 2.2.3 produced.
+"""
+
+from __future__ import annotations
+
+import gzip
+import os
+import queue
+import threading
+from importlib.resources import files
+from pathlib import Path
+
+import numpy as np
+import pandas as pd
+from tqdm import tqdm
+
+from orcai_b200._lib import ORCAI_ERR_TOO_SHORT, OrcaiError
+from orcai_b200.auxiliary import Messenger
+from orcai_b200.io import load_orcai_model, read_json
+from orcai_b200.runtime import get_context
+from orcai_b200.spectrogram import frames_to_time, load_recording, make_spectrogram
+
+
+# ---------------------------------------------------------------------------------------------
+# duration filter (predict.py:14-159)
+# ---------------------------------------------------------------------------------------------
+def _check_duration(calls, call_duration_limits: dict, delta_t: float, label_suffix: str = "*") -> str:
+    label = calls["label"].replace(f"{label_suffix}", "")
+    if label in call_duration_limits:
+        mn, mx = call_duration_limits[label]
+    elif "default" in call_duration_limits:
+        mn, mx = call_duration_limits["default"]
+    else:
+        mn, mx = 0, np.inf
+    mn = 0 if mn is None else mn
+    mx = np.inf if mx is None else mx
+    if calls["duration"] * delta_t < mn:
+        return "too short"
+    if calls["duration"] * delta_t > mx:
+        return "too long"
+    return "keep"
+
+
+def filter_predictions(
+    predicted_labels: pd.DataFrame,
+    delta_t: float,
+    call_duration_limits: (Path | str) | dict = files("orcai_b200.defaults").joinpath("default_call_duration_limits.json"),
+    label_suffix: str = "*",
+    verbosity: int = 2,
+    msgr: Messenger | None = None,
+) -> pd.DataFrame:
+    """Drop predicted calls whose duration is outside the per-label limits."""
+    if msgr is None:
+        msgr = Messenger(verbosity=verbosity, title="Filtering predictions")
+    msgr.part("Filtering predictions")
+    predicted_labels = predicted_labels.copy()
+    predicted_labels["duration"] = predicted_labels["stop"] - predicted_labels["start"]
+    if not isinstance(call_duration_limits, dict):
+        call_duration_limits = read_json(call_duration_limits)
+    msgr.debug("Call duration limits:")
+    msgr.debug(call_duration_limits)
+    msgr.part("Filtering calls based on duration")
+    if len(predicted_labels):
+        verdict = predicted_labels.apply(lambda x: _check_duration(x, call_duration_limits, delta_t, label_suffix), axis=1)
+    else:
+        verdict = pd.Series([], dtype=object)
+    predicted_labels["duration_ok"] = verdict
+    n_long = int((verdict == "too long").sum())
+    n_short = int((verdict == "too short").sum())
+    msgr.info(f"Discarding {n_long + n_short} calls based on duration (too short: {n_short}, too long: {n_long})")
+    out = predicted_labels[predicted_labels["duration_ok"] == "keep"]
+    msgr.success("Filtering predictions finished.")
+    return out
+
+
+def filter_predictions_file(
+    predicted_labels: Path | str,
+    output_file: Path | str = "default",
+    overwrite: bool = False,
+    call_duration_limits: (Path | str) | dict = files("orcai_b200.defaults").joinpath("default_call_duration_limits.json"),
+    label_suffix: str = "*",
+    verbosity: int = 2,
+    msgr: Messenger | None = None,
+):
+    """Filter a saved label file by duration -> ``<stem>_filtered.txt`` (predict.py:162-232)."""
+    if msgr is None:
+        msgr = Messenger(verbosity=verbosity, title="Filtering predictions")
+    if output_file == "default":
+        output_file = Path(predicted_labels).with_name(Path(predicted_labels).stem + "_filtered.txt")
+    else:
+        output_file = Path(output_file)
+    msgr.info(f"Output file: {output_file}")
+    if output_file.exists() and not overwrite:
+        raise FileExistsError(f"Annotation file already exists: {output_file}")
+    table = pd.read_csv(predicted_labels, sep="\t", encoding="utf-8")
+    kept = filter_predictions(table, delta_t=1, call_duration_limits=call_duration_limits, label_suffix=label_suffix, verbosity=verbosity, msgr=msgr)
+    save_predictions(kept, output_file, delta_t=1, msgr=msgr)
+
+
+# ---------------------------------------------------------------------------------------------
+# staged interfaces (predict.py:235-340)
+# ---------------------------------------------------------------------------------------------
+def _context_of(model, orcai_parameter: dict, shape: dict):
+    return getattr(model, "ctx", None) or get_context(orcai_parameter, shape)
+
+
+def compute_aggregated_predictions(
+    recording_path: Path,
+    spectrogram: np.ndarray,
+    model,
+    orcai_parameter: dict,
+    shape: dict,
+    msgr: Messenger = Messenger(verbosity=0),
+    progressbar: tqdm = None,
+) -> tuple[np.ndarray, np.ndarray]:
+    """Snippets -> model.predict -> float64 overlap-average; returns (aggregated (T//16, L), overlap_count)."""
+    snippet_length = shape["input_shape"][0]
+    shift = snippet_length // 2
+    num_snippets = (spectrogram.shape[0] - snippet_length) // shift + 1
+    msgr.info(f"slicing into {num_snippets} snippets for prediction")
+    if num_snippets <= 0:
+        raise ValueError(
+            f"Spectrogram of {Path(recording_path).stem} has {spectrogram.shape[0]} frames, shorter than one snippet ({snippet_length})"
+        )
+    spec = np.ascontiguousarray(spectrogram, dtype=np.float32)
+    # strided window view; model.predict stages it in bounded batches, nothing is materialised on the host
+    windows = np.lib.stride_tricks.sliding_window_view(spec, (snippet_length, spec.shape[1]))[::shift, 0][:num_snippets]
+    msgr.info("Prediction of snippets")
+    predictions = model.predict(windows[..., np.newaxis], verbose=0 if msgr.verbosity < 2 else 1)
+    msgr.info("Aggregating predictions")
+    if progressbar:
+        progressbar.set_description(f"{Path(recording_path).stem} - Aggregating predictions")
+        progressbar.refresh()
+    ctx = _context_of(model, orcai_parameter, shape)
+    agg, cnt, _, _, _ = ctx.postprocess(predictions, spectrogram.shape[0], threshold=0.5, want_agg=True)
+    return agg, cnt
+
+
+def compute_binary_predictions(
+    aggregated_predictions: np.ndarray,
+    overlap_count: np.ndarray,
+    calls: list[str],
+    threshold: float = 0.5,
+    ctx=None,
+) -> tuple[list[int], list[int], list[str]]:
+    """Threshold at threshold/max(overlap) (strict >) and extract per-label runs, label-major order."""
+    if ctx is None:
+        from orcai_b200.runtime import default_context
+
+        ctx = default_context()
+    lab, sta, sto = ctx.threshold_segments(aggregated_predictions, overlap_count, threshold)
+    return [int(v) for v in sta], [int(v) for v in sto], [calls[int(i)] for i in lab]
+
+
+def compute_labels(
+    row_starts: list[int],
+    row_stops: list[int],
+    label_names: list[str],
+    time_steps_per_output_step: int,
+    label_suffix: str | None,
+) -> pd.DataFrame:
+    if (label_suffix is not None) & (label_suffix != ""):
+        label_names = [label + label_suffix for label in label_names]
+    return (
+        pd.DataFrame(
+            {
+                "start": np.asarray(row_starts) * time_steps_per_output_step,
+                "stop": np.asarray(row_stops) * time_steps_per_output_step,
+                "label": label_names,
+            }
+        )
+        .sort_values(by=["start", "stop", "label"])
+        .reset_index(drop=True)
+    )
+
+
+# ---------------------------------------------------------------------------------------------
+# predict_wav (predict.py:367-471)
+# ---------------------------------------------------------------------------------------------
+def predict_wav(
+    recording_path: Path | str,
+    channel: int,
+    model,
+    orcai_parameter: dict,
+    shape: dict,
+    label_suffix: str = "*",
+    msgr: Messenger = Messenger(verbosity=0),
+    progressbar: tqdm = None,
+):
+    """Predicts calls in a single wav file -> (predicted_labels DataFrame, aggregated_predictions, delta_t)."""
+    recording_path = Path(recording_path)
+    if progressbar:
+        progressbar.set_description(f"{recording_path.stem}: Generating spectrogram")
+        progressbar.refresh()
+    sp = orcai_parameter["spectrogram"]
+    msgr.part("Calculating power spectrogram by stft")
+    msgr.info(f"Loading & resampling (to {sp['sampling_rate'] / 1000:.2f} kHz) wav file: {recording_path.stem}")
+    samples = load_recording(recording_path, channel, sp, msgr)
+    ctx = _context_of(model, orcai_parameter, shape)
+    if ctx.params.n_freq != shape["input_shape"][1]:
+        raise ValueError(f"Spectrogram shape ({ctx.params.n_freq}) for {recording_path.stem} not equal to input shape ({shape['input_shape'][1]})")
+    times01 = frames_to_time(2, sp)
+    delta_t = times01[1] - times01[0]
+
+    msgr.part(f"Prediction of annotations for wav_file: {recording_path.stem}")
+    if progressbar:
+        progressbar.set_description(f"{recording_path.stem} - Predicting annotations")
+        progressbar.refresh()
+    try:
+        stats, agg, _cnt, lab, sta, sto = ctx.predict_pcm(samples, threshold=0.5, want_agg=True)
+    except OrcaiError as e:
+        if e.code == ORCAI_ERR_TOO_SHORT:
+            raise ValueError(f"{recording_path.stem}: {e.message}") from e
+        raise
+    msgr.info(f"Duration of wav file: {(int(stats.n_frames) - 1) * delta_t:.2f} seconds")
+    msgr.info("converting binary predictions into start and stop frames")
+    calls = orcai_parameter["calls"]
+    predicted_labels = compute_labels(
+        [int(v) for v in sta],
+        [int(v) for v in sto],
+        [calls[int(i)] for i in lab],
+        time_steps_per_output_step=2 ** len(orcai_parameter["model"]["filters"]),
+        label_suffix=label_suffix,
+    )
+    msgr.info(f"found {len(predicted_labels)} acoustic signals")
+    msgr.success("Prediction finished.")
+    return predicted_labels, agg, delta_t
+
+
+# ---------------------------------------------------------------------------------------------
+# writers (predict.py:343-364, 474-531)
+# ---------------------------------------------------------------------------------------------
+def _seconds_column(values, delta_t: float) -> list[str]:
+    """Text of one time column as pandas 2.2.3 wrote it after ``df.loc[:, c] = df.loc[:, c] * delta_t``.
+
+    An int64 column stays int64 when every product is integer-valued (lossless in-place set), otherwise it
+    becomes float64, rounded half-to-even to 4 decimals and printed with the shortest round-trip repr.
+    """
+    v = np.asarray(values)
+    prod = v * np.float64(delta_t)
+    if prod.size and v.dtype.kind in "iu" and np.all(prod == np.trunc(prod)):
+        return [str(int(x)) for x in prod]
+    return [repr(float(x)) for x in np.round(prod.astype(np.float64), 4)]
+
+
+def labels_to_tsv(predicted_labels: pd.DataFrame, delta_t: float) -> str:
+    start = _seconds_column(predicted_labels["start"].to_numpy(), delta_t)
+    stop = _seconds_column(predicted_labels["stop"].to_numpy(), delta_t)
+    lines = ["start\tstop\tlabel"]
+    lines += [f"{a}\t{b}\t{c}" for a, b, c in zip(start, stop, predicted_labels["label"].tolist())]
+    return "\n".join(lines) + "\n"
+
+
+def save_predictions(predicted_labels: pd.DataFrame, output_path: Path | str, delta_t: float, msgr: Messenger = Messenger(verbosity=0)) -> None:
+    """Audacity-compatible label file: header ``start\\tstop\\tlabel``, times in seconds rounded to 4 decimals."""
+    with open(output_path, "w", encoding="utf-8", newline="") as f:
+        f.write(labels_to_tsv(predicted_labels, delta_t))
+    msgr.info(f"Predictions saved to {output_path}")
+
+
+def probabilities_to_csv(aggregated_predictions: np.ndarray, calls: list[str], delta_t: float) -> str:
+    idx = np.float64(delta_t) * np.arange(len(aggregated_predictions))  # frame delta_t, like the reference (quirk)
+    lines = ["time," + ",".join(calls)]
+    for t, row in zip(idx, np.asarray(aggregated_predictions, dtype=np.float64)):
+        lines.append(repr(float(t)) + "," + ",".join(repr(float(v)) for v in row))
+    return "\n".join(lines) + "\n"
+
+
+def save_prediction_probabilities(
+    aggregated_predictions: np.ndarray,
+    orcai_parameter: dict,
+    delta_t: float,
+    output_path: Path | str,
+    msgr: Messenger = Messenger(verbosity=0),
+) -> None:
+    output_path = Path(output_path)
+    predictions_path = output_path.with_name(f"{output_path.stem}_probabilities.csv.gz")
+    with gzip.open(predictions_path, "wt", encoding="utf-8", newline="") as f:
+        f.write(probabilities_to_csv(aggregated_predictions, orcai_parameter["calls"], delta_t))
+    msgr.info(f"Prediction probabilities saved to {predictions_path}")
+
+
+# ---------------------------------------------------------------------------------------------
+# drivers (predict.py:534-757)
+# ---------------------------------------------------------------------------------------------
+def _predict_and_save(
+    recording_path: Path | str,
+    channel: int,
+    model,
+    orcai_parameter: dict,
+    shape: dict,
+    output_path: Path | str = "default",
+    overwrite: bool = False,
+    save_probabilities: bool = False,
+    call_duration_limits: (Path | str) | dict = None,
+    label_suffix: str = "*",
+    msgr: Messenger = Messenger(verbosity=0),
+    progressbar: tqdm = None,
+) -> None:
+    recording_path = Path(recording_path)
+    if output_path is not None:
+        if output_path == "default":
+            output_path = recording_path.with_name(f"{recording_path.stem}_c{channel}_{orcai_parameter['name']}_predicted.txt")
+        else:
+            output_path = Path(output_path)
+        msgr.info(f"Output file: {output_path}")
+        if output_path.exists():
+            if overwrite:
+                msgr.warning(f"Output file {output_path} already exists. Overwriting.")
+            else:
+                raise FileExistsError(f"Annotation file already exists: {output_path}")
+
+    predicted_labels, aggregated_predictions, delta_t = predict_wav(
+        recording_path=recording_path,
+        channel=channel,
+        model=model,
+        orcai_parameter=orcai_parameter,
+        shape=shape,
+        label_suffix=label_suffix,
+        msgr=msgr,
+        progressbar=progressbar,
+    )
+    if call_duration_limits is not None:
+        predicted_labels = filter_predictions(predicted_labels, delta_t=delta_t, call_duration_limits=call_duration_limits, label_suffix=label_suffix, msgr=msgr)
+    save_predictions(predicted_labels=predicted_labels, output_path=output_path, delta_t=delta_t, msgr=msgr)
+    if save_probabilities:
+        save_prediction_probabilities(aggregated_predictions, orcai_parameter, delta_t, output_path, msgr=msgr)
+
+
+def _visible_devices() -> list[int]:
+    """Devices a table run shards over: ORCAI_B200_DEVICES="0,1,.." | "all"; default: the process' one device."""
+    spec = os.environ.get("ORCAI_B200_DEVICES", "").strip()
+    if not spec:
+        return []
+    if spec == "all":
+        import torch
+
+        return list(range(torch.cuda.device_count()))
+    return [int(x) for x in spec.split(",") if x.strip() != ""]
+
+
+def predict(
+    recording_path: str | Path,
+    channel: int = 1,
+    model_dir: str | Path = files("orcai_b200.models").joinpath("orcai-V1"),
+    output_path: str | Path = "default",
+    overwrite: bool = False,
+    save_probabilities: bool = False,
+    base_dir_recording: str | Path | None = None,
+    call_duration_limits: str | Path | None = None,
+    label_suffix: str = "*",
+    verbosity: int = 2,
+    msgr: Messenger | None = None,
+) -> None:
+    """Predicts calls in a wav file or in every recording of a recording table (.csv)."""
+    if msgr is None:
+        msgr = Messenger(verbosity=verbosity, title="Predicting calls")
+    model_dir = Path(str(model_dir))
+    recording_path = Path(recording_path)
+    msgr.part(f"Loading model: {model_dir.stem}")
+    devices = _visible_devices()
+    model, orcai_parameter, shape = load_orcai_model(model_dir, device=devices[0] if devices else None)
+
+    if recording_path.suffix == ".wav":
+        return _predict_and_save(
+            recording_path=recording_path,
+            channel=channel,
+            model=model,
+            orcai_parameter=orcai_parameter,
+            shape=shape,
+            output_path=output_path,
+            overwrite=overwrite,
+            save_probabilities=save_probabilities,
+            call_duration_limits=call_duration_limits,
+            label_suffix=label_suffix,
+            msgr=msgr,
+            progressbar=None,
+        )
+    elif recording_path.suffix == ".csv":
+        recording_table = pd.read_csv(recording_path)
+    else:
+        raise ValueError("Recording file must be a wav or csv file")
+
+    if base_dir_recording is not None:
+        recording_table["base_dir_recording"] = str(base_dir_recording)
+    if (output_path is not None) & (output_path != "default"):
+        out_paths = [Path(output_path).joinpath(rec + "_" + model_dir.stem + "_predicted.txt") for rec in recording_table["recording"]]
+    else:
+        out_paths = [output_path] * len(recording_table)
+
+    msgr.part(f"Predicting annotations for {len(recording_table)} wav files")
+    rows = list(recording_table.index)
+    progressbar = tqdm(total=len(rows), desc="Starting ...", unit="file")
+
+    def run_row(i, mdl, pb):
+        try:
+            _predict_and_save(
+                recording_path=Path(recording_table.loc[i, "base_dir_recording"]).joinpath(recording_table.loc[i, "rel_recording_path"]),
+                channel=int(recording_table.loc[i, "channel"]),
+                model=mdl,
+                orcai_parameter=orcai_parameter,
+                shape=shape,
+                output_path=out_paths[rows.index(i)],
+                overwrite=overwrite,
+                save_probabilities=save_probabilities,
+                call_duration_limits=call_duration_limits,
+                label_suffix=label_suffix,
+                msgr=Messenger(verbosity=0),
+                progressbar=pb,
+            )
+        except Exception as e:  # per-recording isolation, like the reference loop (predict.py:752-755)
+            msgr.error(f"Error predicting {recording_table.loc[i, 'recording']}: {e.args[0] if e.args else e}")
+
+    if len(devices) <= 1:
+        for i in rows:
+            run_row(i, model, progressbar)
+            progressbar.update(1)
+    else:
+        # shard by recording: one worker (context + stream) per GPU pulling rows from a shared queue; host-side gather only
+        from orcai_b200.model import OrcaiModel
+
+        models = [model] + [OrcaiModel(orcai_parameter, shape, model.weights, device=d) for d in devices[1:]]
+        work: queue.Queue = queue.Queue()
+        for i in rows:
+            work.put(i)
+        lock = threading.Lock()
+
+        def worker(mdl):
+            while True:
+                try:
+                    i = work.get_nowait()
+                except queue.Empty:
+                    return
+                run_row(i, mdl, None)
+                with lock:
+                    progressbar.update(1)
+
+        threads = [threading.Thread(target=worker, args=(m,), daemon=True) for m in models]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+    progressbar.close()
+    msgr.success("Predictions finished.")
