@@ -1,0 +1,47 @@
+import os
+import sys
+from pathlib import Path
+
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu")
+
+
+def _have_gpu() -> bool:
+    try:
+        import torch
+
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.fixture(scope="session")
+def params():
+    from orcai_b200 import runtime
+
+    return runtime.bundled_parameters()
+
+
+@pytest.fixture(scope="session")
+def ctx(params):
+    """liborcai_b200 context on cuda:0 with seeded synthetic weights loaded."""
+    if not _have_gpu():
+        pytest.skip("no CUDA device")
+    from orcai_b200 import runtime
+    from orcai_b200.weights import synthetic_weights
+
+    P, S = params
+    c = runtime.get_context(P, S, 0)
+    c.load_weights(synthetic_weights(P, S, seed=1234))
+    return c
+
+
+@pytest.fixture(scope="session")
+def golden_dir():
+    return ROOT / "tests" / "golden"
