@@ -494,6 +494,8 @@ int net_load_weights(Ctx* c, const char* const* names, const float* const* data,
   if (P.n_blocks != 4 || P.filters[0] != 30 || P.filters[1] != 40 || P.filters[2] != 50 || P.filters[3] != 60 ||
       P.kernel_size != 3 || P.lstm_units != 128)
     ORCAI_FAIL(c, ORCAI_ERR_ARG, "network kernels are built for the orcai-V1 shape (filters 30/40/50/60, k=3, 128 LSTM units)");
+  if (P.snippet_len % (1 << P.n_blocks) != 0)
+    ORCAI_FAIL(c, ORCAI_ERR_ARG, "snippet length must be a multiple of 2^n_blocks (TF 'same' pooling pads only at the end for even heights)");
   nw->n_blocks = P.n_blocks;
   for (int i = 0; i < P.n_blocks; ++i) nw->filters[i] = P.filters[i];
   nw->H = P.snippet_len; nw->Wf = P.n_freq; nw->U = P.lstm_units; nw->L = P.n_labels;

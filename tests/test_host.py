@@ -1,0 +1,193 @@
+"""Host-side logic that needs no GPU: WAV reader, zarr writer, parameter block, writers, CLI surface."""
+
+import gzip
+import json
+import re
+from pathlib import Path
+
+import numpy as np
+import pandas as pd
+import pytest
+from click.testing import CliRunner
+
+from oracle import postprocess_oracle as po
+from orcai_b200 import _lib, cli, io, predict, runtime, wavio
+from orcai_b200.synth import synth_pcm16
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_abi_exports_every_declared_symbol():
+    header = (ROOT / "include" / "orcai_b200.h").read_text()
+    declared = set(re.findall(r"\b(orcai_[a-z_0-9]+)\s*\(", header))
+    lib = _lib.load_library()
+    assert declared == set(_lib.exported_symbols())
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.orcai_version() >= 100
+    assert lib.orcai_num_frames(28800000, 256) == 112501 and lib.orcai_num_snippets(112501, 736) == 304
+    assert lib.orcai_num_snippets(735, 736) == 0 and lib.orcai_num_snippets(736, 736) == 1
+
+
+def test_params_block(params):
+    P, S = params
+    p = _lib.params_from_dicts(P, S)
+    assert (p.n_fft, p.hop, p.band_lo, p.band_hi, p.n_freq, p.snippet_len, p.n_labels, p.n_blocks) == (512, 256, 0, 171, 171, 736, 7, 4)
+    assert p.q_lo == 0.01 and p.q_hi == 0.9990000000000001
+    assert list(p.filters)[:4] == [30, 40, 50, 60] and p.lstm_units == 128
+    assert runtime.shape_for(P) == S
+
+
+def test_no_cpu_fallback(params):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    P, S = params
+    with pytest.raises(_lib.OrcaiError) as e:
+        _lib.Context(P, S, 0)
+    assert "no CPU fallback" in str(e.value)
+
+
+@pytest.mark.parametrize("kind", ["pcm16", "pcm16_stereo", "pcm24", "pcm32", "float32", "u8"])
+def test_wav_reader(tmp_path, kind):
+    import struct
+
+    rng = np.random.default_rng(1)
+    n = 1000
+    x = rng.integers(-32768, 32767, size=(n, 2)).astype(np.int16)
+    path = tmp_path / f"{kind}.wav"
+
+    def write(fmt_tag, ch, bits, payload):
+        hdr = struct.pack("<HHIIHH", fmt_tag, ch, 48000, 48000 * ch * bits // 8, ch * bits // 8, bits)
+        with open(path, "wb") as f:
+            f.write(b"RIFF" + struct.pack("<I", 36 + len(payload)) + b"WAVE" + b"fmt " + struct.pack("<I", 16) + hdr)
+            f.write(b"LIST" + struct.pack("<I", 4) + b"abcd")  # an unrelated chunk to skip
+            f.write(b"data" + struct.pack("<I", len(payload)) + payload)
+
+    if kind == "pcm16":
+        wavio.write_wav_pcm16(path, x[:, 0])
+        y, sr, ch = wavio.read_wav(path)
+        assert y.dtype == np.int16 and np.array_equal(y, x[:, 0]) and (sr, ch) == (48000, 1)
+    elif kind == "pcm16_stereo":
+        wavio.write_wav_pcm16(path, x)
+        y, _, ch = wavio.read_wav(path, channel=2)
+        assert ch == 2 and np.array_equal(y, x[:, 1])
+        with pytest.raises(IndexError):
+            wavio.read_wav(path, channel=3)
+    elif kind == "pcm24":
+        v = x[:, 0].astype(np.int32) * 256 + 17
+        b = np.stack([(v & 0xFF), (v >> 8) & 0xFF, (v >> 16) & 0xFF], axis=1).astype(np.uint8).tobytes()
+        write(1, 1, 24, b)
+        y, _, _ = wavio.read_wav(path)
+        np.testing.assert_array_equal(y, (v / 8388608.0).astype(np.float32))
+    elif kind == "pcm32":
+        v = x[:, 0].astype(np.int32) * 65536
+        write(1, 1, 32, v.astype("<i4").tobytes())
+        y, _, _ = wavio.read_wav(path)
+        np.testing.assert_array_equal(y, (v / 2147483648.0).astype(np.float32))
+    elif kind == "float32":
+        v = (x[:, 0] / 32768.0).astype("<f4")
+        write(3, 1, 32, v.tobytes())
+        y, _, _ = wavio.read_wav(path)
+        np.testing.assert_array_equal(y, v)
+    else:
+        v = rng.integers(0, 255, n).astype(np.uint8)
+        write(1, 1, 8, v.tobytes())
+        y, _, _ = wavio.read_wav(path)
+        np.testing.assert_array_equal(y, ((v.astype(np.float32) - 128) / 128).astype(np.float32))
+
+
+def test_wav_reader_rejects_garbage(tmp_path):
+    p = tmp_path / "x.wav"
+    p.write_bytes(b"not a wave file at all")
+    with pytest.raises(ValueError):
+        wavio.read_wav(p)
+
+
+def test_zarr_v3_store_roundtrip(tmp_path):
+    rng = np.random.default_rng(0)
+    a = rng.random((4321, 171), dtype=np.float32)
+    a[2000:4000] = 0.0  # an all-fill chunk is omitted from the store
+    io.save_as_zarr(a, tmp_path / "spectrogram.zarr")
+    meta = json.loads((tmp_path / "spectrogram.zarr" / "zarr.json").read_text())
+    assert meta["zarr_format"] == 3 and meta["node_type"] == "array" and meta["shape"] == [4321, 171] and meta["data_type"] == "float32"
+    assert meta["chunk_grid"]["configuration"]["chunk_shape"] == [2000, 171]
+    assert [c["name"] for c in meta["codecs"]] == ["bytes", "gzip"]
+    assert (tmp_path / "spectrogram.zarr" / "c" / "0" / "0").exists() and not (tmp_path / "spectrogram.zarr" / "c" / "1").exists()
+    raw = gzip.decompress((tmp_path / "spectrogram.zarr" / "c" / "2" / "0").read_bytes())
+    assert len(raw) == 2000 * 171 * 4  # edge chunk stored full size
+    np.testing.assert_array_equal(io.read_zarr(tmp_path / "spectrogram.zarr"), a)
+    t = np.arange(4321) * 256 / 48000.0
+    io.write_vector_to_json(t, tmp_path / "times.json")
+    assert json.loads((tmp_path / "times.json").read_text()) == {"min": 0.0, "max": float(t[-1]), "length": 4321}
+    np.testing.assert_allclose(io.generate_times_from_spectrogram(tmp_path / "times.json"), t, rtol=0, atol=1e-9)
+
+
+def test_label_writer_matches_oracle_writer(golden_dir, tmp_path):
+    fx = json.loads((golden_dir / "postprocess_seed11.json").read_text())
+    g = np.load(golden_dir / "postprocess_seed11.npz")
+    labels = predict.compute_labels(list(g["starts"]), list(g["stops"]), fx["labels"], 16, "*")
+    assert list(labels.columns) == ["start", "stop", "label"] and labels["start"].dtype == np.int64
+    predict.save_predictions(labels, tmp_path / "out.txt", fx["delta_t"])
+    assert (tmp_path / "out.txt").read_bytes() == fx["tsv"].encode()
+    for case in fx["writer_cases"]:
+        rows = case["rows"]
+        df = predict.compute_labels([r[0] // 16 for r in rows], [r[1] // 16 for r in rows], [r[2][:-1] for r in rows], 16, "*")
+        assert predict.labels_to_tsv(df, fx["delta_t"]) == case["tsv"]
+    empty = predict.compute_labels([], [], [], 16, "*")
+    assert predict.labels_to_tsv(empty, fx["delta_t"]) == "start\tstop\tlabel\n"
+
+
+def test_probability_writer_and_filter(tmp_path):
+    agg = np.random.default_rng(0).random((50, 7))
+    P, _ = runtime.bundled_parameters()
+    predict.save_prediction_probabilities(agg, P, 256 / 48000, tmp_path / "rec_predicted.txt")
+    out = tmp_path / "rec_predicted_probabilities.csv.gz"
+    assert gzip.decompress(out.read_bytes()).decode() == po.probabilities_csv(agg, P["calls"], 256 / 48000)
+    df = pd.DataFrame({"start": [0, 0, 32], "stop": [160, 16, 6000], "label": ["BR*", "SS*", "X*"]})
+    lim = {"default": [0.5, None], "SS": [0, 0.05], "BR": [None, 1.0]}
+    from orcai_b200.auxiliary import Messenger
+
+    kept = predict.filter_predictions(df, 256 / 48000, lim, msgr=Messenger(verbosity=0))
+    assert [tuple(r) for r in kept[["start", "stop", "label"]].itertuples(index=False)] == po.filter_rows(
+        [(0, 160, "BR*"), (0, 16, "SS*"), (32, 6000, "X*")], 256 / 48000, lim
+    )
+
+
+def test_cli_surface():
+    """Option names, short flags and defaults of the two drop-in commands (reference cli.py:93-184, 359-416)."""
+    cmds = cli.cli.commands
+    assert {"predict", "create-spectrograms", "filter-predictions"} <= set(cmds)
+    opts = {o.name: o for o in cmds["predict"].params}
+    assert set(opts) == {"recording_path", "channel", "model", "model_dir", "output_path", "overwrite", "save_probabilities",
+                         "base_dir_recording", "call_duration_limits", "label_suffix", "verbosity"}
+    assert opts["channel"].default == 1 and opts["output_path"].default == "default" and opts["label_suffix"].default == "*"
+    assert opts["verbosity"].default == 2 and opts["model"].default == "orcai-v1"
+    assert set(opts["model_dir"].opts) == {"--model_dir", "-md"} and set(opts["save_probabilities"].opts) == {"--save_probabilities", "-sp"}
+    assert set(opts["call_duration_limits"].opts) == {"--call_duration_limits", "-cdl"} and set(opts["base_dir_recording"].opts) == {"--base_dir_recording", "-bdr"}
+    so = {o.name: o for o in cmds["create-spectrograms"].params}
+    assert set(so) == {"recording_table_path", "output_dir", "base_dir_recording", "orcai_parameter", "include_not_annotated",
+                       "include_no_possible_annotations", "overwrite", "verbosity"}
+    assert set(so["include_not_annotated"].opts) == {"--include_not_annotated", "-en"}
+    assert set(so["include_no_possible_annotations"].opts) == {"--include_no_possible_annotations", "-enp"}
+    r = CliRunner().invoke(cli.cli, ["predict", "--help"])
+    assert r.exit_code == 0 and "RECORDING_PATH" in r.output
+
+
+def test_predict_rejects_unknown_suffix(tmp_path, monkeypatch):
+    import torch
+
+    if not torch.cuda.is_available():
+        pytest.skip("model loading needs the GPU context")
+    monkeypatch.setenv("ORCAI_B200_SYNTHETIC_WEIGHTS", "1234")
+    p = tmp_path / "rec.flac"
+    p.write_bytes(b"x")
+    with pytest.raises(ValueError, match="wav or csv"):
+        predict.predict(p, verbosity=0)
+
+
+def test_synthetic_audio_is_deterministic():
+    a = synth_pcm16(1.0, seed=7)
+    b = synth_pcm16(1.0, seed=7)
+    assert a.dtype == np.int16 and len(a) == 48000 and np.array_equal(a, b) and not np.array_equal(a, synth_pcm16(1.0, seed=8))
