@@ -158,7 +158,7 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--hours", type=float, default=1.0, help="length of the synthetic recording each GPU annotates per step")
-    ap.add_argument("--cpu-sample-seconds", type=float, default=45.0)
+    ap.add_argument("--cpu-sample-seconds", type=float, default=600.0, help="bounded CPU-oracle sample (BASELINE config 0: one 10-min recording)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--chunk", type=int, default=0, help="snippets per network chunk (0 = library default)")
     args = ap.parse_args()
@@ -221,12 +221,14 @@ def main() -> None:
     t0 = time.perf_counter()
     stage = {k: 0.0 for k in ("stft_ms", "select_ms", "network_ms", "post_ms", "total_ms")}
     n_segments = 0
+    net_stage = None
     for _ in range(args.steps):
         out = ctx.predict_pcm(pcm_pinned, want_agg=False, resident=True)  # synchronous: returns after the segments are on the host
         n_segments = len(out[3])
         tm = ctx.timings()
         for k in stage:
             stage[k] += tm[k]
+        net_stage = tm["net_stage_ms"]
     barrier()
     t_res = max_over_ranks(time.perf_counter() - t0)
     clocks = sampler.stop()
@@ -264,6 +266,8 @@ def main() -> None:
                        "network_path": "fp32 cuda-core"},
             "device_ms_per_step": dev_ms,
             "stage_ms": {k: v / args.steps for k, v in stage.items()},
+            "net_stage_ms_first_chunk": dict(zip(["conv0", "block1", "block2", "block3", "block4", "final_sep", "lstm1_proj", "lstm1_rec", "lstm2_proj",
+                                                  "lstm2_rec", "dense"], [round(v, 4) for v in net_stage[:11]])) | {"snippets": int(net_stage[15])},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(pcm.nbytes), "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * t_e2e / args.steps},
             "gpu_launches": int(launches),
             "clocks": clocks,

@@ -158,16 +158,7 @@ int orcai_create(int device, const orcai_params* p, orcai_ctx** out) {
   if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
   for (auto& ev : c->ev)
     if ((e = cudaEventCreate(&ev)) != cudaSuccess) return fail("cudaEventCreate", e);
-  for (int which = 0; which < 2; ++which) {
-    const StftHostTables t = make_stft_tables(which ? 0.5 / 32768.0 : 0.5);
-    std::vector<float> flat;
-    flat.insert(flat.end(), t.win.begin(), t.win.end());
-    flat.insert(flat.end(), t.tw.begin(), t.tw.end());
-    flat.insert(flat.end(), t.ck.begin(), t.ck.end());
-    if ((e = cudaMalloc(&c->d_tables[which], flat.size() * sizeof(float))) != cudaSuccess) return fail("cudaMalloc", e);
-    if ((e = cudaMemcpy(c->d_tables[which], flat.data(), flat.size() * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess)
-      return fail("cudaMemcpy", e);
-  }
+  if (stft_upload_tables(c) != ORCAI_OK) { g_create_error = c->err; orcai_destroy(c); return ORCAI_ERR_CUDA; }
   if ((e = cudaMalloc(&c->d_sel, sizeof(SelectState))) != cudaSuccess) return fail("cudaMalloc", e);
   if ((e = cudaMemset(c->d_sel, 0, sizeof(SelectState))) != cudaSuccess) return fail("cudaMemset", e);
   net_create(c);
@@ -181,6 +172,7 @@ void orcai_destroy(orcai_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   net_destroy(c);
   for (auto& t : c->d_tables) if (t) cudaFree(t);
+  for (auto& t : c->d_tables64) if (t) cudaFree(t);
   if (c->d_sel) cudaFree(c->d_sel);
   if (c->d_pcm) cudaFree(c->d_pcm);
   if (c->d_raw) cudaFree(c->d_raw);
@@ -204,6 +196,7 @@ int orcai_get_timings(const orcai_ctx* c, orcai_timings* out) {
 int orcai_set_option(orcai_ctx* c, const char* key, int64_t value) {
   if (!c || !key) return ORCAI_ERR_ARG;
   if (!strcmp(key, "chunk")) return net_set_chunk(c, (int)value);
+  if (!strcmp(key, "stft_f64")) { c->stft_f64 = value ? 1 : 0; c->have_stats = false; return ORCAI_OK; }
   ORCAI_FAIL(c, ORCAI_ERR_ARG, "unknown option '%s'", key);
 }
 
@@ -315,6 +308,7 @@ int orcai_forward_host(orcai_ctx* c, const float* snippets_host, int64_t n, floa
   ORCAI_CUDA(c, cudaStreamSynchronize(c->stream));
   c->tm.h2d_ms = elapsed(c, EV_START, EV_H2D);
   c->tm.network_ms = elapsed(c, EV_H2D, EV_NET);
+  net_collect_stage_times(c);
   c->tm.d2h_ms = elapsed(c, EV_NET, EV_END);
   c->tm.total_ms = elapsed(c, EV_START, EV_END);
   return ORCAI_OK;
@@ -335,6 +329,7 @@ int orcai_forward_resident(orcai_ctx* c, int64_t first, int64_t n, float* preds_
     ORCAI_CUDA(c, cudaMemcpyAsync(preds_out_host, c->d_preds, (size_t)n * Tn * c->p.n_labels * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   ORCAI_CUDA(c, cudaStreamSynchronize(c->stream));
   c->tm.network_ms = elapsed(c, EV_NORM, EV_NET);
+  net_collect_stage_times(c);
   return ORCAI_OK;
 }
 
@@ -387,6 +382,7 @@ int orcai_predict_resident(orcai_ctx* c, double threshold, orcai_spec_stats* sta
   c->tm.select_ms = elapsed(c, EV_STFT, EV_SELECT);
   c->tm.normalise_ms = elapsed(c, EV_SELECT, EV_NORM);
   c->tm.network_ms = elapsed(c, EV_NORM, EV_NET);
+  net_collect_stage_times(c);
   c->tm.post_ms = elapsed(c, EV_NET, EV_POST);
   c->tm.total_ms = elapsed(c, EV_H2D, EV_POST);
   return rc != ORCAI_OK ? rc : rc2;

@@ -21,8 +21,16 @@ struct SelectState {                 // device-resident scratch of the exact two
   float db_ref;                      // 10*log10(max(1e-10, pmax))
   float lo, hi;                      // selected percentiles (shifted + floored dB)
   unsigned int tile_counter;         // scan kernel dynamic tile id
-  unsigned int pad;
+  int precise_log;                   // 1: dB through log10f (float64 STFT variant), 0: through lg2.approx (fast variant)
 };
+
+#ifdef __CUDACC__
+// 10*log10(max(1e-10, p)): the one expression K1 and the select's reference level share, so that the loudest cell is exactly 0 dB
+__device__ __forceinline__ float power_to_db(float p, bool precise) {
+  const float q = fmaxf(p, 1e-10f);
+  return precise ? 10.0f * log10f(q) : 3.01029995663981195f * __log2f(q);
+}
+#endif
 
 struct NetWeights;                   // net.cu
 
@@ -33,6 +41,8 @@ struct Ctx {
   std::string err;
   // STFT tables on device: [0]=float input scale, [1]=int16 input scale ; each 768 float2
   float* d_tables[2] = {nullptr, nullptr};
+  double* d_tables64[2] = {nullptr, nullptr};
+  int h_flags[2] = {0, 1};           // stable host source for tiny async H2D copies
   SelectState* d_sel = nullptr;
   // current recording
   void* d_pcm = nullptr;  size_t pcm_cap = 0;  int pcm_dtype = 0;  int64_t n_samples = 0;
@@ -51,6 +61,7 @@ struct Ctx {
   cudaEvent_t ev[16] = {};
   uint64_t launches = 0;
   int sm_count = 148;
+  int stft_f64 = 1;                   // 1: float64 FFT (parity grade, default), 0: float32 FFT (fast variant)
 };
 
 #define ORCAI_CUDA(ctx, call)                                                            \
@@ -82,6 +93,7 @@ int ensure_device_buffer(Ctx* c, void** p, size_t* cap, size_t bytes);
 
 // ---- stage launchers (all asynchronous on c->stream) -------------------------------------------
 // K1: fused window + rFFT512 + |.|^2 + 10log10 + crop ; also the global power max.   (stft.cu)
+int stft_upload_tables(Ctx* c);
 int launch_stft(Ctx* c, const void* d_pcm, int dtype, int64_t n_samples, int64_t T, float* d_raw);
 // exact percentiles (radix select on shifted/floored dB) and K2 normalise.          (select.cu)
 int launch_select(Ctx* c, const float* d_raw, int64_t T);
@@ -91,6 +103,7 @@ int launch_read_db(Ctx* c, const float* d_raw, int64_t T, float* d_out);        
 int net_create(Ctx* c);
 void net_destroy(Ctx* c);
 int net_set_chunk(Ctx* c, int chunk);
+void net_collect_stage_times(Ctx* c);
 int net_load_weights(Ctx* c, const char* const* names, const float* const* data, const int64_t* sizes, int n);
 // input_mode 0: raw dB buffer (pitch kRawLd, normalise on load with c->d_sel stats), snippet i starts at row
 //               (first + i) * shift ; input_mode 1: normalised compact snippets (pitch n_freq), snippet stride = snippet_len rows

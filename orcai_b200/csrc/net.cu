@@ -43,6 +43,10 @@ struct NetWeights {
   // activation workspace
   float* ws = nullptr; size_t ws_cap = 0;
   int chunk = 128;
+  // per-stage CUDA events of the first chunk of the last forward (profiling aid, see orcai_timings.net_stage_ms)
+  static constexpr int kNumMarks = 14;
+  cudaEvent_t ev[kNumMarks] = {};
+  long long marked_snippets = 0;
 };
 
 namespace {
@@ -468,13 +472,27 @@ int load_sep(Ctx* c, HostTensors& ht, const std::string& sp, const std::string& 
 
 int net_create(Ctx* c) {
   c->net = new NetWeights();
+  for (auto& e : c->net->ev) ORCAI_CUDA(c, cudaEventCreate(&e));
   return ORCAI_OK;
+}
+
+// stage times of the first chunk of the last forward; call after the stream has been synchronised
+void net_collect_stage_times(Ctx* c) {
+  NetWeights* nw = c->net;
+  if (!nw || nw->marked_snippets == 0) return;
+  for (int i = 0; i + 1 < NetWeights::kNumMarks; ++i) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, nw->ev[i], nw->ev[i + 1]) != cudaSuccess) { cudaGetLastError(); ms = 0.f; }
+    c->tm.net_stage_ms[i] = ms;
+  }
+  c->tm.net_stage_ms[15] = (float)nw->marked_snippets;
 }
 
 void net_destroy(Ctx* c) {
   if (!c->net) return;
   for (void* p : c->net->allocs) cudaFree(p);
   if (c->net->ws) cudaFree(c->net->ws);
+  for (auto& e : c->net->ev) if (e) cudaEventDestroy(e);
   delete c->net;
   c->net = nullptr;
 }
@@ -603,8 +621,13 @@ int net_forward(Ctx* c, const float* d_in, int input_mode, int64_t first, int64_
   float* tB = tA + t_max * chunk;
   const int shift = c->p.snippet_len / 2;
 
+  int mark_i = 0;
+  auto mark = [&](bool on) { if (on && mark_i < NetWeights::kNumMarks) cudaEventRecord(nw->ev[mark_i++], c->stream); };
   for (int64_t s0 = 0; s0 < n; s0 += chunk) {
     const long long m = std::min<long long>(chunk, n - s0);
+    const bool mk = (s0 == 0);
+    if (mk) nw->marked_snippets = m;
+    mark(mk);
     {  // entry conv
       const long long total = m * H * Wf;
       long long grid = (total + 255) / 256;
@@ -616,33 +639,44 @@ int net_forward(Ctx* c, const float* d_in, int input_mode, int64_t first, int64_
       c->launches++;
       ORCAI_CUDA(c, cudaGetLastError());
     }
+    mark(mk);  // 0: conv0
     int h = H, w = Wf;
     ORCAI_CHECK((run_block<16, 30>(c, pA, tA, tB, pB, m, h, w, 0))); h = (h + 1) / 2; w = (w + 1) / 2;
+    mark(mk);  // 1: block1
     ORCAI_CHECK((run_block<30, 40>(c, pB, tA, tB, pA, m, h, w, 1))); h = (h + 1) / 2; w = (w + 1) / 2;
+    mark(mk);  // 2: block2
     ORCAI_CHECK((run_block<40, 50>(c, pA, tA, tB, pB, m, h, w, 2))); h = (h + 1) / 2; w = (w + 1) / 2;
+    mark(mk);  // 3: block3
     ORCAI_CHECK((run_block<50, 60>(c, pB, tA, tB, pA, m, h, w, 3))); h = (h + 1) / 2; w = (w + 1) / 2;
+    mark(mk);  // 4: block4
     // final separable conv -> features (m, Tn, w*36) ; NHWC flattening is already w*36+c
     float* feat = pB;
     ORCAI_CHECK((run_sepconv<60, 36, false, true>(c, pA, feat, m, h, w, nw->fin)));
+    mark(mk);  // 5: final sepconv
     const long long rows = m * Tn;
     float* xz = tA;                       // (rows, 2G)
     float* h1 = tB;                       // (rows, 2U)
     float* h2 = pA;                       // (rows, 2U)
     float* d1 = tB + (size_t)rows * 2 * U;  // (rows, 128)
     ORCAI_CHECK((run_gemm<0>(c, feat, nw->lstm_wih[0], nw->lstm_bih[0], xz, rows, 2 * G, nw->feat)));
+    mark(mk);  // 6: lstm1 input projection
     {
       dim3 grid((unsigned)((m + kSN - 1) / kSN), 2);
       lstm_rec_kernel<128><<<grid, 512, 0, c->stream>>>(xz, nw->lstm_whh[0], h1, m, Tn);
       c->launches++;
     }
+    mark(mk);  // 7: lstm1 recurrence
     ORCAI_CHECK((run_gemm<0>(c, h1, nw->lstm_wih[1], nw->lstm_bih[1], xz, rows, 2 * G, 2 * U)));
+    mark(mk);  // 8: lstm2 input projection
     {
       dim3 grid((unsigned)((m + kSN - 1) / kSN), 2);
       lstm_rec_kernel<128><<<grid, 512, 0, c->stream>>>(xz, nw->lstm_whh[1], h2, m, Tn);
       c->launches++;
     }
+    mark(mk);  // 9: lstm2 recurrence
     ORCAI_CHECK((run_gemm<1>(c, h2, nw->d1_w, nw->d1_b, d1, rows, kDense, 2 * U)));
     ORCAI_CHECK((run_gemm<2>(c, d1, nw->d2_w, nw->d2_b, d_preds + (size_t)s0 * Tn * L, rows, L, kDense)));
+    mark(mk);  // 10: dense head
     ORCAI_CUDA(c, cudaGetLastError());
   }
   return ORCAI_OK;

@@ -15,7 +15,6 @@ namespace orcai {
 
 namespace {
 
-constexpr float kTenLog10Of2 = 3.01029995663981195f;
 constexpr float kTopDb = 80.0f;
 
 __device__ __forceinline__ unsigned int f2key(float v) {
@@ -32,7 +31,7 @@ __global__ void select_init_kernel(SelectState* st, unsigned long long rank_lo, 
   // db_ref through the same expression K1 uses, so the loudest cell is exactly 0 dB
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     const float pmax = __uint_as_float(st->pmax_bits);
-    st->db_ref = kTenLog10Of2 * __log2f(fmaxf(pmax, 1e-10f));
+    st->db_ref = power_to_db(pmax, st->precise_log != 0);
     st->rank[0] = rank_lo;
     st->rank[1] = rank_hi;
     st->prefix[0] = 0u;

@@ -4,11 +4,17 @@
 // reference (the "ref = np.max" shift and the top_db floor are applied by the consumers from the
 // exact global maximum this kernel produces, so no second pass over the 257-bin array exists).
 //
-// Mapping: 8 threads per frame, 4 frames per warp, 8 warps per CTA, 2 CTAs per SM; each warp walks
-// groups of 4 consecutive frames (the 50% overlap makes the second read of every sample an L1 hit).
-// All FFT butterflies are register-resident with immediate twiddles (fft_gen.cuh); the only exchange
-// is one warp-private shared-memory transpose (stft_core.cuh).  HBM traffic per frame: 256 new
-// samples in, band_hi-band_lo floats out.
+// Mapping: 8 threads per frame, 4 frames per warp, 8 warps per CTA; each warp walks groups of 4
+// consecutive frames (the 50% overlap makes the second read of every sample an L1 hit).  All FFT
+// butterflies are register-resident with immediate twiddles (fft_gen.cuh); the only exchange is one
+// warp-private shared-memory transpose (stft_core.cuh).  HBM traffic per frame: 256 new samples in,
+// band_hi-band_lo floats out.
+//
+// Two arithmetic variants of the same code:
+//   RealT = double : the FFT runs in float64 like the reference's numpy.fft.rfft and is rounded to
+//                    complex64 before |.|^2 and log10f - parity grade (default).
+//   RealT = float  : float32 FFT, lg2.approx for the logarithm - the fast variant (tail cells that
+//                    sit > 60 dB below their own frame's peak can be off by up to ~2e-3 dB).
 #include "common.h"
 #include "stft_core.cuh"
 #include "stft_tables.h"
@@ -19,17 +25,23 @@ namespace {
 
 constexpr int kWarpsPerCta = 8;
 constexpr int kFramesPerWarp = 4;
-constexpr int kTableFloat2 = 768;
-constexpr size_t kStftSmem = (size_t)kTableFloat2 * sizeof(float2) +
-                             (size_t)kWarpsPerCta * kFramesPerWarp * kFrameBufFloat2 * sizeof(float2);
+constexpr int kTableCx = 768;
 
-__device__ __forceinline__ float2 ld_pair(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
-__device__ __forceinline__ float2 ld_pair(const int16_t* p) {
+template <typename RealT>
+constexpr size_t stft_smem_bytes() {
+  return (size_t)kTableCx * sizeof(Cx<RealT>) + (size_t)kWarpsPerCta * kFramesPerWarp * kFrameBufCx * sizeof(Cx<RealT>);
+}
+
+__device__ __forceinline__ Cx<float> ld_pair(const float* p) {
+  const float2 v = __ldg(reinterpret_cast<const float2*>(p));
+  return Cx<float>{v.x, v.y};
+}
+__device__ __forceinline__ Cx<float> ld_pair(const int16_t* p) {
   // two PCM16 samples -> exact float integers via the 1.5*2^23 magic constant (no I2F on the slow pipe)
   const unsigned int u = __ldg(reinterpret_cast<const unsigned int*>(p));
   const int lo = (int)(short)(u & 0xffffu);
   const int hi = ((int)u) >> 16;
-  float2 r;
+  Cx<float> r;
   r.x = __int_as_float(0x4B400000 + lo) - 12582912.0f;
   r.y = __int_as_float(0x4B400000 + hi) - 12582912.0f;
   return r;
@@ -37,23 +49,24 @@ __device__ __forceinline__ float2 ld_pair(const int16_t* p) {
 __device__ __forceinline__ float ld_one(const float* p) { return __ldg(p); }
 __device__ __forceinline__ float ld_one(const int16_t* p) { return (float)__ldg(p); }
 
-template <typename SampleT>
-__global__ void __launch_bounds__(kWarpsPerCta * 32, 2)
+template <typename SampleT, typename RealT>
+__global__ void __launch_bounds__(kWarpsPerCta * 32, sizeof(RealT) == 4 ? 2 : 1)
 stft_db_kernel(const SampleT* __restrict__ pcm, long long n_samples, long long T, float* __restrict__ raw,
-               int ld, int band_lo, int band_hi, const float2* __restrict__ tables,
+               int ld, int band_lo, int band_hi, const Cx<RealT>* __restrict__ tables,
                unsigned int* __restrict__ pmax_bits) {
+  constexpr bool kPrecise = sizeof(RealT) == 8;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float2* s_tab = reinterpret_cast<float2*>(smem_raw);
-  float2* s_buf = s_tab + kTableFloat2;
-  for (int i = threadIdx.x; i < kTableFloat2; i += blockDim.x) s_tab[i] = tables[i];
+  Cx<RealT>* s_tab = reinterpret_cast<Cx<RealT>*>(smem_raw);
+  Cx<RealT>* s_buf = s_tab + kTableCx;
+  for (int i = threadIdx.x; i < kTableCx; i += blockDim.x) s_tab[i] = tables[i];
   __syncthreads();
-  const StftTables tb{s_tab, s_tab + 256, s_tab + 512};
+  const StftTables<RealT> tb{s_tab, s_tab + 256, s_tab + 512};
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int t = lane & 7;
   const int fl = lane >> 3;
-  float2* fbuf = s_buf + (size_t)(warp * kFramesPerWarp + fl) * kFrameBufFloat2;
+  Cx<RealT>* fbuf = s_buf + (size_t)(warp * kFramesPerWarp + fl) * kFrameBufCx;
 
   const long long n_groups = (T + kFramesPerWarp - 1) / kFramesPerWarp;
   const long long g_stride = (long long)gridDim.x * kWarpsPerCta;
@@ -63,7 +76,7 @@ stft_db_kernel(const SampleT* __restrict__ pcm, long long n_samples, long long T
   for (long long g = (long long)blockIdx.x * kWarpsPerCta + warp; g < n_groups; g += g_stride) {
     const long long j = g * kFramesPerWarp + fl;
     const long long base = (j - 1) * kHop;  // first sample of frame j (centre padding of n_fft/2)
-    float2 x[32];
+    Cx<float> x[32];
     // warp-uniform: all 4 frames of the group fully inside the recording
     const long long j0 = g * kFramesPerWarp;
     const bool interior = (j0 >= 1) && ((j0 + kFramesPerWarp) * kHop <= n_samples);
@@ -79,13 +92,15 @@ stft_db_kernel(const SampleT* __restrict__ pcm, long long n_samples, long long T
         x[p].y = (s0 + 1 >= 0 && s0 + 1 < n_samples) ? ld_one(pcm + s0 + 1) : 0.0f;
       }
     }
-    stage_a(x, t, tb, fbuf);
+    stage_a<RealT>(x, t, tb, fbuf);
     __syncwarp();
     const bool live = j < T;
     float* out = raw + (size_t)(live ? j : 0) * ld - band_lo;
-    stage_b(t, tb, fbuf, [&](int k, float pw) {
+    stage_b<RealT>(t, tb, fbuf, [&](int k, RealT re, RealT im) {
+      const float fr = (float)re, fi = (float)im;  // complex64 rounding of the reference's stft matrix (no-op for RealT = float)
+      const float pw = fmaf(fr, fr, fi * fi);
       pmax = fmaxf(pmax, live ? pw : 0.0f);
-      if (live && k >= band_lo && k < band_hi) out[k] = kTenLog10Of2 * __log2f(fmaxf(pw, kAminPower));
+      if (live && k >= band_lo && k < band_hi) out[k] = power_to_db(pw, kPrecise);
     });
     __syncwarp();
   }
@@ -93,34 +108,64 @@ stft_db_kernel(const SampleT* __restrict__ pcm, long long n_samples, long long T
   if (lane == 0 && m != 0u) atomicMax(pmax_bits, m);
 }
 
-}  // namespace
-
-int launch_stft(Ctx* c, const void* d_pcm, int dtype, int64_t n_samples, int64_t T, float* d_raw) {
-  static bool attr_set[2] = {false, false};
-  const int which = (dtype == ORCAI_PCM_I16) ? 1 : 0;
-  if (!attr_set[which]) {
-    if (which)
-      ORCAI_CUDA(c, cudaFuncSetAttribute(stft_db_kernel<int16_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStftSmem));
-    else
-      ORCAI_CUDA(c, cudaFuncSetAttribute(stft_db_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStftSmem));
-    attr_set[which] = true;
+template <typename SampleT, typename RealT>
+int launch_variant(Ctx* c, const void* d_pcm, int64_t n_samples, int64_t T, float* d_raw, const void* tab) {
+  static bool attr_set = false;
+  constexpr size_t smem = stft_smem_bytes<RealT>();
+  if (!attr_set) {
+    ORCAI_CUDA(c, cudaFuncSetAttribute(stft_db_kernel<SampleT, RealT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
   }
-  ORCAI_CUDA(c, cudaMemsetAsync(&c->d_sel->pmax_bits, 0, sizeof(unsigned int), c->stream));
   const long long n_groups = (T + kFramesPerWarp - 1) / kFramesPerWarp;
   long long ctas = (n_groups + kWarpsPerCta - 1) / kWarpsPerCta;
-  const long long max_ctas = (long long)c->sm_count * 2;
+  const long long max_ctas = (long long)c->sm_count * (sizeof(RealT) == 4 ? 2 : 1);
   if (ctas > max_ctas) ctas = max_ctas;
   if (ctas < 1) ctas = 1;
-  const float2* tab = reinterpret_cast<const float2*>(c->d_tables[which]);
-  if (which)
-    stft_db_kernel<int16_t><<<(unsigned)ctas, kWarpsPerCta * 32, kStftSmem, c->stream>>>(
-        static_cast<const int16_t*>(d_pcm), n_samples, T, d_raw, kRawLd, c->p.band_lo, c->p.band_hi, tab, &c->d_sel->pmax_bits);
-  else
-    stft_db_kernel<float><<<(unsigned)ctas, kWarpsPerCta * 32, kStftSmem, c->stream>>>(
-        static_cast<const float*>(d_pcm), n_samples, T, d_raw, kRawLd, c->p.band_lo, c->p.band_hi, tab, &c->d_sel->pmax_bits);
+  stft_db_kernel<SampleT, RealT><<<(unsigned)ctas, kWarpsPerCta * 32, smem, c->stream>>>(
+      static_cast<const SampleT*>(d_pcm), n_samples, T, d_raw, kRawLd, c->p.band_lo, c->p.band_hi,
+      static_cast<const Cx<RealT>*>(tab), &c->d_sel->pmax_bits);
   c->launches++;
   ORCAI_CUDA(c, cudaGetLastError());
   return ORCAI_OK;
+}
+
+}  // namespace
+
+int stft_upload_tables(Ctx* c) {
+  for (int which = 0; which < 2; ++which) {
+    const double scale = which ? 0.5 / 32768.0 : 0.5;
+    {
+      const StftHostTables<float> t = make_stft_tables<float>(scale);
+      std::vector<float> flat(t.win);
+      flat.insert(flat.end(), t.tw.begin(), t.tw.end());
+      flat.insert(flat.end(), t.ck.begin(), t.ck.end());
+      ORCAI_CUDA(c, cudaMalloc(&c->d_tables[which], flat.size() * sizeof(float)));
+      ORCAI_CUDA(c, cudaMemcpy(c->d_tables[which], flat.data(), flat.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    {
+      const StftHostTables<double> t = make_stft_tables<double>(scale);
+      std::vector<double> flat(t.win);
+      flat.insert(flat.end(), t.tw.begin(), t.tw.end());
+      flat.insert(flat.end(), t.ck.begin(), t.ck.end());
+      ORCAI_CUDA(c, cudaMalloc(&c->d_tables64[which], flat.size() * sizeof(double)));
+      ORCAI_CUDA(c, cudaMemcpy(c->d_tables64[which], flat.data(), flat.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+  }
+  return ORCAI_OK;
+}
+
+int launch_stft(Ctx* c, const void* d_pcm, int dtype, int64_t n_samples, int64_t T, float* d_raw) {
+  const int which = (dtype == ORCAI_PCM_I16) ? 1 : 0;
+  // pmax and the flag telling the consumers which logarithm K1 used
+  ORCAI_CUDA(c, cudaMemsetAsync(&c->d_sel->pmax_bits, 0, sizeof(unsigned int), c->stream));
+  const int precise = c->stft_f64 ? 1 : 0;
+  ORCAI_CUDA(c, cudaMemcpyAsync(&c->d_sel->precise_log, &c->h_flags[precise], sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  if (c->stft_f64) {
+    if (which) return launch_variant<int16_t, double>(c, d_pcm, n_samples, T, d_raw, c->d_tables64[1]);
+    return launch_variant<float, double>(c, d_pcm, n_samples, T, d_raw, c->d_tables64[0]);
+  }
+  if (which) return launch_variant<int16_t, float>(c, d_pcm, n_samples, T, d_raw, c->d_tables[1]);
+  return launch_variant<float, float>(c, d_pcm, n_samples, T, d_raw, c->d_tables[0]);
 }
 
 }  // namespace orcai

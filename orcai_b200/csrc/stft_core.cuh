@@ -1,5 +1,7 @@
 // Per-thread building blocks of the fused STFT kernel (K1).  Host+device so that the exact
-// index arithmetic can be replayed on the CPU (tests/host_emul/stft_emul.cpp).
+// index arithmetic can be replayed on the CPU (tests/host_emul/stft_emul.cpp).  Templated on the
+// real type: float (fast variant) and double (parity-grade variant: the reference's numpy.fft.rfft
+// runs in float64 and is then rounded to complex64).
 //
 // Replaces the reference's librosa.stft + amplitude_to_db call sites
 // (src/orcAI/spectrogram.py:34-39, 51-53).
@@ -7,11 +9,11 @@
 // One 512-sample frame is handled by 8 threads (t = 0..7):
 //   z[m] = y[2m] + i*y[2m+1], m = 8*n1 + t             (256-point complex FFT of the packed real frame)
 //   stage A : thread t = n2 runs a 32-point FFT over n1, applies W256^(n2*k1), writes row k1 of the
-//             frame's 32x8 exchange buffer in shared memory (XOR-swizzled 16-byte chunks)
+//             frame's 32x8 exchange buffer in shared memory (XOR-swizzled 2-element chunks)
 //   stage B : thread t reads rows k1 in {t, 32-t, 8+t, 24-t} (thread 0: {0,16,8,24}), runs four 8-point
 //             FFTs over n2 -> Z[k1 + 32*k2]; both members of every (k, 256-k) pair live in one thread
 //   pairs   : X[k] = E - G, X[256-k] = conj(E + G) with E = Z[k] + conj Z[256-k], G = i*c_k*(Z[k] - conj Z[256-k])
-//             (the 1/2 is folded into the window table), power, max, 10*log10.
+//             (the 1/2 is folded into the window table); sink(k, re, im) receives every bin once.
 #pragma once
 #include "fft_gen.cuh"
 
@@ -19,8 +21,6 @@
 #define ORCAI_DEV_INLINE __host__ __device__ __forceinline__
 #else
 #define ORCAI_DEV_INLINE inline
-struct float2 { float x, y; };
-struct float4 { float x, y, z, w; };
 #endif
 
 namespace orcai {
@@ -28,19 +28,25 @@ namespace orcai {
 constexpr int kNfft = 512;
 constexpr int kHop = 256;
 constexpr int kBins = 257;
-constexpr int kFrameBufFloat2 = 256 + 8;  // 2048 B + 64 B pad: adjacent frames land in opposite bank halves
+constexpr int kFrameBufCx = 256 + 8;  // 32 rows x 8 + one row of padding: adjacent frames land in opposite bank halves
 constexpr float kAminPower = 1e-10f;
 constexpr float kTenLog10Of2 = 3.01029995663981195f;  // 10*log10(2)
 
-// tables, all float2:  win[256] (Hann pairs * scale), tw[256] (W256^(n2*k1) at k1*8+n2), ck[256] (e^{-2 pi i k/512})
+template <typename T>
+struct alignas(2 * sizeof(T)) Cx {
+  T x, y;
+};
+
+// tables:  win[256] (Hann pairs * scale), tw[256] (W256^(n2*k1) at k1*8+n2), ck[256] (e^{-2 pi i k/512})
+template <typename T>
 struct StftTables {
-  const float2* win;
-  const float2* tw;
-  const float2* ck;
+  const Cx<T>* win;
+  const Cx<T>* tw;
+  const Cx<T>* ck;
 };
 
 ORCAI_DEV_INLINE int swz_elem(int k1, int n2) {
-  // element slot (0..7) of (row k1, column n2) inside the 64-byte row
+  // element slot (0..7) of (row k1, column n2) inside the row
   return ((((n2 >> 1) ^ ((k1 >> 1) & 3)) << 1) | (n2 & 1));
 }
 
@@ -54,64 +60,77 @@ ORCAI_DEV_INLINE int stageb_row(int t, int s) {
   }
 }
 
-// Stage A.  x[p] holds the raw sample pair for n1 = BITREV32[p] (already fetched by the caller).
-ORCAI_DEV_INLINE void stage_a(const float2 (&x)[32], int t, const StftTables& tb, float2* fbuf) {
+// Stage A.  x[p] holds the raw float32 sample pair for n1 = BITREV32[p] (already fetched by the caller).
+template <typename T>
+ORCAI_DEV_INLINE void stage_a(const Cx<float> (&x)[32], int t, const StftTables<T>& tb, Cx<T>* fbuf) {
   constexpr int BR[32] = {ORCAI_BITREV32_LIST};
-  float zr[32], zi[32];
+  T zr[32], zi[32];
 #pragma unroll
   for (int p = 0; p < 32; ++p) {
-    const float2 w = tb.win[8 * BR[p] + t];
-    zr[p] = x[p].x * w.x;
-    zi[p] = x[p].y * w.y;
+    const Cx<T> w = tb.win[8 * BR[p] + t];
+    zr[p] = T(x[p].x) * w.x;
+    zi[p] = T(x[p].y) * w.y;
   }
-  orcai_fft32_dit(zr, zi);
+  orcai_fft32_dit<T>(zr, zi);
 #pragma unroll
   for (int k1 = 0; k1 < 32; ++k1) {
-    const float2 w = tb.tw[8 * k1 + t];
-    float2 v;
+    const Cx<T> w = tb.tw[8 * k1 + t];
+    Cx<T> v;
     v.x = zr[k1] * w.x - zi[k1] * w.y;
     v.y = zr[k1] * w.y + zi[k1] * w.x;
     fbuf[8 * k1 + swz_elem(k1, t)] = v;
   }
 }
 
-// Stage B + pair post-processing.  Calls sink(k, power) for every bin k in 0..256 owned by thread t.
-template <class Sink>
-ORCAI_DEV_INLINE void stage_b(int t, const StftTables& tb, const float2* fbuf, Sink&& sink) {
+// Stage B + pair post-processing.  Calls sink(k, re, im) with X[k] (or its conjugate) for every bin k in 0..256.
+template <typename T, class Sink>
+ORCAI_DEV_INLINE void stage_b(int t, const StftTables<T>& tb, const Cx<T>* fbuf, Sink&& sink) {
   constexpr int BR8[8] = {ORCAI_BITREV8_LIST};
-  float fr[4][8], fi[4][8];
+  T fr[4][8], fi[4][8];
 #pragma unroll
   for (int s = 0; s < 4; ++s) {
     const int k1 = stageb_row(t, s);
-    const float4* row = reinterpret_cast<const float4*>(fbuf + 8 * k1);
+    const Cx<T>* row = fbuf + 8 * k1;
     const int x = (k1 >> 1) & 3;
-    float4 c[4];
+    Cx<T> c[8];
+    if constexpr (sizeof(T) == 4) {
+      // one 16-byte load per 2-element chunk (rows are 64-byte aligned)
+      struct alignas(16) Quad { T a, b, c, d; };
+      const Quad* row4 = reinterpret_cast<const Quad*>(row);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) c[q] = row[q ^ x];  // logical chunk q = columns n2 = 2q, 2q+1
+      for (int q = 0; q < 4; ++q) {
+        const Quad v = row4[q ^ x];
+        c[2 * q].x = v.a; c[2 * q].y = v.b; c[2 * q + 1].x = v.c; c[2 * q + 1].y = v.d;
+      }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {  // logical chunk q = columns n2 = 2q, 2q+1 lives in physical chunk q ^ x
+        c[2 * q] = row[2 * (q ^ x)];
+        c[2 * q + 1] = row[2 * (q ^ x) + 1];
+      }
+    }
 #pragma unroll
     for (int p = 0; p < 8; ++p) {
-      const int n2 = BR8[p];
-      const float4 v = c[n2 >> 1];
-      fr[s][p] = (n2 & 1) ? v.z : v.x;
-      fi[s][p] = (n2 & 1) ? v.w : v.y;
+      fr[s][p] = c[BR8[p]].x;
+      fi[s][p] = c[BR8[p]].y;
     }
-    orcai_fft8_dit(fr[s], fi[s]);
+    orcai_fft8_dit<T>(fr[s], fi[s]);
   }
   const bool t0 = (t == 0);
   // slots 0..7 : rows s=0/1 ; slots 8..15 : rows s=2/3
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
-    float ar, ai, br, bi;
+    T ar, ai, br, bi;
     int k;
     if (i < 8) {
       // thread 0 pairs inside rows 0 and 16, the others pair row t with row 32-t
       constexpr int K0[8] = {0, 32, 64, 96, 16, 48, 80, 112};
-      const int ia0 = (i < 4) ? i : i - 4;            // thread-0 source of a
-      const int ib0 = (i == 0) ? 0 : (i < 4 ? 8 - i : 11 - i);  // thread-0 source of b
-      const float a0r = (i < 4) ? fr[0][ia0] : fr[1][ia0];
-      const float a0i = (i < 4) ? fi[0][ia0] : fi[1][ia0];
-      const float b0r = (i < 4) ? fr[0][ib0] : fr[1][ib0];
-      const float b0i = (i < 4) ? fi[0][ib0] : fi[1][ib0];
+      const int ia0 = (i < 4) ? i : i - 4;                         // thread-0 source of a
+      const int ib0 = (i == 0) ? 0 : (i < 4 ? 8 - i : 11 - i);     // thread-0 source of b
+      const T a0r = (i < 4) ? fr[0][ia0] : fr[1][ia0];
+      const T a0i = (i < 4) ? fi[0][ia0] : fi[1][ia0];
+      const T b0r = (i < 4) ? fr[0][ib0] : fr[1][ib0];
+      const T b0i = (i < 4) ? fi[0][ib0] : fi[1][ib0];
       ar = t0 ? a0r : fr[0][i];
       ai = t0 ? a0i : fi[0][i];
       br = t0 ? b0r : fr[1][7 - i];
@@ -125,21 +144,18 @@ ORCAI_DEV_INLINE void stage_b(int t, const StftTables& tb, const float2* fbuf, S
       bi = fi[3][7 - j];
       k = 8 + t + 32 * j;
     }
-    const float2 c = tb.ck[k];
-    const float er = ar + br, ei = ai - bi;   // E = a + conj(b)
-    const float dr = ar - br, di = ai + bi;   // D = a - conj(b)
+    const Cx<T> c = tb.ck[k];
+    const T er = ar + br, ei = ai - bi;   // E = a + conj(b)
+    const T dr = ar - br, di = ai + bi;   // D = a - conj(b)
     // G = i * c * D
-    const float gr = -(c.x * di + c.y * dr);
-    const float gi = c.x * dr - c.y * di;
-    const float x1r = er - gr, x1i = ei - gi;  // X[k]
-    const float x2r = er + gr, x2i = ei + gi;  // conj(X[256-k])
-    sink(k, x1r * x1r + x1i * x1i);
-    sink(256 - k, x2r * x2r + x2i * x2i);
+    const T gr = -(c.x * di + c.y * dr);
+    const T gi = c.x * dr - c.y * di;
+    sink(k, er - gr, ei - gi);            // X[k]
+    sink(256 - k, er + gr, ei + gi);      // conj(X[256-k])
   }
   if (t0) {
     // k = 128: X[128] = conj(Z[128]); Z is carried at half scale
-    const float zr = fr[0][4], zi = fi[0][4];
-    sink(128, 4.0f * (zr * zr + zi * zi));
+    sink(128, T(2) * fr[0][4], T(2) * fi[0][4]);
   }
 }
 
