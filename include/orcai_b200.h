@@ -138,8 +138,14 @@ int orcai_predict_pcm(orcai_ctx* ctx, const void* pcm_host, int32_t dtype, int64
                       int64_t seg_capacity, int64_t* n_segments);
 
 /* ---- knobs ---------------------------------------------------------------------------------- */
-/* Network path: 0 = fp32 CUDA-core reference path, 1 = bf16 tensor-core path (when built). */
+/* Options: "net_path"  0 = fp32 CUDA-core path, 1 = fp16 tcgen05 path, 2 = bf16 tcgen05 path (fp32 accumulate);
+ *          "stft_f64"  1 = float64 FFT (parity grade, default), 0 = float32 FFT (fast);
+ *          "chunk"     snippets per network launch sequence;
+ *          "debug_stop" stop the forward after a stage (see orcai_debug_read), -1 = off. */
 int orcai_set_option(orcai_ctx* ctx, const char* key, int64_t value);
+/* Test hook: after a forward run with "debug_stop" >= 0, copy that stage's activations of the first chunk to
+ * the host as compact float32 NHWC; dims_out receives (n, h, w, c).  Returns ORCAI_ERR_CAPACITY if too small. */
+int orcai_debug_read(orcai_ctx* ctx, float* out_host, int64_t capacity, int64_t* dims_out);
 
 #ifdef __cplusplus
 }

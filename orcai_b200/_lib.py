@@ -107,6 +107,7 @@ _SIGNATURES = {
     "orcai_predict_resident": (C.c_int, [_P, C.c_double, C.POINTER(SpecStats), _P, _P, _P, _P, _P, C.c_int64, C.POINTER(C.c_int64)]),
     "orcai_predict_pcm": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_double, C.POINTER(SpecStats), _P, _P, _P, _P, _P, C.c_int64, C.POINTER(C.c_int64)]),
     "orcai_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),
+    "orcai_debug_read": (C.c_int, [_P, _P, C.c_int64, C.POINTER(C.c_int64)]),
 }
 
 _lib = None
@@ -208,6 +209,22 @@ class Context:
 
     def set_option(self, key: str, value: int):
         self._check(self.lib.orcai_set_option(self._h, key.encode(), int(value)))
+
+    def debug_stage(self, snippets: np.ndarray, stage: int) -> np.ndarray:
+        """Test hook: run the forward up to `stage` and return that stage's activations (n, h, w, c) float32."""
+        x = np.ascontiguousarray(snippets, dtype=np.float32)
+        self.set_option("debug_stop", stage)
+        try:
+            dummy = np.empty((x.shape[0], self.pred_len, self.params.n_labels), dtype=np.float32)
+            self._check(self.lib.orcai_forward_host(self._h, _ptr(x), x.shape[0], _ptr(dummy)))
+            cap = x.shape[0] * x.shape[1] * x.shape[2] * 64
+            out = np.empty(cap, dtype=np.float32)
+            dims = (C.c_int64 * 4)()
+            self._check(self.lib.orcai_debug_read(self._h, _ptr(out), cap, dims))
+            n, h, w, c = (int(v) for v in dims)
+            return out[: n * h * w * c].reshape(n, h, w, c).copy()
+        finally:
+            self.set_option("debug_stop", -1)
 
     # -- weights -------------------------------------------------------------------------------
     def load_weights(self, W: dict):

@@ -196,8 +196,19 @@ int orcai_get_timings(const orcai_ctx* c, orcai_timings* out) {
 int orcai_set_option(orcai_ctx* c, const char* key, int64_t value) {
   if (!c || !key) return ORCAI_ERR_ARG;
   if (!strcmp(key, "chunk")) return net_set_chunk(c, (int)value);
+  if (!strcmp(key, "net_path")) {
+    if (value < 0 || value > 2) ORCAI_FAIL(c, ORCAI_ERR_ARG, "net_path must be 0 (fp32), 1 (fp16 tensor cores) or 2 (bf16 tensor cores)");
+    return net_set_path(c, (int)value);
+  }
+  if (!strcmp(key, "debug_stop")) return net_set_debug_stop(c, (int)value);
   if (!strcmp(key, "stft_f64")) { c->stft_f64 = value ? 1 : 0; c->have_stats = false; return ORCAI_OK; }
   ORCAI_FAIL(c, ORCAI_ERR_ARG, "unknown option '%s'", key);
+}
+
+int orcai_debug_read(orcai_ctx* c, float* out_host, int64_t capacity, int64_t* dims_out) {
+  if (!c || !out_host || !dims_out) return ORCAI_ERR_ARG;
+  ORCAI_CUDA(c, cudaSetDevice(c->device));
+  return net_debug_read(c, out_host, capacity, dims_out);
 }
 
 int orcai_load_weights(orcai_ctx* c, const char* const* names, const float* const* data, const int64_t* sizes, int32_t n) {

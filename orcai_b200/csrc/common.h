@@ -104,6 +104,9 @@ int net_create(Ctx* c);
 void net_destroy(Ctx* c);
 int net_set_chunk(Ctx* c, int chunk);
 void net_collect_stage_times(Ctx* c);
+int net_set_path(Ctx* c, int path);
+int net_set_debug_stop(Ctx* c, int stage);
+int net_debug_read(Ctx* c, float* out_host, int64_t capacity, int64_t* dims_out);
 int net_load_weights(Ctx* c, const char* const* names, const float* const* data, const int64_t* sizes, int n);
 // input_mode 0: raw dB buffer (pitch kRawLd, normalise on load with c->d_sel stats), snippet i starts at row
 //               (first + i) * shift ; input_mode 1: normalised compact snippets (pitch n_freq), snippet stride = snippet_len rows

@@ -19,35 +19,9 @@
 #include <string>
 
 #include "common.h"
+#include "net.h"
 
 namespace orcai {
-
-struct NetWeights {
-  bool loaded = false;
-  int n_blocks = 0;
-  int filters[kMaxBlocks] = {};
-  int Wf = 0, H = 0, U = 0, L = 0, feat = 0;
-  // device weights (fp32)
-  float* conv0_w = nullptr;  // [9][16]
-  float* conv0_b = nullptr;  // [16]
-  struct Sep { float* dw = nullptr; float* pw = nullptr; float* b = nullptr; int ci = 0, co = 0; };
-  Sep sep1[kMaxBlocks], sep2[kMaxBlocks], fin;
-  float* res_w[kMaxBlocks] = {};  // [ci][co]
-  float* res_b[kMaxBlocks] = {};
-  float* lstm_wih[2] = {};  // [I][2*4U]  (forward gates | backward gates)
-  float* lstm_bih[2] = {};  // [2*4U]
-  float* lstm_whh[2] = {};  // [2][U][4U]
-  float* d1_w = nullptr; float* d1_b = nullptr;   // [2U][128], [128]
-  float* d2_w = nullptr; float* d2_b = nullptr;   // [128][L] with bn_dense folded, [L]
-  std::vector<void*> allocs;
-  // activation workspace
-  float* ws = nullptr; size_t ws_cap = 0;
-  int chunk = 128;
-  // per-stage CUDA events of the first chunk of the last forward (profiling aid, see orcai_timings.net_stage_ms)
-  static constexpr int kNumMarks = 14;
-  cudaEvent_t ev[kNumMarks] = {};
-  long long marked_snippets = 0;
-};
 
 namespace {
 
@@ -411,7 +385,9 @@ size_t per_snippet_floats(const NetWeights* nw) {
   return 2 * prev_max + 2 * t_max;
 }
 
-int upload(Ctx* c, const std::vector<float>& v, float** dptr) {
+}  // namespace
+
+int net_upload(Ctx* c, const std::vector<float>& v, float** dptr) {
   void* p = nullptr;
   ORCAI_CUDA(c, cudaMalloc(&p, v.size() * sizeof(float)));
   c->net->allocs.push_back(p);
@@ -419,6 +395,10 @@ int upload(Ctx* c, const std::vector<float>& v, float** dptr) {
   *dptr = static_cast<float*>(p);
   return ORCAI_OK;
 }
+
+namespace {
+
+int upload(Ctx* c, const std::vector<float>& v, float** dptr) { return net_upload(c, v, dptr); }
 
 struct HostTensors {
   std::map<std::string, std::pair<const float*, int64_t>> m;
@@ -450,7 +430,8 @@ bool bn_fold(HostTensors& ht, const std::string& prefix, int C, std::vector<doub
   return true;
 }
 
-int load_sep(Ctx* c, HostTensors& ht, const std::string& sp, const std::string& bnp, int ci, int co, NetWeights::Sep* out) {
+int load_sep(Ctx* c, HostTensors& ht, const std::string& sp, const std::string& bnp, int ci, int co, NetWeights::Sep* out,
+             NetWeights::HostSep* keep) {
   const float* dw = ht.get(sp + "/depthwise_kernel", 9LL * ci);
   const float* pw = ht.get(sp + "/pointwise_kernel", (int64_t)ci * co);
   const float* b = ht.get(sp + "/bias", co);
@@ -462,6 +443,7 @@ int load_sep(Ctx* c, HostTensors& ht, const std::string& sp, const std::string& 
     for (int o = 0; o < co; ++o) pwv[(size_t)i * co + o] = (float)((double)pw[(size_t)i * co + o] * s[o]);
   for (int o = 0; o < co; ++o) bv[o] = (float)((double)b[o] * s[o] + t[o]);
   out->ci = ci; out->co = co;
+  keep->dw = dwv; keep->pw = pwv; keep->b = bv; keep->ci = ci; keep->co = co;
   ORCAI_CHECK(upload(c, dwv, &out->dw));
   ORCAI_CHECK(upload(c, pwv, &out->pw));
   ORCAI_CHECK(upload(c, bv, &out->b));
@@ -497,6 +479,50 @@ void net_destroy(Ctx* c) {
   c->net = nullptr;
 }
 
+int net_set_path(Ctx* c, int path) {
+  c->net->path = path;
+  return ORCAI_OK;
+}
+
+int net_set_debug_stop(Ctx* c, int stage) {
+  c->net->debug_stop = stage;
+  return ORCAI_OK;
+}
+
+int net_debug_read(Ctx* c, float* out_host, int64_t capacity, int64_t* dims_out) {
+  NetWeights* nw = c->net;
+  if (!nw->dbg_ptr) ORCAI_FAIL(c, ORCAI_ERR_STATE, "no debug buffer recorded (set debug_stop, then run a forward)");
+  ORCAI_CUDA(c, cudaStreamSynchronize(c->stream));
+  const long long npix = nw->dbg_n * nw->dbg_h * nw->dbg_w;
+  dims_out[0] = nw->dbg_n; dims_out[1] = nw->dbg_h; dims_out[2] = nw->dbg_w; dims_out[3] = nw->dbg_c;
+  if (npix * nw->dbg_c > capacity) ORCAI_FAIL(c, ORCAI_ERR_CAPACITY, "debug buffer needs %lld floats", npix * nw->dbg_c);
+  const size_t esz = nw->dbg_kind == 0 ? 4 : 2;
+  std::vector<unsigned char> raw((size_t)npix * nw->dbg_pitch * esz);
+  ORCAI_CUDA(c, cudaMemcpy(raw.data(), nw->dbg_ptr, raw.size(), cudaMemcpyDeviceToHost));
+  for (long long p = 0; p < npix; ++p)
+    for (int ch = 0; ch < nw->dbg_c; ++ch) {
+      const size_t i = (size_t)p * nw->dbg_pitch + ch;
+      float v;
+      if (nw->dbg_kind == 0) {
+        v = reinterpret_cast<const float*>(raw.data())[i];
+      } else {
+        const unsigned short u = reinterpret_cast<const unsigned short*>(raw.data())[i];
+        if (nw->dbg_kind == 2) {  // bf16
+          const unsigned int w = (unsigned int)u << 16;
+          memcpy(&v, &w, 4);
+        } else {                  // fp16
+          const unsigned int sign = (u >> 15) & 1u, ex = (u >> 10) & 0x1fu, man = u & 0x3ffu;
+          if (ex == 0) v = std::ldexp((float)man, -24);
+          else if (ex == 31) v = man ? NAN : INFINITY;
+          else v = std::ldexp((float)(man | 0x400u), (int)ex - 25);
+          if (sign) v = -v;
+        }
+      }
+      out_host[(size_t)p * nw->dbg_c + ch] = v;
+    }
+  return ORCAI_OK;
+}
+
 int net_set_chunk(Ctx* c, int chunk) {
   if (chunk < 1) ORCAI_FAIL(c, ORCAI_ERR_ARG, "chunk must be >= 1");
   c->net->chunk = chunk;
@@ -508,6 +534,7 @@ int net_load_weights(Ctx* c, const char* const* names, const float* const* data,
   for (void* p : nw->allocs) cudaFree(p);
   nw->allocs.clear();
   nw->loaded = false;
+  nw->tc_ready[0] = nw->tc_ready[1] = false;
   const orcai_params& P = c->p;
   if (P.n_blocks != 4 || P.filters[0] != 30 || P.filters[1] != 40 || P.filters[2] != 50 || P.filters[3] != 60 ||
       P.kernel_size != 3 || P.lstm_units != 128)
@@ -529,6 +556,7 @@ int net_load_weights(Ctx* c, const char* const* names, const float* const* data,
     for (int tap = 0; tap < 9; ++tap)
       for (int o = 0; o < kEntry; ++o) kv[tap * kEntry + o] = (float)((double)k[tap * kEntry + o] * s[o]);
     for (int o = 0; o < kEntry; ++o) bv[o] = (float)((double)b[o] * s[o] + t[o]);
+    nw->h_conv0_w = kv; nw->h_conv0_b = bv;
     ORCAI_CHECK(upload(c, kv, &nw->conv0_w));
     ORCAI_CHECK(upload(c, bv, &nw->conv0_b));
   }
@@ -536,8 +564,8 @@ int net_load_weights(Ctx* c, const char* const* names, const float* const* data,
   for (int b = 0; b < nw->n_blocks; ++b) {
     const int co = nw->filters[b];
     const std::string p = "block" + std::to_string(b + 1);
-    ORCAI_CHECK(load_sep(c, ht, p + "/sep1", p + "/bn1", ci, co, &nw->sep1[b]));
-    ORCAI_CHECK(load_sep(c, ht, p + "/sep2", p + "/bn2", co, co, &nw->sep2[b]));
+    ORCAI_CHECK(load_sep(c, ht, p + "/sep1", p + "/bn1", ci, co, &nw->sep1[b], &nw->h_sep1[b]));
+    ORCAI_CHECK(load_sep(c, ht, p + "/sep2", p + "/bn2", co, co, &nw->sep2[b], &nw->h_sep2[b]));
     const float* rk = ht.get(p + "/res/kernel", (int64_t)ci * co);
     const float* rb = ht.get(p + "/res/bias", co);
     if (!rk || !rb) return ORCAI_ERR_ARG;
@@ -546,7 +574,7 @@ int net_load_weights(Ctx* c, const char* const* names, const float* const* data,
     ci = co;
     w = (w + 1) / 2;
   }
-  ORCAI_CHECK(load_sep(c, ht, "final/sep", "final/bn", ci, kFinal, &nw->fin));
+  ORCAI_CHECK(load_sep(c, ht, "final/sep", "final/bn", ci, kFinal, &nw->fin, &nw->h_fin));
   nw->feat = w * kFinal;
   const int U = nw->U, G = 4 * U;
   for (int l = 0; l < 2; ++l) {
@@ -592,10 +620,45 @@ int net_load_weights(Ctx* c, const char* const* names, const float* const* data,
   return ORCAI_OK;
 }
 
+// LSTM x2 + dense head on fp32 features; shared by both network paths
+int net_tail_fp32(Ctx* c, const float* feat, float* scratch, long long m, float* d_preds_out, bool mk) {
+  NetWeights* nw = c->net;
+  const int U = nw->U, G = 4 * U, L = nw->L;
+  const int Tn = nw->H >> nw->n_blocks;
+  const long long rows = m * Tn;
+  float* xz = scratch;                          // (rows, 2G)
+  float* h1 = xz + (size_t)rows * 2 * G;        // (rows, 2U)
+  float* h2 = h1 + (size_t)rows * 2 * U;        // (rows, 2U)
+  float* d1 = h2 + (size_t)rows * 2 * U;        // (rows, 128)
+  auto mark = [&](bool on) { net_mark(c, on); };
+  ORCAI_CHECK((run_gemm<0>(c, feat, nw->lstm_wih[0], nw->lstm_bih[0], xz, rows, 2 * G, nw->feat)));
+  mark(mk);  // 6: lstm1 input projection
+  {
+    dim3 grid((unsigned)((m + kSN - 1) / kSN), 2);
+    lstm_rec_kernel<128><<<grid, 512, 0, c->stream>>>(xz, nw->lstm_whh[0], h1, m, Tn);
+    c->launches++;
+  }
+  mark(mk);  // 7: lstm1 recurrence
+  ORCAI_CHECK((run_gemm<0>(c, h1, nw->lstm_wih[1], nw->lstm_bih[1], xz, rows, 2 * G, 2 * U)));
+  mark(mk);  // 8: lstm2 input projection
+  {
+    dim3 grid((unsigned)((m + kSN - 1) / kSN), 2);
+    lstm_rec_kernel<128><<<grid, 512, 0, c->stream>>>(xz, nw->lstm_whh[1], h2, m, Tn);
+    c->launches++;
+  }
+  mark(mk);  // 9: lstm2 recurrence
+  ORCAI_CHECK((run_gemm<1>(c, h2, nw->d1_w, nw->d1_b, d1, rows, kDense, 2 * U)));
+  ORCAI_CHECK((run_gemm<2>(c, d1, nw->d2_w, nw->d2_b, d_preds_out, rows, L, kDense)));
+  mark(mk);  // 10: dense head
+  ORCAI_CUDA(c, cudaGetLastError());
+  return ORCAI_OK;
+}
+
 int net_forward(Ctx* c, const float* d_in, int input_mode, int64_t first, int64_t n, float* d_preds) {
   NetWeights* nw = c->net;
   if (!nw || !nw->loaded) ORCAI_FAIL(c, ORCAI_ERR_STATE, "no weights loaded (orcai_load_weights)");
-  const int H = nw->H, Wf = nw->Wf, U = nw->U, G = 4 * U, L = nw->L;
+  if (nw->path != 0) return net_forward_tc(c, d_in, input_mode, first, n, d_preds);
+  const int H = nw->H, Wf = nw->Wf, L = nw->L;
   const int Tn = H >> nw->n_blocks;
   const size_t per = per_snippet_floats(nw);
   const long long chunk = std::min<long long>(nw->chunk, n);
@@ -621,8 +684,8 @@ int net_forward(Ctx* c, const float* d_in, int input_mode, int64_t first, int64_
   float* tB = tA + t_max * chunk;
   const int shift = c->p.snippet_len / 2;
 
-  int mark_i = 0;
-  auto mark = [&](bool on) { if (on && mark_i < NetWeights::kNumMarks) cudaEventRecord(nw->ev[mark_i++], c->stream); };
+  nw->mark_i = 0;
+  auto mark = [&](bool on) { net_mark(c, on); };
   for (int64_t s0 = 0; s0 < n; s0 += chunk) {
     const long long m = std::min<long long>(chunk, n - s0);
     const bool mk = (s0 == 0);
@@ -653,30 +716,7 @@ int net_forward(Ctx* c, const float* d_in, int input_mode, int64_t first, int64_
     float* feat = pB;
     ORCAI_CHECK((run_sepconv<60, 36, false, true>(c, pA, feat, m, h, w, nw->fin)));
     mark(mk);  // 5: final sepconv
-    const long long rows = m * Tn;
-    float* xz = tA;                       // (rows, 2G)
-    float* h1 = tB;                       // (rows, 2U)
-    float* h2 = pA;                       // (rows, 2U)
-    float* d1 = tB + (size_t)rows * 2 * U;  // (rows, 128)
-    ORCAI_CHECK((run_gemm<0>(c, feat, nw->lstm_wih[0], nw->lstm_bih[0], xz, rows, 2 * G, nw->feat)));
-    mark(mk);  // 6: lstm1 input projection
-    {
-      dim3 grid((unsigned)((m + kSN - 1) / kSN), 2);
-      lstm_rec_kernel<128><<<grid, 512, 0, c->stream>>>(xz, nw->lstm_whh[0], h1, m, Tn);
-      c->launches++;
-    }
-    mark(mk);  // 7: lstm1 recurrence
-    ORCAI_CHECK((run_gemm<0>(c, h1, nw->lstm_wih[1], nw->lstm_bih[1], xz, rows, 2 * G, 2 * U)));
-    mark(mk);  // 8: lstm2 input projection
-    {
-      dim3 grid((unsigned)((m + kSN - 1) / kSN), 2);
-      lstm_rec_kernel<128><<<grid, 512, 0, c->stream>>>(xz, nw->lstm_whh[1], h2, m, Tn);
-      c->launches++;
-    }
-    mark(mk);  // 9: lstm2 recurrence
-    ORCAI_CHECK((run_gemm<1>(c, h2, nw->d1_w, nw->d1_b, d1, rows, kDense, 2 * U)));
-    ORCAI_CHECK((run_gemm<2>(c, d1, nw->d2_w, nw->d2_b, d_preds + (size_t)s0 * Tn * L, rows, L, kDense)));
-    mark(mk);  // 10: dense head
+    ORCAI_CHECK(net_tail_fp32(c, feat, tA, m, d_preds + (size_t)s0 * Tn * L, mk));
     ORCAI_CUDA(c, cudaGetLastError());
   }
   return ORCAI_OK;

@@ -1,0 +1,67 @@
+// orcai-V1 network state shared by the fp32 path (net.cu) and the tensor-core path (net_tc.cu).
+#pragma once
+#include <vector>
+
+#include "common.h"
+
+namespace orcai {
+
+struct TcSep {            // one fused 3x3 implicit-GEMM layer of the tensor-core path
+  void* w = nullptr;      // 9 taps x [NP x KP] 16-bit, canonical K-major no-swizzle UMMA layout
+  float* bias = nullptr;  // NP floats (folded BatchNorm), zero padded
+};
+
+struct NetWeights {
+  bool loaded = false;
+  int n_blocks = 0;
+  int filters[kMaxBlocks] = {};
+  int Wf = 0, H = 0, U = 0, L = 0, feat = 0;
+  // device weights (fp32)
+  float* conv0_w = nullptr;  // [9][16]
+  float* conv0_b = nullptr;  // [16]
+  struct Sep { float* dw = nullptr; float* pw = nullptr; float* b = nullptr; int ci = 0, co = 0; };
+  Sep sep1[kMaxBlocks], sep2[kMaxBlocks], fin;
+  float* res_w[kMaxBlocks] = {};  // [ci][co]
+  float* res_b[kMaxBlocks] = {};
+  float* lstm_wih[2] = {};  // [I][2*4U]  (forward gates | backward gates)
+  float* lstm_bih[2] = {};  // [2*4U]
+  float* lstm_whh[2] = {};  // [2][U][4U]
+  float* d1_w = nullptr; float* d1_b = nullptr;   // [2U][128], [128]
+  float* d2_w = nullptr; float* d2_b = nullptr;   // [128][L] with bn_dense folded, [L]
+  std::vector<void*> allocs;
+  // activation workspace
+  float* ws = nullptr; size_t ws_cap = 0;
+  int chunk = 128;
+  // per-stage CUDA events of the first chunk of the last forward (profiling aid, see orcai_timings.net_stage_ms)
+  static constexpr int kNumMarks = 14;
+  cudaEvent_t ev[kNumMarks] = {};
+  int mark_i = 0;
+  long long marked_snippets = 0;
+
+  // ---- tensor-core path (net_tc.cu): operands per 16-bit format (0 = fp16, 1 = bf16) ----
+  bool tc_ready[2] = {false, false};
+  void* tc_conv0_w[2] = {};   // [16 x 16] canonical
+  TcSep tc_sep1[2][kMaxBlocks], tc_sep2[2][kMaxBlocks], tc_fin[2];
+  void* tc_ws = nullptr; size_t tc_ws_cap = 0;
+  int path = 0;               // 0 = fp32 CUDA cores, 1 = fp16 tensor cores, 2 = bf16 tensor cores
+  int debug_stop = -1;        // stop the forward after this stage (debug reads), -1 = run everything
+  // last debug buffer: kind 0 f32, 1 fp16, 2 bf16 ; NHWC with channel pitch dbg_pitch
+  const void* dbg_ptr = nullptr; int dbg_kind = 0; long long dbg_n = 0; int dbg_h = 0, dbg_w = 0, dbg_c = 0, dbg_pitch = 0;
+  // folded fp32 weights kept on the host for building the tensor-core operands
+  std::vector<float> h_conv0_w, h_conv0_b;
+  struct HostSep { std::vector<float> dw, pw, b; int ci = 0, co = 0; };
+  HostSep h_sep1[kMaxBlocks], h_sep2[kMaxBlocks], h_fin;
+};
+
+inline void net_mark(Ctx* c, bool on) {
+  NetWeights* nw = c->net;
+  if (on && nw->mark_i < NetWeights::kNumMarks) cudaEventRecord(nw->ev[nw->mark_i++], c->stream);
+}
+
+// LSTM + dense tail on fp32 features (m, Tn, feat).  scratch: m*Tn*(2*4U + 2U + 2U + 128) floats.
+int net_tail_fp32(Ctx* c, const float* feat, float* scratch, long long m, float* d_preds_out, bool mark);
+int net_upload(Ctx* c, const std::vector<float>& v, float** dptr);
+int net_tc_prepare(Ctx* c, int fmt);
+int net_forward_tc(Ctx* c, const float* d_in, int input_mode, int64_t first, int64_t n, float* d_preds);
+
+}  // namespace orcai

@@ -1,0 +1,482 @@
+// orcai-V1 convolutional trunk on the 5th-generation tensor cores (tcgen05 + TMEM), 16-bit activations.
+//
+// Same graph as net.cu (reference src/orcAI/architectures.py:120-241, called from predict.py:266-268).
+// Every separable convolution  [ReLU] -> depthwise 3x3 -> pointwise 1x1 (+ folded BatchNorm) -> [ReLU]
+// is executed as ONE implicit GEMM per 16x8-pixel tile:
+//
+//     D[128 pixels, Cout] = sum over taps (dy,dx)  A_tap[128, Cin] * W'_tap[Cin, Cout],
+//     W'_tap[ci][co] = dw[tap][ci] * pw[ci][co] * bn_scale[co]
+//
+// The depthwise filter is folded into the GEMM weights, so no CUDA-core convolution remains.  The (18x10)-pixel
+// halo tile of the input is copied ONCE into shared memory as [k-chunk of 8 channels][halo pixel][16 bytes];
+// in that layout the A operand of every tap is the same buffer seen through a UMMA shared-memory descriptor
+// whose start address is shifted by (dy*10+dx)*16 bytes (8-row core matrices = 8 consecutive pixels of a tile
+// row, SBO = one halo row = 160 B, LBO = one k-chunk plane = 2880 B).  No im2col, no data movement per tap.
+// One elected thread issues 9*Kpad/16 tcgen05.mma (M=128, N=Cout padded to 16, K=16) into a TMEM accumulator and
+// commits to an mbarrier; the 4 warps then read their 32 accumulator rows with tcgen05.ld, add the bias, apply
+// ReLU, convert and store NHWC with 16-byte stores.  CTAs are persistent (weights stay in shared memory).
+//
+// Activations between kernels are NHWC 16-bit with the channel pitch padded to a multiple of 8 (padding
+// channels are written as zeros), so every (pixel, k-chunk) is one aligned 16-byte vector.
+#include <algorithm>
+#include <cstring>
+
+#include "common.h"
+#include "net.h"
+#include "tc_common.cuh"
+
+namespace orcai {
+
+namespace {
+
+using namespace tc;
+
+__host__ __device__ constexpr int cpad8(int c) { return (c + 7) & ~7; }
+__host__ __device__ constexpr int cpad16(int c) { return (c + 15) & ~15; }
+constexpr int kTileH = 16, kTileW = 8, kHaloW = kTileW + 2, kHaloH = kTileH + 2, kHalo = kHaloH * kHaloW;  // 180
+constexpr float kTopDbF = 80.0f;
+
+template <typename H> __device__ __forceinline__ uint4 relu8(uint4 v);
+template <> __device__ __forceinline__ uint4 relu8<__half>(uint4 v) {
+  __half2* h = reinterpret_cast<__half2*>(&v);
+  const __half2 z = __float2half2_rn(0.f);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __hmax2(h[i], z);
+  return v;
+}
+template <> __device__ __forceinline__ uint4 relu8<__nv_bfloat16>(uint4 v) {
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+  const __nv_bfloat162 z = __float2bfloat162_rn(0.f);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __hmax2(h[i], z);
+  return v;
+}
+
+template <typename H>
+__device__ __forceinline__ uint4 pack8(const float* v) {
+  uint4 r;
+  H* h = reinterpret_cast<H*>(&r);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) h[i] = half_traits<H>::from_float(v[i]);
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused separable convolution as implicit GEMM on tcgen05
+// ------------------------------------------------------------------------------------------------
+template <int CIN, int COUT>
+struct SepTc {
+  static constexpr int CP = cpad8(CIN);       // channel pitch of the input in global memory
+  static constexpr int KP = cpad16(CIN);      // K per tap seen by the MMA
+  static constexpr int NP = cpad16(COUT);     // N of the MMA
+  static constexpr int NCH = KP / 8, NCH_G = CP / 8;
+  static constexpr uint32_t LBO_A = kHalo * 16, SBO_A = kHaloW * 16;
+  static constexpr uint32_t LBO_B = 128, SBO_B = NCH * 128;
+  static constexpr int TM_COLS = NP <= 32 ? 32 : 64;
+  static constexpr size_t w_bytes = (size_t)9 * NP * KP * 2;
+  static constexpr size_t a_bytes = (size_t)NCH * LBO_A;
+  static constexpr size_t smem = w_bytes + a_bytes + NP * sizeof(float) + 16;
+};
+
+template <int CIN, int COUT, bool RELU_IN, bool RELU_OUT, typename H, bool OUT_F32>
+__global__ void __launch_bounds__(128)
+sep_tc_kernel(const H* __restrict__ in, void* __restrict__ out, int Himg, int Wimg, long long n_snip,
+              const H* __restrict__ wgt, const float* __restrict__ bias, int tiles_w, int tiles_h) {
+  using S = SepTc<CIN, COUT>;
+  constexpr int OCP = OUT_F32 ? COUT : cpad8(COUT);
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* s_w = smem;
+  unsigned char* s_a = smem + S::w_bytes;
+  float* s_bias = reinterpret_cast<float*>(s_a + S::a_bytes);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(s_bias + S::NP);
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(bar + 1);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (int)(S::w_bytes / 16); i += 128) reinterpret_cast<uint4*>(s_w)[i] = __ldg(reinterpret_cast<const uint4*>(wgt) + i);
+  for (int i = tid; i < (int)(S::a_bytes / 16); i += 128) reinterpret_cast<uint4*>(s_a)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < S::NP; i += 128) s_bias[i] = bias[i];
+  if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+  __syncwarp();
+  if (warp == 0) tmem_alloc<S::TM_COLS>(tslot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tslot;
+  const uint32_t a_base = smem_u32(s_a), w_base = smem_u32(s_w);
+  constexpr uint32_t idesc = make_idesc_f16(128, S::NP, half_traits<H>::fmt);
+
+  const long long tiles_per = (long long)tiles_w * tiles_h;
+  const long long total = n_snip * tiles_per;
+  uint32_t phase = 0;
+  const int py = tid >> 3, px = tid & 7;
+  for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    const long long b = tile / tiles_per;
+    const int tr = (int)(tile - b * tiles_per);
+    const int h0 = (tr / tiles_w) * kTileH, w0 = (tr % tiles_w) * kTileW;
+    const H* src = in + (size_t)b * Himg * Wimg * S::CP;
+    // halo tile -> [k-chunk][halo pixel][8 channels]
+    for (int idx = tid; idx < S::NCH_G * kHalo; idx += 128) {
+      const int ch = idx / kHalo, hp = idx - ch * kHalo;
+      const int hh = h0 + hp / kHaloW - 1, ww = w0 + hp % kHaloW - 1;
+      uint4 v = make_uint4(0, 0, 0, 0);
+      if (hh >= 0 && hh < Himg && ww >= 0 && ww < Wimg) {
+        v = __ldg(reinterpret_cast<const uint4*>(src + ((size_t)hh * Wimg + ww) * S::CP + ch * 8));
+        if (RELU_IN) v = relu8<H>(v);
+      }
+      *reinterpret_cast<uint4*>(s_a + (size_t)ch * S::LBO_A + hp * 16) = v;
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        const uint32_t a_tap = a_base + ((tap / 3) * kHaloW + (tap % 3)) * 16;
+        const uint32_t w_tap = w_base + tap * (S::NP * S::KP * 2);
+#pragma unroll
+        for (int ks = 0; ks < S::KP / 16; ++ks) {
+          const uint64_t ad = make_smem_desc(a_tap + 2 * ks * S::LBO_A, S::LBO_A, S::SBO_A);
+          const uint64_t bd = make_smem_desc(w_tap + 2 * ks * S::LBO_B, S::LBO_B, S::SBO_B);
+          mma_f16_ss(tmem, ad, bd, idesc, (tap | ks) != 0);
+        }
+      }
+      mma_commit(bar);
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    // epilogue: accumulator row tid = pixel (py, px)
+    const int hh = h0 + py, ww = w0 + px;
+    const bool inside = hh < Himg && ww < Wimg;
+    const size_t pix = ((size_t)b * Himg + hh) * Wimg + ww;
+#pragma unroll
+    for (int c0 = 0; c0 < S::NP; c0 += 16) {
+      float v[16];
+      tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        v[i] += s_bias[c0 + i];
+        if (RELU_OUT) v[i] = fmaxf(v[i], 0.f);
+      }
+      if (inside) {
+        if (OUT_F32) {
+          float* o = reinterpret_cast<float*>(out) + pix * OCP + c0;
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (c0 + 4 * q + 4 <= OCP) reinterpret_cast<float4*>(o)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        } else {
+          H* o = reinterpret_cast<H*>(out) + pix * OCP + c0;
+          if (c0 + 8 <= OCP) reinterpret_cast<uint4*>(o)[0] = pack8<H>(v);
+          if (c0 + 16 <= OCP) reinterpret_cast<uint4*>(o)[1] = pack8<H>(v + 8);
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+  if (warp == 0) tmem_dealloc<S::TM_COLS>(tmem);
+}
+
+// ------------------------------------------------------------------------------------------------
+// entry convolution (1 -> 16 channels): normalise-on-load, the 9 taps are the K dimension (padded to 16)
+// ------------------------------------------------------------------------------------------------
+template <typename H>
+__global__ void __launch_bounds__(128)
+conv0_tc_kernel(const float* __restrict__ in, int mode, long long first, int shift, int in_ld, int Himg, int Wimg,
+                const SelectState* __restrict__ st, const H* __restrict__ wgt, const float* __restrict__ bias,
+                H* __restrict__ out, long long n_snip, int tiles_w, int tiles_h) {
+  __shared__ __align__(128) unsigned char s_a[128 * 16 * 2];   // A: 128 rows x 16 k, LBO 128, SBO 256
+  __shared__ __align__(128) unsigned char s_w[16 * 16 * 2];    // B: 16 rows x 16 k
+  __shared__ float s_x[kHalo];
+  __shared__ float s_bias[16];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tslot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid < 32) reinterpret_cast<uint4*>(s_w)[tid] = __ldg(reinterpret_cast<const uint4*>(wgt) + tid);
+  if (tid < 16) s_bias[tid] = bias[tid];
+  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  __syncwarp();
+  if (warp == 0) tmem_alloc<32>(&tslot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tslot;
+  float db_ref = 0.f, lo = 0.f, hi = 1.f, range = 1.f;
+  if (mode == 0) { db_ref = st->db_ref; lo = st->lo; hi = st->hi; range = hi - lo; }
+  constexpr uint32_t idesc = make_idesc_f16(128, 16, half_traits<H>::fmt);
+  const long long tiles_per = (long long)tiles_w * tiles_h;
+  const long long total = n_snip * tiles_per;
+  uint32_t phase = 0;
+  const int py = tid >> 3, px = tid & 7;
+  for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
+    const long long b = tile / tiles_per;
+    const int tr = (int)(tile - b * tiles_per);
+    const int h0 = (tr / tiles_w) * kTileH, w0 = (tr % tiles_w) * kTileW;
+    const long long row0 = (mode == 0) ? (first + b) * shift : b * (long long)Himg;
+    for (int hp = tid; hp < kHalo; hp += 128) {
+      const int hh = h0 + hp / kHaloW - 1, ww = w0 + hp % kHaloW - 1;
+      float v = 0.f;
+      if (hh >= 0 && hh < Himg && ww >= 0 && ww < Wimg) {
+        v = in[(size_t)(row0 + hh) * in_ld + ww];
+        if (mode == 0) {
+          v = fmaxf(v - db_ref, -kTopDbF);
+          v = __fdiv_rn(fminf(fmaxf(v, lo), hi) - lo, range);
+        }
+      }
+      s_x[hp] = v;
+    }
+    __syncthreads();
+    {
+      float k[16];
+#pragma unroll
+      for (int t = 0; t < 9; ++t) k[t] = s_x[(py + t / 3) * kHaloW + px + t % 3];
+#pragma unroll
+      for (int t = 9; t < 16; ++t) k[t] = 0.f;
+      unsigned char* row = s_a + (tid >> 3) * 256 + (tid & 7) * 16;
+      *reinterpret_cast<uint4*>(row) = pack8<H>(k);
+      *reinterpret_cast<uint4*>(row + 128) = pack8<H>(k + 8);
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      mma_f16_ss(tmem, make_smem_desc(smem_u32(s_a), 128, 256), make_smem_desc(smem_u32(s_w), 128, 256), idesc, 0);
+      mma_commit(&bar);
+    }
+    mbar_wait(&bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    float v[16];
+    tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16), v);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + s_bias[i], 0.f);
+    const int hh = h0 + py, ww = w0 + px;
+    if (hh < Himg && ww < Wimg) {
+      H* o = out + (((size_t)b * Himg + hh) * Wimg + ww) * 16;
+      reinterpret_cast<uint4*>(o)[0] = pack8<H>(v);
+      reinterpret_cast<uint4*>(o)[1] = pack8<H>(v + 8);
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+  if (warp == 0) tmem_dealloc<32>(tmem);
+}
+
+// ------------------------------------------------------------------------------------------------
+// MaxPool (3,2)/2 "same" + residual Conv1x1/2 + add on 16-bit activations (fp32 math)
+// ------------------------------------------------------------------------------------------------
+template <int CIN, int COUT, typename H>
+__global__ void __launch_bounds__(256)
+pool_res_tc_kernel(const H* __restrict__ t4, const H* __restrict__ prev, H* __restrict__ out, int Himg, int Wimg,
+                   int Ho, int Wo, const float* __restrict__ rw, const float* __restrict__ rb, long long n_snip) {
+  constexpr int ICP = cpad8(CIN), OCP = cpad8(COUT);
+  __shared__ float s_w[CIN * COUT + COUT];
+  for (int i = threadIdx.x; i < CIN * COUT; i += blockDim.x) s_w[i] = rw[i];
+  for (int i = threadIdx.x; i < COUT; i += blockDim.x) s_w[CIN * COUT + i] = rb[i];
+  __syncthreads();
+  const long long total = n_snip * Ho * Wo * OCP;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(idx % OCP);
+    long long r = idx / OCP;
+    const int wo = (int)(r % Wo); r /= Wo;
+    const int ho = (int)(r % Ho);
+    const long long b = r / Ho;
+    float res = 0.f;
+    if (c < COUT) {
+      const H* tb = t4 + (size_t)b * Himg * Wimg * OCP;
+      float m = -INFINITY;
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          const int hh = 2 * ho + dy, ww = 2 * wo + dx;
+          if (hh < Himg && ww < Wimg) m = fmaxf(m, half_traits<H>::to_float(tb[((size_t)hh * Wimg + ww) * OCP + c]));
+        }
+      const H* pv = prev + (((size_t)b * Himg + 2 * ho) * Wimg + 2 * wo) * ICP;
+      float a = s_w[CIN * COUT + c];
+#pragma unroll 4
+      for (int ci = 0; ci < CIN; ++ci) a = fmaf(half_traits<H>::to_float(pv[ci]), s_w[ci * COUT + c], a);
+      res = m + a;
+    }
+    out[idx] = half_traits<H>::from_float(res);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+template <typename H> H host_cvt(float x);
+template <> __half host_cvt<__half>(float x) { return __float2half_rn(x); }
+template <> __nv_bfloat16 host_cvt<__nv_bfloat16>(float x) { return __float2bfloat16_rn(x); }
+
+// canonical K-major no-swizzle B operand: element (n, k) of tap t
+inline size_t b_index(int t, int n, int k, int NP, int KP) {
+  const size_t SBO = (size_t)(KP / 8) * 128;
+  return ((size_t)t * NP * KP * 2 + (size_t)(n / 8) * SBO + (size_t)(k / 8) * 128 + (size_t)(n % 8) * 16 + (size_t)(k % 8) * 2) / 2;
+}
+
+template <typename H>
+int build_sep(Ctx* c, const NetWeights::HostSep& hs, TcSep* out) {
+  const int KP = cpad16(hs.ci), NP = cpad16(hs.co);
+  std::vector<H> w((size_t)9 * NP * KP, host_cvt<H>(0.f));
+  for (int t = 0; t < 9; ++t)
+    for (int k = 0; k < hs.ci; ++k)
+      for (int n = 0; n < hs.co; ++n)
+        w[b_index(t, n, k, NP, KP)] = host_cvt<H>(hs.dw[(size_t)t * hs.ci + k] * hs.pw[(size_t)k * hs.co + n]);
+  std::vector<float> b(NP, 0.f);
+  for (int n = 0; n < hs.co; ++n) b[n] = hs.b[n];
+  void* p = nullptr;
+  ORCAI_CUDA(c, cudaMalloc(&p, w.size() * sizeof(H)));
+  c->net->allocs.push_back(p);
+  ORCAI_CUDA(c, cudaMemcpy(p, w.data(), w.size() * sizeof(H), cudaMemcpyHostToDevice));
+  out->w = p;
+  ORCAI_CHECK(net_upload(c, b, &out->bias));
+  return ORCAI_OK;
+}
+
+template <typename H>
+int prepare(Ctx* c, int fmt) {
+  NetWeights* nw = c->net;
+  {  // conv0: B[n][tap], taps 9..15 zero
+    std::vector<H> w(16 * 16, host_cvt<H>(0.f));
+    for (int t = 0; t < 9; ++t)
+      for (int n = 0; n < 16; ++n) w[b_index(0, n, t, 16, 16)] = host_cvt<H>(nw->h_conv0_w[t * 16 + n]);
+    void* p = nullptr;
+    ORCAI_CUDA(c, cudaMalloc(&p, w.size() * sizeof(H)));
+    nw->allocs.push_back(p);
+    ORCAI_CUDA(c, cudaMemcpy(p, w.data(), w.size() * sizeof(H), cudaMemcpyHostToDevice));
+    nw->tc_conv0_w[fmt] = p;
+  }
+  for (int b = 0; b < nw->n_blocks; ++b) {
+    ORCAI_CHECK(build_sep<H>(c, nw->h_sep1[b], &nw->tc_sep1[fmt][b]));
+    ORCAI_CHECK(build_sep<H>(c, nw->h_sep2[b], &nw->tc_sep2[fmt][b]));
+  }
+  ORCAI_CHECK(build_sep<H>(c, nw->h_fin, &nw->tc_fin[fmt]));
+  nw->tc_ready[fmt] = true;
+  return ORCAI_OK;
+}
+
+template <int CIN, int COUT, bool RI, bool RO, typename H, bool OUT_F32>
+int run_sep(Ctx* c, const H* in, void* out, long long n, int Himg, int Wimg, const TcSep& w) {
+  using S = SepTc<CIN, COUT>;
+  static bool attr = false;
+  if (!attr) {
+    ORCAI_CUDA(c, cudaFuncSetAttribute(sep_tc_kernel<CIN, COUT, RI, RO, H, OUT_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::smem));
+    attr = true;
+  }
+  const int tiles_w = (Wimg + kTileW - 1) / kTileW, tiles_h = (Himg + kTileH - 1) / kTileH;
+  const long long total = n * tiles_w * tiles_h;
+  // persistent CTAs: as many as fit (shared memory / 512 TMEM columns), capped by the tile count
+  int per_sm = (int)std::min<size_t>(8, (size_t)(220 * 1024) / (S::smem + 1024));
+  per_sm = std::max(1, std::min(per_sm, 512 / S::TM_COLS));
+  const long long grid = std::min<long long>(total, (long long)c->sm_count * per_sm);
+  sep_tc_kernel<CIN, COUT, RI, RO, H, OUT_F32><<<(unsigned)grid, 128, S::smem, c->stream>>>(
+      in, out, Himg, Wimg, n, static_cast<const H*>(w.w), w.bias, tiles_w, tiles_h);
+  c->launches++;
+  ORCAI_CUDA(c, cudaGetLastError());
+  return ORCAI_OK;
+}
+
+template <int CIN, int COUT, typename H>
+int run_block(Ctx* c, const H* prev, H* t_a, H* t_b, H* next, long long n, int Himg, int Wimg, int blk, int fmt) {
+  NetWeights* nw = c->net;
+  ORCAI_CHECK((run_sep<CIN, COUT, true, true, H, false>(c, prev, t_a, n, Himg, Wimg, nw->tc_sep1[fmt][blk])));
+  ORCAI_CHECK((run_sep<COUT, COUT, false, false, H, false>(c, t_a, t_b, n, Himg, Wimg, nw->tc_sep2[fmt][blk])));
+  const int Ho = (Himg + 1) / 2, Wo = (Wimg + 1) / 2;
+  const long long total = n * Ho * Wo * cpad8(COUT);
+  const long long grid = std::min<long long>((total + 255) / 256, (long long)c->sm_count * 32);
+  pool_res_tc_kernel<CIN, COUT, H><<<(unsigned)grid, 256, 0, c->stream>>>(t_b, prev, next, Himg, Wimg, Ho, Wo, nw->res_w[blk], nw->res_b[blk], n);
+  c->launches++;
+  ORCAI_CUDA(c, cudaGetLastError());
+  return ORCAI_OK;
+}
+
+inline void set_debug(NetWeights* nw, const void* p, int kind, long long n, int h, int w, int ch, int pitch) {
+  nw->dbg_ptr = p; nw->dbg_kind = kind; nw->dbg_n = n; nw->dbg_h = h; nw->dbg_w = w; nw->dbg_c = ch; nw->dbg_pitch = pitch;
+}
+
+template <typename H>
+int forward_tc(Ctx* c, const float* d_in, int input_mode, int64_t first, int64_t n, float* d_preds, int fmt) {
+  NetWeights* nw = c->net;
+  const int Himg = nw->H, Wf = nw->Wf, U = nw->U, L = nw->L;
+  const int Tn = Himg >> nw->n_blocks;
+  const int kind = fmt + 1;
+  // workspace (16-bit elements): two "prev" buffers, two block temporaries; then the fp32 tail
+  const size_t prev_max = (size_t)Himg * Wf * 16;
+  const size_t t_max = (size_t)Himg * Wf * 32;
+  const size_t tail_f = (size_t)Tn * (nw->feat + 2 * 4 * U + 2 * U + 2 * U + 128);
+  const size_t per = (2 * prev_max + 2 * t_max) * 2 + tail_f * 4 + 256;
+  const long long chunk = std::min<long long>(std::max(nw->chunk, 1), n);
+  if (chunk <= 0) return ORCAI_OK;
+  ORCAI_CHECK(ensure_device_buffer(c, &nw->tc_ws, &nw->tc_ws_cap, per * (size_t)chunk));
+  H* pA = static_cast<H*>(nw->tc_ws);
+  H* pB = pA + prev_max * chunk;
+  H* tA = pB + prev_max * chunk;
+  H* tB = tA + t_max * chunk;
+  float* feat = reinterpret_cast<float*>(tB + t_max * chunk);
+  float* scratch = feat + (size_t)Tn * nw->feat * chunk;
+  const int shift = c->p.snippet_len / 2;
+  nw->mark_i = 0;
+  nw->dbg_ptr = nullptr;
+  const int stop = nw->debug_stop;
+
+  for (int64_t s0 = 0; s0 < n; s0 += chunk) {
+    const long long m = std::min<long long>(chunk, n - s0);
+    const bool mk = (s0 == 0);
+    if (mk) nw->marked_snippets = m;
+    net_mark(c, mk);
+    {
+      const int tiles_w = (Wf + kTileW - 1) / kTileW, tiles_h = (Himg + kTileH - 1) / kTileH;
+      const long long total = m * tiles_w * tiles_h;
+      const long long grid = std::min<long long>(total, (long long)c->sm_count * 8);
+      const float* src = (input_mode == 0) ? d_in : d_in + (size_t)s0 * Himg * Wf;
+      conv0_tc_kernel<H><<<(unsigned)grid, 128, 0, c->stream>>>(src, input_mode, first + s0, shift, input_mode == 0 ? kRawLd : Wf, Himg, Wf,
+                                                                 c->d_sel, static_cast<const H*>(nw->tc_conv0_w[fmt]), nw->conv0_b, pA, m,
+                                                                 tiles_w, tiles_h);
+      c->launches++;
+      ORCAI_CUDA(c, cudaGetLastError());
+    }
+    net_mark(c, mk);  // 0: conv0
+    if (stop == 0) { set_debug(nw, pA, kind, m, Himg, Wf, 16, 16); return ORCAI_OK; }
+    int h = Himg, w = Wf;
+    ORCAI_CHECK((run_block<16, 30, H>(c, pA, tA, tB, pB, m, h, w, 0, fmt)));
+    if (stop == 10) { set_debug(nw, tA, kind, m, h, w, 30, 32); return ORCAI_OK; }
+    if (stop == 11) { set_debug(nw, tB, kind, m, h, w, 30, 32); return ORCAI_OK; }
+    h = (h + 1) / 2; w = (w + 1) / 2;
+    net_mark(c, mk);  // 1: block1
+    if (stop == 1) { set_debug(nw, pB, kind, m, h, w, 30, 32); return ORCAI_OK; }
+    ORCAI_CHECK((run_block<30, 40, H>(c, pB, tA, tB, pA, m, h, w, 1, fmt))); h = (h + 1) / 2; w = (w + 1) / 2;
+    net_mark(c, mk);  // 2: block2
+    if (stop == 2) { set_debug(nw, pA, kind, m, h, w, 40, 40); return ORCAI_OK; }
+    ORCAI_CHECK((run_block<40, 50, H>(c, pA, tA, tB, pB, m, h, w, 2, fmt))); h = (h + 1) / 2; w = (w + 1) / 2;
+    net_mark(c, mk);  // 3: block3
+    if (stop == 3) { set_debug(nw, pB, kind, m, h, w, 50, 56); return ORCAI_OK; }
+    ORCAI_CHECK((run_block<50, 60, H>(c, pB, tA, tB, pA, m, h, w, 3, fmt))); h = (h + 1) / 2; w = (w + 1) / 2;
+    net_mark(c, mk);  // 4: block4
+    if (stop == 4) { set_debug(nw, pA, kind, m, h, w, 60, 64); return ORCAI_OK; }
+    ORCAI_CHECK((run_sep<60, 36, false, true, H, true>(c, pA, feat, m, h, w, nw->tc_fin[fmt])));
+    net_mark(c, mk);  // 5: final sepconv (fp32 features, w*36+c)
+    if (stop == 5) { set_debug(nw, feat, 0, m, h, w, 36, 36); return ORCAI_OK; }
+    ORCAI_CHECK(net_tail_fp32(c, feat, scratch, m, d_preds + (size_t)s0 * Tn * L, mk));
+  }
+  return ORCAI_OK;
+}
+
+}  // namespace
+
+int net_tc_prepare(Ctx* c, int fmt) {
+  NetWeights* nw = c->net;
+  if (!nw->loaded) ORCAI_FAIL(c, ORCAI_ERR_STATE, "no weights loaded (orcai_load_weights)");
+  if (nw->tc_ready[fmt]) return ORCAI_OK;
+  return fmt == 0 ? prepare<__half>(c, 0) : prepare<__nv_bfloat16>(c, 1);
+}
+
+int net_forward_tc(Ctx* c, const float* d_in, int input_mode, int64_t first, int64_t n, float* d_preds) {
+  NetWeights* nw = c->net;
+  const int fmt = nw->path == 2 ? 1 : 0;
+  ORCAI_CHECK(net_tc_prepare(c, fmt));
+  return fmt == 0 ? forward_tc<__half>(c, d_in, input_mode, first, n, d_preds, 0)
+                  : forward_tc<__nv_bfloat16>(c, d_in, input_mode, first, n, d_preds, 1);
+}
+
+}  // namespace orcai
