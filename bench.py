@@ -161,6 +161,8 @@ def main() -> None:
     ap.add_argument("--cpu-sample-seconds", type=float, default=600.0, help="bounded CPU-oracle sample (BASELINE config 0: one 10-min recording)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--chunk", type=int, default=0, help="snippets per network chunk (0 = library default)")
+    ap.add_argument("--net-path", type=int, default=1, choices=[0, 1, 2], help="0 fp32 CUDA cores, 1 fp16 tcgen05 (default), 2 bf16 tcgen05")
+    ap.add_argument("--stft-f64", type=int, default=1, choices=[0, 1], help="1 float64 FFT (parity grade, default), 0 float32 FFT")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -189,6 +191,8 @@ def main() -> None:
     ctx.load_weights(synthetic_weights(P, S, seed=1234))
     if args.chunk:
         ctx.set_option("chunk", args.chunk)
+    ctx.set_option("net_path", args.net_path)
+    ctx.set_option("stft_f64", args.stft_f64)
 
     # K <= 8 distinct seeded files; rank r annotates file r % 8
     pcm = make_recording(args.hours, 20251018 + (rank % 8))
@@ -260,10 +264,11 @@ def main() -> None:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * t_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
+            "dtype": {0: "f32", 1: "f16", 2: "bf16"}[args.net_path], "data": "synthetic",
             "config": {"workload": WORKLOAD_NAME, "hours_per_gpu_per_step": args.hours, "frames": T, "snippets": n_snip,
                        "segments_found": n_segments, "parallelism": f"shard-by-recording x{world}", "l2": "inputs larger than L2 (346 MB PCM, 475 MB dB per step)",
-                       "network_path": "fp32 cuda-core"},
+                       "network_path": {0: "fp32 cuda-core", 1: "fp16 tcgen05 implicit-GEMM trunk + fp32 LSTM/dense", 2: "bf16 tcgen05 implicit-GEMM trunk + fp32 LSTM/dense"}[args.net_path],
+                       "stft": "float64 FFT" if args.stft_f64 else "float32 FFT"},
             "device_ms_per_step": dev_ms,
             "stage_ms": {k: v / args.steps for k, v in stage.items()},
             "net_stage_ms_first_chunk": dict(zip(["conv0", "block1", "block2", "block3", "block4", "final_sep", "lstm1_proj", "lstm1_rec", "lstm2_proj",
