@@ -161,7 +161,7 @@ def main() -> None:
     ap.add_argument("--cpu-sample-seconds", type=float, default=600.0, help="bounded CPU-oracle sample (BASELINE config 0: one 10-min recording)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--chunk", type=int, default=0, help="snippets per network chunk (0 = library default)")
-    ap.add_argument("--net-path", type=int, default=1, choices=[0, 1, 2], help="0 fp32 CUDA cores, 1 fp16 tcgen05 (default), 2 bf16 tcgen05")
+    ap.add_argument("--net-path", type=int, default=1, choices=[0, 1, 2, 3], help="0 fp32 CUDA cores, 1 fp16 tcgen05 layer-wise, 2 bf16 tcgen05 layer-wise, 3 fp16 tcgen05 fused residual blocks")
     ap.add_argument("--stft-f64", type=int, default=1, choices=[0, 1], help="1 float64 FFT (parity grade, default), 0 float32 FFT")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -264,10 +264,11 @@ def main() -> None:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * t_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {0: "f32", 1: "f16", 2: "bf16"}[args.net_path], "data": "synthetic",
+            "dtype": {0: "f32", 1: "f16", 2: "bf16", 3: "f16"}[args.net_path], "data": "synthetic",
             "config": {"workload": WORKLOAD_NAME, "hours_per_gpu_per_step": args.hours, "frames": T, "snippets": n_snip,
                        "segments_found": n_segments, "parallelism": f"shard-by-recording x{world}", "l2": "inputs larger than L2 (346 MB PCM, 475 MB dB per step)",
-                       "network_path": {0: "fp32 cuda-core", 1: "fp16 tcgen05 implicit-GEMM trunk + fp32 LSTM/dense", 2: "bf16 tcgen05 implicit-GEMM trunk + fp32 LSTM/dense"}[args.net_path],
+                       "network_path": {0: "fp32 cuda-core", 1: "fp16 tcgen05 implicit-GEMM trunk + fp32 LSTM/dense", 2: "bf16 tcgen05 implicit-GEMM trunk + fp32 LSTM/dense",
+                                        3: "fp16 tcgen05 fused residual-block kernels + fp32 LSTM/dense"}[args.net_path],
                        "stft": "float64 FFT" if args.stft_f64 else "float32 FFT"},
             "device_ms_per_step": dev_ms,
             "stage_ms": {k: v / args.steps for k, v in stage.items()},

@@ -526,6 +526,7 @@ int net_debug_read(Ctx* c, float* out_host, int64_t capacity, int64_t* dims_out)
 int net_set_chunk(Ctx* c, int chunk) {
   if (chunk < 1) ORCAI_FAIL(c, ORCAI_ERR_ARG, "chunk must be >= 1");
   c->net->chunk = chunk;
+  c->net->chunk_fused = chunk;
   return ORCAI_OK;
 }
 
@@ -535,6 +536,7 @@ int net_load_weights(Ctx* c, const char* const* names, const float* const* data,
   nw->allocs.clear();
   nw->loaded = false;
   nw->tc_ready[0] = nw->tc_ready[1] = false;
+  nw->fused_ready = false;
   const orcai_params& P = c->p;
   if (P.n_blocks != 4 || P.filters[0] != 30 || P.filters[1] != 40 || P.filters[2] != 50 || P.filters[3] != 60 ||
       P.kernel_size != 3 || P.lstm_units != 128)
@@ -569,8 +571,10 @@ int net_load_weights(Ctx* c, const char* const* names, const float* const* data,
     const float* rk = ht.get(p + "/res/kernel", (int64_t)ci * co);
     const float* rb = ht.get(p + "/res/bias", co);
     if (!rk || !rb) return ORCAI_ERR_ARG;
-    ORCAI_CHECK(upload(c, std::vector<float>(rk, rk + (size_t)ci * co), &nw->res_w[b]));
-    ORCAI_CHECK(upload(c, std::vector<float>(rb, rb + co), &nw->res_b[b]));
+    nw->h_res_w[b].assign(rk, rk + (size_t)ci * co);
+    nw->h_res_b[b].assign(rb, rb + co);
+    ORCAI_CHECK(upload(c, nw->h_res_w[b], &nw->res_w[b]));
+    ORCAI_CHECK(upload(c, nw->h_res_b[b], &nw->res_b[b]));
     ci = co;
     w = (w + 1) / 2;
   }

@@ -43,7 +43,13 @@ struct NetWeights {
   void* tc_conv0_w[2] = {};   // [16 x 16] canonical
   TcSep tc_sep1[2][kMaxBlocks], tc_sep2[2][kMaxBlocks], tc_fin[2];
   void* tc_ws = nullptr; size_t tc_ws_cap = 0;
-  int path = 0;               // 0 = fp32 CUDA cores, 1 = fp16 tensor cores, 2 = bf16 tensor cores
+  int path = 0;               // 0 = fp32 CUDA cores, 1 = fp16 tensor cores, 2 = bf16 tensor cores, 3 = fp16 fused residual blocks
+  // fused residual-block kernels (net_fused.cuh): packed fp16 operands [sep1 | sep2 | residual] and fp32 biases per block
+  bool fused_ready = false;
+  void* fb_w[kMaxBlocks] = {};
+  float* fb_bias[kMaxBlocks] = {};
+  int chunk_fused = 2048;
+  std::vector<float> h_res_w[kMaxBlocks], h_res_b[kMaxBlocks];
   int debug_stop = -1;        // stop the forward after this stage (debug reads), -1 = run everything
   // last debug buffer: kind 0 f32, 1 fp16, 2 bf16 ; NHWC with channel pitch dbg_pitch
   const void* dbg_ptr = nullptr; int dbg_kind = 0; long long dbg_n = 0; int dbg_h = 0, dbg_w = 0, dbg_c = 0, dbg_pitch = 0;

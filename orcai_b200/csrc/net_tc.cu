@@ -184,7 +184,7 @@ template <typename H>
 __global__ void __launch_bounds__(128)
 conv0_tc_kernel(const float* __restrict__ in, int mode, long long first, int shift, int in_ld, int Himg, int Wimg,
                 const SelectState* __restrict__ st, const H* __restrict__ wgt, const float* __restrict__ bias,
-                H* __restrict__ out, long long n_snip, int tiles_w, int tiles_h) {
+                H* __restrict__ out, H* __restrict__ out_sub, long long n_snip, int tiles_w, int tiles_h) {
   __shared__ __align__(128) unsigned char s_a[128 * 16 * 2];   // A: 128 rows x 16 k, LBO 128, SBO 256
   __shared__ __align__(128) unsigned char s_w[16 * 16 * 2];    // B: 16 rows x 16 k
   __shared__ float s_x[kHalo];
@@ -255,6 +255,11 @@ conv0_tc_kernel(const float* __restrict__ in, int mode, long long first, int shi
       H* o = out + (((size_t)b * Himg + hh) * Wimg + ww) * 16;
       reinterpret_cast<uint4*>(o)[0] = pack8<H>(v);
       reinterpret_cast<uint4*>(o)[1] = pack8<H>(v + 8);
+      if (out_sub != nullptr && !(hh & 1) && !(ww & 1)) {   // input of the first residual 1x1/2 convolution
+        H* os = out_sub + (((size_t)b * (Himg >> 1) + (hh >> 1)) * ((Wimg + 1) >> 1) + (ww >> 1)) * 16;
+        reinterpret_cast<uint4*>(os)[0] = pack8<H>(v);
+        reinterpret_cast<uint4*>(os)[1] = pack8<H>(v + 8);
+      }
     }
     tc_fence_before();
     __syncthreads();
@@ -301,6 +306,8 @@ pool_res_tc_kernel(const H* __restrict__ t4, const H* __restrict__ prev, H* __re
     out[idx] = half_traits<H>::from_float(res);
   }
 }
+
+#include "net_fused.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // host side
@@ -431,8 +438,8 @@ int forward_tc(Ctx* c, const float* d_in, int input_mode, int64_t first, int64_t
       const long long grid = std::min<long long>(total, (long long)c->sm_count * 8);
       const float* src = (input_mode == 0) ? d_in : d_in + (size_t)s0 * Himg * Wf;
       conv0_tc_kernel<H><<<(unsigned)grid, 128, 0, c->stream>>>(src, input_mode, first + s0, shift, input_mode == 0 ? kRawLd : Wf, Himg, Wf,
-                                                                 c->d_sel, static_cast<const H*>(nw->tc_conv0_w[fmt]), nw->conv0_b, pA, m,
-                                                                 tiles_w, tiles_h);
+                                                                 c->d_sel, static_cast<const H*>(nw->tc_conv0_w[fmt]), nw->conv0_b, pA,
+                                                                 static_cast<H*>(nullptr), m, tiles_w, tiles_h);
       c->launches++;
       ORCAI_CUDA(c, cudaGetLastError());
     }
@@ -462,6 +469,152 @@ int forward_tc(Ctx* c, const float* d_in, int input_mode, int64_t first, int64_t
   return ORCAI_OK;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// fused path (net_path 3): conv0 -> 4 fused residual-block kernels -> final sepconv -> fp32 LSTM/dense tail
+// ------------------------------------------------------------------------------------------------
+using FB1 = fused::FB<16, 30, 29, 6, true, 2>;
+using FB2 = fused::FB<30, 40, 43, 4, true, 1>;
+using FB3 = fused::FB<40, 50, 22, 4, true, 1>;
+using FB4 = fused::FB<50, 60, 11, 4, false, 1>;
+
+template <class G>
+int build_fused_block(Ctx* c, int blk) {
+  NetWeights* nw = c->net;
+  const NetWeights::HostSep& s1 = nw->h_sep1[blk];
+  const NetWeights::HostSep& s2 = nw->h_sep2[blk];
+  if (s1.ci != G::CIN || s1.co != G::COUT || s2.ci != G::COUT || s2.co != G::COUT)
+    ORCAI_FAIL(c, ORCAI_ERR_ARG, "fused block %d: kernel geometry does not match the loaded weights", blk + 1);
+  std::vector<__half> w(G::W_BYTES / 2, __float2half_rn(0.f));
+  auto at = [](uint32_t off, uint32_t sbo, int n, int k) { return (off + (uint32_t)(n / 8) * sbo + (uint32_t)(k / 8) * 128 + (n % 8) * 16 + (k % 8) * 2) / 2; };
+  for (int t = 0; t < 9; ++t) {
+    for (int k = 0; k < G::CIN; ++k)
+      for (int n = 0; n < G::COUT; ++n)
+        w[at(G::OFF_W1 + t * G::TAP_W1, G::SBO_W1, n, k)] = __float2half_rn(s1.dw[(size_t)t * G::CIN + k] * s1.pw[(size_t)k * G::COUT + n]);
+    for (int k = 0; k < G::COUT; ++k)
+      for (int n = 0; n < G::COUT; ++n)
+        w[at(G::OFF_W2 + t * G::TAP_W2, G::SBO_W2, n, k)] = __float2half_rn(s2.dw[(size_t)t * G::COUT + k] * s2.pw[(size_t)k * G::COUT + n]);
+  }
+  const std::vector<float>& rw = nw->h_res_w[blk];
+  for (int k = 0; k < G::CIN; ++k)
+    for (int n = 0; n < G::COUT; ++n) w[at(G::OFF_WR, G::SBO_W1, n, k)] = __float2half_rn(rw[(size_t)k * G::COUT + n]);
+  std::vector<float> bias(3 * G::NP, 0.f);
+  for (int n = 0; n < G::COUT; ++n) {
+    bias[n] = s1.b[n];
+    bias[G::NP + n] = s2.b[n];
+    bias[2 * G::NP + n] = nw->h_res_b[blk][n];
+  }
+  void* p = nullptr;
+  ORCAI_CUDA(c, cudaMalloc(&p, G::W_BYTES));
+  nw->allocs.push_back(p);
+  ORCAI_CUDA(c, cudaMemcpy(p, w.data(), G::W_BYTES, cudaMemcpyHostToDevice));
+  nw->fb_w[blk] = p;
+  ORCAI_CHECK(net_upload(c, bias, &nw->fb_bias[blk]));
+  ORCAI_CUDA(c, cudaFuncSetAttribute(fused::fused_block_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
+  return ORCAI_OK;
+}
+
+int prepare_fused(Ctx* c) {
+  NetWeights* nw = c->net;
+  if (nw->fused_ready) return ORCAI_OK;
+  ORCAI_CHECK(net_tc_prepare(c, 0));   // conv0 and the final sepconv reuse the fp16 layer-wise operands
+  ORCAI_CHECK(build_fused_block<FB1>(c, 0));
+  ORCAI_CHECK(build_fused_block<FB2>(c, 1));
+  ORCAI_CHECK(build_fused_block<FB3>(c, 2));
+  ORCAI_CHECK(build_fused_block<FB4>(c, 3));
+  nw->fused_ready = true;
+  return ORCAI_OK;
+}
+
+template <class G>
+int run_fused_block(Ctx* c, int blk, const __half* xr, const __half* xs, __half* yr, __half* ys, long long m, int Himg, int Wimg) {
+  NetWeights* nw = c->net;
+  const int Wo = (Wimg + 1) / 2;
+  const int n_strips = (Wo + G::CP - 1) / G::CP;
+  const long long items = m * n_strips;
+  const long long grid = std::min<long long>(items, (long long)c->sm_count * G::CTAS);
+  fused::fused_block_kernel<G><<<(unsigned)grid, 256, G::SMEM, c->stream>>>(xr, xs, yr, ys, Himg, Wimg, n_strips, items,
+                                                                           static_cast<const unsigned char*>(nw->fb_w[blk]), nw->fb_bias[blk]);
+  c->launches++;
+  ORCAI_CUDA(c, cudaGetLastError());
+  return ORCAI_OK;
+}
+
+int forward_fused(Ctx* c, const float* d_in, int input_mode, int64_t first, int64_t n, float* d_preds) {
+  NetWeights* nw = c->net;
+  using H = __half;
+  const int Himg = nw->H, Wf = nw->Wf, U = nw->U, L = nw->L;
+  const int Tn = Himg >> nw->n_blocks;
+  // geometry of the activation tensors (halfs per snippet)
+  int hs[5], ws[5];
+  hs[0] = Himg; ws[0] = Wf;
+  for (int b = 0; b < 4; ++b) { hs[b + 1] = hs[b] / 2; ws[b + 1] = (ws[b] + 1) / 2; }
+  const int cp[5] = {16, FB1::OCP, FB2::OCP, FB3::OCP, FB4::OCP};
+  size_t full[5], sub[5], halfs = 0;
+  for (int b = 0; b < 5; ++b) {
+    full[b] = (size_t)hs[b] * ws[b] * cp[b];
+    sub[b] = b < 4 ? (size_t)hs[b + 1] * ws[b + 1] * cp[b] : 0;
+    halfs += full[b] + sub[b];
+  }
+  halfs = (halfs + 7) & ~(size_t)7;
+  const size_t tail_f = (size_t)Tn * (nw->feat + 2 * 4 * U + 2 * U + 2 * U + 128);
+  const size_t per = halfs * 2 + tail_f * 4;
+  const long long chunk = std::min<long long>(std::max(nw->chunk_fused, 1), n);
+  if (chunk <= 0) return ORCAI_OK;
+  ORCAI_CHECK(ensure_device_buffer(c, &nw->tc_ws, &nw->tc_ws_cap, per * (size_t)chunk + 256));
+  H* act[5]; H* acts[5];
+  {
+    H* p = static_cast<H*>(nw->tc_ws);
+    for (int b = 0; b < 5; ++b) { act[b] = p; p += full[b] * chunk; acts[b] = p; p += sub[b] * chunk; }
+  }
+  float* feat = reinterpret_cast<float*>(static_cast<H*>(nw->tc_ws) + halfs * chunk);
+  float* scratch = feat + (size_t)Tn * nw->feat * chunk;
+  const int shift = c->p.snippet_len / 2;
+  nw->mark_i = 0;
+  nw->dbg_ptr = nullptr;
+  const int stop = nw->debug_stop;
+
+  for (int64_t s0 = 0; s0 < n; s0 += chunk) {
+    const long long m = std::min<long long>(chunk, n - s0);
+    const bool mk = (s0 == 0);
+    if (mk) nw->marked_snippets = m;
+    net_mark(c, mk);
+    {
+      const int tiles_w = (Wf + kTileW - 1) / kTileW, tiles_h = (Himg + kTileH - 1) / kTileH;
+      const long long total = m * tiles_w * tiles_h;
+      const long long grid = std::min<long long>(total, (long long)c->sm_count * 8);
+      const float* src = (input_mode == 0) ? d_in : d_in + (size_t)s0 * Himg * Wf;
+      conv0_tc_kernel<H><<<(unsigned)grid, 128, 0, c->stream>>>(src, input_mode, first + s0, shift, input_mode == 0 ? kRawLd : Wf, Himg, Wf,
+                                                                 c->d_sel, static_cast<const H*>(nw->tc_conv0_w[0]), nw->conv0_b, act[0], acts[0],
+                                                                 m, tiles_w, tiles_h);
+      c->launches++;
+      ORCAI_CUDA(c, cudaGetLastError());
+    }
+    net_mark(c, mk);  // 0: conv0
+    if (stop == 0) { set_debug(nw, act[0], 1, m, hs[0], ws[0], 16, 16); return ORCAI_OK; }
+    ORCAI_CHECK((run_fused_block<FB1>(c, 0, act[0], acts[0], act[1], acts[1], m, hs[0], ws[0])));
+    net_mark(c, mk);  // 1
+    if (stop == 1) { set_debug(nw, act[1], 1, m, hs[1], ws[1], 30, cp[1]); return ORCAI_OK; }
+    if (stop == 21) { set_debug(nw, acts[1], 1, m, hs[2], ws[2], 30, cp[1]); return ORCAI_OK; }
+    ORCAI_CHECK((run_fused_block<FB2>(c, 1, act[1], acts[1], act[2], acts[2], m, hs[1], ws[1])));
+    net_mark(c, mk);  // 2
+    if (stop == 2) { set_debug(nw, act[2], 1, m, hs[2], ws[2], 40, cp[2]); return ORCAI_OK; }
+    if (stop == 22) { set_debug(nw, acts[2], 1, m, hs[3], ws[3], 40, cp[2]); return ORCAI_OK; }
+    ORCAI_CHECK((run_fused_block<FB3>(c, 2, act[2], acts[2], act[3], acts[3], m, hs[2], ws[2])));
+    net_mark(c, mk);  // 3
+    if (stop == 3) { set_debug(nw, act[3], 1, m, hs[3], ws[3], 50, cp[3]); return ORCAI_OK; }
+    if (stop == 23) { set_debug(nw, acts[3], 1, m, hs[4], ws[4], 50, cp[3]); return ORCAI_OK; }
+    ORCAI_CHECK((run_fused_block<FB4>(c, 3, act[3], acts[3], act[4], static_cast<H*>(nullptr), m, hs[3], ws[3])));
+    net_mark(c, mk);  // 4
+    if (stop == 4) { set_debug(nw, act[4], 1, m, hs[4], ws[4], 60, cp[4]); return ORCAI_OK; }
+    ORCAI_CHECK((run_sep<60, 36, false, true, H, true>(c, act[4], feat, m, hs[4], ws[4], nw->tc_fin[0])));
+    net_mark(c, mk);  // 5: final sepconv (fp32 features, w*36+c)
+    if (stop == 5) { set_debug(nw, feat, 0, m, hs[4], ws[4], 36, 36); return ORCAI_OK; }
+    ORCAI_CHECK(net_tail_fp32(c, feat, scratch, m, d_preds + (size_t)s0 * Tn * L, mk));
+  }
+  return ORCAI_OK;
+}
+
 }  // namespace
 
 int net_tc_prepare(Ctx* c, int fmt) {
@@ -473,6 +626,10 @@ int net_tc_prepare(Ctx* c, int fmt) {
 
 int net_forward_tc(Ctx* c, const float* d_in, int input_mode, int64_t first, int64_t n, float* d_preds) {
   NetWeights* nw = c->net;
+  if (nw->path == 3) {
+    ORCAI_CHECK(prepare_fused(c));
+    return forward_fused(c, d_in, input_mode, first, n, d_preds);
+  }
   const int fmt = nw->path == 2 ? 1 : 0;
   ORCAI_CHECK(net_tc_prepare(c, fmt));
   return fmt == 0 ? forward_tc<__half>(c, d_in, input_mode, first, n, d_preds, 0)
