@@ -1,4 +1,4 @@
-// One residual block of orcai-V1 as ONE persistent tcgen05 kernel (included by net_tc.cu).
+// One residual block of orcai-V1 as ONE persistent, warp-specialised tcgen05 kernel (included by net_tc.cu).
 //
 // Reference graph: src/orcAI/architectures.py:172-196 —
 //     x -> ReLU -> SepConv3x3 -> BN -> ReLU -> SepConv3x3 -> BN -> MaxPool(3,2)/2 "same"  (+)  Conv1x1/2(x)  -> y
@@ -21,18 +21,30 @@
 // GEMM weights (W'_tap = dw[tap] * pw * bn_scale), the residual 1x1 convolution is one more small MMA into its own
 // TMEM columns, and the max-pool + residual add + ReLU run in the epilogue straight out of shared memory / TMEM.
 // HBM sees each block's input once (plus 4 halo columns per strip) and its pooled output once.
+//
+// Warp roles: NEW worker warps (loads, TMEM drains, pooling, stores) and one issuer warp whose elected lane issues
+// every tcgen05.mma.  They meet only through mbarriers, so the tensor pipe runs the NEXT step's first convolution
+// while the workers pool and store the current one:
+//     x_full      workers -> issuer   X / R tiles of a step have landed (cp.async) and are visible to the async proxy
+//     bar1[t]     issuer  -> workers  tcgen05.commit: accumulator tile t of the first convolution is complete
+//     s1_full[t]  workers -> issuer   S1 tile t (and the carried rows) written
+//     bar2[t]     issuer  -> workers  accumulator tile t of the second convolution is complete
+//     barR[2]     issuer  -> workers  residual accumulator (double buffered across steps)
 #pragma once
 
 namespace fused {
 
 __host__ __device__ constexpr int imax(int a, int b) { return a > b ? a : b; }
+__host__ __device__ constexpr int imin(int a, int b) { return a < b ? a : b; }
 __host__ __device__ constexpr int round8(int a) { return (a + 7) & ~7; }
 __host__ __device__ constexpr int pow2cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
 
-template <int CIN_, int COUT_, int CPOOL_, int S_, bool RELU_OUT_, int CTAS_>
+template <int CIN_, int COUT_, int CPOOL_, int S_, bool RELU_OUT_, int CTAS_, int NEW_>
 struct FB {
-  static constexpr int CIN = CIN_, COUT = COUT_, CP = CPOOL_, S = S_, CTAS = CTAS_;
+  static constexpr int CIN = CIN_, COUT = COUT_, CP = CPOOL_, S = S_, CTAS = CTAS_, NEW = NEW_;
   static constexpr bool RELU_OUT = RELU_OUT_;
+  static constexpr int NWORK = NEW * 32, NTHREADS = NWORK + 32;
+  static constexpr int NT = NEW / 4;                 // worker teams per TMEM lane quadrant; a team drains 16 columns
   static constexpr int ICP = cpad8(CIN), OCP = cpad8(COUT);
   static constexpr int KP1 = cpad16(CIN);          // K per tap of sepconv 1 and of the residual convolution
   static constexpr int NP = cpad16(COUT);          // N of every MMA; K per tap of sepconv 2
@@ -61,12 +73,17 @@ struct FB {
   static constexpr uint32_t OFF_S2 = OFF_S1 + MCH * LBO_S1;
   static constexpr uint32_t OFF_BIAS = OFF_S2 + NG * LBO_S2;
   static constexpr uint32_t OFF_BAR = OFF_BIAS + 3 * NP * 4;
-  static constexpr uint32_t SMEM = OFF_BAR + (N1 + N2 + 1) * 8 + 16;
-  static constexpr int COL_R = 0, COL_1 = NP, COL_2 = NP + N1 * NP;
-  static constexpr int TM_COLS = pow2cols(NP * (1 + N1 + N2));
+  // barriers: bar1[N1] bar2[N2] barR[2] s1_full[N1] x_full
+  static constexpr int B_1 = 0, B_2 = N1, B_R = N1 + N2, B_S1 = N1 + N2 + 2, B_X = 2 * N1 + N2 + 2, NBAR = 2 * N1 + N2 + 3;
+  static constexpr uint32_t SMEM = OFF_BAR + NBAR * 8 + 16;
+  static constexpr int COL_R = 0, COL_1 = 2 * NP, COL_2 = 2 * NP + N1 * NP;
+  static constexpr int TM_COLS = pow2cols(NP * (2 + N1 + N2));
+  static_assert(NEW == 8 || NEW == 16, "worker warps come in groups of four (one per TMEM lane quadrant)");
+  static_assert(NT * 2 >= NG, "each worker team drains two channel groups (16 accumulator columns)");
   static_assert(S % 2 == 0 && S >= 2, "steps advance by whole pooled rows");
   static_assert(RQ <= 128, "one residual MMA tile per step");
-  static_assert(NP * (1 + N1 + N2) <= 512 && TM_COLS * CTAS <= 512, "TMEM columns");
+  static_assert(WP <= 126, "a second-convolution tile may only depend on first-convolution tiles t-1 .. t+1");
+  static_assert(NP * (2 + N1 + N2) <= 512 && TM_COLS * CTAS <= 512, "TMEM columns");
   static_assert(SMEM <= 227 * 1024, "shared memory");
   static_assert((128 - RPIX) * 16 <= XCH * LBO_X, "residual tile over-read must stay inside the CTA's shared memory");
 };
@@ -78,20 +95,41 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool v
 __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
-
-// TMEM -> registers: 32 lanes x 8 consecutive fp32 columns
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
-  uint32_t r[8];
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr)
-               : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+// true in exactly one lane of a converged warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred)
+      :
+      : "memory");
+  return pred != 0;
+}
+template <int N>
+__device__ __forceinline__ void worker_sync() {   // named barrier 1: the worker warps only
+  asm volatile("bar.sync 1, %0;" ::"n"(N) : "memory");
 }
 
-__device__ __forceinline__ uint4 pack8h(const float (&v)[8]) {
+// TMEM -> registers: 32 lanes x 16 consecutive fp32 columns (load and wait in one statement)
+__device__ __forceinline__ void tmem_ld16f(uint32_t taddr, float (&v)[16]) {
+  uint32_t r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ uint4 pack8h(const float* v) {
   uint4 r;
   __half2* h = reinterpret_cast<__half2*>(&r);
 #pragma unroll
@@ -107,62 +145,129 @@ __device__ __forceinline__ uint4 hmax8(uint4 a, uint4 b) {
 }
 
 template <class G>
-__global__ void __launch_bounds__(256, G::CTAS)
+__global__ void __launch_bounds__(G::NTHREADS, G::CTAS)
 fused_block_kernel(const __half* __restrict__ Xr, const __half* __restrict__ Xsub, __half* __restrict__ Yr,
                    __half* __restrict__ Ysub, int H, int W, int n_strips, long long n_items,
                    const unsigned char* __restrict__ wpack, const float* __restrict__ bias_pack) {
   extern __shared__ __align__(128) unsigned char smem[];
   float* s_bias = reinterpret_cast<float*>(smem + G::OFF_BIAS);   // [0,NP) sep1, [NP,2NP) sep2, [2NP,3NP) residual
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G::OFF_BAR);  // [0,N1) sep1 tiles, [N1,N1+N2) sep2 tiles, last: residual
-  uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + G::N1 + G::N2 + 1);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G::OFF_BAR);
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + G::NBAR);
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int Ho = H >> 1, Wo = (W + 1) >> 1;
   const int Hs = Ho >> 1, Ws = (Wo + 1) >> 1;
+  const int n_steps = (Ho + 1 + G::S / 2 - 1) / (G::S / 2);
 
-  for (int i = tid; i < (int)(G::W_BYTES / 16); i += 256) reinterpret_cast<uint4*>(smem)[i] = __ldg(reinterpret_cast<const uint4*>(wpack) + i);
-  for (int i = tid + G::W_BYTES / 16; i < (int)(G::OFF_BIAS / 16); i += 256) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
-  for (int i = tid; i < 3 * G::NP; i += 256) s_bias[i] = bias_pack[i];
+  for (int i = tid; i < (int)(G::W_BYTES / 16); i += G::NTHREADS) reinterpret_cast<uint4*>(smem)[i] = __ldg(reinterpret_cast<const uint4*>(wpack) + i);
+  for (int i = tid + G::W_BYTES / 16; i < (int)(G::OFF_BIAS / 16); i += G::NTHREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < 3 * G::NP; i += G::NTHREADS) s_bias[i] = bias_pack[i];
   if (tid == 0) {
-    for (int i = 0; i < G::N1 + G::N2 + 1; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < G::B_S1; ++i) mbar_init(&bars[i], 1);               // tcgen05.commit arrivals
+    for (int i = G::B_S1; i < G::NBAR; ++i) mbar_init(&bars[i], G::NEW);     // one arrival per worker warp
     fence_mbar_init();
   }
   __syncwarp();
   if (warp == 0) tmem_alloc<G::TM_COLS>(tslot);
+  fence_proxy_async();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tslot;
   const uint32_t sbase = smem_u32(smem);
-  constexpr uint32_t idesc = make_idesc_f16(128, G::NP, 0);
 
-  const int row = tid & 127;                     // accumulator row (TMEM lane) this thread drains
-  const int half = tid >> 7;                     // the two thread halves split the channel groups
-  const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-  constexpr int G_SPLIT = (G::NG + 1) / 2;
-  const int g_lo = half ? G_SPLIT : 0, g_hi = half ? G::NG : G_SPLIT;
-  // pooled pixel of the pool / residual epilogue
-  const int q_i = row / G::CP, q_j = row - q_i * G::CP;
+  const long long my_items = blockIdx.x < n_items ? (n_items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const long long total_steps = my_items * n_steps;
 
-  uint32_t phase = 0;
-  for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
-    const long long b = item / n_strips;
-    const int strip = (int)(item - b * n_strips);
-    const int wo0 = strip * G::CP, cb = 2 * wo0 - 2;
-    const __half* xr = Xr + (size_t)b * H * W * G::ICP;
-    const __half* xs = Xsub + (size_t)b * Ho * Wo * G::ICP;
-    const int n_steps = (Ho + 1 + G::S / 2 - 1) / (G::S / 2);
-
-    // rows carried into the first step lie above the image: zero (S2 row 0 is only read by the skipped pooled row -1)
-    for (int i = tid; i < G::NG * 2 * G::WP; i += 256) {
-      const int g = i / (2 * G::WP), px = i - g * 2 * G::WP;
-      *reinterpret_cast<uint4*>(smem + G::OFF_S1 + g * G::LBO_S1 + px * 16) = make_uint4(0, 0, 0, 0);
+  if (warp == G::NEW) {
+    // =============================== MMA issuer ===============================
+    // The whole warp runs the control flow; one elected lane issues (elect.sync keeps the tensor-core instructions in
+    // warp-uniform code, so ptxas emits them back to back instead of wrapping each one in a per-lane loop).
+    if (total_steps > 0) {
+      constexpr uint32_t idesc = make_idesc_f16(128, G::NP, 0);
+      // base descriptors; per-MMA descriptors differ only in the start-address field (16-byte units, no carry out of it)
+      const uint64_t dX = make_smem_desc(sbase + G::OFF_X, G::LBO_X, 128);
+      const uint64_t dS1 = make_smem_desc(sbase + G::OFF_S1, G::LBO_S1, 128);
+      const uint64_t dR = make_smem_desc(sbase + G::OFF_R, G::LBO_R, 128);
+      const uint64_t dW1 = make_smem_desc(sbase + G::OFF_W1, 128, G::SBO_W1);
+      const uint64_t dW2 = make_smem_desc(sbase + G::OFF_W2, 128, G::SBO_W2);
+      const uint64_t dWR = make_smem_desc(sbase + G::OFF_WR, 128, G::SBO_W1);
+      auto issue_first = [&](long long g) {   // residual 1x1 and first separable convolution of step g
+        if (elect_one()) {
+          const uint32_t colr = tmem + G::COL_R + (uint32_t)(g & 1) * G::NP;
+#pragma unroll
+          for (int ks = 0; ks < G::KP1 / 16; ++ks)
+            mma_f16_ss(colr, dR + ((2 * ks * G::LBO_R) >> 4), dWR + ((2 * ks * 128) >> 4), idesc, ks != 0);
+          mma_commit(&bars[G::B_R + (int)(g & 1)]);
+#pragma unroll
+          for (int t = 0; t < G::N1; ++t) {
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+              const uint32_t aoff = (uint32_t)(G::P1_0 + 128 * t - 2 * G::WP - 1 + (tap / 3) * G::WP + (tap % 3));   // pixels = 16-byte units
+#pragma unroll
+              for (int ks = 0; ks < G::KP1 / 16; ++ks)
+                mma_f16_ss(tmem + G::COL_1 + t * G::NP, dX + aoff + ((2 * ks * G::LBO_X) >> 4),
+                           dW1 + ((tap * G::TAP_W1 + 2 * ks * 128) >> 4), idesc, (tap | ks) != 0);
+            }
+            mma_commit(&bars[G::B_1 + t]);
+          }
+        }
+        __syncwarp();
+      };
+      mbar_wait(&bars[G::B_X], 0);
+      tc_fence_after();
+      issue_first(0);
+      for (long long g = 0; g < total_steps; ++g) {
+        const uint32_t par = (uint32_t)(g & 1);
+#pragma unroll
+        for (int t = 0; t < G::N2; ++t) {
+          // tile t of the second convolution reads S1 tiles <= t+1 (and the carried rows, published with tile 0)
+          if (t == 0) mbar_wait(&bars[G::B_S1], par);
+          if (t + 1 < G::N1) mbar_wait(&bars[G::B_S1 + t + 1], par);
+          tc_fence_after();
+          if (elect_one()) {
+#pragma unroll
+            for (int tap = 0; tap < 9; ++tap) {
+              const uint32_t aoff = (uint32_t)(G::P2_0 + 128 * t - G::WP - 1 + (tap / 3) * G::WP + (tap % 3));
+#pragma unroll
+              for (int ks = 0; ks < G::NP / 16; ++ks)
+                mma_f16_ss(tmem + G::COL_2 + t * G::NP, dS1 + aoff + ((2 * ks * G::LBO_S1) >> 4),
+                           dW2 + ((tap * G::TAP_W2 + 2 * ks * 128) >> 4), idesc, (tap | ks) != 0);
+            }
+            mma_commit(&bars[G::B_2 + t]);
+          }
+          __syncwarp();
+        }
+        if (g + 1 < total_steps) {
+          mbar_wait(&bars[G::B_X], par ^ 1);
+          tc_fence_after();
+          issue_first(g + 1);
+        }
+      }
     }
+    __syncwarp();
+  } else {
+    // =============================== workers ===============================
+    const int quad = warp & 3, team = warp >> 2;
+    const int row = quad * 32 + lane;              // accumulator row (TMEM lane) this thread drains
+    const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
+    const int g0 = team * 2;                       // first of the (up to) two channel groups of this team
+    const bool has0 = g0 < G::NG, has1 = g0 + 1 < G::NG;
+    const int q_i = row / G::CP, q_j = row - q_i * G::CP;   // pooled pixel of the pool / residual epilogue
+    // tile-invariant pixel coordinates of the accumulator rows this thread drains
+    int y1[G::N1], c1[G::N1], y2[G::N2], c2[G::N2];
+#pragma unroll
+    for (int t = 0; t < G::N1; ++t) { const int p = G::P1_0 + 128 * t + row; y1[t] = p / G::WP; c1[t] = p - y1[t] * G::WP; }
+#pragma unroll
+    for (int t = 0; t < G::N2; ++t) { const int p = G::P2_0 + 128 * t + row; y2[t] = p / G::WP; c2[t] = p - y2[t] * G::WP; }
 
-    for (int step = 0; step < n_steps; ++step) {
-      const int a = step * G::S - 2;
-      // ---- loads: X rows a+1 .. a+S+2 and the residual input pixels of this step's pooled rows ----
-      for (int idx = tid; idx < (G::S + 2) * G::WP * G::XG; idx += 256) {
+    auto issue_loads = [&](long long item, int step) {
+      const long long b = item / n_strips;
+      const int strip = (int)(item - b * n_strips);
+      const int cb = 2 * strip * G::CP - 2, a = step * G::S - 2;
+      const __half* xr = Xr + (size_t)b * H * W * G::ICP;
+      const __half* xs = Xsub + (size_t)b * Ho * Wo * G::ICP;
+      for (int idx = tid; idx < (G::S + 2) * G::WP * G::XG; idx += G::NWORK) {
         const int px = idx / G::XG, g = idx - px * G::XG;
         const int x = px / G::WP, c = px - x * G::WP;
         const int hh = a + 1 + x, ww = cb + c;
@@ -170,153 +275,148 @@ fused_block_kernel(const __half* __restrict__ Xr, const __half* __restrict__ Xsu
         const __half* src = ok ? xr + ((size_t)hh * W + ww) * G::ICP + g * 8 : xr;
         cp_async16(sbase + G::OFF_X + g * G::LBO_X + px * 16, src, ok);
       }
-      for (int idx = tid; idx < G::RQ * G::XG; idx += 256) {
+      for (int idx = tid; idx < G::RQ * G::XG; idx += G::NWORK) {
         const int q = idx / G::XG, g = idx - q * G::XG;
         const int i = q / G::CP, j = q - i * G::CP;
-        const int ho = (a >> 1) + i, wo = wo0 + j;
+        const int ho = (a >> 1) + i, wo = strip * G::CP + j;
         const bool ok = ho >= 0 && ho < Ho && wo < Wo;
         const __half* src = ok ? xs + ((size_t)ho * Wo + wo) * G::ICP + g * 8 : xs;
         cp_async16(sbase + G::OFF_R + g * G::LBO_R + q * 16, src, ok);
       }
+    };
+    auto publish_loads = [&]() {
       cp_async_wait_all();
       fence_proxy_async();
       tc_fence_before();
-      __syncthreads();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[G::B_X]);
+    };
 
-      // ---- residual 1x1 and first separable convolution ----
-      if (tid == 0) {
-        tc_fence_after();
+    if (my_items > 0) {
+      issue_loads(blockIdx.x, 0);
+      publish_loads();
+    }
+    long long g = 0;
+    for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const long long b = item / n_strips;
+      const int strip = (int)(item - b * n_strips);
+      const int wo0 = strip * G::CP, cb = 2 * wo0 - 2;
+      for (int step = 0; step < n_steps; ++step, ++g) {
+        const int a = step * G::S - 2;
+        const uint32_t par = (uint32_t)(g & 1);
+        // ---- epilogue 1: + bias, ReLU, zero outside the image ("same" padding of the second convolution) -> S1 ----
 #pragma unroll
-        for (int ks = 0; ks < G::KP1 / 16; ++ks)
-          mma_f16_ss(tmem + G::COL_R, make_smem_desc(sbase + G::OFF_R + 2 * ks * G::LBO_R, G::LBO_R, 128),
-                     make_smem_desc(sbase + G::OFF_WR + 2 * ks * 128, 128, G::SBO_W1), idesc, ks != 0);
-        mma_commit(&bars[G::N1 + G::N2]);
-#pragma unroll 1
         for (int t = 0; t < G::N1; ++t) {
+          mbar_wait(&bars[G::B_1 + t], par);
+          tc_fence_after();
+          if (has0) {
+            float v[16];
+            tmem_ld16f(lane_addr + G::COL_1 + t * G::NP + g0 * 8, v);
+            const int p1 = G::P1_0 + 128 * t + row;
+            const int hh = a + y1[t], ww = cb + c1[t];
+            const bool inimg = hh >= 0 && hh < H && ww >= 0 && ww < W;
+            if (p1 < (G::S + 2) * G::WP) {
 #pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {
-            const uint32_t a0 = sbase + G::OFF_X + (uint32_t)(G::P1_0 + 128 * t - 2 * G::WP - 1 + (tap / 3) * G::WP + (tap % 3)) * 16;
-            const uint32_t w0 = sbase + G::OFF_W1 + tap * G::TAP_W1;
-#pragma unroll
-            for (int ks = 0; ks < G::KP1 / 16; ++ks)
-              mma_f16_ss(tmem + G::COL_1 + t * G::NP, make_smem_desc(a0 + 2 * ks * G::LBO_X, G::LBO_X, 128),
-                         make_smem_desc(w0 + 2 * ks * 128, 128, G::SBO_W1), idesc, (tap | ks) != 0);
-          }
-          mma_commit(&bars[t]);
-        }
-      }
-      // epilogue 1: + bias, ReLU, zero outside the image ("same" padding of the second convolution) -> S1
-#pragma unroll 1
-      for (int t = 0; t < G::N1; ++t) {
-        mbar_wait(&bars[t], phase);
-        tc_fence_after();
-        const int p1 = G::P1_0 + 128 * t + row;
-        const int y = p1 / G::WP, c = p1 - y * G::WP;
-        const int hh = a + y, ww = cb + c;
-        const bool inimg = hh >= 0 && hh < H && ww >= 0 && ww < W;
-        const bool st = p1 < (G::S + 2) * G::WP;
-        for (int g = g_lo; g < g_hi; ++g) {
-          float v[8];
-          tmem_ld8(lane_addr + G::COL_1 + t * G::NP + g * 8, v);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = inimg ? fmaxf(v[i] + s_bias[g * 8 + i], 0.f) : 0.f;
-          if (st) *reinterpret_cast<uint4*>(smem + G::OFF_S1 + g * G::LBO_S1 + p1 * 16) = pack8h(v);
-        }
-      }
-      fence_proxy_async();
-      tc_fence_before();
-      __syncthreads();
-
-      // ---- second separable convolution ----
-      if (tid == 0) {
-        tc_fence_after();
-#pragma unroll 1
-        for (int t = 0; t < G::N2; ++t) {
-#pragma unroll
-          for (int tap = 0; tap < 9; ++tap) {
-            const uint32_t a0 = sbase + G::OFF_S1 + (uint32_t)(G::P2_0 + 128 * t - G::WP - 1 + (tap / 3) * G::WP + (tap % 3)) * 16;
-            const uint32_t w0 = sbase + G::OFF_W2 + tap * G::TAP_W2;
-#pragma unroll
-            for (int ks = 0; ks < G::NP / 16; ++ks)
-              mma_f16_ss(tmem + G::COL_2 + t * G::NP, make_smem_desc(a0 + 2 * ks * G::LBO_S1, G::LBO_S1, 128),
-                         make_smem_desc(w0 + 2 * ks * 128, 128, G::SBO_W2), idesc, (tap | ks) != 0);
-          }
-          mma_commit(&bars[G::N1 + t]);
-        }
-      }
-      // epilogue 2: + bias (folded BatchNorm), -inf outside the image (TF "same" max-pool padding) -> S2
-#pragma unroll 1
-      for (int t = 0; t < G::N2; ++t) {
-        mbar_wait(&bars[G::N1 + t], phase);
-        tc_fence_after();
-        const int p2 = G::P2_0 + 128 * t + row;
-        const int z = p2 / G::WP, c = p2 - z * G::WP;
-        const int hh = a + z, ww = cb + c;
-        const bool inimg = hh >= 0 && hh < H && ww >= 0 && ww < W;
-        const bool st = p2 < (G::S + 1) * G::WP;
-        for (int g = g_lo; g < g_hi; ++g) {
-          float v[8];
-          tmem_ld8(lane_addr + G::COL_2 + t * G::NP + g * 8, v);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = inimg ? v[i] + s_bias[G::NP + g * 8 + i] : -INFINITY;
-          if (st) *reinterpret_cast<uint4*>(smem + G::OFF_S2 + g * G::LBO_S2 + p2 * 16) = pack8h(v);
-        }
-      }
-      mbar_wait(&bars[G::N1 + G::N2], phase);   // residual accumulator
-      tc_fence_after();
-      __syncthreads();
-
-      // ---- max-pool (3,2)/2 + residual add (+ ReLU) -> global ----
-      {
-        const int ho = (a >> 1) + q_i, wo = wo0 + q_j;
-        const bool valid = row < G::RQ && ho >= 0 && ho < Ho && wo < Wo;
-        const uint32_t p00 = (uint32_t)((2 * q_i) * G::WP + 2 + 2 * q_j);
-        for (int g = g_lo; g < g_hi; ++g) {
-          float r[8];
-          tmem_ld8(lane_addr + G::COL_R + g * 8, r);
-          if (valid) {
-            const unsigned char* s2 = smem + G::OFF_S2 + g * G::LBO_S2 + p00 * 16;
-            uint4 m = *reinterpret_cast<const uint4*>(s2);
-            m = hmax8(m, *reinterpret_cast<const uint4*>(s2 + 16));
-            m = hmax8(m, *reinterpret_cast<const uint4*>(s2 + G::WP * 16));
-            m = hmax8(m, *reinterpret_cast<const uint4*>(s2 + G::WP * 16 + 16));
-            m = hmax8(m, *reinterpret_cast<const uint4*>(s2 + 2 * G::WP * 16));
-            m = hmax8(m, *reinterpret_cast<const uint4*>(s2 + 2 * G::WP * 16 + 16));
-            const __half2* mh = reinterpret_cast<const __half2*>(&m);
-            float y[8], yr[8];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const float2 f = __half22float2(mh[i]);
-              y[2 * i] = f.x + r[2 * i] + s_bias[2 * G::NP + g * 8 + 2 * i];
-              y[2 * i + 1] = f.y + r[2 * i + 1] + s_bias[2 * G::NP + g * 8 + 2 * i + 1];
+              for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + s_bias[g0 * 8 + i], 0.f);
+              const uint4 z = make_uint4(0, 0, 0, 0);
+              unsigned char* dst = smem + G::OFF_S1 + g0 * G::LBO_S1 + p1 * 16;
+              *reinterpret_cast<uint4*>(dst) = inimg ? pack8h(v) : z;
+              if (has1) *reinterpret_cast<uint4*>(dst + G::LBO_S1) = inimg ? pack8h(v + 8) : z;
             }
+          }
+          fence_proxy_async();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars[G::B_S1 + t]);
+        }
+        // ---- prefetch the next step's tiles (the first convolution has finished reading X and R) ----
+        long long n_item = item;
+        int n_step = step + 1;
+        if (n_step == n_steps) { n_item = item + gridDim.x; n_step = 0; }
+        const bool has_next = n_item < n_items;
+        if (has_next) issue_loads(n_item, n_step);
+        // ---- epilogue 2: + bias (folded BatchNorm), -inf outside the image (TF "same" max-pool padding) -> S2 ----
 #pragma unroll
-            for (int i = 0; i < 8; ++i) yr[i] = G::RELU_OUT ? fmaxf(y[i], 0.f) : y[i];
-            *reinterpret_cast<uint4*>(Yr + (((size_t)b * Ho + ho) * Wo + wo) * G::OCP + g * 8) = pack8h(yr);
-            if (Ysub != nullptr && !(ho & 1) && !(wo & 1))
-              *reinterpret_cast<uint4*>(Ysub + (((size_t)b * Hs + (ho >> 1)) * Ws + (wo >> 1)) * G::OCP + g * 8) = pack8h(y);
+        for (int t = 0; t < G::N2; ++t) {
+          mbar_wait(&bars[G::B_2 + t], par);
+          tc_fence_after();
+          if (has0) {
+            float v[16];
+            tmem_ld16f(lane_addr + G::COL_2 + t * G::NP + g0 * 8, v);
+            const int p2 = G::P2_0 + 128 * t + row;
+            const int hh = a + y2[t], ww = cb + c2[t];
+            const bool inimg = hh >= 0 && hh < H && ww >= 0 && ww < W;
+            if (p2 < (G::S + 1) * G::WP) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] += s_bias[G::NP + g0 * 8 + i];
+              const uint4 ninf = make_uint4(0xFC00FC00u, 0xFC00FC00u, 0xFC00FC00u, 0xFC00FC00u);
+              unsigned char* dst = smem + G::OFF_S2 + g0 * G::LBO_S2 + p2 * 16;
+              *reinterpret_cast<uint4*>(dst) = inimg ? pack8h(v) : ninf;
+              if (has1) *reinterpret_cast<uint4*>(dst + G::LBO_S2) = inimg ? pack8h(v + 8) : ninf;
+            }
           }
         }
-      }
-      tc_fence_before();
-      __syncthreads();
-
-      // ---- carry the overlap rows into the next step ----
-      if (step + 1 < n_steps) {
-        for (int i = tid; i < G::NG * 2 * G::WP; i += 256) {
-          const int g = i / (2 * G::WP), px = i - g * 2 * G::WP;
-          unsigned char* p = smem + G::OFF_S1 + g * G::LBO_S1 + px * 16;
-          *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(p + G::S * G::WP * 16);
+        if (has_next) publish_loads();
+        tc_fence_before();
+        worker_sync<G::NWORK>();   // S2 of this step is complete
+        // ---- max-pool (3,2)/2 + residual add (+ ReLU) -> global ----
+        mbar_wait(&bars[G::B_R + (int)(g & 1)], (uint32_t)((g >> 1) & 1));
+        tc_fence_after();
+        if (has0) {
+          float r[16];
+          tmem_ld16f(lane_addr + G::COL_R + (uint32_t)(g & 1) * G::NP + g0 * 8, r);
+          const int ho = (a >> 1) + q_i, wo = wo0 + q_j;
+          if (row < G::RQ && ho >= 0 && ho < Ho && wo < Wo) {
+            const uint32_t p00 = (uint32_t)((2 * q_i) * G::WP + 2 + 2 * q_j);
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              if (u == 1 && !has1) break;
+              const int gg = g0 + u;
+              const unsigned char* s2 = smem + G::OFF_S2 + gg * G::LBO_S2 + p00 * 16;
+              uint4 m = *reinterpret_cast<const uint4*>(s2);
+              m = hmax8(m, *reinterpret_cast<const uint4*>(s2 + 16));
+              m = hmax8(m, *reinterpret_cast<const uint4*>(s2 + G::WP * 16));
+              m = hmax8(m, *reinterpret_cast<const uint4*>(s2 + G::WP * 16 + 16));
+              m = hmax8(m, *reinterpret_cast<const uint4*>(s2 + 2 * G::WP * 16));
+              m = hmax8(m, *reinterpret_cast<const uint4*>(s2 + 2 * G::WP * 16 + 16));
+              const __half2* mh = reinterpret_cast<const __half2*>(&m);
+              float y[8], yr[8];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float2 f = __half22float2(mh[i]);
+                y[2 * i] = f.x + r[8 * u + 2 * i] + s_bias[2 * G::NP + gg * 8 + 2 * i];
+                y[2 * i + 1] = f.y + r[8 * u + 2 * i + 1] + s_bias[2 * G::NP + gg * 8 + 2 * i + 1];
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) yr[i] = G::RELU_OUT ? fmaxf(y[i], 0.f) : y[i];
+              *reinterpret_cast<uint4*>(Yr + (((size_t)b * Ho + ho) * Wo + wo) * G::OCP + gg * 8) = pack8h(yr);
+              if (Ysub != nullptr && !(ho & 1) && !(wo & 1))
+                *reinterpret_cast<uint4*>(Ysub + (((size_t)b * Hs + (ho >> 1)) * Ws + (wo >> 1)) * G::OCP + gg * 8) = pack8h(y);
+            }
+          }
         }
-        for (int i = tid; i < G::NG * G::WP; i += 256) {
-          const int g = i / G::WP, px = i - g * G::WP;
-          unsigned char* p = smem + G::OFF_S2 + g * G::LBO_S2 + px * 16;
-          *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(p + G::S * G::WP * 16);
+        tc_fence_before();
+        worker_sync<G::NWORK>();   // pooling has finished reading S2
+        // ---- carry the overlap rows into the next step (rows above the next strip's first row are zero) ----
+        if (has_next) {
+          const bool carry = step + 1 < n_steps;
+          for (int i = tid; i < G::NG * 2 * G::WP; i += G::NWORK) {
+            const int gq = i / (2 * G::WP), px = i - gq * 2 * G::WP;
+            unsigned char* p = smem + G::OFF_S1 + gq * G::LBO_S1 + px * 16;
+            *reinterpret_cast<uint4*>(p) = carry ? *reinterpret_cast<const uint4*>(p + G::S * G::WP * 16) : make_uint4(0, 0, 0, 0);
+          }
+          if (carry)
+            for (int i = tid; i < G::NG * G::WP; i += G::NWORK) {
+              const int gq = i / G::WP, px = i - gq * G::WP;
+              unsigned char* p = smem + G::OFF_S2 + gq * G::LBO_S2 + px * 16;
+              *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(p + G::S * G::WP * 16);
+            }
+          worker_sync<G::NWORK>();   // carried rows in place before epilogue 1 overwrites their source rows
         }
       }
-      phase ^= 1;
     }
   }
+  tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc<G::TM_COLS>(tmem);
 }

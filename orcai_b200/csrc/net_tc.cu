@@ -473,10 +473,10 @@ int forward_tc(Ctx* c, const float* d_in, int input_mode, int64_t first, int64_t
 // ------------------------------------------------------------------------------------------------
 // fused path (net_path 3): conv0 -> 4 fused residual-block kernels -> final sepconv -> fp32 LSTM/dense tail
 // ------------------------------------------------------------------------------------------------
-using FB1 = fused::FB<16, 30, 29, 6, true, 2>;
-using FB2 = fused::FB<30, 40, 43, 4, true, 1>;
-using FB3 = fused::FB<40, 50, 22, 4, true, 1>;
-using FB4 = fused::FB<50, 60, 11, 4, false, 1>;
+using FB1 = fused::FB<16, 30, 29, 6, true, 2, 8>;
+using FB2 = fused::FB<30, 40, 43, 4, true, 1, 16>;
+using FB3 = fused::FB<40, 50, 22, 4, true, 1, 16>;
+using FB4 = fused::FB<50, 60, 11, 4, false, 1, 16>;
 
 template <class G>
 int build_fused_block(Ctx* c, int blk) {
@@ -533,7 +533,7 @@ int run_fused_block(Ctx* c, int blk, const __half* xr, const __half* xs, __half*
   const int n_strips = (Wo + G::CP - 1) / G::CP;
   const long long items = m * n_strips;
   const long long grid = std::min<long long>(items, (long long)c->sm_count * G::CTAS);
-  fused::fused_block_kernel<G><<<(unsigned)grid, 256, G::SMEM, c->stream>>>(xr, xs, yr, ys, Himg, Wimg, n_strips, items,
+  fused::fused_block_kernel<G><<<(unsigned)grid, G::NTHREADS, G::SMEM, c->stream>>>(xr, xs, yr, ys, Himg, Wimg, n_strips, items,
                                                                            static_cast<const unsigned char*>(nw->fb_w[blk]), nw->fb_bias[blk]);
   c->launches++;
   ORCAI_CUDA(c, cudaGetLastError());

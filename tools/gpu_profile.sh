@@ -11,6 +11,6 @@ tail -1 gpurun_out/${TAG}_plain.log
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1500 --csv --log-file gpurun_out/${TAG}_launches.csv $CMD > gpurun_out/${TAG}_ncu_launches.log 2>&1
 echo "launch list rc=$?"
 for K in $KERNELS; do
-  ncu --set full --clock-control none --import-source on -k regex:$K -s 2 -c 2 -f -o gpurun_out/${TAG}_$K $CMD > gpurun_out/${TAG}_ncu_$K.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:$K -s ${NCU_SKIP:-2} -c ${NCU_COUNT:-2} -f -o gpurun_out/${TAG}_$K $CMD > gpurun_out/${TAG}_ncu_$K.log 2>&1
   echo "full $K rc=$?"
 done
