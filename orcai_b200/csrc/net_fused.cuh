@@ -22,10 +22,13 @@
 // TMEM columns, and the max-pool + residual add + ReLU run in the epilogue straight out of shared memory / TMEM.
 // HBM sees each block's input once (plus 4 halo columns per strip) and its pooled output once.
 //
-// Warp roles: NEW worker warps (loads, TMEM drains, pooling, stores) and one issuer warp whose elected lane issues
-// every tcgen05.mma.  They meet only through mbarriers, so the tensor pipe runs the NEXT step's first convolution
-// while the workers pool and store the current one:
-//     x_full      workers -> issuer   X / R tiles of a step have landed (cp.async) and are visible to the async proxy
+// Warp roles: NEW worker warps (TMEM drains, pooling, stores), one issuer warp whose elected lane issues every
+// tcgen05.mma, and one producer warp that feeds X / R with TMA (5-D tensor maps over the NHWC activations: the box
+// {8 ch, 1 chunk, WP cols, S+2 rows, 1 snippet} lands as one pixel-linear chunk plane, borders are zero-filled by the
+// TMA unit).  They meet only through mbarriers, so the tensor pipe runs the NEXT step's first convolution while the
+// workers pool and store the current one.  Biases ride on the tensor pipe as well: every accumulator tile starts
+// with one K=16 MMA of a constant "ones" operand against [bias_hi, bias_lo] rows (fp16 split, exact to 2^-22).
+//     x_full      producer -> issuer  X / R tiles of a step have landed (TMA complete_tx)
 //     bar1[t]     issuer  -> workers  tcgen05.commit: accumulator tile t of the first convolution is complete
 //     s1_full[t]  workers -> issuer   S1 tile t (and the carried rows) written
 //     bar2[t]     issuer  -> workers  accumulator tile t of the second convolution is complete
@@ -43,7 +46,7 @@ template <int CIN_, int COUT_, int CPOOL_, int S_, bool RELU_OUT_, int CTAS_, in
 struct FB {
   static constexpr int CIN = CIN_, COUT = COUT_, CP = CPOOL_, S = S_, CTAS = CTAS_, NEW = NEW_;
   static constexpr bool RELU_OUT = RELU_OUT_;
-  static constexpr int NWORK = NEW * 32, NTHREADS = NWORK + 32;
+  static constexpr int NWORK = NEW * 32, NTHREADS = NWORK + 64;   // + issuer warp + producer warp
   static constexpr int NT = NEW / 4;                 // worker teams per TMEM lane quadrant; a team drains 16 columns
   static constexpr int ICP = cpad8(CIN), OCP = cpad8(COUT);
   static constexpr int KP1 = cpad16(CIN);          // K per tap of sepconv 1 and of the residual convolution
@@ -65,17 +68,20 @@ struct FB {
   static constexpr uint32_t SBO_W1 = XG * 128, SBO_W2 = NG * 128;
   static constexpr uint32_t TAP_W1 = NG * SBO_W1, TAP_W2 = NG * SBO_W2;
   static constexpr uint32_t W1_BYTES = 9 * TAP_W1 + 128, W2_BYTES = 9 * TAP_W2 + 128, WR_BYTES = TAP_W1 + 128;
+  static constexpr uint32_t WB_BYTES = NG * 128 + 128;   // [bias_hi, bias_lo] rows of one GEMM: n-groups of one k-chunk
   static constexpr uint32_t OFF_W1 = 0, OFF_W2 = OFF_W1 + W1_BYTES, OFF_WR = OFF_W2 + W2_BYTES;
-  static constexpr uint32_t W_BYTES = OFF_WR + WR_BYTES;
+  static constexpr uint32_t OFF_WB1 = OFF_WR + WR_BYTES, OFF_WB2 = OFF_WB1 + WB_BYTES, OFF_WBR = OFF_WB2 + WB_BYTES;
+  static constexpr uint32_t OFF_ONES = OFF_WBR + WB_BYTES;   // two 8x8 core matrices: k = 0,1 are 1.0, the rest 0 (SBO = 0)
+  static constexpr uint32_t W_BYTES = OFF_ONES + 256;
   static constexpr uint32_t OFF_R = W_BYTES;
   static constexpr uint32_t OFF_X = OFF_R + XCH * LBO_R;
   static constexpr uint32_t OFF_S1 = OFF_X + XCH * LBO_X;
   static constexpr uint32_t OFF_S2 = OFF_S1 + MCH * LBO_S1;
-  static constexpr uint32_t OFF_BIAS = OFF_S2 + NG * LBO_S2;
-  static constexpr uint32_t OFF_BAR = OFF_BIAS + 3 * NP * 4;
+  static constexpr uint32_t OFF_BAR = OFF_S2 + NG * LBO_S2;
   // barriers: bar1[N1] bar2[N2] barR[2] s1_full[N1] x_full
   static constexpr int B_1 = 0, B_2 = N1, B_R = N1 + N2, B_S1 = N1 + N2 + 2, B_X = 2 * N1 + N2 + 2, NBAR = 2 * N1 + N2 + 3;
   static constexpr uint32_t SMEM = OFF_BAR + NBAR * 8 + 16;
+  static constexpr uint32_t TX_BYTES = XG * ((S + 2) * WP + (S / 2) * CP) * 16;   // bytes one step's TMA loads deliver
   static constexpr int COL_R = 0, COL_1 = 2 * NP, COL_2 = 2 * NP + N1 * NP;
   static constexpr int TM_COLS = pow2cols(NP * (2 + N1 + N2));
   static_assert(NEW == 8 || NEW == 16, "worker warps come in groups of four (one per TMEM lane quadrant)");
@@ -84,16 +90,20 @@ struct FB {
   static_assert(RQ <= 128, "one residual MMA tile per step");
   static_assert(WP <= 126, "a second-convolution tile may only depend on first-convolution tiles t-1 .. t+1");
   static_assert(NP * (2 + N1 + N2) <= 512 && TM_COLS * CTAS <= 512, "TMEM columns");
-  static_assert(SMEM <= 227 * 1024, "shared memory");
+  static_assert(SMEM <= 227 * 1024 && (SMEM + 1024) * CTAS <= 228 * 1024, "shared memory (per CTA and per SM)");
   static_assert((128 - RPIX) * 16 <= XCH * LBO_X, "residual tile over-read must stay inside the CTA's shared memory");
 };
 
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
-  const int sz = valid ? 16 : 0;
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void cp_async_wait_all() {
-  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+// TMA: one box of a rank-5 tensor map -> shared memory, completion counted on an mbarrier
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      :
+      : "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
@@ -129,6 +139,13 @@ __device__ __forceinline__ void tmem_ld16f(uint32_t taddr, float (&v)[16]) {
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+__device__ __forceinline__ uint4 relu8h(uint4 a) {
+  __half2* x = reinterpret_cast<__half2*>(&a);
+  const __half2 z = __float2half2_rn(0.f);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) x[i] = __hmax2(x[i], z);
+  return a;
+}
 __device__ __forceinline__ uint4 pack8h(const float* v) {
   uint4 r;
   __half2* h = reinterpret_cast<__half2*>(&r);
@@ -146,11 +163,10 @@ __device__ __forceinline__ uint4 hmax8(uint4 a, uint4 b) {
 
 template <class G>
 __global__ void __launch_bounds__(G::NTHREADS, G::CTAS)
-fused_block_kernel(const __half* __restrict__ Xr, const __half* __restrict__ Xsub, __half* __restrict__ Yr,
+fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmR, __half* __restrict__ Yr,
                    __half* __restrict__ Ysub, int H, int W, int n_strips, long long n_items,
-                   const unsigned char* __restrict__ wpack, const float* __restrict__ bias_pack) {
+                   const unsigned char* __restrict__ wpack) {
   extern __shared__ __align__(128) unsigned char smem[];
-  float* s_bias = reinterpret_cast<float*>(smem + G::OFF_BIAS);   // [0,NP) sep1, [NP,2NP) sep2, [2NP,3NP) residual
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G::OFF_BAR);
   uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + G::NBAR);
 
@@ -160,11 +176,11 @@ fused_block_kernel(const __half* __restrict__ Xr, const __half* __restrict__ Xsu
   const int n_steps = (Ho + 1 + G::S / 2 - 1) / (G::S / 2);
 
   for (int i = tid; i < (int)(G::W_BYTES / 16); i += G::NTHREADS) reinterpret_cast<uint4*>(smem)[i] = __ldg(reinterpret_cast<const uint4*>(wpack) + i);
-  for (int i = tid + G::W_BYTES / 16; i < (int)(G::OFF_BIAS / 16); i += G::NTHREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
-  for (int i = tid; i < 3 * G::NP; i += G::NTHREADS) s_bias[i] = bias_pack[i];
+  for (int i = tid + G::W_BYTES / 16; i < (int)(G::OFF_BAR / 16); i += G::NTHREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0) {
-    for (int i = 0; i < G::B_S1; ++i) mbar_init(&bars[i], 1);               // tcgen05.commit arrivals
-    for (int i = G::B_S1; i < G::NBAR; ++i) mbar_init(&bars[i], G::NEW);     // one arrival per worker warp
+    for (int i = 0; i < G::B_S1; ++i) mbar_init(&bars[i], 1);                 // tcgen05.commit arrivals
+    for (int i = G::B_S1; i < G::B_X; ++i) mbar_init(&bars[i], G::NEW);        // one arrival per worker warp
+    mbar_init(&bars[G::B_X], 1);                                               // producer's arrive.expect_tx
     fence_mbar_init();
   }
   __syncwarp();
@@ -179,7 +195,29 @@ fused_block_kernel(const __half* __restrict__ Xr, const __half* __restrict__ Xsu
   const long long my_items = blockIdx.x < n_items ? (n_items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   const long long total_steps = my_items * n_steps;
 
-  if (warp == G::NEW) {
+  if (warp == G::NEW + 1) {
+    // =============================== TMA producer ===============================
+    long long g = 0;
+    for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const long long b = item / n_strips;
+      const int strip = (int)(item - b * n_strips);
+      const int wo0 = strip * G::CP, cb = 2 * wo0 - 2;
+      for (int step = 0; step < n_steps; ++step, ++g) {
+        const int a = step * G::S - 2;
+        // X and R are free once the previous step's first convolution (and residual MMA) has completed
+        if (g > 0) mbar_wait(&bars[G::B_1 + G::N1 - 1], (uint32_t)((g - 1) & 1));
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&bars[G::B_X], G::TX_BYTES);
+#pragma unroll
+          for (int c = 0; c < G::XG; ++c) {
+            tma_load_5d(sbase + G::OFF_X + c * G::LBO_X, &tmX, &bars[G::B_X], 0, c, cb, a + 1, (int)b);
+            tma_load_5d(sbase + G::OFF_R + c * G::LBO_R, &tmR, &bars[G::B_X], 0, c, wo0, a >> 1, (int)b);
+          }
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == G::NEW) {
     // =============================== MMA issuer ===============================
     // The whole warp runs the control flow; one elected lane issues (elect.sync keeps the tensor-core instructions in
     // warp-uniform code, so ptxas emits them back to back instead of wrapping each one in a per-lane loop).
@@ -192,22 +230,28 @@ fused_block_kernel(const __half* __restrict__ Xr, const __half* __restrict__ Xsu
       const uint64_t dW1 = make_smem_desc(sbase + G::OFF_W1, 128, G::SBO_W1);
       const uint64_t dW2 = make_smem_desc(sbase + G::OFF_W2, 128, G::SBO_W2);
       const uint64_t dWR = make_smem_desc(sbase + G::OFF_WR, 128, G::SBO_W1);
+      const uint64_t dOnes = make_smem_desc(sbase + G::OFF_ONES, 128, 0);       // every 8-row group reads the same core matrix
+      const uint64_t dB1 = make_smem_desc(sbase + G::OFF_WB1, 128, 128);
+      const uint64_t dB2 = make_smem_desc(sbase + G::OFF_WB2, 128, 128);
+      const uint64_t dBR = make_smem_desc(sbase + G::OFF_WBR, 128, 128);
       auto issue_first = [&](long long g) {   // residual 1x1 and first separable convolution of step g
         if (elect_one()) {
           const uint32_t colr = tmem + G::COL_R + (uint32_t)(g & 1) * G::NP;
+          mma_f16_ss(colr, dOnes, dBR, idesc, 0);
 #pragma unroll
           for (int ks = 0; ks < G::KP1 / 16; ++ks)
-            mma_f16_ss(colr, dR + ((2 * ks * G::LBO_R) >> 4), dWR + ((2 * ks * 128) >> 4), idesc, ks != 0);
+            mma_f16_ss(colr, dR + ((2 * ks * G::LBO_R) >> 4), dWR + ((2 * ks * 128) >> 4), idesc, 1);
           mma_commit(&bars[G::B_R + (int)(g & 1)]);
 #pragma unroll
           for (int t = 0; t < G::N1; ++t) {
+            mma_f16_ss(tmem + G::COL_1 + t * G::NP, dOnes, dB1, idesc, 0);
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
               const uint32_t aoff = (uint32_t)(G::P1_0 + 128 * t - 2 * G::WP - 1 + (tap / 3) * G::WP + (tap % 3));   // pixels = 16-byte units
 #pragma unroll
               for (int ks = 0; ks < G::KP1 / 16; ++ks)
                 mma_f16_ss(tmem + G::COL_1 + t * G::NP, dX + aoff + ((2 * ks * G::LBO_X) >> 4),
-                           dW1 + ((tap * G::TAP_W1 + 2 * ks * 128) >> 4), idesc, (tap | ks) != 0);
+                           dW1 + ((tap * G::TAP_W1 + 2 * ks * 128) >> 4), idesc, 1);
             }
             mma_commit(&bars[G::B_1 + t]);
           }
@@ -226,13 +270,14 @@ fused_block_kernel(const __half* __restrict__ Xr, const __half* __restrict__ Xsu
           if (t + 1 < G::N1) mbar_wait(&bars[G::B_S1 + t + 1], par);
           tc_fence_after();
           if (elect_one()) {
+            mma_f16_ss(tmem + G::COL_2 + t * G::NP, dOnes, dB2, idesc, 0);
 #pragma unroll
             for (int tap = 0; tap < 9; ++tap) {
               const uint32_t aoff = (uint32_t)(G::P2_0 + 128 * t - G::WP - 1 + (tap / 3) * G::WP + (tap % 3));
 #pragma unroll
               for (int ks = 0; ks < G::NP / 16; ++ks)
                 mma_f16_ss(tmem + G::COL_2 + t * G::NP, dS1 + aoff + ((2 * ks * G::LBO_S1) >> 4),
-                           dW2 + ((tap * G::TAP_W2 + 2 * ks * 128) >> 4), idesc, (tap | ks) != 0);
+                           dW2 + ((tap * G::TAP_W2 + 2 * ks * 128) >> 4), idesc, 1);
             }
             mma_commit(&bars[G::B_2 + t]);
           }
@@ -261,41 +306,6 @@ fused_block_kernel(const __half* __restrict__ Xr, const __half* __restrict__ Xsu
 #pragma unroll
     for (int t = 0; t < G::N2; ++t) { const int p = G::P2_0 + 128 * t + row; y2[t] = p / G::WP; c2[t] = p - y2[t] * G::WP; }
 
-    auto issue_loads = [&](long long item, int step) {
-      const long long b = item / n_strips;
-      const int strip = (int)(item - b * n_strips);
-      const int cb = 2 * strip * G::CP - 2, a = step * G::S - 2;
-      const __half* xr = Xr + (size_t)b * H * W * G::ICP;
-      const __half* xs = Xsub + (size_t)b * Ho * Wo * G::ICP;
-      for (int idx = tid; idx < (G::S + 2) * G::WP * G::XG; idx += G::NWORK) {
-        const int px = idx / G::XG, g = idx - px * G::XG;
-        const int x = px / G::WP, c = px - x * G::WP;
-        const int hh = a + 1 + x, ww = cb + c;
-        const bool ok = hh >= 0 && hh < H && ww >= 0 && ww < W;
-        const __half* src = ok ? xr + ((size_t)hh * W + ww) * G::ICP + g * 8 : xr;
-        cp_async16(sbase + G::OFF_X + g * G::LBO_X + px * 16, src, ok);
-      }
-      for (int idx = tid; idx < G::RQ * G::XG; idx += G::NWORK) {
-        const int q = idx / G::XG, g = idx - q * G::XG;
-        const int i = q / G::CP, j = q - i * G::CP;
-        const int ho = (a >> 1) + i, wo = strip * G::CP + j;
-        const bool ok = ho >= 0 && ho < Ho && wo < Wo;
-        const __half* src = ok ? xs + ((size_t)ho * Wo + wo) * G::ICP + g * 8 : xs;
-        cp_async16(sbase + G::OFF_R + g * G::LBO_R + q * 16, src, ok);
-      }
-    };
-    auto publish_loads = [&]() {
-      cp_async_wait_all();
-      fence_proxy_async();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars[G::B_X]);
-    };
-
-    if (my_items > 0) {
-      issue_loads(blockIdx.x, 0);
-      publish_loads();
-    }
     long long g = 0;
     for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
       const long long b = item / n_strips;
@@ -304,7 +314,7 @@ fused_block_kernel(const __half* __restrict__ Xr, const __half* __restrict__ Xsu
       for (int step = 0; step < n_steps; ++step, ++g) {
         const int a = step * G::S - 2;
         const uint32_t par = (uint32_t)(g & 1);
-        // ---- epilogue 1: + bias, ReLU, zero outside the image ("same" padding of the second convolution) -> S1 ----
+        // ---- epilogue 1: ReLU, zero outside the image ("same" padding of the second convolution) -> S1 ----
 #pragma unroll
         for (int t = 0; t < G::N1; ++t) {
           mbar_wait(&bars[G::B_1 + t], par);
@@ -316,12 +326,10 @@ fused_block_kernel(const __half* __restrict__ Xr, const __half* __restrict__ Xsu
             const int hh = a + y1[t], ww = cb + c1[t];
             const bool inimg = hh >= 0 && hh < H && ww >= 0 && ww < W;
             if (p1 < (G::S + 2) * G::WP) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i] + s_bias[g0 * 8 + i], 0.f);
               const uint4 z = make_uint4(0, 0, 0, 0);
               unsigned char* dst = smem + G::OFF_S1 + g0 * G::LBO_S1 + p1 * 16;
-              *reinterpret_cast<uint4*>(dst) = inimg ? pack8h(v) : z;
-              if (has1) *reinterpret_cast<uint4*>(dst + G::LBO_S1) = inimg ? pack8h(v + 8) : z;
+              *reinterpret_cast<uint4*>(dst) = inimg ? relu8h(pack8h(v)) : z;
+              if (has1) *reinterpret_cast<uint4*>(dst + G::LBO_S1) = inimg ? relu8h(pack8h(v + 8)) : z;
             }
           }
           fence_proxy_async();
@@ -329,13 +337,7 @@ fused_block_kernel(const __half* __restrict__ Xr, const __half* __restrict__ Xsu
           __syncwarp();
           if (lane == 0) mbar_arrive(&bars[G::B_S1 + t]);
         }
-        // ---- prefetch the next step's tiles (the first convolution has finished reading X and R) ----
-        long long n_item = item;
-        int n_step = step + 1;
-        if (n_step == n_steps) { n_item = item + gridDim.x; n_step = 0; }
-        const bool has_next = n_item < n_items;
-        if (has_next) issue_loads(n_item, n_step);
-        // ---- epilogue 2: + bias (folded BatchNorm), -inf outside the image (TF "same" max-pool padding) -> S2 ----
+        // ---- epilogue 2: -inf outside the image (TF "same" max-pool padding) -> S2 ----
 #pragma unroll
         for (int t = 0; t < G::N2; ++t) {
           mbar_wait(&bars[G::B_2 + t], par);
@@ -347,8 +349,6 @@ fused_block_kernel(const __half* __restrict__ Xr, const __half* __restrict__ Xsu
             const int hh = a + y2[t], ww = cb + c2[t];
             const bool inimg = hh >= 0 && hh < H && ww >= 0 && ww < W;
             if (p2 < (G::S + 1) * G::WP) {
-#pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] += s_bias[G::NP + g0 * 8 + i];
               const uint4 ninf = make_uint4(0xFC00FC00u, 0xFC00FC00u, 0xFC00FC00u, 0xFC00FC00u);
               unsigned char* dst = smem + G::OFF_S2 + g0 * G::LBO_S2 + p2 * 16;
               *reinterpret_cast<uint4*>(dst) = inimg ? pack8h(v) : ninf;
@@ -356,7 +356,6 @@ fused_block_kernel(const __half* __restrict__ Xr, const __half* __restrict__ Xsu
             }
           }
         }
-        if (has_next) publish_loads();
         tc_fence_before();
         worker_sync<G::NWORK>();   // S2 of this step is complete
         // ---- max-pool (3,2)/2 + residual add (+ ReLU) -> global ----
@@ -380,25 +379,24 @@ fused_block_kernel(const __half* __restrict__ Xr, const __half* __restrict__ Xsu
               m = hmax8(m, *reinterpret_cast<const uint4*>(s2 + 2 * G::WP * 16));
               m = hmax8(m, *reinterpret_cast<const uint4*>(s2 + 2 * G::WP * 16 + 16));
               const __half2* mh = reinterpret_cast<const __half2*>(&m);
-              float y[8], yr[8];
+              float y[8];
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
                 const float2 f = __half22float2(mh[i]);
-                y[2 * i] = f.x + r[8 * u + 2 * i] + s_bias[2 * G::NP + gg * 8 + 2 * i];
-                y[2 * i + 1] = f.y + r[8 * u + 2 * i + 1] + s_bias[2 * G::NP + gg * 8 + 2 * i + 1];
+                y[2 * i] = f.x + r[8 * u + 2 * i];
+                y[2 * i + 1] = f.y + r[8 * u + 2 * i + 1];
               }
-#pragma unroll
-              for (int i = 0; i < 8; ++i) yr[i] = G::RELU_OUT ? fmaxf(y[i], 0.f) : y[i];
-              *reinterpret_cast<uint4*>(Yr + (((size_t)b * Ho + ho) * Wo + wo) * G::OCP + gg * 8) = pack8h(yr);
+              const uint4 yp = pack8h(y);
+              *reinterpret_cast<uint4*>(Yr + (((size_t)b * Ho + ho) * Wo + wo) * G::OCP + gg * 8) = G::RELU_OUT ? relu8h(yp) : yp;
               if (Ysub != nullptr && !(ho & 1) && !(wo & 1))
-                *reinterpret_cast<uint4*>(Ysub + (((size_t)b * Hs + (ho >> 1)) * Ws + (wo >> 1)) * G::OCP + gg * 8) = pack8h(y);
+                *reinterpret_cast<uint4*>(Ysub + (((size_t)b * Hs + (ho >> 1)) * Ws + (wo >> 1)) * G::OCP + gg * 8) = yp;
             }
           }
         }
         tc_fence_before();
         worker_sync<G::NWORK>();   // pooling has finished reading S2
         // ---- carry the overlap rows into the next step (rows above the next strip's first row are zero) ----
-        if (has_next) {
+        if (g + 1 < total_steps) {
           const bool carry = step + 1 < n_steps;
           for (int i = tid; i < G::NG * 2 * G::WP; i += G::NWORK) {
             const int gq = i / (2 * G::WP), px = i - gq * 2 * G::WP;

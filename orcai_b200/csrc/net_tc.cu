@@ -18,6 +18,8 @@
 //
 // Activations between kernels are NHWC 16-bit with the channel pitch padded to a multiple of 8 (padding
 // channels are written as zeros), so every (pixel, k-chunk) is one aligned 16-byte vector.
+#include <cuda.h>
+
 #include <algorithm>
 #include <cstring>
 
@@ -498,18 +500,27 @@ int build_fused_block(Ctx* c, int blk) {
   const std::vector<float>& rw = nw->h_res_w[blk];
   for (int k = 0; k < G::CIN; ++k)
     for (int n = 0; n < G::COUT; ++n) w[at(G::OFF_WR, G::SBO_W1, n, k)] = __float2half_rn(rw[(size_t)k * G::COUT + n]);
-  std::vector<float> bias(3 * G::NP, 0.f);
-  for (int n = 0; n < G::COUT; ++n) {
-    bias[n] = s1.b[n];
-    bias[G::NP + n] = s2.b[n];
-    bias[2 * G::NP + n] = nw->h_res_b[blk][n];
+  // bias rows [hi, lo] (k = 0, 1) of the three GEMMs and the constant "ones" A operand
+  auto put_bias = [&](uint32_t off, const float* bv) {
+    for (int n = 0; n < G::COUT; ++n) {
+      const __half hi = __float2half_rn(bv[n]);
+      const __half lo = __float2half_rn(bv[n] - __half2float(hi));
+      w[(off + (uint32_t)(n / 8) * 128 + (n % 8) * 16) / 2] = hi;
+      w[(off + (uint32_t)(n / 8) * 128 + (n % 8) * 16) / 2 + 1] = lo;
+    }
+  };
+  put_bias(G::OFF_WB1, s1.b.data());
+  put_bias(G::OFF_WB2, s2.b.data());
+  put_bias(G::OFF_WBR, nw->h_res_b[blk].data());
+  for (int r = 0; r < 8; ++r) {
+    w[(G::OFF_ONES + r * 16) / 2] = __float2half_rn(1.f);
+    w[(G::OFF_ONES + r * 16) / 2 + 1] = __float2half_rn(1.f);
   }
   void* p = nullptr;
   ORCAI_CUDA(c, cudaMalloc(&p, G::W_BYTES));
   nw->allocs.push_back(p);
   ORCAI_CUDA(c, cudaMemcpy(p, w.data(), G::W_BYTES, cudaMemcpyHostToDevice));
   nw->fb_w[blk] = p;
-  ORCAI_CHECK(net_upload(c, bias, &nw->fb_bias[blk]));
   ORCAI_CUDA(c, cudaFuncSetAttribute(fused::fused_block_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
   return ORCAI_OK;
 }
@@ -526,15 +537,46 @@ int prepare_fused(Ctx* c) {
   return ORCAI_OK;
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda)
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(p);
+  }();
+  return fn;
+}
+
+// rank-5 map over a (n, h, w, chunks, 8) fp16 NHWC tensor; box = {8 ch, 1 chunk, box_w, box_h, 1 snippet}
+int make_act_map(Ctx* c, CUtensorMap* map, const __half* base, long long n, int h, int w, int cpitch, int box_w, int box_h) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) ORCAI_FAIL(c, ORCAI_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t dims[5] = {8, (cuuint64_t)(cpitch / 8), (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  const cuuint64_t strides[4] = {16, (cuuint64_t)cpitch * 2, (cuuint64_t)w * cpitch * 2, (cuuint64_t)h * w * cpitch * 2};
+  const cuuint32_t box[5] = {8, 1, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<__half*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) ORCAI_FAIL(c, ORCAI_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for tensor (%lld, %d, %d, %d)", (int)r, n, h, w, cpitch);
+  return ORCAI_OK;
+}
+
 template <class G>
 int run_fused_block(Ctx* c, int blk, const __half* xr, const __half* xs, __half* yr, __half* ys, long long m, int Himg, int Wimg) {
   NetWeights* nw = c->net;
-  const int Wo = (Wimg + 1) / 2;
+  const int Ho = Himg / 2, Wo = (Wimg + 1) / 2;
   const int n_strips = (Wo + G::CP - 1) / G::CP;
   const long long items = m * n_strips;
   const long long grid = std::min<long long>(items, (long long)c->sm_count * G::CTAS);
-  fused::fused_block_kernel<G><<<(unsigned)grid, G::NTHREADS, G::SMEM, c->stream>>>(xr, xs, yr, ys, Himg, Wimg, n_strips, items,
-                                                                           static_cast<const unsigned char*>(nw->fb_w[blk]), nw->fb_bias[blk]);
+  CUtensorMap tmx, tmr;
+  ORCAI_CHECK(make_act_map(c, &tmx, xr, m, Himg, Wimg, G::ICP, G::WP, G::S + 2));
+  ORCAI_CHECK(make_act_map(c, &tmr, xs, m, Ho, Wo, G::ICP, G::CP, G::S / 2));
+  fused::fused_block_kernel<G><<<(unsigned)grid, G::NTHREADS, G::SMEM, c->stream>>>(tmx, tmr, yr, ys, Himg, Wimg, n_strips, items,
+                                                                                   static_cast<const unsigned char*>(nw->fb_w[blk]));
   c->launches++;
   ORCAI_CUDA(c, cudaGetLastError());
   return ORCAI_OK;
