@@ -54,7 +54,7 @@ struct NetWeights {
   // last debug buffer: kind 0 f32, 1 fp16, 2 bf16 ; NHWC with channel pitch dbg_pitch
   const void* dbg_ptr = nullptr; int dbg_kind = 0; long long dbg_n = 0; int dbg_h = 0, dbg_w = 0, dbg_c = 0, dbg_pitch = 0;
   // folded fp32 weights kept on the host for building the tensor-core operands
-  std::vector<float> h_conv0_w, h_conv0_b;
+  std::vector<float> h_conv0_w, h_conv0_b, h_conv0_pack;
   struct HostSep { std::vector<float> dw, pw, b; int ci = 0, co = 0; };
   HostSep h_sep1[kMaxBlocks], h_sep2[kMaxBlocks], h_fin;
 };

@@ -33,6 +33,9 @@
 //     s1_full[t]  workers -> issuer   S1 tile t (and the carried rows) written
 //     bar2[t]     issuer  -> workers  accumulator tile t of the second convolution is complete
 //     barR[2]     issuer  -> workers  residual accumulator (double buffered across steps)
+//     pool_done   workers -> issuer   the pooling epilogue has read its residual accumulator (it may be overwritten)
+// Worker order inside step g:  drain conv 1 (g) -> pool + store step g-1 (while the tensor pipe runs conv 2 of g)
+//                              -> drain conv 2 (g) -> carry rows;  conv 1 of g+1 is already in flight by then.
 #pragma once
 
 namespace fused {
@@ -78,8 +81,8 @@ struct FB {
   static constexpr uint32_t OFF_S1 = OFF_X + XCH * LBO_X;
   static constexpr uint32_t OFF_S2 = OFF_S1 + MCH * LBO_S1;
   static constexpr uint32_t OFF_BAR = OFF_S2 + NG * LBO_S2;
-  // barriers: bar1[N1] bar2[N2] barR[2] s1_full[N1] x_full
-  static constexpr int B_1 = 0, B_2 = N1, B_R = N1 + N2, B_S1 = N1 + N2 + 2, B_X = 2 * N1 + N2 + 2, NBAR = 2 * N1 + N2 + 3;
+  // barriers: bar1[N1] bar2[N2] barR[2] s1_full[N1] pool_done x_full
+  static constexpr int B_1 = 0, B_2 = N1, B_R = N1 + N2, B_S1 = N1 + N2 + 2, B_P = 2 * N1 + N2 + 2, B_X = B_P + 1, NBAR = B_X + 1;
   static constexpr uint32_t SMEM = OFF_BAR + NBAR * 8 + 16;
   static constexpr uint32_t TX_BYTES = XG * ((S + 2) * WP + (S / 2) * CP) * 16;   // bytes one step's TMA loads deliver
   static constexpr int COL_R = 0, COL_1 = 2 * NP, COL_2 = 2 * NP + N1 * NP;
@@ -179,7 +182,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   for (int i = tid + G::W_BYTES / 16; i < (int)(G::OFF_BAR / 16); i += G::NTHREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
   if (tid == 0) {
     for (int i = 0; i < G::B_S1; ++i) mbar_init(&bars[i], 1);                 // tcgen05.commit arrivals
-    for (int i = G::B_S1; i < G::B_X; ++i) mbar_init(&bars[i], G::NEW);        // one arrival per worker warp
+    for (int i = G::B_S1; i < G::B_X; ++i) mbar_init(&bars[i], G::NEW);        // one arrival per worker warp (s1_full, pool_done)
     mbar_init(&bars[G::B_X], 1);                                               // producer's arrive.expect_tx
     fence_mbar_init();
   }
@@ -284,6 +287,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
           __syncwarp();
         }
         if (g + 1 < total_steps) {
+          if (g >= 1) mbar_wait(&bars[G::B_P], par ^ 1);   // pooling of step g-1 has read the residual buffer step g+1 reuses
           mbar_wait(&bars[G::B_X], par ^ 1);
           tc_fence_after();
           issue_first(g + 1);
@@ -306,7 +310,51 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
 #pragma unroll
     for (int t = 0; t < G::N2; ++t) { const int p = G::P2_0 + 128 * t + row; y2[t] = p / G::WP; c2[t] = p - y2[t] * G::WP; }
 
+    // pooling epilogue of global step gp: max-pool (3,2)/2 + residual add (+ ReLU) -> global
+    auto pool_store = [&](long long gp, long long pb, int pwo0, int pa) {
+      mbar_wait(&bars[G::B_R + (int)(gp & 1)], (uint32_t)((gp >> 1) & 1));
+      tc_fence_after();
+      if (has0) {
+        float r[16];
+        tmem_ld16f(lane_addr + G::COL_R + (uint32_t)(gp & 1) * G::NP + g0 * 8, r);
+        const int ho = (pa >> 1) + q_i, wo = pwo0 + q_j;
+        if (row < G::RQ && ho >= 0 && ho < Ho && wo < Wo) {
+          const uint32_t p00 = (uint32_t)((2 * q_i) * G::WP + 2 + 2 * q_j);
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            if (u == 1 && !has1) break;
+            const int gg = g0 + u;
+            const unsigned char* s2 = smem + G::OFF_S2 + gg * G::LBO_S2 + p00 * 16;
+            uint4 m = *reinterpret_cast<const uint4*>(s2);
+            m = hmax8(m, *reinterpret_cast<const uint4*>(s2 + 16));
+            m = hmax8(m, *reinterpret_cast<const uint4*>(s2 + G::WP * 16));
+            m = hmax8(m, *reinterpret_cast<const uint4*>(s2 + G::WP * 16 + 16));
+            m = hmax8(m, *reinterpret_cast<const uint4*>(s2 + 2 * G::WP * 16));
+            m = hmax8(m, *reinterpret_cast<const uint4*>(s2 + 2 * G::WP * 16 + 16));
+            const __half2* mh = reinterpret_cast<const __half2*>(&m);
+            float y[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float2 f = __half22float2(mh[i]);
+              y[2 * i] = f.x + r[8 * u + 2 * i];
+              y[2 * i + 1] = f.y + r[8 * u + 2 * i + 1];
+            }
+            const uint4 yp = pack8h(y);
+            *reinterpret_cast<uint4*>(Yr + (((size_t)pb * Ho + ho) * Wo + wo) * G::OCP + gg * 8) = G::RELU_OUT ? relu8h(yp) : yp;
+            if (Ysub != nullptr && !(ho & 1) && !(wo & 1))
+              *reinterpret_cast<uint4*>(Ysub + (((size_t)pb * Hs + (ho >> 1)) * Ws + (wo >> 1)) * G::OCP + gg * 8) = yp;
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[G::B_P]);
+    };
+
     long long g = 0;
+    long long prev_b = 0;
+    int prev_wo0 = 0, prev_a = 0;
+    bool prev_carry = false;
     for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
       const long long b = item / n_strips;
       const int strip = (int)(item - b * n_strips);
@@ -337,6 +385,19 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
           __syncwarp();
           if (lane == 0) mbar_arrive(&bars[G::B_S1 + t]);
         }
+        // ---- previous step: pool + store while the tensor pipe runs this step's second convolution ----
+        if (g > 0) {
+          pool_store(g - 1, prev_b, prev_wo0, prev_a);
+          worker_sync<G::NWORK>();   // pooling has finished reading S2
+          if (prev_carry) {
+            for (int i = tid; i < G::NG * G::WP; i += G::NWORK) {
+              const int gq = i / G::WP, px = i - gq * G::WP;
+              unsigned char* p = smem + G::OFF_S2 + gq * G::LBO_S2 + px * 16;
+              *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(p + G::S * G::WP * 16);
+            }
+            worker_sync<G::NWORK>();  // carried S2 row in place before epilogue 2 overwrites its source row
+          }
+        }
         // ---- epilogue 2: -inf outside the image (TF "same" max-pool padding) -> S2 ----
 #pragma unroll
         for (int t = 0; t < G::N2; ++t) {
@@ -357,62 +418,21 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
           }
         }
         tc_fence_before();
-        worker_sync<G::NWORK>();   // S2 of this step is complete
-        // ---- max-pool (3,2)/2 + residual add (+ ReLU) -> global ----
-        mbar_wait(&bars[G::B_R + (int)(g & 1)], (uint32_t)((g >> 1) & 1));
-        tc_fence_after();
-        if (has0) {
-          float r[16];
-          tmem_ld16f(lane_addr + G::COL_R + (uint32_t)(g & 1) * G::NP + g0 * 8, r);
-          const int ho = (a >> 1) + q_i, wo = wo0 + q_j;
-          if (row < G::RQ && ho >= 0 && ho < Ho && wo < Wo) {
-            const uint32_t p00 = (uint32_t)((2 * q_i) * G::WP + 2 + 2 * q_j);
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-              if (u == 1 && !has1) break;
-              const int gg = g0 + u;
-              const unsigned char* s2 = smem + G::OFF_S2 + gg * G::LBO_S2 + p00 * 16;
-              uint4 m = *reinterpret_cast<const uint4*>(s2);
-              m = hmax8(m, *reinterpret_cast<const uint4*>(s2 + 16));
-              m = hmax8(m, *reinterpret_cast<const uint4*>(s2 + G::WP * 16));
-              m = hmax8(m, *reinterpret_cast<const uint4*>(s2 + G::WP * 16 + 16));
-              m = hmax8(m, *reinterpret_cast<const uint4*>(s2 + 2 * G::WP * 16));
-              m = hmax8(m, *reinterpret_cast<const uint4*>(s2 + 2 * G::WP * 16 + 16));
-              const __half2* mh = reinterpret_cast<const __half2*>(&m);
-              float y[8];
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const float2 f = __half22float2(mh[i]);
-                y[2 * i] = f.x + r[8 * u + 2 * i];
-                y[2 * i + 1] = f.y + r[8 * u + 2 * i + 1];
-              }
-              const uint4 yp = pack8h(y);
-              *reinterpret_cast<uint4*>(Yr + (((size_t)b * Ho + ho) * Wo + wo) * G::OCP + gg * 8) = G::RELU_OUT ? relu8h(yp) : yp;
-              if (Ysub != nullptr && !(ho & 1) && !(wo & 1))
-                *reinterpret_cast<uint4*>(Ysub + (((size_t)b * Hs + (ho >> 1)) * Ws + (wo >> 1)) * G::OCP + gg * 8) = yp;
-            }
-          }
-        }
-        tc_fence_before();
-        worker_sync<G::NWORK>();   // pooling has finished reading S2
-        // ---- carry the overlap rows into the next step (rows above the next strip's first row are zero) ----
+        worker_sync<G::NWORK>();   // every worker has seen the second convolution complete: S1 is free, S2 is written
+        // ---- carry the S1 overlap rows into the next step (rows above the next strip's first row are zero) ----
+        const bool carry = step + 1 < n_steps;
         if (g + 1 < total_steps) {
-          const bool carry = step + 1 < n_steps;
           for (int i = tid; i < G::NG * 2 * G::WP; i += G::NWORK) {
             const int gq = i / (2 * G::WP), px = i - gq * 2 * G::WP;
             unsigned char* p = smem + G::OFF_S1 + gq * G::LBO_S1 + px * 16;
             *reinterpret_cast<uint4*>(p) = carry ? *reinterpret_cast<const uint4*>(p + G::S * G::WP * 16) : make_uint4(0, 0, 0, 0);
           }
-          if (carry)
-            for (int i = tid; i < G::NG * G::WP; i += G::NWORK) {
-              const int gq = i / G::WP, px = i - gq * G::WP;
-              unsigned char* p = smem + G::OFF_S2 + gq * G::LBO_S2 + px * 16;
-              *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(p + G::S * G::WP * 16);
-            }
           worker_sync<G::NWORK>();   // carried rows in place before epilogue 1 overwrites their source rows
         }
+        prev_b = b; prev_wo0 = wo0; prev_a = a; prev_carry = carry;
       }
     }
+    if (g > 0) pool_store(g - 1, prev_b, prev_wo0, prev_a);
   }
   tc_fence_before();
   __syncthreads();

@@ -312,6 +312,68 @@ pool_res_tc_kernel(const H* __restrict__ t4, const H* __restrict__ prev, H* __re
 #include "net_fused.cuh"
 
 // ------------------------------------------------------------------------------------------------
+// entry convolution for the fused path: fp32 CUDA-core math (K = 9 is no tensor-core shape), normalise-on-load from the
+// raw dB buffer, folded BatchNorm + ReLU, fp16 NHWC output plus the even-position copy the first residual 1x1/2 reads.
+// Weights sit in constant memory: every FFMA takes its weight as a constant-bank operand, no load instructions.
+// ------------------------------------------------------------------------------------------------
+__constant__ float c_conv0[9 * 16 + 16];   // [tap][16] (BatchNorm folded), then bias[16]
+
+constexpr int kC0TH = 8, kC0TW = 32;
+
+__global__ void __launch_bounds__(256)
+conv0_direct_kernel(const float* __restrict__ in, int mode, long long first, int shift, int in_ld, int Himg, int Wimg,
+                    const SelectState* __restrict__ st, __half* __restrict__ out, __half* __restrict__ out_sub,
+                    int tiles_w, int tiles_h) {
+  __shared__ float s_x[kC0TH + 2][kC0TW + 2];
+  const int tid = threadIdx.x, ty = tid >> 5, tx = tid & 31;
+  const int tiles_per = tiles_w * tiles_h;
+  const long long b = blockIdx.x / tiles_per;
+  const int tr = (int)(blockIdx.x - b * tiles_per);
+  const int h0 = (tr / tiles_w) * kC0TH, w0 = (tr % tiles_w) * kC0TW;
+  float db_ref = 0.f, lo = 0.f, hi = 1.f, range = 1.f;
+  if (mode == 0) { db_ref = st->db_ref; lo = st->lo; hi = st->hi; range = hi - lo; }
+  const long long row0 = (mode == 0) ? (first + b) * shift : b * (long long)Himg;
+  for (int i = tid; i < (kC0TH + 2) * (kC0TW + 2); i += 256) {
+    const int r = i / (kC0TW + 2), cc = i - r * (kC0TW + 2);
+    const int hh = h0 + r - 1, ww = w0 + cc - 1;
+    float v = 0.f;
+    if (hh >= 0 && hh < Himg && ww >= 0 && ww < Wimg) {
+      v = in[(size_t)(row0 + hh) * in_ld + ww];
+      if (mode == 0) {
+        v = fmaxf(v - db_ref, -kTopDbF);
+        v = __fdiv_rn(fminf(fmaxf(v, lo), hi) - lo, range);
+      }
+    }
+    s_x[r][cc] = v;
+  }
+  __syncthreads();
+  const int hh = h0 + ty, ww = w0 + tx;
+  if (hh >= Himg || ww >= Wimg) return;
+  float x[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) x[t] = s_x[ty + t / 3][tx + t % 3];
+  float acc[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) acc[c] = c_conv0[144 + c];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc[c] = fmaf(x[t], c_conv0[t * 16 + c], acc[c]);
+#pragma unroll
+  for (int c = 0; c < 16; ++c) acc[c] = fmaxf(acc[c], 0.f);
+  const uint4 v0 = fused::pack8h(acc), v1 = fused::pack8h(acc + 8);
+  __half* o = out + (((size_t)b * Himg + hh) * Wimg + ww) * 16;
+  reinterpret_cast<uint4*>(o)[0] = v0;
+  reinterpret_cast<uint4*>(o)[1] = v1;
+  if (!(hh & 1) && !(ww & 1)) {
+    __half* os = out_sub + (((size_t)b * (Himg >> 1) + (hh >> 1)) * ((Wimg + 1) >> 1) + (ww >> 1)) * 16;
+    reinterpret_cast<uint4*>(os)[0] = v0;
+    reinterpret_cast<uint4*>(os)[1] = v1;
+  }
+}
+
+
+// ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
 template <typename H> H host_cvt(float x);
@@ -615,6 +677,12 @@ int forward_fused(Ctx* c, const float* d_in, int input_mode, int64_t first, int6
   nw->mark_i = 0;
   nw->dbg_ptr = nullptr;
   const int stop = nw->debug_stop;
+  {  // constant memory is per device, not per context: refresh it stream-ordered before every forward
+    nw->h_conv0_pack.resize(160);
+    memcpy(nw->h_conv0_pack.data(), nw->h_conv0_w.data(), 144 * sizeof(float));
+    memcpy(nw->h_conv0_pack.data() + 144, nw->h_conv0_b.data(), 16 * sizeof(float));
+    ORCAI_CUDA(c, cudaMemcpyToSymbolAsync(c_conv0, nw->h_conv0_pack.data(), 160 * sizeof(float), 0, cudaMemcpyHostToDevice, c->stream));
+  }
 
   for (int64_t s0 = 0; s0 < n; s0 += chunk) {
     const long long m = std::min<long long>(chunk, n - s0);
@@ -622,13 +690,10 @@ int forward_fused(Ctx* c, const float* d_in, int input_mode, int64_t first, int6
     if (mk) nw->marked_snippets = m;
     net_mark(c, mk);
     {
-      const int tiles_w = (Wf + kTileW - 1) / kTileW, tiles_h = (Himg + kTileH - 1) / kTileH;
-      const long long total = m * tiles_w * tiles_h;
-      const long long grid = std::min<long long>(total, (long long)c->sm_count * 8);
+      const int tiles_w = (Wf + kC0TW - 1) / kC0TW, tiles_h = (Himg + kC0TH - 1) / kC0TH;
       const float* src = (input_mode == 0) ? d_in : d_in + (size_t)s0 * Himg * Wf;
-      conv0_tc_kernel<H><<<(unsigned)grid, 128, 0, c->stream>>>(src, input_mode, first + s0, shift, input_mode == 0 ? kRawLd : Wf, Himg, Wf,
-                                                                 c->d_sel, static_cast<const H*>(nw->tc_conv0_w[0]), nw->conv0_b, act[0], acts[0],
-                                                                 m, tiles_w, tiles_h);
+      conv0_direct_kernel<<<(unsigned)(m * tiles_w * tiles_h), 256, 0, c->stream>>>(src, input_mode, first + s0, shift, input_mode == 0 ? kRawLd : Wf,
+                                                                                   Himg, Wf, c->d_sel, act[0], acts[0], tiles_w, tiles_h);
       c->launches++;
       ORCAI_CUDA(c, cudaGetLastError());
     }
