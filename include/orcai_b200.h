@@ -93,6 +93,12 @@ int orcai_load_weights(orcai_ctx* ctx, const char* const* names, const float* co
 int64_t orcai_num_frames(int64_t n_samples, int32_t hop);
 /* Upload mono PCM (host memory) and keep it resident as the context's current recording. */
 int orcai_upload_pcm(orcai_ctx* ctx, const void* pcm_host, int32_t dtype, int64_t n_samples);
+/* Pipelining across recordings (recording tables: predict.py:733-755 loops over rows): start the host->device copy of
+ * the NEXT recording into a second device buffer on a copy stream and return at once (pin `pcm_host` for a truly
+ * asynchronous copy; it must stay valid until orcai_swap_pcm).  orcai_swap_pcm makes that recording the resident one
+ * (the compute stream waits for the copy, the host does not).  Usage: prefetch(k+1); predict_resident(k); swap. */
+int orcai_prefetch_pcm(orcai_ctx* ctx, const void* pcm_host, int32_t dtype, int64_t n_samples);
+int orcai_swap_pcm(orcai_ctx* ctx);
 /* STFT -> dB -> crop -> global max -> exact percentiles on the resident recording.  With
  * `normalise` != 0 also materialises the normalised (T, n_freq) float32 spectrogram on the device. */
 int orcai_spectrogram_resident(orcai_ctx* ctx, int32_t normalise, orcai_spec_stats* stats);

@@ -107,6 +107,8 @@ _SIGNATURES = {
     "orcai_predict_resident": (C.c_int, [_P, C.c_double, C.POINTER(SpecStats), _P, _P, _P, _P, _P, C.c_int64, C.POINTER(C.c_int64)]),
     "orcai_predict_pcm": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_double, C.POINTER(SpecStats), _P, _P, _P, _P, _P, C.c_int64, C.POINTER(C.c_int64)]),
     "orcai_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),
+    "orcai_prefetch_pcm": (C.c_int, [_P, _P, C.c_int32, C.c_int64]),
+    "orcai_swap_pcm": (C.c_int, [_P]),
     "orcai_debug_read": (C.c_int, [_P, _P, C.c_int64, C.POINTER(C.c_int64)]),
 }
 
@@ -252,6 +254,35 @@ class Context:
     def upload_pcm(self, pcm: np.ndarray):
         pcm, dt = self._pcm(pcm)
         self._check(self.lib.orcai_upload_pcm(self._h, _ptr(pcm), dt, pcm.size))
+
+    def prefetch_pcm(self, pcm: np.ndarray):
+        """Start the host->device copy of the NEXT recording on the copy stream (returns at once; keep `pcm` alive)."""
+        pcm, dt = self._pcm(pcm)
+        self._prefetched = pcm
+        self._check(self.lib.orcai_prefetch_pcm(self._h, _ptr(pcm), dt, pcm.size))
+
+    def swap_pcm(self):
+        """Make the prefetched recording the resident one (the compute stream waits for the copy, the host does not)."""
+        self._check(self.lib.orcai_swap_pcm(self._h))
+
+    def predict_stream(self, recordings, threshold: float = 0.5, want_agg: bool = True):
+        """Annotate a sequence of PCM arrays; the upload of recording k+1 overlaps the annotation of recording k.
+
+        Yields what predict_pcm returns, in order.  (Recording tables: predict.py:733-755.)
+        """
+        it = iter(recordings)
+        try:
+            cur = next(it)
+        except StopIteration:
+            return
+        self.prefetch_pcm(cur)
+        while cur is not None:
+            self.swap_pcm()
+            nxt = next(it, None)
+            if nxt is not None:
+                self.prefetch_pcm(nxt)
+            yield self.predict_pcm(cur, threshold=threshold, want_agg=want_agg, resident=True)
+            cur = nxt
 
     def spectrogram_resident(self, normalise: bool = True) -> SpecStats:
         st = SpecStats()

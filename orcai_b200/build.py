@@ -20,7 +20,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 LIB = PKG / "liborcai_b200.so"
 OBJ = PKG / "csrc" / "_obj"
-SOURCES = ["abi.cu", "stft.cu", "select.cu", "post.cu", "net.cu", "net_tc.cu"]
+SOURCES = ["abi.cu", "stft.cu", "select.cu", "post.cu", "net.cu", "net_tc.cu", "net_lstm_tc.cu"]
 NVCC_FLAGS = [
     "-O3",
     "-std=c++17",

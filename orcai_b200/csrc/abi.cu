@@ -156,6 +156,8 @@ int orcai_create(int device, const orcai_params* p, orcai_ctx** out) {
   }
   c->sm_count = prop.multiProcessorCount;
   if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+  if ((e = cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail("cudaStreamCreate", e);
+  if ((e = cudaEventCreateWithFlags(&c->ev_prefetch, cudaEventDisableTiming)) != cudaSuccess) return fail("cudaEventCreate", e);
   for (auto& ev : c->ev)
     if ((e = cudaEventCreate(&ev)) != cudaSuccess) return fail("cudaEventCreate", e);
   if (stft_upload_tables(c) != ORCAI_OK) { g_create_error = c->err; orcai_destroy(c); return ORCAI_ERR_CUDA; }
@@ -174,7 +176,11 @@ void orcai_destroy(orcai_ctx* c) {
   for (auto& t : c->d_tables) if (t) cudaFree(t);
   for (auto& t : c->d_tables64) if (t) cudaFree(t);
   if (c->d_sel) cudaFree(c->d_sel);
+  if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
   if (c->d_pcm) cudaFree(c->d_pcm);
+  if (c->d_pcm_next) cudaFree(c->d_pcm_next);
+  if (c->ev_prefetch) cudaEventDestroy(c->ev_prefetch);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   if (c->d_raw) cudaFree(c->d_raw);
   if (c->d_spec) cudaFree(c->d_spec);
   if (c->d_preds) cudaFree(c->d_preds);
@@ -196,6 +202,7 @@ int orcai_get_timings(const orcai_ctx* c, orcai_timings* out) {
 int orcai_set_option(orcai_ctx* c, const char* key, int64_t value) {
   if (!c || !key) return ORCAI_ERR_ARG;
   if (!strcmp(key, "chunk")) return net_set_chunk(c, (int)value);
+  if (!strcmp(key, "tail_path")) return net_set_tail_path(c, (int)value);
   if (!strcmp(key, "net_path")) {
     if (value < 0 || value > 3)
       ORCAI_FAIL(c, ORCAI_ERR_ARG, "net_path must be 0 (fp32), 1 (fp16 tensor cores), 2 (bf16 tensor cores) or 3 (fp16 fused residual blocks)");
@@ -233,6 +240,38 @@ int orcai_upload_pcm(orcai_ctx* c, const void* pcm_host, int32_t dtype, int64_t 
   c->tm.h2d_ms = elapsed(c, EV_START, EV_H2D);
   c->pcm_dtype = dtype;
   c->n_samples = n_samples;
+  c->have_stats = false;
+  c->T = 0;
+  return ORCAI_OK;
+}
+
+int orcai_prefetch_pcm(orcai_ctx* c, const void* pcm_host, int32_t dtype, int64_t n_samples) {
+  if (!c) return ORCAI_ERR_ARG;
+  if (dtype != ORCAI_PCM_I16 && dtype != ORCAI_PCM_F32) ORCAI_FAIL(c, ORCAI_ERR_ARG, "unknown pcm dtype %d", dtype);
+  if (n_samples < 0 || (n_samples > 0 && !pcm_host)) ORCAI_FAIL(c, ORCAI_ERR_ARG, "bad pcm buffer");
+  ORCAI_CUDA(c, cudaSetDevice(c->device));
+  const size_t esz = dtype == ORCAI_PCM_I16 ? 2 : 4;
+  // a pending prefetch into this buffer must have landed before it is reallocated or overwritten
+  ORCAI_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+  ORCAI_CHECK(ensure_device_buffer(c, &c->d_pcm_next, &c->pcm_next_cap, (size_t)n_samples * esz + 16));
+  if (n_samples) ORCAI_CUDA(c, cudaMemcpyAsync(c->d_pcm_next, pcm_host, (size_t)n_samples * esz, cudaMemcpyHostToDevice, c->copy_stream));
+  ORCAI_CUDA(c, cudaEventRecord(c->ev_prefetch, c->copy_stream));
+  c->pcm_next_dtype = dtype;
+  c->n_samples_next = n_samples;
+  return ORCAI_OK;
+}
+
+int orcai_swap_pcm(orcai_ctx* c) {
+  if (!c) return ORCAI_ERR_ARG;
+  if (c->n_samples_next < 0) ORCAI_FAIL(c, ORCAI_ERR_STATE, "no prefetched recording (orcai_prefetch_pcm)");
+  ORCAI_CUDA(c, cudaSetDevice(c->device));
+  // the previous recording's kernels have finished (every predict call synchronises), so its buffer may be recycled
+  ORCAI_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_prefetch, 0));
+  std::swap(c->d_pcm, c->d_pcm_next);
+  std::swap(c->pcm_cap, c->pcm_next_cap);
+  c->pcm_dtype = c->pcm_next_dtype;
+  c->n_samples = c->n_samples_next;
+  c->n_samples_next = -1;
   c->have_stats = false;
   c->T = 0;
   return ORCAI_OK;

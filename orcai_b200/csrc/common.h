@@ -46,6 +46,9 @@ struct Ctx {
   SelectState* d_sel = nullptr;
   // current recording
   void* d_pcm = nullptr;  size_t pcm_cap = 0;  int pcm_dtype = 0;  int64_t n_samples = 0;
+  // next recording, uploaded on the copy stream while the current one is being annotated (orcai_prefetch_pcm)
+  void* d_pcm_next = nullptr;  size_t pcm_next_cap = 0;  int pcm_next_dtype = 0;  int64_t n_samples_next = -1;
+  cudaStream_t copy_stream = nullptr;  cudaEvent_t ev_prefetch = nullptr;
   float* d_raw = nullptr; size_t raw_cap = 0;  int64_t T = 0;      // raw dB (T, kRawLd)
   float* d_spec = nullptr; size_t spec_cap = 0;                    // normalised (T, n_freq) compact
   bool have_stats = false;
@@ -105,6 +108,7 @@ void net_destroy(Ctx* c);
 int net_set_chunk(Ctx* c, int chunk);
 void net_collect_stage_times(Ctx* c);
 int net_set_path(Ctx* c, int path);
+int net_set_tail_path(Ctx* c, int path);
 int net_set_debug_stop(Ctx* c, int stage);
 int net_debug_read(Ctx* c, float* out_host, int64_t capacity, int64_t* dims_out);
 int net_load_weights(Ctx* c, const char* const* names, const float* const* data, const int64_t* sizes, int n);

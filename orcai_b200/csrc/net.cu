@@ -484,6 +484,12 @@ int net_set_path(Ctx* c, int path) {
   return ORCAI_OK;
 }
 
+int net_set_tail_path(Ctx* c, int path) {
+  if (path < 0 || path > 1) ORCAI_FAIL(c, ORCAI_ERR_ARG, "tail_path must be 0 (fp32) or 1 (tensor cores)");
+  c->net->tail_path = path;
+  return ORCAI_OK;
+}
+
 int net_set_debug_stop(Ctx* c, int stage) {
   c->net->debug_stop = stage;
   return ORCAI_OK;
@@ -537,6 +543,7 @@ int net_load_weights(Ctx* c, const char* const* names, const float* const* data,
   nw->loaded = false;
   nw->tc_ready[0] = nw->tc_ready[1] = false;
   nw->fused_ready = false;
+  nw->tail_tc_ready = false;
   const orcai_params& P = c->p;
   if (P.n_blocks != 4 || P.filters[0] != 30 || P.filters[1] != 40 || P.filters[2] != 50 || P.filters[3] != 60 ||
       P.kernel_size != 3 || P.lstm_units != 128)
@@ -595,6 +602,8 @@ int net_load_weights(Ctx* c, const char* const* names, const float* const* data,
       memcpy(&bih[(size_t)d * G], bb, G * sizeof(float));
       memcpy(&whh[(size_t)d * U * G], r, (size_t)U * G * sizeof(float));
     }
+    nw->h_lstm_wih[l] = wih;
+    nw->h_lstm_whh[l] = whh;
     ORCAI_CHECK(upload(c, wih, &nw->lstm_wih[l]));
     ORCAI_CHECK(upload(c, bih, &nw->lstm_bih[l]));
     ORCAI_CHECK(upload(c, whh, &nw->lstm_whh[l]));
@@ -606,7 +615,8 @@ int net_load_weights(Ctx* c, const char* const* names, const float* const* data,
     const float* b2 = ht.get("dense2/bias", nw->L);
     std::vector<double> s, t;
     if (!k1 || !b1 || !k2 || !b2 || !bn_fold(ht, "bn_dense", kDense, &s, &t)) return ORCAI_ERR_ARG;
-    ORCAI_CHECK(upload(c, std::vector<float>(k1, k1 + (size_t)2 * U * kDense), &nw->d1_w));
+    nw->h_d1_w.assign(k1, k1 + (size_t)2 * U * kDense);
+    ORCAI_CHECK(upload(c, nw->h_d1_w, &nw->d1_w));
     ORCAI_CHECK(upload(c, std::vector<float>(b1, b1 + kDense), &nw->d1_b));
     std::vector<float> w2((size_t)kDense * nw->L), bb2(nw->L);
     for (int o = 0; o < nw->L; ++o) {

@@ -1,5 +1,7 @@
 // orcai-V1 network state shared by the fp32 path (net.cu) and the tensor-core path (net_tc.cu).
 #pragma once
+#include <cuda_fp16.h>
+
 #include <vector>
 
 #include "common.h"
@@ -49,6 +51,13 @@ struct NetWeights {
   void* fb_w[kMaxBlocks] = {};
   float* fb_bias[kMaxBlocks] = {};
   int chunk_fused = 2048;
+  // tensor-core recurrent tail (net_lstm_tc.cu)
+  bool tail_tc_ready = false;
+  int tail_path = 1;          // fused path only: 1 = tensor-core LSTM / dense tail, 0 = fp32 CUDA-core tail
+  __half* tc_wih[2] = {};     // packed B blocks of the input projections [I][2*4U]
+  __half* tc_whh[2] = {};     // [2 directions][4U x U] canonical K-major
+  __half* tc_d1 = nullptr;    // Dense(128) B blocks
+  std::vector<float> h_lstm_wih[2], h_lstm_whh[2], h_d1_w;
   std::vector<float> h_res_w[kMaxBlocks], h_res_b[kMaxBlocks];
   int debug_stop = -1;        // stop the forward after this stage (debug reads), -1 = run everything
   // last debug buffer: kind 0 f32, 1 fp16, 2 bf16 ; NHWC with channel pitch dbg_pitch
@@ -67,6 +76,7 @@ inline void net_mark(Ctx* c, bool on) {
 // LSTM + dense tail on fp32 features (m, Tn, feat).  scratch: m*Tn*(2*4U + 2U + 2U + 128) floats.
 int net_tail_fp32(Ctx* c, const float* feat, float* scratch, long long m, float* d_preds_out, bool mark);
 int net_upload(Ctx* c, const std::vector<float>& v, float** dptr);
+int net_tail_tc(Ctx* c, const float* feat, float* scratch, long long m, float* d_preds_out, bool mark);
 int net_tc_prepare(Ctx* c, int fmt);
 int net_forward_tc(Ctx* c, const float* d_in, int input_mode, int64_t first, int64_t n, float* d_preds);
 

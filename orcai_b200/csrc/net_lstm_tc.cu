@@ -1,0 +1,443 @@
+// Recurrent tail of orcai-V1 on the tensor cores: 2 x Bidirectional(LSTM(128)) + Dense(128, relu) (+ BN, Dense(7, sigmoid)).
+//
+// Reference graph: src/orcAI/architectures.py:210-239 (gate order i, f, c, o; sigmoid recurrent activation; the backward
+// layer runs t = Tn-1 .. 0 and is written back in forward order; [forward | backward] concatenation).
+//
+//   gemm_tc_kernel      C[M, N] = act(A[M, K] * B[K, N] + bias) ; A fp32 or fp16 in HBM, staged as fp16 into the canonical
+//                       K-major no-swizzle UMMA layout by the worker warps, B pre-packed fp16 blocks fetched with one
+//                       cp.async.bulk per K-chunk, fp32 accumulation in TMEM, 2-stage mbarrier pipeline, dedicated issuer warp.
+//                       Used for the LSTM input projections (M = snippets*46, N = 1024) and Dense(128).
+//   lstm_rec_tc_kernel  the recurrence: per CTA R snippets x one direction; W_hh (128 x 512, fp16, 128 KB) stays in shared
+//                       memory, h_{t-1} is a 128 x 128 fp16 A operand rewritten every step, the 4 x 128 gate pre-activations
+//                       of a step are exactly the 512 TMEM columns; workers add the projected input (fp32, from HBM/L2), apply
+//                       the gates with fp32 state in registers and hand h_t back through shared memory.
+#include <algorithm>
+#include <cstring>
+
+#include "common.h"
+#include "net.h"
+#include "tc_common.cuh"
+
+namespace orcai {
+
+namespace {
+
+using namespace tc;
+
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+      "elect.sync rx|px, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, px;\n\t}"
+      : "=r"(pred)
+      :
+      : "memory");
+  return pred != 0;
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// contiguous global -> shared copy through the TMA unit, completion counted on an mbarrier
+__device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src), "r"(bytes),
+               "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld8f(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n\ttcgen05.wait::ld.sync.aligned;"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ uint4 pack8h(const float* v) {
+  uint4 r;
+  __half2* h = reinterpret_cast<__half2*>(&r);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+  return r;
+}
+
+// ------------------------------------------------------------------------------------------------
+// GEMM
+// ------------------------------------------------------------------------------------------------
+constexpr int kGM = 128, kGK = 64;   // rows per CTA, K per pipeline stage
+
+template <int BN>
+struct GemmSmem {
+  static constexpr uint32_t A_STAGE = kGM * kGK * 2, B_STAGE = BN * kGK * 2;
+  static constexpr uint32_t OFF_A = 0, OFF_B = 2 * A_STAGE, OFF_BAR = OFF_B + 2 * B_STAGE;
+  static constexpr uint32_t BYTES = OFF_BAR + 8 * 8 + 16;
+};
+
+__device__ __forceinline__ uint4 load8_as_half(const float* p, int valid) {   // valid: number of readable floats (multiple of 4)
+  float v[8];
+  const float4 a = valid >= 4 ? __ldg(reinterpret_cast<const float4*>(p)) : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 b = valid >= 8 ? __ldg(reinterpret_cast<const float4*>(p) + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  return pack8h(v);
+}
+__device__ __forceinline__ uint4 load8_as_half(const __half* p, int valid) {   // valid: 0 or >= 8
+  return valid >= 8 ? __ldg(reinterpret_cast<const uint4*>(p)) : make_uint4(0, 0, 0, 0);
+}
+
+// ACT: 0 none, 1 relu.  grid = (N / BN, ceil(M / 128)), block = 160 (4 worker warps + issuer warp)
+template <typename TA, int BN, int ACT>
+__global__ void __launch_bounds__(160, 2)
+gemm_tc_kernel(const TA* __restrict__ A, int lda, const __half* __restrict__ Bp, const float* __restrict__ bias,
+               float* __restrict__ C, int ldc, long long M, int K) {
+  using S = GemmSmem<BN>;
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);   // full_a[2] full_b[2] free[2] acc
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 7);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nkc = (K + kGK - 1) / kGK;
+  if (tid == 0) {
+    mbar_init(&bars[0], 4); mbar_init(&bars[1], 4);
+    mbar_init(&bars[2], 1); mbar_init(&bars[3], 1);
+    mbar_init(&bars[4], 1); mbar_init(&bars[5], 1);
+    mbar_init(&bars[6], 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  if (warp == 0) tmem_alloc<BN>(tslot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tslot;
+  const uint32_t sbase = smem_u32(smem);
+  const long long row0 = (long long)blockIdx.y * kGM;
+  const int nt = blockIdx.x;
+
+  if (warp == 4) {
+    constexpr uint32_t idesc = make_idesc_f16(128, BN, 0);
+    for (int kc = 0; kc < nkc; ++kc) {
+      const int s = kc & 1;
+      const uint32_t par = (uint32_t)((kc >> 1) & 1);
+      mbar_wait(&bars[0 + s], par);
+      mbar_wait(&bars[2 + s], par);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint64_t da = make_smem_desc(sbase + S::OFF_A + s * S::A_STAGE, kGM * 16, 128);
+        const uint64_t db = make_smem_desc(sbase + S::OFF_B + s * S::B_STAGE, 128, (kGK / 8) * 128);
+#pragma unroll
+        for (int ks = 0; ks < kGK / 16; ++ks)
+          mma_f16_ss(tmem, da + ((2 * ks * kGM * 16) >> 4), db + ((2 * ks * 128) >> 4), idesc, (kc | ks) != 0);
+        mma_commit(&bars[4 + s]);
+        if (kc == nkc - 1) mma_commit(&bars[6]);
+      }
+      __syncwarp();
+    }
+  } else {
+    const int row = tid;                        // 0..127: A row staged by this thread and accumulator row it drains
+    const bool row_ok = row0 + row < M;
+    const TA* arow = A + (size_t)(row_ok ? row0 + row : 0) * lda;
+    for (int kc = 0; kc < nkc; ++kc) {
+      const int s = kc & 1;
+      if (kc >= 2) mbar_wait(&bars[4 + s], (uint32_t)(((kc - 2) >> 1) & 1));   // the MMAs that read this stage are done
+      if (tid == 0) {
+        mbar_arrive_expect_tx(&bars[2 + s], S::B_STAGE);
+        bulk_copy_g2s(sbase + S::OFF_B + s * S::B_STAGE, Bp + ((size_t)nt * nkc + kc) * (S::B_STAGE / 2), S::B_STAGE, &bars[2 + s]);
+      }
+      unsigned char* dst = smem + S::OFF_A + s * S::A_STAGE + row * 16;
+#pragma unroll
+      for (int j = 0; j < kGK / 8; ++j) {
+        const int k0 = kc * kGK + j * 8;
+        const uint4 v = load8_as_half(arow + k0, row_ok ? K - k0 : 0);
+        *reinterpret_cast<uint4*>(dst + j * (kGM * 16)) = v;
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars[0 + s]);
+    }
+    mbar_wait(&bars[6], 0);
+    tc_fence_after();
+    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+    float* crow = C + (size_t)(row0 + row) * ldc + (size_t)nt * BN;
+#pragma unroll 2
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      float v[16];
+      tmem_ld16(lane_addr + c0, v);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        v[i] += __ldg(bias + nt * BN + c0 + i);
+        if (ACT == 1) v[i] = fmaxf(v[i], 0.f);
+      }
+      if (row_ok) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) reinterpret_cast<float4*>(crow + c0)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<BN>(tmem);
+}
+
+// ------------------------------------------------------------------------------------------------
+// LSTM recurrence
+// ------------------------------------------------------------------------------------------------
+constexpr int kU = 128, kG4 = 4 * kU;
+constexpr uint32_t kRecW = kG4 * kU * 2;             // 128 KB: W_hh^T as [n = gate*128 + unit][k] canonical, SBO = 16 chunks
+constexpr uint32_t kRecH = 128 * kU * 2;             // 32 KB: h as [k-chunk][row][8]
+constexpr uint32_t kRecSmem = kRecW + kRecH + 4 * 8 + 16;
+
+__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
+__device__ __forceinline__ float tanh_fast(float x) { return 2.f * __fdividef(1.f, 1.f + __expf(-2.f * x)) - 1.f; }
+
+// grid = (ceil(n / R), 2 directions), block = 17 warps: 16 workers (quad = w & 3 -> TMEM lanes, cg = w >> 2 -> 32 units) + issuer
+template <int R>
+__global__ void __launch_bounds__(544, 1)
+lstm_rec_tc_kernel(const float* __restrict__ xz, const __half* __restrict__ whh_pack, __half* __restrict__ hout, long long n, int Tn) {
+  static_assert(R == 32 || R == 64 || R == 128, "rows per CTA = whole TMEM lane quadrants");
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* s_h = smem + kRecW;   // W_hh occupies [0, kRecW)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kRecW + kRecH);   // w_full, z_ready, h_ready
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 3);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int dir = blockIdx.y;
+  const long long s0 = (long long)blockIdx.x * R;
+  constexpr int kActive = 4 * (R / 32);               // worker warps that own real rows
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 1);
+    mbar_init(&bars[2], kActive);
+    fence_mbar_init();
+  }
+  for (int i = tid; i < (int)(kRecH / 16); i += 544) reinterpret_cast<uint4*>(s_h)[i] = make_uint4(0, 0, 0, 0);
+  __syncwarp();
+  if (warp == 0) tmem_alloc<512>(tslot);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tslot;
+  const uint32_t sbase = smem_u32(smem);
+
+  if (warp == 16) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(&bars[0], kRecW);
+      // bulk copies are limited in size per instruction; 8 x 16 KB
+      for (int i = 0; i < 8; ++i)
+        bulk_copy_g2s(sbase + i * (kRecW / 8), reinterpret_cast<const unsigned char*>(whh_pack) + (size_t)dir * kRecW + (size_t)i * (kRecW / 8),
+                      kRecW / 8, &bars[0]);
+    }
+    __syncwarp();
+    mbar_wait(&bars[0], 0);
+    constexpr uint32_t idesc = make_idesc_f16(128, 256, 0);
+    const uint64_t dh = make_smem_desc(sbase + kRecW, 128 * 16, 128);
+    const uint64_t dw = make_smem_desc(sbase, 128, (kU / 8) * 128);
+    for (int ti = 1; ti < Tn; ++ti) {            // step 0 has h = 0: no recurrent term
+      mbar_wait(&bars[2], (uint32_t)((ti - 1) & 1));
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int nh = 0; nh < 2; ++nh)
+#pragma unroll
+          for (int ks = 0; ks < kU / 16; ++ks)
+            mma_f16_ss(tmem + nh * 256, dh + ((2 * ks * 128 * 16) >> 4), dw + ((nh * 32 * (kU / 8) * 128 + 2 * ks * 128) >> 4), idesc, ks != 0);
+        mma_commit(&bars[1]);
+      }
+      __syncwarp();
+    }
+  } else if ((warp & 3) < R / 32) {
+    const int quad = warp & 3, cg = warp >> 2;
+    const int row = quad * 32 + lane;
+    const long long s = s0 + row;
+    const bool ok = s < n;
+    const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
+    const int u0 = cg * 32;
+    float cst[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) cst[i] = 0.f;
+    for (int ti = 0; ti < Tn; ++ti) {
+      const int t = dir ? Tn - 1 - ti : ti;
+      const float* xrow = xz + ((size_t)(ok ? s : 0) * Tn + t) * (2 * kG4) + (size_t)dir * kG4 + u0;
+      __half* hrow = hout + ((size_t)(ok ? s : 0) * Tn + t) * (2 * kU) + (size_t)dir * kU + u0;
+      // first sub-chunk of the projected input is fetched before waiting for the tensor pipe
+      float4 xa[4][2];
+#pragma unroll
+      for (int gte = 0; gte < 4; ++gte) {
+        xa[gte][0] = __ldg(reinterpret_cast<const float4*>(xrow + gte * kU));
+        xa[gte][1] = __ldg(reinterpret_cast<const float4*>(xrow + gte * kU) + 1);
+      }
+      if (ti > 0) {
+        mbar_wait(&bars[1], (uint32_t)((ti - 1) & 1));
+        tc_fence_after();
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float4 xb[4][2];
+        if (j < 3) {
+#pragma unroll
+          for (int gte = 0; gte < 4; ++gte) {
+            xb[gte][0] = __ldg(reinterpret_cast<const float4*>(xrow + gte * kU + 8 * (j + 1)));
+            xb[gte][1] = __ldg(reinterpret_cast<const float4*>(xrow + gte * kU + 8 * (j + 1)) + 1);
+          }
+        }
+        float z[4][8];
+#pragma unroll
+        for (int gte = 0; gte < 4; ++gte) {
+          if (ti > 0) {
+            tmem_ld8f(lane_addr + gte * kU + u0 + 8 * j, z[gte]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) z[gte][i] = 0.f;
+          }
+          z[gte][0] += xa[gte][0].x; z[gte][1] += xa[gte][0].y; z[gte][2] += xa[gte][0].z; z[gte][3] += xa[gte][0].w;
+          z[gte][4] += xa[gte][1].x; z[gte][5] += xa[gte][1].y; z[gte][6] += xa[gte][1].z; z[gte][7] += xa[gte][1].w;
+        }
+        float h[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float ig = sigmoid_fast(z[0][i]), fg = sigmoid_fast(z[1][i]), gg = tanh_fast(z[2][i]), og = sigmoid_fast(z[3][i]);
+          const float cn = fg * cst[8 * j + i] + ig * gg;
+          cst[8 * j + i] = cn;
+          h[i] = og * tanh_fast(cn);
+        }
+        const uint4 hp = pack8h(h);
+        *reinterpret_cast<uint4*>(s_h + (size_t)((u0 >> 3) + j) * (128 * 16) + row * 16) = hp;
+        if (ok) *reinterpret_cast<uint4*>(hrow + 8 * j) = hp;
+        if (j < 3) {
+#pragma unroll
+          for (int gte = 0; gte < 4; ++gte) { xa[gte][0] = xb[gte][0]; xa[gte][1] = xb[gte][1]; }
+        }
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0 && ti + 1 < Tn) mbar_arrive(&bars[2]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+// Dense(7) + sigmoid on the Dense(128)+ReLU activations (BatchNorm folded into the weights): one warp per row
+__global__ void __launch_bounds__(256)
+dense_out_kernel(const float* __restrict__ d1, const float* __restrict__ w2, const float* __restrict__ b2, float* __restrict__ out,
+                 long long rows, int L) {
+  __shared__ float s_w[128 * 8];
+  for (int i = threadIdx.x; i < 128 * L; i += blockDim.x) s_w[i] = w2[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  for (long long r = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); r < rows; r += (long long)gridDim.x * 8) {
+    const float4 x = __ldg(reinterpret_cast<const float4*>(d1 + (size_t)r * 128) + lane);
+    for (int o = 0; o < L; ++o) {
+      float a = x.x * s_w[(4 * lane) * L + o] + x.y * s_w[(4 * lane + 1) * L + o] + x.z * s_w[(4 * lane + 2) * L + o] + x.w * s_w[(4 * lane + 3) * L + o];
+#pragma unroll
+      for (int d = 16; d > 0; d >>= 1) a += __shfl_xor_sync(0xffffffffu, a, d);
+      if (lane == 0) out[(size_t)r * L + o] = 1.f / (1.f + expf(-(a + b2[o])));
+    }
+  }
+}
+
+// ---- host side ----------------------------------------------------------------------------------
+// B operand blocks of gemm_tc_kernel: [n-tile][k-chunk][BN x 64] canonical K-major (SBO = 8 chunks)
+std::vector<__half> pack_gemm_b(const float* w, int K, int N, int BN) {   // w: [K][N] row-major (Keras kernel layout)
+  const int nkc = (K + kGK - 1) / kGK, ntiles = N / BN;
+  std::vector<__half> out((size_t)ntiles * nkc * BN * kGK, __float2half_rn(0.f));
+  for (int nt = 0; nt < ntiles; ++nt)
+    for (int kc = 0; kc < nkc; ++kc) {
+      __half* blk = out.data() + ((size_t)nt * nkc + kc) * BN * kGK;
+      for (int nn = 0; nn < BN; ++nn)
+        for (int kk = 0; kk < kGK; ++kk) {
+          const int k = kc * kGK + kk, n = nt * BN + nn;
+          if (k >= K) continue;
+          blk[((size_t)(nn / 8) * (kGK / 8) * 128 + (size_t)(kk / 8) * 128 + (nn % 8) * 16 + (kk % 8) * 2) / 2] = __float2half_rn(w[(size_t)k * N + n]);
+        }
+    }
+  return out;
+}
+
+int upload_half(Ctx* c, const std::vector<__half>& v, __half** out) {
+  void* p = nullptr;
+  ORCAI_CUDA(c, cudaMalloc(&p, v.size() * sizeof(__half)));
+  c->net->allocs.push_back(p);
+  ORCAI_CUDA(c, cudaMemcpy(p, v.data(), v.size() * sizeof(__half), cudaMemcpyHostToDevice));
+  *out = static_cast<__half*>(p);
+  return ORCAI_OK;
+}
+
+template <typename TA, int BN, int ACT>
+int run_gemm_tc(Ctx* c, const TA* A, int lda, const __half* Bp, const float* bias, float* C, int ldc, long long M, int N, int K) {
+  using S = GemmSmem<BN>;
+  static bool attr = false;
+  if (!attr) {
+    ORCAI_CUDA(c, cudaFuncSetAttribute(gemm_tc_kernel<TA, BN, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::BYTES));
+    attr = true;
+  }
+  dim3 grid((unsigned)(N / BN), (unsigned)((M + kGM - 1) / kGM));
+  gemm_tc_kernel<TA, BN, ACT><<<grid, 160, S::BYTES, c->stream>>>(A, lda, Bp, bias, C, ldc, M, K);
+  c->launches++;
+  ORCAI_CUDA(c, cudaGetLastError());
+  return ORCAI_OK;
+}
+
+}  // namespace
+
+int net_tail_tc_prepare(Ctx* c) {
+  NetWeights* nw = c->net;
+  if (nw->tail_tc_ready) return ORCAI_OK;
+  const int U = nw->U, G = 4 * U;
+  if (U != kU) ORCAI_FAIL(c, ORCAI_ERR_ARG, "tensor-core LSTM kernels are built for 128 units");
+  for (int l = 0; l < 2; ++l) {
+    const int I = l == 0 ? nw->feat : 2 * U;
+    ORCAI_CHECK(upload_half(c, pack_gemm_b(nw->h_lstm_wih[l].data(), I, 2 * G, 256), &nw->tc_wih[l]));
+    // W_hh^T per direction: B operand rows n = gate*128 + unit, K = previous hidden unit ; recurrent_kernel is [U][4U]
+    std::vector<__half> wp((size_t)2 * G * U, __float2half_rn(0.f));
+    for (int d = 0; d < 2; ++d)
+      for (int n = 0; n < G; ++n)
+        for (int k = 0; k < U; ++k)
+          wp[(size_t)d * G * U + ((size_t)(n / 8) * (U / 8) * 128 + (size_t)(k / 8) * 128 + (n % 8) * 16 + (k % 8) * 2) / 2] =
+              __float2half_rn(nw->h_lstm_whh[l][(size_t)d * U * G + (size_t)k * G + n]);
+    ORCAI_CHECK(upload_half(c, wp, &nw->tc_whh[l]));
+  }
+  ORCAI_CHECK(upload_half(c, pack_gemm_b(nw->h_d1_w.data(), 2 * U, 128, 128), &nw->tc_d1));
+  ORCAI_CUDA(c, cudaFuncSetAttribute(lstm_rec_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRecSmem));
+  nw->tail_tc_ready = true;
+  return ORCAI_OK;
+}
+
+// scratch: m*Tn*(2*4U + 2U + 2U + 128) floats (same budget as net_tail_fp32)
+int net_tail_tc(Ctx* c, const float* feat, float* scratch, long long m, float* d_preds_out, bool mk) {
+  NetWeights* nw = c->net;
+  ORCAI_CHECK(net_tail_tc_prepare(c));
+  const int U = nw->U, G = 4 * U, L = nw->L;
+  const int Tn = nw->H >> nw->n_blocks;
+  const long long rows = m * Tn;
+  float* xz = scratch;                                               // (rows, 2G) fp32
+  __half* h1 = reinterpret_cast<__half*>(xz + (size_t)rows * 2 * G);  // (rows, 2U) fp16
+  __half* h2 = h1 + (size_t)rows * 2 * U;                             // (rows, 2U) fp16
+  float* d1 = reinterpret_cast<float*>(h2 + (size_t)rows * 2 * U);    // (rows, 128) fp32
+  constexpr int R = 64;
+  const dim3 rgrid((unsigned)((m + R - 1) / R), 2);
+  ORCAI_CHECK((run_gemm_tc<float, 256, 0>(c, feat, nw->feat, nw->tc_wih[0], nw->lstm_bih[0], xz, 2 * G, rows, 2 * G, nw->feat)));
+  net_mark(c, mk);  // 6: lstm1 input projection
+  lstm_rec_tc_kernel<R><<<rgrid, 544, kRecSmem, c->stream>>>(xz, nw->tc_whh[0], h1, m, Tn);
+  c->launches++;
+  net_mark(c, mk);  // 7: lstm1 recurrence
+  ORCAI_CHECK((run_gemm_tc<__half, 256, 0>(c, h1, 2 * U, nw->tc_wih[1], nw->lstm_bih[1], xz, 2 * G, rows, 2 * G, 2 * U)));
+  net_mark(c, mk);  // 8: lstm2 input projection
+  lstm_rec_tc_kernel<R><<<rgrid, 544, kRecSmem, c->stream>>>(xz, nw->tc_whh[1], h2, m, Tn);
+  c->launches++;
+  net_mark(c, mk);  // 9: lstm2 recurrence
+  ORCAI_CHECK((run_gemm_tc<__half, 128, 1>(c, h2, 2 * U, nw->tc_d1, nw->d1_b, d1, 128, rows, 128, 2 * U)));
+  {
+    const long long grid = std::min<long long>((rows + 7) / 8, (long long)c->sm_count * 8);
+    dense_out_kernel<<<(unsigned)grid, 256, 0, c->stream>>>(d1, nw->d2_w, nw->d2_b, d_preds_out, rows, L);
+    c->launches++;
+  }
+  net_mark(c, mk);  // 10: dense head
+  ORCAI_CUDA(c, cudaGetLastError());
+  return ORCAI_OK;
+}
+
+}  // namespace orcai

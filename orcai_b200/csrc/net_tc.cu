@@ -717,7 +717,8 @@ int forward_fused(Ctx* c, const float* d_in, int input_mode, int64_t first, int6
     ORCAI_CHECK((run_sep<60, 36, false, true, H, true>(c, act[4], feat, m, hs[4], ws[4], nw->tc_fin[0])));
     net_mark(c, mk);  // 5: final sepconv (fp32 features, w*36+c)
     if (stop == 5) { set_debug(nw, feat, 0, m, hs[4], ws[4], 36, 36); return ORCAI_OK; }
-    ORCAI_CHECK(net_tail_fp32(c, feat, scratch, m, d_preds + (size_t)s0 * Tn * L, mk));
+    if (nw->tail_path == 1) ORCAI_CHECK(net_tail_tc(c, feat, scratch, m, d_preds + (size_t)s0 * Tn * L, mk));
+    else ORCAI_CHECK(net_tail_fp32(c, feat, scratch, m, d_preds + (size_t)s0 * Tn * L, mk));
   }
   return ORCAI_OK;
 }

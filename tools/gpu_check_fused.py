@@ -58,10 +58,12 @@ def main() -> int:
             e_hw = np.where(np.isfinite(err), err, 1e9).max(axis=(0, 3))
             hh, ww = np.where(e_hw > 0.05 * scale + 1e-2)
             print(f"      bad rows {np.unique(hh)[:24]} ... cols {np.unique(ww)[:24]} ({len(hh)} bad pixels of {e_hw.size})")
-    out = ctx.forward_host(x)
-    e = np.abs(out - ref)
-    print(f"[fused] probabilities max err {e.max():.3e} mean {e.mean():.3e}", flush=True)
-    ok &= bool(e.max() < 5e-3)
+    for tail in (0, 1):
+        ctx.set_option("tail_path", tail)
+        out = ctx.forward_host(x)
+        e = np.abs(out - ref)
+        print(f"[fused] tail_path {tail}: probabilities max err {e.max():.3e} mean {e.mean():.3e}", flush=True)
+        ok &= bool(e.max() < 5e-3)
     ctx.set_option("net_path", 1)
     out1 = ctx.forward_host(x)
     print(f"[fused] vs layer-wise fp16 path: max diff {np.abs(out - out1).max():.3e}")
