@@ -7,14 +7,28 @@ Stands in for the ``keras.Model`` that the reference's ``load_orcai_model`` retu
 
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 from orcai_b200.runtime import get_context
 from orcai_b200.weights import check_weights
 
 
+# network arithmetic: "fast" = fp16 tcgen05 fused residual blocks + tensor-core LSTM tail (probabilities within ~2e-3 of the
+# fp32 graph, the same order as TensorFlow's default TF32 execution on GPUs); "reference" = fp32 CUDA-core path (1e-6).
+PRECISION_PATHS = {"fast": 3, "reference": 0}
+
+
+def precision_from_env() -> str:
+    p = os.environ.get("ORCAI_B200_PRECISION", "fast").strip().lower()
+    if p not in PRECISION_PATHS:
+        raise ValueError(f"ORCAI_B200_PRECISION must be one of {sorted(PRECISION_PATHS)}, got {p!r}")
+    return p
+
+
 class OrcaiModel:
-    def __init__(self, orcai_parameter: dict, shape: dict, weights: dict, device: int | None = None):
+    def __init__(self, orcai_parameter: dict, shape: dict, weights: dict, device: int | None = None, precision: str | None = None):
         if orcai_parameter.get("architecture", "ResNetLSTM") != "ResNetLSTM":
             raise ValueError(f"Unknown model architecture: {orcai_parameter.get('architecture')}")
         check_weights(weights, orcai_parameter, shape)
@@ -23,6 +37,8 @@ class OrcaiModel:
         self.weights = weights
         self.ctx = get_context(orcai_parameter, shape, device)
         self.ctx.load_weights(weights)
+        self.precision = precision or precision_from_env()
+        self.ctx.set_option("net_path", PRECISION_PATHS[self.precision])
         n_blocks = len(orcai_parameter["model"]["filters"])
         self.input_shape = (None, *shape["input_shape"])
         self.output_shape = (None, shape["input_shape"][0] // 2**n_blocks, shape["num_labels"])

@@ -17,6 +17,7 @@ import gzip
 import os
 import queue
 import threading
+from concurrent.futures import ThreadPoolExecutor
 from importlib.resources import files
 from pathlib import Path
 
@@ -196,8 +197,12 @@ def predict_wav(
     label_suffix: str = "*",
     msgr: Messenger = Messenger(verbosity=0),
     progressbar: tqdm = None,
+    _resident_samples=None,
 ):
-    """Predicts calls in a single wav file -> (predicted_labels DataFrame, aggregated_predictions, delta_t)."""
+    """Predicts calls in a single wav file -> (predicted_labels DataFrame, aggregated_predictions, delta_t).
+
+    ``_resident_samples`` (table mode): the recording has already been read and uploaded by the prefetcher.
+    """
     recording_path = Path(recording_path)
     if progressbar:
         progressbar.set_description(f"{recording_path.stem}: Generating spectrogram")
@@ -205,7 +210,7 @@ def predict_wav(
     sp = orcai_parameter["spectrogram"]
     msgr.part("Calculating power spectrogram by stft")
     msgr.info(f"Loading & resampling (to {sp['sampling_rate'] / 1000:.2f} kHz) wav file: {recording_path.stem}")
-    samples = load_recording(recording_path, channel, sp, msgr)
+    samples = _resident_samples if _resident_samples is not None else load_recording(recording_path, channel, sp, msgr)
     ctx = _context_of(model, orcai_parameter, shape)
     if ctx.params.n_freq != shape["input_shape"][1]:
         raise ValueError(f"Spectrogram shape ({ctx.params.n_freq}) for {recording_path.stem} not equal to input shape ({shape['input_shape'][1]})")
@@ -217,7 +222,7 @@ def predict_wav(
         progressbar.set_description(f"{recording_path.stem} - Predicting annotations")
         progressbar.refresh()
     try:
-        stats, agg, _cnt, lab, sta, sto = ctx.predict_pcm(samples, threshold=0.5, want_agg=True)
+        stats, agg, _cnt, lab, sta, sto = ctx.predict_pcm(samples, threshold=0.5, want_agg=True, resident=_resident_samples is not None)
     except OrcaiError as e:
         if e.code == ORCAI_ERR_TOO_SHORT:
             raise ValueError(f"{recording_path.stem}: {e.message}") from e
@@ -306,6 +311,7 @@ def _predict_and_save(
     label_suffix: str = "*",
     msgr: Messenger = Messenger(verbosity=0),
     progressbar: tqdm = None,
+    _resident_samples=None,
 ) -> None:
     recording_path = Path(recording_path)
     if output_path is not None:
@@ -329,6 +335,7 @@ def _predict_and_save(
         label_suffix=label_suffix,
         msgr=msgr,
         progressbar=progressbar,
+        _resident_samples=_resident_samples,
     )
     if call_duration_limits is not None:
         predicted_labels = filter_predictions(predicted_labels, delta_t=delta_t, call_duration_limits=call_duration_limits, label_suffix=label_suffix, msgr=msgr)
@@ -402,10 +409,15 @@ def predict(
     rows = list(recording_table.index)
     progressbar = tqdm(total=len(rows), desc="Starting ...", unit="file")
 
-    def run_row(i, mdl, pb):
+    def row_path(i):
+        return Path(recording_table.loc[i, "base_dir_recording"]).joinpath(recording_table.loc[i, "rel_recording_path"])
+
+    def run_row(i, mdl, pb, resident=None):
         try:
+            if isinstance(resident, BaseException):
+                raise resident
             _predict_and_save(
-                recording_path=Path(recording_table.loc[i, "base_dir_recording"]).joinpath(recording_table.loc[i, "rel_recording_path"]),
+                recording_path=row_path(i),
                 channel=int(recording_table.loc[i, "channel"]),
                 model=mdl,
                 orcai_parameter=orcai_parameter,
@@ -417,14 +429,36 @@ def predict(
                 label_suffix=label_suffix,
                 msgr=Messenger(verbosity=0),
                 progressbar=pb,
+                _resident_samples=resident,
             )
         except Exception as e:  # per-recording isolation, like the reference loop (predict.py:752-755)
             msgr.error(f"Error predicting {recording_table.loc[i, 'recording']}: {e.args[0] if e.args else e}")
 
+    def pipelined(mdl, my_rows, pb, tick):
+        """Reading + uploading recording k+1 overlaps the annotation of recording k (orcai_prefetch_pcm / orcai_swap_pcm)."""
+        ctx = _context_of(mdl, orcai_parameter, shape)
+        sp = orcai_parameter["spectrogram"]
+
+        def load_and_prefetch(i):
+            try:
+                samples = load_recording(row_path(i), int(recording_table.loc[i, "channel"]), sp, Messenger(verbosity=0))
+                ctx.prefetch_pcm(samples)
+                return samples
+            except Exception as e:  # surfaced inside run_row so that the row is reported like any other failure
+                return e
+
+        with ThreadPoolExecutor(max_workers=1) as ex:
+            fut = ex.submit(load_and_prefetch, my_rows[0]) if my_rows else None
+            for k, i in enumerate(my_rows):
+                res = fut.result()
+                if not isinstance(res, BaseException):
+                    ctx.swap_pcm()
+                fut = ex.submit(load_and_prefetch, my_rows[k + 1]) if k + 1 < len(my_rows) else None
+                run_row(i, mdl, pb, resident=res)
+                tick()
+
     if len(devices) <= 1:
-        for i in rows:
-            run_row(i, model, progressbar)
-            progressbar.update(1)
+        pipelined(model, rows, progressbar, lambda: progressbar.update(1))
     else:
         # shard by recording: one worker (context + stream) per GPU pulling rows from a shared queue; host-side gather only
         from orcai_b200.model import OrcaiModel

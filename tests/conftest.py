@@ -45,3 +45,16 @@ def ctx(params):
 @pytest.fixture(scope="session")
 def golden_dir():
     return ROOT / "tests" / "golden"
+
+
+@pytest.fixture(autouse=True)
+def _reference_precision_by_default(request):
+    """GPU tests start on the fp32 network path; tests of the fast path select it explicitly."""
+    if "gpu" in request.keywords and _have_gpu():
+        from orcai_b200 import runtime
+
+        P, S = runtime.bundled_parameters()
+        c = runtime.get_context(P, S, 0)
+        c.set_option("net_path", 0)
+        c.set_option("tail_path", 1)
+    yield
