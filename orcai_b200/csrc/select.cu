@@ -44,6 +44,28 @@ __global__ void select_init_kernel(SelectState* st, unsigned long long rank_lo, 
 // PASS 0: digit = key >> 21 (11 bits), one shared histogram (stored in hist[0]).
 // PASS 1: digit = (key >> 10) & 2047 for keys whose top 11 bits equal prefix[r] >> 21.
 // PASS 2: digit = key & 1023 for keys whose top 22 bits equal prefix[r] >> 10.
+// The raw dB buffer is streamed as float4 (row pitch kRawLd = 44 float4; the pad columns are masked), four independent
+// loads in flight per thread.  Pass 0 sees very few distinct digits (the top 11 key bits are sign + exponent + 2 mantissa
+// bits of a value in [-80, 0]), so its shared-memory atomics are aggregated per warp with match.any first.
+template <int PASS>
+__device__ __forceinline__ void select_count(unsigned int (*sh)[2048], float raw, bool valid, float db_ref, unsigned int p0, unsigned int p1) {
+  const unsigned int key = f2key(shifted_db(raw, db_ref));
+  if (PASS == 0) {
+    const unsigned int active = __ballot_sync(0xffffffffu, valid);
+    if (valid) {
+      const unsigned int d = key >> 21;
+      const unsigned int peers = __match_any_sync(active, d);
+      if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&sh[0][d], (unsigned int)__popc(peers));
+    }
+  } else if (PASS == 1) {
+    if (valid && (key >> 21) == (p0 >> 21)) atomicAdd(&sh[0][(key >> 10) & 2047u], 1u);
+    if (valid && (key >> 21) == (p1 >> 21)) atomicAdd(&sh[1][(key >> 10) & 2047u], 1u);
+  } else {
+    if (valid && (key >> 10) == (p0 >> 10)) atomicAdd(&sh[0][key & 1023u], 1u);
+    if (valid && (key >> 10) == (p1 >> 10)) atomicAdd(&sh[1][key & 1023u], 1u);
+  }
+}
+
 template <int PASS>
 __global__ void __launch_bounds__(256)
 select_hist_kernel(const float* __restrict__ raw, long long T, int ld, int nb, SelectState* st) {
@@ -52,21 +74,28 @@ select_hist_kernel(const float* __restrict__ raw, long long T, int ld, int nb, S
   __syncthreads();
   const float db_ref = st->db_ref;
   const unsigned int p0 = st->prefix[0], p1 = st->prefix[1];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
-  for (long long j = (long long)blockIdx.x * (blockDim.x >> 5) + warp; j < T; j += wstride) {
-    const float* row = raw + (size_t)j * ld;
-    for (int b = lane; b < nb; b += 32) {
-      const unsigned int key = f2key(shifted_db(row[b], db_ref));
-      if (PASS == 0) {
-        atomicAdd(&sh[0][key >> 21], 1u);
-      } else if (PASS == 1) {
-        if ((key >> 21) == (p0 >> 21)) atomicAdd(&sh[0][(key >> 10) & 2047u], 1u);
-        if ((key >> 21) == (p1 >> 21)) atomicAdd(&sh[1][(key >> 10) & 2047u], 1u);
-      } else {
-        if ((key >> 10) == (p0 >> 10)) atomicAdd(&sh[0][key & 1023u], 1u);
-        if ((key >> 10) == (p1 >> 10)) atomicAdd(&sh[1][key & 1023u], 1u);
-      }
+  const int ld4 = ld >> 2;
+  const long long n4 = T * ld4;
+  const float4* raw4 = reinterpret_cast<const float4*>(raw);
+  constexpr int ILP = 4;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  // whole warps stay in the loop together (match.any / ballot need converged warps): iterate to a warp-uniform bound
+  for (long long base = (long long)blockIdx.x * blockDim.x; base < n4; base += stride * ILP) {
+    float4 v[ILP];
+    long long e[ILP];
+#pragma unroll
+    for (int q = 0; q < ILP; ++q) {
+      e[q] = base + q * stride + threadIdx.x;
+      v[q] = e[q] < n4 ? __ldg(raw4 + e[q]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int q = 0; q < ILP; ++q) {
+      const int c = (int)(e[q] % ld4) * 4;
+      const bool in = e[q] < n4;
+      select_count<PASS>(sh, v[q].x, in && c < nb, db_ref, p0, p1);
+      select_count<PASS>(sh, v[q].y, in && c + 1 < nb, db_ref, p0, p1);
+      select_count<PASS>(sh, v[q].z, in && c + 2 < nb, db_ref, p0, p1);
+      select_count<PASS>(sh, v[q].w, in && c + 3 < nb, db_ref, p0, p1);
     }
   }
   __syncthreads();
@@ -164,7 +193,7 @@ int launch_select(Ctx* c, const float* d_raw, int64_t T) {
   // np.percentile 'nearest': index = around((n - 1) * q), half to even
   const unsigned long long r0 = (unsigned long long)nearbyint((double)(n - 1) * c->p.q_lo);
   const unsigned long long r1 = (unsigned long long)nearbyint((double)(n - 1) * c->p.q_hi);
-  const int grid = c->sm_count * 4;
+  const int grid = c->sm_count * 8;
   select_init_kernel<<<8, 512, 0, c->stream>>>(c->d_sel, r0, r1);
   select_hist_kernel<0><<<grid, 256, 0, c->stream>>>(d_raw, T, kRawLd, nb, c->d_sel);
   select_scan_kernel<0><<<1, 1024, 0, c->stream>>>(c->d_sel);
