@@ -490,6 +490,12 @@ int net_set_tail_path(Ctx* c, int path) {
   return ORCAI_OK;
 }
 
+int net_set_conv0_path(Ctx* c, int path) {
+  if (path < 0 || path > 1) ORCAI_FAIL(c, ORCAI_ERR_ARG, "conv0_path must be 0 (fp32 CUDA cores) or 1 (tensor cores)");
+  c->net->conv0_path = path;
+  return ORCAI_OK;
+}
+
 int net_set_debug_stop(Ctx* c, int stage) {
   c->net->debug_stop = stage;
   return ORCAI_OK;

@@ -51,6 +51,8 @@ struct NetWeights {
   void* fb_w[kMaxBlocks] = {};
   float* fb_bias[kMaxBlocks] = {};
   int chunk_fused = 2048;
+  void* conv0_mma_w = nullptr;   // banded B operand of the tensor-core entry convolution (conv0_mma.cuh)
+  int conv0_path = 1;            // fused path: 1 = tensor-core pixel-group convolution, 0 = fp32 CUDA-core convolution
   // tensor-core recurrent tail (net_lstm_tc.cu)
   bool tail_tc_ready = false;
   int tail_path = 1;          // fused path only: 1 = tensor-core LSTM / dense tail, 0 = fp32 CUDA-core tail

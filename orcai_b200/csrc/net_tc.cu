@@ -310,6 +310,7 @@ pool_res_tc_kernel(const H* __restrict__ t4, const H* __restrict__ prev, H* __re
 }
 
 #include "net_fused.cuh"
+#include "conv0_mma.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // entry convolution for the fused path: fp32 CUDA-core math (K = 9 is no tensor-core shape), normalise-on-load from the
@@ -587,10 +588,47 @@ int build_fused_block(Ctx* c, int blk) {
   return ORCAI_OK;
 }
 
+// banded (Toeplitz) B operand of the pixel-group entry convolution + bias rows + ones tile (conv0_mma.cuh)
+int build_conv0_mma(Ctx* c) {
+  NetWeights* nw = c->net;
+  std::vector<__half> w(conv0::kWBytes / 2, __float2half_rn(0.f));
+  auto at = [](int blk, int n, int k) { return (conv0::OFF_B + blk * conv0::kBBlock + (uint32_t)(n / 8) * 256 + (uint32_t)(k / 8) * 128 + (n % 8) * 16 + (k % 8) * 2) / 2; };
+  for (int dy = 0; dy < 3; ++dy)
+    for (int pr = 0; pr < 2; ++pr)
+      for (int k = 0; k < 16; ++k) {
+        if (pr == 1 && k >= 8) continue;                 // second chunk of the [g+1 | -] step carries no weight
+        const int pos = pr == 0 ? k - 8 : 8 + k;          // input pixel relative to the first pixel of the output group
+        for (int j = 0; j < 8; ++j) {
+          const int dx = pos - j + 1;
+          if (dx < 0 || dx > 2) continue;
+          for (int ch = 0; ch < 16; ++ch) w[at(dy * 2 + pr, j * 16 + ch, k)] = __float2half_rn(nw->h_conv0_w[(dy * 3 + dx) * 16 + ch]);
+        }
+      }
+  for (int j = 0; j < 8; ++j)
+    for (int ch = 0; ch < 16; ++ch) {
+      const float bv = nw->h_conv0_b[ch];
+      const __half hi = __float2half_rn(bv);
+      w[at(6, j * 16 + ch, 0)] = hi;
+      w[at(6, j * 16 + ch, 1)] = __float2half_rn(bv - __half2float(hi));
+    }
+  for (int r = 0; r < 8; ++r) {
+    w[(conv0::OFF_ONES + r * 16) / 2] = __float2half_rn(1.f);
+    w[(conv0::OFF_ONES + r * 16) / 2 + 1] = __float2half_rn(1.f);
+  }
+  void* p = nullptr;
+  ORCAI_CUDA(c, cudaMalloc(&p, conv0::kWBytes));
+  nw->allocs.push_back(p);
+  ORCAI_CUDA(c, cudaMemcpy(p, w.data(), conv0::kWBytes, cudaMemcpyHostToDevice));
+  nw->conv0_mma_w = p;
+  ORCAI_CUDA(c, cudaFuncSetAttribute(conv0::conv0_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)conv0::kSmem));
+  return ORCAI_OK;
+}
+
 int prepare_fused(Ctx* c) {
   NetWeights* nw = c->net;
   if (nw->fused_ready) return ORCAI_OK;
-  ORCAI_CHECK(net_tc_prepare(c, 0));   // conv0 and the final sepconv reuse the fp16 layer-wise operands
+  ORCAI_CHECK(net_tc_prepare(c, 0));   // the final sepconv reuses the fp16 layer-wise operands
+  ORCAI_CHECK(build_conv0_mma(c));
   ORCAI_CHECK(build_fused_block<FB1>(c, 0));
   ORCAI_CHECK(build_fused_block<FB2>(c, 1));
   ORCAI_CHECK(build_fused_block<FB3>(c, 2));
@@ -660,16 +698,18 @@ int forward_fused(Ctx* c, const float* d_in, int input_mode, int64_t first, int6
     sub[b] = b < 4 ? (size_t)hs[b + 1] * ws[b + 1] * cp[b] : 0;
     halfs += full[b] + sub[b];
   }
+  halfs += (size_t)Himg * conv0::kSpecLd;   // fp16 normalised spectrogram rows of the chunk (upper bound: non-overlapping snippets)
   halfs = (halfs + 7) & ~(size_t)7;
   const size_t tail_f = (size_t)Tn * (nw->feat + 2 * 4 * U + 2 * U + 2 * U + 128);
   const size_t per = halfs * 2 + tail_f * 4;
   const long long chunk = std::min<long long>(std::max(nw->chunk_fused, 1), n);
   if (chunk <= 0) return ORCAI_OK;
   ORCAI_CHECK(ensure_device_buffer(c, &nw->tc_ws, &nw->tc_ws_cap, per * (size_t)chunk + 256));
-  H* act[5]; H* acts[5];
+  H* act[5]; H* acts[5]; H* spec16 = nullptr;
   {
     H* p = static_cast<H*>(nw->tc_ws);
     for (int b = 0; b < 5; ++b) { act[b] = p; p += full[b] * chunk; acts[b] = p; p += sub[b] * chunk; }
+    spec16 = p;
   }
   float* feat = reinterpret_cast<float*>(static_cast<H*>(nw->tc_ws) + halfs * chunk);
   float* scratch = feat + (size_t)Tn * nw->feat * chunk;
@@ -689,7 +729,33 @@ int forward_fused(Ctx* c, const float* d_in, int input_mode, int64_t first, int6
     const bool mk = (s0 == 0);
     if (mk) nw->marked_snippets = m;
     net_mark(c, mk);
-    {
+    if (nw->conv0_path == 1) {
+      // fp16 normalised rows of this chunk, then the pixel-group tensor-core convolution over a strided snippet view
+      const long long srows = input_mode == 0 ? (m - 1) * shift + Himg : m * (long long)Himg;
+      const float* src = (input_mode == 0) ? d_in + (size_t)(first + s0) * shift * kRawLd : d_in + (size_t)s0 * Himg * Wf;
+      const long long total2 = srows * (conv0::kSpecLd / 2);
+      conv0::spec_half_kernel<<<(unsigned)std::min<long long>((total2 + 255) / 256, (long long)c->sm_count * 16), 256, 0, c->stream>>>(
+          src, input_mode, input_mode == 0 ? kRawLd : Wf, srows, Wf, c->d_sel, spec16);
+      CUtensorMap tms;
+      {
+        EncodeTiledFn fn = encode_tiled_fn();
+        if (!fn) ORCAI_FAIL(c, ORCAI_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+        const cuuint64_t dims[3] = {(cuuint64_t)conv0::kSpecLd, (cuuint64_t)Himg, (cuuint64_t)m};
+        const cuuint64_t strides[2] = {(cuuint64_t)conv0::kSpecLd * 2, (cuuint64_t)(input_mode == 0 ? shift : Himg) * conv0::kSpecLd * 2};
+        const cuuint32_t box[3] = {(cuuint32_t)conv0::kBoxW, (cuuint32_t)conv0::kRI, 1};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        const CUresult r = fn(&tms, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, spec16, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) ORCAI_FAIL(c, ORCAI_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for the spectrogram view", (int)r);
+      }
+      const int tiles_per = (Himg + conv0::kRT - 1) / conv0::kRT;
+      const long long n_tiles = m * tiles_per;
+      const long long grid = std::min<long long>(n_tiles, (long long)c->sm_count * 4);
+      conv0::conv0_mma_kernel<<<(unsigned)grid, 160, conv0::kSmem, c->stream>>>(tms, act[0], acts[0], Himg, Wf, tiles_per, n_tiles,
+                                                                               static_cast<const unsigned char*>(nw->conv0_mma_w));
+      c->launches += 2;
+      ORCAI_CUDA(c, cudaGetLastError());
+    } else {
       const int tiles_w = (Wf + kC0TW - 1) / kC0TW, tiles_h = (Himg + kC0TH - 1) / kC0TH;
       const float* src = (input_mode == 0) ? d_in : d_in + (size_t)s0 * Himg * Wf;
       conv0_direct_kernel<<<(unsigned)(m * tiles_w * tiles_h), 256, 0, c->stream>>>(src, input_mode, first + s0, shift, input_mode == 0 ? kRawLd : Wf,
