@@ -38,6 +38,12 @@ UNIT = "h_audio/s"
 STFT_BYTES_PER_FRAME_F32 = 1024 + 684  # 256 new float32 samples in + 171 float32 out
 STFT_BYTES_PER_FRAME_I16 = 512 + 684
 FLOP_PER_SNIPPET = 0.972e9  # 485.8 M MAC
+# residual block 1 (the dominant kernel): SepConv 16->30 and 30->30 at 736x171 plus the 1x1/2 residual convolution
+BLOCK1_MAC_PER_SNIPPET = 736 * 171 * (9 * 16 + 16 * 30) + 736 * 171 * (9 * 30 + 30 * 30) + 368 * 86 * 16 * 30
+# what the folded implicit GEMM executes for it: 123 steps x 3 strips per snippet, 88 tcgen05.mma of 128 x 32 x 16 per step
+BLOCK1_EXECUTED_MAC_PER_SNIPPET = 123 * 3 * 88 * 128 * 32 * 16
+# dram__bytes_read + dram__bytes_write of that kernel per snippet, from the ncu --set full capture under profiles/ (None until measured)
+BLOCK1_TRAFFIC_BYTES_PER_SNIPPET = (919.085568e6 + 431.915008e6) / 182  # profiles/r01e_ncu_full_summary.csv (182-snippet launch)
 
 
 def _peaks() -> dict:
@@ -262,6 +268,23 @@ def main() -> None:
         net_ms = stage["network_ms"] / args.steps
         stft_gbs = T * STFT_BYTES_PER_FRAME_I16 / (stft_ms * 1e-3) / 1e9
         net_tflops = n_snip * FLOP_PER_SNIPPET / (net_ms * 1e-3) / 1e12
+        if args.net_path == 3 and net_stage[15] > 0:
+            # dominant kernel = fused residual block 1; duration = CUDA events around its launch (first chunk) on the compute stream
+            b1_ms, b1_snips = float(net_stage[1]), float(net_stage[15])
+            b1_tflops = 2.0 * BLOCK1_MAC_PER_SNIPPET * b1_snips / (b1_ms * 1e-3) / 1e12
+            roofline_main = {"kernel": "fused_block_kernel<block 1: sepconv 16->30, sepconv 30->30, maxpool(3,2)/2 + residual 1x1/2>",
+                             "bound": "tensor", "achieved": b1_tflops, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                             "frac": b1_tflops / peaks["bf16_tflops_sustained"], "traffic": BLOCK1_TRAFFIC_BYTES_PER_SNIPPET * b1_snips if BLOCK1_TRAFFIC_BYTES_PER_SNIPPET else None,
+                             "peak_source": peaks["source"] + " bf16 sustained", "ms": b1_ms, "snippets": int(b1_snips),
+                             "algorithmic_mac_per_snippet": BLOCK1_MAC_PER_SNIPPET,
+                             "executed_tflops": 2.0 * BLOCK1_EXECUTED_MAC_PER_SNIPPET * b1_snips / (b1_ms * 1e-3) / 1e12,
+                             "note": "achieved counts the reference graph's MACs; the depthwise filter is folded into the GEMM weights, so the tensor pipe "
+                                     "executes 9 taps x pointwise MACs (executed_tflops); the kernel is bound by shared-memory operand bandwidth "
+                                     "(A re-read per tap at N = 32), see DESIGN.md"}
+        else:
+            roofline_main = {"kernel": "orcai-V1 forward (all layer kernels)", "bound": "tensor", "achieved": net_tflops, "peak": peaks["bf16_tflops_sustained"],
+                             "unit": "TFLOP/s", "frac": net_tflops / peaks["bf16_tflops_sustained"], "traffic": None,
+                             "peak_source": peaks["source"] + " bf16 sustained", "flop_per_snippet": FLOP_PER_SNIPPET}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * t_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -269,7 +292,7 @@ def main() -> None:
             "config": {"workload": WORKLOAD_NAME, "hours_per_gpu_per_step": args.hours, "frames": T, "snippets": n_snip,
                        "segments_found": n_segments, "parallelism": f"shard-by-recording x{world}", "l2": "inputs larger than L2 (346 MB PCM, 475 MB dB per step)",
                        "network_path": {0: "fp32 cuda-core", 1: "fp16 tcgen05 implicit-GEMM trunk + fp32 LSTM/dense", 2: "bf16 tcgen05 implicit-GEMM trunk + fp32 LSTM/dense",
-                                        3: "fp16 tcgen05 fused residual-block kernels + fp32 LSTM/dense"}[args.net_path],
+                                        3: "fp16 tcgen05: pixel-group entry conv, fused residual-block kernels, tcgen05 LSTM projections + TMEM-resident recurrence"}[args.net_path],
                        "stft": "float64 FFT" if args.stft_f64 else "float32 FFT"},
             "device_ms_per_step": dev_ms,
             "stage_ms": {k: v / args.steps for k, v in stage.items()},
@@ -278,9 +301,10 @@ def main() -> None:
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(pcm.nbytes), "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * t_e2e / args.steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"kernel": "orcai-V1 forward (all layer kernels)", "bound": "tensor", "achieved": net_tflops, "peak": peaks["bf16_tflops_sustained"],
-                         "unit": "TFLOP/s", "frac": net_tflops / peaks["bf16_tflops_sustained"], "traffic": None, "peak_source": peaks["source"] + " bf16 sustained",
-                         "flop_per_snippet": FLOP_PER_SNIPPET},
+            "roofline": roofline_main,
+            "roofline_network": {"kernel": "orcai-V1 forward (all layer kernels)", "bound": "tensor", "achieved": net_tflops, "peak": peaks["bf16_tflops_sustained"],
+                                 "unit": "TFLOP/s", "frac": net_tflops / peaks["bf16_tflops_sustained"], "traffic": None,
+                                 "peak_source": peaks["source"] + " bf16 sustained", "flop_per_snippet": FLOP_PER_SNIPPET},
             "roofline_stft": {"kernel": "stft_db_kernel<int16>", "bound": "hbm", "achieved": stft_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                               "frac": stft_gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"] + " copy",
                               "bytes_per_frame": STFT_BYTES_PER_FRAME_I16, "ms": stft_ms},

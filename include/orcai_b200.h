@@ -144,7 +144,12 @@ int orcai_predict_pcm(orcai_ctx* ctx, const void* pcm_host, int32_t dtype, int64
                       int64_t seg_capacity, int64_t* n_segments);
 
 /* ---- knobs ---------------------------------------------------------------------------------- */
-/* Options: "net_path"  0 = fp32 CUDA-core path, 1 = fp16 tcgen05 path, 2 = bf16 tcgen05 path (fp32 accumulate);
+/* Options: "net_path"  0 = fp32 CUDA-core path (reference grade, library default), 1 = fp16 / 2 = bf16 layer-wise tcgen05
+ *                      path, 3 = fp16 fused tcgen05 path (what orcai_b200's Python layer selects unless
+ *                      ORCAI_B200_PRECISION=reference): tensor-core entry convolution, fused residual-block kernels,
+ *                      tensor-core LSTM tail; fp32 accumulation everywhere;
+ *          "tail_path" (net_path 3) 1 = tensor-core LSTM/dense tail (default), 0 = fp32 CUDA-core tail;
+ *          "conv0_path" (net_path 3) 1 = tensor-core entry convolution (default), 0 = fp32 CUDA-core entry convolution;
  *          "stft_f64"  1 = float64 FFT (parity grade, default), 0 = float32 FFT (fast);
  *          "chunk"     snippets per network launch sequence;
  *          "debug_stop" stop the forward after a stage (see orcai_debug_read), -1 = off. */
