@@ -63,7 +63,10 @@ struct FB {
   static constexpr int P1_0 = 2 * WP + 1, P2_0 = WP + 2;
   static constexpr int XPIX = round8(imax((S + 2) * WP, P1_0 + 128 * N1 + 1));
   static constexpr int S1PIX = round8(imax((S + 2) * WP, P2_0 + 128 * N2 + WP + 1));
-  static constexpr int S2PIX = round8((S + 1) * WP);
+  // S2 is stored de-interleaved: even image columns in the first half of a chunk plane, odd columns in the second half
+  // (offset by 64 B modulo 128), so that the pooling epilogue's lanes (one pooled column each) read consecutive 16-byte pieces
+  static constexpr int S2HALF = round8((S + 1) * (WP / 2)) + 4;
+  static constexpr int S2PIX = 2 * S2HALF;
   static constexpr int RQ = (S / 2) * CP, RPIX = round8(RQ);
   static constexpr uint32_t LBO_X = XPIX * 16, LBO_S1 = S1PIX * 16, LBO_S2 = S2PIX * 16, LBO_R = RPIX * 16;
   // trimmed weight storage: only k-chunks / n-groups that carry data are stored; the MMA's reads of the missing
@@ -319,18 +322,18 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         tmem_ld16f(lane_addr + G::COL_R + (uint32_t)(gp & 1) * G::NP + g0 * 8, r);
         const int ho = (pa >> 1) + q_i, wo = pwo0 + q_j;
         if (row < G::RQ && ho >= 0 && ho < Ho && wo < Wo) {
-          const uint32_t p00 = (uint32_t)((2 * q_i) * G::WP + 2 + 2 * q_j);
+          const uint32_t p00 = (uint32_t)((2 * q_i) * (G::WP / 2) + 1 + q_j);   // even column 2 + 2j of row 2i; the odd column 3 + 2j sits S2HALF further
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
             if (u == 1 && !has1) break;
             const int gg = g0 + u;
             const unsigned char* s2 = smem + G::OFF_S2 + gg * G::LBO_S2 + p00 * 16;
             uint4 m = *reinterpret_cast<const uint4*>(s2);
-            m = hmax8(m, *reinterpret_cast<const uint4*>(s2 + 16));
+            m = hmax8(m, *reinterpret_cast<const uint4*>(s2 + G::S2HALF * 16));
+            m = hmax8(m, *reinterpret_cast<const uint4*>(s2 + (G::WP / 2) * 16));
+            m = hmax8(m, *reinterpret_cast<const uint4*>(s2 + (G::WP / 2 + G::S2HALF) * 16));
             m = hmax8(m, *reinterpret_cast<const uint4*>(s2 + G::WP * 16));
-            m = hmax8(m, *reinterpret_cast<const uint4*>(s2 + G::WP * 16 + 16));
-            m = hmax8(m, *reinterpret_cast<const uint4*>(s2 + 2 * G::WP * 16));
-            m = hmax8(m, *reinterpret_cast<const uint4*>(s2 + 2 * G::WP * 16 + 16));
+            m = hmax8(m, *reinterpret_cast<const uint4*>(s2 + (G::WP + G::S2HALF) * 16));
             const __half2* mh = reinterpret_cast<const __half2*>(&m);
             float y[8];
 #pragma unroll
@@ -392,8 +395,9 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
           if (prev_carry) {
             for (int i = tid; i < G::NG * G::WP; i += G::NWORK) {
               const int gq = i / G::WP, px = i - gq * G::WP;
-              unsigned char* p = smem + G::OFF_S2 + gq * G::LBO_S2 + px * 16;
-              *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(p + G::S * G::WP * 16);
+              const int hp = px / (G::WP / 2), cc = px - hp * (G::WP / 2);   // half-plane (column parity), column / 2
+              unsigned char* p = smem + G::OFF_S2 + gq * G::LBO_S2 + (hp * G::S2HALF + cc) * 16;
+              *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(p + G::S * (G::WP / 2) * 16);
             }
             worker_sync<G::NWORK>();  // carried S2 row in place before epilogue 2 overwrites its source row
           }
@@ -411,7 +415,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
             const bool inimg = hh >= 0 && hh < H && ww >= 0 && ww < W;
             if (p2 < (G::S + 1) * G::WP) {
               const uint4 ninf = make_uint4(0xFC00FC00u, 0xFC00FC00u, 0xFC00FC00u, 0xFC00FC00u);
-              unsigned char* dst = smem + G::OFF_S2 + g0 * G::LBO_S2 + p2 * 16;
+              unsigned char* dst = smem + G::OFF_S2 + g0 * G::LBO_S2 + ((c2[t] & 1) * G::S2HALF + y2[t] * (G::WP / 2) + (c2[t] >> 1)) * 16;
               *reinterpret_cast<uint4*>(dst) = inimg ? pack8h(v) : ninf;
               if (has1) *reinterpret_cast<uint4*>(dst + G::LBO_S2) = inimg ? pack8h(v + 8) : ninf;
             }
