@@ -47,15 +47,6 @@ __device__ __forceinline__ void bulk_copy_g2s(uint32_t dst, const void* src, uin
                "r"(smem_u32(bar))
                : "memory");
 }
-__device__ __forceinline__ void tmem_ld8f(uint32_t taddr, float (&v)[8]) {
-  uint32_t r[8];
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n\ttcgen05.wait::ld.sync.aligned;"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-               : "r"(taddr)
-               : "memory");
-#pragma unroll
-  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
-}
 __device__ __forceinline__ uint4 pack8h(const float* v) {
   uint4 r;
   __half2* h = reinterpret_cast<__half2*>(&r);
@@ -76,15 +67,20 @@ struct GemmSmem {
   static constexpr uint32_t BYTES = OFF_BAR + 8 * 8 + 16;
 };
 
-__device__ __forceinline__ uint4 load8_as_half(const float* p, int valid) {   // valid: number of readable floats (multiple of 4)
-  float v[8];
-  const float4 a = valid >= 4 ? __ldg(reinterpret_cast<const float4*>(p)) : make_float4(0.f, 0.f, 0.f, 0.f);
-  const float4 b = valid >= 8 ? __ldg(reinterpret_cast<const float4*>(p) + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
-  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-  return pack8h(v);
+// one K-chunk (64 elements) of an A row as fp16, 8 x 16 bytes; `valid` = readable elements from p (multiple of 4 / 8)
+__device__ __forceinline__ void stage_row(const float* p, int valid, uint4 (&out)[kGK / 8]) {
+  float4 v[kGK / 4];
+#pragma unroll
+  for (int q = 0; q < kGK / 4; ++q) v[q] = 4 * q + 4 <= valid ? __ldg(reinterpret_cast<const float4*>(p) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int j = 0; j < kGK / 8; ++j) {
+    const float f[8] = {v[2 * j].x, v[2 * j].y, v[2 * j].z, v[2 * j].w, v[2 * j + 1].x, v[2 * j + 1].y, v[2 * j + 1].z, v[2 * j + 1].w};
+    out[j] = pack8h(f);
+  }
 }
-__device__ __forceinline__ uint4 load8_as_half(const __half* p, int valid) {   // valid: 0 or >= 8
-  return valid >= 8 ? __ldg(reinterpret_cast<const uint4*>(p)) : make_uint4(0, 0, 0, 0);
+__device__ __forceinline__ void stage_row(const __half* p, int valid, uint4 (&out)[kGK / 8]) {
+#pragma unroll
+  for (int j = 0; j < kGK / 8; ++j) out[j] = 8 * j + 8 <= valid ? __ldg(reinterpret_cast<const uint4*>(p) + j) : make_uint4(0, 0, 0, 0);
 }
 
 // ACT: 0 none, 1 relu.  grid = (N / BN, ceil(M / 128)), block = 160 (4 worker warps + issuer warp)
@@ -146,12 +142,11 @@ gemm_tc_kernel(const TA* __restrict__ A, int lda, const __half* __restrict__ Bp,
         bulk_copy_g2s(sbase + S::OFF_B + s * S::B_STAGE, Bp + ((size_t)nt * nkc + kc) * (S::B_STAGE / 2), S::B_STAGE, &bars[2 + s]);
       }
       unsigned char* dst = smem + S::OFF_A + s * S::A_STAGE + row * 16;
+      // all loads of the chunk are issued before the first conversion (one memory round trip per chunk, not eight)
+      uint4 staged[kGK / 8];
+      stage_row(arow + kc * kGK, row_ok ? K - kc * kGK : 0, staged);
 #pragma unroll
-      for (int j = 0; j < kGK / 8; ++j) {
-        const int k0 = kc * kGK + j * 8;
-        const uint4 v = load8_as_half(arow + k0, row_ok ? K - k0 : 0);
-        *reinterpret_cast<uint4*>(dst + j * (kGM * 16)) = v;
-      }
+      for (int j = 0; j < kGK / 8; ++j) *reinterpret_cast<uint4*>(dst + j * (kGM * 16)) = staged[j];
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bars[0 + s]);
@@ -188,29 +183,44 @@ constexpr uint32_t kRecW = kG4 * kU * 2;             // 128 KB: W_hh^T as [n = g
 constexpr uint32_t kRecH = 128 * kU * 2;             // 32 KB: h as [k-chunk][row][8]
 constexpr uint32_t kRecSmem = kRecW + kRecH + 4 * 8 + 16;
 
-__device__ __forceinline__ float sigmoid_fast(float x) { return __fdividef(1.f, 1.f + __expf(-x)); }
-__device__ __forceinline__ float tanh_fast(float x) { return 2.f * __fdividef(1.f, 1.f + __expf(-2.f * x)) - 1.f; }
+// ex2.approx / rcp.approx directly (2 ulp / 1 ulp): sigmoid = 4 instructions, tanh = 5
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sigmoid_fast(float x) { return rcp_approx(1.f + ex2_approx(-1.4426950408889634f * x)); }
+__device__ __forceinline__ float tanh_fast(float x) { return fmaf(2.f, rcp_approx(1.f + ex2_approx(-2.8853900817779268f * x)), -1.f); }
 
-// grid = (ceil(n / R), 2 directions), block = 17 warps: 16 workers (quad = w & 3 -> TMEM lanes, cg = w >> 2 -> 32 units) + issuer
-template <int R>
-__global__ void __launch_bounds__(544, 1)
+__device__ __forceinline__ void tmem_ld4f(uint32_t taddr, float (&v)[4]) {
+  uint32_t r[4];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];\n\ttcgen05.wait::ld.sync.aligned;"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr)
+               : "memory");
+#pragma unroll
+  for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// grid = (ceil(n / 64), 2 directions), block = 32 warps.  A warp can only read the TMEM lane quadrant (warp id % 4), and a
+// CTA owns 64 snippets = quadrants 0 and 1, so the 16 warps with (id % 4) < 2 are the workers (quad = id % 4 -> rows,
+// cg = id / 4 -> 16 hidden units each), warp 3 issues the MMAs, the rest idle.  Sixteen active warps instead of eight halve
+// the per-step latency of the gate math, which is what bounds this kernel (10 MUFU ops per unit and step).
+constexpr int kRecRows = 64;
+__global__ void __launch_bounds__(1024, 1)
 lstm_rec_tc_kernel(const float* __restrict__ xz, const __half* __restrict__ whh_pack, __half* __restrict__ hout, long long n, int Tn) {
-  static_assert(R == 32 || R == 64 || R == 128, "rows per CTA = whole TMEM lane quadrants");
   extern __shared__ __align__(128) unsigned char smem[];
   unsigned char* s_h = smem + kRecW;   // W_hh occupies [0, kRecW)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kRecW + kRecH);   // w_full, z_ready, h_ready
   uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 3);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int dir = blockIdx.y;
-  const long long s0 = (long long)blockIdx.x * R;
-  constexpr int kActive = 4 * (R / 32);               // worker warps that own real rows
+  const long long s0 = (long long)blockIdx.x * kRecRows;
+  constexpr int kActive = 16;
   if (tid == 0) {
     mbar_init(&bars[0], 1);
     mbar_init(&bars[1], 1);
     mbar_init(&bars[2], kActive);
     fence_mbar_init();
   }
-  for (int i = tid; i < (int)(kRecH / 16); i += 544) reinterpret_cast<uint4*>(s_h)[i] = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < (int)(kRecH / 16); i += 1024) reinterpret_cast<uint4*>(s_h)[i] = make_uint4(0, 0, 0, 0);
   __syncwarp();
   if (warp == 0) tmem_alloc<512>(tslot);
   fence_proxy_async();
@@ -220,10 +230,9 @@ lstm_rec_tc_kernel(const float* __restrict__ xz, const __half* __restrict__ whh_
   const uint32_t tmem = *tslot;
   const uint32_t sbase = smem_u32(smem);
 
-  if (warp == 16) {
+  if (warp == 3) {
     if (elect_one()) {
       mbar_arrive_expect_tx(&bars[0], kRecW);
-      // bulk copies are limited in size per instruction; 8 x 16 KB
       for (int i = 0; i < 8; ++i)
         bulk_copy_g2s(sbase + i * (kRecW / 8), reinterpret_cast<const unsigned char*>(whh_pack) + (size_t)dir * kRecW + (size_t)i * (kRecW / 8),
                       kRecW / 8, &bars[0]);
@@ -246,67 +255,70 @@ lstm_rec_tc_kernel(const float* __restrict__ xz, const __half* __restrict__ whh_
       }
       __syncwarp();
     }
-  } else if ((warp & 3) < R / 32) {
-    const int quad = warp & 3, cg = warp >> 2;
+  } else if ((warp & 3) < 2) {
+    const int quad = warp & 3, cg = warp >> 2;     // cg 0..7
     const int row = quad * 32 + lane;
     const long long s = s0 + row;
     const bool ok = s < n;
     const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
-    const int u0 = cg * 32;
-    float cst[32];
+    const int u0 = cg * 16;
+    float cst[16];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) cst[i] = 0.f;
+    for (int i = 0; i < 16; ++i) cst[i] = 0.f;
     for (int ti = 0; ti < Tn; ++ti) {
       const int t = dir ? Tn - 1 - ti : ti;
       const float* xrow = xz + ((size_t)(ok ? s : 0) * Tn + t) * (2 * kG4) + (size_t)dir * kG4 + u0;
       __half* hrow = hout + ((size_t)(ok ? s : 0) * Tn + t) * (2 * kU) + (size_t)dir * kU + u0;
-      // first sub-chunk of the projected input is fetched before waiting for the tensor pipe
-      float4 xa[4][2];
+      // pull the projected inputs of the step after next into L2 (they stream from HBM: 345 MB per layer do not stay resident)
+      if (ti + 2 < Tn) {
+        const int t2 = dir ? Tn - 3 - ti : ti + 2;
+        const float* xn = xz + ((size_t)(ok ? s : 0) * Tn + t2) * (2 * kG4) + (size_t)dir * kG4 + u0;
 #pragma unroll
-      for (int gte = 0; gte < 4; ++gte) {
-        xa[gte][0] = __ldg(reinterpret_cast<const float4*>(xrow + gte * kU));
-        xa[gte][1] = __ldg(reinterpret_cast<const float4*>(xrow + gte * kU) + 1);
+        for (int gte = 0; gte < 4; ++gte) asm volatile("prefetch.global.L2 [%0];" ::"l"(xn + gte * kU));
       }
+      // the projected input of the first four units is fetched before waiting for the tensor pipe
+      float4 xa[4];
+#pragma unroll
+      for (int gte = 0; gte < 4; ++gte) xa[gte] = __ldg(reinterpret_cast<const float4*>(xrow + gte * kU));
       if (ti > 0) {
         mbar_wait(&bars[1], (uint32_t)((ti - 1) & 1));
         tc_fence_after();
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        float4 xb[4][2];
+        float4 xb[4];
         if (j < 3) {
 #pragma unroll
-          for (int gte = 0; gte < 4; ++gte) {
-            xb[gte][0] = __ldg(reinterpret_cast<const float4*>(xrow + gte * kU + 8 * (j + 1)));
-            xb[gte][1] = __ldg(reinterpret_cast<const float4*>(xrow + gte * kU + 8 * (j + 1)) + 1);
-          }
+          for (int gte = 0; gte < 4; ++gte) xb[gte] = __ldg(reinterpret_cast<const float4*>(xrow + gte * kU + 4 * (j + 1)));
         }
-        float z[4][8];
+        float z[4][4];
 #pragma unroll
         for (int gte = 0; gte < 4; ++gte) {
           if (ti > 0) {
-            tmem_ld8f(lane_addr + gte * kU + u0 + 8 * j, z[gte]);
+            tmem_ld4f(lane_addr + gte * kU + u0 + 4 * j, z[gte]);
           } else {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) z[gte][i] = 0.f;
+            for (int i = 0; i < 4; ++i) z[gte][i] = 0.f;
           }
-          z[gte][0] += xa[gte][0].x; z[gte][1] += xa[gte][0].y; z[gte][2] += xa[gte][0].z; z[gte][3] += xa[gte][0].w;
-          z[gte][4] += xa[gte][1].x; z[gte][5] += xa[gte][1].y; z[gte][6] += xa[gte][1].z; z[gte][7] += xa[gte][1].w;
+          z[gte][0] += xa[gte].x; z[gte][1] += xa[gte].y; z[gte][2] += xa[gte].z; z[gte][3] += xa[gte].w;
         }
-        float h[8];
+        float h[4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < 4; ++i) {
           const float ig = sigmoid_fast(z[0][i]), fg = sigmoid_fast(z[1][i]), gg = tanh_fast(z[2][i]), og = sigmoid_fast(z[3][i]);
-          const float cn = fg * cst[8 * j + i] + ig * gg;
-          cst[8 * j + i] = cn;
+          const float cn = fg * cst[4 * j + i] + ig * gg;
+          cst[4 * j + i] = cn;
           h[i] = og * tanh_fast(cn);
         }
-        const uint4 hp = pack8h(h);
-        *reinterpret_cast<uint4*>(s_h + (size_t)((u0 >> 3) + j) * (128 * 16) + row * 16) = hp;
-        if (ok) *reinterpret_cast<uint4*>(hrow + 8 * j) = hp;
+        uint2 hp;
+        *reinterpret_cast<__half2*>(&hp.x) = __floats2half2_rn(h[0], h[1]);
+        *reinterpret_cast<__half2*>(&hp.y) = __floats2half2_rn(h[2], h[3]);
+        const int u = u0 + 4 * j;
+        *reinterpret_cast<uint2*>(s_h + (size_t)(u >> 3) * (128 * 16) + row * 16 + (u & 4) * 2) = hp;
+        if (ok) *reinterpret_cast<uint2*>(hrow + 4 * j) = hp;
         if (j < 3) {
 #pragma unroll
-          for (int gte = 0; gte < 4; ++gte) { xa[gte][0] = xb[gte][0]; xa[gte][1] = xb[gte][1]; }
+          for (int gte = 0; gte < 4; ++gte) xa[gte] = xb[gte];
         }
       }
       fence_proxy_async();
@@ -401,7 +413,7 @@ int net_tail_tc_prepare(Ctx* c) {
     ORCAI_CHECK(upload_half(c, wp, &nw->tc_whh[l]));
   }
   ORCAI_CHECK(upload_half(c, pack_gemm_b(nw->h_d1_w.data(), 2 * U, 128, 128), &nw->tc_d1));
-  ORCAI_CUDA(c, cudaFuncSetAttribute(lstm_rec_tc_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRecSmem));
+  ORCAI_CUDA(c, cudaFuncSetAttribute(lstm_rec_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRecSmem));
   nw->tail_tc_ready = true;
   return ORCAI_OK;
 }
@@ -417,16 +429,15 @@ int net_tail_tc(Ctx* c, const float* feat, float* scratch, long long m, float* d
   __half* h1 = reinterpret_cast<__half*>(xz + (size_t)rows * 2 * G);  // (rows, 2U) fp16
   __half* h2 = h1 + (size_t)rows * 2 * U;                             // (rows, 2U) fp16
   float* d1 = reinterpret_cast<float*>(h2 + (size_t)rows * 2 * U);    // (rows, 128) fp32
-  constexpr int R = 64;
-  const dim3 rgrid((unsigned)((m + R - 1) / R), 2);
+  const dim3 rgrid((unsigned)((m + kRecRows - 1) / kRecRows), 2);
   ORCAI_CHECK((run_gemm_tc<float, 256, 0>(c, feat, nw->feat, nw->tc_wih[0], nw->lstm_bih[0], xz, 2 * G, rows, 2 * G, nw->feat)));
   net_mark(c, mk);  // 6: lstm1 input projection
-  lstm_rec_tc_kernel<R><<<rgrid, 544, kRecSmem, c->stream>>>(xz, nw->tc_whh[0], h1, m, Tn);
+  lstm_rec_tc_kernel<<<rgrid, 1024, kRecSmem, c->stream>>>(xz, nw->tc_whh[0], h1, m, Tn);
   c->launches++;
   net_mark(c, mk);  // 7: lstm1 recurrence
   ORCAI_CHECK((run_gemm_tc<__half, 256, 0>(c, h1, 2 * U, nw->tc_wih[1], nw->lstm_bih[1], xz, 2 * G, rows, 2 * G, 2 * U)));
   net_mark(c, mk);  // 8: lstm2 input projection
-  lstm_rec_tc_kernel<R><<<rgrid, 544, kRecSmem, c->stream>>>(xz, nw->tc_whh[1], h2, m, Tn);
+  lstm_rec_tc_kernel<<<rgrid, 1024, kRecSmem, c->stream>>>(xz, nw->tc_whh[1], h2, m, Tn);
   c->launches++;
   net_mark(c, mk);  // 9: lstm2 recurrence
   ORCAI_CHECK((run_gemm_tc<__half, 128, 1>(c, h2, 2 * U, nw->tc_d1, nw->d1_b, d1, 128, rows, 128, 2 * U)));
