@@ -153,7 +153,7 @@ conv0_mma_kernel(const __grid_constant__ CUtensorMap tmS, __half* __restrict__ o
           if (rr < kRT && h2 < Himg && gg >= 1 && ww < Wimg) {
             __half* o = out + (((size_t)b * Himg + h2) * Wimg + ww) * 16 + (part & 1) * 8;
             *reinterpret_cast<uint4*>(o) = val;
-            if (!(h2 & 1) && !(ww & 1)) {   // input of the first residual 1x1/2 convolution
+            if (out_sub != nullptr && !(h2 & 1) && !(ww & 1)) {   // optional even-position copy
               __half* os = out_sub + (((size_t)b * Ho + (h2 >> 1)) * Wo + (ww >> 1)) * 16 + (part & 1) * 8;
               *reinterpret_cast<uint4*>(os) = val;
             }

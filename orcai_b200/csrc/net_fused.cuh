@@ -169,7 +169,7 @@ __device__ __forceinline__ uint4 hmax8(uint4 a, uint4 b) {
 
 template <class G>
 __global__ void __launch_bounds__(G::NTHREADS, G::CTAS)
-fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmR, __half* __restrict__ Yr,
+fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmR, int r_step, __half* __restrict__ Yr,
                    __half* __restrict__ Ysub, int H, int W, int n_strips, long long n_items,
                    const unsigned char* __restrict__ wpack) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -217,7 +217,8 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
 #pragma unroll
           for (int c = 0; c < G::XG; ++c) {
             tma_load_5d(sbase + G::OFF_X + c * G::LBO_X, &tmX, &bars[G::B_X], 0, c, cb, a + 1, (int)b);
-            tma_load_5d(sbase + G::OFF_R + c * G::LBO_R, &tmR, &bars[G::B_X], 0, c, wo0, a >> 1, (int)b);
+            // residual input pixels (2*ho, 2*wo): coordinates in the even-position tensor, or in the full tensor read with stride 2
+            tma_load_5d(sbase + G::OFF_R + c * G::LBO_R, &tmR, &bars[G::B_X], 0, c, wo0 * r_step, (a >> 1) * r_step, (int)b);
           }
         }
         __syncwarp();

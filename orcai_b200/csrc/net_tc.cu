@@ -366,7 +366,7 @@ conv0_direct_kernel(const float* __restrict__ in, int mode, long long first, int
   __half* o = out + (((size_t)b * Himg + hh) * Wimg + ww) * 16;
   reinterpret_cast<uint4*>(o)[0] = v0;
   reinterpret_cast<uint4*>(o)[1] = v1;
-  if (!(hh & 1) && !(ww & 1)) {
+  if (out_sub != nullptr && !(hh & 1) && !(ww & 1)) {
     __half* os = out_sub + (((size_t)b * (Himg >> 1) + (hh >> 1)) * ((Wimg + 1) >> 1) + (ww >> 1)) * 16;
     reinterpret_cast<uint4*>(os)[0] = v0;
     reinterpret_cast<uint4*>(os)[1] = v1;
@@ -652,13 +652,14 @@ EncodeTiledFn encode_tiled_fn() {
 }
 
 // rank-5 map over a (n, h, w, chunks, 8) fp16 NHWC tensor; box = {8 ch, 1 chunk, box_w, box_h, 1 snippet}
-int make_act_map(Ctx* c, CUtensorMap* map, const __half* base, long long n, int h, int w, int cpitch, int box_w, int box_h) {
+// `step` = traversal stride along w and h (2: every other pixel, box_w x box_h pixels are still what lands in shared memory)
+int make_act_map(Ctx* c, CUtensorMap* map, const __half* base, long long n, int h, int w, int cpitch, int box_w, int box_h, int step = 1) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) ORCAI_FAIL(c, ORCAI_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
   const cuuint64_t dims[5] = {8, (cuuint64_t)(cpitch / 8), (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
   const cuuint64_t strides[4] = {16, (cuuint64_t)cpitch * 2, (cuuint64_t)w * cpitch * 2, (cuuint64_t)h * w * cpitch * 2};
-  const cuuint32_t box[5] = {8, 1, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
-  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const cuuint32_t box[5] = {8, 1, (cuuint32_t)(box_w * step), (cuuint32_t)(box_h * step), 1};
+  const cuuint32_t estr[5] = {1, 1, (cuuint32_t)step, (cuuint32_t)step, 1};
   const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<__half*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) ORCAI_FAIL(c, ORCAI_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for tensor (%lld, %d, %d, %d)", (int)r, n, h, w, cpitch);
@@ -674,8 +675,11 @@ int run_fused_block(Ctx* c, int blk, const __half* xr, const __half* xs, __half*
   const long long grid = std::min<long long>(items, (long long)c->sm_count * G::CTAS);
   CUtensorMap tmx, tmr;
   ORCAI_CHECK(make_act_map(c, &tmx, xr, m, Himg, Wimg, G::ICP, G::WP, G::S + 2));
-  ORCAI_CHECK(make_act_map(c, &tmr, xs, m, Ho, Wo, G::ICP, G::CP, G::S / 2));
-  fused::fused_block_kernel<G><<<(unsigned)grid, G::NTHREADS, G::SMEM, c->stream>>>(tmx, tmr, yr, ys, Himg, Wimg, n_strips, items,
+  // residual input = x at even positions: its own tensor, or (xs == nullptr: x is non-negative, ReLU(x) == x) the full tensor
+  // traversed with element stride 2
+  if (xs) ORCAI_CHECK(make_act_map(c, &tmr, xs, m, Ho, Wo, G::ICP, G::CP, G::S / 2));
+  else ORCAI_CHECK(make_act_map(c, &tmr, xr, m, Himg, Wimg, G::ICP, G::CP, G::S / 2, 2));
+  fused::fused_block_kernel<G><<<(unsigned)grid, G::NTHREADS, G::SMEM, c->stream>>>(tmx, tmr, xs ? 1 : 2, yr, ys, Himg, Wimg, n_strips, items,
                                                                                    static_cast<const unsigned char*>(nw->fb_w[blk]));
   c->launches++;
   ORCAI_CUDA(c, cudaGetLastError());
@@ -751,7 +755,7 @@ int forward_fused(Ctx* c, const float* d_in, int input_mode, int64_t first, int6
       const int tiles_per = (Himg + conv0::kRT - 1) / conv0::kRT;
       const long long n_tiles = m * tiles_per;
       const long long grid = std::min<long long>(n_tiles, (long long)c->sm_count * 4);
-      conv0::conv0_mma_kernel<<<(unsigned)grid, 160, conv0::kSmem, c->stream>>>(tms, act[0], acts[0], Himg, Wf, tiles_per, n_tiles,
+      conv0::conv0_mma_kernel<<<(unsigned)grid, 160, conv0::kSmem, c->stream>>>(tms, act[0], static_cast<H*>(nullptr), Himg, Wf, tiles_per, n_tiles,
                                                                                static_cast<const unsigned char*>(nw->conv0_mma_w));
       c->launches += 2;
       ORCAI_CUDA(c, cudaGetLastError());
@@ -759,13 +763,13 @@ int forward_fused(Ctx* c, const float* d_in, int input_mode, int64_t first, int6
       const int tiles_w = (Wf + kC0TW - 1) / kC0TW, tiles_h = (Himg + kC0TH - 1) / kC0TH;
       const float* src = (input_mode == 0) ? d_in : d_in + (size_t)s0 * Himg * Wf;
       conv0_direct_kernel<<<(unsigned)(m * tiles_w * tiles_h), 256, 0, c->stream>>>(src, input_mode, first + s0, shift, input_mode == 0 ? kRawLd : Wf,
-                                                                                   Himg, Wf, c->d_sel, act[0], acts[0], tiles_w, tiles_h);
+                                                                                   Himg, Wf, c->d_sel, act[0], static_cast<H*>(nullptr), tiles_w, tiles_h);
       c->launches++;
       ORCAI_CUDA(c, cudaGetLastError());
     }
     net_mark(c, mk);  // 0: conv0
     if (stop == 0) { set_debug(nw, act[0], 1, m, hs[0], ws[0], 16, 16); return ORCAI_OK; }
-    ORCAI_CHECK((run_fused_block<FB1>(c, 0, act[0], acts[0], act[1], acts[1], m, hs[0], ws[0])));
+    ORCAI_CHECK((run_fused_block<FB1>(c, 0, act[0], static_cast<const H*>(nullptr), act[1], acts[1], m, hs[0], ws[0])));
     net_mark(c, mk);  // 1
     if (stop == 1) { set_debug(nw, act[1], 1, m, hs[1], ws[1], 30, cp[1]); return ORCAI_OK; }
     if (stop == 21) { set_debug(nw, acts[1], 1, m, hs[2], ws[2], 30, cp[1]); return ORCAI_OK; }
