@@ -15,7 +15,6 @@ from __future__ import annotations
 
 import gzip
 import os
-import queue
 import threading
 from concurrent.futures import ThreadPoolExecutor
 from importlib.resources import files
@@ -460,26 +459,23 @@ def predict(
     if len(devices) <= 1:
         pipelined(model, rows, progressbar, lambda: progressbar.update(1))
     else:
-        # shard by recording: one worker (context + stream) per GPU pulling rows from a shared queue; host-side gather only
+        # shard by recording: one worker thread (context + streams) per GPU; rows are assigned
+        # longest-first (LPT on the file sizes) and every worker pipelines its own share; host-side gather only
         from orcai_b200.model import OrcaiModel
+        from orcai_b200.sharding import assign_rows, recording_costs
 
         models = [model] + [OrcaiModel(orcai_parameter, shape, model.weights, device=d) for d in devices[1:]]
-        work: queue.Queue = queue.Queue()
-        for i in rows:
-            work.put(i)
+        plan = assign_rows(recording_costs([row_path(i) for i in rows]), len(models))
         lock = threading.Lock()
 
-        def worker(mdl):
-            while True:
-                try:
-                    i = work.get_nowait()
-                except queue.Empty:
-                    return
-                run_row(i, mdl, None)
-                with lock:
-                    progressbar.update(1)
+        def tick():
+            with lock:
+                progressbar.update(1)
 
-        threads = [threading.Thread(target=worker, args=(m,), daemon=True) for m in models]
+        threads = [
+            threading.Thread(target=pipelined, args=(m, [rows[j] for j in share], None, tick), daemon=True)
+            for m, share in zip(models, plan)
+        ]
         for t in threads:
             t.start()
         for t in threads:

@@ -191,3 +191,37 @@ def test_synthetic_audio_is_deterministic():
     a = synth_pcm16(1.0, seed=7)
     b = synth_pcm16(1.0, seed=7)
     assert a.dtype == np.int16 and len(a) == 48000 and np.array_equal(a, b) and not np.array_equal(a, synth_pcm16(1.0, seed=8))
+
+
+def test_precision_selector(monkeypatch):
+    from orcai_b200 import model
+
+    monkeypatch.delenv("ORCAI_B200_PRECISION", raising=False)
+    assert model.precision_from_env() == "fast" and model.PRECISION_PATHS["fast"] == 3
+    monkeypatch.setenv("ORCAI_B200_PRECISION", "Reference ")
+    assert model.precision_from_env() == "reference" and model.PRECISION_PATHS["reference"] == 0
+    monkeypatch.setenv("ORCAI_B200_PRECISION", "bf16")
+    with pytest.raises(ValueError, match="ORCAI_B200_PRECISION"):
+        model.precision_from_env()
+
+
+def test_predict_stream_order_of_calls():
+    """Context.predict_stream: prefetch(k+1) is issued after swap(k) and before predict(k); results come back in order."""
+    from orcai_b200._lib import Context
+
+    log = []
+
+    class Fake:
+        prefetch_pcm = lambda self, pcm: log.append(("prefetch", int(pcm[0])))  # noqa: E731
+        swap_pcm = lambda self: log.append(("swap",))  # noqa: E731
+
+        def predict_pcm(self, pcm, threshold=0.5, want_agg=True, resident=False):
+            assert resident
+            log.append(("predict", int(pcm[0])))
+            return int(pcm[0])
+
+    recs = [np.array([k], np.int16) for k in range(3)]
+    out = list(Context.predict_stream(Fake(), iter(recs)))
+    assert out == [0, 1, 2]
+    assert log == [("prefetch", 0), ("swap",), ("prefetch", 1), ("predict", 0), ("swap",), ("prefetch", 2), ("predict", 1), ("swap",), ("predict", 2)]
+    assert list(Context.predict_stream(Fake(), iter([]))) == []
