@@ -166,6 +166,7 @@ def main() -> None:
     ap.add_argument("--hours", type=float, default=1.0, help="length of the synthetic recording each GPU annotates per step")
     ap.add_argument("--cpu-sample-seconds", type=float, default=600.0, help="bounded CPU-oracle sample (BASELINE config 0: one 10-min recording)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the fp32-path comparison of the measured recording")
     ap.add_argument("--chunk", type=int, default=0, help="snippets per network chunk (0 = library default)")
     ap.add_argument("--net-path", type=int, default=3, choices=[0, 1, 2, 3], help="0 fp32 CUDA cores, 1 fp16 tcgen05 layer-wise, 2 bf16 tcgen05 layer-wise, 3 fp16 tcgen05 fused residual blocks")
     ap.add_argument("--stft-f64", type=int, default=1, choices=[0, 1], help="1 float64 FFT (parity grade, default), 0 float32 FFT")
@@ -258,6 +259,23 @@ def main() -> None:
     barrier()
     t_e2e = max_over_ranks(time.perf_counter() - t0)
 
+    # ---------------- parity of the measured path (outside every timed region) ----------------
+    parity = None
+    if rank == 0 and args.net_path != 0 and not args.no_parity:
+        # the same recording through the fp32 reference-grade network path: aggregated probabilities and segments
+        st_f, agg_f, cnt_f, lab_f, sta_f, sto_f = ctx.predict_pcm(pcm_pinned, want_agg=True, resident=True)
+        ctx.set_option("net_path", 0)
+        st_r, agg_r, cnt_r, lab_r, sta_r, sto_r = ctx.predict_pcm(pcm_pinned, want_agg=True, resident=True)
+        ctx.set_option("net_path", args.net_path)
+        seg_f = set(zip(lab_f.tolist(), sta_f.tolist(), sto_f.tolist()))
+        seg_r = set(zip(lab_r.tolist(), sta_r.tolist(), sto_r.tolist()))
+        mask_f, mask_r = agg_f > 0.25, agg_r > 0.25
+        parity = {"against": "fp32 CUDA-core network path (1e-6 vs the CPU oracle) on the same recording",
+                  "probability_max_abs_dev": float(np.abs(agg_f - agg_r).max()), "probability_mean_abs_dev": float(np.abs(agg_f - agg_r).mean()),
+                  "frames_with_different_mask_frac": float((mask_f != mask_r).mean()),
+                  "segments": len(seg_f), "segments_reference_path": len(seg_r), "segments_identical": len(seg_f & seg_r),
+                  "spectrogram_stats_equal": bool(st_f.lo == st_r.lo and st_f.hi == st_r.hi and st_f.db_ref == st_r.db_ref)}
+
     hours_total = args.hours * world * args.steps
     value = hours_total / t_res
     e2e_value = hours_total / t_e2e
@@ -300,6 +318,7 @@ def main() -> None:
                                                   "lstm2_rec", "dense"], [round(v, 4) for v in net_stage[:11]])) | {"snippets": int(net_stage[15])},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(pcm.nbytes), "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * t_e2e / args.steps},
             "gpu_launches": int(launches),
+            "parity": parity,
             "clocks": clocks,
             "roofline": roofline_main,
             "roofline_network": {"kernel": "orcai-V1 forward (all layer kernels)", "bound": "tensor", "achieved": net_tflops, "peak": peaks["bf16_tflops_sustained"],

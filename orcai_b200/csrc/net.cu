@@ -18,6 +18,8 @@
 #include <map>
 #include <string>
 
+#include <atomic>
+
 #include "common.h"
 #include "net.h"
 
@@ -334,10 +336,11 @@ lstm_rec_kernel(const float* __restrict__ xz, const float* __restrict__ whh, flo
 template <int CIN, int COUT, bool RI, bool RO>
 int run_sepconv(Ctx* c, const float* in, float* out, long long n, int H, int W, const NetWeights::Sep& s) {
   using S = SepSmem<CIN, COUT>;
-  static bool attr = false;
-  if (!attr) {
+  // the attribute is per device: remember which devices have it (several contexts can live in one process)
+  static std::atomic<unsigned long long> attr_devices{0ull};
+  if (!((attr_devices.load() >> (c->device & 63)) & 1ull)) {
     ORCAI_CUDA(c, cudaFuncSetAttribute(sepconv_kernel<CIN, COUT, RI, RO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::bytes));
-    attr = true;
+    attr_devices.fetch_or(1ull << (c->device & 63));
   }
   const int tiles_w = (W + kTW - 1) / kTW, tiles_h = (H + kTH - 1) / kTH;
   const long long grid = n * tiles_w * tiles_h;

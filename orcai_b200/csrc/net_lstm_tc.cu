@@ -14,6 +14,8 @@
 #include <algorithm>
 #include <cstring>
 
+#include <atomic>
+
 #include "common.h"
 #include "net.h"
 #include "tc_common.cuh"
@@ -381,10 +383,11 @@ int upload_half(Ctx* c, const std::vector<__half>& v, __half** out) {
 template <typename TA, int BN, int ACT>
 int run_gemm_tc(Ctx* c, const TA* A, int lda, const __half* Bp, const float* bias, float* C, int ldc, long long M, int N, int K) {
   using S = GemmSmem<BN>;
-  static bool attr = false;
-  if (!attr) {
+  // the attribute is per device: remember which devices have it (several contexts can live in one process)
+  static std::atomic<unsigned long long> attr_devices{0ull};
+  if (!((attr_devices.load() >> (c->device & 63)) & 1ull)) {
     ORCAI_CUDA(c, cudaFuncSetAttribute(gemm_tc_kernel<TA, BN, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::BYTES));
-    attr = true;
+    attr_devices.fetch_or(1ull << (c->device & 63));
   }
   dim3 grid((unsigned)(N / BN), (unsigned)((M + kGM - 1) / kGM));
   gemm_tc_kernel<TA, BN, ACT><<<grid, 160, S::BYTES, c->stream>>>(A, lda, Bp, bias, C, ldc, M, K);

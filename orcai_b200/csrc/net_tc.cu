@@ -23,6 +23,8 @@
 #include <algorithm>
 #include <cstring>
 
+#include <atomic>
+
 #include "common.h"
 #include "net.h"
 #include "tc_common.cuh"
@@ -431,10 +433,11 @@ int prepare(Ctx* c, int fmt) {
 template <int CIN, int COUT, bool RI, bool RO, typename H, bool OUT_F32>
 int run_sep(Ctx* c, const H* in, void* out, long long n, int Himg, int Wimg, const TcSep& w) {
   using S = SepTc<CIN, COUT>;
-  static bool attr = false;
-  if (!attr) {
+  // the attribute is per device: remember which devices have it (several contexts can live in one process)
+  static std::atomic<unsigned long long> attr_devices{0ull};
+  if (!((attr_devices.load() >> (c->device & 63)) & 1ull)) {
     ORCAI_CUDA(c, cudaFuncSetAttribute(sep_tc_kernel<CIN, COUT, RI, RO, H, OUT_F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::smem));
-    attr = true;
+    attr_devices.fetch_or(1ull << (c->device & 63));
   }
   const int tiles_w = (Wimg + kTileW - 1) / kTileW, tiles_h = (Himg + kTileH - 1) / kTileH;
   const long long total = n * tiles_w * tiles_h;

@@ -15,6 +15,8 @@
 //                    complex64 before |.|^2 and log10f - parity grade (default).
 //   RealT = float  : float32 FFT, lg2.approx for the logarithm - the fast variant (tail cells that
 //                    sit > 60 dB below their own frame's peak can be off by up to ~2e-3 dB).
+#include <atomic>
+
 #include "common.h"
 #include "stft_core.cuh"
 #include "stft_tables.h"
@@ -110,11 +112,12 @@ stft_db_kernel(const SampleT* __restrict__ pcm, long long n_samples, long long T
 
 template <typename SampleT, typename RealT>
 int launch_variant(Ctx* c, const void* d_pcm, int64_t n_samples, int64_t T, float* d_raw, const void* tab) {
-  static bool attr_set = false;
+  // the attribute is per device: remember which devices have it (several contexts can live in one process)
+  static std::atomic<unsigned long long> attr_devices{0ull};
   constexpr size_t smem = stft_smem_bytes<RealT>();
-  if (!attr_set) {
+  if (!((attr_devices.load() >> (c->device & 63)) & 1ull)) {
     ORCAI_CUDA(c, cudaFuncSetAttribute(stft_db_kernel<SampleT, RealT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    attr_devices.fetch_or(1ull << (c->device & 63));
   }
   const long long n_groups = (T + kFramesPerWarp - 1) / kFramesPerWarp;
   long long ctas = (n_groups + kWarpsPerCta - 1) / kWarpsPerCta;

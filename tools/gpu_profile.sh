@@ -4,7 +4,7 @@
 set -u
 TAG=${1:-prof}; shift
 KERNELS=${1:-}; shift
-CMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --hours 0.1 $*"
+CMD="python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-parity --hours 0.1 $*"
 mkdir -p gpurun_out
 $CMD > gpurun_out/${TAG}_plain.log 2>&1 || { echo "plain run failed"; tail -20 gpurun_out/${TAG}_plain.log; exit 1; }
 tail -1 gpurun_out/${TAG}_plain.log
