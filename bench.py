@@ -166,6 +166,7 @@ def main() -> None:
     ap.add_argument("--hours", type=float, default=1.0, help="length of the synthetic recording each GPU annotates per step")
     ap.add_argument("--cpu-sample-seconds", type=float, default=600.0, help="bounded CPU-oracle sample (BASELINE config 0: one 10-min recording)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-calibrate", action="store_true", help="skip the weight-rounding bias calibration of the tensor-core paths")
     ap.add_argument("--no-parity", action="store_true", help="skip the fp32-path comparison of the measured recording")
     ap.add_argument("--chunk", type=int, default=0, help="snippets per network chunk (0 = library default)")
     ap.add_argument("--net-path", type=int, default=3, choices=[0, 1, 2, 3], help="0 fp32 CUDA cores, 1 fp16 tcgen05 layer-wise, 2 bf16 tcgen05 layer-wise, 3 fp16 tcgen05 fused residual blocks")
@@ -200,6 +201,8 @@ def main() -> None:
         ctx.set_option("chunk", args.chunk)
     ctx.set_option("net_path", args.net_path)
     ctx.set_option("stft_f64", args.stft_f64)
+    if args.net_path != 0 and not args.no_calibrate:
+        ctx.calibrate()   # what OrcaiModel does when it loads weights (built-in synthetic calibration recording, not the bench file)
 
     # K <= 8 distinct seeded files; rank r annotates file r % 8
     pcm = make_recording(args.hours, 20251018 + (rank % 8))

@@ -143,6 +143,14 @@ int orcai_predict_pcm(orcai_ctx* ctx, const void* pcm_host, int32_t dtype, int64
                       int32_t* seg_label, int64_t* seg_start, int64_t* seg_stop,
                       int64_t seg_capacity, int64_t* n_segments);
 
+/* ---- calibration of the 16-bit tensor-core paths ------------------------------------------------ */
+/* fp16 weight rounding is identical at every pixel, so (to first order) it shifts each layer's output by the constant
+ * sum_k dW[k][n] * mean(A[k]).  This call measures the channel means of every GEMM input on the first `max_snippets`
+ * (<= 0: 8) snippets of the RESIDENT recording (after orcai_spectrogram_resident) and folds the correction into the bias
+ * rows of the tensor-core operands (they are split fp16 hi+lo, i.e. exact).  Deterministic; the fp32 path is not affected;
+ * orcai_load_weights clears it.  The Python layer calibrates on a built-in synthetic recording when weights are loaded. */
+int orcai_calibrate(orcai_ctx* ctx, int64_t max_snippets);
+
 /* ---- knobs ---------------------------------------------------------------------------------- */
 /* Options: "net_path"  0 = fp32 CUDA-core path (reference grade, library default), 1 = fp16 / 2 = bf16 layer-wise tcgen05
  *                      path, 3 = fp16 fused tcgen05 path (what orcai_b200's Python layer selects unless

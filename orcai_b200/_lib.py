@@ -107,6 +107,7 @@ _SIGNATURES = {
     "orcai_predict_resident": (C.c_int, [_P, C.c_double, C.POINTER(SpecStats), _P, _P, _P, _P, _P, C.c_int64, C.POINTER(C.c_int64)]),
     "orcai_predict_pcm": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_double, C.POINTER(SpecStats), _P, _P, _P, _P, _P, C.c_int64, C.POINTER(C.c_int64)]),
     "orcai_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),
+    "orcai_calibrate": (C.c_int, [_P, C.c_int64]),
     "orcai_prefetch_pcm": (C.c_int, [_P, _P, C.c_int32, C.c_int64]),
     "orcai_swap_pcm": (C.c_int, [_P]),
     "orcai_debug_read": (C.c_int, [_P, _P, C.c_int64, C.POINTER(C.c_int64)]),
@@ -238,6 +239,20 @@ class Context:
         c_sizes = (C.c_int64 * n)(*[a.size for a in arrs])
         self._check(self.lib.orcai_load_weights(self._h, c_names, c_data, c_sizes, n))
         self.weights_loaded = True
+
+    def calibrate(self, pcm: np.ndarray | None = None, max_snippets: int = 8):
+        """Fold the mean effect of fp16 weight rounding into the biases of the tensor-core operands (orcai_calibrate).
+
+        `pcm`: a representative recording (>= one snippet); default: a built-in deterministic synthetic recording.
+        Replaces the context's resident recording.
+        """
+        if pcm is None:
+            from orcai_b200.synth import synth_pcm16
+
+            pcm = synth_pcm16(24.0, seed=20251018, calls_per_minute=30.0)
+        self.upload_pcm(pcm)
+        self.spectrogram_resident(False)
+        self._check(self.lib.orcai_calibrate(self._h, int(max_snippets)))
 
     # -- spectrogram ---------------------------------------------------------------------------
     @staticmethod

@@ -199,6 +199,12 @@ int orcai_get_timings(const orcai_ctx* c, orcai_timings* out) {
   return ORCAI_OK;
 }
 
+int orcai_calibrate(orcai_ctx* c, int64_t max_snippets) {
+  if (!c) return ORCAI_ERR_ARG;
+  ORCAI_CUDA(c, cudaSetDevice(c->device));
+  return net_calibrate(c, max_snippets);
+}
+
 int orcai_set_option(orcai_ctx* c, const char* key, int64_t value) {
   if (!c || !key) return ORCAI_ERR_ARG;
   if (!strcmp(key, "chunk")) return net_set_chunk(c, (int)value);

@@ -109,6 +109,7 @@ int net_set_chunk(Ctx* c, int chunk);
 void net_collect_stage_times(Ctx* c);
 int net_set_path(Ctx* c, int path);
 int net_set_tail_path(Ctx* c, int path);
+int net_calibrate(Ctx* c, int64_t max_snippets);
 int net_set_conv0_path(Ctx* c, int path);
 int net_set_debug_stop(Ctx* c, int stage);
 int net_debug_read(Ctx* c, float* out_host, int64_t capacity, int64_t* dims_out);

@@ -553,6 +553,7 @@ int net_load_weights(Ctx* c, const char* const* names, const float* const* data,
   nw->tc_ready[0] = nw->tc_ready[1] = false;
   nw->fused_ready = false;
   nw->tail_tc_ready = false;
+  nw->calib = Calib();
   const orcai_params& P = c->p;
   if (P.n_blocks != 4 || P.filters[0] != 30 || P.filters[1] != 40 || P.filters[2] != 50 || P.filters[3] != 60 ||
       P.kernel_size != 3 || P.lstm_units != 128)
@@ -613,6 +614,7 @@ int net_load_weights(Ctx* c, const char* const* names, const float* const* data,
     }
     nw->h_lstm_wih[l] = wih;
     nw->h_lstm_whh[l] = whh;
+    nw->h_lstm_bih[l] = bih;
     ORCAI_CHECK(upload(c, wih, &nw->lstm_wih[l]));
     ORCAI_CHECK(upload(c, bih, &nw->lstm_bih[l]));
     ORCAI_CHECK(upload(c, whh, &nw->lstm_whh[l]));
@@ -626,7 +628,8 @@ int net_load_weights(Ctx* c, const char* const* names, const float* const* data,
     if (!k1 || !b1 || !k2 || !b2 || !bn_fold(ht, "bn_dense", kDense, &s, &t)) return ORCAI_ERR_ARG;
     nw->h_d1_w.assign(k1, k1 + (size_t)2 * U * kDense);
     ORCAI_CHECK(upload(c, nw->h_d1_w, &nw->d1_w));
-    ORCAI_CHECK(upload(c, std::vector<float>(b1, b1 + kDense), &nw->d1_b));
+    nw->h_d1_b.assign(b1, b1 + kDense);
+    ORCAI_CHECK(upload(c, nw->h_d1_b, &nw->d1_b));
     std::vector<float> w2((size_t)kDense * nw->L), bb2(nw->L);
     for (int o = 0; o < nw->L; ++o) {
       double acc = b2[o];

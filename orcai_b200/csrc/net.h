@@ -13,8 +13,22 @@ struct TcSep {            // one fused 3x3 implicit-GEMM layer of the tensor-cor
   float* bias = nullptr;  // NP floats (folded BatchNorm), zero padded
 };
 
+// Channel means of every GEMM's A operand on a calibration recording (net_calibrate).  fp16 weight rounding is the same at
+// every pixel, so its effect on a layer's output is, to first order, the constant  sum_k dW[k][n] * mean(A[k])  per output
+// channel; the tensor-core paths subtract exactly that from the (split-fp16, exact) bias rows when they pack their operands.
+struct Calib {
+  bool valid = false;
+  double spec = 0.0;                          // normalised spectrogram value (entry convolution input)
+  std::vector<double> in_relu[kMaxBlocks];    // ReLU(block input)                 -> first separable convolution
+  std::vector<double> in_even[kMaxBlocks];    // block input at even positions     -> residual 1x1/2 convolution
+  std::vector<double> s1[kMaxBlocks];         // first sepconv output (post-ReLU)  -> second separable convolution
+  std::vector<double> fin;                    // block-4 output                    -> final separable convolution
+  std::vector<double> feat, h1, h2;           // inputs of LSTM 1, LSTM 2 (and the recurrent terms), Dense(128)
+};
+
 struct NetWeights {
   bool loaded = false;
+  Calib calib;
   int n_blocks = 0;
   int filters[kMaxBlocks] = {};
   int Wf = 0, H = 0, U = 0, L = 0, feat = 0;
@@ -51,6 +65,9 @@ struct NetWeights {
   void* fb_w[kMaxBlocks] = {};
   float* fb_bias[kMaxBlocks] = {};
   int chunk_fused = 2048;
+  TcSep fb_fin;                  // final separable convolution with the calibrated bias (fused path)
+  float* tc_bih[2] = {};         // projection biases with the weight-rounding correction folded in
+  float* tc_d1_b = nullptr;
   void* conv0_mma_w = nullptr;   // banded B operand of the tensor-core entry convolution (conv0_mma.cuh)
   int conv0_path = 1;            // fused path: 1 = tensor-core pixel-group convolution, 0 = fp32 CUDA-core convolution
   // tensor-core recurrent tail (net_lstm_tc.cu)
@@ -59,7 +76,7 @@ struct NetWeights {
   __half* tc_wih[2] = {};     // packed B blocks of the input projections [I][2*4U]
   __half* tc_whh[2] = {};     // [2 directions][4U x U] canonical K-major
   __half* tc_d1 = nullptr;    // Dense(128) B blocks
-  std::vector<float> h_lstm_wih[2], h_lstm_whh[2], h_d1_w;
+  std::vector<float> h_lstm_wih[2], h_lstm_whh[2], h_lstm_bih[2], h_d1_w, h_d1_b;
   std::vector<float> h_res_w[kMaxBlocks], h_res_b[kMaxBlocks];
   int debug_stop = -1;        // stop the forward after this stage (debug reads), -1 = run everything
   // last debug buffer: kind 0 f32, 1 fp16, 2 bf16 ; NHWC with channel pitch dbg_pitch
@@ -80,6 +97,7 @@ int net_tail_fp32(Ctx* c, const float* feat, float* scratch, long long m, float*
 int net_upload(Ctx* c, const std::vector<float>& v, float** dptr);
 int net_tail_tc(Ctx* c, const float* feat, float* scratch, long long m, float* d_preds_out, bool mark);
 int net_tc_prepare(Ctx* c, int fmt);
+int net_calibrate(Ctx* c, int64_t max_snippets);
 int net_forward_tc(Ctx* c, const float* d_in, int input_mode, int64_t first, int64_t n, float* d_preds);
 
 }  // namespace orcai

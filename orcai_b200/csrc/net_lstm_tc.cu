@@ -403,6 +403,8 @@ int net_tail_tc_prepare(Ctx* c) {
   if (nw->tail_tc_ready) return ORCAI_OK;
   const int U = nw->U, G = 4 * U;
   if (U != kU) ORCAI_FAIL(c, ORCAI_ERR_ARG, "tensor-core LSTM kernels are built for 128 units");
+  const Calib& cal = nw->calib;
+  auto qerr = [](float v) { return (double)__half2float(__float2half_rn(v)) - (double)v; };
   for (int l = 0; l < 2; ++l) {
     const int I = l == 0 ? nw->feat : 2 * U;
     ORCAI_CHECK(upload_half(c, pack_gemm_b(nw->h_lstm_wih[l].data(), I, 2 * G, 256), &nw->tc_wih[l]));
@@ -414,8 +416,32 @@ int net_tail_tc_prepare(Ctx* c) {
           wp[(size_t)d * G * U + ((size_t)(n / 8) * (U / 8) * 128 + (size_t)(k / 8) * 128 + (n % 8) * 16 + (k % 8) * 2) / 2] =
               __float2half_rn(nw->h_lstm_whh[l][(size_t)d * U * G + (size_t)k * G + n]);
     ORCAI_CHECK(upload_half(c, wp, &nw->tc_whh[l]));
+    // projection bias minus what fp16 rounding of W_ih and W_hh adds on average (Calib, net.h)
+    std::vector<float> bih(nw->h_lstm_bih[l]);
+    if (cal.valid) {
+      const std::vector<double>& mu_in = l == 0 ? cal.feat : cal.h1;
+      const std::vector<double>& mu_h = l == 0 ? cal.h1 : cal.h2;
+      for (int n = 0; n < 2 * G; ++n) {
+        double dsum = 0.0;
+        for (int k = 0; k < I; ++k) dsum += qerr(nw->h_lstm_wih[l][(size_t)k * 2 * G + n]) * mu_in[k];
+        const int d = n / G, nn = n % G;
+        for (int k = 0; k < U; ++k) dsum += qerr(nw->h_lstm_whh[l][(size_t)d * U * G + (size_t)k * G + nn]) * mu_h[(size_t)d * U + k];
+        bih[n] = (float)((double)bih[n] - dsum);
+      }
+    }
+    ORCAI_CHECK(net_upload(c, bih, &nw->tc_bih[l]));
   }
   ORCAI_CHECK(upload_half(c, pack_gemm_b(nw->h_d1_w.data(), 2 * U, 128, 128), &nw->tc_d1));
+  {
+    std::vector<float> b1(nw->h_d1_b);
+    if (cal.valid)
+      for (int n = 0; n < 128; ++n) {
+        double dsum = 0.0;
+        for (int k = 0; k < 2 * U; ++k) dsum += qerr(nw->h_d1_w[(size_t)k * 128 + n]) * cal.h2[k];
+        b1[n] = (float)((double)b1[n] - dsum);
+      }
+    ORCAI_CHECK(net_upload(c, b1, &nw->tc_d1_b));
+  }
   ORCAI_CUDA(c, cudaFuncSetAttribute(lstm_rec_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRecSmem));
   nw->tail_tc_ready = true;
   return ORCAI_OK;
@@ -433,17 +459,17 @@ int net_tail_tc(Ctx* c, const float* feat, float* scratch, long long m, float* d
   __half* h2 = h1 + (size_t)rows * 2 * U;                             // (rows, 2U) fp16
   float* d1 = reinterpret_cast<float*>(h2 + (size_t)rows * 2 * U);    // (rows, 128) fp32
   const dim3 rgrid((unsigned)((m + kRecRows - 1) / kRecRows), 2);
-  ORCAI_CHECK((run_gemm_tc<float, 256, 0>(c, feat, nw->feat, nw->tc_wih[0], nw->lstm_bih[0], xz, 2 * G, rows, 2 * G, nw->feat)));
+  ORCAI_CHECK((run_gemm_tc<float, 256, 0>(c, feat, nw->feat, nw->tc_wih[0], nw->tc_bih[0], xz, 2 * G, rows, 2 * G, nw->feat)));
   net_mark(c, mk);  // 6: lstm1 input projection
   lstm_rec_tc_kernel<<<rgrid, 1024, kRecSmem, c->stream>>>(xz, nw->tc_whh[0], h1, m, Tn);
   c->launches++;
   net_mark(c, mk);  // 7: lstm1 recurrence
-  ORCAI_CHECK((run_gemm_tc<__half, 256, 0>(c, h1, 2 * U, nw->tc_wih[1], nw->lstm_bih[1], xz, 2 * G, rows, 2 * G, 2 * U)));
+  ORCAI_CHECK((run_gemm_tc<__half, 256, 0>(c, h1, 2 * U, nw->tc_wih[1], nw->tc_bih[1], xz, 2 * G, rows, 2 * G, 2 * U)));
   net_mark(c, mk);  // 8: lstm2 input projection
   lstm_rec_tc_kernel<<<rgrid, 1024, kRecSmem, c->stream>>>(xz, nw->tc_whh[1], h2, m, Tn);
   c->launches++;
   net_mark(c, mk);  // 9: lstm2 recurrence
-  ORCAI_CHECK((run_gemm_tc<__half, 128, 1>(c, h2, 2 * U, nw->tc_d1, nw->d1_b, d1, 128, rows, 128, 2 * U)));
+  ORCAI_CHECK((run_gemm_tc<__half, 128, 1>(c, h2, 2 * U, nw->tc_d1, nw->tc_d1_b, d1, 128, rows, 128, 2 * U)));
   {
     const long long grid = std::min<long long>((rows + 7) / 8, (long long)c->sm_count * 8);
     dense_out_kernel<<<(unsigned)grid, 256, 0, c->stream>>>(d1, nw->d2_w, nw->d2_b, d_preds_out, rows, L);

@@ -470,8 +470,55 @@ inline void set_debug(NetWeights* nw, const void* p, int kind, long long n, int 
   nw->dbg_ptr = p; nw->dbg_kind = kind; nw->dbg_n = n; nw->dbg_h = h; nw->dbg_w = w; nw->dbg_c = ch; nw->dbg_pitch = pitch;
 }
 
+// ---- calibration: per-channel sums of activation tensors (net_calibrate) ----------------------------------
+// x: (n_rows, pitch) of fp32 (kind 0) or fp16 (kind 1); rows are pixels of (.., Himg, Wimg) images when `even` is set
+__global__ void __launch_bounds__(256)
+channel_sum_kernel(const void* __restrict__ x, int kind, long long n_rows, int pitch, int C, int relu, int Himg, int Wimg, int even,
+                   double* __restrict__ sums) {
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  for (int ch = tx; ch < C; ch += 64) {
+    double acc = 0.0;
+    for (long long r = (long long)blockIdx.x * 4 + ty; r < n_rows; r += (long long)gridDim.x * 4) {
+      if (even) {
+        const int w = (int)(r % Wimg), h = (int)((r / Wimg) % Himg);
+        if ((w | h) & 1) continue;
+      }
+      float v = kind == 0 ? static_cast<const float*>(x)[(size_t)r * pitch + ch] : __half2float(static_cast<const __half*>(x)[(size_t)r * pitch + ch]);
+      if (relu) v = fmaxf(v, 0.f);
+      acc += (double)v;
+    }
+    atomicAdd(&sums[ch], acc);
+  }
+}
+
+// mean of the normalised spectrogram over rows [row0, row0 + n_rows) of the raw dB buffer
+__global__ void __launch_bounds__(256)
+spec_sum_kernel(const float* __restrict__ raw, long long n_rows, int ld, int nb, const SelectState* __restrict__ st, double* __restrict__ sum) {
+  const float db_ref = st->db_ref, lo = st->lo, hi = st->hi, range = hi - lo;
+  double acc = 0.0;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_rows * nb; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / nb;
+    const int b = (int)(i - r * nb);
+    float v = fmaxf(raw[(size_t)r * ld + b] - db_ref, -kTopDbF);
+    acc += (double)__fdiv_rn(fminf(fmaxf(v, lo), hi) - lo, range);
+  }
+  atomicAdd(sum, acc);
+}
+
+struct CalibSink {          // device accumulators laid out in slots of kCalSlot doubles
+  static constexpr int kCalSlot = 512;
+  enum { IN_RELU = 0, IN_EVEN = 4, S1 = 8, FIN = 12, FEAT = 13, H1 = 14, H2 = 15, SPEC = 16, NSLOTS = 17 };
+  double* d = nullptr;
+  Ctx* c = nullptr;
+  void add(int slot, const void* x, int kind, long long rows, int pitch, int C, int relu, int Himg = 1, int Wimg = 1, int even = 0) const {
+    const long long grid = std::min<long long>((rows + 3) / 4, 1184);
+    channel_sum_kernel<<<(unsigned)std::max<long long>(grid, 1), 256, 0, c->stream>>>(x, kind, rows, pitch, C, relu, Himg, Wimg, even, d + (size_t)slot * kCalSlot);
+    c->launches++;
+  }
+};
+
 template <typename H>
-int forward_tc(Ctx* c, const float* d_in, int input_mode, int64_t first, int64_t n, float* d_preds, int fmt) {
+int forward_tc(Ctx* c, const float* d_in, int input_mode, int64_t first, int64_t n, float* d_preds, int fmt, const CalibSink* cal = nullptr) {
   NetWeights* nw = c->net;
   const int Himg = nw->H, Wf = nw->Wf, U = nw->U, L = nw->L;
   const int Tn = Himg >> nw->n_blocks;
@@ -514,25 +561,51 @@ int forward_tc(Ctx* c, const float* d_in, int input_mode, int64_t first, int64_t
     net_mark(c, mk);  // 0: conv0
     if (stop == 0) { set_debug(nw, pA, kind, m, Himg, Wf, 16, 16); return ORCAI_OK; }
     int h = Himg, w = Wf;
+    auto cal_in = [&](int blk, const H* x, int C, int pitch) {   // A operands fed by a block's input tensor
+      if (!cal) return;
+      cal->add(CalibSink::IN_RELU + blk, x, 1, m * h * w, pitch, C, 1);
+      cal->add(CalibSink::IN_EVEN + blk, x, 1, m * h * w, pitch, C, 0, h, w, 1);
+    };
+    auto cal_s1 = [&](int blk, int C, int pitch) { if (cal) cal->add(CalibSink::S1 + blk, tA, 1, m * h * w, pitch, C, 0); };
+    cal_in(0, pA, 16, 16);
     ORCAI_CHECK((run_block<16, 30, H>(c, pA, tA, tB, pB, m, h, w, 0, fmt)));
+    cal_s1(0, 30, 32);
     if (stop == 10) { set_debug(nw, tA, kind, m, h, w, 30, 32); return ORCAI_OK; }
     if (stop == 11) { set_debug(nw, tB, kind, m, h, w, 30, 32); return ORCAI_OK; }
     h = (h + 1) / 2; w = (w + 1) / 2;
     net_mark(c, mk);  // 1: block1
     if (stop == 1) { set_debug(nw, pB, kind, m, h, w, 30, 32); return ORCAI_OK; }
-    ORCAI_CHECK((run_block<30, 40, H>(c, pB, tA, tB, pA, m, h, w, 1, fmt))); h = (h + 1) / 2; w = (w + 1) / 2;
+    cal_in(1, pB, 30, 32);
+    ORCAI_CHECK((run_block<30, 40, H>(c, pB, tA, tB, pA, m, h, w, 1, fmt)));
+    cal_s1(1, 40, 40);
+    h = (h + 1) / 2; w = (w + 1) / 2;
     net_mark(c, mk);  // 2: block2
     if (stop == 2) { set_debug(nw, pA, kind, m, h, w, 40, 40); return ORCAI_OK; }
-    ORCAI_CHECK((run_block<40, 50, H>(c, pA, tA, tB, pB, m, h, w, 2, fmt))); h = (h + 1) / 2; w = (w + 1) / 2;
+    cal_in(2, pA, 40, 40);
+    ORCAI_CHECK((run_block<40, 50, H>(c, pA, tA, tB, pB, m, h, w, 2, fmt)));
+    cal_s1(2, 50, 56);
+    h = (h + 1) / 2; w = (w + 1) / 2;
     net_mark(c, mk);  // 3: block3
     if (stop == 3) { set_debug(nw, pB, kind, m, h, w, 50, 56); return ORCAI_OK; }
-    ORCAI_CHECK((run_block<50, 60, H>(c, pB, tA, tB, pA, m, h, w, 3, fmt))); h = (h + 1) / 2; w = (w + 1) / 2;
+    cal_in(3, pB, 50, 56);
+    ORCAI_CHECK((run_block<50, 60, H>(c, pB, tA, tB, pA, m, h, w, 3, fmt)));
+    cal_s1(3, 60, 64);
+    h = (h + 1) / 2; w = (w + 1) / 2;
     net_mark(c, mk);  // 4: block4
     if (stop == 4) { set_debug(nw, pA, kind, m, h, w, 60, 64); return ORCAI_OK; }
+    if (cal) cal->add(CalibSink::FIN, pA, 1, m * h * w, 64, 60, 0);
     ORCAI_CHECK((run_sep<60, 36, false, true, H, true>(c, pA, feat, m, h, w, nw->tc_fin[fmt])));
     net_mark(c, mk);  // 5: final sepconv (fp32 features, w*36+c)
     if (stop == 5) { set_debug(nw, feat, 0, m, h, w, 36, 36); return ORCAI_OK; }
     ORCAI_CHECK(net_tail_fp32(c, feat, scratch, m, d_preds + (size_t)s0 * Tn * L, mk));
+    if (cal) {   // tail inputs: features, hidden states of both LSTM layers (net_tail_fp32's scratch layout)
+      const long long rows = m * Tn;
+      const float* h1 = scratch + (size_t)rows * 2 * 4 * U;
+      const float* h2 = h1 + (size_t)rows * 2 * U;
+      cal->add(CalibSink::FEAT, feat, 0, rows, nw->feat, nw->feat, 0);
+      cal->add(CalibSink::H1, h1, 0, rows, 2 * U, 2 * U, 0);
+      cal->add(CalibSink::H2, h2, 0, rows, 2 * U, 2 * U, 0);
+    }
   }
   return ORCAI_OK;
 }
@@ -555,17 +628,33 @@ int build_fused_block(Ctx* c, int blk) {
     ORCAI_FAIL(c, ORCAI_ERR_ARG, "fused block %d: kernel geometry does not match the loaded weights", blk + 1);
   std::vector<__half> w(G::W_BYTES / 2, __float2half_rn(0.f));
   auto at = [](uint32_t off, uint32_t sbo, int n, int k) { return (off + (uint32_t)(n / 8) * sbo + (uint32_t)(k / 8) * 128 + (n % 8) * 16 + (k % 8) * 2) / 2; };
+  // d?[n] = sum_k (fp16(W[k][n]) - W[k][n]) * mean(A[k]): what fp16 weight rounding adds to every output pixel (Calib, net.h)
+  const Calib& cal = nw->calib;
+  std::vector<double> d1(G::COUT, 0.0), d2(G::COUT, 0.0), dr(G::COUT, 0.0);
+  auto put = [&](size_t idx, double v, double mu, double* acc) {
+    const __half q = __float2half_rn((float)v);
+    w[idx] = q;
+    *acc += ((double)__half2float(q) - v) * mu;
+  };
   for (int t = 0; t < 9; ++t) {
     for (int k = 0; k < G::CIN; ++k)
       for (int n = 0; n < G::COUT; ++n)
-        w[at(G::OFF_W1 + t * G::TAP_W1, G::SBO_W1, n, k)] = __float2half_rn(s1.dw[(size_t)t * G::CIN + k] * s1.pw[(size_t)k * G::COUT + n]);
+        put(at(G::OFF_W1 + t * G::TAP_W1, G::SBO_W1, n, k), (double)(s1.dw[(size_t)t * G::CIN + k] * s1.pw[(size_t)k * G::COUT + n]),
+            cal.valid ? cal.in_relu[blk][k] : 0.0, &d1[n]);
     for (int k = 0; k < G::COUT; ++k)
       for (int n = 0; n < G::COUT; ++n)
-        w[at(G::OFF_W2 + t * G::TAP_W2, G::SBO_W2, n, k)] = __float2half_rn(s2.dw[(size_t)t * G::COUT + k] * s2.pw[(size_t)k * G::COUT + n]);
+        put(at(G::OFF_W2 + t * G::TAP_W2, G::SBO_W2, n, k), (double)(s2.dw[(size_t)t * G::COUT + k] * s2.pw[(size_t)k * G::COUT + n]),
+            cal.valid ? cal.s1[blk][k] : 0.0, &d2[n]);
   }
   const std::vector<float>& rw = nw->h_res_w[blk];
   for (int k = 0; k < G::CIN; ++k)
-    for (int n = 0; n < G::COUT; ++n) w[at(G::OFF_WR, G::SBO_W1, n, k)] = __float2half_rn(rw[(size_t)k * G::COUT + n]);
+    for (int n = 0; n < G::COUT; ++n) put(at(G::OFF_WR, G::SBO_W1, n, k), (double)rw[(size_t)k * G::COUT + n], cal.valid ? cal.in_even[blk][k] : 0.0, &dr[n]);
+  std::vector<float> b1c(G::COUT), b2c(G::COUT), brc(G::COUT);
+  for (int n = 0; n < G::COUT; ++n) {
+    b1c[n] = (float)((double)s1.b[n] - d1[n]);
+    b2c[n] = (float)((double)s2.b[n] - d2[n]);
+    brc[n] = (float)((double)nw->h_res_b[blk][n] - dr[n]);
+  }
   // bias rows [hi, lo] (k = 0, 1) of the three GEMMs and the constant "ones" A operand
   auto put_bias = [&](uint32_t off, const float* bv) {
     for (int n = 0; n < G::COUT; ++n) {
@@ -575,9 +664,9 @@ int build_fused_block(Ctx* c, int blk) {
       w[(off + (uint32_t)(n / 8) * 128 + (n % 8) * 16) / 2 + 1] = lo;
     }
   };
-  put_bias(G::OFF_WB1, s1.b.data());
-  put_bias(G::OFF_WB2, s2.b.data());
-  put_bias(G::OFF_WBR, nw->h_res_b[blk].data());
+  put_bias(G::OFF_WB1, b1c.data());
+  put_bias(G::OFF_WB2, b2c.data());
+  put_bias(G::OFF_WBR, brc.data());
   for (int r = 0; r < 8; ++r) {
     w[(G::OFF_ONES + r * 16) / 2] = __float2half_rn(1.f);
     w[(G::OFF_ONES + r * 16) / 2 + 1] = __float2half_rn(1.f);
@@ -607,9 +696,17 @@ int build_conv0_mma(Ctx* c) {
           for (int ch = 0; ch < 16; ++ch) w[at(dy * 2 + pr, j * 16 + ch, k)] = __float2half_rn(nw->h_conv0_w[(dy * 3 + dx) * 16 + ch]);
         }
       }
+  // weight-rounding correction (Calib): every tap multiplies the same mean spectrogram value
+  double d0[16] = {};
+  if (nw->calib.valid)
+    for (int t = 0; t < 9; ++t)
+      for (int ch = 0; ch < 16; ++ch) {
+        const float v = nw->h_conv0_w[t * 16 + ch];
+        d0[ch] += ((double)__half2float(__float2half_rn(v)) - (double)v) * nw->calib.spec;
+      }
   for (int j = 0; j < 8; ++j)
     for (int ch = 0; ch < 16; ++ch) {
-      const float bv = nw->h_conv0_b[ch];
+      const float bv = (float)((double)nw->h_conv0_b[ch] - d0[ch]);
       const __half hi = __float2half_rn(bv);
       w[at(6, j * 16 + ch, 0)] = hi;
       w[at(6, j * 16 + ch, 1)] = __float2half_rn(bv - __half2float(hi));
@@ -636,6 +733,22 @@ int prepare_fused(Ctx* c) {
   ORCAI_CHECK(build_fused_block<FB2>(c, 1));
   ORCAI_CHECK(build_fused_block<FB3>(c, 2));
   ORCAI_CHECK(build_fused_block<FB4>(c, 3));
+  {  // final separable convolution: the layer-wise fp16 operand with a corrected bias
+    const NetWeights::HostSep& hs = nw->h_fin;
+    std::vector<float> b(cpad16(hs.co), 0.f);
+    for (int n = 0; n < hs.co; ++n) {
+      double d = 0.0;
+      if (nw->calib.valid)
+        for (int t = 0; t < 9; ++t)
+          for (int k = 0; k < hs.ci; ++k) {
+            const float v = hs.dw[(size_t)t * hs.ci + k] * hs.pw[(size_t)k * hs.co + n];
+            d += ((double)__half2float(__float2half_rn(v)) - (double)v) * nw->calib.fin[k];
+          }
+      b[n] = (float)((double)hs.b[n] - d);
+    }
+    nw->fb_fin.w = nw->tc_fin[0].w;
+    ORCAI_CHECK(net_upload(c, b, &nw->fb_fin.bias));
+  }
   nw->fused_ready = true;
   return ORCAI_OK;
 }
@@ -787,7 +900,7 @@ int forward_fused(Ctx* c, const float* d_in, int input_mode, int64_t first, int6
     ORCAI_CHECK((run_fused_block<FB4>(c, 3, act[3], acts[3], act[4], static_cast<H*>(nullptr), m, hs[3], ws[3])));
     net_mark(c, mk);  // 4
     if (stop == 4) { set_debug(nw, act[4], 1, m, hs[4], ws[4], 60, cp[4]); return ORCAI_OK; }
-    ORCAI_CHECK((run_sep<60, 36, false, true, H, true>(c, act[4], feat, m, hs[4], ws[4], nw->tc_fin[0])));
+    ORCAI_CHECK((run_sep<60, 36, false, true, H, true>(c, act[4], feat, m, hs[4], ws[4], nw->fb_fin)));
     net_mark(c, mk);  // 5: final sepconv (fp32 features, w*36+c)
     if (stop == 5) { set_debug(nw, feat, 0, m, hs[4], ws[4], 36, 36); return ORCAI_OK; }
     if (nw->tail_path == 1) ORCAI_CHECK(net_tail_tc(c, feat, scratch, m, d_preds + (size_t)s0 * Tn * L, mk));
@@ -797,6 +910,65 @@ int forward_fused(Ctx* c, const float* d_in, int input_mode, int64_t first, int6
 }
 
 }  // namespace
+
+// Channel means of every GEMM's A operand on the first snippets of the resident recording (layer-wise fp16 path), see Calib.
+int net_calibrate(Ctx* c, int64_t max_snippets) {
+  NetWeights* nw = c->net;
+  if (!nw->loaded) ORCAI_FAIL(c, ORCAI_ERR_STATE, "no weights loaded (orcai_load_weights)");
+  if (!c->have_stats) ORCAI_FAIL(c, ORCAI_ERR_STATE, "no spectrogram resident (orcai_spectrogram_resident)");
+  const int64_t N = orcai_num_snippets(c->T, c->p.snippet_len);
+  const int64_t K = std::min<int64_t>(N, max_snippets > 0 ? max_snippets : 8);
+  if (K <= 0) ORCAI_FAIL(c, ORCAI_ERR_TOO_SHORT, "calibration recording is shorter than one snippet");
+  ORCAI_CHECK(net_tc_prepare(c, 0));
+  const int Himg = nw->H, Wf = nw->Wf, U = nw->U;
+  const int Tn = Himg >> nw->n_blocks, shift = c->p.snippet_len / 2;
+  constexpr int SL = CalibSink::kCalSlot;
+  double* d_sums = nullptr;
+  ORCAI_CUDA(c, cudaMalloc(&d_sums, sizeof(double) * SL * CalibSink::NSLOTS));
+  ORCAI_CUDA(c, cudaMemsetAsync(d_sums, 0, sizeof(double) * SL * CalibSink::NSLOTS, c->stream));
+  const CalibSink sink{d_sums, c};
+  const long long srows = (K - 1) * shift + Himg;
+  spec_sum_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(c->d_raw, srows, kRawLd, Wf, c->d_sel, d_sums + (size_t)CalibSink::SPEC * SL);
+  float* d_tmp = nullptr;
+  ORCAI_CUDA(c, cudaMalloc(&d_tmp, sizeof(float) * (size_t)K * Tn * nw->L));
+  const int chunk_saved = nw->chunk, stop_saved = nw->debug_stop;
+  nw->chunk = (int)std::max<int64_t>(nw->chunk, K);   // one chunk: the sums must cover every calibration snippet exactly once
+  nw->debug_stop = -1;
+  int rc = forward_tc<__half>(c, c->d_raw, 0, 0, K, d_tmp, 0, &sink);
+  nw->chunk = chunk_saved;
+  nw->debug_stop = stop_saved;
+  std::vector<double> hs((size_t)SL * CalibSink::NSLOTS);
+  if (rc == ORCAI_OK) {
+    cudaError_t e = cudaMemcpyAsync(hs.data(), d_sums, hs.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e != cudaSuccess) { c->err = cudaGetErrorString(e); rc = ORCAI_ERR_CUDA; }
+  }
+  cudaFree(d_tmp);
+  cudaFree(d_sums);
+  if (rc != ORCAI_OK) return rc;
+  Calib& cal = nw->calib;
+  auto mean = [&](int slot, int C, double count, std::vector<double>* out) {
+    out->assign(C, 0.0);
+    for (int i = 0; i < C; ++i) (*out)[i] = hs[(size_t)slot * SL + i] / count;
+  };
+  int h = Himg, w = Wf, ci = 16;
+  for (int b = 0; b < nw->n_blocks; ++b) {
+    mean(CalibSink::IN_RELU + b, ci, (double)K * h * w, &cal.in_relu[b]);
+    mean(CalibSink::IN_EVEN + b, ci, (double)K * ((h + 1) / 2) * ((w + 1) / 2), &cal.in_even[b]);
+    mean(CalibSink::S1 + b, nw->filters[b], (double)K * h * w, &cal.s1[b]);
+    ci = nw->filters[b];
+    h = (h + 1) / 2; w = (w + 1) / 2;
+  }
+  mean(CalibSink::FIN, ci, (double)K * h * w, &cal.fin);
+  mean(CalibSink::FEAT, nw->feat, (double)K * Tn, &cal.feat);
+  mean(CalibSink::H1, 2 * U, (double)K * Tn, &cal.h1);
+  mean(CalibSink::H2, 2 * U, (double)K * Tn, &cal.h2);
+  cal.spec = hs[(size_t)CalibSink::SPEC * SL] / ((double)srows * Wf);
+  cal.valid = true;
+  nw->fused_ready = false;     // operands are re-packed with the corrected biases on the next forward
+  nw->tail_tc_ready = false;
+  return ORCAI_OK;
+}
 
 int net_tc_prepare(Ctx* c, int fmt) {
   NetWeights* nw = c->net;

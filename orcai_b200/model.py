@@ -15,9 +15,9 @@ from orcai_b200.runtime import get_context
 from orcai_b200.weights import check_weights
 
 
-# network arithmetic: "fast" = fp16 tcgen05 fused residual blocks + tensor-core LSTM tail (probabilities: mean deviation
-# 2e-4 from the fp32 graph, max 2e-3 .. 7e-3 with the seeded synthetic weights; operand precision of TensorFlow's default
-# TF32 execution on GPUs); "reference" = fp32 CUDA-core path (1e-6), 11x slower.
+# network arithmetic: "fast" = fp16 tcgen05 fused residual blocks + tensor-core LSTM tail, biases calibrated against fp16
+# weight rounding (probabilities: mean deviation 1e-4 from the fp32 graph, max ~2e-3 over an hour of audio; operand precision
+# of TensorFlow's default TF32 execution on GPUs); "reference" = fp32 CUDA-core path (1e-6), 11x slower.
 PRECISION_PATHS = {"fast": 3, "reference": 0}
 
 
@@ -40,6 +40,8 @@ class OrcaiModel:
         self.ctx.load_weights(weights)
         self.precision = precision or precision_from_env()
         self.ctx.set_option("net_path", PRECISION_PATHS[self.precision])
+        if self.precision == "fast":
+            self.ctx.calibrate()   # bias correction for fp16 weight rounding, on the built-in calibration recording
         n_blocks = len(orcai_parameter["model"]["filters"])
         self.input_shape = (None, *shape["input_shape"])
         self.output_shape = (None, shape["input_shape"][0] // 2**n_blocks, shape["num_labels"])

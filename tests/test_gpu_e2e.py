@@ -53,7 +53,7 @@ def oracle_label_text(pcm, P, S, probs_from=None):
     return po.labels_tsv(po.label_rows(s, e, n, 16, "*"), float(t[1] - t[0])), agg
 
 
-@pytest.mark.parametrize("precision,tol", [("reference", 1e-3), ("fast", 1e-2)])  # fast: see FAST_TOL in test_gpu_network.py
+@pytest.mark.parametrize("precision,tol", [("reference", 1e-3), ("fast", 2.5e-3)])  # fast: see FAST_TOL in test_gpu_network.py
 def test_predict_single_wav_file_contract(ctx, params, model_dir, wavs, monkeypatch, precision, tol):
     monkeypatch.setenv("ORCAI_B200_PRECISION", precision)
     P, S = params

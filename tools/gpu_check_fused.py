@@ -64,6 +64,20 @@ def main() -> int:
         e = np.abs(out - ref)
         print(f"[fused] tail_path {tail}: probabilities max err {e.max():.3e} mean {e.mean():.3e}", flush=True)
         ok &= bool(e.max() < 5e-3)
+    # weight-rounding bias calibration (built-in synthetic recording) and a realistic input: snippets of another synthetic recording
+    from oracle import postprocess_oracle as po, spectrogram_oracle as so
+    from orcai_b200.synth import pcm16_to_float, synth_pcm16
+    pcm = synth_pcm16(40.0, seed=4242, calls_per_minute=20.0)
+    spec, _, _ = so.make_spectrogram(pcm16_to_float(pcm), P["spectrogram"])
+    xa = po.cut_snippets(spec, 736)[:8]
+    refa = network_oracle.forward(xa, W)
+    ctx.set_option("tail_path", 1)
+    ea = np.abs(ctx.forward_host(xa) - refa)
+    print(f"[fused] audio snippets, uncalibrated: max err {ea.max():.3e} mean {ea.mean():.3e}", flush=True)
+    ctx.calibrate()
+    ea = np.abs(ctx.forward_host(xa) - refa)
+    e = np.abs(ctx.forward_host(x) - ref)
+    print(f"[fused] audio snippets, calibrated:   max err {ea.max():.3e} mean {ea.mean():.3e}   (uniform-random input: {e.max():.3e})", flush=True)
     ctx.set_option("net_path", 1)
     out1 = ctx.forward_host(x)
     print(f"[fused] vs layer-wise fp16 path: max diff {np.abs(out - out1).max():.3e}")
