@@ -28,12 +28,34 @@ def load_recording(wav_file_path: Path | str, channel: int, spectrogram_paramete
     samples, sr, n_ch = read_wav(wav_file_path, channel)
     if n_ch > 1 and msgr is not None:
         msgr.warning(f"Multiple channels found, using channel {channel}")
-    if sr != spectrogram_parameter["sampling_rate"]:
-        raise ValueError(
-            f"{wav_file_path}: sampling rate {sr} Hz differs from the model's {spectrogram_parameter['sampling_rate']} Hz; "
-            "resampling (soxr_hq in the reference) is not implemented in orcai_b200"
-        )
+    target = int(spectrogram_parameter["sampling_rate"])
+    if sr != target:
+        samples = resample(samples, sr, target)
+        if msgr is not None:
+            msgr.warning(
+                f"{Path(wav_file_path).name}: resampled {sr} -> {target} Hz with a polyphase Kaiser filter on the host "
+                "(the reference uses soxr_hq; results agree only to resampler tolerance)"
+            )
     return samples
+
+
+def resample(samples: np.ndarray, sr: int, target: int) -> np.ndarray:
+    """Host-side rational resampling to the model's rate -> float32 in [-1, 1] scale.
+
+    The reference's ``librosa.load(sr=...)`` resamples with soxr_hq (spectrogram.py:23-27), a third-party resampler that is
+    not available here and has no in-tree specification, so this step is NOT parity-pinned:
+    ``scipy.signal.resample_poly`` (polyphase FIR, Kaiser beta 5) in float64.
+    """
+    from math import gcd
+
+    from scipy.signal import resample_poly
+
+    x = np.asarray(samples)
+    if x.dtype == np.int16:
+        x = x.astype(np.float64) / 32768.0
+    g = gcd(int(sr), int(target))
+    y = resample_poly(x.astype(np.float64), int(target) // g, int(sr) // g)
+    return np.ascontiguousarray(y, dtype=np.float32)
 
 
 def fft_frequencies(spectrogram_parameter: dict) -> np.ndarray:

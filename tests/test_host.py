@@ -225,3 +225,17 @@ def test_predict_stream_order_of_calls():
     assert out == [0, 1, 2]
     assert log == [("prefetch", 0), ("swap",), ("prefetch", 1), ("predict", 0), ("swap",), ("prefetch", 2), ("predict", 1), ("swap",), ("predict", 2)]
     assert list(Context.predict_stream(Fake(), iter([]))) == []
+
+
+def test_host_resampler_preserves_a_tone():
+    from orcai_b200.spectrogram import resample
+
+    sr, target = 44100, 48000
+    t = np.arange(sr) / sr
+    x = (0.5 * np.sin(2 * np.pi * 1000.0 * t) * 32767).astype(np.int16)
+    y = resample(x, sr, target)
+    assert y.dtype == np.float32 and abs(len(y) - target) <= 1
+    ref = 0.5 * np.sin(2 * np.pi * 1000.0 * np.arange(len(y)) / target) * 32767 / 32768
+    assert np.abs(y[2000:-2000] - ref[2000:-2000]).max() < 2e-3
+    z = resample(x.astype(np.float32) / 32768.0, sr, target)
+    np.testing.assert_allclose(z, y, atol=1e-6)
