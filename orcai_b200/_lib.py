@@ -249,7 +249,7 @@ class Context:
         if pcm is None:
             from orcai_b200.synth import synth_pcm16
 
-            pcm = synth_pcm16(24.0, seed=20251018, calls_per_minute=30.0)
+            pcm = synth_pcm16(24.0, seed=918273645, calls_per_minute=30.0)   # a seed no test, smoke or bench recording uses
         self.upload_pcm(pcm)
         self.spectrogram_resident(False)
         self._check(self.lib.orcai_calibrate(self._h, int(max_snippets)))

@@ -16,7 +16,7 @@ from orcai_b200.weights import check_weights
 
 
 # network arithmetic: "fast" = fp16 tcgen05 fused residual blocks + tensor-core LSTM tail, biases calibrated against fp16
-# weight rounding (probabilities: mean deviation 1e-4 from the fp32 graph, max ~2e-3 over an hour of audio; operand precision
+# weight rounding (probabilities: mean deviation 1e-4 from the fp32 graph, max ~2.7e-3 over an hour of audio; operand precision
 # of TensorFlow's default TF32 execution on GPUs); "reference" = fp32 CUDA-core path (1e-6), 11x slower.
 PRECISION_PATHS = {"fast": 3, "reference": 0}
 
