@@ -680,7 +680,30 @@ int net_tail_fp32(Ctx* c, const float* feat, float* scratch, long long m, float*
   return ORCAI_OK;
 }
 
+// A recording whose clipped dB range is empty (silence: lo == hi) normalises to 0/0 = NaN everywhere in the reference
+// (spectrogram.py:81-83); Keras propagates the NaNs to every probability and nothing gets labelled.  CUDA's fmaxf / __hmax2
+// ReLU would silently turn NaN into 0, so the all-or-nothing case is restored here: NaN probabilities for a degenerate range.
+__global__ void poison_degenerate_kernel(float* __restrict__ preds, long long count, const SelectState* __restrict__ st) {
+  const float range = st->hi - st->lo;
+  if (range > 0.f) return;   // false for 0 and for NaN
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (long long)gridDim.x * blockDim.x)
+    preds[i] = __int_as_float(0x7fc00000);
+}
+
+static int net_forward_paths(Ctx* c, const float* d_in, int input_mode, int64_t first, int64_t n, float* d_preds);
+
 int net_forward(Ctx* c, const float* d_in, int input_mode, int64_t first, int64_t n, float* d_preds) {
+  ORCAI_CHECK(net_forward_paths(c, d_in, input_mode, first, n, d_preds));
+  if (input_mode == 0 && n > 0 && c->net->debug_stop < 0) {
+    const long long count = (long long)n * (c->net->H >> c->net->n_blocks) * c->net->L;
+    poison_degenerate_kernel<<<(unsigned)std::min<long long>((count + 255) / 256, 1024), 256, 0, c->stream>>>(d_preds, count, c->d_sel);
+    c->launches++;
+    ORCAI_CUDA(c, cudaGetLastError());
+  }
+  return ORCAI_OK;
+}
+
+static int net_forward_paths(Ctx* c, const float* d_in, int input_mode, int64_t first, int64_t n, float* d_preds) {
   NetWeights* nw = c->net;
   if (!nw || !nw->loaded) ORCAI_FAIL(c, ORCAI_ERR_STATE, "no weights loaded (orcai_load_weights)");
   if (nw->path != 0) return net_forward_tc(c, d_in, input_mode, first, n, d_preds);

@@ -175,3 +175,39 @@ def test_calibration_reduces_weight_rounding_error(ctx, params):
             ctx.calibrate(synth_pcm16(2.0, seed=1))
     finally:
         ctx.set_option("net_path", 0)
+
+
+def test_fast_path_edge_lengths(ctx, params):
+    """One snippet exactly (T = 736), one snippet plus an uncovered tail, and an odd multi-snippet length on the fast path."""
+    P, S = params
+    W = synthetic_weights(P, S, seed=1234)
+    ctx.calibrate()
+    for n_samples in (735 * 256, 735 * 256 + 367 * 256 + 17, (736 + 368 * 4 + 5) * 256 + 3):
+        pcm = synth_pcm16(n_samples / 48000.0 + 0.01, seed=123, calls_per_minute=60.0)[:n_samples]
+        T = 1 + n_samples // 256
+        n = (T - 736) // 368 + 1
+        ctx.set_option("net_path", 0)
+        ref = ctx.predict_pcm(pcm)
+        ctx.set_option("net_path", 3)
+        try:
+            got = ctx.predict_pcm(pcm)
+        finally:
+            ctx.set_option("net_path", 0)
+        assert got[0].n_frames == T and got[1].shape == (T // 16, 7)
+        np.testing.assert_array_equal(got[2], ref[2])                      # overlap counts
+        assert np.abs(got[1] - ref[1]).max() <= FAST_TOL                   # aggregated probabilities vs the fp32 path
+        assert (got[1][23 * (n - 1) + 46:] == 0).all()                     # steps no snippet covers stay 0
+
+
+def test_silent_recording_labels_nothing(ctx):
+    """All-zero audio: the reference's normalisation is 0/0 = NaN everywhere (spectrogram.py:81-83), Keras propagates it and
+    nothing is labelled; both network paths reproduce that (NaN probabilities, no segments, no crash)."""
+    ctx.calibrate()
+    for path in (0, 3):
+        ctx.set_option("net_path", path)
+        try:
+            st, agg, cnt, lab, sta, sto = ctx.predict_pcm(np.zeros(48000 * 6, np.int16))
+        finally:
+            ctx.set_option("net_path", 0)
+        assert len(lab) == 0 and len(sta) == 0 and cnt.max() == 2
+        assert np.isnan(agg[cnt > 0]).all()
