@@ -67,7 +67,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
             )
             threading.Thread(target=self._pump, daemon=True).start()
@@ -245,7 +245,6 @@ def main() -> None:
         net_stage = tm["net_stage_ms"]
     barrier()
     t_res = max_over_ranks(time.perf_counter() - t0)
-    clocks = sampler.stop()
     launches = ctx.timings()["kernel_launches"] - launches0
     dev_ms = max_over_ranks(stage["total_ms"] / args.steps)
 
@@ -261,6 +260,7 @@ def main() -> None:
         d2h = agg.nbytes + cnt.nbytes + lab.nbytes + sta.nbytes + sto.nbytes
     barrier()
     t_e2e = max_over_ranks(time.perf_counter() - t0)
+    clocks = sampler.stop()   # sampled every 50 ms across both timed regions (and the short warm-up between them)
 
     # ---------------- parity of the measured path (outside every timed region) ----------------
     parity = None

@@ -108,7 +108,13 @@ def test_fast_path_fused_tensor_core_blocks(ctx, params, golden_dir, tail_path):
         np.testing.assert_array_equal(ctx.forward_host(x7[4:5]), full[4:5])
         W = synthetic_weights(P, S, seed=1234)
         assert np.abs(full - network_oracle.forward(x7, W)).max() <= FAST_TOL
+        # the fp32 CUDA-core entry convolution (conv0_path 0) instead of the tensor-core pixel-group one
+        ctx.set_option("conv0_path", 0)
+        alt = ctx.forward_host(x7)
+        ctx.set_option("conv0_path", 1)
+        assert np.abs(alt - full).max() <= FAST_TOL
     finally:
+        ctx.set_option("conv0_path", 1)
         ctx.set_option("net_path", 0)
         ctx.set_option("tail_path", 1)
         ctx.set_option("chunk", 128)
