@@ -41,7 +41,15 @@ class OrcaiModel:
         self.precision = precision or precision_from_env()
         self.ctx.set_option("net_path", PRECISION_PATHS[self.precision])
         if self.precision == "fast":
-            self.ctx.calibrate()   # bias correction for fp16 weight rounding, on the built-in calibration recording
+            # bias correction for fp16 weight rounding: channel means from a calibration recording - the built-in synthetic one,
+            # or a representative recording of the deployment named by ORCAI_B200_CALIBRATION=<wav file>
+            cal = os.environ.get("ORCAI_B200_CALIBRATION", "").strip()
+            if cal:
+                from orcai_b200.spectrogram import load_recording
+
+                self.ctx.calibrate(load_recording(cal, 1, orcai_parameter["spectrogram"]))
+            else:
+                self.ctx.calibrate()
         n_blocks = len(orcai_parameter["model"]["filters"])
         self.input_shape = (None, *shape["input_shape"])
         self.output_shape = (None, shape["input_shape"][0] // 2**n_blocks, shape["num_labels"])
