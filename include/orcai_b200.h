@@ -157,7 +157,8 @@ int orcai_calibrate(orcai_ctx* ctx, int64_t max_snippets);
  *                      ORCAI_B200_PRECISION=reference): tensor-core entry convolution, fused residual-block kernels,
  *                      tensor-core LSTM tail; fp32 accumulation everywhere;
  *          "tail_path" (net_path 3) 1 = tensor-core LSTM/dense tail (default), 0 = fp32 CUDA-core tail;
- *          "conv0_path" (net_path 3) 1 = tensor-core entry convolution (default), 0 = fp32 CUDA-core entry convolution;
+ *          "conv0_path" (net_path 3) 1 = tensor-core entry convolution (default), 0 = fp32 CUDA-core entry convolution,
+ *          2 = entry convolution fused into the first residual block's kernel (measured slower, kept as an option);
  *          "stft_f64"  1 = float64 FFT (parity grade, default), 0 = float32 FFT (fast);
  *          "chunk"     snippets per network launch sequence;
  *          "debug_stop" stop the forward after a stage (see orcai_debug_read), -1 = off. */

@@ -107,7 +107,18 @@ extern "C" {
 
 int orcai_version(void) { return 100; }
 
-const char* orcai_last_error(const orcai_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+const char* orcai_last_error(const orcai_ctx* ctx) {
+  if (!ctx) return g_create_error.c_str();
+  const unsigned int* ti = orcai::net_trap_info();
+  if (ti != nullptr && ti[0] == 0x7241u) {
+    static thread_local std::string s;
+    char b[160];
+    snprintf(b, sizeof b, " [mbarrier wait gave up: block %u thread %u barrier@0x%x parity %u]", ti[1], ti[2], ti[3], ti[4]);
+    s = ctx->err + b;
+    return s.c_str();
+  }
+  return ctx->err.c_str();
+}
 
 int64_t orcai_num_frames(int64_t n_samples, int32_t hop) { return hop > 0 && n_samples >= 0 ? 1 + n_samples / hop : 0; }
 

@@ -54,6 +54,33 @@ spec_half_kernel(const float* __restrict__ in, int mode, int in_ld, long long ro
   }
 }
 
+// The same rows cut into overlapping column strips for the entry convolution fused into block 1 (net_fused.cuh, CONV0):
+// out[row][strip][x] = spectrogram[row][strip * strip_step + col0 + x] (zero outside 0 .. nb-1), x < strip_w.  Every strip
+// starts a 128-byte line, so the TMA boxes that fetch them have an aligned innermost coordinate (0).
+__global__ void __launch_bounds__(256)
+spec_strips_kernel(const float* __restrict__ in, int mode, int in_ld, long long rows, int nb, const orcai::SelectState* __restrict__ st,
+                   __half* __restrict__ out, int n_strips, int strip_step, int col0, int strip_w) {
+  float db_ref = 0.f, lo = 0.f, hi = 1.f, range = 1.f;
+  if (mode == 0) { db_ref = st->db_ref; lo = st->lo; hi = st->hi; range = hi - lo; }
+  const int per_row = n_strips * strip_w;
+  const long long total = rows * per_row;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / per_row;
+    const int q = (int)(i - r * per_row);
+    const int s = q / strip_w, x = q - s * strip_w;
+    const int c = s * strip_step + col0 + x;
+    float v = 0.f;
+    if (c >= 0 && c < nb) {
+      v = __ldg(in + (size_t)r * in_ld + c);
+      if (mode == 0) {
+        v = fmaxf(v - db_ref, -80.0f);
+        v = __fdiv_rn(fminf(fmaxf(v, lo), hi) - lo, range);
+      }
+    }
+    out[i] = __float2half_rn(v);
+  }
+}
+
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
   asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                :

@@ -494,7 +494,7 @@ int net_set_tail_path(Ctx* c, int path) {
 }
 
 int net_set_conv0_path(Ctx* c, int path) {
-  if (path < 0 || path > 1) ORCAI_FAIL(c, ORCAI_ERR_ARG, "conv0_path must be 0 (fp32 CUDA cores) or 1 (tensor cores)");
+  if (path < 0 || path > 2) ORCAI_FAIL(c, ORCAI_ERR_ARG, "conv0_path must be 0 (fp32 CUDA cores), 1 (tensor cores) or 2 (fused into block 1)");
   c->net->conv0_path = path;
   return ORCAI_OK;
 }

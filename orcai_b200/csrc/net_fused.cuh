@@ -45,11 +45,13 @@ __host__ __device__ constexpr int imin(int a, int b) { return a < b ? a : b; }
 __host__ __device__ constexpr int round8(int a) { return (a + 7) & ~7; }
 __host__ __device__ constexpr int pow2cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
 
-template <int CIN_, int COUT_, int CPOOL_, int S_, bool RELU_OUT_, int CTAS_, int NEW_>
+// CONV0_: the block's input is produced in-kernel from the fp16 spectrogram by the entry convolution (CUDA-core producer warps)
+template <int CIN_, int COUT_, int CPOOL_, int S_, bool RELU_OUT_, int CTAS_, int NEW_, bool CONV0_ = false>
 struct FB {
   static constexpr int CIN = CIN_, COUT = COUT_, CP = CPOOL_, S = S_, CTAS = CTAS_, NEW = NEW_;
-  static constexpr bool RELU_OUT = RELU_OUT_;
-  static constexpr int NWORK = NEW * 32, NTHREADS = NWORK + 64;   // + issuer warp + producer warp
+  static constexpr bool RELU_OUT = RELU_OUT_, CONV0 = CONV0_;
+  static constexpr int NPROD = CONV0 ? 2 : 1;                       // producer warps: one TMA warp, or two entry-convolution warps
+  static constexpr int NWORK = NEW * 32, NTHREADS = NWORK + 32 + 32 * NPROD;   // + issuer warp + producer warp(s)
   static constexpr int NT = NEW / 4;                 // worker teams per TMEM lane quadrant; a team drains 16 columns
   static constexpr int ICP = cpad8(CIN), OCP = cpad8(COUT);
   static constexpr int KP1 = cpad16(CIN);          // K per tap of sepconv 1 and of the residual convolution
@@ -83,9 +85,13 @@ struct FB {
   static constexpr uint32_t OFF_X = OFF_R + XCH * LBO_R;
   static constexpr uint32_t OFF_S1 = OFF_X + XCH * LBO_X;
   static constexpr uint32_t OFF_S2 = OFF_S1 + MCH * LBO_S1;
-  static constexpr uint32_t OFF_BAR = OFF_S2 + NG * LBO_S2;
-  // barriers: bar1[N1] bar2[N2] barR[2] s1_full[N1] pool_done x_full
-  static constexpr int B_1 = 0, B_2 = N1, B_R = N1 + N2, B_S1 = N1 + N2 + 2, B_P = 2 * N1 + N2 + 2, B_X = B_P + 1, NBAR = B_X + 1;
+  // entry-convolution input: two (S+5) x SPW fp16 tiles of the normalised spectrogram (rows a-1 .. a+S+3, columns cb-1 ..)
+  static constexpr int SPW = 64, SPH = S + 5;
+  static constexpr uint32_t SPEC_BYTES = CONV0 ? SPH * SPW * 2 : 0;
+  static constexpr uint32_t OFF_SPEC = OFF_S2 + NG * LBO_S2;
+  static constexpr uint32_t OFF_BAR = OFF_SPEC + 2 * ((SPEC_BYTES + 127) / 128 * 128);
+  // barriers: bar1[N1] bar2[N2] barR[2] s1_full[N1] pool_done x_full spec_full[2]
+  static constexpr int B_1 = 0, B_2 = N1, B_R = N1 + N2, B_S1 = N1 + N2 + 2, B_P = 2 * N1 + N2 + 2, B_X = B_P + 1, B_SP = B_X + 1, NBAR = B_SP + 2;
   static constexpr uint32_t SMEM = OFF_BAR + NBAR * 8 + 16;
   static constexpr uint32_t TX_BYTES = XG * ((S + 2) * WP + (S / 2) * CP) * 16;   // bytes one step's TMA loads deliver
   static constexpr int COL_R = 0, COL_1 = 2 * NP, COL_2 = 2 * NP + N1 * NP;
@@ -95,6 +101,7 @@ struct FB {
   static_assert(S % 2 == 0 && S >= 2, "steps advance by whole pooled rows");
   static_assert(RQ <= 128, "one residual MMA tile per step");
   static_assert(WP <= 126, "a second-convolution tile may only depend on first-convolution tiles t-1 .. t+1");
+  static_assert(!CONV0 || (CIN == 16 && WP + 2 <= SPW && 2 * CP + 3 <= SPW), "entry-convolution tile: 16 channels, WP + 2 spectrogram columns");
   static_assert(NP * (2 + N1 + N2) <= 512 && TM_COLS * CTAS <= 512, "TMEM columns");
   static_assert(SMEM <= 227 * 1024 && (SMEM + 1024) * CTAS <= 228 * 1024, "shared memory (per CTA and per SM)");
   static_assert((128 - RPIX) * 16 <= XCH * LBO_X, "residual tile over-read must stay inside the CTA's shared memory");
@@ -113,6 +120,12 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+               :
+               : "r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
 }
 // true in exactly one lane of a converged warp
 __device__ __forceinline__ bool elect_one() {
@@ -186,7 +199,8 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   if (tid == 0) {
     for (int i = 0; i < G::B_S1; ++i) mbar_init(&bars[i], 1);                 // tcgen05.commit arrivals
     for (int i = G::B_S1; i < G::B_X; ++i) mbar_init(&bars[i], G::NEW);        // one arrival per worker warp (s1_full, pool_done)
-    mbar_init(&bars[G::B_X], 1);                                               // producer's arrive.expect_tx
+    mbar_init(&bars[G::B_X], G::CONV0 ? G::NPROD : 1);                         // TMA arrive.expect_tx, or one arrival per entry-conv warp
+    mbar_init(&bars[G::B_SP], 1); mbar_init(&bars[G::B_SP + 1], 1);            // spectrogram tiles of the entry convolution
     fence_mbar_init();
   }
   __syncwarp();
@@ -201,7 +215,93 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   const long long my_items = blockIdx.x < n_items ? (n_items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   const long long total_steps = my_items * n_steps;
 
-  if (warp == G::NEW + 1) {
+  if (warp > G::NEW) {
+    if constexpr (G::CONV0) {
+      // =============================== entry-convolution producers ===============================
+      // Conv2D 3x3 1->16 + folded BatchNorm + ReLU (architectures.py:162-168) on the CUDA cores, straight into the X planes
+      // (and the residual-input planes R = X at even positions): fp32 math on the fp16 spectrogram, weights as constant-bank
+      // FFMA operands.  tmX is the rank-4 map of the strip-cut spectrogram (conv0::spec_strips_kernel: SPW columns of a strip,
+      // strip, rows of a snippet, snippet); its outer stride is the snippet shift, rows outside the snippet are zero-filled,
+      // columns outside the image are zero in the buffer.  Lane = X column; 64 lanes walk the S+2 rows with a sliding 3x3 window.
+      const int pl = (warp - G::NEW - 1) * 32 + lane;     // 0..63
+      const __half* s_spec = reinterpret_cast<const __half*>(smem + G::OFF_SPEC);
+      constexpr uint32_t SPEC_STRIDE = (G::SPEC_BYTES + 127) / 128 * 128;
+      auto load_spec = [&](long long gg, long long item2, int step2) {   // elected lane of producer warp 0
+        const long long b2 = item2 / n_strips;
+        const int strip2 = (int)(item2 - b2 * n_strips);
+        mbar_arrive_expect_tx(&bars[G::B_SP + (int)(gg & 1)], G::SPEC_BYTES);
+        tma_load_4d(sbase + G::OFF_SPEC + (uint32_t)(gg & 1) * SPEC_STRIDE, &tmX, &bars[G::B_SP + (int)(gg & 1)], 0, strip2,
+                    step2 * G::S - 3, (int)b2);
+      };
+      if (warp == G::NEW + 1 && total_steps > 0 && elect_one()) load_spec(0, blockIdx.x, 0);
+      __syncwarp();
+      long long g = 0;
+      for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const long long b = item / n_strips;
+        const int strip = (int)(item - b * n_strips);
+        const int wo0 = strip * G::CP, cb = 2 * wo0 - 2;
+        for (int step = 0; step < n_steps; ++step, ++g) {
+          const int a = step * G::S - 2;
+          // X and R are free once the previous step's first convolution (and residual MMA) has completed; that also
+          // means BOTH producer warps have finished step g-1, i.e. the other spectrogram buffer has no readers left
+          if (g > 0) mbar_wait(&bars[G::B_1 + G::N1 - 1], (uint32_t)((g - 1) & 1));
+          // prefetch the next step's spectrogram tile into the other buffer
+          if (warp == G::NEW + 1 && g + 1 < total_steps && elect_one()) {
+            if (step + 1 < n_steps) load_spec(g + 1, item, step + 1);
+            else load_spec(g + 1, item + gridDim.x, 0);
+          }
+          __syncwarp();
+          mbar_wait(&bars[G::B_SP + (int)(g & 1)], (uint32_t)((g >> 1) & 1));
+          const __half* sp = s_spec + (size_t)(g & 1) * (SPEC_STRIDE / 2);   // tile row y = image row a-1+y, tile col x = image col cb-1+x
+          auto conv_px = [&](const float (&w)[3][3], bool inimg, unsigned char* dst0, unsigned char* dst1) {
+            float acc[16];
+#pragma unroll
+            for (int ch = 0; ch < 16; ++ch) acc[ch] = c_conv0[144 + ch];
+#pragma unroll
+            for (int t = 0; t < 9; ++t)
+#pragma unroll
+              for (int ch = 0; ch < 16; ++ch) acc[ch] = fmaf(w[t / 3][t % 3], c_conv0[t * 16 + ch], acc[ch]);
+#pragma unroll
+            for (int ch = 0; ch < 16; ++ch) acc[ch] = inimg ? fmaxf(acc[ch], 0.f) : 0.f;
+            *reinterpret_cast<uint4*>(dst0) = pack8h(acc);
+            *reinterpret_cast<uint4*>(dst1) = pack8h(acc + 8);
+          };
+          if (pl < G::WP) {
+            const int ww = cb + pl;
+            const bool col_ok = ww >= 0 && ww < W;
+            float w[3][3];
+#pragma unroll
+            for (int r = 0; r < 2; ++r)
+#pragma unroll
+              for (int q = 0; q < 3; ++q) w[r + 1][q] = __half2float(sp[(r + 1) * G::SPW + pl + q]);   // tile rows 1, 2
+#pragma unroll 1
+            for (int xr = 0; xr < G::S + 2; ++xr) {     // X local row xr = image row a+1+xr = tile rows xr+1 .. xr+3
+#pragma unroll
+              for (int q = 0; q < 3; ++q) { w[0][q] = w[1][q]; w[1][q] = w[2][q]; w[2][q] = __half2float(sp[(xr + 3) * G::SPW + pl + q]); }
+              const int hh = a + 1 + xr;
+              unsigned char* dst = smem + G::OFF_X + (xr * G::WP + pl) * 16;
+              conv_px(w, col_ok && hh >= 0 && hh < H, dst, dst + G::LBO_X);
+            }
+          }
+          // residual input: X at image (a + 2i, 2(wo0 + j)) = tile rows 2i .. 2i+2, tile columns 2+2j .. 4+2j
+          for (int q = pl; q < G::RQ; q += 64) {
+            const int i = q / G::CP, j = q - i * G::CP;
+            const int hh = a + 2 * i, wo = wo0 + j;
+            float w[3][3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+              for (int c2 = 0; c2 < 3; ++c2) w[r][c2] = __half2float(sp[(2 * i + r) * G::SPW + 2 + 2 * j + c2]);
+            unsigned char* dst = smem + G::OFF_R + q * 16;
+            conv_px(w, hh >= 0 && hh < H && 2 * wo < W, dst, dst + G::LBO_R);
+          }
+          fence_proxy_async();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars[G::B_X]);
+        }
+      }
+    } else {
     // =============================== TMA producer ===============================
     long long g = 0;
     for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -223,6 +323,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         }
         __syncwarp();
       }
+    }
     }
   } else if (warp == G::NEW) {
     // =============================== MMA issuer ===============================

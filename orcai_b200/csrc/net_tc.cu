@@ -311,6 +311,9 @@ pool_res_tc_kernel(const H* __restrict__ t4, const H* __restrict__ prev, H* __re
   }
 }
 
+// entry-convolution weights for the CUDA-core producers / kernels: every FFMA takes its weight as a constant-bank operand
+__constant__ float c_conv0[9 * 16 + 16];   // [tap][16] (BatchNorm folded), then bias[16]
+
 #include "net_fused.cuh"
 #include "conv0_mma.cuh"
 
@@ -319,7 +322,6 @@ pool_res_tc_kernel(const H* __restrict__ t4, const H* __restrict__ prev, H* __re
 // raw dB buffer, folded BatchNorm + ReLU, fp16 NHWC output plus the even-position copy the first residual 1x1/2 reads.
 // Weights sit in constant memory: every FFMA takes its weight as a constant-bank operand, no load instructions.
 // ------------------------------------------------------------------------------------------------
-__constant__ float c_conv0[9 * 16 + 16];   // [tap][16] (BatchNorm folded), then bias[16]
 
 constexpr int kC0TH = 8, kC0TW = 32;
 
@@ -618,6 +620,8 @@ using FB1 = fused::FB<16, 30, 29, 6, true, 2, 8>;
 using FB2 = fused::FB<30, 40, 43, 4, true, 1, 16>;
 using FB3 = fused::FB<40, 50, 22, 4, true, 1, 16>;
 using FB4 = fused::FB<50, 60, 11, 4, false, 1, 16>;
+using FB1C = fused::FB<16, 30, 29, 6, true, 2, 8, true>;   // block 1 with the entry convolution fused in (conv0_path 2)
+static_assert(FB1C::W_BYTES == FB1::W_BYTES && FB1C::OFF_SPEC % 128 == 0, "FB1C shares FB1's weight pack; TMA destinations are 128-byte aligned");
 
 template <class G>
 int build_fused_block(Ctx* c, int blk) {
@@ -724,12 +728,22 @@ int build_conv0_mma(Ctx* c) {
   return ORCAI_OK;
 }
 
+unsigned int* g_trap_host = nullptr;   // mapped host memory behind tc::g_trap_info (ORCAI_B200_TRAPINFO=1)
+
 int prepare_fused(Ctx* c) {
   NetWeights* nw = c->net;
   if (nw->fused_ready) return ORCAI_OK;
+  if (g_trap_host == nullptr && getenv("ORCAI_B200_TRAPINFO") != nullptr) {
+    unsigned int* d = nullptr;
+    ORCAI_CUDA(c, cudaHostAlloc(reinterpret_cast<void**>(&g_trap_host), 64, cudaHostAllocMapped));
+    memset(g_trap_host, 0, 64);
+    ORCAI_CUDA(c, cudaHostGetDevicePointer(reinterpret_cast<void**>(&d), g_trap_host, 0));
+    ORCAI_CUDA(c, cudaMemcpyToSymbol(tc::g_trap_info, &d, sizeof d));
+  }
   ORCAI_CHECK(net_tc_prepare(c, 0));   // the final sepconv reuses the fp16 layer-wise operands
   ORCAI_CHECK(build_conv0_mma(c));
   ORCAI_CHECK(build_fused_block<FB1>(c, 0));
+  ORCAI_CUDA(c, cudaFuncSetAttribute(fused::fused_block_kernel<FB1C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FB1C::SMEM));
   ORCAI_CHECK(build_fused_block<FB2>(c, 1));
   ORCAI_CHECK(build_fused_block<FB3>(c, 2));
   ORCAI_CHECK(build_fused_block<FB4>(c, 3));
@@ -802,6 +816,32 @@ int run_fused_block(Ctx* c, int blk, const __half* xr, const __half* xs, __half*
   return ORCAI_OK;
 }
 
+// block 1 fed by the fp16 normalised spectrogram: its producer warps run the entry convolution (fused::FB<..., CONV0 = true>)
+int run_fused_block1_conv0(Ctx* c, const __half* spec16, long long snippet_stride_rows, __half* yr, __half* ys, long long m, int Himg, int Wimg) {
+  using G = FB1C;
+  NetWeights* nw = c->net;
+  const int Wo = (Wimg + 1) / 2;
+  const int n_strips = (Wo + G::CP - 1) / G::CP;
+  const long long items = m * n_strips;
+  const long long grid = std::min<long long>(items, (long long)c->sm_count * G::CTAS);
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) ORCAI_FAIL(c, ORCAI_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  CUtensorMap tms;
+  const cuuint64_t row_bytes = (cuuint64_t)n_strips * G::SPW * 2;
+  const cuuint64_t dims[4] = {(cuuint64_t)G::SPW, (cuuint64_t)n_strips, (cuuint64_t)Himg, (cuuint64_t)m};
+  const cuuint64_t strides[3] = {(cuuint64_t)G::SPW * 2, row_bytes, (cuuint64_t)snippet_stride_rows * row_bytes};
+  const cuuint32_t box[4] = {(cuuint32_t)G::SPW, 1, (cuuint32_t)G::SPH, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = fn(&tms, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(spec16), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) ORCAI_FAIL(c, ORCAI_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for the spectrogram view of block 1", (int)r);
+  fused::fused_block_kernel<G><<<(unsigned)grid, G::NTHREADS, G::SMEM, c->stream>>>(tms, tms, 2, yr, ys, Himg, Wimg, n_strips, items,
+                                                                                   static_cast<const unsigned char*>(nw->fb_w[0]));
+  c->launches++;
+  ORCAI_CUDA(c, cudaGetLastError());
+  return ORCAI_OK;
+}
+
 int forward_fused(Ctx* c, const float* d_in, int input_mode, int64_t first, int64_t n, float* d_preds) {
   NetWeights* nw = c->net;
   using H = __half;
@@ -818,7 +858,8 @@ int forward_fused(Ctx* c, const float* d_in, int input_mode, int64_t first, int6
     sub[b] = b < 4 ? (size_t)hs[b + 1] * ws[b + 1] * cp[b] : 0;
     halfs += full[b] + sub[b];
   }
-  halfs += (size_t)Himg * conv0::kSpecLd;   // fp16 normalised spectrogram rows of the chunk (upper bound: non-overlapping snippets)
+  // fp16 normalised spectrogram rows of the chunk (upper bound: non-overlapping snippets), plain or cut into block 1's strips
+  halfs += (size_t)Himg * std::max<int>(conv0::kSpecLd, (((Wf + 1) / 2 + FB1C::CP - 1) / FB1C::CP) * FB1C::SPW);
   halfs = (halfs + 7) & ~(size_t)7;
   const size_t tail_f = (size_t)Tn * (nw->feat + 2 * 4 * U + 2 * U + 2 * U + 128);
   const size_t per = halfs * 2 + tail_f * 4;
@@ -849,13 +890,26 @@ int forward_fused(Ctx* c, const float* d_in, int input_mode, int64_t first, int6
     const bool mk = (s0 == 0);
     if (mk) nw->marked_snippets = m;
     net_mark(c, mk);
-    if (nw->conv0_path == 1) {
+    const bool fuse0 = nw->conv0_path == 2 && stop != 0;   // the entry convolution runs inside block 1 (debug stage 0 needs its own output)
+    if (fuse0) {
+      // fp16 normalised rows of this chunk, cut into block 1's overlapping column strips (image columns 2*CP*s - 3 ...)
+      const long long srows = input_mode == 0 ? (m - 1) * shift + Himg : m * (long long)Himg;
+      const float* src = (input_mode == 0) ? d_in + (size_t)(first + s0) * shift * kRawLd : d_in + (size_t)s0 * Himg * Wf;
+      const int n_strips1 = ((Wf + 1) / 2 + FB1C::CP - 1) / FB1C::CP;
+      const long long total = srows * n_strips1 * FB1C::SPW;
+      conv0::spec_strips_kernel<<<(unsigned)std::min<long long>((total + 255) / 256, (long long)c->sm_count * 16), 256, 0, c->stream>>>(
+          src, input_mode, input_mode == 0 ? kRawLd : Wf, srows, Wf, c->d_sel, spec16, n_strips1, 2 * FB1C::CP, -3, FB1C::SPW);
+      c->launches++;
+      ORCAI_CUDA(c, cudaGetLastError());
+    } else if (nw->conv0_path >= 1) {
       // fp16 normalised rows of this chunk, then the pixel-group tensor-core convolution over a strided snippet view
       const long long srows = input_mode == 0 ? (m - 1) * shift + Himg : m * (long long)Himg;
       const float* src = (input_mode == 0) ? d_in + (size_t)(first + s0) * shift * kRawLd : d_in + (size_t)s0 * Himg * Wf;
       const long long total2 = srows * (conv0::kSpecLd / 2);
       conv0::spec_half_kernel<<<(unsigned)std::min<long long>((total2 + 255) / 256, (long long)c->sm_count * 16), 256, 0, c->stream>>>(
           src, input_mode, input_mode == 0 ? kRawLd : Wf, srows, Wf, c->d_sel, spec16);
+      c->launches++;
+      ORCAI_CUDA(c, cudaGetLastError());
       CUtensorMap tms;
       {
         EncodeTiledFn fn = encode_tiled_fn();
@@ -873,7 +927,7 @@ int forward_fused(Ctx* c, const float* d_in, int input_mode, int64_t first, int6
       const long long grid = std::min<long long>(n_tiles, (long long)c->sm_count * 4);
       conv0::conv0_mma_kernel<<<(unsigned)grid, 160, conv0::kSmem, c->stream>>>(tms, act[0], static_cast<H*>(nullptr), Himg, Wf, tiles_per, n_tiles,
                                                                                static_cast<const unsigned char*>(nw->conv0_mma_w));
-      c->launches += 2;
+      c->launches++;
       ORCAI_CUDA(c, cudaGetLastError());
     } else {
       const int tiles_w = (Wf + kC0TW - 1) / kC0TW, tiles_h = (Himg + kC0TH - 1) / kC0TH;
@@ -885,7 +939,8 @@ int forward_fused(Ctx* c, const float* d_in, int input_mode, int64_t first, int6
     }
     net_mark(c, mk);  // 0: conv0
     if (stop == 0) { set_debug(nw, act[0], 1, m, hs[0], ws[0], 16, 16); return ORCAI_OK; }
-    ORCAI_CHECK((run_fused_block<FB1>(c, 0, act[0], static_cast<const H*>(nullptr), act[1], acts[1], m, hs[0], ws[0])));
+    if (fuse0) ORCAI_CHECK(run_fused_block1_conv0(c, spec16, input_mode == 0 ? shift : Himg, act[1], acts[1], m, hs[0], ws[0]));
+    else ORCAI_CHECK((run_fused_block<FB1>(c, 0, act[0], static_cast<const H*>(nullptr), act[1], acts[1], m, hs[0], ws[0])));
     net_mark(c, mk);  // 1
     if (stop == 1) { set_debug(nw, act[1], 1, m, hs[1], ws[1], 30, cp[1]); return ORCAI_OK; }
     if (stop == 21) { set_debug(nw, acts[1], 1, m, hs[2], ws[2], 30, cp[1]); return ORCAI_OK; }
@@ -969,6 +1024,8 @@ int net_calibrate(Ctx* c, int64_t max_snippets) {
   nw->tail_tc_ready = false;
   return ORCAI_OK;
 }
+
+const unsigned int* net_trap_info() { return g_trap_host; }
 
 int net_tc_prepare(Ctx* c, int fmt) {
   NetWeights* nw = c->net;

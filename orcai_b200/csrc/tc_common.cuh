@@ -44,6 +44,11 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
+// Bring-up aid: when the host points this at mapped host memory (ORCAI_B200_TRAPINFO=1, net_tc.cu), a wait that gives up
+// records {magic, blockIdx.x, threadIdx.x, barrier shared address, parity} there before it traps; orcai_last_error
+// appends the record.  One copy per translation unit (no relocatable device code).
+static __device__ unsigned int* g_trap_info = nullptr;
+
 // Wait for the phase with the given parity.  Bounded: a broken pipeline traps instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
@@ -56,7 +61,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(done)
         : "r"(addr), "r"(parity)
         : "memory");
-    if (!done && spin > (1u << 26)) __trap();
+    if (!done && spin > (1u << 26)) {
+      unsigned int* ti = g_trap_info;
+      if (ti != nullptr && atomicCAS(ti, 0u, 0x7241u) == 0u) {
+        ti[1] = blockIdx.x; ti[2] = threadIdx.x; ti[3] = addr; ti[4] = parity;
+        __threadfence_system();
+      }
+      __trap();
+    }
   }
 }
 

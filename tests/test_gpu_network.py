@@ -113,6 +113,15 @@ def test_fast_path_fused_tensor_core_blocks(ctx, params, golden_dir, tail_path):
         alt = ctx.forward_host(x7)
         ctx.set_option("conv0_path", 1)
         assert np.abs(alt - full).max() <= FAST_TOL
+        # the entry convolution fused into block 1 (conv0_path 2: CUDA-core producer warps fed by a strip-cut spectrogram)
+        ctx.set_option("conv0_path", 2)
+        fused0 = ctx.forward_host(x7)
+        ctx.set_option("chunk", 3)
+        np.testing.assert_array_equal(ctx.forward_host(x7), fused0)
+        ctx.set_option("chunk", 2048)
+        ctx.set_option("conv0_path", 1)
+        assert np.abs(fused0 - full).max() <= FAST_TOL
+        assert np.abs(fused0 - network_oracle.forward(x7, W)).max() <= FAST_TOL
     finally:
         ctx.set_option("conv0_path", 1)
         ctx.set_option("net_path", 0)
