@@ -124,10 +124,11 @@ def load_orcai_model(model_dir: Path | str, device: int | None = None):
     """Load a model directory -> (model, orcai_parameter, shape).
 
     The directory holds ``orcai_parameter.json`` and ``model_shape.json`` like the reference's.  Weights are
-    looked up as ``<name>.weights.npz`` (this package's container, see ``orcai_b200/weights.py``).  The Keras
-    artefacts ``<name>.keras`` / ``model_weights.h5`` cannot be read here yet (no HDF5 library in the image;
-    SURVEY.md section 8f rank 2).  With ``ORCAI_B200_SYNTHETIC_WEIGHTS=<seed>`` set, seeded synthetic weights are
-    used instead (benchmarks / smoke tests; the packaged orcai-v1.keras blob is absent from the reference mount).
+    looked up as ``<name>.weights.npz`` (this package's container, see ``orcai_b200/weights.py``), then - like the
+    reference, ``io.py:386-404`` - as ``<name>.keras`` (Keras 3 archive) and as the legacy ``model_weights.h5``; both are
+    read by ``orcai_b200.keras_weights`` on top of the pure-Python HDF5 reader ``orcai_b200.hdf5_min`` (no keras / h5py).
+    With ``ORCAI_B200_SYNTHETIC_WEIGHTS=<seed>`` set, seeded synthetic weights are used instead (benchmarks / smoke
+    tests; the packaged orcai-v1.keras blob is absent from the reference mount).
     """
     from orcai_b200.model import OrcaiModel
     from orcai_b200.weights import load_npz, synthetic_weights
@@ -142,12 +143,14 @@ def load_orcai_model(model_dir: Path | str, device: int | None = None):
         W = load_npz(npz)
     elif synth is not None:
         W = synthetic_weights(orcai_parameter, shape, seed=int(synth) if synth.strip().lstrip("-").isdigit() else 1234)
-    elif model_dir.joinpath(name + ".keras").exists() or model_dir.joinpath("model_weights.h5").exists():
-        raise NotImplementedError(
-            f"{model_dir}: Keras/HDF5 weight files cannot be read by orcai_b200 yet; export them once with "
-            "`python tools/export_keras_weights.py` on a machine with keras and place "
-            f"{name}.weights.npz next to orcai_parameter.json"
-        )
+    elif model_dir.joinpath(name + ".keras").exists():
+        from orcai_b200.keras_weights import load_keras_archive
+
+        W = load_keras_archive(model_dir.joinpath(name + ".keras"), orcai_parameter, shape)
+    elif model_dir.joinpath("model_weights.h5").exists():
+        from orcai_b200.keras_weights import load_weights_h5
+
+        W = load_weights_h5(model_dir.joinpath("model_weights.h5"), orcai_parameter, shape)
     else:
         raise ValueError(f"Couldn't find model weights ({name}.weights.npz, model_weights.h5) or keras model file in {model_dir}")
     model = OrcaiModel(orcai_parameter, shape, W, device=device)
