@@ -107,12 +107,15 @@ def test_fast_path_fused_tensor_core_blocks(ctx, params, golden_dir, tail_path):
         np.testing.assert_array_equal(full, chunked)
         np.testing.assert_array_equal(ctx.forward_host(x7[4:5]), full[4:5])
         W = synthetic_weights(P, S, seed=1234)
-        assert np.abs(full - network_oracle.forward(x7, W)).max() <= FAST_TOL
-        # the fp32 CUDA-core entry convolution (conv0_path 0) instead of the tensor-core pixel-group one
+        ref7 = network_oracle.forward(x7, W)
+        assert np.abs(full - ref7).max() <= FAST_TOL
+        # the fp32 CUDA-core entry convolution (conv0_path 0) instead of the tensor-core pixel-group one: each variant is held
+        # to the oracle; two variants may differ from each other by up to twice that
         ctx.set_option("conv0_path", 0)
         alt = ctx.forward_host(x7)
         ctx.set_option("conv0_path", 1)
-        assert np.abs(alt - full).max() <= FAST_TOL
+        assert np.abs(alt - ref7).max() <= FAST_TOL
+        assert np.abs(alt - full).max() <= 2 * FAST_TOL
         # the entry convolution fused into block 1 (conv0_path 2: CUDA-core producer warps fed by a strip-cut spectrogram)
         ctx.set_option("conv0_path", 2)
         fused0 = ctx.forward_host(x7)
@@ -120,8 +123,8 @@ def test_fast_path_fused_tensor_core_blocks(ctx, params, golden_dir, tail_path):
         np.testing.assert_array_equal(ctx.forward_host(x7), fused0)
         ctx.set_option("chunk", 2048)
         ctx.set_option("conv0_path", 1)
-        assert np.abs(fused0 - full).max() <= FAST_TOL
-        assert np.abs(fused0 - network_oracle.forward(x7, W)).max() <= FAST_TOL
+        assert np.abs(fused0 - ref7).max() <= FAST_TOL
+        assert np.abs(fused0 - full).max() <= 2 * FAST_TOL
     finally:
         ctx.set_option("conv0_path", 1)
         ctx.set_option("net_path", 0)
