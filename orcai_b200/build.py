@@ -22,6 +22,7 @@ LIB = PKG / "liborcai_b200.so"
 OBJ = PKG / "csrc" / "_obj"
 SOURCES = ["abi.cu", "stft.cu", "select.cu", "post.cu", "net.cu", "net_tc.cu", "net_lstm_tc.cu"]
 NVCC_FLAGS = [
+    *os.environ.get("ORCAI_B200_NVCC_EXTRA", "").split(),   # bring-up aids: -DORCAI_TRAP_INFO (which mbarrier wait gave up), -DORCAI_FUSED_TRACE (hand-off timeline)
     "-O3",
     "-std=c++17",
     "-gencode",

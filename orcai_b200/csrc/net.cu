@@ -463,6 +463,7 @@ int net_create(Ctx* c) {
 
 // stage times of the first chunk of the last forward; call after the stream has been synchronised
 void net_collect_stage_times(Ctx* c) {
+  net_trace_dump();
   NetWeights* nw = c->net;
   if (!nw || nw->marked_snippets == 0) return;
   for (int i = 0; i + 1 < NetWeights::kNumMarks; ++i) {

@@ -46,12 +46,17 @@ __host__ __device__ constexpr int round8(int a) { return (a + 7) & ~7; }
 __host__ __device__ constexpr int pow2cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
 
 // CONV0_: the block's input is produced in-kernel from the fp16 spectrogram by the entry convolution (CUDA-core producer warps)
-template <int CIN_, int COUT_, int CPOOL_, int S_, bool RELU_OUT_, int CTAS_, int NEW_, bool CONV0_ = false>
+// ISS_: issuer warps.  One tcgen05.mma stream sustains ~59 cycles per M128 K16 MMA whatever N <= 64 is; two streams on an
+//        SM reach the shared-memory bound (41 / 47 / 52 cycles at N = 32 / 48 / 64; tools/microbench/mma_cost.cu).  With
+//        ISS_ = 2 the first convolution (+ residual 1x1) and the second convolution are issued by separate warps
+//        (splitting the TILES of each convolution between two warps instead measured 7-10 % slower).
+template <int CIN_, int COUT_, int CPOOL_, int S_, bool RELU_OUT_, int CTAS_, int NEW_, bool CONV0_ = false, int ISS_ = 1>
 struct FB {
-  static constexpr int CIN = CIN_, COUT = COUT_, CP = CPOOL_, S = S_, CTAS = CTAS_, NEW = NEW_;
+  static constexpr int CIN = CIN_, COUT = COUT_, CP = CPOOL_, S = S_, CTAS = CTAS_, NEW = NEW_, ISS = ISS_;
   static constexpr bool RELU_OUT = RELU_OUT_, CONV0 = CONV0_;
   static constexpr int NPROD = CONV0 ? 2 : 1;                       // producer warps: one TMA warp, or two entry-convolution warps
-  static constexpr int NWORK = NEW * 32, NTHREADS = NWORK + 32 + 32 * NPROD;   // + issuer warp + producer warp(s)
+  static constexpr int NWORK = NEW * 32, NTHREADS = NWORK + 32 * ISS + 32 * NPROD;   // + issuer warp(s) + producer warp(s)
+  static_assert(ISS == 1 || ISS == 2, "one or two issuer warps");
   static constexpr int NT = NEW / 4;                 // worker teams per TMEM lane quadrant; a team drains 16 columns
   static constexpr int ICP = cpad8(CIN), OCP = cpad8(COUT);
   static constexpr int KP1 = cpad16(CIN);          // K per tap of sepconv 1 and of the residual convolution
@@ -139,6 +144,20 @@ __device__ __forceinline__ bool elect_one() {
       : "memory");
   return pred != 0;
 }
+// Bring-up aid (compile with -DORCAI_FUSED_TRACE, run with ORCAI_B200_TRACE=<file>): CTA 0 stamps clock64() at the hand-offs
+// of a few steps into device memory (plain stores, one slot per event); tools/scratch/trace_timeline.py prints the timeline.  Compiled out by default.
+#ifdef ORCAI_FUSED_TRACE
+static __device__ long long* g_trace = nullptr;   // device memory: [CIN / 10][step - 40][tag] clock64() stamps, plain stores
+__device__ __forceinline__ void trace_event(int kernel, int tag, long long g) {
+  long long* t = g_trace;
+  if (t == nullptr || blockIdx.x != 0 || g < 40 || g >= 44 || (threadIdx.x & 31) != 0) return;
+  t[(kernel / 10) * 256 + (int)(g - 40) * 64 + tag] = clock64();
+}
+#define FB_TRACE(tag, g) trace_event(G::CIN, tag, g)
+#else
+#define FB_TRACE(tag, g)
+#endif
+
 template <int N>
 __device__ __forceinline__ void worker_sync() {   // named barrier 1: the worker warps only
   asm volatile("bar.sync 1, %0;" ::"n"(N) : "memory");
@@ -215,7 +234,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   const long long my_items = blockIdx.x < n_items ? (n_items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   const long long total_steps = my_items * n_steps;
 
-  if (warp > G::NEW) {
+  if (warp >= G::NEW + G::ISS) {
     if constexpr (G::CONV0) {
       // =============================== entry-convolution producers ===============================
       // Conv2D 3x3 1->16 + folded BatchNorm + ReLU (architectures.py:162-168) on the CUDA cores, straight into the X planes
@@ -223,7 +242,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       // FFMA operands.  tmX is the rank-4 map of the strip-cut spectrogram (conv0::spec_strips_kernel: SPW columns of a strip,
       // strip, rows of a snippet, snippet); its outer stride is the snippet shift, rows outside the snippet are zero-filled,
       // columns outside the image are zero in the buffer.  Lane = X column; 64 lanes walk the S+2 rows with a sliding 3x3 window.
-      const int pl = (warp - G::NEW - 1) * 32 + lane;     // 0..63
+      const int pl = (warp - G::NEW - G::ISS) * 32 + lane;     // 0..63
       const __half* s_spec = reinterpret_cast<const __half*>(smem + G::OFF_SPEC);
       constexpr uint32_t SPEC_STRIDE = (G::SPEC_BYTES + 127) / 128 * 128;
       auto load_spec = [&](long long gg, long long item2, int step2) {   // elected lane of producer warp 0
@@ -233,7 +252,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         tma_load_4d(sbase + G::OFF_SPEC + (uint32_t)(gg & 1) * SPEC_STRIDE, &tmX, &bars[G::B_SP + (int)(gg & 1)], 0, strip2,
                     step2 * G::S - 3, (int)b2);
       };
-      if (warp == G::NEW + 1 && total_steps > 0 && elect_one()) load_spec(0, blockIdx.x, 0);
+      if (warp == G::NEW + G::ISS && total_steps > 0 && elect_one()) load_spec(0, blockIdx.x, 0);
       __syncwarp();
       long long g = 0;
       for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
@@ -246,7 +265,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
           // means BOTH producer warps have finished step g-1, i.e. the other spectrogram buffer has no readers left
           if (g > 0) mbar_wait(&bars[G::B_1 + G::N1 - 1], (uint32_t)((g - 1) & 1));
           // prefetch the next step's spectrogram tile into the other buffer
-          if (warp == G::NEW + 1 && g + 1 < total_steps && elect_one()) {
+          if (warp == G::NEW + G::ISS && g + 1 < total_steps && elect_one()) {
             if (step + 1 < n_steps) load_spec(g + 1, item, step + 1);
             else load_spec(g + 1, item + gridDim.x, 0);
           }
@@ -312,6 +331,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         const int a = step * G::S - 2;
         // X and R are free once the previous step's first convolution (and residual MMA) has completed
         if (g > 0) mbar_wait(&bars[G::B_1 + G::N1 - 1], (uint32_t)((g - 1) & 1));
+        FB_TRACE(5, g);
         if (elect_one()) {
           mbar_arrive_expect_tx(&bars[G::B_X], G::TX_BYTES);
 #pragma unroll
@@ -325,8 +345,8 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       }
     }
     }
-  } else if (warp == G::NEW) {
-    // =============================== MMA issuer ===============================
+  } else if (warp >= G::NEW) {
+    // =============================== MMA issuer(s) ===============================
     // The whole warp runs the control flow; one elected lane issues (elect.sync keeps the tensor-core instructions in
     // warp-uniform code, so ptxas emits them back to back instead of wrapping each one in a per-lane loop).
     if (total_steps > 0) {
@@ -342,60 +362,129 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       const uint64_t dB1 = make_smem_desc(sbase + G::OFF_WB1, 128, 128);
       const uint64_t dB2 = make_smem_desc(sbase + G::OFF_WB2, 128, 128);
       const uint64_t dBR = make_smem_desc(sbase + G::OFF_WBR, 128, 128);
-      auto issue_first = [&](long long g) {   // residual 1x1 and first separable convolution of step g
-        if (elect_one()) {
-          const uint32_t colr = tmem + G::COL_R + (uint32_t)(g & 1) * G::NP;
-          mma_f16_ss(colr, dOnes, dBR, idesc, 0);
-#pragma unroll
-          for (int ks = 0; ks < G::KP1 / 16; ++ks)
-            mma_f16_ss(colr, dR + ((2 * ks * G::LBO_R) >> 4), dWR + ((2 * ks * 128) >> 4), idesc, 1);
-          mma_commit(&bars[G::B_R + (int)(g & 1)]);
-#pragma unroll
-          for (int t = 0; t < G::N1; ++t) {
-            mma_f16_ss(tmem + G::COL_1 + t * G::NP, dOnes, dB1, idesc, 0);
-#pragma unroll
-            for (int tap = 0; tap < 9; ++tap) {
-              const uint32_t aoff = (uint32_t)(G::P1_0 + 128 * t - 2 * G::WP - 1 + (tap / 3) * G::WP + (tap % 3));   // pixels = 16-byte units
-#pragma unroll
-              for (int ks = 0; ks < G::KP1 / 16; ++ks)
-                mma_f16_ss(tmem + G::COL_1 + t * G::NP, dX + aoff + ((2 * ks * G::LBO_X) >> 4),
-                           dW1 + ((tap * G::TAP_W1 + 2 * ks * 128) >> 4), idesc, 1);
-            }
-            mma_commit(&bars[G::B_1 + t]);
-          }
-        }
-        __syncwarp();
-      };
-      mbar_wait(&bars[G::B_X], 0);
-      tc_fence_after();
-      issue_first(0);
-      for (long long g = 0; g < total_steps; ++g) {
-        const uint32_t par = (uint32_t)(g & 1);
-#pragma unroll
-        for (int t = 0; t < G::N2; ++t) {
-          // tile t of the second convolution reads S1 tiles <= t+1 (and the carried rows, published with tile 0)
-          if (t == 0) mbar_wait(&bars[G::B_S1], par);
-          if (t + 1 < G::N1) mbar_wait(&bars[G::B_S1 + t + 1], par);
-          tc_fence_after();
+      if constexpr (G::ISS == 1) {
+        auto issue_first = [&](long long g) {   // residual 1x1 and first separable convolution of step g
           if (elect_one()) {
-            mma_f16_ss(tmem + G::COL_2 + t * G::NP, dOnes, dB2, idesc, 0);
+            const uint32_t colr = tmem + G::COL_R + (uint32_t)(g & 1) * G::NP;
+            mma_f16_ss(colr, dOnes, dBR, idesc, 0);
 #pragma unroll
-            for (int tap = 0; tap < 9; ++tap) {
-              const uint32_t aoff = (uint32_t)(G::P2_0 + 128 * t - G::WP - 1 + (tap / 3) * G::WP + (tap % 3));
+            for (int ks = 0; ks < G::KP1 / 16; ++ks)
+              mma_f16_ss(colr, dR + ((2 * ks * G::LBO_R) >> 4), dWR + ((2 * ks * 128) >> 4), idesc, 1);
+            mma_commit(&bars[G::B_R + (int)(g & 1)]);
 #pragma unroll
-              for (int ks = 0; ks < G::NP / 16; ++ks)
-                mma_f16_ss(tmem + G::COL_2 + t * G::NP, dS1 + aoff + ((2 * ks * G::LBO_S1) >> 4),
-                           dW2 + ((tap * G::TAP_W2 + 2 * ks * 128) >> 4), idesc, 1);
+            for (int t = 0; t < G::N1; ++t) {
+              mma_f16_ss(tmem + G::COL_1 + t * G::NP, dOnes, dB1, idesc, 0);
+#pragma unroll
+              for (int tap = 0; tap < 9; ++tap) {
+                const uint32_t aoff = (uint32_t)(G::P1_0 + 128 * t - 2 * G::WP - 1 + (tap / 3) * G::WP + (tap % 3));   // pixels = 16-byte units
+#pragma unroll
+                for (int ks = 0; ks < G::KP1 / 16; ++ks)
+                  mma_f16_ss(tmem + G::COL_1 + t * G::NP, dX + aoff + ((2 * ks * G::LBO_X) >> 4),
+                             dW1 + ((tap * G::TAP_W1 + 2 * ks * 128) >> 4), idesc, 1);
+              }
+              mma_commit(&bars[G::B_1 + t]);
             }
-            mma_commit(&bars[G::B_2 + t]);
           }
           __syncwarp();
+        };
+        mbar_wait(&bars[G::B_X], 0);
+        tc_fence_after();
+        issue_first(0);
+        for (long long g = 0; g < total_steps; ++g) {
+          const uint32_t par = (uint32_t)(g & 1);
+#pragma unroll
+          for (int t = 0; t < G::N2; ++t) {
+            // tile t of the second convolution reads S1 tiles <= t+1 (and the carried rows, published with tile 0)
+            if (t == 0) mbar_wait(&bars[G::B_S1], par);
+            if (t + 1 < G::N1) mbar_wait(&bars[G::B_S1 + t + 1], par);
+            tc_fence_after();
+            if (elect_one()) {
+              mma_f16_ss(tmem + G::COL_2 + t * G::NP, dOnes, dB2, idesc, 0);
+#pragma unroll
+              for (int tap = 0; tap < 9; ++tap) {
+                const uint32_t aoff = (uint32_t)(G::P2_0 + 128 * t - G::WP - 1 + (tap / 3) * G::WP + (tap % 3));
+#pragma unroll
+                for (int ks = 0; ks < G::NP / 16; ++ks)
+                  mma_f16_ss(tmem + G::COL_2 + t * G::NP, dS1 + aoff + ((2 * ks * G::LBO_S1) >> 4),
+                             dW2 + ((tap * G::TAP_W2 + 2 * ks * 128) >> 4), idesc, 1);
+              }
+              mma_commit(&bars[G::B_2 + t]);
+            }
+            __syncwarp();
+          }
+          if (g + 1 < total_steps) {
+            if (g >= 1) mbar_wait(&bars[G::B_P], par ^ 1);   // pooling of step g-1 has read the residual buffer step g+1 reuses
+            mbar_wait(&bars[G::B_X], par ^ 1);
+            tc_fence_after();
+            issue_first(g + 1);
+          }
         }
-        if (g + 1 < total_steps) {
-          if (g >= 1) mbar_wait(&bars[G::B_P], par ^ 1);   // pooling of step g-1 has read the residual buffer step g+1 reuses
-          mbar_wait(&bars[G::B_X], par ^ 1);
+      } else if (warp == G::NEW) {
+        // ---- issuer A: residual 1x1 + first separable convolution of every step ----
+        // Its own stream no longer follows the second convolution of the previous step, so it waits explicitly until the
+        // workers have drained the accumulator tile it is about to overwrite (s1_full[t] of step g-1).
+        for (long long g = 0; g < total_steps; ++g) {
+          if (g >= 2) mbar_wait(&bars[G::B_P], (uint32_t)(g & 1));   // pooling of step g-2 has read the residual buffer step g reuses
+          mbar_wait(&bars[G::B_X], (uint32_t)(g & 1));
           tc_fence_after();
-          issue_first(g + 1);
+          FB_TRACE(1, g);
+          if (elect_one()) {
+            const uint32_t colr = tmem + G::COL_R + (uint32_t)(g & 1) * G::NP;
+            mma_f16_ss(colr, dOnes, dBR, idesc, 0);
+#pragma unroll
+            for (int ks = 0; ks < G::KP1 / 16; ++ks)
+              mma_f16_ss(colr, dR + ((2 * ks * G::LBO_R) >> 4), dWR + ((2 * ks * 128) >> 4), idesc, 1);
+            mma_commit(&bars[G::B_R + (int)(g & 1)]);
+          }
+          __syncwarp();
+#pragma unroll
+          for (int t = 0; t < G::N1; ++t) {
+            if (g > 0) {
+              mbar_wait(&bars[G::B_S1 + t], (uint32_t)((g - 1) & 1));
+              tc_fence_after();
+            }
+            if (elect_one()) {
+              mma_f16_ss(tmem + G::COL_1 + t * G::NP, dOnes, dB1, idesc, 0);
+#pragma unroll
+              for (int tap = 0; tap < 9; ++tap) {
+                const uint32_t aoff = (uint32_t)(G::P1_0 + 128 * t - 2 * G::WP - 1 + (tap / 3) * G::WP + (tap % 3));   // pixels = 16-byte units
+#pragma unroll
+                for (int ks = 0; ks < G::KP1 / 16; ++ks)
+                  mma_f16_ss(tmem + G::COL_1 + t * G::NP, dX + aoff + ((2 * ks * G::LBO_X) >> 4),
+                             dW1 + ((tap * G::TAP_W1 + 2 * ks * 128) >> 4), idesc, 1);
+              }
+              mma_commit(&bars[G::B_1 + t]);
+            }
+            __syncwarp();
+          }
+          FB_TRACE(2, g);
+        }
+      } else {
+        // ---- issuer B: second separable convolution of every step ----
+        for (long long g = 0; g < total_steps; ++g) {
+          const uint32_t par = (uint32_t)(g & 1);
+          FB_TRACE(3, g);
+#pragma unroll
+          for (int t = 0; t < G::N2; ++t) {
+            // tile t of the second convolution reads S1 tiles <= t+1 (and the carried rows, published with tile 0)
+            if (t == 0) mbar_wait(&bars[G::B_S1], par);
+            if (t + 1 < G::N1) mbar_wait(&bars[G::B_S1 + t + 1], par);
+            tc_fence_after();
+            if (elect_one()) {
+              mma_f16_ss(tmem + G::COL_2 + t * G::NP, dOnes, dB2, idesc, 0);
+#pragma unroll
+              for (int tap = 0; tap < 9; ++tap) {
+                const uint32_t aoff = (uint32_t)(G::P2_0 + 128 * t - G::WP - 1 + (tap / 3) * G::WP + (tap % 3));
+#pragma unroll
+                for (int ks = 0; ks < G::NP / 16; ++ks)
+                  mma_f16_ss(tmem + G::COL_2 + t * G::NP, dS1 + aoff + ((2 * ks * G::LBO_S1) >> 4),
+                             dW2 + ((tap * G::TAP_W2 + 2 * ks * 128) >> 4), idesc, 1);
+              }
+              mma_commit(&bars[G::B_2 + t]);
+            }
+            __syncwarp();
+          }
+          FB_TRACE(4, g);
         }
       }
     }
@@ -472,6 +561,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         for (int t = 0; t < G::N1; ++t) {
           mbar_wait(&bars[G::B_1 + t], par);
           tc_fence_after();
+          if (warp == 0) FB_TRACE(10 + t, g);
           if (has0) {
             float v[16];
             tmem_ld16f(lane_addr + G::COL_1 + t * G::NP + g0 * 8, v);
@@ -491,8 +581,10 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
           if (lane == 0) mbar_arrive(&bars[G::B_S1 + t]);
         }
         // ---- previous step: pool + store while the tensor pipe runs this step's second convolution ----
+        if (warp == 0) FB_TRACE(20, g);
         if (g > 0) {
           pool_store(g - 1, prev_b, prev_wo0, prev_a);
+          if (warp == 0) FB_TRACE(21, g);
           worker_sync<G::NWORK>();   // pooling has finished reading S2
           if (prev_carry) {
             for (int i = tid; i < G::NG * G::WP; i += G::NWORK) {
@@ -507,8 +599,10 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         // ---- epilogue 2: -inf outside the image (TF "same" max-pool padding) -> S2 ----
 #pragma unroll
         for (int t = 0; t < G::N2; ++t) {
+          if (warp == 0 && t == 0) FB_TRACE(22, g);
           mbar_wait(&bars[G::B_2 + t], par);
           tc_fence_after();
+          if (warp == 0) FB_TRACE(30 + t, g);
           if (has0) {
             float v[16];
             tmem_ld16f(lane_addr + G::COL_2 + t * G::NP + g0 * 8, v);
@@ -524,7 +618,9 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
           }
         }
         tc_fence_before();
+        if (warp == 0) FB_TRACE(39, g);
         worker_sync<G::NWORK>();   // every worker has seen the second convolution complete: S1 is free, S2 is written
+        if (warp == 0) FB_TRACE(40, g);
         // ---- carry the S1 overlap rows into the next step (rows above the next strip's first row are zero) ----
         const bool carry = step + 1 < n_steps;
         if (g + 1 < total_steps) {
@@ -535,6 +631,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
           }
           worker_sync<G::NWORK>();   // carried rows in place before epilogue 1 overwrites their source rows
         }
+        if (warp == 0) FB_TRACE(41, g);
         prev_b = b; prev_wo0 = wo0; prev_a = a; prev_carry = carry;
       }
     }

@@ -617,9 +617,10 @@ int forward_tc(Ctx* c, const float* d_in, int input_mode, int64_t first, int64_t
 // fused path (net_path 3): conv0 -> 4 fused residual-block kernels -> final sepconv -> fp32 LSTM/dense tail
 // ------------------------------------------------------------------------------------------------
 using FB1 = fused::FB<16, 30, 29, 6, true, 2, 8>;
-using FB2 = fused::FB<30, 40, 43, 4, true, 1, 16>;
-using FB3 = fused::FB<40, 50, 22, 4, true, 1, 16>;
-using FB4 = fused::FB<50, 60, 11, 4, false, 1, 16>;
+// blocks 2-4 run one CTA per SM: two issuer warps, or the single MMA stream would cost ~59 cycles per MMA instead of 47-52
+using FB2 = fused::FB<30, 40, 43, 4, true, 1, 16, false, 2>;
+using FB3 = fused::FB<40, 50, 22, 4, true, 1, 16, false, 2>;
+using FB4 = fused::FB<50, 60, 11, 4, false, 1, 16, false, 2>;
 using FB1C = fused::FB<16, 30, 29, 6, true, 2, 8, true>;   // block 1 with the entry convolution fused in (conv0_path 2)
 static_assert(FB1C::W_BYTES == FB1::W_BYTES && FB1C::OFF_SPEC % 128 == 0, "FB1C shares FB1's weight pack; TMA destinations are 128-byte aligned");
 
@@ -728,11 +729,22 @@ int build_conv0_mma(Ctx* c) {
   return ORCAI_OK;
 }
 
-unsigned int* g_trap_host = nullptr;   // mapped host memory behind tc::g_trap_info (ORCAI_B200_TRAPINFO=1)
+unsigned int* g_trap_host = nullptr;   // mapped host memory behind tc::g_trap_info (-DORCAI_TRAP_INFO builds, ORCAI_B200_TRAPINFO=1)
+#ifdef ORCAI_FUSED_TRACE
+long long* g_trace_dev = nullptr;      // device memory behind fused::g_trace (ORCAI_B200_TRACE=<file>)
+#endif
 
 int prepare_fused(Ctx* c) {
   NetWeights* nw = c->net;
   if (nw->fused_ready) return ORCAI_OK;
+#ifdef ORCAI_FUSED_TRACE
+  if (g_trace_dev == nullptr && getenv("ORCAI_B200_TRACE") != nullptr) {
+    ORCAI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&g_trace_dev), 8 * 8 * 256));
+    ORCAI_CUDA(c, cudaMemset(g_trace_dev, 0, 8 * 8 * 256));
+    ORCAI_CUDA(c, cudaMemcpyToSymbol(fused::g_trace, &g_trace_dev, sizeof g_trace_dev));
+  }
+#endif
+#ifdef ORCAI_TRAP_INFO
   if (g_trap_host == nullptr && getenv("ORCAI_B200_TRAPINFO") != nullptr) {
     unsigned int* d = nullptr;
     ORCAI_CUDA(c, cudaHostAlloc(reinterpret_cast<void**>(&g_trap_host), 64, cudaHostAllocMapped));
@@ -740,6 +752,7 @@ int prepare_fused(Ctx* c) {
     ORCAI_CUDA(c, cudaHostGetDevicePointer(reinterpret_cast<void**>(&d), g_trap_host, 0));
     ORCAI_CUDA(c, cudaMemcpyToSymbol(tc::g_trap_info, &d, sizeof d));
   }
+#endif
   ORCAI_CHECK(net_tc_prepare(c, 0));   // the final sepconv reuses the fp16 layer-wise operands
   ORCAI_CHECK(build_conv0_mma(c));
   ORCAI_CHECK(build_fused_block<FB1>(c, 0));
@@ -1026,6 +1039,25 @@ int net_calibrate(Ctx* c, int64_t max_snippets) {
 }
 
 const unsigned int* net_trap_info() { return g_trap_host; }
+
+#ifdef ORCAI_FUSED_TRACE
+// called after a stream synchronise: append the recorded hand-off stamps to $ORCAI_B200_TRACE and clear them
+void net_trace_dump() {
+  const char* path = getenv("ORCAI_B200_TRACE");
+  if (!path || !g_trace_dev) return;
+  std::vector<long long> h(8 * 256);
+  if (cudaMemcpy(h.data(), g_trace_dev, h.size() * 8, cudaMemcpyDeviceToHost) != cudaSuccess) return;
+  cudaMemset(g_trace_dev, 0, h.size() * 8);
+  if (FILE* f = fopen(path, "a")) {
+    for (size_t i = 0; i < h.size(); ++i)
+      if (h[i]) fprintf(f, "%lld %lld\n", (long long)(((i / 256) * 10) << 32 | (40 + (i % 256) / 64) << 8 | (i % 64)), h[i]);
+    fprintf(f, "-1 -1\n");
+    fclose(f);
+  }
+}
+#else
+void net_trace_dump() {}
+#endif
 
 int net_tc_prepare(Ctx* c, int fmt) {
   NetWeights* nw = c->net;

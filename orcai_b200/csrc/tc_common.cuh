@@ -44,10 +44,13 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
-// Bring-up aid: when the host points this at mapped host memory (ORCAI_B200_TRAPINFO=1, net_tc.cu), a wait that gives up
-// records {magic, blockIdx.x, threadIdx.x, barrier shared address, parity} there before it traps; orcai_last_error
-// appends the record.  One copy per translation unit (no relocatable device code).
-static __device__ unsigned int* g_trap_info = nullptr;
+// Bring-up aid (compile with -DORCAI_TRAP_INFO, run with ORCAI_B200_TRAPINFO=1; net_tc.cu): a wait that gives up records
+// {magic, blockIdx.x, threadIdx.x, barrier shared address, parity} in mapped host memory before it traps, and
+// orcai_last_error appends the record.  Compiled out by default: the extra live values of the cold path cost registers
+// (spills in conv0_mma_kernel and lstm_rec_tc_kernel, +0.5 ms per hour of audio when it was always on).
+#ifdef ORCAI_TRAP_INFO
+static __device__ unsigned int* g_trap_info = nullptr;   // one copy per translation unit (no relocatable device code)
+#endif
 
 // Wait for the phase with the given parity.  Bounded: a broken pipeline traps instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
@@ -62,11 +65,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "r"(addr), "r"(parity)
         : "memory");
     if (!done && spin > (1u << 26)) {
+#ifdef ORCAI_TRAP_INFO
       unsigned int* ti = g_trap_info;
       if (ti != nullptr && atomicCAS(ti, 0u, 0x7241u) == 0u) {
         ti[1] = blockIdx.x; ti[2] = threadIdx.x; ti[3] = addr; ti[4] = parity;
         __threadfence_system();
       }
+#endif
       __trap();
     }
   }

@@ -37,7 +37,7 @@ constexpr uint32_t kLboA = kAPix * 16;      // chunk plane stride
 constexpr uint32_t OFF_A = 0, OFF_B = 2 * kLboA, OFF_BAR = OFF_B + 256 * 16 * 2 * 2, SMEM = OFF_BAR + 64;
 
 // mode 0: SS, 1: TS, 2: CP only, 3: TS with one CP per 3 MMAs (the "one staged copy serves the three dy taps" pattern)
-template <int N, int MODE, int CTAS>
+template <int N, int MODE, int CTAS, int NACC = 2, int NISS = 1>
 __global__ void __launch_bounds__(128, CTAS) cost_kernel(long long* out_cycles, int reps, int per_commit) {
   constexpr int COLS = 512 / CTAS;
   extern __shared__ __align__(128) unsigned char smem[];
@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(128, CTAS) cost_kernel(long long* out_cycles, 
   uint32_t* tslot = reinterpret_cast<uint32_t*>(bar + 2);
   const int tid = threadIdx.x, warp = tid >> 5;
   for (int i = tid; i < (int)(OFF_BAR / 4); i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;   // fp16 1.0 pairs
-  if (tid == 0) { mbar_init(bar, 1); fence_mbar_init(); }
+  if (tid == 0) { mbar_init(bar, 1); mbar_init(bar + 1, 1); fence_mbar_init(); }
   __syncwarp();
   if (warp == 0) tmem_alloc<COLS>(tslot);
   fence_proxy_async();
@@ -54,8 +54,10 @@ __global__ void __launch_bounds__(128, CTAS) cost_kernel(long long* out_cycles, 
   tc_fence_after();
   const uint32_t tmem = *tslot;
   const uint32_t sbase = smem_u32(smem);
-  if (warp == 1) {
+  if (warp >= 1 && warp <= NISS) {   // NISS issuing warps, each with its own accumulators and its own completion barrier
+    bar += warp - 1;
     constexpr uint32_t idesc = make_idesc_f16(128, N, 0);
+    static_assert(NACC * N + 32 <= COLS || NACC == 2, "accumulators must fit");
     constexpr uint32_t D1 = (2 * N + 32 <= COLS) ? N : 0;   // second accumulator tile (or the same one when TMEM is short)
     const uint64_t dA = make_smem_desc(sbase + OFF_A, kLboA, 128);
     const uint64_t dB = make_smem_desc(sbase + OFF_B, 128, 256);
@@ -67,14 +69,14 @@ __global__ void __launch_bounds__(128, CTAS) cost_kernel(long long* out_cycles, 
       for (int r = 0; r < reps; ++r) {
         if (elect_one()) {
           for (int i = 0; i < per_commit; ++i) {
-            const uint32_t d = tmem + (uint32_t)(i & 1) * D1;
+            const uint32_t d = tmem + (uint32_t)(warp - 1) * (NISS > 1 ? 2 * N : 0) + (NACC == 2 ? (uint32_t)(i & 1) * D1 : (uint32_t)(i % NACC) * N);   // NACC independent accumulation chains
             const uint32_t aoff = (uint32_t)((i % 9) / 3 * 62 + (i % 3));   // tap shift in pixels = 16-byte units
-            if (MODE == 0) mma_f16_ss(d, dA + aoff, dB, idesc, i > 1);
-            if (MODE == 1) mma_f16_ts(d, a_tm + (uint32_t)(i % 3) * 8, dB, idesc, i > 1);
+            if (MODE == 0) mma_f16_ss(d, dA + aoff, dB, idesc, i >= NACC);
+            if (MODE == 1) mma_f16_ts(d, a_tm + (uint32_t)(i % 3) * 8, dB, idesc, i >= NACC);
             if (MODE == 2) tmem_cp_128x256b(a_tm + (uint32_t)(i % 3) * 8, dA + aoff);
             if (MODE == 3) {
               if (i % 3 == 0) tmem_cp_128x256b(a_tm + (uint32_t)((i / 3) % 3) * 8, dA + aoff);
-              mma_f16_ts(d, a_tm + (uint32_t)((i / 3) % 3) * 8, dB, idesc, i > 1);
+              mma_f16_ts(d, a_tm + (uint32_t)((i / 3) % 3) * 8, dB, idesc, i >= NACC);
             }
           }
           mma_commit(bar);
@@ -85,7 +87,7 @@ __global__ void __launch_bounds__(128, CTAS) cost_kernel(long long* out_cycles, 
       }
       t1 = clock64();
     }
-    if ((tid & 31) == 0) out_cycles[blockIdx.x] = t1 - t0;
+    if ((tid & 31) == 0 && warp == 1) out_cycles[blockIdx.x] = t1 - t0;
   }
   tc_fence_before();
   __syncthreads();
@@ -143,21 +145,21 @@ __global__ void __launch_bounds__(128, 1) check_kernel(const __half* a_in, const
   if (warp == 0) tmem_dealloc<128>(tmem);
 }
 
-template <int N, int MODE, int CTAS>
+template <int N, int MODE, int CTAS, int NACC = 2, int NISS = 1>
 void run(const char* name, int sms) {
   const int grid = sms * CTAS;
   long long* d = nullptr;
   cudaMalloc(&d, sizeof(long long) * grid);
-  cudaFuncSetAttribute(cost_kernel<N, MODE, CTAS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
+  cudaFuncSetAttribute(cost_kernel<N, MODE, CTAS, NACC, NISS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM);
   const int reps = 200, per = 54;
-  cost_kernel<N, MODE, CTAS><<<grid, 128, SMEM>>>(d, reps, per);
+  cost_kernel<N, MODE, CTAS, NACC, NISS><<<grid, 128, SMEM>>>(d, reps, per);
   cudaError_t e = cudaDeviceSynchronize();
   if (e != cudaSuccess) { printf("%-24s N=%3d: %s\n", name, N, cudaGetErrorString(e)); exit(1); }
   std::vector<long long> h(grid);
   cudaMemcpy(h.data(), d, sizeof(long long) * grid, cudaMemcpyDeviceToHost);
   std::sort(h.begin(), h.end());
-  const double ops = (double)reps * per * CTAS;   // per SM
-  printf("%-24s N=%3d  %d CTA/SM on %3d SMs: %6.1f cycles per op per SM (median CTA; min %.1f max %.1f)\n", name, N, CTAS, sms, h[grid / 2] / ops,
+  const double ops = (double)reps * per * CTAS * NISS;   // per SM
+  printf("%-24s N=%3d  %d CTA/SM x %d issuer warp(s), %d accumulators, %3d SMs: %6.1f cycles per op per SM (median CTA; min %.1f max %.1f)\n", name, N, CTAS, NISS, NACC, sms, h[grid / 2] / ops,
          h[0] / ops, h[grid - 1] / ops);
   cudaFree(d);
 }
@@ -189,24 +191,39 @@ int main() {
       }
     printf("check: SS vs host max err %.3e ; TS (A staged by tcgen05.cp.128x256b) vs SS max diff %.3e\n", err_ref, err_ts);
   }
-  for (int sms : {1, 148}) {
-    run<32, 0, 1>("SS (A,B from smem)", sms);
-    run<64, 0, 1>("SS (A,B from smem)", sms);
-    run<96, 0, 1>("SS (A,B from smem)", sms);
-    run<128, 0, 1>("SS (A,B from smem)", sms);
-    run<256, 0, 1>("SS (A,B from smem)", sms);
-    run<32, 0, 2>("SS (A,B from smem)", sms);
-    run<64, 0, 2>("SS (A,B from smem)", sms);
-    run<96, 0, 2>("SS (A,B from smem)", sms);
-    run<32, 1, 1>("TS (A from TMEM)", sms);
-    run<64, 1, 1>("TS (A from TMEM)", sms);
-    run<128, 1, 1>("TS (A from TMEM)", sms);
-    run<32, 1, 2>("TS (A from TMEM)", sms);
-    run<32, 2, 1>("CP 128x256b only", sms);
-    run<32, 2, 2>("CP 128x256b only", sms);
-    run<32, 3, 1>("TS + 1 CP per 3 MMAs", sms);
-    run<64, 3, 1>("TS + 1 CP per 3 MMAs", sms);
-    run<32, 3, 2>("TS + 1 CP per 3 MMAs", sms);
-  }
+  const int sms = 148;
+  run<32, 0, 1>("SS (A,B from smem)", sms);
+  run<64, 0, 1>("SS (A,B from smem)", sms);
+  run<96, 0, 1>("SS (A,B from smem)", sms);
+  run<128, 0, 1>("SS (A,B from smem)", sms);
+  run<256, 0, 1>("SS (A,B from smem)", sms);
+  run<32, 0, 1, 1>("SS (A,B from smem)", sms);
+  run<32, 0, 1, 3>("SS (A,B from smem)", sms);
+  run<32, 0, 1, 4>("SS (A,B from smem)", sms);
+  run<32, 0, 1, 6>("SS (A,B from smem)", sms);
+  run<48, 0, 1, 1>("SS (A,B from smem)", sms);
+  run<48, 0, 1, 3>("SS (A,B from smem)", sms);
+  run<48, 0, 1, 6>("SS (A,B from smem)", sms);
+  run<64, 0, 1, 1>("SS (A,B from smem)", sms);
+  run<64, 0, 1, 3>("SS (A,B from smem)", sms);
+  run<64, 0, 1, 6>("SS (A,B from smem)", sms);
+  run<32, 0, 1, 2, 2>("SS (A,B from smem)", sms);
+  run<48, 0, 1, 2, 2>("SS (A,B from smem)", sms);
+  run<64, 0, 1, 2, 2>("SS (A,B from smem)", sms);
+  run<96, 0, 1, 2, 2>("SS (A,B from smem)", sms);
+  run<32, 0, 2>("SS (A,B from smem)", sms);
+  run<32, 0, 2, 1>("SS (A,B from smem)", sms);
+  run<32, 0, 2, 3>("SS (A,B from smem)", sms);
+  run<64, 0, 2>("SS (A,B from smem)", sms);
+  run<96, 0, 2>("SS (A,B from smem)", sms);
+  run<32, 1, 1>("TS (A from TMEM)", sms);
+  run<64, 1, 1>("TS (A from TMEM)", sms);
+  run<128, 1, 1>("TS (A from TMEM)", sms);
+  run<32, 1, 2>("TS (A from TMEM)", sms);
+  run<32, 2, 1>("CP 128x256b only", sms);
+  run<32, 2, 2>("CP 128x256b only", sms);
+  run<32, 3, 1>("TS + 1 CP per 3 MMAs", sms);
+  run<64, 3, 1>("TS + 1 CP per 3 MMAs", sms);
+  run<32, 3, 2>("TS + 1 CP per 3 MMAs", sms);
   return 0;
 }
