@@ -42,22 +42,21 @@ float elapsed(Ctx* c, int a, int b) {
   return ms;
 }
 
-int ensure_pinned(Ctx* c, size_t bytes) {
-  if (bytes <= c->pin_cap && c->h_pin) return ORCAI_OK;
-  if (c->h_pin) { ORCAI_CUDA(c, cudaFreeHost(c->h_pin)); c->h_pin = nullptr; c->pin_cap = 0; }
-  ORCAI_CUDA(c, cudaMallocHost(&c->h_pin, bytes));
-  c->pin_cap = bytes;
+struct StatsTail { unsigned long long rank[2]; unsigned int prefix[2]; unsigned int pmax_bits; float db_ref, lo, hi; };
+
+// selected statistics of the resident recording: enqueue the read-back into pinned memory, interpret it after the next
+// stream synchronise (so that a predict call pays one synchronise for statistics, segments and aggregates together)
+int stats_enqueue(Ctx* c) {
+  if (!c->h_small) ORCAI_CUDA(c, cudaMallocHost(&c->h_small, 256));
+  ORCAI_CUDA(c, cudaMemcpyAsync(c->h_small, reinterpret_cast<const unsigned char*>(c->d_sel) + offsetof(SelectState, rank), sizeof(StatsTail),
+                                cudaMemcpyDeviceToHost, c->stream));
   return ORCAI_OK;
 }
 
-int fill_stats(Ctx* c, orcai_spec_stats* stats) {
-  if (!stats) return ORCAI_OK;
-  SelectState* h = static_cast<SelectState*>(nullptr);
-  (void)h;
-  struct Tail { unsigned long long rank[2]; unsigned int prefix[2]; unsigned int pmax_bits; float db_ref, lo, hi; } t;
-  ORCAI_CUDA(c, cudaMemcpyAsync(&t, reinterpret_cast<const unsigned char*>(c->d_sel) + offsetof(SelectState, rank), sizeof t,
-                                cudaMemcpyDeviceToHost, c->stream));
-  ORCAI_CUDA(c, cudaStreamSynchronize(c->stream));
+void stats_finish(Ctx* c, orcai_spec_stats* stats) {
+  if (!stats) return;
+  StatsTail t;
+  memcpy(&t, c->h_small, sizeof t);
   const int nb = c->p.band_hi - c->p.band_lo;
   const unsigned long long n = (unsigned long long)c->T * (unsigned long long)nb;
   stats->n_frames = c->T;
@@ -67,6 +66,13 @@ int fill_stats(Ctx* c, orcai_spec_stats* stats) {
   stats->hi = t.hi;
   stats->rank_lo = (int64_t)nearbyint((double)(n - 1) * c->p.q_lo);
   stats->rank_hi = (int64_t)nearbyint((double)(n - 1) * c->p.q_hi);
+}
+
+int fill_stats(Ctx* c, orcai_spec_stats* stats) {
+  if (!stats) return ORCAI_OK;
+  ORCAI_CHECK(stats_enqueue(c));
+  ORCAI_CUDA(c, cudaStreamSynchronize(c->stream));
+  stats_finish(c, stats);
   return ORCAI_OK;
 }
 
@@ -197,6 +203,7 @@ void orcai_destroy(orcai_ctx* c) {
   if (c->d_preds) cudaFree(c->d_preds);
   if (c->d_post) cudaFree(c->d_post);
   if (c->h_pin) cudaFreeHost(c->h_pin);
+  if (c->h_small) cudaFreeHost(c->h_small);
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
   if (c->stream) cudaStreamDestroy(c->stream);
   cudaGetLastError();
@@ -441,12 +448,14 @@ int orcai_predict_resident(orcai_ctx* c, double threshold, orcai_spec_stats* sta
   ORCAI_CHECK(ensure_preds(c, N));
   ORCAI_CHECK(net_forward(c, c->d_raw, 0, 0, N, c->d_preds));
   ORCAI_CHECK(rec(c, EV_NET));
+  if (stats) ORCAI_CHECK(stats_enqueue(c));
   int rc = launch_postprocess(c, c->d_preds, N, c->T, threshold, agg_out, cnt_out, seg_label, seg_start, seg_stop,
                               seg_capacity, n_segments);
   cudaEventRecord(c->ev[EV_POST], c->stream);
   cudaStreamSynchronize(c->stream);
   if (rc != ORCAI_OK && rc != ORCAI_ERR_CAPACITY) return rc;
-  int rc2 = fill_stats(c, stats);
+  stats_finish(c, stats);
+  const int rc2 = ORCAI_OK;
   c->tm.stft_ms = elapsed(c, EV_H2D, EV_STFT);
   c->tm.select_ms = elapsed(c, EV_STFT, EV_SELECT);
   c->tm.normalise_ms = elapsed(c, EV_SELECT, EV_NORM);

@@ -59,6 +59,7 @@ struct Ctx {
   void* d_post = nullptr; size_t post_cap = 0;
   // pinned staging
   void* h_pin = nullptr; size_t pin_cap = 0;
+  void* h_small = nullptr;           // 256 pinned bytes: statistics read-back
   // timing / accounting of the last call
   orcai_timings tm{};
   cudaEvent_t ev[16] = {};
@@ -93,6 +94,7 @@ struct Ctx {
   } while (0)
 
 int ensure_device_buffer(Ctx* c, void** p, size_t* cap, size_t bytes);
+int ensure_pinned(Ctx* c, size_t bytes);   // c->h_pin: pinned host staging of at least `bytes` (post.cu)
 
 // ---- stage launchers (all asynchronous on c->stream) -------------------------------------------
 // K1: fused window + rFFT512 + |.|^2 + 10log10 + crop ; also the global power max.   (stft.cu)

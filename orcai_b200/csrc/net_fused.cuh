@@ -145,7 +145,7 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 // Bring-up aid (compile with -DORCAI_FUSED_TRACE, run with ORCAI_B200_TRACE=<file>): CTA 0 stamps clock64() at the hand-offs
-// of a few steps into device memory (plain stores, one slot per event); tools/scratch/trace_timeline.py prints the timeline.  Compiled out by default.
+// of a few steps into device memory (plain stores, one slot per event); tools/bringup/trace_timeline.py prints the timeline.  Compiled out by default.
 #ifdef ORCAI_FUSED_TRACE
 static __device__ long long* g_trace = nullptr;   // device memory: [CIN / 10][step - 40][tag] clock64() stamps, plain stores
 __device__ __forceinline__ void trace_event(int kernel, int tag, long long g) {

@@ -33,3 +33,14 @@ t0 = time.perf_counter(); ctx.swap_pcm(); t1 = time.perf_counter(); print("swap 
 # network time while a copy is in flight
 ctx.prefetch_pcm(pinned); r = ctx.predict_pcm(pinned, want_agg=False, resident=True); print("device total_ms with concurrent H2D", ctx.timings()["total_ms"], ctx.timings()["network_ms"])
 torch.cuda.synchronize(); r = ctx.predict_pcm(pinned, want_agg=False, resident=True); print("device total_ms alone", ctx.timings()["total_ms"], ctx.timings()["network_ms"])
+# device time per recording inside the streaming loop
+tot = []
+t0 = time.perf_counter()
+for out in ctx.predict_stream((pinned for _ in range(8)), want_agg=True):
+    tot.append((round(ctx.timings()["total_ms"], 3), round((time.perf_counter() - t0) * 1e3, 3)))
+    t0 = time.perf_counter()
+print("stream: (device total_ms, host ms per iteration)", tot)
+import cProfile, pstats
+pr = cProfile.Profile(); pr.enable()
+for out in ctx.predict_stream((pinned for _ in range(8)), want_agg=True): pass
+pr.disable(); pstats.Stats(pr).sort_stats("cumulative").print_stats(12)

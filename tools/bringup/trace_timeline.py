@@ -2,7 +2,7 @@
 """Print the hand-off timeline recorded by a -DORCAI_FUSED_TRACE build (net_fused.cuh: FB_TRACE).
 
     ORCAI_B200_NVCC_EXTRA=-DORCAI_FUSED_TRACE python -m orcai_b200.build --force
-    ORCAI_B200_TRACE=/tmp/trace.txt python tools/scratch/trace_run.py ; python tools/scratch/trace_timeline.py /tmp/trace.txt
+    ORCAI_B200_TRACE=/tmp/trace.txt python tools/bringup/trace_run.py ; python tools/bringup/trace_timeline.py /tmp/trace.txt
 """
 import sys
 from collections import defaultdict
