@@ -151,6 +151,22 @@ int orcai_predict_pcm(orcai_ctx* ctx, const void* pcm_host, int32_t dtype, int64
  * orcai_load_weights clears it.  The Python layer calibrates on a built-in synthetic recording when weights are loaded. */
 int orcai_calibrate(orcai_ctx* ctx, int64_t max_snippets);
 
+/* ---- one recording split by time across several contexts / GPUs ------------------------------------
+ * The reference computes ONE reference level (ref = np.max over all 257 bins and all frames, spectrogram.py:51-53) and ONE
+ * pair of percentiles (spectrogram.py:70-75) per recording, so chunks of a recording must agree on them: each context
+ * holds a chunk (with halo frames) and the host combines the chunks' partial statistics between these calls
+ * (orcai_b200/timesplit.py): max of the maxima, sum of the radix-select histograms.  Rows are frame indices of the chunk.
+ *   orcai_chunk_spectrogram  STFT -> dB of the uploaded chunk; *max_power_out = max |S|^2 over rows [stat_row0, stat_row1)
+ *   orcai_chunk_select_begin the recording-wide maximum -> reference level (computed on the device, like the one-GPU path)
+ *   orcai_chunk_histogram    pass 0/1/2 of the exact radix select over rows [row0, row1): hist_out[2][2048] counts of the
+ *                            11/11/10-bit digit, restricted to keys that start with prefix[r] (pass 0: one histogram)
+ *   orcai_chunk_select_end   the decided 32-bit keys -> lo / hi; the chunk is then ready for orcai_forward_resident
+ * Results are bit-identical to the one-context path (tests/test_gpu_timesplit.py). */
+int orcai_chunk_spectrogram(orcai_ctx* ctx, int64_t stat_row0, int64_t stat_row1, float* max_power_out);
+int orcai_chunk_select_begin(orcai_ctx* ctx, float max_power);
+int orcai_chunk_histogram(orcai_ctx* ctx, int32_t pass, int64_t row0, int64_t row1, const uint32_t* prefix, uint64_t* hist_out);
+int orcai_chunk_select_end(orcai_ctx* ctx, const uint32_t* keys, orcai_spec_stats* stats);
+
 /* ---- knobs ---------------------------------------------------------------------------------- */
 /* Options: "net_path"  0 = fp32 CUDA-core path (reference grade, library default), 1 = fp16 / 2 = bf16 layer-wise tcgen05
  *                      path, 3 = fp16 fused tcgen05 path (what orcai_b200's Python layer selects unless

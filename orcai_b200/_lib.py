@@ -111,6 +111,10 @@ _SIGNATURES = {
     "orcai_prefetch_pcm": (C.c_int, [_P, _P, C.c_int32, C.c_int64]),
     "orcai_swap_pcm": (C.c_int, [_P]),
     "orcai_debug_read": (C.c_int, [_P, _P, C.c_int64, C.POINTER(C.c_int64)]),
+    "orcai_chunk_spectrogram": (C.c_int, [_P, C.c_int64, C.c_int64, C.POINTER(C.c_float)]),
+    "orcai_chunk_select_begin": (C.c_int, [_P, C.c_float]),
+    "orcai_chunk_histogram": (C.c_int, [_P, C.c_int32, C.c_int64, C.c_int64, _P, _P]),
+    "orcai_chunk_select_end": (C.c_int, [_P, _P, C.POINTER(SpecStats)]),
 }
 
 _lib = None
@@ -322,6 +326,28 @@ class Context:
         out = np.empty((nrows, self.params.n_freq), dtype=np.float32)
         self._check(self.lib.orcai_read_db(self._h, row0, nrows, _ptr(out)))
         return out
+
+    # -- time chunks of one recording (orcai_b200/timesplit.py) -----------------------------------
+    def chunk_spectrogram(self, stat_row0: int, stat_row1: int) -> float:
+        """STFT -> dB of the uploaded chunk; max |S|^2 over the rows [stat_row0, stat_row1) the chunk owns."""
+        m = C.c_float(0.0)
+        self._check(self.lib.orcai_chunk_spectrogram(self._h, int(stat_row0), int(stat_row1), C.byref(m)))
+        return float(m.value)
+
+    def chunk_select_begin(self, max_power: float):
+        self._check(self.lib.orcai_chunk_select_begin(self._h, float(max_power)))
+
+    def chunk_histogram(self, pass_: int, row0: int, row1: int, prefix) -> np.ndarray:
+        pre = np.asarray(prefix, dtype=np.uint32)
+        hist = np.zeros((2, 2048), dtype=np.uint64)
+        self._check(self.lib.orcai_chunk_histogram(self._h, int(pass_), int(row0), int(row1), _ptr(pre), _ptr(hist)))
+        return hist
+
+    def chunk_select_end(self, keys) -> SpecStats:
+        k = np.asarray(keys, dtype=np.uint32)
+        st = SpecStats()
+        self._check(self.lib.orcai_chunk_select_end(self._h, _ptr(k), C.byref(st)))
+        return st
 
     # -- network -------------------------------------------------------------------------------
     def forward_host(self, snippets: np.ndarray) -> np.ndarray:

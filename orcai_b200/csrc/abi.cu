@@ -84,7 +84,7 @@ int spectrogram_stages(Ctx* c, int normalise) {
     ORCAI_CHECK(ensure_device_buffer(c, &p, &c->raw_cap, (size_t)c->T * kRawLd * sizeof(float)));
     c->d_raw = static_cast<float*>(p);
   }
-  ORCAI_CHECK(launch_stft(c, c->d_pcm, c->pcm_dtype, c->n_samples, c->T, c->d_raw));
+  ORCAI_CHECK(launch_stft(c, c->d_pcm, c->pcm_dtype, c->n_samples, c->T, c->d_raw, 0, c->T));
   ORCAI_CHECK(rec(c, EV_STFT));
   ORCAI_CHECK(launch_select(c, c->d_raw, c->T));
   ORCAI_CHECK(rec(c, EV_SELECT));
@@ -464,6 +464,51 @@ int orcai_predict_resident(orcai_ctx* c, double threshold, orcai_spec_stats* sta
   c->tm.post_ms = elapsed(c, EV_NET, EV_POST);
   c->tm.total_ms = elapsed(c, EV_H2D, EV_POST);
   return rc != ORCAI_OK ? rc : rc2;
+}
+
+/* ---- time chunks of ONE recording (orcai_b200/timesplit.py) ---------------------------------------- */
+int orcai_chunk_spectrogram(orcai_ctx* c, int64_t stat_row0, int64_t stat_row1, float* max_power_out) {
+  if (!c || !max_power_out) return ORCAI_ERR_ARG;
+  ORCAI_CUDA(c, cudaSetDevice(c->device));
+  if (!c->d_pcm || c->n_samples < 0) ORCAI_FAIL(c, ORCAI_ERR_STATE, "no recording uploaded (orcai_upload_pcm)");
+  c->T = orcai_num_frames(c->n_samples, c->p.hop);
+  if (stat_row0 < 0 || stat_row1 > c->T || stat_row0 > stat_row1) ORCAI_FAIL(c, ORCAI_ERR_ARG, "statistic rows [%lld, %lld) outside the chunk's %lld frames", (long long)stat_row0, (long long)stat_row1, (long long)c->T);
+  {
+    void* p = c->d_raw;
+    ORCAI_CHECK(ensure_device_buffer(c, &p, &c->raw_cap, (size_t)c->T * kRawLd * sizeof(float)));
+    c->d_raw = static_cast<float*>(p);
+  }
+  c->have_stats = false;
+  ORCAI_CHECK(launch_stft(c, c->d_pcm, c->pcm_dtype, c->n_samples, c->T, c->d_raw, stat_row0, stat_row1));
+  if (!c->h_small) ORCAI_CUDA(c, cudaMallocHost(&c->h_small, 256));
+  ORCAI_CUDA(c, cudaMemcpyAsync(c->h_small, &c->d_sel->pmax_bits, 4, cudaMemcpyDeviceToHost, c->stream));
+  ORCAI_CUDA(c, cudaStreamSynchronize(c->stream));
+  memcpy(max_power_out, c->h_small, 4);
+  return ORCAI_OK;
+}
+
+int orcai_chunk_select_begin(orcai_ctx* c, float max_power) {
+  if (!c || !(max_power >= 0.f)) return ORCAI_ERR_ARG;
+  ORCAI_CUDA(c, cudaSetDevice(c->device));
+  if (c->T <= 0 || !c->d_raw) ORCAI_FAIL(c, ORCAI_ERR_STATE, "no chunk spectrogram resident (orcai_chunk_spectrogram)");
+  return launch_select_begin(c, max_power);
+}
+
+int orcai_chunk_histogram(orcai_ctx* c, int32_t pass, int64_t row0, int64_t row1, const uint32_t* prefix, uint64_t* hist_out) {
+  if (!c || !prefix || !hist_out || pass < 0 || pass > 2) return ORCAI_ERR_ARG;
+  ORCAI_CUDA(c, cudaSetDevice(c->device));
+  if (c->T <= 0 || !c->d_raw) ORCAI_FAIL(c, ORCAI_ERR_STATE, "no chunk spectrogram resident (orcai_chunk_spectrogram)");
+  if (row0 < 0 || row1 > c->T || row0 > row1) ORCAI_FAIL(c, ORCAI_ERR_ARG, "rows [%lld, %lld) outside the chunk's %lld frames", (long long)row0, (long long)row1, (long long)c->T);
+  return launch_select_histogram(c, c->d_raw + (size_t)row0 * kRawLd, row1 - row0, pass, prefix, hist_out);
+}
+
+int orcai_chunk_select_end(orcai_ctx* c, const uint32_t* keys, orcai_spec_stats* stats) {
+  if (!c || !keys) return ORCAI_ERR_ARG;
+  ORCAI_CUDA(c, cudaSetDevice(c->device));
+  if (c->T <= 0 || !c->d_raw) ORCAI_FAIL(c, ORCAI_ERR_STATE, "no chunk spectrogram resident (orcai_chunk_spectrogram)");
+  ORCAI_CHECK(launch_select_end(c, keys));
+  c->have_stats = true;
+  return fill_stats(c, stats);
 }
 
 int orcai_predict_pcm(orcai_ctx* c, const void* pcm_host, int32_t dtype, int64_t n_samples, double threshold,

@@ -99,9 +99,14 @@ int ensure_pinned(Ctx* c, size_t bytes);   // c->h_pin: pinned host staging of a
 // ---- stage launchers (all asynchronous on c->stream) -------------------------------------------
 // K1: fused window + rFFT512 + |.|^2 + 10log10 + crop ; also the global power max.   (stft.cu)
 int stft_upload_tables(Ctx* c);
-int launch_stft(Ctx* c, const void* d_pcm, int dtype, int64_t n_samples, int64_t T, float* d_raw);
+// stat rows: the frames that count towards the global power maximum (all of them, or the rows a time chunk owns)
+int launch_stft(Ctx* c, const void* d_pcm, int dtype, int64_t n_samples, int64_t T, float* d_raw, int64_t stat_row0, int64_t stat_row1);
 // exact percentiles (radix select on shifted/floored dB) and K2 normalise.          (select.cu)
 int launch_select(Ctx* c, const float* d_raw, int64_t T);
+// time chunks of ONE recording (orcai_chunk_*): the select's passes driven from the host, which sums the chunks' histograms
+int launch_select_begin(Ctx* c, float max_power);                                              // global max -> db_ref
+int launch_select_histogram(Ctx* c, const float* d_raw_rows, int64_t n_rows, int pass, const uint32_t prefix[2], uint64_t* h_hist);
+int launch_select_end(Ctx* c, const uint32_t key[2]);                                          // decided keys -> lo, hi
 int launch_normalise(Ctx* c, const float* d_raw, int64_t T, float* d_spec);
 int launch_read_db(Ctx* c, const float* d_raw, int64_t T, float* d_out);             // shifted + floored dB, compact
 // network forward                                                                    (net.cu)

@@ -9,6 +9,7 @@
 // order-preserving integer image of the float32 values v; both ranks are resolved in the same
 // passes.  Passes 2 and 3 only count elements that match the already-decided prefix, so they are
 // plain streaming reads.
+#include <cstring>
 #include "common.h"
 
 namespace orcai {
@@ -202,6 +203,54 @@ int launch_select(Ctx* c, const float* d_raw, int64_t T) {
   select_hist_kernel<2><<<grid, 256, 0, c->stream>>>(d_raw, T, kRawLd, nb, c->d_sel);
   select_scan_kernel<2><<<1, 1024, 0, c->stream>>>(c->d_sel);
   c->launches += 7;
+  ORCAI_CUDA(c, cudaGetLastError());
+  return ORCAI_OK;
+}
+
+namespace {
+__global__ void select_set_prefix_kernel(SelectState* st, unsigned int p0, unsigned int p1) {
+  st->prefix[0] = p0;
+  st->prefix[1] = p1;
+}
+__global__ void select_set_keys_kernel(SelectState* st, unsigned int k0, unsigned int k1) {
+  st->prefix[0] = k0;
+  st->prefix[1] = k1;
+  st->lo = key2f(k0);
+  st->hi = key2f(k1);
+}
+__global__ void select_set_pmax_kernel(SelectState* st, unsigned int bits) { st->pmax_bits = bits; }
+}  // namespace
+
+int launch_select_begin(Ctx* c, float max_power) {
+  unsigned int bits;
+  memcpy(&bits, &max_power, 4);
+  select_set_pmax_kernel<<<1, 1, 0, c->stream>>>(c->d_sel, bits);
+  select_init_kernel<<<8, 512, 0, c->stream>>>(c->d_sel, 0ull, 0ull);   // db_ref from the global maximum; clears the histograms
+  c->launches += 2;
+  ORCAI_CUDA(c, cudaGetLastError());
+  return ORCAI_OK;
+}
+
+int launch_select_histogram(Ctx* c, const float* d_raw_rows, int64_t n_rows, int pass, const uint32_t prefix[2], uint64_t* h_hist) {
+  const int nb = c->p.band_hi - c->p.band_lo;
+  const int grid = c->sm_count * 8;
+  select_set_prefix_kernel<<<1, 1, 0, c->stream>>>(c->d_sel, prefix[0], prefix[1]);
+  if (n_rows > 0) {
+    if (pass == 0) select_hist_kernel<0><<<grid, 256, 0, c->stream>>>(d_raw_rows, n_rows, kRawLd, nb, c->d_sel);
+    else if (pass == 1) select_hist_kernel<1><<<grid, 256, 0, c->stream>>>(d_raw_rows, n_rows, kRawLd, nb, c->d_sel);
+    else select_hist_kernel<2><<<grid, 256, 0, c->stream>>>(d_raw_rows, n_rows, kRawLd, nb, c->d_sel);
+  }
+  c->launches += 2;
+  ORCAI_CUDA(c, cudaGetLastError());
+  ORCAI_CUDA(c, cudaMemcpyAsync(h_hist, &c->d_sel->hist[0][0], sizeof(unsigned long long) * 2 * 2048, cudaMemcpyDeviceToHost, c->stream));
+  ORCAI_CUDA(c, cudaMemsetAsync(&c->d_sel->hist[0][0], 0, sizeof(unsigned long long) * 2 * 2048, c->stream));
+  ORCAI_CUDA(c, cudaStreamSynchronize(c->stream));
+  return ORCAI_OK;
+}
+
+int launch_select_end(Ctx* c, const uint32_t key[2]) {
+  select_set_keys_kernel<<<1, 1, 0, c->stream>>>(c->d_sel, key[0], key[1]);
+  c->launches++;
   ORCAI_CUDA(c, cudaGetLastError());
   return ORCAI_OK;
 }

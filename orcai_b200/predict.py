@@ -187,6 +187,24 @@ def compute_labels(
 # ---------------------------------------------------------------------------------------------
 # predict_wav (predict.py:367-471)
 # ---------------------------------------------------------------------------------------------
+def _time_split_contexts(model, ctx):
+    """Contexts (one per device of ORCAI_B200_DEVICES) that annotate ONE recording together, or None for the one-device path.
+
+    Replicas of the model on the other devices are created once and kept on the model object.
+    """
+    devs = _visible_devices()
+    if len(devs) < 2 or not hasattr(model, "weights"):
+        return None
+    from orcai_b200.model import OrcaiModel
+
+    cache = model.__dict__.setdefault("_device_replicas", {ctx.device: model})
+    for d in devs:
+        if d not in cache:
+            cache[d] = OrcaiModel(model.orcai_parameter, model.shape, model.weights, device=d, precision=model.precision)
+    ordered = [ctx.device] + [d for d in devs if d != ctx.device]
+    return [cache[d].ctx for d in ordered]
+
+
 def predict_wav(
     recording_path: Path | str,
     channel: int,
@@ -197,10 +215,13 @@ def predict_wav(
     msgr: Messenger = Messenger(verbosity=0),
     progressbar: tqdm = None,
     _resident_samples=None,
+    _time_split: bool = False,
 ):
     """Predicts calls in a single wav file -> (predicted_labels DataFrame, aggregated_predictions, delta_t).
 
     ``_resident_samples`` (table mode): the recording has already been read and uploaded by the prefetcher.
+    ``_time_split`` (single-file mode of ``predict``): with several devices in ORCAI_B200_DEVICES the recording is cut into
+    time chunks, one per device (``orcai_b200/timesplit.py``); the result is bit-identical to the one-device path.
     """
     recording_path = Path(recording_path)
     if progressbar:
@@ -221,7 +242,15 @@ def predict_wav(
         progressbar.set_description(f"{recording_path.stem} - Predicting annotations")
         progressbar.refresh()
     try:
-        stats, agg, _cnt, lab, sta, sto = ctx.predict_pcm(samples, threshold=0.5, want_agg=True, resident=_resident_samples is not None)
+        replicas = _time_split_contexts(model, ctx) if (_time_split and _resident_samples is None) else None
+        if replicas:
+            # ONE recording on several GPUs: time chunks with halos, one host-side exchange of statistics (timesplit.py)
+            from orcai_b200.timesplit import predict_pcm_timesplit
+
+            msgr.info(f"splitting the recording by time across {len(replicas)} devices")
+            stats, agg, _cnt, lab, sta, sto = predict_pcm_timesplit(replicas, samples, threshold=0.5, want_agg=True)
+        else:
+            stats, agg, _cnt, lab, sta, sto = ctx.predict_pcm(samples, threshold=0.5, want_agg=True, resident=_resident_samples is not None)
     except OrcaiError as e:
         if e.code == ORCAI_ERR_TOO_SHORT:
             raise ValueError(f"{recording_path.stem}: {e.message}") from e
@@ -311,6 +340,7 @@ def _predict_and_save(
     msgr: Messenger = Messenger(verbosity=0),
     progressbar: tqdm = None,
     _resident_samples=None,
+    _time_split: bool = False,
 ) -> None:
     recording_path = Path(recording_path)
     if output_path is not None:
@@ -335,6 +365,7 @@ def _predict_and_save(
         msgr=msgr,
         progressbar=progressbar,
         _resident_samples=_resident_samples,
+        _time_split=_time_split,
     )
     if call_duration_limits is not None:
         predicted_labels = filter_predictions(predicted_labels, delta_t=delta_t, call_duration_limits=call_duration_limits, label_suffix=label_suffix, msgr=msgr)
@@ -391,6 +422,7 @@ def predict(
             label_suffix=label_suffix,
             msgr=msgr,
             progressbar=None,
+            _time_split=True,
         )
     elif recording_path.suffix == ".csv":
         recording_table = pd.read_csv(recording_path)
