@@ -30,6 +30,7 @@ def main() -> int:
     ap.add_argument("--hours", type=float, default=4.0)
     ap.add_argument("--devices", default="0,1")
     ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--tile-hours", type=float, default=0.0, help="generate this many hours and repeat them (a 24-h recording takes minutes to synthesise)")
     a = ap.parse_args()
     devs = [int(x) for x in a.devices.split(",")]
     P, S = runtime.bundled_parameters()
@@ -41,7 +42,13 @@ def main() -> int:
         c.set_option("net_path", 3)
         c.calibrate()
         ctxs.append(c)
-    pcm = torch.from_numpy(bench.make_recording(a.hours, 20251018)).pin_memory().numpy()
+    if a.tile_hours > 0:
+        unit = bench.make_recording(a.tile_hours, 20251018)
+        raw = np.tile(unit, int(np.ceil(a.hours / a.tile_hours)))[: int(a.hours * 3600 * 48000)]
+    else:
+        raw = bench.make_recording(a.hours, 20251018)
+    pcm = torch.from_numpy(raw).pin_memory().numpy()
+    del raw
 
     def timed(fn):
         fn()
@@ -59,7 +66,7 @@ def main() -> int:
     same = all(np.array_equal(x, y) for x, y in zip(one[1:], split[1:])) and (one[0].lo, one[0].hi, one[0].db_ref) == (split[0].lo, split[0].hi, split[0].db_ref)
     chunks = plan_chunks(pcm.size, len(devs))
     print(json.dumps({
-        "workload": f"orcai predict on ONE synthetic {a.hours:g}-hour recording, host buffers -> segments (upload inside the timed region)",
+        "workload": f"orcai predict on ONE synthetic {a.hours:g}-hour recording" + (f" ({a.tile_hours:g} h of audio repeated)" if a.tile_hours > 0 else "") + ", host buffers -> segments (upload inside the timed region)",
         "devices": devs, "chunks": [{"snippets": c.n_snippets, "samples": c.sample1 - c.sample0} for c in chunks],
         "one_gpu": {"seconds": t_one, "h_audio_per_s": a.hours / t_one},
         "time_split": {"seconds": t_split, "h_audio_per_s": a.hours / t_split},
