@@ -110,6 +110,38 @@ def test_time_split_is_bit_identical_to_one_context(ctx, params, n_chunks, net_p
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("seconds", [3.93, 7.9, 9.87, 23.456, 44.4])
+def test_time_split_ragged_lengths_and_more_chunks_than_snippets(ctx, params, seconds):
+    """Recordings of 1 .. 22 snippets, lengths that are not multiples of the hop, float32 samples, up to 4 chunks."""
+    from orcai_b200._lib import Context, OrcaiError
+    from orcai_b200.synth import pcm16_to_float, synth_pcm16
+    from orcai_b200.timesplit import predict_pcm_timesplit
+    from orcai_b200.weights import synthetic_weights
+
+    P, S = params
+    pcm = synth_pcm16(seconds, seed=int(seconds * 1000), calls_per_minute=60.0)[: int(seconds * 48000) - 77]
+    W = synthetic_weights(P, S, seed=1234)
+    extra = [Context(P, S, device=0) for _ in range(3)]
+    try:
+        for c in extra:
+            c.load_weights(W)
+        T = 1 + pcm.size // 256
+        if T < 736:
+            with pytest.raises(ValueError):
+                predict_pcm_timesplit([ctx] + extra, pcm)
+            return
+        for samples in (pcm, pcm16_to_float(pcm)):
+            one = ctx.predict_pcm(samples)
+            split = predict_pcm_timesplit([ctx] + extra, samples)
+            assert (split[0].lo, split[0].hi, split[0].db_ref, split[0].n_frames) == (one[0].lo, one[0].hi, one[0].db_ref, one[0].n_frames)
+            for a, b in zip(split[1:], one[1:]):
+                np.testing.assert_array_equal(a, b)
+    finally:
+        for c in extra:
+            c.close()
+
+
+@pytest.mark.gpu
 def test_predict_single_wav_on_two_devices_writes_the_same_file(tmp_path, params, monkeypatch):
     """`orcai predict one.wav` with ORCAI_B200_DEVICES=0,1: time chunks on two GPUs, same label file as on one."""
     import torch
