@@ -50,8 +50,16 @@ __host__ __device__ constexpr int pow2cols(int c) { return c <= 32 ? 32 : c <= 6
 //        SM reach the shared-memory bound (41 / 47 / 52 cycles at N = 32 / 48 / 64; tools/microbench/mma_cost.cu).  With
 //        ISS_ = 2 the first convolution (+ residual 1x1) and the second convolution are issued by separate warps
 //        (splitting the TILES of each convolution between two warps instead measured 7-10 % slower).
-template <int CIN_, int COUT_, int CPOOL_, int S_, bool RELU_OUT_, int CTAS_, int NEW_, bool CONV0_ = false, int ISS_ = 1>
+// XBUF_: X / R operand buffers.  With one buffer the load of step g+1 can only start when the first convolution of step g has
+//        completed, and the first convolution of step g+1 only when it has landed 2-4 k cycles later
+//        (profiles/r01l_fused_block_handoff_timeline.txt).  Two buffers (where the shared memory allows: block 2) take the
+//        load off that cycle: 1.18 -> 1.12 ms per 10 min of audio.  (Also tried: issuing the residual MMA after the tiles so
+//        that the first convolution does not wait for the pooling epilogue of step g-2 - it then competes with the second
+//        convolution of step g, which is on the critical path: 1.12 -> 1.25 ms.)
+template <int CIN_, int COUT_, int CPOOL_, int S_, bool RELU_OUT_, int CTAS_, int NEW_, bool CONV0_ = false, int ISS_ = 1, int XBUF_ = 1>
 struct FB {
+  static constexpr int XBUF = XBUF_;
+  static_assert(XBUF_ == 1 || (XBUF_ == 2 && ISS_ == 2 && !CONV0_), "two X buffers: two-issuer TMA configuration only");
   static constexpr int CIN = CIN_, COUT = COUT_, CP = CPOOL_, S = S_, CTAS = CTAS_, NEW = NEW_, ISS = ISS_;
   static constexpr bool RELU_OUT = RELU_OUT_, CONV0 = CONV0_;
   static constexpr int NPROD = CONV0 ? 2 : 1;                       // producer warps: one TMA warp, or two entry-convolution warps
@@ -68,7 +76,9 @@ struct FB {
   static constexpr int WP = 2 * CP + 4;
   static constexpr int N1 = (S * WP - 2 + 127) / 128, N2 = (S * WP - 4 + 127) / 128;
   static constexpr int P1_0 = 2 * WP + 1, P2_0 = WP + 2;
-  static constexpr int XPIX = round8(imax((S + 2) * WP, P1_0 + 128 * N1 + 1));
+  // one buffer: padded so that the last tile's over-read stays inside it; two buffers: packed (the over-read of rows that
+  // feed no consumed accumulator row runs into the next plane / buffer, which is finite shared memory of this CTA)
+  static constexpr int XPIX = XBUF_ == 2 ? round8((S + 2) * WP) : round8(imax((S + 2) * WP, P1_0 + 128 * N1 + 1));
   static constexpr int S1PIX = round8(imax((S + 2) * WP, P2_0 + 128 * N2 + WP + 1));
   // S2 is stored de-interleaved: even image columns in the first half of a chunk plane, odd columns in the second half
   // (offset by 64 B modulo 128), so that the pooling epilogue's lanes (one pooled column each) read consecutive 16-byte pieces
@@ -88,15 +98,16 @@ struct FB {
   static constexpr uint32_t W_BYTES = OFF_ONES + 256;
   static constexpr uint32_t OFF_R = W_BYTES;
   static constexpr uint32_t OFF_X = OFF_R + XCH * LBO_R;
-  static constexpr uint32_t OFF_S1 = OFF_X + XCH * LBO_X;
+  static constexpr uint32_t XR_BYTES = XCH * LBO_R + XCH * LBO_X;        // one R + X buffer; buffer b sits b * XR_BYTES further
+  static constexpr uint32_t OFF_S1 = OFF_X + XCH * LBO_X + (XBUF - 1) * XR_BYTES;
   static constexpr uint32_t OFF_S2 = OFF_S1 + MCH * LBO_S1;
   // entry-convolution input: two (S+5) x SPW fp16 tiles of the normalised spectrogram (rows a-1 .. a+S+3, columns cb-1 ..)
   static constexpr int SPW = 64, SPH = S + 5;
   static constexpr uint32_t SPEC_BYTES = CONV0 ? SPH * SPW * 2 : 0;
   static constexpr uint32_t OFF_SPEC = OFF_S2 + NG * LBO_S2;
   static constexpr uint32_t OFF_BAR = OFF_SPEC + 2 * ((SPEC_BYTES + 127) / 128 * 128);
-  // barriers: bar1[N1] bar2[N2] barR[2] s1_full[N1] pool_done x_full spec_full[2]
-  static constexpr int B_1 = 0, B_2 = N1, B_R = N1 + N2, B_S1 = N1 + N2 + 2, B_P = 2 * N1 + N2 + 2, B_X = B_P + 1, B_SP = B_X + 1, NBAR = B_SP + 2;
+  // barriers: bar1[N1] bar2[N2] barR[2] s1_full[N1] pool_done x_full[2] x_free[2] spec_full[2]
+  static constexpr int B_1 = 0, B_2 = N1, B_R = N1 + N2, B_S1 = N1 + N2 + 2, B_P = 2 * N1 + N2 + 2, B_X = B_P + 1, B_XF = B_X + 2, B_SP = B_XF + 2, NBAR = B_SP + 2;
   static constexpr uint32_t SMEM = OFF_BAR + NBAR * 8 + 16;
   static constexpr uint32_t TX_BYTES = XG * ((S + 2) * WP + (S / 2) * CP) * 16;   // bytes one step's TMA loads deliver
   static constexpr int COL_R = 0, COL_1 = 2 * NP, COL_2 = 2 * NP + N1 * NP;
@@ -218,7 +229,10 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   if (tid == 0) {
     for (int i = 0; i < G::B_S1; ++i) mbar_init(&bars[i], 1);                 // tcgen05.commit arrivals
     for (int i = G::B_S1; i < G::B_X; ++i) mbar_init(&bars[i], G::NEW);        // one arrival per worker warp (s1_full, pool_done)
-    mbar_init(&bars[G::B_X], G::CONV0 ? G::NPROD : 1);                         // TMA arrive.expect_tx, or one arrival per entry-conv warp
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars[G::B_X + i], G::CONV0 ? G::NPROD : 1);                   // TMA arrive.expect_tx, or one arrival per entry-conv warp
+      mbar_init(&bars[G::B_XF + i], 1);                                        // tcgen05.commit: the buffer's first convolution is done
+    }
     mbar_init(&bars[G::B_SP], 1); mbar_init(&bars[G::B_SP + 1], 1);            // spectrogram tiles of the entry convolution
     fence_mbar_init();
   }
@@ -329,16 +343,21 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       const int wo0 = strip * G::CP, cb = 2 * wo0 - 2;
       for (int step = 0; step < n_steps; ++step, ++g) {
         const int a = step * G::S - 2;
-        // X and R are free once the previous step's first convolution (and residual MMA) has completed
-        if (g > 0) mbar_wait(&bars[G::B_1 + G::N1 - 1], (uint32_t)((g - 1) & 1));
+        // X and R are free once the first convolution (and residual MMA) of the step that used the buffer has completed
+        const int xb = G::XBUF == 2 ? (int)(g & 1) : 0;
+        if (G::XBUF == 1) {
+          if (g > 0) mbar_wait(&bars[G::B_1 + G::N1 - 1], (uint32_t)((g - 1) & 1));
+        } else if (g >= 2) {
+          mbar_wait(&bars[G::B_XF + xb], (uint32_t)(((g >> 1) - 1) & 1));
+        }
         FB_TRACE(5, g);
         if (elect_one()) {
-          mbar_arrive_expect_tx(&bars[G::B_X], G::TX_BYTES);
+          mbar_arrive_expect_tx(&bars[G::B_X + xb], G::TX_BYTES);
 #pragma unroll
           for (int c = 0; c < G::XG; ++c) {
-            tma_load_5d(sbase + G::OFF_X + c * G::LBO_X, &tmX, &bars[G::B_X], 0, c, cb, a + 1, (int)b);
+            tma_load_5d(sbase + G::OFF_X + xb * G::XR_BYTES + c * G::LBO_X, &tmX, &bars[G::B_X + xb], 0, c, cb, a + 1, (int)b);
             // residual input pixels (2*ho, 2*wo): coordinates in the even-position tensor, or in the full tensor read with stride 2
-            tma_load_5d(sbase + G::OFF_R + c * G::LBO_R, &tmR, &bars[G::B_X], 0, c, wo0 * r_step, (a >> 1) * r_step, (int)b);
+            tma_load_5d(sbase + G::OFF_R + xb * G::XR_BYTES + c * G::LBO_R, &tmR, &bars[G::B_X + xb], 0, c, wo0 * r_step, (a >> 1) * r_step, (int)b);
           }
         }
         __syncwarp();
@@ -425,15 +444,17 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         // workers have drained the accumulator tile it is about to overwrite (s1_full[t] of step g-1).
         for (long long g = 0; g < total_steps; ++g) {
           if (g >= 2) mbar_wait(&bars[G::B_P], (uint32_t)(g & 1));   // pooling of step g-2 has read the residual buffer step g reuses
-          mbar_wait(&bars[G::B_X], (uint32_t)(g & 1));
+          const int xb = G::XBUF == 2 ? (int)(g & 1) : 0;
+          mbar_wait(&bars[G::B_X + xb], (uint32_t)((G::XBUF == 2 ? (g >> 1) : g) & 1));
           tc_fence_after();
           FB_TRACE(1, g);
+          const uint64_t dXb = dX + ((xb * G::XR_BYTES) >> 4), dRb = dR + ((xb * G::XR_BYTES) >> 4);
           if (elect_one()) {
             const uint32_t colr = tmem + G::COL_R + (uint32_t)(g & 1) * G::NP;
             mma_f16_ss(colr, dOnes, dBR, idesc, 0);
 #pragma unroll
             for (int ks = 0; ks < G::KP1 / 16; ++ks)
-              mma_f16_ss(colr, dR + ((2 * ks * G::LBO_R) >> 4), dWR + ((2 * ks * 128) >> 4), idesc, 1);
+              mma_f16_ss(colr, dRb + ((2 * ks * G::LBO_R) >> 4), dWR + ((2 * ks * 128) >> 4), idesc, 1);
             mma_commit(&bars[G::B_R + (int)(g & 1)]);
           }
           __syncwarp();
@@ -450,10 +471,11 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                 const uint32_t aoff = (uint32_t)(G::P1_0 + 128 * t - 2 * G::WP - 1 + (tap / 3) * G::WP + (tap % 3));   // pixels = 16-byte units
 #pragma unroll
                 for (int ks = 0; ks < G::KP1 / 16; ++ks)
-                  mma_f16_ss(tmem + G::COL_1 + t * G::NP, dX + aoff + ((2 * ks * G::LBO_X) >> 4),
+                  mma_f16_ss(tmem + G::COL_1 + t * G::NP, dXb + aoff + ((2 * ks * G::LBO_X) >> 4),
                              dW1 + ((tap * G::TAP_W1 + 2 * ks * 128) >> 4), idesc, 1);
               }
               mma_commit(&bars[G::B_1 + t]);
+              if (G::XBUF == 2 && t == G::N1 - 1) mma_commit(&bars[G::B_XF + xb]);   // this step's X / R buffer may be reloaded
             }
             __syncwarp();
           }

@@ -618,7 +618,7 @@ int forward_tc(Ctx* c, const float* d_in, int input_mode, int64_t first, int64_t
 // ------------------------------------------------------------------------------------------------
 using FB1 = fused::FB<16, 30, 29, 6, true, 2, 8>;   // two CTAs per SM already give the tensor pipe two streams (a second issuer warp: 1.91 -> 2.01 ms per 10 min)
 // blocks 2-4 run one CTA per SM: two issuer warps, or the single MMA stream would cost ~59 cycles per MMA instead of 47-52
-using FB2 = fused::FB<30, 40, 43, 4, true, 1, 16, false, 2>;
+using FB2 = fused::FB<30, 40, 43, 4, true, 1, 16, false, 2, 2>;   // the only block whose shared memory has room for a second X buffer
 using FB3 = fused::FB<40, 50, 22, 4, true, 1, 16, false, 2>;
 using FB4 = fused::FB<50, 60, 11, 4, false, 1, 16, false, 2>;
 using FB1C = fused::FB<16, 30, 29, 6, true, 2, 8, true>;   // block 1 with the entry convolution fused in (conv0_path 2)
