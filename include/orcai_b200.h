@@ -175,6 +175,8 @@ int orcai_chunk_select_end(orcai_ctx* ctx, const uint32_t* keys, orcai_spec_stat
  *          "tail_path" (net_path 3) 1 = tensor-core LSTM/dense tail (default), 0 = fp32 CUDA-core tail;
  *          "conv0_path" (net_path 3) 1 = tensor-core entry convolution (default), 0 = fp32 CUDA-core entry convolution,
  *          2 = entry convolution fused into the first residual block's kernel (measured slower, kept as an option);
+ *          "block1_path" (net_path 3) 0 = one MMA per tap (default), 1 = N-widened MMAs: the three dx taps as column
+ *          blocks of one MMA, combined by warp shuffles in the epilogue (correct, measured slower: epilogue-bound);
  *          "stft_f64"  1 = float64 FFT (parity grade, default), 0 = float32 FFT (fast);
  *          "chunk"     snippets per network launch sequence;
  *          "debug_stop" stop the forward after a stage (see orcai_debug_read), -1 = off. */

@@ -494,6 +494,12 @@ int net_set_tail_path(Ctx* c, int path) {
   return ORCAI_OK;
 }
 
+int net_set_block1_path(Ctx* c, int path) {
+  if (path < 0 || path > 1) ORCAI_FAIL(c, ORCAI_ERR_ARG, "block1_path must be 0 (one MMA per tap) or 1 (N-widened MMAs)");
+  c->net->block1_path = path;
+  return ORCAI_OK;
+}
+
 int net_set_conv0_path(Ctx* c, int path) {
   if (path < 0 || path > 2) ORCAI_FAIL(c, ORCAI_ERR_ARG, "conv0_path must be 0 (fp32 CUDA cores), 1 (tensor cores) or 2 (fused into block 1)");
   c->net->conv0_path = path;

@@ -69,6 +69,8 @@ struct NetWeights {
   float* tc_bih[2] = {};         // projection biases with the weight-rounding correction folded in
   float* tc_d1_b = nullptr;
   void* conv0_mma_w = nullptr;   // banded B operand of the tensor-core entry convolution (conv0_mma.cuh)
+  int block1_path = 0;           // fused path, block 1: 0 = one MMA per tap (net_fused.cuh), 1 = N-widened MMAs (net_fused_w.cuh)
+  void* fb_w1_wide = nullptr;    // operands of the N-widened block 1
   int conv0_path = 1;            // fused path: 1 = tensor-core pixel-group convolution, 0 = fp32 CUDA-core convolution
   // tensor-core recurrent tail (net_lstm_tc.cu)
   bool tail_tc_ready = false;

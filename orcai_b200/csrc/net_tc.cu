@@ -315,6 +315,7 @@ pool_res_tc_kernel(const H* __restrict__ t4, const H* __restrict__ prev, H* __re
 __constant__ float c_conv0[9 * 16 + 16];   // [tap][16] (BatchNorm folded), then bias[16]
 
 #include "net_fused.cuh"
+#include "net_fused_w.cuh"
 #include "conv0_mma.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -621,6 +622,7 @@ using FB1 = fused::FB<16, 30, 29, 6, true, 2, 8>;   // two CTAs per SM already g
 using FB2 = fused::FB<30, 40, 43, 4, true, 1, 16, false, 2, 2>;   // the only block whose shared memory has room for a second X buffer
 using FB3 = fused::FB<40, 50, 22, 4, true, 1, 16, false, 2>;
 using FB4 = fused::FB<50, 60, 11, 4, false, 1, 16, false, 2>;
+using FB1W = fused::FBW<16, 30, 29, 6, true, 2, 8>;          // block 1, N-widened MMAs (block1_path 1)
 using FB1C = fused::FB<16, 30, 29, 6, true, 2, 8, true>;   // block 1 with the entry convolution fused in (conv0_path 2)
 static_assert(FB1C::W_BYTES == FB1::W_BYTES && FB1C::OFF_SPEC % 128 == 0, "FB1C shares FB1's weight pack; TMA destinations are 128-byte aligned");
 
@@ -682,6 +684,63 @@ int build_fused_block(Ctx* c, int blk) {
   ORCAI_CUDA(c, cudaMemcpy(p, w.data(), G::W_BYTES, cudaMemcpyHostToDevice));
   nw->fb_w[blk] = p;
   ORCAI_CUDA(c, cudaFuncSetAttribute(fused::fused_block_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
+  return ORCAI_OK;
+}
+
+// operands of the N-widened block kernel (net_fused_w.cuh): per dy one B matrix whose rows are (dx, n)
+template <class G>
+int build_fused_block_w(Ctx* c, int blk, void** out) {
+  NetWeights* nw = c->net;
+  const NetWeights::HostSep& s1 = nw->h_sep1[blk];
+  const NetWeights::HostSep& s2 = nw->h_sep2[blk];
+  if (s1.ci != G::CIN || s1.co != G::COUT || s2.ci != G::COUT || s2.co != G::COUT)
+    ORCAI_FAIL(c, ORCAI_ERR_ARG, "fused block %d: kernel geometry does not match the loaded weights", blk + 1);
+  std::vector<__half> w(G::W_BYTES / 2, __float2half_rn(0.f));
+  auto at = [](uint32_t off, uint32_t sbo, int n, int k) { return (off + (uint32_t)(n / 8) * sbo + (uint32_t)(k / 8) * 128 + (n % 8) * 16 + (k % 8) * 2) / 2; };
+  const Calib& cal = nw->calib;
+  std::vector<double> d1(G::COUT, 0.0), d2(G::COUT, 0.0), dr(G::COUT, 0.0);
+  auto put = [&](size_t idx, double v, double mu, double* acc) {
+    const __half q = __float2half_rn((float)v);
+    w[idx] = q;
+    *acc += ((double)__half2float(q) - v) * mu;
+  };
+  for (int t = 0; t < 9; ++t) {
+    const int dy = t / 3, dx = t % 3;
+    for (int k = 0; k < G::CIN; ++k)
+      for (int n = 0; n < G::COUT; ++n)
+        put(at(G::OFF_W1 + dy * G::DY_W1, G::SBO_W1, dx * G::NP + n, k), (double)(s1.dw[(size_t)t * G::CIN + k] * s1.pw[(size_t)k * G::COUT + n]),
+            cal.valid ? cal.in_relu[blk][k] : 0.0, &d1[n]);
+    for (int k = 0; k < G::COUT; ++k)
+      for (int n = 0; n < G::COUT; ++n)
+        put(at(G::OFF_W2 + dy * G::DY_W2, G::SBO_W2, dx * G::NP + n, k), (double)(s2.dw[(size_t)t * G::COUT + k] * s2.pw[(size_t)k * G::COUT + n]),
+            cal.valid ? cal.s1[blk][k] : 0.0, &d2[n]);
+  }
+  const std::vector<float>& rw = nw->h_res_w[blk];
+  for (int k = 0; k < G::CIN; ++k)
+    for (int n = 0; n < G::COUT; ++n) put(at(G::OFF_WR, G::SBO_W1, n, k), (double)rw[(size_t)k * G::COUT + n], cal.valid ? cal.in_even[blk][k] : 0.0, &dr[n]);
+  // bias rows [hi, lo] (k = 0, 1): the convolutions' sit in the centre column block (dx = 1) only
+  auto put_bias = [&](uint32_t off, int n0, double bv) {
+    const float b = (float)bv;
+    const __half hi = __float2half_rn(b);
+    const __half lo = __float2half_rn(b - __half2float(hi));
+    w[(off + (uint32_t)(n0 / 8) * 128 + (n0 % 8) * 16) / 2] = hi;
+    w[(off + (uint32_t)(n0 / 8) * 128 + (n0 % 8) * 16) / 2 + 1] = lo;
+  };
+  for (int n = 0; n < G::COUT; ++n) {
+    put_bias(G::OFF_WB1, G::NP + n, (double)s1.b[n] - d1[n]);
+    put_bias(G::OFF_WB2, G::NP + n, (double)s2.b[n] - d2[n]);
+    put_bias(G::OFF_WBR, n, (double)nw->h_res_b[blk][n] - dr[n]);
+  }
+  for (int r = 0; r < 8; ++r) {
+    w[(G::OFF_ONES + r * 16) / 2] = __float2half_rn(1.f);
+    w[(G::OFF_ONES + r * 16) / 2 + 1] = __float2half_rn(1.f);
+  }
+  void* p = nullptr;
+  ORCAI_CUDA(c, cudaMalloc(&p, G::W_BYTES));
+  nw->allocs.push_back(p);
+  ORCAI_CUDA(c, cudaMemcpy(p, w.data(), G::W_BYTES, cudaMemcpyHostToDevice));
+  *out = p;
+  ORCAI_CUDA(c, cudaFuncSetAttribute(fused::fused_block_w_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
   return ORCAI_OK;
 }
 
@@ -757,6 +816,7 @@ int prepare_fused(Ctx* c) {
   ORCAI_CHECK(build_conv0_mma(c));
   ORCAI_CHECK(build_fused_block<FB1>(c, 0));
   ORCAI_CUDA(c, cudaFuncSetAttribute(fused::fused_block_kernel<FB1C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FB1C::SMEM));
+  ORCAI_CHECK(build_fused_block_w<FB1W>(c, 0, &nw->fb_w1_wide));
   ORCAI_CHECK(build_fused_block<FB2>(c, 1));
   ORCAI_CHECK(build_fused_block<FB3>(c, 2));
   ORCAI_CHECK(build_fused_block<FB4>(c, 3));
@@ -824,6 +884,24 @@ int run_fused_block(Ctx* c, int blk, const __half* xr, const __half* xs, __half*
   else ORCAI_CHECK(make_act_map(c, &tmr, xr, m, Himg, Wimg, G::ICP, G::CP, G::S / 2, 2));
   fused::fused_block_kernel<G><<<(unsigned)grid, G::NTHREADS, G::SMEM, c->stream>>>(tmx, tmr, xs ? 1 : 2, yr, ys, Himg, Wimg, n_strips, items,
                                                                                    static_cast<const unsigned char*>(nw->fb_w[blk]));
+  c->launches++;
+  ORCAI_CUDA(c, cudaGetLastError());
+  return ORCAI_OK;
+}
+
+// block 1 through the N-widened kernel (net_fused_w.cuh)
+int run_fused_block1_wide(Ctx* c, const __half* xr, __half* yr, __half* ys, long long m, int Himg, int Wimg) {
+  using G = FB1W;
+  NetWeights* nw = c->net;
+  const int Wo = (Wimg + 1) / 2;
+  const int n_strips = (Wo + G::CP - 1) / G::CP;
+  const long long items = m * n_strips;
+  const long long grid = std::min<long long>(items, (long long)c->sm_count * G::CTAS);
+  CUtensorMap tmx, tmr;
+  ORCAI_CHECK(make_act_map(c, &tmx, xr, m, Himg, Wimg, G::ICP, G::WP, G::S + 2));
+  ORCAI_CHECK(make_act_map(c, &tmr, xr, m, Himg, Wimg, G::ICP, G::CP, G::S / 2, 2));
+  fused::fused_block_w_kernel<G><<<(unsigned)grid, G::NTHREADS, G::SMEM, c->stream>>>(tmx, tmr, 2, yr, ys, Himg, Wimg, n_strips, items,
+                                                                                     static_cast<const unsigned char*>(nw->fb_w1_wide));
   c->launches++;
   ORCAI_CUDA(c, cudaGetLastError());
   return ORCAI_OK;
@@ -953,6 +1031,7 @@ int forward_fused(Ctx* c, const float* d_in, int input_mode, int64_t first, int6
     net_mark(c, mk);  // 0: conv0
     if (stop == 0) { set_debug(nw, act[0], 1, m, hs[0], ws[0], 16, 16); return ORCAI_OK; }
     if (fuse0) ORCAI_CHECK(run_fused_block1_conv0(c, spec16, input_mode == 0 ? shift : Himg, act[1], acts[1], m, hs[0], ws[0]));
+    else if (nw->block1_path == 1) ORCAI_CHECK(run_fused_block1_wide(c, act[0], act[1], acts[1], m, hs[0], ws[0]));
     else ORCAI_CHECK((run_fused_block<FB1>(c, 0, act[0], static_cast<const H*>(nullptr), act[1], acts[1], m, hs[0], ws[0])));
     net_mark(c, mk);  // 1
     if (stop == 1) { set_debug(nw, act[1], 1, m, hs[1], ws[1], 30, cp[1]); return ORCAI_OK; }

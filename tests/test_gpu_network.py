@@ -229,3 +229,35 @@ def test_silent_recording_labels_nothing(ctx):
             ctx.set_option("net_path", 0)
         assert len(lab) == 0 and len(sta) == 0 and cnt.max() == 2
         assert np.isnan(agg[cnt > 0]).all()
+
+
+def test_block1_n_widened_variant(ctx, params):
+    """block1_path 1 (net_fused_w.cuh): the three dx taps as column blocks of one MMA + shuffle epilogue; same result as the
+    per-tap kernel up to fp16 storage rounding (the fp32 accumulation order differs), same tolerance against the oracle."""
+    P, S = params
+    W = synthetic_weights(P, S, seed=1234)
+    x = np.random.default_rng(21).random((4, 736, 171), dtype=np.float32)
+    ref = network_oracle.forward(x, W)
+    ctx.calibrate()
+    ctx.set_option("net_path", 3)
+    try:
+        base = ctx.forward_host(x)
+        ctx.set_option("block1_path", 1)
+        wide = ctx.forward_host(x)
+        ctx.set_option("chunk", 3)
+        np.testing.assert_array_equal(ctx.forward_host(x), wide)
+        ctx.set_option("chunk", 2048)
+        # same error class as the per-tap kernel on the same input: the MEAN deviation is the stable statistic (within 10 %); the
+        # maximum over 1 288 probabilities is one noise realisation per kernel (here 2.0e-3 vs 2.6e-3, on other inputs the other
+        # way round) and is held to the documented whole-recording maximum of the 16-bit path plus margin
+        e_base, e_wide = np.abs(base - ref), np.abs(wide - ref)
+        assert e_wide.mean() <= max(FAST_MEAN_TOL, 1.10 * e_base.mean())
+        assert e_wide.max() <= 3.5e-3 and np.abs(wide - base).max() <= 3.5e-3
+        b0 = ctx.debug_stage(x[:2], 1)
+        ctx.set_option("block1_path", 0)
+        b1 = ctx.debug_stage(x[:2], 1)
+        assert np.abs(b0 - b1).max() <= 2 ** -7      # one fp16 ulp at |x| < 16
+    finally:
+        ctx.set_option("block1_path", 0)
+        ctx.set_option("net_path", 0)
+        ctx.set_option("chunk", 128)
