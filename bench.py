@@ -316,6 +316,12 @@ def main() -> None:
                              "peak_source": peaks["source"] + " bf16 sustained", "ms": b1_ms, "snippets": int(b1_snips),
                              "algorithmic_mac_per_snippet": BLOCK1_MAC_PER_SNIPPET,
                              "executed_tflops": 2.0 * BLOCK1_EXECUTED_MAC_PER_SNIPPET * b1_snips / (b1_ms * 1e-3) / 1e12,
+                             # what actually bounds it: every M128 K16 N32 MMA fetches 4 KB + 1 KB of operands from shared memory at
+                             # 128 B/clk = 41.3 cycles measured with two issuing CTAs per SM (tools/microbench/mma_cost.cu);
+                             # 3 strips x 123 steps x 89 MMAs per snippet, 148 SMs
+                             "operand_fetch_bound": (lambda model_ms: {"model_ms": model_ms, "frac": model_ms / b1_ms, "cycles_per_mma": 41.3,
+                                                                       "mma_per_snippet": 3 * 123 * 89})(
+                                 b1_snips * 3 * 123 * 89 * 41.3 / 148 / ((clocks.get("sm_mhz") or 1965.0) * 1e3)),
                              "note": "achieved counts the reference graph's MACs; the depthwise filter is folded into the GEMM weights, so the tensor pipe "
                                      "executes 9 taps x pointwise MACs (executed_tflops); the kernel is bound by shared-memory operand bandwidth "
                                      "(A re-read per tap at N = 32), see DESIGN.md"}
