@@ -111,6 +111,8 @@ _SIGNATURES = {
     "orcai_prefetch_pcm": (C.c_int, [_P, _P, C.c_int32, C.c_int64]),
     "orcai_swap_pcm": (C.c_int, [_P]),
     "orcai_debug_read": (C.c_int, [_P, _P, C.c_int64, C.POINTER(C.c_int64)]),
+    "orcai_host_alloc": (_P, [C.c_size_t]),
+    "orcai_host_free": (None, [_P]),
     "orcai_chunk_spectrogram": (C.c_int, [_P, C.c_int64, C.c_int64, C.POINTER(C.c_float)]),
     "orcai_chunk_select_begin": (C.c_int, [_P, C.c_float]),
     "orcai_chunk_histogram": (C.c_int, [_P, C.c_int32, C.c_int64, C.c_int64, _P, _P]),
@@ -176,6 +178,64 @@ def params_from_dicts(orcai_parameter: dict, shape: dict) -> Params:
     return p
 
 
+class PinnedPool:
+    """A few page-locked host buffers that recordings are decoded into (orcai_host_alloc): uploads from them are plain DMA.
+
+    ``take(nbytes)`` -> uint8 ndarray of at least nbytes (keep it until ``give`` returns it); thread-safe.  Pinning memory is
+    slow (~0.3 ms/MB), so buffers are recycled; a buffer that is too small is replaced by a larger one.
+    """
+
+    def __init__(self, max_free: int = 6):
+        import threading
+
+        self.lib = load_library()
+        self._free: list[np.ndarray] = []
+        self._ptr: dict[int, int] = {}       # id(base array) -> device-visible host pointer
+        self._lock = threading.Lock()
+        self._max_free = max_free
+
+    def _alloc(self, nbytes: int) -> np.ndarray:
+        nbytes = max(int(nbytes), 1)
+        nbytes = (nbytes + (1 << 20) - 1) & ~((1 << 20) - 1)
+        p = self.lib.orcai_host_alloc(nbytes)
+        if not p:
+            raise MemoryError(f"orcai_host_alloc({nbytes}) failed")
+        a = np.ctypeslib.as_array((C.c_ubyte * nbytes).from_address(p))
+        self._ptr[id(a)] = p
+        self._keep = getattr(self, "_keep", {})
+        self._keep[id(a)] = a
+        return a
+
+    def take(self, nbytes: int) -> np.ndarray:
+        with self._lock:
+            best = None
+            for i, a in enumerate(self._free):
+                if a.size >= nbytes and (best is None or a.size < self._free[best].size):
+                    best = i
+            if best is not None:
+                return self._free.pop(best)
+            if len(self._free) >= self._max_free:      # every free buffer is too small: drop the smallest
+                self._release(self._free.pop(min(range(len(self._free)), key=lambda j: self._free[j].size)))
+        return self._alloc(nbytes)
+
+    def give(self, a: np.ndarray) -> None:
+        with self._lock:
+            if id(a) in self._ptr:
+                self._free.append(a)
+
+    def _release(self, a: np.ndarray) -> None:
+        p = self._ptr.pop(id(a), None)
+        self._keep.pop(id(a), None)
+        if p:
+            self.lib.orcai_host_free(p)
+
+    def close(self) -> None:
+        with self._lock:
+            for a in self._free:
+                self._release(a)
+            self._free.clear()
+
+
 class Context:
     """One liborcai_b200 context = one device, one stream, one resident recording."""
 
@@ -195,6 +255,9 @@ class Context:
 
     # -- plumbing ------------------------------------------------------------------------------
     def close(self):
+        pool = self.__dict__.pop("_pinned_pool", None)
+        if pool is not None:
+            pool.close()
         if getattr(self, "_h", None):
             self.lib.orcai_destroy(self._h)
             self._h = None

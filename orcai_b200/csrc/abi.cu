@@ -113,6 +113,16 @@ extern "C" {
 
 int orcai_version(void) { return 100; }
 
+void* orcai_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (bytes == 0 || cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+
+void orcai_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
 const char* orcai_last_error(const orcai_ctx* ctx) {
   if (!ctx) return g_create_error.c_str();
   const unsigned int* ti = orcai::net_trap_info();

@@ -205,24 +205,8 @@ def _time_split_contexts(model, ctx):
     return [cache[d].ctx for d in ordered]
 
 
-def predict_wav(
-    recording_path: Path | str,
-    channel: int,
-    model,
-    orcai_parameter: dict,
-    shape: dict,
-    label_suffix: str = "*",
-    msgr: Messenger = Messenger(verbosity=0),
-    progressbar: tqdm = None,
-    _resident_samples=None,
-    _time_split: bool = False,
-):
-    """Predicts calls in a single wav file -> (predicted_labels DataFrame, aggregated_predictions, delta_t).
-
-    ``_resident_samples`` (table mode): the recording has already been read and uploaded by the prefetcher.
-    ``_time_split`` (single-file mode of ``predict``): with several devices in ORCAI_B200_DEVICES the recording is cut into
-    time chunks, one per device (``orcai_b200/timesplit.py``); the result is bit-identical to the one-device path.
-    """
+def _device_predict(recording_path, channel, model, orcai_parameter, shape, msgr, progressbar, _resident_samples=None, _time_split=False):
+    """The device part of predict_wav: samples -> (stats, aggregated probabilities, label indices, start steps, stop steps, delta_t)."""
     recording_path = Path(recording_path)
     if progressbar:
         progressbar.set_description(f"{recording_path.stem}: Generating spectrogram")
@@ -256,16 +240,45 @@ def predict_wav(
             raise ValueError(f"{recording_path.stem}: {e.message}") from e
         raise
     msgr.info(f"Duration of wav file: {(int(stats.n_frames) - 1) * delta_t:.2f} seconds")
+    return stats, agg, lab, sta, sto, delta_t
+
+
+def _labels_of(lab, sta, sto, orcai_parameter: dict, label_suffix: str, msgr) -> pd.DataFrame:
+    """Segments of the device scan -> the reference's label table (predict.py:320-340)."""
     msgr.info("converting binary predictions into start and stop frames")
     calls = orcai_parameter["calls"]
     predicted_labels = compute_labels(
-        [int(v) for v in sta],
-        [int(v) for v in sto],
-        [calls[int(i)] for i in lab],
+        sta.tolist(),
+        sto.tolist(),
+        [calls[i] for i in lab.tolist()],
         time_steps_per_output_step=2 ** len(orcai_parameter["model"]["filters"]),
         label_suffix=label_suffix,
     )
     msgr.info(f"found {len(predicted_labels)} acoustic signals")
+    return predicted_labels
+
+
+def predict_wav(
+    recording_path: Path | str,
+    channel: int,
+    model,
+    orcai_parameter: dict,
+    shape: dict,
+    label_suffix: str = "*",
+    msgr: Messenger = Messenger(verbosity=0),
+    progressbar: tqdm = None,
+    _resident_samples=None,
+    _time_split: bool = False,
+):
+    """Predicts calls in a single wav file -> (predicted_labels DataFrame, aggregated_predictions, delta_t).
+
+    ``_resident_samples`` (table mode): the recording has already been read and uploaded by the prefetcher.
+    ``_time_split`` (single-file mode of ``predict``): with several devices in ORCAI_B200_DEVICES the recording is cut into
+    time chunks, one per device (``orcai_b200/timesplit.py``); the result is bit-identical to the one-device path.
+    """
+    _stats, agg, lab, sta, sto, delta_t = _device_predict(recording_path, channel, model, orcai_parameter, shape, msgr, progressbar,
+                                                           _resident_samples, _time_split)
+    predicted_labels = _labels_of(lab, sta, sto, orcai_parameter, label_suffix, msgr)
     msgr.success("Prediction finished.")
     return predicted_labels, agg, delta_t
 
@@ -341,7 +354,10 @@ def _predict_and_save(
     progressbar: tqdm = None,
     _resident_samples=None,
     _time_split: bool = False,
-) -> None:
+    _writer=None,
+):
+    """``_writer`` (table mode): an executor that takes the host-side tail (label table, filter, files) off the thread that
+    drives the GPU; the future is returned so that the caller can report a failure against the right row."""
     recording_path = Path(recording_path)
     if output_path is not None:
         if output_path == "default":
@@ -355,23 +371,23 @@ def _predict_and_save(
             else:
                 raise FileExistsError(f"Annotation file already exists: {output_path}")
 
-    predicted_labels, aggregated_predictions, delta_t = predict_wav(
-        recording_path=recording_path,
-        channel=channel,
-        model=model,
-        orcai_parameter=orcai_parameter,
-        shape=shape,
-        label_suffix=label_suffix,
-        msgr=msgr,
-        progressbar=progressbar,
-        _resident_samples=_resident_samples,
-        _time_split=_time_split,
+    _stats, aggregated_predictions, lab, sta, sto, delta_t = _device_predict(
+        recording_path, channel, model, orcai_parameter, shape, msgr, progressbar, _resident_samples, _time_split
     )
-    if call_duration_limits is not None:
-        predicted_labels = filter_predictions(predicted_labels, delta_t=delta_t, call_duration_limits=call_duration_limits, label_suffix=label_suffix, msgr=msgr)
-    save_predictions(predicted_labels=predicted_labels, output_path=output_path, delta_t=delta_t, msgr=msgr)
-    if save_probabilities:
-        save_prediction_probabilities(aggregated_predictions, orcai_parameter, delta_t, output_path, msgr=msgr)
+
+    def finish():
+        predicted_labels = _labels_of(lab, sta, sto, orcai_parameter, label_suffix, msgr)
+        msgr.success("Prediction finished.")
+        if call_duration_limits is not None:
+            predicted_labels = filter_predictions(predicted_labels, delta_t=delta_t, call_duration_limits=call_duration_limits, label_suffix=label_suffix, msgr=msgr)
+        save_predictions(predicted_labels=predicted_labels, output_path=output_path, delta_t=delta_t, msgr=msgr)
+        if save_probabilities:
+            save_prediction_probabilities(aggregated_predictions, orcai_parameter, delta_t, output_path, msgr=msgr)
+
+    if _writer is not None:
+        return _writer.submit(finish)
+    finish()
+    return None
 
 
 def _visible_devices() -> list[int]:
@@ -443,11 +459,15 @@ def predict(
     def row_path(i):
         return Path(recording_table.loc[i, "base_dir_recording"]).joinpath(recording_table.loc[i, "rel_recording_path"])
 
-    def run_row(i, mdl, pb, resident=None):
+    def report(i, e):
+        msgr.error(f"Error predicting {recording_table.loc[i, 'recording']}: {e.args[0] if e.args else e}")
+
+    def run_row(i, mdl, pb, resident=None, writer=None):
+        """-> future of the row's host-side tail (or None); failures are reported per row, like the reference loop (predict.py:752-755)"""
         try:
             if isinstance(resident, BaseException):
                 raise resident
-            _predict_and_save(
+            return _predict_and_save(
                 recording_path=row_path(i),
                 channel=int(recording_table.loc[i, "channel"]),
                 model=mdl,
@@ -461,32 +481,78 @@ def predict(
                 msgr=Messenger(verbosity=0),
                 progressbar=pb,
                 _resident_samples=resident,
+                _writer=writer,
             )
-        except Exception as e:  # per-recording isolation, like the reference loop (predict.py:752-755)
-            msgr.error(f"Error predicting {recording_table.loc[i, 'recording']}: {e.args[0] if e.args else e}")
+        except Exception as e:
+            report(i, e)
+            return None
 
     def pipelined(mdl, my_rows, pb, tick):
-        """Reading + uploading recording k+1 overlaps the annotation of recording k (orcai_prefetch_pcm / orcai_swap_pcm)."""
+        """One GPU's share of the table as a three-stage pipeline around the device:
+        loader threads decode WAV files straight into page-locked buffers (a 1-h file takes ~70 ms to read, three times the
+        device time, hence several loaders) -> this thread uploads recording k+1 (DMA, orcai_prefetch_pcm / orcai_swap_pcm)
+        while the device annotates recording k -> a writer thread builds the label table and writes the files."""
+        from orcai_b200._lib import PinnedPool
+
         ctx = _context_of(mdl, orcai_parameter, shape)
         sp = orcai_parameter["spectrogram"]
+        n_load = 3
+        depth = n_load + 1
+        # the pool lives on the context: page-locking 346 MB takes ~0.1 s, a table run must not pay it per call
+        pool = ctx.__dict__.get("_pinned_pool")
+        if pool is None:
+            pool = ctx.__dict__["_pinned_pool"] = PinnedPool(max_free=depth + 2)
 
-        def load_and_prefetch(i):
+        def load(i):
+            taken = []
+
+            def alloc(nbytes):
+                a = pool.take(nbytes)
+                taken.append(a)
+                return a
+
             try:
-                samples = load_recording(row_path(i), int(recording_table.loc[i, "channel"]), sp, Messenger(verbosity=0))
-                ctx.prefetch_pcm(samples)
-                return samples
+                return load_recording(row_path(i), int(recording_table.loc[i, "channel"]), sp, Messenger(verbosity=0), alloc=alloc), taken
             except Exception as e:  # surfaced inside run_row so that the row is reported like any other failure
-                return e
+                for a in taken:
+                    pool.give(a)
+                return e, []
 
-        with ThreadPoolExecutor(max_workers=1) as ex:
-            fut = ex.submit(load_and_prefetch, my_rows[0]) if my_rows else None
+        pending = []
+        with ThreadPoolExecutor(max_workers=n_load) as loaders, ThreadPoolExecutor(max_workers=1) as writer:
+            futs = {k: loaders.submit(load, my_rows[k]) for k in range(min(depth, len(my_rows)))}
+
+            def fetch(k):
+                """wait for recording k on the host and start its upload"""
+                res, taken = futs.pop(k).result()
+                if not isinstance(res, BaseException):
+                    try:
+                        ctx.prefetch_pcm(res)
+                    except Exception as e:
+                        for a in taken:
+                            pool.give(a)
+                        return e, []
+                return res, taken
+
+            cur = fetch(0) if my_rows else None
             for k, i in enumerate(my_rows):
-                res = fut.result()
+                res, taken = cur
                 if not isinstance(res, BaseException):
                     ctx.swap_pcm()
-                fut = ex.submit(load_and_prefetch, my_rows[k + 1]) if k + 1 < len(my_rows) else None
-                run_row(i, mdl, pb, resident=res)
+                if k + depth < len(my_rows):
+                    futs[k + depth] = loaders.submit(load, my_rows[k + depth])
+                cur = fetch(k + 1) if k + 1 < len(my_rows) else None   # its upload overlaps the annotation of recording k
+                fut = run_row(i, mdl, pb, resident=res, writer=writer)
+                if fut is not None:
+                    pending.append((i, fut))
+                for a in taken:
+                    pool.give(a)
                 tick()
+            for i, fut in pending:
+                try:
+                    fut.result()
+                except Exception as e:
+                    report(i, e)
 
     if len(devices) <= 1:
         pipelined(model, rows, progressbar, lambda: progressbar.update(1))

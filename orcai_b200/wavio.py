@@ -75,13 +75,30 @@ def read_wav_info(path: Path | str) -> WavInfo:
                 f.seek(1, 1)
 
 
-def read_wav(path: Path | str, channel: int = 1) -> tuple[np.ndarray, int, int]:
+def read_wav(path: Path | str, channel: int = 1, alloc=None) -> tuple[np.ndarray, int, int]:
     """Return (mono samples, sample_rate, n_channels).
 
     ``channel`` is 1-indexed and only used for multi-channel files (reference
     spectrogram.py:29-31).  The result is int16 for PCM16 input, else float32.
+    ``alloc(nbytes) -> uint8 ndarray``: where to put the samples (e.g. page-locked memory, ``_lib.PinnedPool.take``); a mono
+    PCM16 file is read straight into it, everything else is decoded first and then copied.
     """
     info = read_wav_info(path)
+    if alloc is not None:
+        if info.channels == 1 and info.bits == 16 and not info.is_float:
+            n = info.n_frames
+            buf = alloc(2 * n)
+            with open(path, "rb") as f:
+                f.seek(info.data_offset)
+                got = f.readinto(memoryview(buf)[: 2 * n])
+            if got != 2 * n:
+                raise ValueError(f"{path}: truncated data chunk ({got} of {2 * n} bytes)")
+            return buf[: 2 * n].view("<i2"), info.sample_rate, 1
+        samples, sr, ch = read_wav(path, channel)
+        buf = alloc(samples.nbytes)
+        out = buf[: samples.nbytes].view(samples.dtype)
+        out[:] = samples
+        return out, sr, ch
     ch = info.channels
     if ch > 1 and not (1 <= channel <= ch):
         raise IndexError(f"channel {channel} out of range for a {ch}-channel file")
