@@ -15,7 +15,6 @@ from __future__ import annotations
 
 import gzip
 import os
-import threading
 from concurrent.futures import ThreadPoolExecutor
 from importlib.resources import files
 from pathlib import Path
@@ -402,6 +401,58 @@ def _visible_devices() -> list[int]:
     return [int(x) for x in spec.split(",") if x.strip() != ""]
 
 
+def _predict_worker(kwargs: dict) -> None:
+    """Entry point of a table worker process (spawned): one GPU, its share of the rows."""
+    q = kwargs["_worker"]["queue"]
+    try:
+        os.environ["ORCAI_B200_DEVICES"] = str(kwargs["_worker"]["device"])
+        predict(**kwargs)
+    except BaseException as e:  # noqa: BLE001 - everything is reported to the parent
+        q.put(("fatal", f"worker on device {kwargs['_worker']['device']}: {type(e).__name__}: {e}"))
+    finally:
+        q.put(("done", None))
+
+
+def _predict_table_multiprocess(recording_table, rows, devices, msgr, kwargs) -> None:
+    """Shard a recording table by recording over one process per GPU; host-side gather of ticks and error messages only."""
+    import multiprocessing as mp
+    import queue as queue_mod
+
+    from orcai_b200.sharding import assign_rows, recording_costs
+
+    paths = [Path(recording_table.loc[i, "base_dir_recording"]).joinpath(recording_table.loc[i, "rel_recording_path"]) for i in rows]
+    plan = assign_rows(recording_costs(paths), len(devices))
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = []
+    for d, share in zip(devices, plan):
+        kw = dict(kwargs, _worker={"device": int(d), "rows": [rows[j] for j in share], "queue": q})
+        p = ctx.Process(target=_predict_worker, args=(kw,), daemon=True)
+        p.start()
+        procs.append(p)
+    progressbar = tqdm(total=len(rows), desc=f"{len(devices)} GPUs", unit="file")
+    done = 0
+    while done < len(procs):
+        try:
+            kind, text = q.get(timeout=1.0)
+        except queue_mod.Empty:
+            if not any(p.is_alive() for p in procs) and q.empty():
+                break
+            continue
+        if kind == "tick":
+            progressbar.update(1)
+        elif kind == "error":
+            msgr.error(text)
+        elif kind == "fatal":
+            msgr.error(f"Error in table worker: {text}")
+        elif kind == "done":
+            done += 1
+    for p in procs:
+        p.join(timeout=30)
+    progressbar.close()
+    msgr.success("Predictions finished.")
+
+
 def predict(
     recording_path: str | Path,
     channel: int = 1,
@@ -414,15 +465,23 @@ def predict(
     label_suffix: str = "*",
     verbosity: int = 2,
     msgr: Messenger | None = None,
+    _worker: dict | None = None,
 ) -> None:
-    """Predicts calls in a wav file or in every recording of a recording table (.csv)."""
+    """Predicts calls in a wav file or in every recording of a recording table (.csv).
+
+    A table with several devices in ORCAI_B200_DEVICES is sharded by recording over ONE PROCESS PER GPU: the
+    parent plans the shares (longest files first) and spawns the workers, which call this function again with ``_worker``
+    = {"device", "rows", "queue"}; the only traffic between them is progress ticks and per-row error messages.
+    """
     if msgr is None:
         msgr = Messenger(verbosity=verbosity, title="Predicting calls")
     model_dir = Path(str(model_dir))
     recording_path = Path(recording_path)
-    msgr.part(f"Loading model: {model_dir.stem}")
-    devices = _visible_devices()
-    model, orcai_parameter, shape = load_orcai_model(model_dir, device=devices[0] if devices else None)
+    devices = [_worker["device"]] if _worker else _visible_devices()
+    multi = recording_path.suffix == ".csv" and len(devices) > 1
+    if not multi:
+        msgr.part(f"Loading model: {model_dir.stem}")
+        model, orcai_parameter, shape = load_orcai_model(model_dir, device=devices[0] if devices else None)
 
     if recording_path.suffix == ".wav":
         return _predict_and_save(
@@ -454,13 +513,24 @@ def predict(
 
     msgr.part(f"Predicting annotations for {len(recording_table)} wav files")
     rows = list(recording_table.index)
-    progressbar = tqdm(total=len(rows), desc="Starting ...", unit="file")
+    if multi:
+        return _predict_table_multiprocess(
+            recording_table, rows, devices, msgr,
+            dict(recording_path=recording_path, channel=channel, model_dir=model_dir, output_path=output_path, overwrite=overwrite,
+                 save_probabilities=save_probabilities, base_dir_recording=base_dir_recording, call_duration_limits=call_duration_limits,
+                 label_suffix=label_suffix, verbosity=0),
+        )
+    progressbar = None if _worker else tqdm(total=len(rows), desc="Starting ...", unit="file")
 
     def row_path(i):
         return Path(recording_table.loc[i, "base_dir_recording"]).joinpath(recording_table.loc[i, "rel_recording_path"])
 
     def report(i, e):
-        msgr.error(f"Error predicting {recording_table.loc[i, 'recording']}: {e.args[0] if e.args else e}")
+        text = f"Error predicting {recording_table.loc[i, 'recording']}: {e.args[0] if e.args else e}"
+        if _worker:
+            _worker["queue"].put(("error", text))
+        else:
+            msgr.error(text)
 
     def run_row(i, mdl, pb, resident=None, writer=None):
         """-> future of the row's host-side tail (or None); failures are reported per row, like the reference loop (predict.py:752-755)"""
@@ -554,29 +624,10 @@ def predict(
                 except Exception as e:
                     report(i, e)
 
-    if len(devices) <= 1:
-        pipelined(model, rows, progressbar, lambda: progressbar.update(1))
-    else:
-        # shard by recording: one worker thread (context + streams) per GPU; rows are assigned
-        # longest-first (LPT on the file sizes) and every worker pipelines its own share; host-side gather only
-        from orcai_b200.model import OrcaiModel
-        from orcai_b200.sharding import assign_rows, recording_costs
-
-        models = [model] + [OrcaiModel(orcai_parameter, shape, model.weights, device=d) for d in devices[1:]]
-        plan = assign_rows(recording_costs([row_path(i) for i in rows]), len(models))
-        lock = threading.Lock()
-
-        def tick():
-            with lock:
-                progressbar.update(1)
-
-        threads = [
-            threading.Thread(target=pipelined, args=(m, [rows[j] for j in share], None, tick), daemon=True)
-            for m, share in zip(models, plan)
-        ]
-        for t in threads:
-            t.start()
-        for t in threads:
-            t.join()
+    if _worker:
+        q = _worker["queue"]
+        pipelined(model, [i for i in rows if i in set(_worker["rows"])], None, lambda: q.put(("tick", None)))
+        return None
+    pipelined(model, rows, progressbar, lambda: progressbar.update(1))
     progressbar.close()
     msgr.success("Predictions finished.")

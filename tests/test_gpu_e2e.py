@@ -171,3 +171,39 @@ def test_table_mode_and_cli(ctx, params, model_dir, wavs, tmp_path, capsys):
     assert tj["length"] == spec.shape[0] and tj["max"] == times[-1]
     r = CliRunner().invoke(cli.cli, ["create-spectrograms", str(csv2), str(sdir2), "-en", "-enp", "-v", "0"])
     assert r.exit_code == 0 and (sdir2 / "rec1").exists() and (sdir2 / "rec2").exists()
+
+
+def test_table_mode_one_process_per_gpu(params, model_dir, wavs, tmp_path, monkeypatch):
+    """A table with several devices in ORCAI_B200_DEVICES runs one worker PROCESS per device (here: two processes on device 0):
+    same label files as the one-device run, per-row errors reported by the parent."""
+    from orcai_b200 import predict as opredict
+
+    P, S = params
+    d, files = wavs
+    names = ["a0", "a1", "gone", "a2", "a3", "a4"]
+    table = pd.DataFrame({"recording": names, "channel": 1, "base_dir_recording": str(d),
+                          "rel_recording_path": ["rec0.wav", "rec1.wav", "nope.wav", "rec2.wav", "rec1.wav", "rec0.wav"]})
+    csv = tmp_path / "t.csv"
+    table.to_csv(csv, index=False)
+    one, two = tmp_path / "one", tmp_path / "two"
+    one.mkdir(); two.mkdir()
+    monkeypatch.delenv("ORCAI_B200_DEVICES", raising=False)
+    opredict.predict(csv, model_dir=model_dir, output_path=str(one), verbosity=0)
+
+    class Collect(Messenger):
+        def __init__(self):
+            super().__init__(verbosity=0)
+            self.errors = []
+
+        def error(self, text, *a, **k):
+            self.errors.append(str(text))
+
+    m = Collect()
+    monkeypatch.setenv("ORCAI_B200_DEVICES", "0,0")
+    opredict.predict(csv, model_dir=model_dir, output_path=str(two), verbosity=0, msgr=m)
+    assert any("Error predicting gone" in e for e in m.errors), m.errors
+    for n in names:
+        f1, f2 = one / f"{n}_orcai-V1_predicted.txt", two / f"{n}_orcai-V1_predicted.txt"
+        assert f1.exists() == f2.exists() == (n != "gone")
+        if n != "gone":
+            assert f1.read_bytes() == f2.read_bytes()
