@@ -15,6 +15,7 @@ from __future__ import annotations
 
 import gzip
 import os
+import threading
 from concurrent.futures import ThreadPoolExecutor
 from importlib.resources import files
 from pathlib import Path
@@ -478,8 +479,12 @@ def predict(
     model_dir = Path(str(model_dir))
     recording_path = Path(recording_path)
     devices = [_worker["device"]] if _worker else _visible_devices()
-    multi = recording_path.suffix == ".csv" and len(devices) > 1
+    # several devices: worker THREADS in this process by default (measured: 66.6 h/s on 8 B200, bound by the interpreter lock
+    # around the per-recording host work), worker PROCESSES with ORCAI_B200_TABLE_PROCESSES=1 (no shared interpreter, but every
+    # process pays its own start-up: CUDA context, model, calibration, page-locked buffers)
+    multi = recording_path.suffix == ".csv" and len(devices) > 1 and os.environ.get("ORCAI_B200_TABLE_PROCESSES", "0") == "1"
     if not multi:
+        devices = list(dict.fromkeys(devices))   # one context per device in this process: a device listed twice counts once
         msgr.part(f"Loading model: {model_dir.stem}")
         model, orcai_parameter, shape = load_orcai_model(model_dir, device=devices[0] if devices else None)
 
@@ -628,6 +633,29 @@ def predict(
         q = _worker["queue"]
         pipelined(model, [i for i in rows if i in set(_worker["rows"])], None, lambda: q.put(("tick", None)))
         return None
-    pipelined(model, rows, progressbar, lambda: progressbar.update(1))
+    if len(devices) <= 1:
+        pipelined(model, rows, progressbar, lambda: progressbar.update(1))
+    else:
+        # shard by recording: one worker thread (context + streams) per GPU; rows are assigned
+        # longest-first (LPT on the file sizes) and every worker pipelines its own share; host-side gather only
+        from orcai_b200.model import OrcaiModel
+        from orcai_b200.sharding import assign_rows, recording_costs
+
+        models = [model] + [OrcaiModel(orcai_parameter, shape, model.weights, device=d) for d in devices[1:]]
+        plan = assign_rows(recording_costs([row_path(i) for i in rows]), len(models))
+        lock = threading.Lock()
+
+        def tick():
+            with lock:
+                progressbar.update(1)
+
+        threads = [
+            threading.Thread(target=pipelined, args=(m, [rows[j] for j in share], None, tick), daemon=True)
+            for m, share in zip(models, plan)
+        ]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
     progressbar.close()
     msgr.success("Predictions finished.")

@@ -174,8 +174,8 @@ def test_table_mode_and_cli(ctx, params, model_dir, wavs, tmp_path, capsys):
 
 
 def test_table_mode_one_process_per_gpu(params, model_dir, wavs, tmp_path, monkeypatch):
-    """A table with several devices in ORCAI_B200_DEVICES runs one worker PROCESS per device (here: two processes on device 0):
-    same label files as the one-device run, per-row errors reported by the parent."""
+    """A table with several devices in ORCAI_B200_DEVICES: one worker thread per device by default, one worker PROCESS per device with
+    ORCAI_B200_TABLE_PROCESSES=1 (here: two workers on device 0): same label files as the one-device run, per-row errors reported."""
     from orcai_b200 import predict as opredict
 
     P, S = params
@@ -200,7 +200,16 @@ def test_table_mode_one_process_per_gpu(params, model_dir, wavs, tmp_path, monke
 
     m = Collect()
     monkeypatch.setenv("ORCAI_B200_DEVICES", "0,0")
+    monkeypatch.setenv("ORCAI_B200_TABLE_PROCESSES", "1")
     opredict.predict(csv, model_dir=model_dir, output_path=str(two), verbosity=0, msgr=m)
+    # the default for several devices: worker threads in this process (two contexts on device 0)
+    three = tmp_path / "three"
+    three.mkdir()
+    monkeypatch.setenv("ORCAI_B200_TABLE_PROCESSES", "0")
+    opredict.predict(csv, model_dir=model_dir, output_path=str(three), verbosity=0)
+    for n in names:
+        if n != "gone":
+            assert (one / f"{n}_orcai-V1_predicted.txt").read_bytes() == (three / f"{n}_orcai-V1_predicted.txt").read_bytes()
     assert any("Error predicting gone" in e for e in m.errors), m.errors
     for n in names:
         f1, f2 = one / f"{n}_orcai-V1_predicted.txt", two / f"{n}_orcai-V1_predicted.txt"
