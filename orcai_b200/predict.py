@@ -171,14 +171,20 @@ def compute_labels(
 ) -> pd.DataFrame:
     if (label_suffix is not None) & (label_suffix != ""):
         label_names = [label + label_suffix for label in label_names]
+    start = np.asarray(row_starts) * time_steps_per_output_step
+    stop = np.asarray(row_stops) * time_steps_per_output_step
+    if len(label_names) and start.dtype.kind in "iu":
+        # sort_values(by=[start, stop, label]) of the reference (predict.py:329-339) as one lexsort: labels compare like their
+        # rank among the distinct names (a table run builds thousands of these tables under the interpreter lock)
+        names = sorted(set(label_names))
+        rank = {n: r for r, n in enumerate(names)}
+        lab = np.fromiter((rank[n] for n in label_names), dtype=np.int64, count=len(label_names))
+        order = np.lexsort((lab, stop, start))
+        name_arr = np.empty(len(names), dtype=object)
+        name_arr[:] = names
+        return pd.DataFrame({"start": start[order], "stop": stop[order], "label": name_arr[lab[order]]})
     return (
-        pd.DataFrame(
-            {
-                "start": np.asarray(row_starts) * time_steps_per_output_step,
-                "stop": np.asarray(row_stops) * time_steps_per_output_step,
-                "label": label_names,
-            }
-        )
+        pd.DataFrame({"start": start, "stop": stop, "label": label_names})
         .sort_values(by=["start", "stop", "label"])
         .reset_index(drop=True)
     )
@@ -244,16 +250,22 @@ def _device_predict(recording_path, channel, model, orcai_parameter, shape, msgr
 
 
 def _labels_of(lab, sta, sto, orcai_parameter: dict, label_suffix: str, msgr) -> pd.DataFrame:
-    """Segments of the device scan -> the reference's label table (predict.py:320-340)."""
+    """Segments of the device scan -> the reference's label table (predict.py:320-340): what ``compute_labels`` returns for
+    the same segments, built from the label INDICES with array operations only (no per-segment Python work)."""
     msgr.info("converting binary predictions into start and stop frames")
-    calls = orcai_parameter["calls"]
-    predicted_labels = compute_labels(
-        sta.tolist(),
-        sto.tolist(),
-        [calls[i] for i in lab.tolist()],
-        time_steps_per_output_step=2 ** len(orcai_parameter["model"]["filters"]),
-        label_suffix=label_suffix,
-    )
+    step = 2 ** len(orcai_parameter["model"]["filters"])
+    lab = np.asarray(lab, dtype=np.int64)
+    if lab.size == 0:
+        return compute_labels([], [], [], step, label_suffix)
+    suffix = label_suffix if (label_suffix is not None) and (label_suffix != "") else ""
+    names = np.empty(len(orcai_parameter["calls"]), dtype=object)
+    names[:] = [c + suffix for c in orcai_parameter["calls"]]
+    rank = np.empty(len(names), dtype=np.int64)
+    rank[sorted(range(len(names)), key=lambda j: names[j])] = np.arange(len(names))   # labels compare like their names
+    start = np.asarray(sta, dtype=np.int64) * step
+    stop = np.asarray(sto, dtype=np.int64) * step
+    order = np.lexsort((rank[lab], stop, start))
+    predicted_labels = pd.DataFrame({"start": start[order], "stop": stop[order], "label": names[lab[order]]})
     msgr.info(f"found {len(predicted_labels)} acoustic signals")
     return predicted_labels
 
@@ -286,6 +298,9 @@ def predict_wav(
 # ---------------------------------------------------------------------------------------------
 # writers (predict.py:343-364, 474-531)
 # ---------------------------------------------------------------------------------------------
+_SECONDS_TEXT: dict[float, dict[int, str]] = {}   # delta_t -> {frame index: text of its time in seconds}
+
+
 def _seconds_column(values, delta_t: float) -> list[str]:
     """Text of one time column as pandas 2.2.3 wrote it after ``df.loc[:, c] = df.loc[:, c] * delta_t``.
 
@@ -296,6 +311,19 @@ def _seconds_column(values, delta_t: float) -> list[str]:
     prod = v * np.float64(delta_t)
     if prod.size and v.dtype.kind in "iu" and np.all(prod == np.trunc(prod)):
         return [str(int(x)) for x in prod]
+    if v.dtype.kind in "iu" and v.size > 64:
+        # frame indices repeat from recording to recording: format each distinct (delta_t, frame) once per process
+        cache = _SECONDS_TEXT.setdefault(float(delta_t), {})
+        keys = v.tolist()
+        missing = [k for k in set(keys) if k not in cache]
+        if missing:
+            m = np.asarray(missing, dtype=v.dtype)
+            for k, x in zip(missing, np.round((m * np.float64(delta_t)).astype(np.float64), 4)):
+                cache[k] = repr(float(x))
+            if len(cache) > 4_000_000:
+                cache.clear()
+                return [repr(float(x)) for x in np.round(prod.astype(np.float64), 4)]
+        return [cache[k] for k in keys]
     return [repr(float(x)) for x in np.round(prod.astype(np.float64), 4)]
 
 

@@ -239,3 +239,38 @@ def test_host_resampler_preserves_a_tone():
     assert np.abs(y[2000:-2000] - ref[2000:-2000]).max() < 2e-3
     z = resample(x.astype(np.float32) / 32768.0, sr, target)
     np.testing.assert_allclose(z, y, atol=1e-6)
+
+
+def test_fast_label_table_equals_compute_labels():
+    """predict._labels_of (array operations on label indices, used by predict_wav / table mode) == the reference-shaped
+    compute_labels (predict.py:320-340) on the same segments, including ties, every suffix and the empty result; the cached
+    time formatting writes the same text as the uncached one."""
+    import pandas as pd
+
+    from orcai_b200 import predict as op, runtime
+    from orcai_b200.auxiliary import Messenger
+
+    P, _ = runtime.bundled_parameters()
+    calls = P["calls"]
+    rng = np.random.default_rng(1)
+    m = Messenger(verbosity=0)
+    for suf in ("*", "", None, "_x"):
+        for n in (0, 1, 7, 3000):
+            sta = np.sort(rng.integers(0, 42000, n))
+            sto = sta + rng.integers(0, 30, n)
+            lab = rng.integers(0, len(calls), n).astype(np.int32)
+            if n > 20:
+                sta[10:20] = sta[10]
+                sto[10:20] = sto[10]
+            a = op._labels_of(lab, sta, sto, P, suf, m)
+            b = op.compute_labels(sta.tolist(), sto.tolist(), [calls[i] for i in lab.tolist()], 16, suf)
+            pd.testing.assert_frame_equal(a, b)
+            dt = 256 / 48000
+            text = op.labels_to_tsv(a, dt)
+            assert text == op.labels_to_tsv(b, dt)
+            if n:
+                want = "start\tstop\tlabel\n" + "".join(
+                    f"{float(x)!r}\t{float(y)!r}\t{l}\n"
+                    for x, y, l in zip(np.round(b["start"].to_numpy() * np.float64(dt), 4), np.round(b["stop"].to_numpy() * np.float64(dt), 4), b["label"])
+                )
+                assert text == want
