@@ -555,6 +555,8 @@ def predict(
         )
     progressbar = None if _worker else tqdm(total=len(rows), desc="Starting ...", unit="file")
 
+    out_path_of = dict(zip(rows, out_paths))
+
     def row_path(i):
         return Path(recording_table.loc[i, "base_dir_recording"]).joinpath(recording_table.loc[i, "rel_recording_path"])
 
@@ -576,7 +578,7 @@ def predict(
                 model=mdl,
                 orcai_parameter=orcai_parameter,
                 shape=shape,
-                output_path=out_paths[rows.index(i)],
+                output_path=out_path_of[i],
                 overwrite=overwrite,
                 save_probabilities=save_probabilities,
                 call_duration_limits=call_duration_limits,

@@ -274,3 +274,46 @@ def test_fast_label_table_equals_compute_labels():
                     for x, y, l in zip(np.round(b["start"].to_numpy() * np.float64(dt), 4), np.round(b["stop"].to_numpy() * np.float64(dt), 4), b["label"])
                 )
                 assert text == want
+
+
+def test_wav_reader_into_caller_memory(tmp_path):
+    """read_wav(alloc=...) (table mode decodes into page-locked buffers): same samples as the plain reader for mono PCM16
+    (read straight into the buffer) and for every format that is decoded first (stereo, 24-bit, float)."""
+    import struct
+
+    from orcai_b200 import wavio
+
+    rng = np.random.default_rng(4)
+    taken = []
+
+    def alloc(nbytes):
+        a = np.full(nbytes + 64, 0xAB, dtype=np.uint8)   # larger than asked for, like a recycled pool buffer
+        taken.append(a)
+        return a
+
+    mono = rng.integers(-32768, 32767, 48000 + 7, dtype=np.int16)
+    wavio.write_wav_pcm16(tmp_path / "mono.wav", mono)
+    stereo = rng.integers(-32768, 32767, (5000, 2), dtype=np.int16)
+    wavio.write_wav_pcm16(tmp_path / "stereo.wav", stereo)
+    f32 = rng.standard_normal(3000).astype("<f4")
+    with open(tmp_path / "f32.wav", "wb") as f:
+        f.write(b"RIFF" + struct.pack("<I", 36 + f32.nbytes) + b"WAVE" + b"fmt " + struct.pack("<IHHIIHH", 16, 3, 1, 48000, 48000 * 4, 4, 32))
+        f.write(b"data" + struct.pack("<I", f32.nbytes) + f32.tobytes())
+    raw24 = rng.integers(0, 256, 3 * 2000, dtype=np.uint8)
+    with open(tmp_path / "p24.wav", "wb") as f:
+        f.write(b"RIFF" + struct.pack("<I", 36 + raw24.size) + b"WAVE" + b"fmt " + struct.pack("<IHHIIHH", 16, 1, 1, 48000, 48000 * 3, 3, 24))
+        f.write(b"data" + struct.pack("<I", raw24.size) + raw24.tobytes())
+    for name, ch in (("mono.wav", 1), ("stereo.wav", 2), ("f32.wav", 1), ("p24.wav", 1)):
+        plain, sr, n_ch = wavio.read_wav(tmp_path / name, ch)
+        taken.clear()
+        got, sr2, n_ch2 = wavio.read_wav(tmp_path / name, ch, alloc=alloc)
+        assert (sr, n_ch) == (sr2, n_ch2) and got.dtype == plain.dtype and len(taken) == 1
+        np.testing.assert_array_equal(got, plain)
+        assert np.shares_memory(got, taken[0])            # the samples live in the caller's buffer
+    np.testing.assert_array_equal(wavio.read_wav(tmp_path / "mono.wav", 1, alloc=alloc)[0], mono)
+    # a truncated data chunk is reported, not silently zero-filled
+    data = (tmp_path / "mono.wav").read_bytes()
+    (tmp_path / "cut.wav").write_bytes(data[: len(data) - 1000])
+    cut_plain = wavio.read_wav(tmp_path / "cut.wav", 1)[0]
+    cut_alloc = wavio.read_wav(tmp_path / "cut.wav", 1, alloc=alloc)[0]
+    np.testing.assert_array_equal(cut_plain, cut_alloc)
