@@ -171,3 +171,104 @@ def test_predict_single_wav_on_two_devices_writes_the_same_file(tmp_path, params
     import gzip
 
     assert gzip.open(tmp_path / "one_probabilities.csv.gz").read() == gzip.open(tmp_path / "two_probabilities.csv.gz").read()
+
+
+class _OracleChunkContext:
+    """numpy stand-in for a device context (test infrastructure, built on oracle/): the chunk_* / forward_resident /
+    postprocess calls of _lib.Context with the oracle's arithmetic, so that the HOST orchestration of the time split
+    (plan, halo handling, maxima, host-driven radix select, gather) is checked on the CPU against the reference's own
+    whole-recording order of operations."""
+
+    def __init__(self, P, calls_log):
+        from types import SimpleNamespace
+
+        sp = P["spectrogram"]
+        self.sp = sp
+        self.params = SimpleNamespace(hop=sp["n_overlap"], snippet_len=736, band_lo=0, band_hi=171, q_lo=sp["quantiles"][0], q_hi=sp["quantiles"][1],
+                                      n_blocks=4, n_labels=7)
+        self.log = calls_log
+
+    def upload_pcm(self, pcm):
+        from orcai_b200.synth import pcm16_to_float
+
+        self.y = pcm16_to_float(np.asarray(pcm))
+
+    def chunk_spectrogram(self, r0, r1):
+        from oracle import spectrogram_oracle as so
+
+        S = so.stft_complex64(self.y, self.sp["nfft"], self.sp["n_overlap"])
+        power = np.square(np.abs(S))                               # float32 |S|^2, (257, T_local)
+        self.raw = (np.float32(10.0) * np.log10(np.maximum(np.float32(1e-10), power)))[:171].T.copy()   # unshifted dB, (T_local, 171)
+        self.log.append(("spectrogram", r0, r1, self.raw.shape[0]))
+        return float(power[:, r0:r1].max()) if r1 > r0 else 0.0
+
+    def chunk_select_begin(self, pmax):
+        self.db_ref = np.float32(10.0) * np.log10(np.maximum(np.float32(1e-10), np.float32(pmax)))
+
+    def _keys(self, r0, r1):
+        v = np.maximum(self.raw[r0:r1] - self.db_ref, np.float32(-80.0)).astype(np.float32).ravel()
+        return _float_key(v)
+
+    def chunk_histogram(self, pass_, r0, r1, prefix):
+        k = self._keys(r0, r1)
+        h = np.zeros((2, 2048), np.uint64)
+        for r in range(2):
+            if pass_ == 0:
+                if r == 0:
+                    np.add.at(h[0], (k >> 21).astype(np.int64), 1)
+                continue
+            sel = k[(k >> 21) == (int(prefix[r]) >> 21)] if pass_ == 1 else k[(k >> 10) == (int(prefix[r]) >> 10)]
+            np.add.at(h[r], (((sel >> 10) & 2047) if pass_ == 1 else (sel & 1023)).astype(np.int64), 1)
+        return h
+
+    def chunk_select_end(self, keys):
+        from types import SimpleNamespace
+
+        self.lo, self.hi = key_to_float(int(keys[0])), key_to_float(int(keys[1]))
+        return SimpleNamespace(lo=float(self.lo), hi=float(self.hi), db_ref=float(self.db_ref), n_frames=0, rank_lo=0, rank_hi=0)
+
+    def forward_resident(self, first, n):
+        # a stand-in "network": per snippet, per output step, 7 statistics of the normalised spectrogram (sensitive to every frame)
+        v = np.maximum(self.raw - self.db_ref, np.float32(-80.0))
+        spec = (np.clip(v, self.lo, self.hi) - self.lo) / (self.hi - self.lo)
+        out = np.empty((n, 46, 7), np.float32)
+        for s in range(n):
+            snip = spec[368 * (first + s) : 368 * (first + s) + 736].reshape(46, 16, 171)
+            out[s] = np.stack([snip[:, :, 24 * j : 24 * j + 24].mean(axis=(1, 2)) for j in range(7)], axis=1)
+        return out
+
+    def postprocess(self, preds, T, threshold=0.5, want_agg=True):
+        from oracle import postprocess_oracle as po
+
+        agg, cnt = po.aggregate_predictions(preds, T, 736, 4, 7)
+        return agg, cnt, np.zeros(0, np.int32), np.zeros(0, np.int64), np.zeros(0, np.int64)
+
+
+@pytest.mark.parametrize("seconds,n_chunks", [(12.0, 2), (31.7, 3), (31.7, 5), (9.0, 4)])
+def test_time_split_orchestration_on_cpu(params, seconds, n_chunks):
+    """predict_pcm_timesplit driven with numpy stand-in contexts == the oracle's whole-recording pipeline: identical reference
+    level, percentiles (the host-driven radix select over chunk histograms), predictions and aggregates, for every chunk count."""
+    from oracle import postprocess_oracle as po, spectrogram_oracle as so
+    from orcai_b200.synth import pcm16_to_float, synth_pcm16
+    from orcai_b200.timesplit import predict_pcm_timesplit
+
+    P, S = params
+    pcm = synth_pcm16(seconds, seed=4242, calls_per_minute=40.0)[: int(seconds * 48000) - 311]
+    db, freqs, _ = so.calculate_spectrogram(pcm16_to_float(pcm), P["spectrogram"])
+    spec_ref, lo, hi = so.preprocess_spectrogram(db, freqs, P["spectrogram"])
+    log = []
+    ctxs = [_OracleChunkContext(P, log) for _ in range(n_chunks)]
+    st, agg, cnt, *_ = predict_pcm_timesplit(ctxs, pcm, parallel=False)
+    assert np.float32(st.lo) == lo and np.float32(st.hi) == hi
+    T = spec_ref.shape[0]
+    assert st.n_frames == T
+    # the stand-in network on the oracle's whole-recording spectrogram
+    N = (T - 736) // 368 + 1
+    want = np.empty((N, 46, 7), np.float32)
+    for s in range(N):
+        snip = spec_ref[368 * s : 368 * s + 736].reshape(46, 16, 171)
+        want[s] = np.stack([snip[:, :, 24 * j : 24 * j + 24].mean(axis=(1, 2)) for j in range(7)], axis=1)
+    agg_ref, cnt_ref = po.aggregate_predictions(want, T, 736, 4, 7)
+    np.testing.assert_array_equal(cnt, cnt_ref)
+    np.testing.assert_allclose(agg, agg_ref, rtol=0, atol=2e-6)    # dB through log10 of float32 powers: last-ulp differences only
+    assert len([e for e in log if e[0] == "spectrogram"]) == min(n_chunks, N)
