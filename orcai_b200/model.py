@@ -18,7 +18,10 @@ from orcai_b200.weights import check_weights
 # network arithmetic: "fast" = fp16 tcgen05 fused residual blocks + tensor-core LSTM tail, biases calibrated against fp16
 # weight rounding (probabilities: mean deviation 1e-4 from the fp32 graph, max ~2.7e-3 over an hour of audio; operand precision
 # of TensorFlow's default TF32 execution on GPUs); "reference" = fp32 CUDA-core path (1e-6), 11x slower.
-PRECISION_PATHS = {"fast": 3, "reference": 0}
+# "accurate" = "fast" with the fp32 CUDA-core entry convolution (fp32 spectrogram, weights and accumulation in the first layer):
+# +5 % network time, mean deviation -29 % with BatchNorm-matched weights.
+PRECISION_PATHS = {"fast": 3, "accurate": 3, "reference": 0}
+PRECISION_CONV0 = {"fast": 1, "accurate": 0, "reference": 1}     # "conv0_path" option of the fused path
 
 
 def precision_from_env() -> str:
@@ -40,7 +43,8 @@ class OrcaiModel:
         self.ctx.load_weights(weights)
         self.precision = precision or precision_from_env()
         self.ctx.set_option("net_path", PRECISION_PATHS[self.precision])
-        if self.precision == "fast":
+        self.ctx.set_option("conv0_path", PRECISION_CONV0[self.precision])
+        if PRECISION_PATHS[self.precision] == 3:
             # bias correction for fp16 weight rounding: channel means from a calibration recording - the built-in synthetic one,
             # or a representative recording of the deployment named by ORCAI_B200_CALIBRATION=<wav file>
             cal = os.environ.get("ORCAI_B200_CALIBRATION", "").strip()

@@ -200,6 +200,9 @@ def test_precision_selector(monkeypatch):
     assert model.precision_from_env() == "fast" and model.PRECISION_PATHS["fast"] == 3
     monkeypatch.setenv("ORCAI_B200_PRECISION", "Reference ")
     assert model.precision_from_env() == "reference" and model.PRECISION_PATHS["reference"] == 0
+    monkeypatch.setenv("ORCAI_B200_PRECISION", "accurate")
+    assert model.precision_from_env() == "accurate" and model.PRECISION_PATHS["accurate"] == 3 and model.PRECISION_CONV0["accurate"] == 0
+    assert model.PRECISION_CONV0["fast"] == 1
     monkeypatch.setenv("ORCAI_B200_PRECISION", "bf16")
     with pytest.raises(ValueError, match="ORCAI_B200_PRECISION"):
         model.precision_from_env()
