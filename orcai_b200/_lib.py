@@ -190,7 +190,8 @@ class PinnedPool:
 
         self.lib = load_library()
         self._free: list[np.ndarray] = []
-        self._ptr: dict[int, int] = {}       # id(base array) -> device-visible host pointer
+        self._ptr: dict[int, int] = {}       # id(buffer) -> host pointer
+        self._keep: dict[int, np.ndarray] = {}   # keeps every live buffer's array object (and thereby its id) alive
         self._lock = threading.Lock()
         self._max_free = max_free
 
@@ -202,7 +203,6 @@ class PinnedPool:
             raise MemoryError(f"orcai_host_alloc({nbytes}) failed")
         a = np.ctypeslib.as_array((C.c_ubyte * nbytes).from_address(p))
         self._ptr[id(a)] = p
-        self._keep = getattr(self, "_keep", {})
         self._keep[id(a)] = a
         return a
 
