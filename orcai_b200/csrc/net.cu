@@ -549,6 +549,7 @@ int net_set_chunk(Ctx* c, int chunk) {
   if (chunk < 1) ORCAI_FAIL(c, ORCAI_ERR_ARG, "chunk must be >= 1");
   c->net->chunk = chunk;
   c->net->chunk_fused = chunk;
+  c->net->chunk_precise = chunk;
   return ORCAI_OK;
 }
 
@@ -560,6 +561,7 @@ int net_load_weights(Ctx* c, const char* const* names, const float* const* data,
   nw->tc_ready[0] = nw->tc_ready[1] = false;
   nw->fused_ready = false;
   nw->tail_tc_ready = false;
+  nw->precise_ready = nw->tail_precise_ready = false;
   nw->calib = Calib();
   const orcai_params& P = c->p;
   if (P.n_blocks != 4 || P.filters[0] != 30 || P.filters[1] != 40 || P.filters[2] != 50 || P.filters[3] != 60 ||
@@ -650,6 +652,15 @@ int net_load_weights(Ctx* c, const char* const* names, const float* const* data,
     ORCAI_CHECK(upload(c, bb2, &nw->d2_b));
   }
   nw->loaded = true;
+  return ORCAI_OK;
+}
+
+int net_lstm_rec_fp32(Ctx* c, const float* xz, const float* whh, float* out, long long m, int Tn) {
+  if (m <= 0) return ORCAI_OK;
+  dim3 grid((unsigned)((m + kSN - 1) / kSN), 2);
+  lstm_rec_kernel<128><<<grid, 512, 0, c->stream>>>(xz, whh, out, m, Tn);
+  c->launches++;
+  ORCAI_CUDA(c, cudaGetLastError());
   return ORCAI_OK;
 }
 

@@ -63,6 +63,7 @@ struct NetWeights {
   // fused residual-block kernels (net_fused.cuh): packed fp16 operands [sep1 | sep2 | residual] and fp32 biases per block
   bool fused_ready = false;
   void* fb_w[kMaxBlocks] = {};
+  void* fbp_w[kMaxBlocks] = {};   // precise path (net_path 4): split-fp16 (hi, lo) operand sets of the fused blocks
   float* fb_bias[kMaxBlocks] = {};
   int chunk_fused = 2048;
   TcSep fb_fin;                  // final separable convolution with the calibrated bias (fused path)
@@ -80,6 +81,15 @@ struct NetWeights {
   __half* tc_d1 = nullptr;    // Dense(128) B blocks
   std::vector<float> h_lstm_wih[2], h_lstm_whh[2], h_lstm_bih[2], h_d1_w, h_d1_b;
   std::vector<float> h_res_w[kMaxBlocks], h_res_b[kMaxBlocks];
+  // fp32-grade tensor-core path (net_path 4, net_precise.cuh)
+  bool precise_ready = false, tail_precise_ready = false;
+  __half* tp_wih[2] = {};     // split (hi, lo) B blocks of the LSTM input projections
+  __half* tp_d1 = nullptr;    // ... of Dense(128)
+  struct PreciseSep { float* dw = nullptr; __half* pw = nullptr; float* bias = nullptr; };   // [9][CIP] fp32, split B blocks [CIP][64], 64 floats
+  PreciseSep p_sep1[kMaxBlocks], p_sep2[kMaxBlocks], p_fin;
+  float* p_res_w[kMaxBlocks] = {};   // [CIP][COP] fp32, zero padded
+  float* p_res_b[kMaxBlocks] = {};   // [COP]
+  int chunk_precise = 1024;
   int debug_stop = -1;        // stop the forward after this stage (debug reads), -1 = run everything
   // last debug buffer: kind 0 f32, 1 fp16, 2 bf16 ; NHWC with channel pitch dbg_pitch
   const void* dbg_ptr = nullptr; int dbg_kind = 0; long long dbg_n = 0; int dbg_h = 0, dbg_w = 0, dbg_c = 0, dbg_pitch = 0;
@@ -98,6 +108,12 @@ inline void net_mark(Ctx* c, bool on) {
 int net_tail_fp32(Ctx* c, const float* feat, float* scratch, long long m, float* d_preds_out, bool mark);
 int net_upload(Ctx* c, const std::vector<float>& v, float** dptr);
 int net_tail_tc(Ctx* c, const float* feat, float* scratch, long long m, float* d_preds_out, bool mark);
+// fp32-grade path (net_path 4): split-fp16 tensor-core GEMMs (net_lstm_tc.cu), fp32 recurrence (net.cu)
+int net_tail_precise(Ctx* c, const float* feat, float* scratch, long long m, float* d_preds_out, bool mark);
+int net_pack_split_b(Ctx* c, const float* w, int K, int n_src, int N, __half** out);
+int net_gemm_split(Ctx* c, const float* A, int lda, const __half* Bp, const float* bias, float* C, int ldc, long long M, int N, int K, int n_valid,
+                   int act);
+int net_lstm_rec_fp32(Ctx* c, const float* xz, const float* whh, float* out, long long m, int Tn);
 int net_tc_prepare(Ctx* c, int fmt);
 int net_calibrate(Ctx* c, int64_t max_snippets);
 int net_forward_tc(Ctx* c, const float* d_in, int input_mode, int64_t first, int64_t n, float* d_preds);

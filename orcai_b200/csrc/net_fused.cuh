@@ -56,9 +56,17 @@ __host__ __device__ constexpr int pow2cols(int c) { return c <= 32 ? 32 : c <= 6
 //        load off that cycle: 1.18 -> 1.12 ms per 10 min of audio.  (Also tried: issuing the residual MMA after the tiles so
 //        that the first convolution does not wait for the pooling epilogue of step g-2 - it then competes with the second
 //        convolution of step g, which is on the critical path: 1.12 -> 1.25 ms.)
-template <int CIN_, int COUT_, int CPOOL_, int S_, bool RELU_OUT_, int CTAS_, int NEW_, bool CONV0_ = false, int ISS_ = 1, int XBUF_ = 1>
+// PREC_: fp32-grade arithmetic on the fp16 tensor cores.  Every operand is the pair (hi, lo) = (fp16(v), fp16(v - hi)), exact to
+//        2^-22, and every product runs as  A_hi*W_hi + A_lo*W_hi + A_hi*W_lo  into the same fp32 accumulator (the dropped
+//        A_lo*W_lo term is 2^-22 relative): the X / R / S1 / S2 buffers, the weight set and the activation tensors in HBM all
+//        come as a hi plane set followed by a lo plane set.  Why: fp16 operands alone put the probabilities 2.7e-3 from the
+//        fp32 graph (tools/precision_plan.py: every weight tensor and every stored activation contributes 2e-4 .. 2e-3).
+template <int CIN_, int COUT_, int CPOOL_, int S_, bool RELU_OUT_, int CTAS_, int NEW_, bool CONV0_ = false, int ISS_ = 1, int XBUF_ = 1, bool PREC_ = false>
 struct FB {
   static constexpr int XBUF = XBUF_;
+  static constexpr bool PREC = PREC_;
+  static constexpr int PL = PREC_ ? 2 : 1;           // operand plane sets: hi (, lo)
+  static_assert(!(PREC_ && CONV0_), "the in-kernel entry convolution writes single fp16 operands");
   static_assert(XBUF_ == 1 || (XBUF_ == 2 && ISS_ == 2 && !CONV0_), "two X buffers: two-issuer TMA configuration only");
   static constexpr int CIN = CIN_, COUT = COUT_, CP = CPOOL_, S = S_, CTAS = CTAS_, NEW = NEW_, ISS = ISS_;
   static constexpr bool RELU_OUT = RELU_OUT_, CONV0 = CONV0_;
@@ -93,23 +101,26 @@ struct FB {
   static constexpr uint32_t W1_BYTES = 9 * TAP_W1 + 128, W2_BYTES = 9 * TAP_W2 + 128, WR_BYTES = TAP_W1 + 128;
   static constexpr uint32_t WB_BYTES = NG * 128 + 128;   // [bias_hi, bias_lo] rows of one GEMM: n-groups of one k-chunk
   static constexpr uint32_t OFF_W1 = 0, OFF_W2 = OFF_W1 + W1_BYTES, OFF_WR = OFF_W2 + W2_BYTES;
-  static constexpr uint32_t OFF_WB1 = OFF_WR + WR_BYTES, OFF_WB2 = OFF_WB1 + WB_BYTES, OFF_WBR = OFF_WB2 + WB_BYTES;
+  static constexpr uint32_t WSET = OFF_WR + WR_BYTES;        // one weight set [sep1 | sep2 | residual]; PREC: the lo set follows
+  static constexpr uint32_t W_LO = PREC_ ? WSET : 0;
+  static constexpr uint32_t OFF_WB1 = WSET * PL, OFF_WB2 = OFF_WB1 + WB_BYTES, OFF_WBR = OFF_WB2 + WB_BYTES;
   static constexpr uint32_t OFF_ONES = OFF_WBR + WB_BYTES;   // two 8x8 core matrices: k = 0,1 are 1.0, the rest 0 (SBO = 0)
   static constexpr uint32_t W_BYTES = OFF_ONES + 256;
   static constexpr uint32_t OFF_R = W_BYTES;
-  static constexpr uint32_t OFF_X = OFF_R + XCH * LBO_R;
-  static constexpr uint32_t XR_BYTES = XCH * LBO_R + XCH * LBO_X;        // one R + X buffer; buffer b sits b * XR_BYTES further
-  static constexpr uint32_t OFF_S1 = OFF_X + XCH * LBO_X + (XBUF - 1) * XR_BYTES;
-  static constexpr uint32_t OFF_S2 = OFF_S1 + MCH * LBO_S1;
+  static constexpr uint32_t R_LO = XCH * LBO_R, X_LO = XCH * LBO_X, S1_LO = MCH * LBO_S1, S2_LO = NG * LBO_S2;   // hi -> lo plane set
+  static constexpr uint32_t OFF_X = OFF_R + PL * XCH * LBO_R;
+  static constexpr uint32_t XR_BYTES = PL * (XCH * LBO_R + XCH * LBO_X);        // one R + X buffer; buffer b sits b * XR_BYTES further
+  static constexpr uint32_t OFF_S1 = OFF_X + PL * XCH * LBO_X + (XBUF - 1) * XR_BYTES;
+  static constexpr uint32_t OFF_S2 = OFF_S1 + PL * MCH * LBO_S1;
   // entry-convolution input: two (S+5) x SPW fp16 tiles of the normalised spectrogram (rows a-1 .. a+S+3, columns cb-1 ..)
   static constexpr int SPW = 64, SPH = S + 5;
   static constexpr uint32_t SPEC_BYTES = CONV0 ? SPH * SPW * 2 : 0;
-  static constexpr uint32_t OFF_SPEC = OFF_S2 + NG * LBO_S2;
+  static constexpr uint32_t OFF_SPEC = OFF_S2 + PL * NG * LBO_S2;
   static constexpr uint32_t OFF_BAR = OFF_SPEC + 2 * ((SPEC_BYTES + 127) / 128 * 128);
   // barriers: bar1[N1] bar2[N2] barR[2] s1_full[N1] pool_done x_full[2] x_free[2] spec_full[2]
   static constexpr int B_1 = 0, B_2 = N1, B_R = N1 + N2, B_S1 = N1 + N2 + 2, B_P = 2 * N1 + N2 + 2, B_X = B_P + 1, B_XF = B_X + 2, B_SP = B_XF + 2, NBAR = B_SP + 2;
   static constexpr uint32_t SMEM = OFF_BAR + NBAR * 8 + 16;
-  static constexpr uint32_t TX_BYTES = XG * ((S + 2) * WP + (S / 2) * CP) * 16;   // bytes one step's TMA loads deliver
+  static constexpr uint32_t TX_BYTES = PL * XG * ((S + 2) * WP + (S / 2) * CP) * 16;   // bytes one step's TMA loads deliver
   static constexpr int COL_R = 0, COL_1 = 2 * NP, COL_2 = 2 * NP + N1 * NP;
   static constexpr int TM_COLS = pow2cols(NP * (2 + N1 + N2));
   static_assert(NEW == 8 || NEW == 16, "worker warps come in groups of four (one per TMEM lane quadrant)");
@@ -202,6 +213,30 @@ __device__ __forceinline__ uint4 pack8h(const float* v) {
   for (int i = 0; i < 4; ++i) h[i] = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
   return r;
 }
+// (hi, lo) = (fp16(v), fp16(v - hi)): v to 2^-22
+__device__ __forceinline__ void split8h(const float* v, uint4& hi, uint4& lo) {
+  hi = pack8h(v);
+  const __half2* h = reinterpret_cast<const __half2*>(&hi);
+  float r[8];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 f = __half22float2(h[i]);
+    r[2 * i] = v[2 * i] - f.x;
+    r[2 * i + 1] = v[2 * i + 1] - f.y;
+  }
+  lo = pack8h(r);
+}
+// elementwise max of m[8] with the values (hi + lo)
+__device__ __forceinline__ void fmax8_split(float (&m)[8], uint4 hi, uint4 lo) {
+  const __half2* h = reinterpret_cast<const __half2*>(&hi);
+  const __half2* l = reinterpret_cast<const __half2*>(&lo);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 a = __half22float2(h[i]), b = __half22float2(l[i]);
+    m[2 * i] = fmaxf(m[2 * i], a.x + b.x);
+    m[2 * i + 1] = fmaxf(m[2 * i + 1], a.y + b.y);
+  }
+}
 __device__ __forceinline__ uint4 hmax8(uint4 a, uint4 b) {
   __half2* x = reinterpret_cast<__half2*>(&a);
   const __half2* y = reinterpret_cast<const __half2*>(&b);
@@ -214,7 +249,9 @@ template <class G>
 __global__ void __launch_bounds__(G::NTHREADS, G::CTAS)
 fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmR, int r_step, __half* __restrict__ Yr,
                    __half* __restrict__ Ysub, int H, int W, int n_strips, long long n_items,
-                   const unsigned char* __restrict__ wpack) {
+                   const unsigned char* __restrict__ wpack,
+                   // PREC: maps of the lo tensors; Yr / Ysub are then fp32 arrays
+                   const __grid_constant__ CUtensorMap tmXl, const __grid_constant__ CUtensorMap tmRl) {
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G::OFF_BAR);
   uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + G::NBAR);
@@ -358,6 +395,10 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
             tma_load_5d(sbase + G::OFF_X + xb * G::XR_BYTES + c * G::LBO_X, &tmX, &bars[G::B_X + xb], 0, c, cb, a + 1, (int)b);
             // residual input pixels (2*ho, 2*wo): coordinates in the even-position tensor, or in the full tensor read with stride 2
             tma_load_5d(sbase + G::OFF_R + xb * G::XR_BYTES + c * G::LBO_R, &tmR, &bars[G::B_X + xb], 0, c, wo0 * r_step, (a >> 1) * r_step, (int)b);
+            if constexpr (G::PREC) {
+              tma_load_5d(sbase + G::OFF_X + G::X_LO + xb * G::XR_BYTES + c * G::LBO_X, &tmXl, &bars[G::B_X + xb], 0, c, cb, a + 1, (int)b);
+              tma_load_5d(sbase + G::OFF_R + G::R_LO + xb * G::XR_BYTES + c * G::LBO_R, &tmRl, &bars[G::B_X + xb], 0, c, wo0 * r_step, (a >> 1) * r_step, (int)b);
+            }
           }
         }
         __syncwarp();
@@ -381,6 +422,14 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       const uint64_t dB1 = make_smem_desc(sbase + G::OFF_WB1, 128, 128);
       const uint64_t dB2 = make_smem_desc(sbase + G::OFF_WB2, 128, 128);
       const uint64_t dBR = make_smem_desc(sbase + G::OFF_WBR, 128, 128);
+      // one operand product; PREC: A_hi*W_hi + A_lo*W_hi + A_hi*W_lo (a_lo / G::W_LO: hi -> lo plane set, 16-byte units)
+      auto mma_x = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t a_lo) {
+        mma_f16_ss(d, a, b, idesc, 1);
+        if constexpr (G::PREC) {
+          mma_f16_ss(d, a + a_lo, b, idesc, 1);
+          mma_f16_ss(d, a, b + (G::W_LO >> 4), idesc, 1);
+        }
+      };
       if constexpr (G::ISS == 1) {
         auto issue_first = [&](long long g) {   // residual 1x1 and first separable convolution of step g
           if (elect_one()) {
@@ -388,7 +437,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
             mma_f16_ss(colr, dOnes, dBR, idesc, 0);
 #pragma unroll
             for (int ks = 0; ks < G::KP1 / 16; ++ks)
-              mma_f16_ss(colr, dR + ((2 * ks * G::LBO_R) >> 4), dWR + ((2 * ks * 128) >> 4), idesc, 1);
+              mma_x(colr, dR + ((2 * ks * G::LBO_R) >> 4), dWR + ((2 * ks * 128) >> 4), G::R_LO >> 4);
             mma_commit(&bars[G::B_R + (int)(g & 1)]);
 #pragma unroll
             for (int t = 0; t < G::N1; ++t) {
@@ -398,8 +447,8 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                 const uint32_t aoff = (uint32_t)(G::P1_0 + 128 * t - 2 * G::WP - 1 + (tap / 3) * G::WP + (tap % 3));   // pixels = 16-byte units
 #pragma unroll
                 for (int ks = 0; ks < G::KP1 / 16; ++ks)
-                  mma_f16_ss(tmem + G::COL_1 + t * G::NP, dX + aoff + ((2 * ks * G::LBO_X) >> 4),
-                             dW1 + ((tap * G::TAP_W1 + 2 * ks * 128) >> 4), idesc, 1);
+                  mma_x(tmem + G::COL_1 + t * G::NP, dX + aoff + ((2 * ks * G::LBO_X) >> 4),
+                        dW1 + ((tap * G::TAP_W1 + 2 * ks * 128) >> 4), G::X_LO >> 4);
               }
               mma_commit(&bars[G::B_1 + t]);
             }
@@ -424,8 +473,8 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                 const uint32_t aoff = (uint32_t)(G::P2_0 + 128 * t - G::WP - 1 + (tap / 3) * G::WP + (tap % 3));
 #pragma unroll
                 for (int ks = 0; ks < G::NP / 16; ++ks)
-                  mma_f16_ss(tmem + G::COL_2 + t * G::NP, dS1 + aoff + ((2 * ks * G::LBO_S1) >> 4),
-                             dW2 + ((tap * G::TAP_W2 + 2 * ks * 128) >> 4), idesc, 1);
+                  mma_x(tmem + G::COL_2 + t * G::NP, dS1 + aoff + ((2 * ks * G::LBO_S1) >> 4),
+                        dW2 + ((tap * G::TAP_W2 + 2 * ks * 128) >> 4), G::S1_LO >> 4);
               }
               mma_commit(&bars[G::B_2 + t]);
             }
@@ -454,7 +503,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
             mma_f16_ss(colr, dOnes, dBR, idesc, 0);
 #pragma unroll
             for (int ks = 0; ks < G::KP1 / 16; ++ks)
-              mma_f16_ss(colr, dRb + ((2 * ks * G::LBO_R) >> 4), dWR + ((2 * ks * 128) >> 4), idesc, 1);
+              mma_x(colr, dRb + ((2 * ks * G::LBO_R) >> 4), dWR + ((2 * ks * 128) >> 4), G::R_LO >> 4);
             mma_commit(&bars[G::B_R + (int)(g & 1)]);
           }
           __syncwarp();
@@ -471,8 +520,8 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                 const uint32_t aoff = (uint32_t)(G::P1_0 + 128 * t - 2 * G::WP - 1 + (tap / 3) * G::WP + (tap % 3));   // pixels = 16-byte units
 #pragma unroll
                 for (int ks = 0; ks < G::KP1 / 16; ++ks)
-                  mma_f16_ss(tmem + G::COL_1 + t * G::NP, dXb + aoff + ((2 * ks * G::LBO_X) >> 4),
-                             dW1 + ((tap * G::TAP_W1 + 2 * ks * 128) >> 4), idesc, 1);
+                  mma_x(tmem + G::COL_1 + t * G::NP, dXb + aoff + ((2 * ks * G::LBO_X) >> 4),
+                        dW1 + ((tap * G::TAP_W1 + 2 * ks * 128) >> 4), G::X_LO >> 4);
               }
               mma_commit(&bars[G::B_1 + t]);
               if (G::XBUF == 2 && t == G::N1 - 1) mma_commit(&bars[G::B_XF + xb]);   // this step's X / R buffer may be reloaded
@@ -499,8 +548,8 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                 const uint32_t aoff = (uint32_t)(G::P2_0 + 128 * t - G::WP - 1 + (tap / 3) * G::WP + (tap % 3));
 #pragma unroll
                 for (int ks = 0; ks < G::NP / 16; ++ks)
-                  mma_f16_ss(tmem + G::COL_2 + t * G::NP, dS1 + aoff + ((2 * ks * G::LBO_S1) >> 4),
-                             dW2 + ((tap * G::TAP_W2 + 2 * ks * 128) >> 4), idesc, 1);
+                  mma_x(tmem + G::COL_2 + t * G::NP, dS1 + aoff + ((2 * ks * G::LBO_S1) >> 4),
+                        dW2 + ((tap * G::TAP_W2 + 2 * ks * 128) >> 4), G::S1_LO >> 4);
               }
               mma_commit(&bars[G::B_2 + t]);
             }
@@ -541,6 +590,34 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
             if (u == 1 && !has1) break;
             const int gg = g0 + u;
             const unsigned char* s2 = smem + G::OFF_S2 + gg * G::LBO_S2 + p00 * 16;
+            const size_t o_full = (((size_t)pb * Ho + ho) * Wo + wo) * G::OCP + gg * 8;
+            const size_t o_sub = (((size_t)pb * Hs + (ho >> 1)) * Ws + (wo >> 1)) * G::OCP + gg * 8;
+            const bool sub = Ysub != nullptr && !(ho & 1) && !(wo & 1);
+            if constexpr (G::PREC) {
+              float y[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) y[i] = -INFINITY;
+#pragma unroll
+              for (int q = 0; q < 6; ++q) {
+                const uint32_t off = (uint32_t)((q >> 1) * (G::WP / 2) + (q & 1) * G::S2HALF) * 16;
+                fmax8_split(y, *reinterpret_cast<const uint4*>(s2 + off), *reinterpret_cast<const uint4*>(s2 + G::S2_LO + off));
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) y[i] += r[8 * u + i];
+              // PREC blocks hand fp32 tensors to the next stage (Yr / Ysub are float arrays of the same shape)
+              float* yf = reinterpret_cast<float*>(Yr) + o_full;
+              if (sub) {
+                float* ys = reinterpret_cast<float*>(Ysub) + o_sub;
+                reinterpret_cast<float4*>(ys)[0] = make_float4(y[0], y[1], y[2], y[3]);
+                reinterpret_cast<float4*>(ys)[1] = make_float4(y[4], y[5], y[6], y[7]);
+              }
+              if (G::RELU_OUT) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) y[i] = fmaxf(y[i], 0.f);
+              }
+              reinterpret_cast<float4*>(yf)[0] = make_float4(y[0], y[1], y[2], y[3]);
+              reinterpret_cast<float4*>(yf)[1] = make_float4(y[4], y[5], y[6], y[7]);
+            } else {
             uint4 m = *reinterpret_cast<const uint4*>(s2);
             m = hmax8(m, *reinterpret_cast<const uint4*>(s2 + G::S2HALF * 16));
             m = hmax8(m, *reinterpret_cast<const uint4*>(s2 + (G::WP / 2) * 16));
@@ -556,9 +633,9 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
               y[2 * i + 1] = f.y + r[8 * u + 2 * i + 1];
             }
             const uint4 yp = pack8h(y);
-            *reinterpret_cast<uint4*>(Yr + (((size_t)pb * Ho + ho) * Wo + wo) * G::OCP + gg * 8) = G::RELU_OUT ? relu8h(yp) : yp;
-            if (Ysub != nullptr && !(ho & 1) && !(wo & 1))
-              *reinterpret_cast<uint4*>(Ysub + (((size_t)pb * Hs + (ho >> 1)) * Ws + (wo >> 1)) * G::OCP + gg * 8) = yp;
+            *reinterpret_cast<uint4*>(Yr + o_full) = G::RELU_OUT ? relu8h(yp) : yp;
+            if (sub) *reinterpret_cast<uint4*>(Ysub + o_sub) = yp;
+            }
           }
         }
       }
@@ -593,8 +670,22 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
             if (p1 < (G::S + 2) * G::WP) {
               const uint4 z = make_uint4(0, 0, 0, 0);
               unsigned char* dst = smem + G::OFF_S1 + g0 * G::LBO_S1 + p1 * 16;
+              if constexpr (G::PREC) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = inimg ? fmaxf(v[i], 0.f) : 0.f;
+                uint4 hi, lo;
+                split8h(v, hi, lo);
+                *reinterpret_cast<uint4*>(dst) = hi;
+                *reinterpret_cast<uint4*>(dst + G::S1_LO) = lo;
+                if (has1) {
+                  split8h(v + 8, hi, lo);
+                  *reinterpret_cast<uint4*>(dst + G::LBO_S1) = hi;
+                  *reinterpret_cast<uint4*>(dst + G::LBO_S1 + G::S1_LO) = lo;
+                }
+              } else {
               *reinterpret_cast<uint4*>(dst) = inimg ? relu8h(pack8h(v)) : z;
               if (has1) *reinterpret_cast<uint4*>(dst + G::LBO_S1) = inimg ? relu8h(pack8h(v + 8)) : z;
+              }
             }
           }
           fence_proxy_async();
@@ -609,7 +700,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
           if (warp == 0) FB_TRACE(21, g);
           worker_sync<G::NWORK>();   // pooling has finished reading S2
           if (prev_carry) {
-            for (int i = tid; i < G::NG * G::WP; i += G::NWORK) {
+            for (int i = tid; i < G::PL * G::NG * G::WP; i += G::NWORK) {   // the lo plane set follows the hi set
               const int gq = i / G::WP, px = i - gq * G::WP;
               const int hp = px / (G::WP / 2), cc = px - hp * (G::WP / 2);   // half-plane (column parity), column / 2
               unsigned char* p = smem + G::OFF_S2 + gq * G::LBO_S2 + (hp * G::S2HALF + cc) * 16;
@@ -634,8 +725,21 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
             if (p2 < (G::S + 1) * G::WP) {
               const uint4 ninf = make_uint4(0xFC00FC00u, 0xFC00FC00u, 0xFC00FC00u, 0xFC00FC00u);
               unsigned char* dst = smem + G::OFF_S2 + g0 * G::LBO_S2 + ((c2[t] & 1) * G::S2HALF + y2[t] * (G::WP / 2) + (c2[t] >> 1)) * 16;
+              if constexpr (G::PREC) {
+                const uint4 z = make_uint4(0, 0, 0, 0);
+                uint4 hi, lo;
+                split8h(v, hi, lo);
+                *reinterpret_cast<uint4*>(dst) = inimg ? hi : ninf;
+                *reinterpret_cast<uint4*>(dst + G::S2_LO) = inimg ? lo : z;
+                if (has1) {
+                  split8h(v + 8, hi, lo);
+                  *reinterpret_cast<uint4*>(dst + G::LBO_S2) = inimg ? hi : ninf;
+                  *reinterpret_cast<uint4*>(dst + G::LBO_S2 + G::S2_LO) = inimg ? lo : z;
+                }
+              } else {
               *reinterpret_cast<uint4*>(dst) = inimg ? pack8h(v) : ninf;
               if (has1) *reinterpret_cast<uint4*>(dst + G::LBO_S2) = inimg ? pack8h(v + 8) : ninf;
+              }
             }
           }
         }
@@ -646,8 +750,9 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         // ---- carry the S1 overlap rows into the next step (rows above the next strip's first row are zero) ----
         const bool carry = step + 1 < n_steps;
         if (g + 1 < total_steps) {
-          for (int i = tid; i < G::NG * 2 * G::WP; i += G::NWORK) {
-            const int gq = i / (2 * G::WP), px = i - gq * 2 * G::WP;
+          for (int i = tid; i < G::PL * G::NG * 2 * G::WP; i += G::NWORK) {
+            const int gs = i / (2 * G::WP), px = i - gs * 2 * G::WP;
+            const int gq = gs % G::NG + (gs / G::NG) * G::MCH;   // lo planes sit MCH planes after the hi planes
             unsigned char* p = smem + G::OFF_S1 + gq * G::LBO_S1 + px * 16;
             *reinterpret_cast<uint4*>(p) = carry ? *reinterpret_cast<const uint4*>(p + G::S * G::WP * 16) : make_uint4(0, 0, 0, 0);
           }

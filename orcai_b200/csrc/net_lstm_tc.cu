@@ -62,11 +62,15 @@ __device__ __forceinline__ uint4 pack8h(const float* v) {
 // ------------------------------------------------------------------------------------------------
 constexpr int kGM = 128, kGK = 64;   // rows per CTA, K per pipeline stage
 
-template <int BN>
+// SPLIT: both operands as (hi, lo) fp16 pairs, three MMAs per K step (A_hi*B_hi + A_lo*B_hi + A_hi*B_lo): fp32-grade products
+// on the fp16 tensor cores.  A stage = [A_hi | A_lo], B block = [B_hi | B_lo].
+template <int BN, bool SPLIT = false>
 struct GemmSmem {
-  static constexpr uint32_t A_STAGE = kGM * kGK * 2, B_STAGE = BN * kGK * 2;
+  static constexpr uint32_t A_HALF = kGM * kGK * 2, B_HALF = BN * kGK * 2;
+  static constexpr uint32_t A_STAGE = A_HALF * (SPLIT ? 2 : 1), B_STAGE = B_HALF * (SPLIT ? 2 : 1);
   static constexpr uint32_t OFF_A = 0, OFF_B = 2 * A_STAGE, OFF_BAR = OFF_B + 2 * B_STAGE;
   static constexpr uint32_t BYTES = OFF_BAR + 8 * 8 + 16;
+  static constexpr int CTAS = BYTES <= 110 * 1024 ? 2 : 1;
 };
 
 // one K-chunk (64 elements) of an A row as fp16, 8 x 16 bytes; `valid` = readable elements from p (multiple of 4 / 8)
@@ -80,17 +84,38 @@ __device__ __forceinline__ void stage_row(const float* p, int valid, uint4 (&out
     out[j] = pack8h(f);
   }
 }
+// the same chunk as (hi, lo) pairs
+__device__ __forceinline__ void stage_row_split(const float* p, int valid, uint4 (&hi)[kGK / 8], uint4 (&lo)[kGK / 8]) {
+  float4 v[kGK / 4];
+#pragma unroll
+  for (int q = 0; q < kGK / 4; ++q) v[q] = 4 * q + 4 <= valid ? __ldg(reinterpret_cast<const float4*>(p) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int j = 0; j < kGK / 8; ++j) {
+    const float f[8] = {v[2 * j].x, v[2 * j].y, v[2 * j].z, v[2 * j].w, v[2 * j + 1].x, v[2 * j + 1].y, v[2 * j + 1].z, v[2 * j + 1].w};
+    hi[j] = pack8h(f);
+    const __half2* h = reinterpret_cast<const __half2*>(&hi[j]);
+    float r[8];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 g = __half22float2(h[i]);
+      r[2 * i] = f[2 * i] - g.x;
+      r[2 * i + 1] = f[2 * i + 1] - g.y;
+    }
+    lo[j] = pack8h(r);
+  }
+}
 __device__ __forceinline__ void stage_row(const __half* p, int valid, uint4 (&out)[kGK / 8]) {
 #pragma unroll
   for (int j = 0; j < kGK / 8; ++j) out[j] = 8 * j + 8 <= valid ? __ldg(reinterpret_cast<const uint4*>(p) + j) : make_uint4(0, 0, 0, 0);
 }
 
-// ACT: 0 none, 1 relu.  grid = (N / BN, ceil(M / 128)), block = 160 (4 worker warps + issuer warp)
-template <typename TA, int BN, int ACT>
-__global__ void __launch_bounds__(160, 2)
+// ACT: 0 none, 1 relu.  grid = (ceil(M / 128), N / BN), block = 160 (4 worker warps + issuer warp).  Columns >= n_valid
+// (a multiple of 4) of a row are not stored.
+template <typename TA, int BN, int ACT, bool SPLIT = false>
+__global__ void __launch_bounds__(160, (GemmSmem<BN, SPLIT>::CTAS))
 gemm_tc_kernel(const TA* __restrict__ A, int lda, const __half* __restrict__ Bp, const float* __restrict__ bias,
-               float* __restrict__ C, int ldc, long long M, int K) {
-  using S = GemmSmem<BN>;
+               float* __restrict__ C, int ldc, long long M, int K, int n_valid) {
+  using S = GemmSmem<BN, SPLIT>;
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);   // full_a[2] full_b[2] free[2] acc
   uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 7);
@@ -110,8 +135,8 @@ gemm_tc_kernel(const TA* __restrict__ A, int lda, const __half* __restrict__ Bp,
   tc_fence_after();
   const uint32_t tmem = *tslot;
   const uint32_t sbase = smem_u32(smem);
-  const long long row0 = (long long)blockIdx.y * kGM;
-  const int nt = blockIdx.x;
+  const long long row0 = (long long)blockIdx.x * kGM;   // row tiles along x: their count exceeds the 65 535 limit of grid.y
+  const int nt = blockIdx.y;
 
   if (warp == 4) {
     constexpr uint32_t idesc = make_idesc_f16(128, BN, 0);
@@ -125,8 +150,13 @@ gemm_tc_kernel(const TA* __restrict__ A, int lda, const __half* __restrict__ Bp,
         const uint64_t da = make_smem_desc(sbase + S::OFF_A + s * S::A_STAGE, kGM * 16, 128);
         const uint64_t db = make_smem_desc(sbase + S::OFF_B + s * S::B_STAGE, 128, (kGK / 8) * 128);
 #pragma unroll
-        for (int ks = 0; ks < kGK / 16; ++ks)
+        for (int ks = 0; ks < kGK / 16; ++ks) {
           mma_f16_ss(tmem, da + ((2 * ks * kGM * 16) >> 4), db + ((2 * ks * 128) >> 4), idesc, (kc | ks) != 0);
+          if constexpr (SPLIT) {
+            mma_f16_ss(tmem, da + ((S::A_HALF + 2 * ks * kGM * 16) >> 4), db + ((2 * ks * 128) >> 4), idesc, 1);
+            mma_f16_ss(tmem, da + ((2 * ks * kGM * 16) >> 4), db + ((S::B_HALF + 2 * ks * 128) >> 4), idesc, 1);
+          }
+        }
         mma_commit(&bars[4 + s]);
         if (kc == nkc - 1) mma_commit(&bars[6]);
       }
@@ -146,7 +176,14 @@ gemm_tc_kernel(const TA* __restrict__ A, int lda, const __half* __restrict__ Bp,
       unsigned char* dst = smem + S::OFF_A + s * S::A_STAGE + row * 16;
       // all loads of the chunk are issued before the first conversion (one memory round trip per chunk, not eight)
       uint4 staged[kGK / 8];
-      stage_row(arow + kc * kGK, row_ok ? K - kc * kGK : 0, staged);
+      if constexpr (SPLIT) {
+        uint4 staged_lo[kGK / 8];
+        stage_row_split(arow + kc * kGK, row_ok ? K - kc * kGK : 0, staged, staged_lo);
+#pragma unroll
+        for (int j = 0; j < kGK / 8; ++j) *reinterpret_cast<uint4*>(dst + S::A_HALF + j * (kGM * 16)) = staged_lo[j];
+      } else {
+        stage_row(arow + kc * kGK, row_ok ? K - kc * kGK : 0, staged);
+      }
 #pragma unroll
       for (int j = 0; j < kGK / 8; ++j) *reinterpret_cast<uint4*>(dst + j * (kGM * 16)) = staged[j];
       fence_proxy_async();
@@ -168,7 +205,8 @@ gemm_tc_kernel(const TA* __restrict__ A, int lda, const __half* __restrict__ Bp,
       }
       if (row_ok) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q) reinterpret_cast<float4*>(crow + c0)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        for (int q = 0; q < 4; ++q)
+          if (nt * BN + c0 + 4 * q + 4 <= n_valid) reinterpret_cast<float4*>(crow + c0)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
       }
     }
   }
@@ -355,17 +393,25 @@ dense_out_kernel(const float* __restrict__ d1, const float* __restrict__ w2, con
 
 // ---- host side ----------------------------------------------------------------------------------
 // B operand blocks of gemm_tc_kernel: [n-tile][k-chunk][BN x 64] canonical K-major (SBO = 8 chunks)
-std::vector<__half> pack_gemm_b(const float* w, int K, int N, int BN) {   // w: [K][N] row-major (Keras kernel layout)
+// split: every block is [hi | lo] (GemmSmem<BN, true>).  w has n_src columns (ldw apart); columns n_src .. N-1 of the operand are zero
+std::vector<__half> pack_gemm_b(const float* w, int K, int N, int BN, bool split = false, int n_src = -1, int ldw = -1) {   // w: [K][N] row-major (Keras kernel layout)
+  if (n_src < 0) n_src = N;
+  if (ldw < 0) ldw = n_src;
   const int nkc = (K + kGK - 1) / kGK, ntiles = N / BN;
-  std::vector<__half> out((size_t)ntiles * nkc * BN * kGK, __float2half_rn(0.f));
+  const size_t half_blk = (size_t)BN * kGK, blk_sz = half_blk * (split ? 2 : 1);
+  std::vector<__half> out((size_t)ntiles * nkc * blk_sz, __float2half_rn(0.f));
   for (int nt = 0; nt < ntiles; ++nt)
     for (int kc = 0; kc < nkc; ++kc) {
-      __half* blk = out.data() + ((size_t)nt * nkc + kc) * BN * kGK;
+      __half* blk = out.data() + ((size_t)nt * nkc + kc) * blk_sz;
       for (int nn = 0; nn < BN; ++nn)
         for (int kk = 0; kk < kGK; ++kk) {
           const int k = kc * kGK + kk, n = nt * BN + nn;
-          if (k >= K) continue;
-          blk[((size_t)(nn / 8) * (kGK / 8) * 128 + (size_t)(kk / 8) * 128 + (nn % 8) * 16 + (kk % 8) * 2) / 2] = __float2half_rn(w[(size_t)k * N + n]);
+          if (k >= K || n >= n_src) continue;
+          const size_t at = ((size_t)(nn / 8) * (kGK / 8) * 128 + (size_t)(kk / 8) * 128 + (nn % 8) * 16 + (kk % 8) * 2) / 2;
+          const float v = w[(size_t)k * ldw + n];
+          const __half hi = __float2half_rn(v);
+          blk[at] = hi;
+          if (split) blk[half_blk + at] = __float2half_rn(v - __half2float(hi));
         }
     }
   return out;
@@ -380,17 +426,18 @@ int upload_half(Ctx* c, const std::vector<__half>& v, __half** out) {
   return ORCAI_OK;
 }
 
-template <typename TA, int BN, int ACT>
-int run_gemm_tc(Ctx* c, const TA* A, int lda, const __half* Bp, const float* bias, float* C, int ldc, long long M, int N, int K) {
-  using S = GemmSmem<BN>;
+template <typename TA, int BN, int ACT, bool SPLIT = false>
+int run_gemm_tc(Ctx* c, const TA* A, int lda, const __half* Bp, const float* bias, float* C, int ldc, long long M, int N, int K, int n_valid = -1) {
+  using S = GemmSmem<BN, SPLIT>;
   // the attribute is per device: remember which devices have it (several contexts can live in one process)
   static std::atomic<unsigned long long> attr_devices{0ull};
   if (!((attr_devices.load() >> (c->device & 63)) & 1ull)) {
-    ORCAI_CUDA(c, cudaFuncSetAttribute(gemm_tc_kernel<TA, BN, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::BYTES));
+    ORCAI_CUDA(c, cudaFuncSetAttribute(gemm_tc_kernel<TA, BN, ACT, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)S::BYTES));
     attr_devices.fetch_or(1ull << (c->device & 63));
   }
-  dim3 grid((unsigned)(N / BN), (unsigned)((M + kGM - 1) / kGM));
-  gemm_tc_kernel<TA, BN, ACT><<<grid, 160, S::BYTES, c->stream>>>(A, lda, Bp, bias, C, ldc, M, K);
+  if (M <= 0) return ORCAI_OK;
+  dim3 grid((unsigned)((M + kGM - 1) / kGM), (unsigned)(N / BN));
+  gemm_tc_kernel<TA, BN, ACT, SPLIT><<<grid, 160, S::BYTES, c->stream>>>(A, lda, Bp, bias, C, ldc, M, K, n_valid < 0 ? N : n_valid);
   c->launches++;
   ORCAI_CUDA(c, cudaGetLastError());
   return ORCAI_OK;
@@ -444,6 +491,63 @@ int net_tail_tc_prepare(Ctx* c) {
   }
   ORCAI_CUDA(c, cudaFuncSetAttribute(lstm_rec_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kRecSmem));
   nw->tail_tc_ready = true;
+  return ORCAI_OK;
+}
+
+// ---- fp32-grade products on the fp16 tensor cores (net_path 4) -----------------------------------
+// device copy of the packed split B operand (BN = 64) of a [K][n_src] row-major weight matrix, N columns (multiple of 64)
+int net_pack_split_b(Ctx* c, const float* w, int K, int n_src, int N, __half** out) {
+  return upload_half(c, pack_gemm_b(w, K, N, 64, true, n_src, n_src), out);
+}
+
+// C[M, ldc] = act(A[M, lda] * W + bias), act 0 none / 1 relu; columns >= n_valid are not stored; bias holds N floats
+int net_gemm_split(Ctx* c, const float* A, int lda, const __half* Bp, const float* bias, float* C, int ldc, long long M, int N, int K, int n_valid,
+                   int act) {
+  if (act == 1) return run_gemm_tc<float, 64, 1, true>(c, A, lda, Bp, bias, C, ldc, M, N, K, n_valid);
+  return run_gemm_tc<float, 64, 0, true>(c, A, lda, Bp, bias, C, ldc, M, N, K, n_valid);
+}
+
+int net_tail_precise_prepare(Ctx* c) {
+  NetWeights* nw = c->net;
+  if (nw->tail_precise_ready) return ORCAI_OK;
+  const int U = nw->U, G = 4 * U;
+  for (int l = 0; l < 2; ++l) {
+    const int I = l == 0 ? nw->feat : 2 * U;
+    ORCAI_CHECK(net_pack_split_b(c, nw->h_lstm_wih[l].data(), I, 2 * G, 2 * G, &nw->tp_wih[l]));
+  }
+  ORCAI_CHECK(net_pack_split_b(c, nw->h_d1_w.data(), 2 * U, 128, 128, &nw->tp_d1));
+  nw->tail_precise_ready = true;
+  return ORCAI_OK;
+}
+
+// LSTM x2 + dense head at fp32 grade: split-fp16 tensor-core GEMMs for the input projections and Dense(128), the fp32 CUDA-core
+// recurrence of the reference-grade path (W_hh as (hi, lo) would need 256 KB of shared memory per CTA).  Scratch as net_tail_fp32.
+int net_tail_precise(Ctx* c, const float* feat, float* scratch, long long m, float* d_preds_out, bool mk) {
+  NetWeights* nw = c->net;
+  ORCAI_CHECK(net_tail_precise_prepare(c));
+  const int U = nw->U, G = 4 * U, L = nw->L;
+  const int Tn = nw->H >> nw->n_blocks;
+  const long long rows = m * Tn;
+  float* xz = scratch;                          // (rows, 2G)
+  float* h1 = xz + (size_t)rows * 2 * G;        // (rows, 2U)
+  float* h2 = h1 + (size_t)rows * 2 * U;        // (rows, 2U)
+  float* d1 = h2 + (size_t)rows * 2 * U;        // (rows, 128)
+  ORCAI_CHECK(net_gemm_split(c, feat, nw->feat, nw->tp_wih[0], nw->lstm_bih[0], xz, 2 * G, rows, 2 * G, nw->feat, 2 * G, 0));
+  net_mark(c, mk);  // 6: lstm1 input projection
+  ORCAI_CHECK(net_lstm_rec_fp32(c, xz, nw->lstm_whh[0], h1, m, Tn));
+  net_mark(c, mk);  // 7: lstm1 recurrence
+  ORCAI_CHECK(net_gemm_split(c, h1, 2 * U, nw->tp_wih[1], nw->lstm_bih[1], xz, 2 * G, rows, 2 * G, 2 * U, 2 * G, 0));
+  net_mark(c, mk);  // 8: lstm2 input projection
+  ORCAI_CHECK(net_lstm_rec_fp32(c, xz, nw->lstm_whh[1], h2, m, Tn));
+  net_mark(c, mk);  // 9: lstm2 recurrence
+  ORCAI_CHECK(net_gemm_split(c, h2, 2 * U, nw->tp_d1, nw->d1_b, d1, 128, rows, 128, 2 * U, 128, 1));
+  {
+    const long long grid = std::min<long long>((rows + 7) / 8, (long long)c->sm_count * 8);
+    dense_out_kernel<<<(unsigned)grid, 256, 0, c->stream>>>(d1, nw->d2_w, nw->d2_b, d_preds_out, rows, L);
+    c->launches++;
+  }
+  net_mark(c, mk);  // 10: dense head
+  ORCAI_CUDA(c, cudaGetLastError());
   return ORCAI_OK;
 }
 

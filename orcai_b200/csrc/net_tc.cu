@@ -326,10 +326,12 @@ __constant__ float c_conv0[9 * 16 + 16];   // [tap][16] (BatchNorm folded), then
 
 constexpr int kC0TH = 8, kC0TW = 32;
 
+// SPLIT: the result as (hi, lo) fp16 pairs, out_lo = fp16(v - hi) (fp32-grade path, net_precise.cuh)
+template <bool SPLIT>
 __global__ void __launch_bounds__(256)
 conv0_direct_kernel(const float* __restrict__ in, int mode, long long first, int shift, int in_ld, int Himg, int Wimg,
                     const SelectState* __restrict__ st, __half* __restrict__ out, __half* __restrict__ out_sub,
-                    int tiles_w, int tiles_h) {
+                    int tiles_w, int tiles_h, __half* __restrict__ out_lo) {
   __shared__ float s_x[kC0TH + 2][kC0TW + 2];
   const int tid = threadIdx.x, ty = tid >> 5, tx = tid & 31;
   const int tiles_per = tiles_w * tiles_h;
@@ -367,6 +369,17 @@ conv0_direct_kernel(const float* __restrict__ in, int mode, long long first, int
     for (int c = 0; c < 16; ++c) acc[c] = fmaf(x[t], c_conv0[t * 16 + c], acc[c]);
 #pragma unroll
   for (int c = 0; c < 16; ++c) acc[c] = fmaxf(acc[c], 0.f);
+  if constexpr (SPLIT) {
+    uint4 h0, l0, h1, l1;
+    fused::split8h(acc, h0, l0);
+    fused::split8h(acc + 8, h1, l1);
+    const size_t at = (((size_t)b * Himg + hh) * Wimg + ww) * 16;
+    reinterpret_cast<uint4*>(out + at)[0] = h0;
+    reinterpret_cast<uint4*>(out + at)[1] = h1;
+    reinterpret_cast<uint4*>(out_lo + at)[0] = l0;
+    reinterpret_cast<uint4*>(out_lo + at)[1] = l1;
+    return;
+  }
   const uint4 v0 = fused::pack8h(acc), v1 = fused::pack8h(acc + 8);
   __half* o = out + (((size_t)b * Himg + hh) * Wimg + ww) * 16;
   reinterpret_cast<uint4*>(o)[0] = v0;
@@ -641,7 +654,8 @@ int build_fused_block(Ctx* c, int blk) {
   auto put = [&](size_t idx, double v, double mu, double* acc) {
     const __half q = __float2half_rn((float)v);
     w[idx] = q;
-    *acc += ((double)__half2float(q) - v) * mu;
+    if (G::PREC) w[idx + G::W_LO / 2] = __float2half_rn((float)(v - (double)__half2float(q)));   // lo set: the weight is exact to 2^-22
+    else *acc += ((double)__half2float(q) - v) * mu;
   };
   for (int t = 0; t < 9; ++t) {
     for (int k = 0; k < G::CIN; ++k)
@@ -682,7 +696,7 @@ int build_fused_block(Ctx* c, int blk) {
   ORCAI_CUDA(c, cudaMalloc(&p, G::W_BYTES));
   nw->allocs.push_back(p);
   ORCAI_CUDA(c, cudaMemcpy(p, w.data(), G::W_BYTES, cudaMemcpyHostToDevice));
-  nw->fb_w[blk] = p;
+  (G::PREC ? nw->fbp_w[blk] : nw->fb_w[blk]) = p;
   ORCAI_CUDA(c, cudaFuncSetAttribute(fused::fused_block_kernel<G>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G::SMEM));
   return ORCAI_OK;
 }
@@ -869,21 +883,30 @@ int make_act_map(Ctx* c, CUtensorMap* map, const __half* base, long long n, int 
   return ORCAI_OK;
 }
 
+// PREC blocks take their input tensors as (hi, lo) pairs (xr_lo, xs_lo) and write fp32 tensors (yr, ys point to floats)
 template <class G>
-int run_fused_block(Ctx* c, int blk, const __half* xr, const __half* xs, __half* yr, __half* ys, long long m, int Himg, int Wimg) {
+int run_fused_block(Ctx* c, int blk, const __half* xr, const __half* xs, __half* yr, __half* ys, long long m, int Himg, int Wimg,
+                    const __half* xr_lo = nullptr, const __half* xs_lo = nullptr) {
   NetWeights* nw = c->net;
   const int Ho = Himg / 2, Wo = (Wimg + 1) / 2;
   const int n_strips = (Wo + G::CP - 1) / G::CP;
   const long long items = m * n_strips;
   const long long grid = std::min<long long>(items, (long long)c->sm_count * G::CTAS);
-  CUtensorMap tmx, tmr;
+  CUtensorMap tmx, tmr, tmxl, tmrl;
   ORCAI_CHECK(make_act_map(c, &tmx, xr, m, Himg, Wimg, G::ICP, G::WP, G::S + 2));
   // residual input = x at even positions: its own tensor, or (xs == nullptr: x is non-negative, ReLU(x) == x) the full tensor
   // traversed with element stride 2
   if (xs) ORCAI_CHECK(make_act_map(c, &tmr, xs, m, Ho, Wo, G::ICP, G::CP, G::S / 2));
   else ORCAI_CHECK(make_act_map(c, &tmr, xr, m, Himg, Wimg, G::ICP, G::CP, G::S / 2, 2));
+  tmxl = tmx; tmrl = tmr;
+  if (G::PREC) {
+    ORCAI_CHECK(make_act_map(c, &tmxl, xr_lo, m, Himg, Wimg, G::ICP, G::WP, G::S + 2));
+    if (xs) ORCAI_CHECK(make_act_map(c, &tmrl, xs_lo, m, Ho, Wo, G::ICP, G::CP, G::S / 2));
+    else ORCAI_CHECK(make_act_map(c, &tmrl, xr_lo, m, Himg, Wimg, G::ICP, G::CP, G::S / 2, 2));
+  }
   fused::fused_block_kernel<G><<<(unsigned)grid, G::NTHREADS, G::SMEM, c->stream>>>(tmx, tmr, xs ? 1 : 2, yr, ys, Himg, Wimg, n_strips, items,
-                                                                                   static_cast<const unsigned char*>(nw->fb_w[blk]));
+                                                                                   static_cast<const unsigned char*>(G::PREC ? nw->fbp_w[blk] : nw->fb_w[blk]),
+                                                                                   tmxl, tmrl);
   c->launches++;
   ORCAI_CUDA(c, cudaGetLastError());
   return ORCAI_OK;
@@ -927,7 +950,7 @@ int run_fused_block1_conv0(Ctx* c, const __half* spec16, long long snippet_strid
                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) ORCAI_FAIL(c, ORCAI_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for the spectrogram view of block 1", (int)r);
   fused::fused_block_kernel<G><<<(unsigned)grid, G::NTHREADS, G::SMEM, c->stream>>>(tms, tms, 2, yr, ys, Himg, Wimg, n_strips, items,
-                                                                                   static_cast<const unsigned char*>(nw->fb_w[0]));
+                                                                                   static_cast<const unsigned char*>(nw->fb_w[0]), tms, tms);
   c->launches++;
   ORCAI_CUDA(c, cudaGetLastError());
   return ORCAI_OK;
@@ -1023,8 +1046,9 @@ int forward_fused(Ctx* c, const float* d_in, int input_mode, int64_t first, int6
     } else {
       const int tiles_w = (Wf + kC0TW - 1) / kC0TW, tiles_h = (Himg + kC0TH - 1) / kC0TH;
       const float* src = (input_mode == 0) ? d_in : d_in + (size_t)s0 * Himg * Wf;
-      conv0_direct_kernel<<<(unsigned)(m * tiles_w * tiles_h), 256, 0, c->stream>>>(src, input_mode, first + s0, shift, input_mode == 0 ? kRawLd : Wf,
-                                                                                   Himg, Wf, c->d_sel, act[0], static_cast<H*>(nullptr), tiles_w, tiles_h);
+      conv0_direct_kernel<false><<<(unsigned)(m * tiles_w * tiles_h), 256, 0, c->stream>>>(src, input_mode, first + s0, shift, input_mode == 0 ? kRawLd : Wf,
+                                                                                          Himg, Wf, c->d_sel, act[0], static_cast<H*>(nullptr), tiles_w, tiles_h,
+                                                                                          static_cast<H*>(nullptr));
       c->launches++;
       ORCAI_CUDA(c, cudaGetLastError());
     }
@@ -1055,6 +1079,8 @@ int forward_fused(Ctx* c, const float* d_in, int input_mode, int64_t first, int6
   }
   return ORCAI_OK;
 }
+
+#include "net_precise.cuh"
 
 }  // namespace
 
@@ -1150,6 +1176,10 @@ int net_forward_tc(Ctx* c, const float* d_in, int input_mode, int64_t first, int
   if (nw->path == 3) {
     ORCAI_CHECK(prepare_fused(c));
     return forward_fused(c, d_in, input_mode, first, n, d_preds);
+  }
+  if (nw->path == 4) {
+    ORCAI_CHECK(prepare_precise(c));
+    return forward_precise(c, d_in, input_mode, first, n, d_preds);
   }
   const int fmt = nw->path == 2 ? 1 : 0;
   ORCAI_CHECK(net_tc_prepare(c, fmt));
