@@ -119,6 +119,7 @@ int net_set_tail_path(Ctx* c, int path);
 int net_calibrate(Ctx* c, int64_t max_snippets);
 int net_set_conv0_path(Ctx* c, int path);
 int net_set_block1_path(Ctx* c, int path);
+int net_set_precise_tall(Ctx* c, int on);   // net_path 4 on resident recordings: 1 = shared interior (tall image + border rows), 0 = snippet by snippet
 void net_trace_dump();                  // bring-up aid (net_fused.cuh: ORCAI_FUSED_TRACE), no-op in normal builds
 const unsigned int* net_trap_info();   // bring-up aid (tc_common.cuh: g_trap_info), nullptr unless ORCAI_B200_TRAPINFO is set
 int net_set_debug_stop(Ctx* c, int stage);

@@ -500,6 +500,11 @@ int net_set_block1_path(Ctx* c, int path) {
   return ORCAI_OK;
 }
 
+int net_set_precise_tall(Ctx* c, int on) {
+  c->net->precise_tall = on ? 1 : 0;
+  return ORCAI_OK;
+}
+
 int net_set_conv0_path(Ctx* c, int path) {
   if (path < 0 || path > 2) ORCAI_FAIL(c, ORCAI_ERR_ARG, "conv0_path must be 0 (fp32 CUDA cores), 1 (tensor cores) or 2 (fused into block 1)");
   c->net->conv0_path = path;

@@ -90,6 +90,7 @@ struct NetWeights {
   float* p_res_w[kMaxBlocks] = {};   // [CIP][COP] fp32, zero padded
   float* p_res_b[kMaxBlocks] = {};   // [COP]
   int chunk_precise = 1024;
+  int precise_tall = 1;       // resident recordings: trunk once over the chunk's rows as one tall image + per-snippet border rows
   int debug_stop = -1;        // stop the forward after this stage (debug reads), -1 = run everything
   // last debug buffer: kind 0 f32, 1 fp16, 2 bf16 ; NHWC with channel pitch dbg_pitch
   const void* dbg_ptr = nullptr; int dbg_kind = 0; long long dbg_n = 0; int dbg_h = 0, dbg_w = 0, dbg_c = 0, dbg_pitch = 0;

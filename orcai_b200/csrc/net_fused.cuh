@@ -245,13 +245,23 @@ __device__ __forceinline__ uint4 hmax8(uint4 a, uint4 b) {
   return a;
 }
 
+// Tall-image mode (net_precise.cuh): the images of the batch are overlapping row windows of ONE tall image - image b covers
+// tall rows [b * stride - warm, b * stride - warm + H) (the tensor maps are built with that outer stride and a base shifted by
+// -warm rows).  Padding ("outside the image") is then decided on TALL rows [0, rows), the first warm / 2 output rows of every
+// window are warm-up (the carried rows of a window's first step are not real) and are not stored, and output row ho of window b
+// is tall output row (b * stride - warm) / 2 + ho.  on = 0: independent images, as before.
+struct TallView {
+  int on = 0, stride = 0, warm = 0;
+  long long rows = 0;
+};
+
 template <class G>
 __global__ void __launch_bounds__(G::NTHREADS, G::CTAS)
 fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmR, int r_step, __half* __restrict__ Yr,
                    __half* __restrict__ Ysub, int H, int W, int n_strips, long long n_items,
                    const unsigned char* __restrict__ wpack,
                    // PREC: maps of the lo tensors; Yr / Ysub are then fp32 arrays
-                   const __grid_constant__ CUtensorMap tmXl, const __grid_constant__ CUtensorMap tmRl) {
+                   const __grid_constant__ CUtensorMap tmXl, const __grid_constant__ CUtensorMap tmRl, const TallView tall) {
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + G::OFF_BAR);
   uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + G::NBAR);
@@ -583,14 +593,17 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         float r[16];
         tmem_ld16f(lane_addr + G::COL_R + (uint32_t)(gp & 1) * G::NP + g0 * 8, r);
         const int ho = (pa >> 1) + q_i, wo = pwo0 + q_j;
-        if (row < G::RQ && ho >= 0 && ho < Ho && wo < Wo) {
+        // output row in the output tensor: image pb's own rows, or (tall view) the window's rows past its warm-up
+        const long long orow = tall.on ? (pb * tall.stride - tall.warm) / 2 + ho : pb * Ho + ho;
+        const bool row_ok = tall.on ? (ho >= tall.warm / 2 && ho < Ho && orow < tall.rows / 2) : (ho >= 0 && ho < Ho);
+        if (row < G::RQ && row_ok && wo < Wo) {
           const uint32_t p00 = (uint32_t)((2 * q_i) * (G::WP / 2) + 1 + q_j);   // even column 2 + 2j of row 2i; the odd column 3 + 2j sits S2HALF further
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
             if (u == 1 && !has1) break;
             const int gg = g0 + u;
             const unsigned char* s2 = smem + G::OFF_S2 + gg * G::LBO_S2 + p00 * 16;
-            const size_t o_full = (((size_t)pb * Ho + ho) * Wo + wo) * G::OCP + gg * 8;
+            const size_t o_full = ((size_t)orow * Wo + wo) * G::OCP + gg * 8;
             const size_t o_sub = (((size_t)pb * Hs + (ho >> 1)) * Ws + (wo >> 1)) * G::OCP + gg * 8;
             const bool sub = Ysub != nullptr && !(ho & 1) && !(wo & 1);
             if constexpr (G::PREC) {
@@ -652,6 +665,8 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       const long long b = item / n_strips;
       const int strip = (int)(item - b * n_strips);
       const int wo0 = strip * G::CP, cb = 2 * wo0 - 2;
+      // rows that count as "inside the image": this image's [0, H), or (tall view) the tall image's [0, rows) seen from window b
+      const long long img_row0 = tall.on ? b * tall.stride - tall.warm : 0, img_rows = tall.on ? tall.rows : H;
       for (int step = 0; step < n_steps; ++step, ++g) {
         const int a = step * G::S - 2;
         const uint32_t par = (uint32_t)(g & 1);
@@ -665,8 +680,9 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
             float v[16];
             tmem_ld16f(lane_addr + G::COL_1 + t * G::NP + g0 * 8, v);
             const int p1 = G::P1_0 + 128 * t + row;
-            const int hh = a + y1[t], ww = cb + c1[t];
-            const bool inimg = hh >= 0 && hh < H && ww >= 0 && ww < W;
+            const long long hh = img_row0 + a + y1[t];
+            const int ww = cb + c1[t];
+            const bool inimg = hh >= 0 && hh < img_rows && ww >= 0 && ww < W;
             if (p1 < (G::S + 2) * G::WP) {
               const uint4 z = make_uint4(0, 0, 0, 0);
               unsigned char* dst = smem + G::OFF_S1 + g0 * G::LBO_S1 + p1 * 16;
@@ -720,8 +736,9 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
             float v[16];
             tmem_ld16f(lane_addr + G::COL_2 + t * G::NP + g0 * 8, v);
             const int p2 = G::P2_0 + 128 * t + row;
-            const int hh = a + y2[t], ww = cb + c2[t];
-            const bool inimg = hh >= 0 && hh < H && ww >= 0 && ww < W;
+            const long long hh = img_row0 + a + y2[t];
+            const int ww = cb + c2[t];
+            const bool inimg = hh >= 0 && hh < img_rows && ww >= 0 && ww < W;
             if (p2 < (G::S + 1) * G::WP) {
               const uint4 ninf = make_uint4(0xFC00FC00u, 0xFC00FC00u, 0xFC00FC00u, 0xFC00FC00u);
               unsigned char* dst = smem + G::OFF_S2 + g0 * G::LBO_S2 + ((c2[t] & 1) * G::S2HALF + y2[t] * (G::WP / 2) + (c2[t] >> 1)) * 16;

@@ -101,10 +101,53 @@ pool_res_f32_kernel(const float* __restrict__ s2, const float* __restrict__ xs, 
   }
 }
 
+// Border images of a level (tall-image mode, see forward_precise): image b < n is rows [0, 8) of snippet b, image n + b rows
+// [H - 8, H) of snippet b.  A row comes from the snippet's own border values `alt` (the previous level's border outputs: 4 rows
+// per image; rows [0, nt) of a top image, the last nb rows of a bottom image) or from the tall tensor (snippet i starts at tall
+// row i * stride).  tall: (rows, W, C), alt: (2n, 4, W, C), out: (2n, 8, W, C); one thread per float4.
+__global__ void __launch_bounds__(256)
+gather_border_kernel(const float* __restrict__ tall, const float* __restrict__ alt, float* __restrict__ out, long long n, int stride, int H, int row_f4,
+                     int nt, int nb) {
+  const long long total = 2 * n * 8 * row_f4;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(idx % row_f4);
+    long long r = idx / row_f4;
+    const int j = (int)(r % 8);
+    const long long img = r / 8;
+    const bool top = img < n;
+    const long long i = top ? img : img - n;
+    const float4* src;
+    if (top) src = j < nt ? reinterpret_cast<const float4*>(alt) + (img * 4 + j) * row_f4 : reinterpret_cast<const float4*>(tall) + (i * stride + j) * row_f4;
+    else src = j >= 8 - nb ? reinterpret_cast<const float4*>(alt) + (img * 4 + (j - 4)) * row_f4
+                           : reinterpret_cast<const float4*>(tall) + (i * stride + H - 8 + j) * row_f4;
+    reinterpret_cast<float4*>(out)[idx] = __ldg(src + q);
+  }
+}
+
+// features of snippet i, row r (of Tn): the tall tensor's row i * stride + r, except the nt first / nb last rows, which are the
+// snippet's own (border images of 8 rows: top image rows [0, 8), bottom image rows [Tn - 8, Tn))
+__global__ void __launch_bounds__(256)
+assemble_feat_kernel(const float* __restrict__ tall, const float* __restrict__ border, float* __restrict__ out, long long n, int stride, int Tn, int row_f4,
+                     int nt, int nb) {
+  const long long total = n * Tn * row_f4;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(idx % row_f4);
+    long long r = idx / row_f4;
+    const int j = (int)(r % Tn);
+    const long long i = r / Tn;
+    const float4* src;
+    if (j < nt) src = reinterpret_cast<const float4*>(border) + (i * 8 + j) * row_f4;
+    else if (j >= Tn - nb) src = reinterpret_cast<const float4*>(border) + ((n + i) * 8 + (j - (Tn - 8))) * row_f4;
+    else src = reinterpret_cast<const float4*>(tall) + (i * stride + j) * row_f4;
+    reinterpret_cast<float4*>(out)[idx] = __ldg(src + q);
+  }
+}
+
 }  // namespace precise
 
-// block 1 of the fp32-grade path: one CTA per SM (the (hi, lo) plane sets fill its shared memory), two issuer warps
-using FB1P = fused::FB<16, 30, 29, 6, true, 1, 8, false, 2, 1, true>;
+// block 1 of the fp32-grade path: one CTA per SM (the (hi, lo) plane sets fill its shared memory), two issuer warps; its output
+// is the un-rectified block output in fp32 (the next block applies the ReLU on load and walks it with stride 2 for its residual)
+using FB1P = fused::FB<16, 30, 29, 6, false, 1, 8, false, 2, 1, true>;
 
 inline std::vector<float> pad_matrix(const float* w, int rows, int cols, int rows_p, int cols_p) {
   std::vector<float> out((size_t)rows_p * cols_p, 0.f);
@@ -140,58 +183,100 @@ int prepare_precise(Ctx* c) {
 }
 
 // one un-folded separable convolution: d = dw3x3(f(x)) ; out = act(d * pw + bias).  x (n, h, w, cip) fp32 -> out (n, h, w, ldc) fp32
-int run_precise_sep(Ctx* c, const float* x, float* d, float* out, long long n, int h, int w, int cip, int ldc, int n_valid, bool relu_in,
+int run_precise_sep(Ctx* c, const float* x, float* d, float* out, long long n, long long h, int w, int cip, int ldc, int n_valid, bool relu_in,
                     bool relu_out, const NetWeights::PreciseSep& ps) {
   const long long total = n * h * w * (cip / 4);
   if (total <= 0) return ORCAI_OK;
   const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, (long long)c->sm_count * 32);
-  if (relu_in) precise::dw3x3_kernel<true><<<grid, 256, 0, c->stream>>>(x, d, ps.dw, n, h, w, cip);
-  else precise::dw3x3_kernel<false><<<grid, 256, 0, c->stream>>>(x, d, ps.dw, n, h, w, cip);
+  if (relu_in) precise::dw3x3_kernel<true><<<grid, 256, 0, c->stream>>>(x, d, ps.dw, n, (int)h, w, cip);
+  else precise::dw3x3_kernel<false><<<grid, 256, 0, c->stream>>>(x, d, ps.dw, n, (int)h, w, cip);
   c->launches++;
   ORCAI_CUDA(c, cudaGetLastError());
   return net_gemm_split(c, d, cip, ps.pw, ps.bias, out, ldc, n * h * w, 64, cip, n_valid, relu_out ? 1 : 0);
 }
 
-int run_pool_res(Ctx* c, const float* s2, const float* xs, long long xs_img, long long xs_row, int xs_px, float* y, long long n, int h, int w,
-                 int cip, int cop, int blk) {
+// residual block b (1-based index blk >= 1 into the weights) on fp32 images x (n, h, w, cip), un-rectified -> y (n, h/2, ceil(w/2), cop)
+int run_precise_block(Ctx* c, int blk, const float* x, float* ta, float* tb, float* tc, float* y, long long n, long long h, int w, int cip, int cop) {
   NetWeights* nw = c->net;
-  const int ho = h / 2, wo = (w + 1) / 2;
+  ORCAI_CHECK(run_precise_sep(c, x, ta, tb, n, h, w, cip, cop, cop, true, true, nw->p_sep1[blk]));
+  ORCAI_CHECK(run_precise_sep(c, tb, ta, tc, n, h, w, cop, cop, cop, false, false, nw->p_sep2[blk]));
+  const long long ho = h / 2;
+  const int wo = (w + 1) / 2;
   const long long total = n * ho * wo * (cop / 4);
   if (total <= 0) return ORCAI_OK;
   const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, (long long)c->sm_count * 16);
   const size_t smem = ((size_t)cip * cop + cop) * sizeof(float);
-  precise::pool_res_f32_kernel<<<grid, 256, smem, c->stream>>>(s2, xs, xs_img, xs_row, xs_px, y, n, h, w, ho, wo, cip, cop, nw->p_res_w[blk], nw->p_res_b[blk]);
+  // the residual 1x1/2 convolution walks the block input with stride 2
+  precise::pool_res_f32_kernel<<<grid, 256, smem, c->stream>>>(tc, x, h * w * cip, (long long)2 * w * cip, 2 * cip, y, n, (int)h, w, (int)ho, wo, cip, cop,
+                                                              nw->p_res_w[blk], nw->p_res_b[blk]);
   c->launches++;
   ORCAI_CUDA(c, cudaGetLastError());
   return ORCAI_OK;
 }
 
-int forward_precise(Ctx* c, const float* d_in, int input_mode, int64_t first, int64_t n, float* d_preds) {
+int run_conv0_split(Ctx* c, const float* src, int input_mode, long long first, int in_ld, long long n_img, int Himg, int Wf, __half* hi, __half* lo,
+                    long long n_snip, int off_bot, int Hfull) {
+  const int tiles_w = (Wf + kC0TW - 1) / kC0TW, tiles_h = (Himg + kC0TH - 1) / kC0TH;
+  const long long blocks = n_img * tiles_w * tiles_h;
+  if (blocks <= 0) return ORCAI_OK;
+  conv0_direct_kernel<true><<<(unsigned)blocks, 256, 0, c->stream>>>(src, input_mode, first, c->p.snippet_len / 2, in_ld, Himg, Wf, c->d_sel, hi,
+                                                                     static_cast<__half*>(nullptr), tiles_w, tiles_h, lo, n_snip, off_bot, Hfull);
+  c->launches++;
+  ORCAI_CUDA(c, cudaGetLastError());
+  return ORCAI_OK;
+}
+
+// block 1 over ONE tall image (rows, W) of (hi, lo) fp16 pairs, cut into windows of `stride` rows (+ warm-up); guard rows of
+// zeros lie before x (>= warm rows) and after it (>= stride + 16 rows)
+int run_block1_tall(Ctx* c, const __half* x_hi, const __half* x_lo, float* y, long long rows, int Wimg, int stride, int warm) {
+  using G = FB1P;
+  NetWeights* nw = c->net;
+  const int Wo = (Wimg + 1) / 2;
+  const int n_strips = (Wo + G::CP - 1) / G::CP;
+  const long long n_win = (rows + stride - 1) / stride;
+  const long long items = n_win * n_strips;
+  const long long grid = std::min<long long>(items, (long long)c->sm_count * G::CTAS);
+  const int Hloc = warm + stride;
+  const size_t shift = (size_t)warm * Wimg * G::ICP;
+  CUtensorMap tmx, tmr, tmxl, tmrl;
+  ORCAI_CHECK(make_act_map(c, &tmx, x_hi - shift, n_win, Hloc + 8, Wimg, G::ICP, G::WP, G::S + 2, 1, stride));
+  ORCAI_CHECK(make_act_map(c, &tmr, x_hi - shift, n_win, Hloc + 8, Wimg, G::ICP, G::CP, G::S / 2, 2, stride));
+  ORCAI_CHECK(make_act_map(c, &tmxl, x_lo - shift, n_win, Hloc + 8, Wimg, G::ICP, G::WP, G::S + 2, 1, stride));
+  ORCAI_CHECK(make_act_map(c, &tmrl, x_lo - shift, n_win, Hloc + 8, Wimg, G::ICP, G::CP, G::S / 2, 2, stride));
+  fused::TallView tv;
+  tv.on = 1; tv.stride = stride; tv.warm = warm; tv.rows = rows;
+  fused::fused_block_kernel<G><<<(unsigned)grid, G::NTHREADS, G::SMEM, c->stream>>>(tmx, tmr, 2, reinterpret_cast<__half*>(y), static_cast<__half*>(nullptr), Hloc,
+                                                                                   Wimg, n_strips, items, static_cast<const unsigned char*>(nw->fbp_w[0]), tmxl,
+                                                                                   tmrl, tv);
+  c->launches++;
+  ORCAI_CUDA(c, cudaGetLastError());
+  return ORCAI_OK;
+}
+
+struct PreciseGeom {
+  int hs[5], ws[5], cp[5];
+};
+
+// ---- independent snippets: host-provided batches (input_mode 1) and the stage-debug reads ------------------------------------
+int forward_precise_snippets(Ctx* c, const float* d_in, int input_mode, int64_t first, int64_t n, float* d_preds, const PreciseGeom& g) {
   NetWeights* nw = c->net;
   using H16 = __half;
   const int Himg = nw->H, Wf = nw->Wf, U = nw->U, L = nw->L;
   const int Tn = Himg >> nw->n_blocks;
-  int hs[5], ws[5];
-  hs[0] = Himg; ws[0] = Wf;
-  for (int b = 0; b < 4; ++b) { hs[b + 1] = hs[b] / 2; ws[b + 1] = (ws[b] + 1) / 2; }
-  const int cp[5] = {16, cpad8(nw->filters[0]), cpad8(nw->filters[1]), cpad8(nw->filters[2]), cpad8(nw->filters[3])};
-  // per snippet: entry-convolution output as (hi, lo) fp16; fp32 block outputs y1 (ReLU'd) + y1 at even positions, y2, y3, y4;
-  // three fp32 temporaries sized for block 2's widest tensor; the tail
+  const int *hs = g.hs, *ws = g.ws, *cp = g.cp;
   const size_t c0_h = (size_t)hs[0] * ws[0] * 16;                       // halfs per plane set
-  const size_t y1 = (size_t)hs[1] * ws[1] * cp[1], y1s = (size_t)hs[2] * ws[2] * cp[1];
-  const size_t y2 = (size_t)hs[2] * ws[2] * cp[2], y3 = (size_t)hs[3] * ws[3] * cp[3], y4 = (size_t)hs[4] * ws[4] * cp[4];
+  const size_t y1 = (size_t)hs[1] * ws[1] * cp[1], y2 = (size_t)hs[2] * ws[2] * cp[2], y3 = (size_t)hs[3] * ws[3] * cp[3], y4 = (size_t)hs[4] * ws[4] * cp[4];
   const size_t tmp = (size_t)hs[1] * ws[1] * cp[2];
   const size_t feat_f = (size_t)Tn * nw->feat;
   const size_t tail_f = (size_t)Tn * (2 * 4 * U + 2 * U + 2 * U + 128);
-  const size_t per = c0_h * 2 * 2 + (y1 + y1s + y2 + y3 + y4 + 3 * tmp + feat_f + tail_f) * 4;
+  const size_t per = c0_h * 2 * 2 + (y1 + y2 + y3 + y4 + 3 * tmp + feat_f + tail_f) * 4;
   const long long chunk = std::min<long long>(std::max(nw->chunk_precise, 1), n);
   if (chunk <= 0) return ORCAI_OK;
   ORCAI_CHECK(ensure_device_buffer(c, &nw->tc_ws, &nw->tc_ws_cap, per * (size_t)chunk + 256));
   H16* c0hi = static_cast<H16*>(nw->tc_ws);
   H16* c0lo = c0hi + c0_h * chunk;
   float* Y1 = reinterpret_cast<float*>(c0lo + c0_h * chunk);
-  float* Y1s = Y1 + y1 * chunk;
-  float* Y2 = Y1s + y1s * chunk;
+  float* Y2 = Y1 + y1 * chunk;
   float* Y3 = Y2 + y2 * chunk;
   float* Y4 = Y3 + y3 * chunk;
   float* TA = Y4 + y4 * chunk;
@@ -199,51 +284,27 @@ int forward_precise(Ctx* c, const float* d_in, int input_mode, int64_t first, in
   float* TC = TB + tmp * chunk;
   float* feat = TC + tmp * chunk;
   float* scratch = feat + feat_f * chunk;
-  const int shift = c->p.snippet_len / 2;
-  nw->mark_i = 0;
-  nw->dbg_ptr = nullptr;
   const int stop = nw->debug_stop;
-  {  // constant memory is per device, not per context: refresh it stream-ordered before every forward
-    nw->h_conv0_pack.resize(160);
-    memcpy(nw->h_conv0_pack.data(), nw->h_conv0_w.data(), 144 * sizeof(float));
-    memcpy(nw->h_conv0_pack.data() + 144, nw->h_conv0_b.data(), 16 * sizeof(float));
-    ORCAI_CUDA(c, cudaMemcpyToSymbolAsync(c_conv0, nw->h_conv0_pack.data(), 160 * sizeof(float), 0, cudaMemcpyHostToDevice, c->stream));
-  }
   for (int64_t s0 = 0; s0 < n; s0 += chunk) {
     const long long m = std::min<long long>(chunk, n - s0);
     const bool mk = (s0 == 0);
     if (mk) nw->marked_snippets = m;
     net_mark(c, mk);
-    {
-      const int tiles_w = (Wf + kC0TW - 1) / kC0TW, tiles_h = (Himg + kC0TH - 1) / kC0TH;
-      const float* src = (input_mode == 0) ? d_in : d_in + (size_t)s0 * Himg * Wf;
-      conv0_direct_kernel<true><<<(unsigned)(m * tiles_w * tiles_h), 256, 0, c->stream>>>(src, input_mode, first + s0, shift, input_mode == 0 ? kRawLd : Wf,
-                                                                                         Himg, Wf, c->d_sel, c0hi, static_cast<H16*>(nullptr), tiles_w, tiles_h, c0lo);
-      c->launches++;
-      ORCAI_CUDA(c, cudaGetLastError());
-    }
+    const float* src = (input_mode == 0) ? d_in : d_in + (size_t)s0 * Himg * Wf;
+    ORCAI_CHECK(run_conv0_split(c, src, input_mode, first + s0, input_mode == 0 ? kRawLd : Wf, m, Himg, Wf, c0hi, c0lo, m, 0, Himg));
     net_mark(c, mk);  // 0: conv0
     if (stop == 0) { set_debug(nw, c0hi, 1, m, hs[0], ws[0], 16, 16); return ORCAI_OK; }
-    ORCAI_CHECK((run_fused_block<FB1P>(c, 0, c0hi, static_cast<const H16*>(nullptr), reinterpret_cast<H16*>(Y1), reinterpret_cast<H16*>(Y1s), m, hs[0], ws[0],
+    ORCAI_CHECK((run_fused_block<FB1P>(c, 0, c0hi, static_cast<const H16*>(nullptr), reinterpret_cast<H16*>(Y1), static_cast<H16*>(nullptr), m, hs[0], ws[0],
                                        c0lo, static_cast<const H16*>(nullptr))));
     net_mark(c, mk);  // 1
     if (stop == 1) { set_debug(nw, Y1, 0, m, hs[1], ws[1], 30, cp[1]); return ORCAI_OK; }
-    if (stop == 21) { set_debug(nw, Y1s, 0, m, hs[2], ws[2], 30, cp[1]); return ORCAI_OK; }
-    // block 2: its input arrives ReLU'd (Y1) plus un-rectified at even positions (Y1s)
-    ORCAI_CHECK(run_precise_sep(c, Y1, TA, TB, m, hs[1], ws[1], cp[1], cp[2], cp[2], false, true, nw->p_sep1[1]));
-    ORCAI_CHECK(run_precise_sep(c, TB, TA, TC, m, hs[1], ws[1], cp[2], cp[2], cp[2], false, false, nw->p_sep2[1]));
-    ORCAI_CHECK(run_pool_res(c, TC, Y1s, (long long)y1s, (long long)ws[2] * cp[1], cp[1], Y2, m, hs[1], ws[1], cp[1], cp[2], 1));
+    ORCAI_CHECK(run_precise_block(c, 1, Y1, TA, TB, TC, Y2, m, hs[1], ws[1], cp[1], cp[2]));
     net_mark(c, mk);  // 2
     if (stop == 2) { set_debug(nw, Y2, 0, m, hs[2], ws[2], 40, cp[2]); return ORCAI_OK; }
-    // blocks 3, 4: input un-rectified (ReLU on load; the residual convolution walks it with stride 2)
-    ORCAI_CHECK(run_precise_sep(c, Y2, TA, TB, m, hs[2], ws[2], cp[2], cp[3], cp[3], true, true, nw->p_sep1[2]));
-    ORCAI_CHECK(run_precise_sep(c, TB, TA, TC, m, hs[2], ws[2], cp[3], cp[3], cp[3], false, false, nw->p_sep2[2]));
-    ORCAI_CHECK(run_pool_res(c, TC, Y2, (long long)y2, (long long)2 * ws[2] * cp[2], 2 * cp[2], Y3, m, hs[2], ws[2], cp[2], cp[3], 2));
+    ORCAI_CHECK(run_precise_block(c, 2, Y2, TA, TB, TC, Y3, m, hs[2], ws[2], cp[2], cp[3]));
     net_mark(c, mk);  // 3
     if (stop == 3) { set_debug(nw, Y3, 0, m, hs[3], ws[3], 50, cp[3]); return ORCAI_OK; }
-    ORCAI_CHECK(run_precise_sep(c, Y3, TA, TB, m, hs[3], ws[3], cp[3], cp[4], cp[4], true, true, nw->p_sep1[3]));
-    ORCAI_CHECK(run_precise_sep(c, TB, TA, TC, m, hs[3], ws[3], cp[4], cp[4], cp[4], false, false, nw->p_sep2[3]));
-    ORCAI_CHECK(run_pool_res(c, TC, Y3, (long long)y3, (long long)2 * ws[3] * cp[3], 2 * cp[3], Y4, m, hs[3], ws[3], cp[3], cp[4], 3));
+    ORCAI_CHECK(run_precise_block(c, 3, Y3, TA, TB, TC, Y4, m, hs[3], ws[3], cp[3], cp[4]));
     net_mark(c, mk);  // 4
     if (stop == 4) { set_debug(nw, Y4, 0, m, hs[4], ws[4], 60, cp[4]); return ORCAI_OK; }
     // final separable convolution -> features (m, Tn, w*36 + c)
@@ -253,4 +314,131 @@ int forward_precise(Ctx* c, const float* d_in, int input_mode, int64_t first, in
     ORCAI_CHECK(net_tail_precise(c, feat, scratch, m, d_preds + (size_t)s0 * Tn * L, mk));
   }
   return ORCAI_OK;
+}
+
+// ---- snippets of the resident recording (input_mode 0): shared interior ---------------------------------------------------------
+// Consecutive snippets overlap by half their length, and away from a snippet's own zero-padded top and bottom the convolutional
+// trunk computes the same numbers for both (predict.py:252-261 cuts the windows; the 16-row alignment of the shift keeps the
+// pooling grids aligned).  So the trunk runs ONCE over the chunk's rows as one tall image (half the rows of the snippet batch),
+// and only the rows that feel a snippet's own border are recomputed per snippet from 8-row border images: at every level the
+// first nt = 2 and last nb = 3 output rows of a snippet (1 / 1 after the entry convolution, 2 / 2 after block 1, 3 / 4 of the
+// features).  Every kernel computes a pixel from its own receptive field only, with one fixed instruction sequence, so the
+// result is BIT-IDENTICAL to the per-snippet evaluation (tests/test_gpu_network.py holds the two to assert_array_equal).
+int forward_precise_tall(Ctx* c, const float* d_raw, int64_t first, int64_t n, float* d_preds, const PreciseGeom& g) {
+  NetWeights* nw = c->net;
+  using H16 = __half;
+  const int Himg = nw->H, Wf = nw->Wf, U = nw->U, L = nw->L;
+  const int Tn = Himg >> nw->n_blocks;
+  const int *hs = g.hs, *ws = g.ws, *cp = g.cp;
+  const int shift = c->p.snippet_len / 2;
+  constexpr int kWarm = 6, kGuardB = 8;            // block 1: warm-up rows of a window (one step), zero rows before the tall tensor
+  const int kWin = shift;                          // block 1: rows per window
+  const int kGuardA = kWin + 16;                   // zero rows after the tall tensor
+  const int nt[6] = {1, 2, 2, 2, 2, 3}, nb[6] = {1, 2, 3, 3, 3, 4};   // rows of a snippet that feel its top / bottom border, per level (5 = features)
+  const long long chunk = std::min<long long>(std::max(nw->chunk_precise, 1), n);
+  if (chunk <= 0) return ORCAI_OK;
+  // workspace (per chunk of m snippets: tall rows R_l = (m + 1) * (shift >> l) at level l)
+  auto rows_at = [&](long long m, int l) { return (m + 1) * (long long)(shift >> l); };
+  const long long M = chunk;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
+  const size_t c0_plane = (size_t)(kGuardB + rows_at(M, 0) + kGuardA) * ws[0] * 16 * 2;
+  const size_t o_c0hi = take(c0_plane), o_c0lo = take(c0_plane);
+  size_t o_y[5] = {};
+  for (int l = 1; l <= 4; ++l) o_y[l] = take((size_t)rows_at(M, l) * ws[l] * cp[l] * 4);
+  const size_t tmp = (size_t)rows_at(M, 1) * ws[1] * cp[2] * 4;
+  const size_t o_ta = take(tmp), o_tb = take(tmp), o_tc = take(tmp);
+  const size_t o_featt = take((size_t)rows_at(M, 4) * nw->feat * 4);
+  const size_t b0_plane = (size_t)2 * M * 8 * ws[0] * 16 * 2;
+  const size_t o_b0hi = take(b0_plane), o_b0lo = take(b0_plane);
+  const size_t alt_sz = (size_t)2 * M * 4 * ws[1] * cp[1] * 4, bimg_sz = (size_t)2 * M * 8 * ws[1] * cp[1] * 4, btmp = (size_t)2 * M * 8 * ws[1] * cp[2] * 4;
+  const size_t o_alt = take(alt_sz), o_bimg = take(bimg_sz), o_bta = take(btmp), o_btb = take(btmp), o_btc = take(btmp);
+  const size_t o_featb = take((size_t)2 * M * 8 * nw->feat * 4);
+  const size_t o_feat = take((size_t)M * Tn * nw->feat * 4);
+  const size_t o_tail = take((size_t)M * Tn * (2 * 4 * U + 2 * U + 2 * U + 128) * 4);
+  ORCAI_CHECK(ensure_device_buffer(c, &nw->tc_ws, &nw->tc_ws_cap, off + 256));
+  unsigned char* base = static_cast<unsigned char*>(nw->tc_ws);
+  auto F = [&](size_t o) { return reinterpret_cast<float*>(base + o); };
+  const size_t c0_row = (size_t)ws[0] * 16;        // halfs per row of the entry convolution's output
+  H16* c0hi = reinterpret_cast<H16*>(base + o_c0hi) + kGuardB * c0_row;
+  H16* c0lo = reinterpret_cast<H16*>(base + o_c0lo) + kGuardB * c0_row;
+  float* Y[5] = {nullptr, F(o_y[1]), F(o_y[2]), F(o_y[3]), F(o_y[4])};
+  float *TA = F(o_ta), *TB = F(o_tb), *TC = F(o_tc), *FEATT = F(o_featt);
+  H16* b0hi = reinterpret_cast<H16*>(base + o_b0hi);
+  H16* b0lo = reinterpret_cast<H16*>(base + o_b0lo);
+  float *ALT = F(o_alt), *BIMG = F(o_bimg), *BTA = F(o_bta), *BTB = F(o_btb), *BTC = F(o_btc), *FEATB = F(o_featb);
+  float *feat = F(o_feat), *scratch = F(o_tail);
+
+  for (int64_t s0 = 0; s0 < n; s0 += chunk) {
+    const long long m = std::min<long long>(chunk, n - s0);
+    const bool mk = (s0 == 0);
+    if (mk) nw->marked_snippets = m;
+    const long long R0 = rows_at(m, 0);
+    net_mark(c, mk);
+    // entry convolution: the chunk's rows as one image, and the 8-row border images of every snippet (its own zero padding)
+    for (H16* p : {c0hi, c0lo}) {
+      ORCAI_CUDA(c, cudaMemsetAsync(p - kGuardB * c0_row, 0, kGuardB * c0_row * 2, c->stream));
+      ORCAI_CUDA(c, cudaMemsetAsync(p + R0 * c0_row, 0, (size_t)kGuardA * c0_row * 2, c->stream));
+    }
+    ORCAI_CHECK(run_conv0_split(c, d_raw, 0, first + s0, kRawLd, 1, (int)R0, Wf, c0hi, c0lo, 1, 0, (int)R0));
+    ORCAI_CHECK(run_conv0_split(c, d_raw, 0, first + s0, kRawLd, 2 * m, 8, Wf, b0hi, b0lo, m, Himg - 8, Himg));
+    net_mark(c, mk);  // 0: conv0
+    // block 1: fused kernel over windows of the tall image; border images as independent 8-row images -> ALT (2m, 4, ..)
+    ORCAI_CHECK(run_block1_tall(c, c0hi, c0lo, Y[1], R0, Wf, kWin, kWarm));
+    ORCAI_CHECK((run_fused_block<FB1P>(c, 0, b0hi, static_cast<const H16*>(nullptr), reinterpret_cast<H16*>(ALT), static_cast<H16*>(nullptr), 2 * m, 8, ws[0],
+                                       b0lo, static_cast<const H16*>(nullptr))));
+    net_mark(c, mk);  // 1
+    // blocks 2 - 4: tall image, then the border images gathered from the tall tensor and the previous level's border rows
+    for (int l = 1; l <= 3; ++l) {
+      ORCAI_CHECK(run_precise_block(c, l, Y[l], TA, TB, TC, Y[l + 1], 1, rows_at(m, l), ws[l], cp[l], cp[l + 1]));
+      const int row_f4 = ws[l] * cp[l] / 4;
+      const long long total = 2 * m * 8 * row_f4;
+      precise::gather_border_kernel<<<(unsigned)std::min<long long>((total + 255) / 256, (long long)c->sm_count * 16), 256, 0, c->stream>>>(
+          Y[l], ALT, BIMG, m, shift >> l, hs[l], row_f4, nt[l], nb[l]);
+      c->launches++;
+      ORCAI_CUDA(c, cudaGetLastError());
+      ORCAI_CHECK(run_precise_block(c, l, BIMG, BTA, BTB, BTC, ALT, 2 * m, 8, ws[l], cp[l], cp[l + 1]));
+      net_mark(c, mk);  // 2, 3, 4
+    }
+    {  // final separable convolution (no pooling: 8-row border images give 8 feature rows) and the per-snippet feature rows
+      ORCAI_CHECK(run_precise_sep(c, Y[4], TA, FEATT, 1, rows_at(m, 4), ws[4], cp[4], 36, 36, false, true, nw->p_fin));
+      const int row_f4 = ws[4] * cp[4] / 4;
+      const long long total = 2 * m * 8 * row_f4;
+      precise::gather_border_kernel<<<(unsigned)std::min<long long>((total + 255) / 256, (long long)c->sm_count * 16), 256, 0, c->stream>>>(
+          Y[4], ALT, BIMG, m, shift >> 4, hs[4], row_f4, nt[4], nb[4]);
+      c->launches++;
+      ORCAI_CHECK(run_precise_sep(c, BIMG, BTA, FEATB, 2 * m, 8, ws[4], cp[4], 36, 36, false, true, nw->p_fin));
+      const int feat_f4 = nw->feat / 4;
+      const long long tot2 = m * Tn * feat_f4;
+      precise::assemble_feat_kernel<<<(unsigned)std::min<long long>((tot2 + 255) / 256, (long long)c->sm_count * 16), 256, 0, c->stream>>>(
+          FEATT, FEATB, feat, m, shift >> 4, Tn, feat_f4, nt[5], nb[5]);
+      c->launches++;
+      ORCAI_CUDA(c, cudaGetLastError());
+    }
+    net_mark(c, mk);  // 5
+    ORCAI_CHECK(net_tail_precise(c, feat, scratch, m, d_preds + (size_t)s0 * Tn * L, mk));
+  }
+  return ORCAI_OK;
+}
+
+int forward_precise(Ctx* c, const float* d_in, int input_mode, int64_t first, int64_t n, float* d_preds) {
+  NetWeights* nw = c->net;
+  PreciseGeom g;
+  g.hs[0] = nw->H; g.ws[0] = nw->Wf;
+  for (int b = 0; b < 4; ++b) { g.hs[b + 1] = g.hs[b] / 2; g.ws[b + 1] = (g.ws[b] + 1) / 2; }
+  g.cp[0] = 16;
+  for (int b = 0; b < 4; ++b) g.cp[b + 1] = cpad8(nw->filters[b]);
+  nw->mark_i = 0;
+  nw->dbg_ptr = nullptr;
+  {  // constant memory is per device, not per context: refresh it stream-ordered before every forward
+    nw->h_conv0_pack.resize(160);
+    memcpy(nw->h_conv0_pack.data(), nw->h_conv0_w.data(), 144 * sizeof(float));
+    memcpy(nw->h_conv0_pack.data() + 144, nw->h_conv0_b.data(), 16 * sizeof(float));
+    ORCAI_CUDA(c, cudaMemcpyToSymbolAsync(c_conv0, nw->h_conv0_pack.data(), 160 * sizeof(float), 0, cudaMemcpyHostToDevice, c->stream));
+  }
+  // the shared-interior evaluation needs the geometry it was derived for: 4 blocks, snippets half a length apart, 16-row aligned
+  const bool tall_ok = input_mode == 0 && nw->debug_stop < 0 && nw->precise_tall && nw->n_blocks == 4 && (c->p.snippet_len / 2) % 16 == 0 &&
+                       nw->H >= 128 && nw->H % 16 == 0;
+  if (tall_ok) return forward_precise_tall(c, d_in, first, n, d_preds, g);
+  return forward_precise_snippets(c, d_in, input_mode, first, n, d_preds, g);
 }

@@ -327,11 +327,14 @@ __constant__ float c_conv0[9 * 16 + 16];   // [tap][16] (BatchNorm folded), then
 constexpr int kC0TH = 8, kC0TW = 32;
 
 // SPLIT: the result as (hi, lo) fp16 pairs, out_lo = fp16(v - hi) (fp32-grade path, net_precise.cuh)
+// Row windows (net_precise.cuh, border images): image b is rows [off, off + Himg) of snippet b % n_snip, off = 0 for b < n_snip
+// and off_bot for the others; zero padding applies outside the snippet's rows [0, Hfull).  Plain use: n_snip = image count,
+// off_bot = 0, Hfull = Himg.
 template <bool SPLIT>
 __global__ void __launch_bounds__(256)
 conv0_direct_kernel(const float* __restrict__ in, int mode, long long first, int shift, int in_ld, int Himg, int Wimg,
                     const SelectState* __restrict__ st, __half* __restrict__ out, __half* __restrict__ out_sub,
-                    int tiles_w, int tiles_h, __half* __restrict__ out_lo) {
+                    int tiles_w, int tiles_h, __half* __restrict__ out_lo, long long n_snip, int off_bot, int Hfull) {
   __shared__ float s_x[kC0TH + 2][kC0TW + 2];
   const int tid = threadIdx.x, ty = tid >> 5, tx = tid & 31;
   const int tiles_per = tiles_w * tiles_h;
@@ -340,12 +343,14 @@ conv0_direct_kernel(const float* __restrict__ in, int mode, long long first, int
   const int h0 = (tr / tiles_w) * kC0TH, w0 = (tr % tiles_w) * kC0TW;
   float db_ref = 0.f, lo = 0.f, hi = 1.f, range = 1.f;
   if (mode == 0) { db_ref = st->db_ref; lo = st->lo; hi = st->hi; range = hi - lo; }
-  const long long row0 = (mode == 0) ? (first + b) * shift : b * (long long)Himg;
+  const long long snip = b % n_snip;
+  const int off = b < n_snip ? 0 : off_bot;
+  const long long row0 = ((mode == 0) ? (first + snip) * shift : snip * (long long)Hfull) + off;
   for (int i = tid; i < (kC0TH + 2) * (kC0TW + 2); i += 256) {
     const int r = i / (kC0TW + 2), cc = i - r * (kC0TW + 2);
     const int hh = h0 + r - 1, ww = w0 + cc - 1;
     float v = 0.f;
-    if (hh >= 0 && hh < Himg && ww >= 0 && ww < Wimg) {
+    if (off + hh >= 0 && off + hh < Hfull && ww >= 0 && ww < Wimg) {
       v = in[(size_t)(row0 + hh) * in_ld + ww];
       if (mode == 0) {
         v = fmaxf(v - db_ref, -kTopDbF);
@@ -870,11 +875,13 @@ EncodeTiledFn encode_tiled_fn() {
 
 // rank-5 map over a (n, h, w, chunks, 8) fp16 NHWC tensor; box = {8 ch, 1 chunk, box_w, box_h, 1 snippet}
 // `step` = traversal stride along w and h (2: every other pixel, box_w x box_h pixels are still what lands in shared memory)
-int make_act_map(Ctx* c, CUtensorMap* map, const __half* base, long long n, int h, int w, int cpitch, int box_w, int box_h, int step = 1) {
+// img_rows > 0: consecutive images start img_rows rows apart (overlapping row windows of one tall image) instead of h rows
+int make_act_map(Ctx* c, CUtensorMap* map, const __half* base, long long n, int h, int w, int cpitch, int box_w, int box_h, int step = 1,
+                 long long img_rows = 0) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (!fn) ORCAI_FAIL(c, ORCAI_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
   const cuuint64_t dims[5] = {8, (cuuint64_t)(cpitch / 8), (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
-  const cuuint64_t strides[4] = {16, (cuuint64_t)cpitch * 2, (cuuint64_t)w * cpitch * 2, (cuuint64_t)h * w * cpitch * 2};
+  const cuuint64_t strides[4] = {16, (cuuint64_t)cpitch * 2, (cuuint64_t)w * cpitch * 2, (cuuint64_t)(img_rows > 0 ? img_rows : h) * w * cpitch * 2};
   const cuuint32_t box[5] = {8, 1, (cuuint32_t)(box_w * step), (cuuint32_t)(box_h * step), 1};
   const cuuint32_t estr[5] = {1, 1, (cuuint32_t)step, (cuuint32_t)step, 1};
   const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<__half*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -906,7 +913,7 @@ int run_fused_block(Ctx* c, int blk, const __half* xr, const __half* xs, __half*
   }
   fused::fused_block_kernel<G><<<(unsigned)grid, G::NTHREADS, G::SMEM, c->stream>>>(tmx, tmr, xs ? 1 : 2, yr, ys, Himg, Wimg, n_strips, items,
                                                                                    static_cast<const unsigned char*>(G::PREC ? nw->fbp_w[blk] : nw->fb_w[blk]),
-                                                                                   tmxl, tmrl);
+                                                                                   tmxl, tmrl, fused::TallView());
   c->launches++;
   ORCAI_CUDA(c, cudaGetLastError());
   return ORCAI_OK;
@@ -950,7 +957,7 @@ int run_fused_block1_conv0(Ctx* c, const __half* spec16, long long snippet_strid
                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) ORCAI_FAIL(c, ORCAI_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for the spectrogram view of block 1", (int)r);
   fused::fused_block_kernel<G><<<(unsigned)grid, G::NTHREADS, G::SMEM, c->stream>>>(tms, tms, 2, yr, ys, Himg, Wimg, n_strips, items,
-                                                                                   static_cast<const unsigned char*>(nw->fb_w[0]), tms, tms);
+                                                                                   static_cast<const unsigned char*>(nw->fb_w[0]), tms, tms, fused::TallView());
   c->launches++;
   ORCAI_CUDA(c, cudaGetLastError());
   return ORCAI_OK;
@@ -1048,7 +1055,7 @@ int forward_fused(Ctx* c, const float* d_in, int input_mode, int64_t first, int6
       const float* src = (input_mode == 0) ? d_in : d_in + (size_t)s0 * Himg * Wf;
       conv0_direct_kernel<false><<<(unsigned)(m * tiles_w * tiles_h), 256, 0, c->stream>>>(src, input_mode, first + s0, shift, input_mode == 0 ? kRawLd : Wf,
                                                                                           Himg, Wf, c->d_sel, act[0], static_cast<H*>(nullptr), tiles_w, tiles_h,
-                                                                                          static_cast<H*>(nullptr));
+                                                                                          static_cast<H*>(nullptr), m, 0, Himg);
       c->launches++;
       ORCAI_CUDA(c, cudaGetLastError());
     }

@@ -31,6 +31,7 @@ def main() -> int:
     ap.add_argument("--bn-matched", action="store_true", help="also check weights whose BatchNorm statistics match the activations")
     ap.add_argument("--path", type=int, default=4)
     ap.add_argument("--json", default="")
+    ap.add_argument("--only-timing", action="store_true", help="skip the stage checks (profiling runs)")
     args = ap.parse_args()
     P, S = runtime.bundled_parameters()
     ctx = runtime.get_context(P, S, 0)
@@ -44,7 +45,7 @@ def main() -> int:
     ctx.set_option("net_path", args.path)
     stages = [(0, "conv0 (hi plane)", nhwc["conv0"]), (1, "block1 relu", np.maximum(nhwc["block1"], 0)), (21, "block1 sub", nhwc["block1"][:, ::2, ::2]),
               (2, "block2", nhwc["block2"]), (3, "block3", nhwc["block3"]), (4, "block4", nhwc["block4"]), (5, "final", nhwc["final"])]
-    for stage, key, want in stages:
+    for stage, key, want in ([] if args.only_timing else stages):
         t0 = time.time()
         got = ctx.debug_stage(x, stage)
         if got.shape != want.shape:
@@ -92,12 +93,31 @@ def main() -> int:
         for path in (args.path, 3):
             ctx.set_option("net_path", path)
             if path == 3:
-                ctx.calibrate()
+                ctx.calibrate()          # runs on the built-in calibration recording: bring ours back
+                ctx.upload_pcm(pcm)
+                ctx.spectrogram_resident(normalise=False)
+            if path == 4:   # shared interior (tall image + border rows) against the snippet-by-snippet evaluation: bit-identical
+                ctx.set_option("precise_tall", 0)
+                per_snippet = ctx.forward_resident(0, n)
+                ns0 = ctx.timings()["net_stage_ms"]
+                print("          snippet-by-snippet stage ms: " + " ".join(f"{k}={v:.3f}" for k, v in zip(STAGE_NAMES, ns0)))
+                ctx.set_option("precise_tall", 1)
+                ctx.set_option("chunk", 100)     # several chunks, ragged last one
+                chunked = ctx.forward_resident(0, n)
+                ctx.set_option("chunk", 1024)
             ctx.forward_resident(0, min(n, 64))
             t0 = time.time()
             got = ctx.forward_resident(0, n)
             dt = time.time() - t0
             tm = ctx.timings()
+            if path == 4:
+                same = np.array_equal(got, per_snippet) and np.array_equal(got, chunked)
+                nd = int((got != per_snippet).sum())
+                print(f"[precise] {tag}: tall-image evaluation bit-identical to snippet-by-snippet: {same} ({nd} of {got.size} values differ, max {np.abs(got - per_snippet).max():.3e}; chunked equal: {np.array_equal(got, chunked)})")
+                if nd:
+                    bad = np.argwhere(got != per_snippet)
+                    print("          first differing (snippet, row, label):", bad[:8].tolist(), " rows:", np.unique(bad[:, 1])[:46].tolist())
+                ok &= same
             d = np.abs(got - ref32)
             ns = tm["net_stage_ms"]
             res[path] = {"max": float(d.max()), "mean": float(d.mean()), "p999": float(np.quantile(d, 0.999)), "snippets": n, "wall_s": dt,
