@@ -169,7 +169,9 @@ def main() -> None:
     ap.add_argument("--no-calibrate", action="store_true", help="skip the weight-rounding bias calibration of the tensor-core paths")
     ap.add_argument("--no-parity", action="store_true", help="skip the fp32-path comparison of the measured recording")
     ap.add_argument("--chunk", type=int, default=0, help="snippets per network chunk (0 = library default)")
-    ap.add_argument("--net-path", type=int, default=3, choices=[0, 1, 2, 3], help="0 fp32 CUDA cores, 1 fp16 tcgen05 layer-wise, 2 bf16 tcgen05 layer-wise, 3 fp16 tcgen05 fused residual blocks")
+    ap.add_argument("--net-path", type=int, default=4, choices=[0, 1, 2, 3, 4],
+                    help="4 split-fp16 tcgen05, fp32 grade (the shipped default, inside the 1e-3 gate); 3 single-fp16 fused blocks (opt-in 'fast', outside the gate); "
+                         "0 fp32 CUDA cores; 1 / 2 fp16 / bf16 tcgen05 layer-wise")
     ap.add_argument("--stft-f64", type=int, default=1, choices=[0, 1], help="1 float64 FFT (parity grade, default), 0 float32 FFT")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -201,7 +203,7 @@ def main() -> None:
         ctx.set_option("chunk", args.chunk)
     ctx.set_option("net_path", args.net_path)
     ctx.set_option("stft_f64", args.stft_f64)
-    if args.net_path != 0 and not args.no_calibrate:
+    if args.net_path in (1, 2, 3) and not args.no_calibrate:
         ctx.calibrate()   # what OrcaiModel does when it loads weights (built-in synthetic calibration recording, not the bench file)
 
     # K <= 8 distinct seeded files; rank r annotates file r % 8
@@ -306,7 +308,7 @@ def main() -> None:
         net_ms = stage["network_ms"] / args.steps
         stft_gbs = T * STFT_BYTES_PER_FRAME_I16 / (stft_ms * 1e-3) / 1e9
         net_tflops = n_snip * FLOP_PER_SNIPPET / (net_ms * 1e-3) / 1e12
-        if args.net_path == 3 and net_stage[15] > 0:
+        if args.net_path in (3, 4) and net_stage[15] > 0:
             # dominant kernel = fused residual block 1; duration = CUDA events around its launch (first chunk) on the compute stream
             b1_ms, b1_snips = float(net_stage[1]), float(net_stage[15])
             b1_tflops = 2.0 * BLOCK1_MAC_PER_SNIPPET * b1_snips / (b1_ms * 1e-3) / 1e12
@@ -332,11 +334,13 @@ def main() -> None:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * t_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {0: "f32", 1: "f16", 2: "bf16", 3: "f16"}[args.net_path], "data": "synthetic",
+            "dtype": {0: "f32", 1: "f16", 2: "bf16", 3: "f16", 4: "f16x3 (split fp16 operands, fp32 accumulate: fp32 grade)"}[args.net_path], "data": "synthetic",
             "config": {"workload": WORKLOAD_NAME, "hours_per_gpu_per_step": args.hours, "frames": T, "snippets": n_snip,
                        "segments_found": n_segments, "parallelism": f"shard-by-recording x{world}", "l2": "inputs larger than L2 (346 MB PCM, 475 MB dB per step)",
                        "network_path": {0: "fp32 cuda-core", 1: "fp16 tcgen05 implicit-GEMM trunk + fp32 LSTM/dense", 2: "bf16 tcgen05 implicit-GEMM trunk + fp32 LSTM/dense",
-                                        3: "fp16 tcgen05: pixel-group entry conv, fused residual-block kernels, tcgen05 LSTM projections + TMEM-resident recurrence"}[args.net_path],
+                                        3: "fp16 tcgen05: pixel-group entry conv, fused residual-block kernels, tcgen05 LSTM projections + TMEM-resident recurrence",
+                                        4: "split-fp16 tcgen05 (A_hi*W_hi + A_lo*W_hi + A_hi*W_lo): fused block 1, un-folded blocks 2-4 on split GEMMs, split-GEMM LSTM "
+                                           "projections + fp32 recurrence; shared interior of overlapping snippets (tall image + border rows)"}[args.net_path],
                        "stft": "float64 FFT" if args.stft_f64 else "float32 FFT"},
             "device_ms_per_step": dev_ms,
             "stage_ms": {k: v / args.steps for k, v in stage.items()},

@@ -306,6 +306,7 @@ class Context:
         c_sizes = (C.c_int64 * n)(*[a.size for a in arrs])
         self._check(self.lib.orcai_load_weights(self._h, c_names, c_data, c_sizes, n))
         self.weights_loaded = True
+        self.owner = None   # the OrcaiModel whose weights / options are bound (model.bind()); raw loads belong to nobody
 
     def calibrate(self, pcm: np.ndarray | None = None, max_snippets: int = 8):
         """Fold the mean effect of fp16 weight rounding into the biases of the tensor-core operands (orcai_calibrate).

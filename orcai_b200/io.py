@@ -13,6 +13,7 @@ from __future__ import annotations
 import gzip
 import json
 import os
+import warnings
 import zlib
 from concurrent.futures import ThreadPoolExecutor
 from pathlib import Path
@@ -127,8 +128,9 @@ def load_orcai_model(model_dir: Path | str, device: int | None = None):
     looked up as ``<name>.weights.npz`` (this package's container, see ``orcai_b200/weights.py``), then - like the
     reference, ``io.py:386-404`` - as ``<name>.keras`` (Keras 3 archive) and as the legacy ``model_weights.h5``; both are
     read by ``orcai_b200.keras_weights`` on top of the pure-Python HDF5 reader ``orcai_b200.hdf5_min`` (no keras / h5py).
-    With ``ORCAI_B200_SYNTHETIC_WEIGHTS=<seed>`` set, seeded synthetic weights are used instead (benchmarks / smoke
-    tests; the packaged orcai-v1.keras blob is absent from the reference mount).
+    Only when the directory holds NO weight file at all, ``ORCAI_B200_SYNTHETIC_WEIGHTS=<seed>`` substitutes seeded
+    synthetic weights (benchmarks / smoke tests: the packaged orcai-v1.keras blob is absent from the reference mount) and
+    says so with a warning; real weights are never shadowed by the variable.
     """
     from orcai_b200.model import OrcaiModel
     from orcai_b200.weights import load_npz, synthetic_weights
@@ -141,8 +143,6 @@ def load_orcai_model(model_dir: Path | str, device: int | None = None):
     synth = os.environ.get("ORCAI_B200_SYNTHETIC_WEIGHTS")
     if npz.exists():
         W = load_npz(npz)
-    elif synth is not None:
-        W = synthetic_weights(orcai_parameter, shape, seed=int(synth) if synth.strip().lstrip("-").isdigit() else 1234)
     elif model_dir.joinpath(name + ".keras").exists():
         from orcai_b200.keras_weights import load_keras_archive
 
@@ -151,6 +151,11 @@ def load_orcai_model(model_dir: Path | str, device: int | None = None):
         from orcai_b200.keras_weights import load_weights_h5
 
         W = load_weights_h5(model_dir.joinpath("model_weights.h5"), orcai_parameter, shape)
+    elif synth is not None:
+        seed = int(synth) if synth.strip().lstrip("-").isdigit() else 1234
+        warnings.warn(f"{model_dir} holds no weight file: using SYNTHETIC random weights (ORCAI_B200_SYNTHETIC_WEIGHTS, seed {seed}); "
+                      "the label files of this run are meaningless", RuntimeWarning, stacklevel=2)
+        W = synthetic_weights(orcai_parameter, shape, seed=seed)
     else:
         raise ValueError(f"Couldn't find model weights ({name}.weights.npz, model_weights.h5) or keras model file in {model_dir}")
     model = OrcaiModel(orcai_parameter, shape, W, device=device)

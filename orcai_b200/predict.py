@@ -111,6 +111,9 @@ def filter_predictions_file(
 # staged interfaces (predict.py:235-340)
 # ---------------------------------------------------------------------------------------------
 def _context_of(model, orcai_parameter: dict, shape: dict):
+    """The model's context with THIS model's weights and arithmetic bound (contexts are shared per device, model.bind())."""
+    if hasattr(model, "bind"):
+        return model.bind()
     return getattr(model, "ctx", None) or get_context(orcai_parameter, shape)
 
 
@@ -299,6 +302,7 @@ def predict_wav(
 # writers (predict.py:343-364, 474-531)
 # ---------------------------------------------------------------------------------------------
 _SECONDS_TEXT: dict[float, dict[int, str]] = {}   # delta_t -> {frame index: text of its time in seconds}
+_SECONDS_LOCK = threading.Lock()                  # writer threads of several GPUs share the cache
 
 
 def _seconds_column(values, delta_t: float) -> list[str]:
@@ -313,17 +317,17 @@ def _seconds_column(values, delta_t: float) -> list[str]:
         return [str(int(x)) for x in prod]
     if v.dtype.kind in "iu" and v.size > 64:
         # frame indices repeat from recording to recording: format each distinct (delta_t, frame) once per process
-        cache = _SECONDS_TEXT.setdefault(float(delta_t), {})
         keys = v.tolist()
-        missing = [k for k in set(keys) if k not in cache]
-        if missing:
-            m = np.asarray(missing, dtype=v.dtype)
-            for k, x in zip(missing, np.round((m * np.float64(delta_t)).astype(np.float64), 4)):
-                cache[k] = repr(float(x))
+        with _SECONDS_LOCK:
+            cache = _SECONDS_TEXT.setdefault(float(delta_t), {})
             if len(cache) > 4_000_000:
-                cache.clear()
-                return [repr(float(x)) for x in np.round(prod.astype(np.float64), 4)]
-        return [cache[k] for k in keys]
+                cache = _SECONDS_TEXT[float(delta_t)] = {}      # readers holding the old dict keep a consistent view
+            missing = [k for k in set(keys) if k not in cache]
+            if missing:
+                m = np.asarray(missing, dtype=v.dtype)
+                for k, x in zip(missing, np.round((m * np.float64(delta_t)).astype(np.float64), 4)):
+                    cache[k] = repr(float(x))
+            return [cache[k] for k in keys]
     return [repr(float(x)) for x in np.round(prod.astype(np.float64), 4)]
 
 
@@ -515,6 +519,8 @@ def predict(
         devices = list(dict.fromkeys(devices))   # one context per device in this process: a device listed twice counts once
         msgr.part(f"Loading model: {model_dir.stem}")
         model, orcai_parameter, shape = load_orcai_model(model_dir, device=devices[0] if devices else None)
+        if hasattr(model, "describe"):
+            msgr.info(model.describe())
 
     if recording_path.suffix == ".wav":
         return _predict_and_save(
@@ -642,11 +648,19 @@ def predict(
             cur = fetch(0) if my_rows else None
             for k, i in enumerate(my_rows):
                 res, taken = cur
-                if not isinstance(res, BaseException):
-                    ctx.swap_pcm()
+                # everything of row k - including the hand-over of its samples - fails into row k's report, like the reference
+                # loop (predict.py:752-755); the rows after it still run
+                try:
+                    if not isinstance(res, BaseException):
+                        ctx.swap_pcm()
+                except Exception as e:
+                    res = e
                 if k + depth < len(my_rows):
                     futs[k + depth] = loaders.submit(load, my_rows[k + depth])
-                cur = fetch(k + 1) if k + 1 < len(my_rows) else None   # its upload overlaps the annotation of recording k
+                try:
+                    cur = fetch(k + 1) if k + 1 < len(my_rows) else None   # its upload overlaps the annotation of recording k
+                except Exception as e:
+                    cur = (e, [])
                 fut = run_row(i, mdl, pb, resident=res, writer=writer)
                 if fut is not None:
                     pending.append((i, fut))
@@ -661,7 +675,8 @@ def predict(
 
     if _worker:
         q = _worker["queue"]
-        pipelined(model, [i for i in rows if i in set(_worker["rows"])], None, lambda: q.put(("tick", None)))
+        mine = set(_worker["rows"])
+        pipelined(model, [i for i in rows if i in mine], None, lambda: q.put(("tick", None)))
         return None
     if len(devices) <= 1:
         pipelined(model, rows, progressbar, lambda: progressbar.update(1))
@@ -679,13 +694,20 @@ def predict(
             with lock:
                 progressbar.update(1)
 
-        threads = [
-            threading.Thread(target=pipelined, args=(m, [rows[j] for j in share], None, tick), daemon=True)
-            for m, share in zip(models, plan)
-        ]
+        failures = []
+
+        def guarded(m, share):
+            try:
+                pipelined(m, share, None, tick)
+            except BaseException as e:  # noqa: BLE001 - a dead worker must not look like a finished table
+                failures.append((m.ctx.device if hasattr(m.ctx, "device") else "?", e, share))
+
+        threads = [threading.Thread(target=guarded, args=(m, [rows[j] for j in share]), daemon=True) for m, share in zip(models, plan)]
         for t in threads:
             t.start()
         for t in threads:
             t.join()
+        for dev, e, share in failures:
+            msgr.error(f"Error in table worker on device {dev}: {type(e).__name__}: {e} ({len(share)} recordings assigned, some not processed)")
     progressbar.close()
     msgr.success("Predictions finished.")

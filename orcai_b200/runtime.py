@@ -42,7 +42,7 @@ def shape_for(orcai_parameter: dict) -> dict:
 
 def get_context(orcai_parameter: dict, shape: dict, device: int | None = None) -> Context:
     dev = default_device() if device is None else int(device)
-    key = (dev, json.dumps(orcai_parameter["spectrogram"], sort_keys=True), json.dumps(orcai_parameter["model"].get("filters")),
+    key = (dev, json.dumps(orcai_parameter["spectrogram"], sort_keys=True), json.dumps(orcai_parameter["model"], sort_keys=True),
            json.dumps(shape, sort_keys=True))
     ctx = _contexts.get(key)
     if ctx is None:

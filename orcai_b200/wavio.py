@@ -6,9 +6,10 @@ any channel count.  Conversion to float follows libsndfile: PCM16 / 2^15, PCM24 
 PCM32 / 2^31, unsigned 8 bit (x-128) / 2^7, floats unchanged.  PCM16 mono is handed to the
 GPU as raw int16 (half the upload); the kernel applies the same exact power-of-two scale.
 
-Resampling is NOT implemented: the reference resamples through soxr_hq when the file rate
-differs from orcai_parameter["spectrogram"]["sampling_rate"]; that resampler has no in-tree
-specification.  Such files raise ``ValueError``.
+This module never resamples.  The reference resamples through soxr_hq when the file rate differs
+from orcai_parameter["spectrogram"]["sampling_rate"]; that resampler has no in-tree specification
+(SURVEY.md section 8f rank 3), so ``orcai_b200.spectrogram.load_recording`` stands in with a
+polyphase resampler (scipy.signal.resample_poly) - the one step of the path whose parity is unpinned.
 """
 
 from __future__ import annotations

@@ -53,9 +53,14 @@ def oracle_label_text(pcm, P, S, probs_from=None):
     return po.labels_tsv(po.label_rows(s, e, n, 16, "*"), float(t[1] - t[0])), agg
 
 
-@pytest.mark.parametrize("precision,tol", [("reference", 1e-3), ("fast", 2.5e-3)])  # fast: see FAST_TOL in test_gpu_network.py
+# None = the shipped default (precise: split-fp16 tensor cores), held to 1e-4; "fast" is opt-in and outside the 1e-3 gate
+# (FAST_TOL in test_gpu_network.py)
+@pytest.mark.parametrize("precision,tol", [(None, 1e-4), ("reference", 1e-3), ("fast", 2.5e-3)])
 def test_predict_single_wav_file_contract(ctx, params, model_dir, wavs, monkeypatch, precision, tol):
-    monkeypatch.setenv("ORCAI_B200_PRECISION", precision)
+    if precision is None:
+        monkeypatch.delenv("ORCAI_B200_PRECISION", raising=False)
+    else:
+        monkeypatch.setenv("ORCAI_B200_PRECISION", precision)
     P, S = params
     d, files = wavs
     wav, pcm = files[0]

@@ -10,10 +10,14 @@ from orcai_b200.weights import synthetic_weights
 pytestmark = pytest.mark.gpu
 
 PROB_TOL = 1e-3  # north_star: per-frame probabilities within 1e-3 absolute (fp32 path: measured 1e-6)
-# 16-bit tensor-core operands (fp16, fp32 accumulation), after the weight-rounding bias calibration (orcai_calibrate, on the
-# built-in synthetic recording - never on the test input).  Measured against the fp32 graph: max 0.9e-3 on the cases below,
-# 2.7e-3 over a whole 1-h recording (295 k probabilities), mean 1.0e-4.  Uncalibrated: 2e-3 .. 7e-3 (fp16 weight rounding is
-# coherent across pixels; tools/precision_study.py reproduces this on the CPU), bf16: 1.2e-2 .. 1.9e-2.
+# The DEFAULT network path (net_path 4, "precise"): every GEMM on the fp16 tensor cores as the three-term split
+# A_hi*W_hi + A_lo*W_hi + A_hi*W_lo with fp32 accumulation.  Held ten times tighter than the gate; measured 4e-6 on the cases
+# below and 2e-5 over a whole recording (tools/gpu_check_precise.py, profiles/r02*).
+PRECISE_TOL = 1e-4
+# OPT-IN fast path (net_path 3, ORCAI_B200_PRECISION=fast): single fp16 operands, biases calibrated against the weight rounding
+# (orcai_calibrate on the built-in synthetic recording).  It does NOT meet the 1e-3 gate: max 0.9e-3 on the cases below but
+# 2.7e-3 over a whole 1-h recording, mean 1.0e-4 (tools/precision_plan.py attributes it: every fp16 weight tensor and stored
+# activation costs 2e-4 .. 2e-3).  These bounds document that path; nothing shipped by default depends on them.
 FAST_TOL = 2.5e-3
 FAST_MEAN_TOL = 3e-4
 
@@ -261,3 +265,141 @@ def test_block1_n_widened_variant(ctx, params):
         ctx.set_option("block1_path", 0)
         ctx.set_option("net_path", 0)
         ctx.set_option("chunk", 128)
+
+
+# ------------------------------------------------------------------------------------------------
+# the default path: split-fp16 tensor-core GEMMs (net_path 4)
+# ------------------------------------------------------------------------------------------------
+def _bn_matched(W, P, seconds=20.0):
+    """Weights whose BatchNorm moving statistics match their activations (as training leaves them): the harder case for 16-bit
+    arithmetic."""
+    import sys
+    from pathlib import Path
+
+    sys.path.insert(0, str(Path(__file__).resolve().parent.parent / "tools"))
+    import precision_study as ps
+
+    spec, _, _ = so.make_spectrogram(pcm16_to_float(synth_pcm16(seconds, seed=20251018)), P["spectrogram"])
+    return ps.calibrate_bn(W, po.cut_snippets(spec, 736)[:2])
+
+
+def test_precise_path_against_oracle(ctx, params, golden_dir):
+    """net_path 4 against the golden probabilities and the oracle: 1e-4 (gate 1e-3); chunking and batch composition change nothing."""
+    P, S = params
+    W = synthetic_weights(P, S, seed=1234)
+    g = np.load(golden_dir / "network_seed1234.npz")
+    x = np.random.default_rng(5).random((2, 736, 171), dtype=np.float32)
+    ctx.set_option("net_path", 4)
+    try:
+        out = ctx.forward_host(x)
+        assert out.shape == (2, 46, 7) and out.dtype == np.float32 and np.isfinite(out).all()
+        assert np.abs(out - g["probs"]).max() <= PRECISE_TOL
+        x7 = np.random.default_rng(9).random((7, 736, 171), dtype=np.float32)
+        full = ctx.forward_host(x7)
+        assert np.abs(full - network_oracle.forward(x7, W)).max() <= PRECISE_TOL
+        ctx.set_option("chunk", 3)
+        np.testing.assert_array_equal(ctx.forward_host(x7), full)
+        ctx.set_option("chunk", 1024)
+        np.testing.assert_array_equal(ctx.forward_host(x7[4:5]), full[4:5])
+        # stage by stage against the oracle's intermediates (un-rectified block outputs, fp32)
+        _, inter = network_oracle.forward(x[:1], W, return_intermediates=True)
+        for stage, key in ((1, "block1"), (2, "block2"), (3, "block3"), (4, "block4"), (5, "final")):
+            want = np.transpose(inter[key], (0, 2, 3, 1))
+            got = ctx.debug_stage(x[:1], stage)
+            assert got.shape == want.shape
+            assert np.abs(got - want).max() <= 2e-5 * np.abs(want).max() + 1e-5, key
+    finally:
+        ctx.set_option("net_path", 0)
+        ctx.set_option("chunk", 128)
+
+
+def test_precise_shared_interior_is_bit_identical(ctx, params):
+    """Resident recordings run the trunk once over the recording as a tall image and recompute only the rows that feel a
+    snippet's own border (predict.py:252-261 cuts overlapping windows).  That must not change a single bit against the
+    snippet-by-snippet evaluation, for any chunking and any sub-range, and both must sit on the fp32 path."""
+    P, S = params
+    pcm = synth_pcm16(61.0, seed=77, calls_per_minute=40.0)
+    spec, st = ctx.spectrogram(pcm)
+    n = int((st.n_frames - 736) // 368 + 1)
+    assert n >= 29
+    ref32 = ctx.forward_resident(0, n)
+    ctx.set_option("net_path", 4)
+    try:
+        ctx.set_option("precise_tall", 0)
+        per_snippet = ctx.forward_resident(0, n)
+        copies = ctx.forward_host(po.cut_snippets(spec, 736))
+        np.testing.assert_array_equal(per_snippet, copies)          # the strided snippet batcher == materialised copies
+        ctx.set_option("precise_tall", 1)
+        tall = ctx.forward_resident(0, n)
+        np.testing.assert_array_equal(tall, per_snippet)
+        ctx.set_option("chunk", 5)                                   # ragged chunks: the tall images overlap by one snippet shift
+        np.testing.assert_array_equal(ctx.forward_resident(0, n), per_snippet)
+        ctx.set_option("chunk", 1024)
+        np.testing.assert_array_equal(ctx.forward_resident(3, 7), per_snippet[3:10])
+        np.testing.assert_array_equal(ctx.forward_resident(n - 1, 1), per_snippet[n - 1:])
+        assert np.abs(tall - ref32).max() <= PRECISE_TOL
+    finally:
+        ctx.set_option("precise_tall", 1)
+        ctx.set_option("net_path", 0)
+        ctx.set_option("chunk", 128)
+
+
+@pytest.mark.parametrize("bn_matched", [False, True])
+def test_precise_path_one_hour_inside_the_gate(ctx, params, bn_matched):
+    """A 1-h recording (1 833 snippets, 590 k probabilities), seeded and BatchNorm-matched weights: the default path stays
+    within 1e-3 of the fp32 path (which is held to the oracle at 1e-6) - measured 2e-5 - and labels the same segments."""
+    P, S = params
+    W = synthetic_weights(P, S, seed=1234)
+    if bn_matched:
+        W = _bn_matched(W, P)
+    pcm = synth_pcm16(3600.0, seed=20251018)
+    try:
+        ctx.load_weights(W)
+        ctx.set_option("chunk", 1024)
+        ctx.upload_pcm(pcm)
+        st = ctx.spectrogram_resident(normalise=False)
+        n = int((st.n_frames - 736) // 368 + 1)
+        assert n == 1833
+        ref32 = ctx.forward_resident(0, n)
+        seg32 = ctx.predict_pcm(pcm, resident=True)
+        ctx.set_option("net_path", 4)
+        got = ctx.forward_resident(0, n)
+        seg = ctx.predict_pcm(pcm, resident=True)
+        dev = np.abs(got - ref32)
+        assert dev.max() <= PROB_TOL, dev.max()
+        assert dev.max() <= PRECISE_TOL, dev.max()
+        # identical thresholded masks -> identical segments (labels, starts, stops)
+        for i in (3, 4, 5):
+            np.testing.assert_array_equal(seg[i], seg32[i])
+        assert np.abs(seg[1] - seg32[1]).max() <= PRECISE_TOL
+    finally:
+        ctx.set_option("net_path", 0)
+        ctx.set_option("chunk", 128)
+        ctx.load_weights(synthetic_weights(P, S, seed=1234))
+
+
+def test_precise_path_edge_lengths_and_silence(ctx):
+    """One snippet exactly, one snippet plus an uncovered tail, an odd multi-snippet length, and all-zero audio on the default path."""
+    for n_samples in (735 * 256, 735 * 256 + 367 * 256 + 17, (736 + 368 * 4 + 5) * 256 + 3):
+        pcm = synth_pcm16(n_samples / 48000.0 + 0.01, seed=123, calls_per_minute=60.0)[:n_samples]
+        T = 1 + n_samples // 256
+        n = (T - 736) // 368 + 1
+        ctx.set_option("net_path", 0)
+        ref = ctx.predict_pcm(pcm)
+        ctx.set_option("net_path", 4)
+        try:
+            got = ctx.predict_pcm(pcm)
+        finally:
+            ctx.set_option("net_path", 0)
+        assert got[0].n_frames == T and got[1].shape == (T // 16, 7)
+        np.testing.assert_array_equal(got[2], ref[2])
+        assert np.abs(got[1] - ref[1]).max() <= PRECISE_TOL
+        assert (got[1][23 * (n - 1) + 46:] == 0).all()
+        for i in (3, 4, 5):
+            np.testing.assert_array_equal(got[i], ref[i])
+    ctx.set_option("net_path", 4)
+    try:
+        st, agg, cnt, lab, sta, sto = ctx.predict_pcm(np.zeros(48000 * 6, np.int16))
+    finally:
+        ctx.set_option("net_path", 0)
+    assert len(lab) == 0 and len(sta) == 0 and cnt.max() == 2 and np.isnan(agg[cnt > 0]).all()

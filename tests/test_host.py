@@ -197,6 +197,9 @@ def test_precision_selector(monkeypatch):
     from orcai_b200 import model
 
     monkeypatch.delenv("ORCAI_B200_PRECISION", raising=False)
+    # the shipped default is the path inside the 1e-3 gate; the single-fp16 "fast" path is opt-in
+    assert model.precision_from_env() == "precise" == model.DEFAULT_PRECISION and model.PRECISION_PATHS["precise"] == 4
+    monkeypatch.setenv("ORCAI_B200_PRECISION", "fast")
     assert model.precision_from_env() == "fast" and model.PRECISION_PATHS["fast"] == 3
     monkeypatch.setenv("ORCAI_B200_PRECISION", "Reference ")
     assert model.precision_from_env() == "reference" and model.PRECISION_PATHS["reference"] == 0
@@ -320,3 +323,42 @@ def test_wav_reader_into_caller_memory(tmp_path):
     cut_plain = wavio.read_wav(tmp_path / "cut.wav", 1)[0]
     cut_alloc = wavio.read_wav(tmp_path / "cut.wav", 1, alloc=alloc)[0]
     np.testing.assert_array_equal(cut_plain, cut_alloc)
+
+
+def test_model_rebinds_a_shared_context(monkeypatch):
+    """Contexts are shared per (device, parameters); a model must re-bind its own weights and arithmetic before it predicts,
+    so that loading a second model never makes the first one predict with the other's weights (model.bind())."""
+    from orcai_b200 import model as model_mod, runtime
+    from orcai_b200.weights import synthetic_weights
+
+    calls = []
+
+    class FakeCtx:
+        owner = None
+
+        def load_weights(self, W):
+            calls.append(("load", float(W["dense2/bias"][0])))
+            self.owner = None
+
+        def set_option(self, k, v):
+            calls.append((k, v))
+
+        def calibrate(self, *a, **k):
+            calls.append(("calibrate",))
+
+    fake = FakeCtx()
+    monkeypatch.setattr(model_mod, "get_context", lambda *a, **k: fake)
+    P, S = runtime.bundled_parameters()
+    W1 = synthetic_weights(P, S, seed=1)
+    W2 = {k: v.copy() for k, v in W1.items()}
+    W2["dense2/bias"] = W2["dense2/bias"] + 1.0
+    m1 = model_mod.OrcaiModel(P, S, W1, precision="precise")
+    m2 = model_mod.OrcaiModel(P, S, W2, precision="fast")
+    assert ("net_path", 4) in calls and ("net_path", 3) in calls and ("calibrate",) in calls
+    del calls[:]
+    assert m2.bind() is fake and calls == []                     # still the owner: nothing to do
+    m1.bind()                                                    # m1 takes the context back: its weights, its path, no calibration
+    assert calls[0] == ("load", float(W1["dense2/bias"][0])) and ("net_path", 4) in calls and ("calibrate",) not in calls
+    assert "precise" in m1.describe() and "calibration" in m2.describe()
+    with pytest.raises(ValueError):
+        model_mod.OrcaiModel(P, S, W1, precision="bf16")
