@@ -90,6 +90,7 @@ struct NetWeights {
   float* p_res_w[kMaxBlocks] = {};   // [CIP][COP] fp32, zero padded
   float* p_res_b[kMaxBlocks] = {};   // [COP]
   int chunk_precise = 1024;
+  int precise_sep_path = 1;   // un-folded separable convolutions: 1 = depthwise fused into the split GEMM (sep_uf_kernel), 0 = two kernels
   int precise_tall = 1;       // resident recordings: trunk once over the chunk's rows as one tall image + per-snippet border rows
   int debug_stop = -1;        // stop the forward after this stage (debug reads), -1 = run everything
   // last debug buffer: kind 0 f32, 1 fp16, 2 bf16 ; NHWC with channel pitch dbg_pitch

@@ -143,6 +143,192 @@ assemble_feat_kernel(const float* __restrict__ tall, const float* __restrict__ b
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// One un-folded separable convolution as ONE kernel: depthwise 3x3 on the CUDA cores straight into the A operand of the
+// pointwise split GEMM.   out[p][n] = act( sum_k d[p][k] * PW[k][n] + bias[n] ),  d[p][k] = sum_taps dw[tap][k] * f(x[p + tap][k])
+//
+//   tile      16 x 8 pixels = the 128 rows of one tcgen05.mma; its 18 x 10 halo arrives as ONE TMA box of the fp32 NHWC tensor
+//             ([18][10][CP] floats; image borders are zero-filled by the TMA unit = the "same" padding)
+//   workers   4 warps.  Thread t < 8 * Q (Q = CP / 4 channel quads) owns tile column t / Q and channel quad t % Q and walks the
+//             rows with a sliding 3 x 3 window in registers: 3 conflict-free LDS.128 + 36 FFMA per output float4; the results go
+//             to the (hi, lo) A planes (canonical K-major, plane pitch padded by 16 B against bank conflicts)
+//   issuer    1 warp: TMA of the next halo as soon as the workers have read the current one, then 3 MMAs per K step
+//             (A_hi*B_hi + A_lo*B_hi + A_hi*B_lo, N = 64, fp32 accumulation in TMEM)
+//   epilogue  the workers drain TMEM (thread = pixel), add the bias, apply the ReLU, store fp32 NHWC rows
+// Two CTAs per SM overlap each other's phases.  x: (n, H, W, CP), out: (n, H, W, ldc); CP <= 64, ldc <= 64.
+constexpr int kUfTH = 16, kUfTW = 8, kUfHalo = (kUfTH + 2) * (kUfTW + 2);
+constexpr uint32_t kUfLboA = 128 * 16 + 16;                           // A plane pitch (one 8-channel chunk of 128 rows) + pad
+struct UfSmem {
+  static constexpr uint32_t OFF_HALO = 0;                              // [18][10][CP] fp32, up to 46 080 B
+  static constexpr uint32_t OFF_A = 46080;                             // 8 hi planes, 8 lo planes
+  static constexpr uint32_t A_HALF = 8 * kUfLboA;
+  static constexpr uint32_t OFF_B = OFF_A + 2 * A_HALF;                // [hi | lo] 64 x 64 fp16 blocks
+  static constexpr uint32_t B_HALF = 64 * 64 * 2;
+  static constexpr uint32_t OFF_BAR = OFF_B + 2 * B_HALF;              // halo_full, halo_free, a_full, acc_full, acc_free, b_full
+  static constexpr uint32_t BYTES = OFF_BAR + 6 * 8 + 16;
+};
+static_assert(UfSmem::BYTES * 2 + 2048 <= 227 * 1024, "two CTAs per SM");
+
+template <bool RELU_IN, int ACT>
+__global__ void __launch_bounds__(160, 2)
+sep_uf_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__ dw, const __half* __restrict__ Bp, const float* __restrict__ bias,
+              float* __restrict__ out, long long n_img, int H, int W, int CP, int ldc, int n_valid, int tiles_w, int tiles_h) {
+  using S = UfSmem;
+  extern __shared__ __align__(128) unsigned char smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 6);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int Q = CP >> 2;
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);      // halo_full: TMA complete_tx
+    mbar_init(&bars[1], 4);      // halo_free: one arrival per worker warp
+    mbar_init(&bars[2], 4);      // a_full
+    mbar_init(&bars[3], 1);      // acc_full: tcgen05.commit
+    mbar_init(&bars[4], 4);      // acc_free
+    mbar_init(&bars[5], 1);      // b_full
+    fence_mbar_init();
+  }
+  for (int i = tid; i < (int)(2 * S::A_HALF / 16); i += 160) reinterpret_cast<uint4*>(smem + S::OFF_A)[i] = make_uint4(0, 0, 0, 0);   // unused K planes stay zero
+  __syncwarp();
+  if (warp == 0) tmem_alloc<64>(tslot);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tslot;
+  const uint32_t sbase = smem_u32(smem);
+  const long long tiles_per = (long long)tiles_w * tiles_h;
+  const long long total = n_img * tiles_per;
+  const uint32_t halo_bytes = (uint32_t)kUfHalo * CP * 4;
+
+  if (warp == 4) {
+    // =============================== issuer: TMA + MMA ===============================
+    if (fused::elect_one()) {
+      fused::mbar_arrive_expect_tx(&bars[5], 2 * S::B_HALF);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sbase + S::OFF_B), "l"(Bp),
+                   "r"(2 * S::B_HALF), "r"(smem_u32(&bars[5]))
+                   : "memory");
+    }
+    __syncwarp();
+    constexpr uint32_t idesc = make_idesc_f16(128, 64, 0);
+    const uint64_t da = make_smem_desc(sbase + S::OFF_A, kUfLboA, 128);
+    const uint64_t db = make_smem_desc(sbase + S::OFF_B, 128, 8 * 128);
+    const int ksteps = (CP + 15) >> 4;
+    long long it = 0;
+    for (long long tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+      const long long b = tile / tiles_per;
+      const int tr = (int)(tile - b * tiles_per);
+      const int h0 = (tr / tiles_w) * kUfTH, w0 = (tr % tiles_w) * kUfTW;
+      if (it > 0) mbar_wait(&bars[1], (uint32_t)((it - 1) & 1));          // the workers have read the previous halo
+      if (fused::elect_one()) {
+        fused::mbar_arrive_expect_tx(&bars[0], halo_bytes);
+        fused::tma_load_4d(sbase + S::OFF_HALO, &tmX, &bars[0], 0, w0 - 1, h0 - 1, (int)b);
+      }
+      __syncwarp();
+      if (it == 0) mbar_wait(&bars[5], 0);
+      mbar_wait(&bars[2], (uint32_t)(it & 1));                             // A planes of this tile written
+      if (it > 0) mbar_wait(&bars[4], (uint32_t)((it - 1) & 1));          // accumulator drained
+      tc_fence_after();
+      if (fused::elect_one()) {
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint64_t a = da + ((2 * ks * kUfLboA) >> 4), bb = db + ((2 * ks * 128) >> 4);
+          mma_f16_ss(tmem, a, bb, idesc, ks != 0);
+          mma_f16_ss(tmem, a + (S::A_HALF >> 4), bb, idesc, 1);
+          mma_f16_ss(tmem, a, bb + (S::B_HALF >> 4), idesc, 1);
+        }
+        mma_commit(&bars[3]);
+      }
+      __syncwarp();
+    }
+  } else {
+    // =============================== workers ===============================
+    const int nseg = 128 / (8 * Q) >= 2 ? 2 : 1;                            // Q = 8: two row segments of 8 rows, else one of 16
+    const int cq = tid % (8 * Q), seg = tid / (8 * Q);
+    const bool active = seg < nseg;
+    const int col = cq / Q, quad = cq - col * Q;
+    const int rows = kUfTH / nseg, r0 = seg * rows;
+    float4 k[9];
+#pragma unroll
+    for (int t = 0; t < 9; ++t) k[t] = active ? __ldg(reinterpret_cast<const float4*>(dw + t * CP + 4 * quad)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4* halo = reinterpret_cast<const float4*>(smem + S::OFF_HALO);
+    const int hrow = (kUfTW + 2) * Q;                                       // float4 per halo row
+    auto ld = [&](int y, int x) {
+      float4 v = halo[y * hrow + x * Q + quad];
+      if (RELU_IN) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+      return v;
+    };
+    const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+    long long it = 0;
+    for (long long tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+      const long long b = tile / tiles_per;
+      const int tr = (int)(tile - b * tiles_per);
+      const int h0 = (tr / tiles_w) * kUfTH, w0 = (tr % tiles_w) * kUfTW;
+      mbar_wait(&bars[0], (uint32_t)(it & 1));
+      if (it > 0) mbar_wait(&bars[3], (uint32_t)((it - 1) & 1));          // the MMAs that read the A planes are done ...
+      // (... and this thread's epilogue of the previous tile below has run: program order)
+      if (active) {
+        float4 w[3][3];
+#pragma unroll
+        for (int y = 0; y < 2; ++y)
+#pragma unroll
+          for (int x = 0; x < 3; ++x) w[y + 1][x] = ld(r0 + y, col + x);
+        for (int r = 0; r < rows; ++r) {
+#pragma unroll
+          for (int x = 0; x < 3; ++x) { w[0][x] = w[1][x]; w[1][x] = w[2][x]; w[2][x] = ld(r0 + r + 2, col + x); }
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int t = 0; t < 9; ++t) {
+            const float4 v = w[t / 3][t % 3];
+            acc.x = fmaf(v.x, k[t].x, acc.x); acc.y = fmaf(v.y, k[t].y, acc.y); acc.z = fmaf(v.z, k[t].z, acc.z); acc.w = fmaf(v.w, k[t].w, acc.w);
+          }
+          const __half2 h01 = __floats2half2_rn(acc.x, acc.y), h23 = __floats2half2_rn(acc.z, acc.w);
+          const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+          const __half2 l01 = __floats2half2_rn(acc.x - f01.x, acc.y - f01.y), l23 = __floats2half2_rn(acc.z - f23.x, acc.w - f23.y);
+          const int prow = (r0 + r) * kUfTW + col;
+          unsigned char* dst = smem + S::OFF_A + (quad >> 1) * kUfLboA + prow * 16 + (quad & 1) * 8;
+          uint2 hv, lv;
+          hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+          lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+          *reinterpret_cast<uint2*>(dst) = hv;
+          *reinterpret_cast<uint2*>(dst + S::A_HALF) = lv;
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) { fused::mbar_arrive(&bars[1]); fused::mbar_arrive(&bars[2]); }
+      // ---- epilogue: accumulator row tid = pixel (tid / 8, tid % 8) ----
+      mbar_wait(&bars[3], (uint32_t)(it & 1));
+      tc_fence_after();
+      const int hh = h0 + (tid >> 3), ww = w0 + (tid & 7);
+      const bool inside = hh < H && ww < W;
+      float* orow = out + (((size_t)b * H + hh) * W + ww) * ldc;
+#pragma unroll 2
+      for (int c0 = 0; c0 < 64; c0 += 16) {
+        if (c0 >= n_valid) break;
+        float v[16];
+        tmem_ld16(lane_addr + c0, v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          v[i] += __ldg(bias + c0 + i);
+          if (ACT == 1) v[i] = fmaxf(v[i], 0.f);
+        }
+        if (inside) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            if (c0 + 4 * q + 4 <= n_valid) reinterpret_cast<float4*>(orow + c0)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) fused::mbar_arrive(&bars[4]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<64>(tmem);
+}
+
 }  // namespace precise
 
 // block 1 of the fp32-grade path: one CTA per SM (the (hi, lo) plane sets fill its shared memory), two issuer warps; its output
@@ -182,11 +368,52 @@ int prepare_precise(Ctx* c) {
   return ORCAI_OK;
 }
 
-// one un-folded separable convolution: d = dw3x3(f(x)) ; out = act(d * pw + bias).  x (n, h, w, cip) fp32 -> out (n, h, w, ldc) fp32
+// rank-4 map over an fp32 NHWC tensor (n, h, w, cp); box = {cp, 10, 18, 1}: the halo of a 16 x 8 pixel tile
+int make_uf_map(Ctx* c, CUtensorMap* map, const float* base, long long n, long long h, int w, int cp) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) ORCAI_FAIL(c, ORCAI_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t dims[4] = {(cuuint64_t)cp, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  const cuuint64_t strides[3] = {(cuuint64_t)cp * 4, (cuuint64_t)w * cp * 4, (cuuint64_t)h * w * cp * 4};
+  const cuuint32_t box[4] = {(cuuint32_t)cp, (cuuint32_t)(precise::kUfTW + 2), (cuuint32_t)(precise::kUfTH + 2), 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) ORCAI_FAIL(c, ORCAI_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for tensor (%lld, %lld, %d, %d)", (int)r, n, h, w, cp);
+  return ORCAI_OK;
+}
+
+template <bool RELU_IN, int ACT>
+int launch_sep_uf(Ctx* c, const float* x, float* out, long long n, long long h, int w, int cip, int ldc, int n_valid, const NetWeights::PreciseSep& ps) {
+  static std::atomic<unsigned long long> attr_devices{0ull};
+  if (!((attr_devices.load() >> (c->device & 63)) & 1ull)) {
+    ORCAI_CUDA(c, cudaFuncSetAttribute(precise::sep_uf_kernel<RELU_IN, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)precise::UfSmem::BYTES));
+    attr_devices.fetch_or(1ull << (c->device & 63));
+  }
+  CUtensorMap tm;
+  ORCAI_CHECK(make_uf_map(c, &tm, x, n, h, w, cip));
+  const int tiles_w = (w + precise::kUfTW - 1) / precise::kUfTW, tiles_h = (int)((h + precise::kUfTH - 1) / precise::kUfTH);
+  const long long total = n * tiles_w * tiles_h;
+  const unsigned grid = (unsigned)std::min<long long>(total, (long long)c->sm_count * 2);
+  precise::sep_uf_kernel<RELU_IN, ACT><<<grid, 160, precise::UfSmem::BYTES, c->stream>>>(tm, ps.dw, ps.pw, ps.bias, out, n, (int)h, w, cip, ldc, n_valid, tiles_w,
+                                                                                        tiles_h);
+  c->launches++;
+  ORCAI_CUDA(c, cudaGetLastError());
+  return ORCAI_OK;
+}
+
+// one un-folded separable convolution: out = act(dw3x3(f(x)) * pw + bias).  x (n, h, w, cip) fp32 -> out (n, h, w, ldc) fp32.
+// sep_path 1 (default): one kernel (sep_uf_kernel); 0: depthwise kernel -> d, then the split GEMM (bit-identical results: the same
+// fp32 FMA order per pixel and the same three MMAs per K step).
 int run_precise_sep(Ctx* c, const float* x, float* d, float* out, long long n, long long h, int w, int cip, int ldc, int n_valid, bool relu_in,
                     bool relu_out, const NetWeights::PreciseSep& ps) {
   const long long total = n * h * w * (cip / 4);
   if (total <= 0) return ORCAI_OK;
+  if (c->net->precise_sep_path == 1) {
+    if (relu_in && relu_out) return launch_sep_uf<true, 1>(c, x, out, n, h, w, cip, ldc, n_valid, ps);
+    if (relu_in) return launch_sep_uf<true, 0>(c, x, out, n, h, w, cip, ldc, n_valid, ps);
+    if (relu_out) return launch_sep_uf<false, 1>(c, x, out, n, h, w, cip, ldc, n_valid, ps);
+    return launch_sep_uf<false, 0>(c, x, out, n, h, w, cip, ldc, n_valid, ps);
+  }
   const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, (long long)c->sm_count * 32);
   if (relu_in) precise::dw3x3_kernel<true><<<grid, 256, 0, c->stream>>>(x, d, ps.dw, n, (int)h, w, cip);
   else precise::dw3x3_kernel<false><<<grid, 256, 0, c->stream>>>(x, d, ps.dw, n, (int)h, w, cip);

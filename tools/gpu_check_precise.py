@@ -78,6 +78,13 @@ def main() -> int:
     same = np.array_equal(full, chunked) and np.array_equal(ctx.forward_host(x7[4:5]), full[4:5])
     print(f"[precise] chunking / batch independence bit-identical: {same}")
     ok &= same
+    if args.path == 4:   # depthwise fused into the split GEMM (default) against the two-kernel form
+        ctx.set_option("precise_sep_path", 0)
+        two = ctx.forward_host(x7)
+        ctx.set_option("precise_sep_path", 1)
+        same = np.array_equal(two, full)
+        print(f"[precise] fused depthwise+GEMM kernel bit-identical to depthwise kernel -> GEMM: {same} (max diff {np.abs(two - full).max():.3e})")
+        ok &= same
 
     # whole recording: per-snippet probabilities against the fp32 CUDA-core path, stage timings
     def whole(tag, weights):
