@@ -42,8 +42,12 @@ FLOP_PER_SNIPPET = 0.972e9  # 485.8 M MAC
 BLOCK1_MAC_PER_SNIPPET = 736 * 171 * (9 * 16 + 16 * 30) + 736 * 171 * (9 * 30 + 30 * 30) + 368 * 86 * 16 * 30
 # what the folded implicit GEMM executes for it: 123 steps x 3 strips per snippet, 88 tcgen05.mma of 128 x 32 x 16 per step
 BLOCK1_EXECUTED_MAC_PER_SNIPPET = 123 * 3 * 88 * 128 * 32 * 16
-# dram__bytes_read + dram__bytes_write of that kernel per snippet, from the ncu --set full capture under profiles/ (None until measured)
-BLOCK1_TRAFFIC_BYTES_PER_SNIPPET = (919.085568e6 + 431.915008e6) / 182  # profiles/r01e_ncu_full_summary.csv (182-snippet launch)
+# dram__bytes_read + dram__bytes_write of the dominant kernel per snippet, from the LATEST committed ncu --set full capture of that
+# kernel (profiles/; the file is named with the number): net_path -> {bytes_per_snippet, source}
+BLOCK1_TRAFFIC = {
+    3: {"bytes_per_snippet": (734.0e6 + 425.0e6) / 182, "source": "profiles/r01g_ncu_full_summary.csv (182-snippet launch)"},
+}
+SELECT_PASSES = 3   # times the select streams the 704 B/frame dB buffer
 
 
 def _peaks() -> dict:
@@ -155,6 +159,52 @@ def run_reference(args) -> None:
 
 
 WORKLOAD_NAME = "orcai predict (orcai-V1, synthetic weights) on one synthetic 1-hour 48 kHz mono PCM16 recording per GPU per step"
+NET_PATH_NAMES = {
+    0: "fp32 cuda-core", 1: "fp16 tcgen05 implicit-GEMM trunk + fp32 LSTM/dense", 2: "bf16 tcgen05 implicit-GEMM trunk + fp32 LSTM/dense",
+    3: "fp16 tcgen05: pixel-group entry conv, fused residual-block kernels, tcgen05 LSTM projections + TMEM-resident recurrence",
+    4: "split-fp16 tcgen05 (A_hi*W_hi + A_lo*W_hi + A_hi*W_lo, fp32 accumulate = fp32 grade): fused block 1, un-folded blocks 2-4 with the depthwise "
+       "filter fused into the split pointwise GEMM, split-GEMM LSTM projections + fp32 recurrence; shared interior of overlapping snippets",
+}
+NET_DTYPE = {0: "f32", 1: "f16", 2: "bf16", 3: "f16", 4: "f16x3 (split fp16 operands, fp32 accumulate)"}
+STAGES = ["conv0", "block1", "block2", "block3", "block4", "final_sep", "lstm1_proj", "lstm1_rec", "lstm2_proj", "lstm2_rec", "dense"]
+
+
+def bench_dir() -> Path:
+    d = Path(os.environ.get("ORCAI_BENCH_DIR", f"/tmp/orcai_b200_bench_{os.getuid()}"))
+    d.mkdir(parents=True, exist_ok=True)
+    return d
+
+
+def prepare_table(workdir: Path, rank: int, world: int, hours: float, rows_per_rank: int, barrier) -> tuple[Path, Path, int]:
+    """The recording table of the e2e arm: rows_per_rank * world rows over K <= 8 distinct seeded 1-h WAV files ON DISK,
+    a model directory with the seeded synthetic weights; rank r writes the files r, r + world, .."""
+    import pandas as pd
+
+    from orcai_b200 import runtime
+    from orcai_b200.wavio import write_wav_pcm16
+    from orcai_b200.weights import save_npz, synthetic_weights
+
+    n_files = min(8, max(2, world))
+    for k in range(rank, n_files, world):
+        f = workdir / f"bench_{hours:g}h_{k}.wav"
+        if not f.exists() or f.stat().st_size < hours * 3600 * 96000:
+            write_wav_pcm16(f, make_recording(hours, 20251018 + k))
+    model_dir = workdir / "orcai-V1"
+    if rank == 0:
+        from importlib.resources import files as pkg_files
+
+        model_dir.mkdir(exist_ok=True)
+        src = pkg_files("orcai_b200.models").joinpath("orcai-V1")
+        for name in ("orcai_parameter.json", "model_shape.json"):
+            (model_dir / name).write_text(src.joinpath(name).read_text())
+        P, S = runtime.bundled_parameters()
+        if not (model_dir / "orcai-v1.weights.npz").exists():
+            save_npz(synthetic_weights(P, S, seed=1234), model_dir / "orcai-v1.weights.npz")
+        n_rows = rows_per_rank * world
+        pd.DataFrame({"recording": [f"rec{j:04d}" for j in range(n_rows)], "channel": 1, "base_dir_recording": str(workdir),
+                      "rel_recording_path": [f"bench_{hours:g}h_{j % n_files}.wav" for j in range(n_rows)]}).to_csv(workdir / f"table_{world}.csv", index=False)
+    barrier()
+    return workdir / f"table_{world}.csv", model_dir, n_files
 
 
 def main() -> None:
@@ -164,9 +214,10 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--hours", type=float, default=1.0, help="length of the synthetic recording each GPU annotates per step")
+    ap.add_argument("--rows-per-gpu", type=int, default=4, help="e2e arm: recordings per GPU in the table one step annotates")
     ap.add_argument("--cpu-sample-seconds", type=float, default=600.0, help="bounded CPU-oracle sample (BASELINE config 0: one 10-min recording)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-calibrate", action="store_true", help="skip the weight-rounding bias calibration of the tensor-core paths")
+    ap.add_argument("--no-configs", action="store_true", help="skip BASELINE configs 1, 2, 4 (create-spectrograms, 24-h recording, batch sweep)")
     ap.add_argument("--no-parity", action="store_true", help="skip the fp32-path comparison of the measured recording")
     ap.add_argument("--chunk", type=int, default=0, help="snippets per network chunk (0 = library default)")
     ap.add_argument("--net-path", type=int, default=4, choices=[0, 1, 2, 3, 4],
@@ -192,26 +243,29 @@ def main() -> None:
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    # this process = ONE GPU's worker, whatever else is visible (a table run would otherwise shard over every visible GPU)
+    os.environ["ORCAI_B200_DEVICE"] = str(local_rank)
+    os.environ["ORCAI_B200_DEVICES"] = str(local_rank)
+    precision = {0: "reference", 3: "fast", 4: "precise"}.get(args.net_path)
+    if precision:
+        os.environ["ORCAI_B200_PRECISION"] = precision
 
-    from orcai_b200 import runtime
+    from orcai_b200 import predict as opredict, runtime
     from orcai_b200.weights import synthetic_weights
 
     P, S = runtime.bundled_parameters()
     ctx = runtime.get_context(P, S, local_rank)
-    ctx.load_weights(synthetic_weights(P, S, seed=1234))
-    if args.chunk:
-        ctx.set_option("chunk", args.chunk)
-    ctx.set_option("net_path", args.net_path)
-    ctx.set_option("stft_f64", args.stft_f64)
-    if args.net_path in (1, 2, 3) and not args.no_calibrate:
-        ctx.calibrate()   # what OrcaiModel does when it loads weights (built-in synthetic calibration recording, not the bench file)
 
-    # K <= 8 distinct seeded files; rank r annotates file r % 8
-    pcm = make_recording(args.hours, 20251018 + (rank % 8))
-    pinned = torch.from_numpy(pcm).pin_memory()
-    pcm_pinned = pinned.numpy()
-    T = 1 + pcm.size // 256
-    n_snip = (T - 736) // 368 + 1
+    def bind_bench_weights():
+        ctx.load_weights(synthetic_weights(P, S, seed=1234))
+        if args.chunk:
+            ctx.set_option("chunk", args.chunk)
+        ctx.set_option("net_path", args.net_path)
+        ctx.set_option("stft_f64", args.stft_f64)
+        if args.net_path in (1, 2, 3):
+            ctx.calibrate()   # what OrcaiModel does for the fp16 paths (built-in synthetic calibration recording, not the bench file)
+
+    bind_bench_weights()
 
     def barrier():
         torch.cuda.synchronize()
@@ -225,6 +279,18 @@ def main() -> None:
         t = torch.tensor([x], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
+
+    workdir = bench_dir()
+    table_csv, model_dir, n_files = prepare_table(workdir, rank, world, args.hours, args.rows_per_gpu, barrier)
+
+    # K <= 8 distinct seeded files; rank r keeps file r % K resident for the device arm
+    from orcai_b200.wavio import read_wav
+
+    pcm, _sr, _ch = read_wav(workdir / f"bench_{args.hours:g}h_{rank % n_files}.wav")
+    pinned = torch.from_numpy(np.ascontiguousarray(pcm)).pin_memory()
+    pcm_pinned = pinned.numpy()
+    T = 1 + pcm.size // 256
+    n_snip = (T - 736) // 368 + 1
 
     # ---------------- device-resident arm (`value`) ----------------
     ctx.upload_pcm(pcm_pinned)
@@ -250,57 +316,62 @@ def main() -> None:
     launches = ctx.timings()["kernel_launches"] - launches0
     dev_ms = max_over_ranks(stage["total_ms"] / args.steps)
 
-    # ---------------- end-to-end arm (`e2e`): host buffers through the public entry point ----------------
-    # The upload of recording k+1 overlaps the annotation of recording k (predict_stream = what table mode runs);
-    # every step's H2D copy and D2H read are inside the timed region.
-    for _ in ctx.predict_stream((pcm_pinned for _ in range(max(2, args.warmup // 2))), want_agg=True):
-        pass
+    # ---------------- end-to-end arm (`e2e`): the product's own table run, files -> label files ----------------
+    # Every rank runs the SAME public call, `orcai_b200.predict.predict(TABLE.csv, output_path=DIR)` (what `orcai predict TABLE.csv -o DIR`
+    # and `torchrun ... -m orcai_b200.cli predict ...` run): it takes its longest-first share of the rows (RANK / WORLD_SIZE), reads the
+    # WAV files from disk into page-locked buffers on loader threads, uploads recording k+1 while the device annotates recording k,
+    # builds the label tables and writes the label files.  Everything of a step is inside the timed region.
+    outdir = workdir / f"out_{world}_{rank}"
+    outdir.mkdir(exist_ok=True)
+    silent = opredict.Messenger(verbosity=0)
+
+    def table_step():
+        opredict.predict(table_csv, model_dir=model_dir, output_path=str(outdir), overwrite=True, verbosity=0, msgr=silent)
+
+    for _ in range(max(1, args.warmup // 2)):
+        table_step()               # first call: model directory -> weights on the device; later calls reuse the cached model
     barrier()
+    le0 = ctx.timings()["kernel_launches"]
     t0 = time.perf_counter()
-    d2h = 0
-    for st, agg, cnt, lab, sta, sto in ctx.predict_stream((pcm_pinned for _ in range(args.steps)), want_agg=True):
-        d2h = agg.nbytes + cnt.nbytes + lab.nbytes + sta.nbytes + sto.nbytes
+    for _ in range(args.steps):
+        table_step()
     barrier()
     t_e2e = max_over_ranks(time.perf_counter() - t0)
+    launches_e2e = ctx.timings()["kernel_launches"] - le0
     clocks = sampler.stop()   # sampled every 50 ms across both timed regions (and the short warm-up between them)
-
-    # ---------------- BASELINE configs[1]: create-spectrograms device stage on the same 1-h recording ----------------
-    # STFT -> dB -> crop (+ global max), exact percentile select, clip + normalise into the compact (T, 171) float32 array
-    # that create-spectrograms stores; CUDA events on the compute stream per stage.
-    cs = {k: 0.0 for k in ("stft_ms", "select_ms", "normalise_ms", "total_ms")}
-    ctx.upload_pcm(pcm_pinned)
-    for i in range(2 + args.steps):
-        ctx.spectrogram_resident(normalise=True)
-        if i >= 2:
-            tm = ctx.timings()
-            for k in cs:
-                cs[k] += tm[k] / args.steps
-    ctx.set_option("stft_f64", 0)
-    for _ in range(3):
-        ctx.spectrogram_resident(normalise=True)
-    stft_f32_ms = ctx.timings()["stft_ms"]
-    ctx.set_option("stft_f64", args.stft_f64)
+    rows_total = args.rows_per_gpu * world
+    label_files = len(list(outdir.glob("*_predicted.txt")))
+    bind_bench_weights()      # the table run bound the model directory's weights (the same seeded set) and options
 
     # ---------------- parity of the measured path (outside every timed region) ----------------
     parity = None
     if rank == 0 and args.net_path != 0 and not args.no_parity:
-        # the same recording through the fp32 reference-grade network path: aggregated probabilities and segments
+        ctx.upload_pcm(pcm_pinned)
         st_f, agg_f, cnt_f, lab_f, sta_f, sto_f = ctx.predict_pcm(pcm_pinned, want_agg=True, resident=True)
+        raw_f = ctx.forward_resident(0, n_snip)
         ctx.set_option("net_path", 0)
         st_r, agg_r, cnt_r, lab_r, sta_r, sto_r = ctx.predict_pcm(pcm_pinned, want_agg=True, resident=True)
+        raw_r = ctx.forward_resident(0, n_snip)
         ctx.set_option("net_path", args.net_path)
         seg_f = set(zip(lab_f.tolist(), sta_f.tolist(), sto_f.tolist()))
         seg_r = set(zip(lab_r.tolist(), sta_r.tolist(), sto_r.tolist()))
         mask_f, mask_r = agg_f > 0.25, agg_r > 0.25
-        parity = {"against": "fp32 CUDA-core network path (1e-6 vs the CPU oracle) on the same recording",
+        parity = {"against": "the library's fp32 CUDA-core network path on the same recording (that path is held to the CPU oracle at 1e-6 in tests/; "
+                             "the oracle itself cannot annotate an hour within the bench)",
+                  "gate": 1e-3,
                   "probability_max_abs_dev": float(np.abs(agg_f - agg_r).max()), "probability_mean_abs_dev": float(np.abs(agg_f - agg_r).mean()),
+                  "per_snippet_probability_max_abs_dev": float(np.abs(raw_f - raw_r).max()),
                   "frames_with_different_mask_frac": float((mask_f != mask_r).mean()),
                   "segments": len(seg_f), "segments_reference_path": len(seg_r), "segments_identical": len(seg_f & seg_r),
                   "spectrogram_stats_equal": bool(st_f.lo == st_r.lo and st_f.hi == st_r.hi and st_f.db_ref == st_r.db_ref)}
 
     hours_total = args.hours * world * args.steps
     value = hours_total / t_res
-    e2e_value = hours_total / t_e2e
+    e2e_value = args.hours * rows_total * args.steps / t_e2e
+
+    configs = None
+    if rank == 0 and world == 1 and not args.no_configs:
+        configs = run_configs(ctx, args, pcm_pinned, T, workdir, bind_bench_weights)
 
     if rank == 0:
         peaks = _peaks()
@@ -308,74 +379,58 @@ def main() -> None:
         net_ms = stage["network_ms"] / args.steps
         stft_gbs = T * STFT_BYTES_PER_FRAME_I16 / (stft_ms * 1e-3) / 1e9
         net_tflops = n_snip * FLOP_PER_SNIPPET / (net_ms * 1e-3) / 1e12
+        roofline_net = {"kernel": "orcai-V1 forward (all layer kernels)", "bound": "tensor", "achieved": net_tflops, "peak": peaks["bf16_tflops_sustained"],
+                        "unit": "TFLOP/s", "frac": net_tflops / peaks["bf16_tflops_sustained"], "traffic": None,
+                        "peak_source": peaks["source"] + " bf16 sustained", "flop_per_snippet": FLOP_PER_SNIPPET}
         if args.net_path in (3, 4) and net_stage[15] > 0:
-            # dominant kernel = fused residual block 1; duration = CUDA events around its launch (first chunk) on the compute stream
+            # dominant kernel = fused residual block 1; duration = CUDA events around its launch(es) (first chunk) on the compute stream
             b1_ms, b1_snips = float(net_stage[1]), float(net_stage[15])
             b1_tflops = 2.0 * BLOCK1_MAC_PER_SNIPPET * b1_snips / (b1_ms * 1e-3) / 1e12
-            roofline_main = {"kernel": "fused_block_kernel<block 1: sepconv 16->30, sepconv 30->30, maxpool(3,2)/2 + residual 1x1/2>",
+            traffic = BLOCK1_TRAFFIC.get(args.net_path)
+            roofline_main = {"kernel": "fused_block_kernel<block 1: sepconv 16->30, sepconv 30->30, maxpool(3,2)/2 + residual 1x1/2>"
+                                       + (" PREC (split fp16), tall image + border images" if args.net_path == 4 else ""),
                              "bound": "tensor", "achieved": b1_tflops, "peak": peaks["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                             "frac": b1_tflops / peaks["bf16_tflops_sustained"], "traffic": BLOCK1_TRAFFIC_BYTES_PER_SNIPPET * b1_snips if BLOCK1_TRAFFIC_BYTES_PER_SNIPPET else None,
+                             "frac": b1_tflops / peaks["bf16_tflops_sustained"],
+                             "traffic": traffic["bytes_per_snippet"] * b1_snips if traffic else None, "traffic_source": traffic["source"] if traffic else None,
                              "peak_source": peaks["source"] + " bf16 sustained", "ms": b1_ms, "snippets": int(b1_snips),
                              "algorithmic_mac_per_snippet": BLOCK1_MAC_PER_SNIPPET,
-                             "executed_tflops": 2.0 * BLOCK1_EXECUTED_MAC_PER_SNIPPET * b1_snips / (b1_ms * 1e-3) / 1e12,
-                             # what actually bounds it: every M128 K16 N32 MMA fetches 4 KB + 1 KB of operands from shared memory at
-                             # 128 B/clk = 41.3 cycles measured with two issuing CTAs per SM (tools/microbench/mma_cost.cu);
-                             # 3 strips x 123 steps x 89 MMAs per snippet, 148 SMs
-                             "operand_fetch_bound": (lambda model_ms: {"model_ms": model_ms, "frac": model_ms / b1_ms, "cycles_per_mma": 41.3,
-                                                                       "mma_per_snippet": 3 * 123 * 89})(
-                                 b1_snips * 3 * 123 * 89 * 41.3 / 148 / ((clocks.get("sm_mhz") or 1965.0) * 1e3)),
-                             "note": "achieved counts the reference graph's MACs; the depthwise filter is folded into the GEMM weights, so the tensor pipe "
-                                     "executes 9 taps x pointwise MACs (executed_tflops); the kernel is bound by shared-memory operand bandwidth "
-                                     "(A re-read per tap at N = 32), see DESIGN.md"}
+                             "note": "achieved counts the reference graph's MACs of block 1 for every snippet of the chunk (the reference evaluates each "
+                                     "snippet separately); the kernel folds the depthwise filter into the GEMM weights (9 taps x pointwise MACs)"
+                                     + (", issues three MMAs per product (split fp16) and evaluates the shared interior of overlapping snippets once"
+                                        if args.net_path == 4 else "") + "; its bound is the shared-memory operand bandwidth of the tensor pipe, see DESIGN.md"}
         else:
-            roofline_main = {"kernel": "orcai-V1 forward (all layer kernels)", "bound": "tensor", "achieved": net_tflops, "peak": peaks["bf16_tflops_sustained"],
-                             "unit": "TFLOP/s", "frac": net_tflops / peaks["bf16_tflops_sustained"], "traffic": None,
-                             "peak_source": peaks["source"] + " bf16 sustained", "flop_per_snippet": FLOP_PER_SNIPPET}
+            roofline_main = roofline_net
+        agg_bytes = (T // 16) * (7 + 1) * 8
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * t_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {0: "f32", 1: "f16", 2: "bf16", 3: "f16", 4: "f16x3 (split fp16 operands, fp32 accumulate: fp32 grade)"}[args.net_path], "data": "synthetic",
+            "dtype": NET_DTYPE[args.net_path], "data": "synthetic",
             "config": {"workload": WORKLOAD_NAME, "hours_per_gpu_per_step": args.hours, "frames": T, "snippets": n_snip,
                        "segments_found": n_segments, "parallelism": f"shard-by-recording x{world}", "l2": "inputs larger than L2 (346 MB PCM, 475 MB dB per step)",
-                       "network_path": {0: "fp32 cuda-core", 1: "fp16 tcgen05 implicit-GEMM trunk + fp32 LSTM/dense", 2: "bf16 tcgen05 implicit-GEMM trunk + fp32 LSTM/dense",
-                                        3: "fp16 tcgen05: pixel-group entry conv, fused residual-block kernels, tcgen05 LSTM projections + TMEM-resident recurrence",
-                                        4: "split-fp16 tcgen05 (A_hi*W_hi + A_lo*W_hi + A_hi*W_lo): fused block 1, un-folded blocks 2-4 on split GEMMs, split-GEMM LSTM "
-                                           "projections + fp32 recurrence; shared interior of overlapping snippets (tall image + border rows)"}[args.net_path],
-                       "stft": "float64 FFT" if args.stft_f64 else "float32 FFT"},
+                       "network_path": NET_PATH_NAMES[args.net_path], "stft": "float64 FFT" if args.stft_f64 else "float32 FFT",
+                       "cpu_arm_note": "the CPU arms (cpu_baseline, --impl reference) time a bounded 600-s sample of the same synthetic audio and report the same rate"},
             "device_ms_per_step": dev_ms,
             "stage_ms": {k: v / args.steps for k, v in stage.items()},
-            "net_stage_ms_first_chunk": dict(zip(["conv0", "block1", "block2", "block3", "block4", "final_sep", "lstm1_proj", "lstm1_rec", "lstm2_proj",
-                                                  "lstm2_rec", "dense"], [round(v, 4) for v in net_stage[:11]])) | {"snippets": int(net_stage[15])},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(pcm.nbytes), "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * t_e2e / args.steps},
-            "gpu_launches": int(launches),
+            "net_stage_ms_first_chunk": dict(zip(STAGES, [round(v, 4) for v in net_stage[:11]])) | {"snippets": int(net_stage[15])},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(pcm.nbytes) * rows_total,
+                    "d2h_bytes_per_step": int(agg_bytes + 20 * n_segments) * rows_total, "ms_per_step": 1e3 * t_e2e / args.steps,
+                    "what": f"orcai_b200.predict.predict(TABLE.csv, output_path=DIR): {rows_total} rows of 1-h WAV files on disk ({n_files} distinct files) -> "
+                            f"{rows_total} label files per step; every rank = one GPU's worker process taking its longest-first share (RANK / WORLD_SIZE)",
+                    "recordings_per_step": rows_total, "label_files_written_rank0": label_files,
+                    "limiter": "per recording: WAV read + decode on 3 loader threads, one H2D copy of 346 MB overlapped with the previous recording's kernels, "
+                               "device time, label table + label file on a writer thread; the slowest of these per recording bounds the rate"},
+            "gpu_launches": int(launches), "gpu_launches_e2e": int(launches_e2e),
             "parity": parity,
             "clocks": clocks,
             "roofline": roofline_main,
-            "roofline_network": {"kernel": "orcai-V1 forward (all layer kernels)", "bound": "tensor", "achieved": net_tflops, "peak": peaks["bf16_tflops_sustained"],
-                                 "unit": "TFLOP/s", "frac": net_tflops / peaks["bf16_tflops_sustained"], "traffic": None,
-                                 "peak_source": peaks["source"] + " bf16 sustained", "flop_per_snippet": FLOP_PER_SNIPPET},
+            "roofline_network": roofline_net,
             "roofline_stft": {"kernel": "stft_db_kernel<int16>", "bound": "hbm", "achieved": stft_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                               "frac": stft_gbs / peaks["hbm_gbs"], "traffic": None, "peak_source": peaks["source"] + " copy",
                               "bytes_per_frame": STFT_BYTES_PER_FRAME_I16, "ms": stft_ms},
         }
-        hbm = peaks["hbm_gbs"]
-        line["create_spectrograms"] = {
-            "workload": "BASELINE configs[1]: create-spectrograms device stage (STFT/dB/crop + exact percentiles + clip/normalise) on the same 1-h recording",
-            "stage_ms": {k: round(v, 4) for k, v in cs.items()},
-            "hours_per_second_device": args.hours / (cs["total_ms"] * 1e-3),
-            "compulsory_bytes_per_frame": STFT_BYTES_PER_FRAME_I16,
-            "whole_stage": {"achieved": T * STFT_BYTES_PER_FRAME_I16 / (cs["total_ms"] * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
-                            "frac": T * STFT_BYTES_PER_FRAME_I16 / (cs["total_ms"] * 1e-3) / 1e9 / hbm,
-                            "note": "compulsory traffic only (int16 samples in, 171 float32 out); the stage also streams the 704 B/frame dB buffer 3x for the "
-                                    "exact select and once more for the normalise"},
-            "normalise_kernel": {"bytes_per_frame": 1368, "achieved": T * 1368 / (cs["normalise_ms"] * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
-                                 "frac": T * 1368 / (cs["normalise_ms"] * 1e-3) / 1e9 / hbm},
-            "select_passes": {"bytes_per_frame": 3 * 704, "achieved": T * 3 * 704 / (cs["select_ms"] * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
-                              "frac": T * 3 * 704 / (cs["select_ms"] * 1e-3) / 1e9 / hbm},
-            "stft_float32_fft_variant": {"ms": stft_f32_ms, "achieved": T * STFT_BYTES_PER_FRAME_I16 / (stft_f32_ms * 1e-3) / 1e9, "unit": "GB/s",
-                                         "frac": T * STFT_BYTES_PER_FRAME_I16 / (stft_f32_ms * 1e-3) / 1e9 / hbm,
-                                         "note": "max error 1e-3 dB against the float64 oracle: at the gate, hence not the default"},
-        }
+        if configs:
+            line["create_spectrograms"] = configs.pop("create_spectrograms")
+            line["configs"] = configs
         if world == 1 and not args.no_cpu_baseline:
             threads = len(os.sched_getaffinity(0))
             v, dt = cpu_oracle_hours_per_second(args.cpu_sample_seconds, 20251018, threads)
@@ -384,6 +439,119 @@ def main() -> None:
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_configs(ctx, args, pcm_pinned, T, workdir, rebind) -> dict:
+    """BASELINE configs beyond the headline, one GPU, outside the headline's timed regions:
+    configs[1] create-spectrograms (device stage + files -> zarr wall time), configs[2] one 24-h recording, configs[4] batch sweep."""
+    import torch
+
+    from orcai_b200 import spectrogram as ospec
+    from orcai_b200.auxiliary import Messenger
+
+    peaks = _peaks()
+    hbm = peaks["hbm_gbs"]
+    out = {}
+    # ---- configs[1]: STFT -> dB -> crop (+ global max), exact percentile select, clip + normalise into the compact (T, 171) array ----
+    cs = {k: 0.0 for k in ("stft_ms", "select_ms", "normalise_ms", "total_ms")}
+    ctx.upload_pcm(pcm_pinned)
+    reps = max(3, args.steps)
+    for i in range(2 + reps):
+        ctx.spectrogram_resident(normalise=True)
+        if i >= 2:
+            tm = ctx.timings()
+            for k in cs:
+                cs[k] += tm[k] / reps
+    ctx.set_option("stft_f64", 0)
+    for _ in range(3):
+        ctx.spectrogram_resident(normalise=True)
+    stft_f32_ms = ctx.timings()["stft_ms"]
+    ctx.set_option("stft_f64", args.stft_f64)
+    # the application: one-row recording table -> OUTDIR/<recording>/spectrogram/{spectrogram.zarr, times.json, frequencies.json}
+    import pandas as pd
+    import shutil
+
+    tab = workdir / "spec_table.csv"
+    P, _S = __import__("orcai_b200.runtime", fromlist=["x"]).bundled_parameters()
+    row = {"recording": "spec0", "channel": 1, "base_dir_recording": str(workdir), "rel_recording_path": f"bench_{args.hours:g}h_0.wav", "base_dir_annotation": "x"}
+    row.update({c: True for c in P["calls"]})
+    pd.DataFrame([row]).to_csv(tab, index=False)
+    walls = []
+    for _ in range(3):
+        shutil.rmtree(workdir / "spec_out", ignore_errors=True)
+        t0 = time.perf_counter()
+        ospec.create_spectrograms(tab, workdir / "spec_out", orcai_parameter=P, verbosity=0, msgr=Messenger(verbosity=0))
+        walls.append(time.perf_counter() - t0)
+    zarr_bytes = sum(f.stat().st_size for f in (workdir / "spec_out").rglob("*") if f.is_file())
+    shutil.rmtree(workdir / "spec_out", ignore_errors=True)
+    from orcai_b200 import io as oio
+
+    out["create_spectrograms"] = {
+        "workload": "BASELINE configs[1]: create-spectrograms on the same 1-h recording: device stage (STFT/dB/crop + exact percentiles + clip/normalise) and the application (WAV file -> zarr store)",
+        "stage_ms": {k: round(v, 4) for k, v in cs.items()},
+        "hours_per_second_device": args.hours / (cs["total_ms"] * 1e-3),
+        "compulsory_bytes_per_frame": STFT_BYTES_PER_FRAME_I16,
+        "whole_stage": {"achieved": T * STFT_BYTES_PER_FRAME_I16 / (cs["total_ms"] * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                        "frac": T * STFT_BYTES_PER_FRAME_I16 / (cs["total_ms"] * 1e-3) / 1e9 / hbm,
+                        "note": "compulsory traffic only (int16 samples in, 171 float32 out); the stage also streams the 704 B/frame dB buffer for the exact select and once more for the normalise"},
+        "normalise_kernel": {"bytes_per_frame": 1368, "achieved": T * 1368 / (cs["normalise_ms"] * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                             "frac": T * 1368 / (cs["normalise_ms"] * 1e-3) / 1e9 / hbm},
+        "select_passes": {"bytes_per_frame": SELECT_PASSES * 704, "achieved": T * SELECT_PASSES * 704 / (cs["select_ms"] * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                          "frac": T * SELECT_PASSES * 704 / (cs["select_ms"] * 1e-3) / 1e9 / hbm},
+        "stft_float32_fft_variant": {"ms": stft_f32_ms, "achieved": T * STFT_BYTES_PER_FRAME_I16 / (stft_f32_ms * 1e-3) / 1e9, "unit": "GB/s",
+                                     "frac": T * STFT_BYTES_PER_FRAME_I16 / (stft_f32_ms * 1e-3) / 1e9 / hbm,
+                                     "note": "max error 1e-3 dB against the float64 oracle: at the gate, hence not the default"},
+        "application": {"what": "orcai_b200.spectrogram.create_spectrograms(TABLE.csv, OUTDIR): 1-h WAV on disk -> spectrogram.zarr (zarr v3, chunks (2000, 171), gzip) + times.json + frequencies.json",
+                        "wall_s_best_of_3": min(walls), "hours_per_second": args.hours / min(walls), "gzip_threads": oio.gzip_workers(),
+                        "store_bytes": zarr_bytes, "limiter": "host: gzip of 462 MB per hour of audio on the stated threads, then file writes"},
+    }
+    # ---- configs[2]: ONE 24-h recording (the 1-h recording repeated 24 times: 4.15 G samples, 8.3 GB of PCM16), long sliding-window path ----
+    try:
+        long_pcm = np.tile(np.asarray(pcm_pinned), 24)
+        pin24 = torch.from_numpy(long_pcm).pin_memory()
+        p24 = pin24.numpy()
+        del long_pcm
+        ctx.predict_pcm(p24, want_agg=True)                      # warm-up: buffers grow to the 24-h size
+        t0 = time.perf_counter()
+        r = ctx.predict_pcm(p24, want_agg=True)                  # host buffer -> H2D -> predict -> aggregates + segments on the host
+        wall = time.perf_counter() - t0
+        tm = ctx.timings()
+        out["one_24h_recording"] = {"workload": "BASELINE configs[2]: orcai predict on ONE 24-hour recording, 1 B200 (the 1-h recording repeated 24 times)",
+                                    "frames": int(r[0].n_frames), "snippets": int((r[0].n_frames - 736) // 368 + 1), "segments": int(len(r[3])),
+                                    "device_ms": tm["total_ms"], "network_ms": tm["network_ms"], "e2e_ms": 1e3 * wall, "h2d_bytes": int(p24.nbytes),
+                                    "hours_per_second_device": 24.0 / (tm["total_ms"] * 1e-3), "hours_per_second_e2e": 24.0 / wall}
+        # ---- configs[4]: snippet forward, batch sweep 1 - 4096 on the resident 24-h recording ----
+        ctx.upload_pcm(p24)
+        ctx.spectrogram_resident(False)
+        ctx.set_option("chunk", 4096)
+        sizes = [1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096]
+        ref, rows = {}, []
+        for path, name in ((0, "fp32 CUDA cores"), (4, "split-fp16 tcgen05 (default)"), (3, "single-fp16 tcgen05 fused, calibrated (opt-in)"), (2, "bf16 tcgen05 layer-wise")):
+            if path == 3:
+                ctx.calibrate()                                   # replaces the resident recording
+                ctx.upload_pcm(p24)
+                ctx.spectrogram_resident(False)
+            ctx.set_option("net_path", path)
+            for n in sizes:
+                if path in (0, 2) and n > 512:
+                    continue                                      # the slow paths only serve as tolerance references
+                res = ctx.forward_resident(0, n)                  # warm-up + result
+                best = 1e30
+                for _ in range(3):
+                    ctx.forward_resident(0, n)
+                    best = min(best, ctx.timings()["network_ms"])
+                if path == 0:
+                    ref[n] = res
+                rows.append({"path": name, "batch": n, "ms": round(best, 4), "snippets_per_s": n / (best * 1e-3), "tflops": n * FLOP_PER_SNIPPET / (best * 1e-3) / 1e12,
+                             "max_abs_dev_vs_fp32": float(np.abs(res - ref[n]).max()) if n in ref else None})
+        out["batch_sweep"] = {"workload": "BASELINE configs[4]: orcai-V1 snippet forward, batch 1 - 4096 snippets of a resident recording; deviation of the per-snippet "
+                                          "probabilities from the fp32 path (gate 1e-3); tensor-pipe use = tflops / measured bf16 peak", "rows": rows}
+        del pin24, p24
+    except Exception as e:  # noqa: BLE001 - the headline must not die with an optional config
+        out["configs_error"] = f"{type(e).__name__}: {e}"
+    rebind()
+    ctx.set_option("chunk", args.chunk if args.chunk else 1024)
+    return out
 
 
 if __name__ == "__main__":

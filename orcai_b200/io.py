@@ -97,9 +97,14 @@ def save_as_zarr(obj: np.ndarray, filename: Path | str, chunk_rows: int = 2000, 
         d.mkdir(parents=True, exist_ok=True)
         (d / "0").write_bytes(_gzip_chunk(blk.tobytes()))
 
-    workers = threads or min(32, len(os.sched_getaffinity(0)))
+    workers = threads or gzip_workers()
     with ThreadPoolExecutor(max_workers=max(1, workers)) as ex:  # zlib releases the GIL
         list(ex.map(write_chunk, range(n_chunks)))
+
+
+def gzip_workers() -> int:
+    """Threads that compress the chunks of one store (zlib releases the interpreter lock): the cores this process may use, at most 32."""
+    return min(32, len(os.sched_getaffinity(0)))
 
 
 def read_zarr(filename: Path | str) -> np.ndarray:
@@ -121,6 +126,9 @@ def read_zarr(filename: Path | str) -> np.ndarray:
 # ---------------------------------------------------------------------------------------------
 # model artefact
 # ---------------------------------------------------------------------------------------------
+_MODEL_CACHE: dict = {}
+
+
 def load_orcai_model(model_dir: Path | str, device: int | None = None):
     """Load a model directory -> (model, orcai_parameter, shape).
 
@@ -135,7 +143,21 @@ def load_orcai_model(model_dir: Path | str, device: int | None = None):
     from orcai_b200.model import OrcaiModel
     from orcai_b200.weights import load_npz, synthetic_weights
 
+    from orcai_b200.model import precision_from_env
+    from orcai_b200.runtime import default_device
+
     model_dir = Path(model_dir)
+    # a process that annotates table after table (worker processes, services) loads a model directory once per (device, arithmetic):
+    # the key holds the size and mtime of every file in the directory, so edited weights or parameters are re-read
+    try:
+        files_sig = tuple(sorted((f.name, f.stat().st_size, f.stat().st_mtime_ns) for f in model_dir.iterdir() if f.is_file()))
+    except OSError:
+        files_sig = ()
+    cache_key = (str(model_dir.resolve()), files_sig, default_device() if device is None else int(device), precision_from_env(),
+                 os.environ.get("ORCAI_B200_SYNTHETIC_WEIGHTS"), os.environ.get("ORCAI_B200_CALIBRATION"))
+    hit = _MODEL_CACHE.get(cache_key)
+    if hit is not None:
+        return hit
     orcai_parameter = read_json(model_dir.joinpath("orcai_parameter.json"))
     shape = read_json(model_dir.joinpath("model_shape.json"))
     name = orcai_parameter["name"]
@@ -159,4 +181,5 @@ def load_orcai_model(model_dir: Path | str, device: int | None = None):
     else:
         raise ValueError(f"Couldn't find model weights ({name}.weights.npz, model_weights.h5) or keras model file in {model_dir}")
     model = OrcaiModel(orcai_parameter, shape, W, device=device)
+    _MODEL_CACHE[cache_key] = (model, orcai_parameter, shape)
     return model, orcai_parameter, shape

@@ -423,7 +423,7 @@ def _predict_and_save(
 
 
 def _visible_devices() -> list[int]:
-    """Devices a table run shards over: ORCAI_B200_DEVICES="0,1,.." | "all"; default: the process' one device."""
+    """Devices named by ORCAI_B200_DEVICES="0,1,.." | "all" (ONE recording is split by time over them); default: the process' one device."""
     spec = os.environ.get("ORCAI_B200_DEVICES", "").strip()
     if not spec:
         return []
@@ -432,6 +432,35 @@ def _visible_devices() -> list[int]:
 
         return list(range(torch.cuda.device_count()))
     return [int(x) for x in spec.split(",") if x.strip() != ""]
+
+
+def _table_devices() -> list[int]:
+    """Devices a recording TABLE shards over: ORCAI_B200_DEVICES if set, else every GPU the process can see."""
+    devs = _visible_devices()
+    if devs or os.environ.get("ORCAI_B200_DEVICES", "").strip():
+        return devs
+    try:
+        import torch
+
+        return list(range(torch.cuda.device_count()))
+    except Exception:
+        return []
+
+
+def _rank_shard() -> tuple[int, int] | None:
+    """(rank, world) when this process is ONE WORKER of a job that runs the same `orcai predict TABLE.csv` in every process:
+    `torchrun --nproc-per-node N -m orcai_b200.cli predict TABLE.csv -o DIR` (RANK / WORLD_SIZE / LOCAL_RANK from the launcher)
+    or ORCAI_B200_SHARD="rank/world".  Every worker computes the same longest-first plan from the file sizes and annotates
+    its own share on its own GPU; nothing is exchanged (shard by recording, no collective)."""
+    spec = os.environ.get("ORCAI_B200_SHARD", "").strip()
+    if spec:
+        r, w = spec.split("/")
+        return int(r), int(w)
+    w = os.environ.get("WORLD_SIZE", "")
+    r = os.environ.get("RANK", "")
+    if w.isdigit() and r.isdigit() and int(w) > 1:
+        return int(r), int(w)
+    return None
 
 
 def _predict_worker(kwargs: dict) -> None:
@@ -510,11 +539,28 @@ def predict(
         msgr = Messenger(verbosity=verbosity, title="Predicting calls")
     model_dir = Path(str(model_dir))
     recording_path = Path(recording_path)
-    devices = [_worker["device"]] if _worker else _visible_devices()
-    # several devices: worker THREADS in this process by default (measured: 66.6 h/s on 8 B200, bound by the interpreter lock
-    # around the per-recording host work), worker PROCESSES with ORCAI_B200_TABLE_PROCESSES=1 (no shared interpreter, but every
-    # process pays its own start-up: CUDA context, model, calibration, page-locked buffers)
-    multi = recording_path.suffix == ".csv" and len(devices) > 1 and os.environ.get("ORCAI_B200_TABLE_PROCESSES", "0") == "1"
+    is_table = recording_path.suffix == ".csv"
+    shard = _rank_shard() if (is_table and not _worker) else None
+    if _worker:
+        devices = [_worker["device"]]
+    elif shard:
+        devices = []                       # one worker of a multi-process job: its own device (LOCAL_RANK / ORCAI_B200_DEVICE)
+    elif is_table:
+        devices = _table_devices()         # every visible GPU unless ORCAI_B200_DEVICES narrows it
+    else:
+        devices = _visible_devices()
+    # A table on several devices: one worker PROCESS per GPU (own interpreter: the per-recording host work - WAV decode, label
+    # table, label file - does not serialise on one interpreter lock; measured round 1: threads reached 2.1x on 8 GPUs).  The
+    # workers live for the whole table, so their start-up (CUDA context, model, page-locked buffers) is paid once; tables too
+    # short to amortise it (fewer than 2 rows per device) and ORCAI_B200_TABLE_PROCESSES=0 use worker THREADS instead.
+    n_rows_hint = None
+    if is_table and len(devices) > 1 and not _worker:
+        try:
+            n_rows_hint = sum(1 for _ in open(recording_path)) - 1
+        except OSError:
+            n_rows_hint = None
+    procs_default = "1" if (n_rows_hint is not None and n_rows_hint >= 2 * len(devices)) else "0"
+    multi = is_table and len(devices) > 1 and not _worker and os.environ.get("ORCAI_B200_TABLE_PROCESSES", procs_default) == "1"
     if not multi:
         devices = list(dict.fromkeys(devices))   # one context per device in this process: a device listed twice counts once
         msgr.part(f"Loading model: {model_dir.stem}")
@@ -552,6 +598,13 @@ def predict(
 
     msgr.part(f"Predicting annotations for {len(recording_table)} wav files")
     rows = list(recording_table.index)
+    if shard:
+        from orcai_b200.sharding import assign_rows, recording_costs
+
+        rank, world = shard
+        plan = assign_rows(recording_costs([Path(recording_table.loc[i, "base_dir_recording"]).joinpath(recording_table.loc[i, "rel_recording_path"]) for i in rows]), world)
+        rows = [rows[j] for j in plan[rank]]
+        msgr.info(f"worker {rank} of {world}: {len(rows)} of {len(recording_table)} recordings")
     if multi:
         return _predict_table_multiprocess(
             recording_table, rows, devices, msgr,
@@ -559,6 +612,8 @@ def predict(
                  save_probabilities=save_probabilities, base_dir_recording=base_dir_recording, call_duration_limits=call_duration_limits,
                  label_suffix=label_suffix, verbosity=0),
         )
+    if len(devices) > max(1, len(rows)):
+        devices = devices[: max(1, len(rows))]      # no more worker contexts than recordings
     progressbar = None if _worker else tqdm(total=len(rows), desc="Starting ...", unit="file")
 
     out_path_of = dict(zip(rows, out_paths))

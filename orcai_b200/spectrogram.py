@@ -168,7 +168,50 @@ def create_spectrograms(
     if base_dir_recording is not None:
         recording_table = recording_table.assign(base_dir_recording=str(base_dir_recording))
 
-    msgr.part(f"Creating {len(recording_table)} spectrograms")
-    for recording in tqdm(recording_table.itertuples(index=False), desc="Making spectrograms", total=len(recording_table)):
-        _make_and_save_spectrogram(recording, orcai_parameter, output_dir)
+    # Sharding by recording (the reference loop, spectrogram.py:313-318, is sequential; every recording is independent):
+    #   * one worker of a multi-process job (torchrun / ORCAI_B200_SHARD, see predict._rank_shard) takes its longest-first share;
+    #   * otherwise one worker thread per visible GPU (ORCAI_B200_DEVICES narrows the set) - the host side of a recording is the
+    #     WAV read, the 462 MB/h read-back and the gzip of the zarr chunks, all of which release the interpreter lock.
+    import threading
+
+    from orcai_b200.predict import _rank_shard, _table_devices
+    from orcai_b200.sharding import assign_rows, recording_costs
+
+    recordings = list(recording_table.itertuples(index=False))
+    costs = recording_costs([Path(r.base_dir_recording).joinpath(r.rel_recording_path) for r in recordings])
+    shard = _rank_shard()
+    if shard:
+        rank, world = shard
+        recordings = [recordings[j] for j in assign_rows(costs, world)[rank]]
+        costs = recording_costs([Path(r.base_dir_recording).joinpath(r.rel_recording_path) for r in recordings])
+        devices = [None]
+        msgr.info(f"worker {rank} of {world}: {len(recordings)} recordings")
+    else:
+        devices = _table_devices()[: max(1, len(recordings))] or [None]
+    msgr.part(f"Creating {len(recordings)} spectrograms")
+    progress = tqdm(desc="Making spectrograms", total=len(recordings))
+    if len(devices) <= 1:
+        for recording in recordings:
+            _make_and_save_spectrogram(recording, orcai_parameter, output_dir, device=devices[0])
+            progress.update(1)
+    else:
+        lock, failures = threading.Lock(), []
+
+        def work(dev, share):
+            try:
+                for j in share:
+                    _make_and_save_spectrogram(recordings[j], orcai_parameter, output_dir, device=dev)
+                    with lock:
+                        progress.update(1)
+            except BaseException as e:  # noqa: BLE001 - re-raised below, like the sequential loop would
+                failures.append(e)
+
+        threads = [threading.Thread(target=work, args=(d, sh), daemon=True) for d, sh in zip(devices, assign_rows(costs, len(devices)))]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if failures:
+            raise failures[0]
+    progress.close()
     msgr.success("Spectrograms created.")

@@ -53,3 +53,24 @@ def test_two_rank_gloo_shard_and_gather():
     rows = sorted(i for part in got for i, _ in part)
     assert rows == list(range(25))  # disjoint cover: every recording annotated exactly once
     assert all(k == i % 5 for part in got for i, k in part)
+
+
+def test_rank_shard_from_launcher_environment(monkeypatch):
+    """The table run of one worker process: RANK / WORLD_SIZE (torchrun) or ORCAI_B200_SHARD name its share; all workers derive
+    the same plan from the file sizes, so the shares are a disjoint cover without any exchange."""
+    from orcai_b200 import predict
+
+    for k in ("RANK", "WORLD_SIZE", "ORCAI_B200_SHARD"):
+        monkeypatch.delenv(k, raising=False)
+    assert predict._rank_shard() is None
+    monkeypatch.setenv("WORLD_SIZE", "1"); monkeypatch.setenv("RANK", "0")
+    assert predict._rank_shard() is None                       # a single process is not a shard
+    monkeypatch.setenv("WORLD_SIZE", "8"); monkeypatch.setenv("RANK", "5")
+    assert predict._rank_shard() == (5, 8)
+    monkeypatch.setenv("ORCAI_B200_SHARD", "1/4")               # explicit setting wins over the launcher's
+    assert predict._rank_shard() == (1, 4)
+    costs = [float(3 + (i * 5) % 11) for i in range(40)]
+    shares = [rows_for_rank(costs, 8, r) for r in range(8)]
+    assert sorted(i for sh in shares for i in sh) == list(range(40))
+    loads = [sum(costs[i] for i in sh) for sh in shares]
+    assert max(loads) - min(loads) <= max(costs)

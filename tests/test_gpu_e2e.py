@@ -221,3 +221,32 @@ def test_table_mode_one_process_per_gpu(params, model_dir, wavs, tmp_path, monke
         assert f1.exists() == f2.exists() == (n != "gone")
         if n != "gone":
             assert f1.read_bytes() == f2.read_bytes()
+
+
+def test_table_sharded_by_rank_like_torchrun(params, model_dir, wavs, tmp_path, monkeypatch):
+    """`torchrun --nproc-per-node N -m orcai_b200.cli predict TABLE.csv -o DIR`: every process runs the same command, takes its
+    longest-first share of the rows (RANK / WORLD_SIZE, or ORCAI_B200_SHARD) and writes its own label files; together they write
+    exactly what one process writes, each file once."""
+    from orcai_b200 import predict as opredict
+
+    d, files = wavs
+    names = [f"r{k}" for k in range(5)]
+    table = pd.DataFrame({"recording": names, "channel": 1, "base_dir_recording": str(d),
+                          "rel_recording_path": ["rec0.wav", "rec1.wav", "rec2.wav", "rec1.wav", "rec2.wav"]})
+    csv = tmp_path / "t.csv"
+    table.to_csv(csv, index=False)
+    whole, parts = tmp_path / "whole", [tmp_path / "p0", tmp_path / "p1"]
+    for p in [whole, *parts]:
+        p.mkdir()
+    monkeypatch.delenv("ORCAI_B200_DEVICES", raising=False)
+    monkeypatch.delenv("ORCAI_B200_SHARD", raising=False)
+    opredict.predict(csv, model_dir=model_dir, output_path=str(whole), verbosity=0)
+    monkeypatch.setenv("ORCAI_B200_SHARD", "0/2")
+    opredict.predict(csv, model_dir=model_dir, output_path=str(parts[0]), verbosity=0)
+    monkeypatch.delenv("ORCAI_B200_SHARD")
+    monkeypatch.setenv("RANK", "1"); monkeypatch.setenv("WORLD_SIZE", "2"); monkeypatch.setenv("LOCAL_RANK", "0")
+    opredict.predict(csv, model_dir=model_dir, output_path=str(parts[1]), verbosity=0)
+    got = {f.name: f.read_bytes() for p in parts for f in p.iterdir()}
+    assert sum(len(list(p.iterdir())) for p in parts) == len(names) == len(got)      # disjoint cover
+    assert all(len(list(p.iterdir())) >= 2 for p in parts)
+    assert got == {f.name: f.read_bytes() for f in whole.iterdir()}
