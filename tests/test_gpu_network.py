@@ -403,3 +403,36 @@ def test_precise_path_edge_lengths_and_silence(ctx):
     finally:
         ctx.set_option("net_path", 0)
     assert len(lab) == 0 and len(sta) == 0 and cnt.max() == 2 and np.isnan(agg[cnt > 0]).all()
+
+
+def test_one_24_hour_recording_full_path(ctx, params):
+    """BASELINE configs[2]: ONE 24-h recording (4.15 G samples, 16.2 M frames, 44 020 snippets) through the whole predict path on
+    one GPU - the default network path against the fp32 path on the same device spectrogram: aggregated probabilities within 1e-4,
+    overlap counts equal, and wherever the thresholded masks agree (everywhere but probabilities within 1e-5 of the threshold) the
+    segments are identical."""
+    one_hour = synth_pcm16(3600.0, seed=20251018)
+    pcm = np.tile(one_hour, 24)
+    del one_hour
+    try:
+        ctx.set_option("chunk", 1024)
+        ctx.upload_pcm(pcm)
+        ctx.set_option("net_path", 0)
+        ref = ctx.predict_pcm(pcm, resident=True)
+        ctx.set_option("net_path", 4)
+        got = ctx.predict_pcm(pcm, resident=True)
+    finally:
+        ctx.set_option("net_path", 0)
+        ctx.set_option("chunk", 128)
+    T = 1 + pcm.size // 256
+    assert got[0].n_frames == T == 16200001 and got[1].shape == (T // 16, 7)
+    assert got[0].lo == ref[0].lo and got[0].hi == ref[0].hi and got[0].db_ref == ref[0].db_ref
+    np.testing.assert_array_equal(got[2], ref[2])
+    assert np.abs(got[1] - ref[1]).max() <= PRECISE_TOL
+    thr = 0.25
+    same_mask = ((got[1] > thr) == (ref[1] > thr)).all(axis=0)            # per label: every frame on the same side of the threshold
+    assert same_mask.sum() >= 5
+    seg_g = {(int(a), int(b), int(c)) for a, b, c in zip(got[3], got[4], got[5])}
+    seg_r = {(int(a), int(b), int(c)) for a, b, c in zip(ref[3], ref[4], ref[5])}
+    for lab in np.flatnonzero(same_mask):
+        assert {s for s in seg_g if s[0] == lab} == {s for s in seg_r if s[0] == lab}
+    assert len(seg_g ^ seg_r) <= 8 and len(seg_g) > 100000
