@@ -61,10 +61,17 @@ __host__ __device__ constexpr int pow2cols(int c) { return c <= 32 ? 32 : c <= 6
 //        A_lo*W_lo term is 2^-22 relative): the X / R / S1 / S2 buffers, the weight set and the activation tensors in HBM all
 //        come as a hi plane set followed by a lo plane set.  Why: fp16 operands alone put the probabilities 2.7e-3 from the
 //        fp32 graph (tools/precision_plan.py: every weight tensor and every stored activation contributes 2e-4 .. 2e-3).
-template <int CIN_, int COUT_, int CPOOL_, int S_, bool RELU_OUT_, int CTAS_, int NEW_, bool CONV0_ = false, int ISS_ = 1, int XBUF_ = 1, bool PREC_ = false>
+// UF2_ (with PREC_): the SECOND separable convolution un-folded.  Folding the depthwise filter into the GEMM costs nine taps x
+//        three split products = 27 MMAs per K chunk; instead the worker warps run the depthwise 3x3 on the CUDA cores (fp32 FMAs on
+//        an fp32 S1 kept in quad-planar [4-channel quad][pixel][4 floats] layout: one conflict-free LDS.128 per window position,
+//        sliding window down the rows) straight into a (hi, lo) A operand D2, and the tensor pipe runs the pointwise 1x1 only:
+//        3 MMAs per K chunk.  S1 is then no MMA operand any more, hence fp32.
+template <int CIN_, int COUT_, int CPOOL_, int S_, bool RELU_OUT_, int CTAS_, int NEW_, bool CONV0_ = false, int ISS_ = 1, int XBUF_ = 1, bool PREC_ = false,
+          bool UF2_ = false>
 struct FB {
   static constexpr int XBUF = XBUF_;
-  static constexpr bool PREC = PREC_;
+  static constexpr bool PREC = PREC_, UF2 = UF2_;
+  static_assert(!UF2_ || (PREC_ && ISS_ == 2), "the un-folded second convolution: split-fp16 configuration with two issuer warps");
   static constexpr int PL = PREC_ ? 2 : 1;           // operand plane sets: hi (, lo)
   static_assert(!(PREC_ && CONV0_), "the in-kernel entry convolution writes single fp16 operands");
   static_assert(XBUF_ == 1 || (XBUF_ == 2 && ISS_ == 2 && !CONV0_), "two X buffers: two-issuer TMA configuration only");
@@ -98,27 +105,33 @@ struct FB {
   // chunk alias the next group (finite values times a zero A chunk), missing n-groups only feed unused columns.
   static constexpr uint32_t SBO_W1 = XG * 128, SBO_W2 = NG * 128;
   static constexpr uint32_t TAP_W1 = NG * SBO_W1, TAP_W2 = NG * SBO_W2;
-  static constexpr uint32_t W1_BYTES = 9 * TAP_W1 + 128, W2_BYTES = 9 * TAP_W2 + 128, WR_BYTES = TAP_W1 + 128;
+  static constexpr uint32_t W1_BYTES = 9 * TAP_W1 + 128, W2_BYTES = (UF2_ ? 1 : 9) * TAP_W2 + 128, WR_BYTES = TAP_W1 + 128;
   static constexpr uint32_t WB_BYTES = NG * 128 + 128;   // [bias_hi, bias_lo] rows of one GEMM: n-groups of one k-chunk
   static constexpr uint32_t OFF_W1 = 0, OFF_W2 = OFF_W1 + W1_BYTES, OFF_WR = OFF_W2 + W2_BYTES;
   static constexpr uint32_t WSET = OFF_WR + WR_BYTES;        // one weight set [sep1 | sep2 | residual]; PREC: the lo set follows
   static constexpr uint32_t W_LO = PREC_ ? WSET : 0;
   static constexpr uint32_t OFF_WB1 = WSET * PL, OFF_WB2 = OFF_WB1 + WB_BYTES, OFF_WBR = OFF_WB2 + WB_BYTES;
   static constexpr uint32_t OFF_ONES = OFF_WBR + WB_BYTES;   // two 8x8 core matrices: k = 0,1 are 1.0, the rest 0 (SBO = 0)
-  static constexpr uint32_t W_BYTES = OFF_ONES + 256;
+  static constexpr uint32_t OFF_DW2 = OFF_ONES + 256;          // UF2: depthwise taps of the second convolution, [9][NP] fp32
+  static constexpr uint32_t W_BYTES = OFF_DW2 + (UF2_ ? 9 * NP * 4 : 0);
   static constexpr uint32_t OFF_R = W_BYTES;
   static constexpr uint32_t R_LO = XCH * LBO_R, X_LO = XCH * LBO_X, S1_LO = MCH * LBO_S1, S2_LO = NG * LBO_S2;   // hi -> lo plane set
+  static constexpr int NQ = OCP / 4;                             // UF2: fp32 S1 planes (4-channel quads), LBO_S1 apart
+  static constexpr uint32_t S1_BYTES = UF2_ ? NQ * LBO_S1 : PL * MCH * LBO_S1;
+  static constexpr int D2PIX = N2 * 128;                         // UF2: A operand of the pointwise GEMM, accumulator-row order
+  static constexpr uint32_t LBO_D2 = D2PIX * 16, D2_LO = MCH * LBO_D2, D2_BYTES = UF2_ ? 2 * MCH * LBO_D2 : 0;
   static constexpr uint32_t OFF_X = OFF_R + PL * XCH * LBO_R;
   static constexpr uint32_t XR_BYTES = PL * (XCH * LBO_R + XCH * LBO_X);        // one R + X buffer; buffer b sits b * XR_BYTES further
   static constexpr uint32_t OFF_S1 = OFF_X + PL * XCH * LBO_X + (XBUF - 1) * XR_BYTES;
-  static constexpr uint32_t OFF_S2 = OFF_S1 + PL * MCH * LBO_S1;
+  static constexpr uint32_t OFF_S2 = OFF_S1 + S1_BYTES;
   // entry-convolution input: two (S+5) x SPW fp16 tiles of the normalised spectrogram (rows a-1 .. a+S+3, columns cb-1 ..)
   static constexpr int SPW = 64, SPH = S + 5;
   static constexpr uint32_t SPEC_BYTES = CONV0 ? SPH * SPW * 2 : 0;
-  static constexpr uint32_t OFF_SPEC = OFF_S2 + PL * NG * LBO_S2;
+  static constexpr uint32_t OFF_D2 = OFF_S2 + PL * NG * LBO_S2;
+  static constexpr uint32_t OFF_SPEC = OFF_D2 + D2_BYTES;
   static constexpr uint32_t OFF_BAR = OFF_SPEC + 2 * ((SPEC_BYTES + 127) / 128 * 128);
   // barriers: bar1[N1] bar2[N2] barR[2] s1_full[N1] pool_done x_full[2] x_free[2] spec_full[2]
-  static constexpr int B_1 = 0, B_2 = N1, B_R = N1 + N2, B_S1 = N1 + N2 + 2, B_P = 2 * N1 + N2 + 2, B_X = B_P + 1, B_XF = B_X + 2, B_SP = B_XF + 2, NBAR = B_SP + 2;
+  static constexpr int B_1 = 0, B_2 = N1, B_R = N1 + N2, B_S1 = N1 + N2 + 2, B_P = 2 * N1 + N2 + 2, B_X = B_P + 1, B_XF = B_X + 2, B_SP = B_XF + 2, B_D2 = B_SP + 2, NBAR = B_D2 + 1;
   static constexpr uint32_t SMEM = OFF_BAR + NBAR * 8 + 16;
   static constexpr uint32_t TX_BYTES = PL * XG * ((S + 2) * WP + (S / 2) * CP) * 16;   // bytes one step's TMA loads deliver
   static constexpr int COL_R = 0, COL_1 = 2 * NP, COL_2 = 2 * NP + N1 * NP;
@@ -281,6 +294,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       mbar_init(&bars[G::B_XF + i], 1);                                        // tcgen05.commit: the buffer's first convolution is done
     }
     mbar_init(&bars[G::B_SP], 1); mbar_init(&bars[G::B_SP + 1], 1);            // spectrogram tiles of the entry convolution
+    mbar_init(&bars[G::B_D2], G::NEW);                                         // UF2: D2 written, one arrival per worker warp
     fence_mbar_init();
   }
   __syncwarp();
@@ -545,6 +559,25 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         for (long long g = 0; g < total_steps; ++g) {
           const uint32_t par = (uint32_t)(g & 1);
           FB_TRACE(3, g);
+          if constexpr (G::UF2) {
+            // un-folded: the workers have written D2 = depthwise(S1) as (hi, lo) rows in accumulator order; pointwise 1x1 only
+            const uint64_t dD2 = make_smem_desc(sbase + G::OFF_D2, G::LBO_D2, 128);
+            mbar_wait(&bars[G::B_D2], par);
+            tc_fence_after();
+#pragma unroll
+            for (int t = 0; t < G::N2; ++t) {
+              if (elect_one()) {
+                mma_f16_ss(tmem + G::COL_2 + t * G::NP, dOnes, dB2, idesc, 0);
+#pragma unroll
+                for (int ks = 0; ks < G::NP / 16; ++ks)
+                  mma_x(tmem + G::COL_2 + t * G::NP, dD2 + (uint32_t)(128 * t) + ((2 * ks * G::LBO_D2) >> 4), dW2 + ((2 * ks * 128) >> 4), G::D2_LO >> 4);
+                mma_commit(&bars[G::B_2 + t]);
+              }
+              __syncwarp();
+            }
+            FB_TRACE(4, g);
+            continue;
+          }
 #pragma unroll
           for (int t = 0; t < G::N2; ++t) {
             // tile t of the second convolution reads S1 tiles <= t+1 (and the carried rows, published with tile 0)
@@ -686,7 +719,14 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
             if (p1 < (G::S + 2) * G::WP) {
               const uint4 z = make_uint4(0, 0, 0, 0);
               unsigned char* dst = smem + G::OFF_S1 + g0 * G::LBO_S1 + p1 * 16;
-              if constexpr (G::PREC) {
+              if constexpr (G::UF2) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = inimg ? fmaxf(v[i], 0.f) : 0.f;
+                unsigned char* dq = smem + G::OFF_S1 + (2 * g0) * G::LBO_S1 + p1 * 16;     // quads 2 g0 .. 2 g0 + 3
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                  if (q < 2 || has1) *reinterpret_cast<float4*>(dq + q * G::LBO_S1) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+              } else if constexpr (G::PREC) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] = inimg ? fmaxf(v[i], 0.f) : 0.f;
                 uint4 hi, lo;
@@ -708,6 +748,50 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&bars[G::B_S1 + t]);
+        }
+        if constexpr (G::UF2) {
+          // ---- depthwise 3x3 of the second separable convolution on the CUDA cores: S1 (fp32) -> D2 (hi, lo) ----
+          worker_sync<G::NWORK>();   // every S1 pixel of this step and the carried rows are in place
+          for (int u = tid; u < G::NQ * G::WP; u += G::NWORK) {
+            const int q = u / G::WP, c = u - q * G::WP;             // channel quad, column: consecutive lanes = consecutive pixels
+            const float4* kw = reinterpret_cast<const float4*>(smem + G::OFF_DW2) + q;
+            float4 k[9];
+#pragma unroll
+            for (int t = 0; t < 9; ++t) k[t] = kw[t * (G::NP / 4)];
+            const unsigned char* s1q = smem + G::OFF_S1 + q * G::LBO_S1;
+            auto ld = [&](int y, int x) { return *reinterpret_cast<const float4*>(s1q + (y * G::WP + x) * 16); };
+            float4 w[3][3];
+#pragma unroll
+            for (int y = 0; y < 2; ++y)
+#pragma unroll
+              for (int x = 0; x < 3; ++x) w[y + 1][x] = ld(y, c - 1 + x);
+#pragma unroll 1
+            for (int r = 1; r <= G::S; ++r) {                        // S2 row r <- S1 rows r-1 .. r+1
+#pragma unroll
+              for (int x = 0; x < 3; ++x) { w[0][x] = w[1][x]; w[1][x] = w[2][x]; w[2][x] = ld(r + 1, c - 1 + x); }
+              float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+              for (int t = 0; t < 9; ++t) {
+                const float4 a = w[t / 3][t % 3];
+                acc.x = fmaf(a.x, k[t].x, acc.x); acc.y = fmaf(a.y, k[t].y, acc.y); acc.z = fmaf(a.z, k[t].z, acc.z); acc.w = fmaf(a.w, k[t].w, acc.w);
+              }
+              const int m = r * G::WP + c - G::P2_0;                 // accumulator row (all tiles) of this pixel
+              if (m >= 0 && m < G::D2PIX) {
+                const __half2 h01 = __floats2half2_rn(acc.x, acc.y), h23 = __floats2half2_rn(acc.z, acc.w);
+                const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                const __half2 l01 = __floats2half2_rn(acc.x - f01.x, acc.y - f01.y), l23 = __floats2half2_rn(acc.z - f23.x, acc.w - f23.y);
+                unsigned char* dst = smem + G::OFF_D2 + (q >> 1) * G::LBO_D2 + m * 16 + (q & 1) * 8;
+                uint2 hv, lv;
+                hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+                lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+                *reinterpret_cast<uint2*>(dst) = hv;
+                *reinterpret_cast<uint2*>(dst + G::D2_LO) = lv;
+              }
+            }
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&bars[G::B_D2]);
         }
         // ---- previous step: pool + store while the tensor pipe runs this step's second convolution ----
         if (warp == 0) FB_TRACE(20, g);
@@ -767,9 +851,10 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         // ---- carry the S1 overlap rows into the next step (rows above the next strip's first row are zero) ----
         const bool carry = step + 1 < n_steps;
         if (g + 1 < total_steps) {
-          for (int i = tid; i < G::PL * G::NG * 2 * G::WP; i += G::NWORK) {
+          constexpr int kCarryPlanes = G::UF2 ? G::NQ : G::PL * G::NG;
+          for (int i = tid; i < kCarryPlanes * 2 * G::WP; i += G::NWORK) {
             const int gs = i / (2 * G::WP), px = i - gs * 2 * G::WP;
-            const int gq = gs % G::NG + (gs / G::NG) * G::MCH;   // lo planes sit MCH planes after the hi planes
+            const int gq = G::UF2 ? gs : gs % G::NG + (gs / G::NG) * G::MCH;   // lo planes sit MCH planes after the hi planes
             unsigned char* p = smem + G::OFF_S1 + gq * G::LBO_S1 + px * 16;
             *reinterpret_cast<uint4*>(p) = carry ? *reinterpret_cast<const uint4*>(p + G::S * G::WP * 16) : make_uint4(0, 0, 0, 0);
           }

@@ -333,7 +333,7 @@ sep_uf_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__
 
 // block 1 of the fp32-grade path: one CTA per SM (the (hi, lo) plane sets fill its shared memory), two issuer warps; its output
 // is the un-rectified block output in fp32 (the next block applies the ReLU on load and walks it with stride 2 for its residual)
-using FB1P = fused::FB<16, 30, 29, 6, false, 1, 8, false, 2, 1, true>;
+using FB1P = fused::FB<16, 30, 29, 4, false, 1, 8, false, 2, 1, true, true>;   // S = 4: the D2 operand takes the room of two more rows
 
 inline std::vector<float> pad_matrix(const float* w, int rows, int cols, int rows_p, int cols_p) {
   std::vector<float> out((size_t)rows_p * cols_p, 0.f);
@@ -558,7 +558,7 @@ int forward_precise_tall(Ctx* c, const float* d_raw, int64_t first, int64_t n, f
   const int Tn = Himg >> nw->n_blocks;
   const int *hs = g.hs, *ws = g.ws, *cp = g.cp;
   const int shift = c->p.snippet_len / 2;
-  constexpr int kWarm = 6, kGuardB = 8;            // block 1: warm-up rows of a window (one step), zero rows before the tall tensor
+  constexpr int kWarm = 2 * FB1P::S, kGuardB = 8;            // block 1: warm-up rows of a window (one step), zero rows before the tall tensor
   const int kWin = shift;                          // block 1: rows per window
   const int kGuardA = kWin + 16;                   // zero rows after the tall tensor
   const int nt[6] = {1, 2, 2, 2, 2, 3}, nb[6] = {1, 2, 3, 3, 3, 4};   // rows of a snippet that feel its top / bottom border, per level (5 = features)

@@ -667,10 +667,18 @@ int build_fused_block(Ctx* c, int blk) {
       for (int n = 0; n < G::COUT; ++n)
         put(at(G::OFF_W1 + t * G::TAP_W1, G::SBO_W1, n, k), (double)(s1.dw[(size_t)t * G::CIN + k] * s1.pw[(size_t)k * G::COUT + n]),
             cal.valid ? cal.in_relu[blk][k] : 0.0, &d1[n]);
+    if (!G::UF2)
+      for (int k = 0; k < G::COUT; ++k)
+        for (int n = 0; n < G::COUT; ++n)
+          put(at(G::OFF_W2 + t * G::TAP_W2, G::SBO_W2, n, k), (double)(s2.dw[(size_t)t * G::COUT + k] * s2.pw[(size_t)k * G::COUT + n]),
+              cal.valid ? cal.s1[blk][k] : 0.0, &d2[n]);
+  }
+  if (G::UF2) {   // un-folded second convolution: pointwise weights as the GEMM operand, depthwise taps as fp32 for the worker warps
     for (int k = 0; k < G::COUT; ++k)
-      for (int n = 0; n < G::COUT; ++n)
-        put(at(G::OFF_W2 + t * G::TAP_W2, G::SBO_W2, n, k), (double)(s2.dw[(size_t)t * G::COUT + k] * s2.pw[(size_t)k * G::COUT + n]),
-            cal.valid ? cal.s1[blk][k] : 0.0, &d2[n]);
+      for (int n = 0; n < G::COUT; ++n) put(at(G::OFF_W2, G::SBO_W2, n, k), (double)s2.pw[(size_t)k * G::COUT + n], 0.0, &d2[n]);
+    float* taps = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(w.data()) + G::OFF_DW2);
+    for (int t = 0; t < 9; ++t)
+      for (int k = 0; k < G::COUT; ++k) taps[t * G::NP + k] = s2.dw[(size_t)t * G::COUT + k];
   }
   const std::vector<float>& rw = nw->h_res_w[blk];
   for (int k = 0; k < G::CIN; ++k)

@@ -616,7 +616,7 @@ def predict(
         devices = devices[: max(1, len(rows))]      # no more worker contexts than recordings
     progressbar = None if _worker else tqdm(total=len(rows), desc="Starting ...", unit="file")
 
-    out_path_of = dict(zip(rows, out_paths))
+    out_path_of = dict(zip(recording_table.index, out_paths))
 
     def row_path(i):
         return Path(recording_table.loc[i, "base_dir_recording"]).joinpath(recording_table.loc[i, "rel_recording_path"])
