@@ -416,12 +416,17 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
           mbar_arrive_expect_tx(&bars[G::B_X + xb], G::TX_BYTES);
 #pragma unroll
           for (int c = 0; c < G::XG; ++c) {
+            if constexpr (G::PREC) {
+              // chunk-planar (hi, lo) tensors, maps {8 ch, w, h, image, chunk}: a box row is one contiguous run (an NHWC tensor would
+              // make every pixel of the box its own 16-byte element: the TMA unit then needs 6 k cycles per step)
+              tma_load_5d(sbase + G::OFF_X + xb * G::XR_BYTES + c * G::LBO_X, &tmX, &bars[G::B_X + xb], 0, cb, a + 1, (int)b, c);
+              tma_load_5d(sbase + G::OFF_R + xb * G::XR_BYTES + c * G::LBO_R, &tmR, &bars[G::B_X + xb], 0, wo0 * r_step, (a >> 1) * r_step, (int)b, c);
+              tma_load_5d(sbase + G::OFF_X + G::X_LO + xb * G::XR_BYTES + c * G::LBO_X, &tmXl, &bars[G::B_X + xb], 0, cb, a + 1, (int)b, c);
+              tma_load_5d(sbase + G::OFF_R + G::R_LO + xb * G::XR_BYTES + c * G::LBO_R, &tmRl, &bars[G::B_X + xb], 0, wo0 * r_step, (a >> 1) * r_step, (int)b, c);
+            } else {
             tma_load_5d(sbase + G::OFF_X + xb * G::XR_BYTES + c * G::LBO_X, &tmX, &bars[G::B_X + xb], 0, c, cb, a + 1, (int)b);
             // residual input pixels (2*ho, 2*wo): coordinates in the even-position tensor, or in the full tensor read with stride 2
             tma_load_5d(sbase + G::OFF_R + xb * G::XR_BYTES + c * G::LBO_R, &tmR, &bars[G::B_X + xb], 0, c, wo0 * r_step, (a >> 1) * r_step, (int)b);
-            if constexpr (G::PREC) {
-              tma_load_5d(sbase + G::OFF_X + G::X_LO + xb * G::XR_BYTES + c * G::LBO_X, &tmXl, &bars[G::B_X + xb], 0, c, cb, a + 1, (int)b);
-              tma_load_5d(sbase + G::OFF_R + G::R_LO + xb * G::XR_BYTES + c * G::LBO_R, &tmRl, &bars[G::B_X + xb], 0, c, wo0 * r_step, (a >> 1) * r_step, (int)b);
             }
           }
         }
@@ -765,8 +770,8 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
             for (int y = 0; y < 2; ++y)
 #pragma unroll
               for (int x = 0; x < 3; ++x) w[y + 1][x] = ld(y, c - 1 + x);
-#pragma unroll 1
-            for (int r = 1; r <= G::S; ++r) {                        // S2 row r <- S1 rows r-1 .. r+1
+#pragma unroll
+            for (int r = 1; r <= G::S; ++r) {                        // S2 row r <- S1 rows r-1 .. r+1 (unrolled: the window rotates by renaming)
 #pragma unroll
               for (int x = 0; x < 3; ++x) { w[0][x] = w[1][x]; w[1][x] = w[2][x]; w[2][x] = ld(r + 1, c - 1 + x); }
               float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -792,6 +797,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) mbar_arrive(&bars[G::B_D2]);
+          if (warp == 0) FB_TRACE(23, g);
         }
         // ---- previous step: pool + store while the tensor pipe runs this step's second convolution ----
         if (warp == 0) FB_TRACE(20, g);

@@ -355,6 +355,7 @@ int build_precise_sep(Ctx* c, const NetWeights::HostSep& hs, NetWeights::Precise
 int prepare_precise(Ctx* c) {
   NetWeights* nw = c->net;
   if (nw->precise_ready) return ORCAI_OK;
+  ORCAI_CHECK(prepare_bringup_aids(c));
   ORCAI_CHECK(build_fused_block<FB1P>(c, 0));
   for (int b = 1; b < nw->n_blocks; ++b) {
     ORCAI_CHECK(build_precise_sep(c, nw->h_sep1[b], &nw->p_sep1[b]));
@@ -442,12 +443,12 @@ int run_precise_block(Ctx* c, int blk, const float* x, float* ta, float* tb, flo
 }
 
 int run_conv0_split(Ctx* c, const float* src, int input_mode, long long first, int in_ld, long long n_img, int Himg, int Wf, __half* hi, __half* lo,
-                    long long n_snip, int off_bot, int Hfull) {
+                    long long n_snip, int off_bot, int Hfull, long long plane_halfs) {
   const int tiles_w = (Wf + kC0TW - 1) / kC0TW, tiles_h = (Himg + kC0TH - 1) / kC0TH;
   const long long blocks = n_img * tiles_w * tiles_h;
   if (blocks <= 0) return ORCAI_OK;
   conv0_direct_kernel<true><<<(unsigned)blocks, 256, 0, c->stream>>>(src, input_mode, first, c->p.snippet_len / 2, in_ld, Himg, Wf, c->d_sel, hi,
-                                                                     static_cast<__half*>(nullptr), tiles_w, tiles_h, lo, n_snip, off_bot, Hfull);
+                                                                     static_cast<__half*>(nullptr), tiles_w, tiles_h, lo, n_snip, off_bot, Hfull, plane_halfs);
   c->launches++;
   ORCAI_CUDA(c, cudaGetLastError());
   return ORCAI_OK;
@@ -455,7 +456,7 @@ int run_conv0_split(Ctx* c, const float* src, int input_mode, long long first, i
 
 // block 1 over ONE tall image (rows, W) of (hi, lo) fp16 pairs, cut into windows of `stride` rows (+ warm-up); guard rows of
 // zeros lie before x (>= warm rows) and after it (>= stride + 16 rows)
-int run_block1_tall(Ctx* c, const __half* x_hi, const __half* x_lo, float* y, long long rows, int Wimg, int stride, int warm) {
+int run_block1_tall(Ctx* c, const __half* x_hi, const __half* x_lo, long long plane_halfs, float* y, long long rows, int Wimg, int stride, int warm) {
   using G = FB1P;
   NetWeights* nw = c->net;
   const int Wo = (Wimg + 1) / 2;
@@ -464,12 +465,12 @@ int run_block1_tall(Ctx* c, const __half* x_hi, const __half* x_lo, float* y, lo
   const long long items = n_win * n_strips;
   const long long grid = std::min<long long>(items, (long long)c->sm_count * G::CTAS);
   const int Hloc = warm + stride;
-  const size_t shift = (size_t)warm * Wimg * G::ICP;
+  const size_t shift = (size_t)warm * Wimg * 8;      // halfs per plane
   CUtensorMap tmx, tmr, tmxl, tmrl;
-  ORCAI_CHECK(make_act_map(c, &tmx, x_hi - shift, n_win, Hloc + 8, Wimg, G::ICP, G::WP, G::S + 2, 1, stride));
-  ORCAI_CHECK(make_act_map(c, &tmr, x_hi - shift, n_win, Hloc + 8, Wimg, G::ICP, G::CP, G::S / 2, 2, stride));
-  ORCAI_CHECK(make_act_map(c, &tmxl, x_lo - shift, n_win, Hloc + 8, Wimg, G::ICP, G::WP, G::S + 2, 1, stride));
-  ORCAI_CHECK(make_act_map(c, &tmrl, x_lo - shift, n_win, Hloc + 8, Wimg, G::ICP, G::CP, G::S / 2, 2, stride));
+  ORCAI_CHECK(make_planar_map(c, &tmx, x_hi - shift, n_win, Hloc + 8, Wimg, G::XG, plane_halfs, G::WP, G::S + 2, 1, stride));
+  ORCAI_CHECK(make_planar_map(c, &tmr, x_hi - shift, n_win, Hloc + 8, Wimg, G::XG, plane_halfs, G::CP, G::S / 2, 2, stride));
+  ORCAI_CHECK(make_planar_map(c, &tmxl, x_lo - shift, n_win, Hloc + 8, Wimg, G::XG, plane_halfs, G::WP, G::S + 2, 1, stride));
+  ORCAI_CHECK(make_planar_map(c, &tmrl, x_lo - shift, n_win, Hloc + 8, Wimg, G::XG, plane_halfs, G::CP, G::S / 2, 2, stride));
   fused::TallView tv;
   tv.on = 1; tv.stride = stride; tv.warm = warm; tv.rows = rows;
   fused::fused_block_kernel<G><<<(unsigned)grid, G::NTHREADS, G::SMEM, c->stream>>>(tmx, tmr, 2, reinterpret_cast<__half*>(y), static_cast<__half*>(nullptr), Hloc,
@@ -518,11 +519,12 @@ int forward_precise_snippets(Ctx* c, const float* d_in, int input_mode, int64_t 
     if (mk) nw->marked_snippets = m;
     net_mark(c, mk);
     const float* src = (input_mode == 0) ? d_in : d_in + (size_t)s0 * Himg * Wf;
-    ORCAI_CHECK(run_conv0_split(c, src, input_mode, first + s0, input_mode == 0 ? kRawLd : Wf, m, Himg, Wf, c0hi, c0lo, m, 0, Himg));
+    const long long plane = (long long)m * hs[0] * ws[0] * 8;   // chunk-planar (hi, lo) output: two planes of 8 channels each
+    ORCAI_CHECK(run_conv0_split(c, src, input_mode, first + s0, input_mode == 0 ? kRawLd : Wf, m, Himg, Wf, c0hi, c0lo, m, 0, Himg, plane));
     net_mark(c, mk);  // 0: conv0
-    if (stop == 0) { set_debug(nw, c0hi, 1, m, hs[0], ws[0], 16, 16); return ORCAI_OK; }
+    if (stop == 0) { set_debug(nw, c0hi, 1, m, hs[0], ws[0], 8, 8); return ORCAI_OK; }   // channels 0-7, hi plane
     ORCAI_CHECK((run_fused_block<FB1P>(c, 0, c0hi, static_cast<const H16*>(nullptr), reinterpret_cast<H16*>(Y1), static_cast<H16*>(nullptr), m, hs[0], ws[0],
-                                       c0lo, static_cast<const H16*>(nullptr))));
+                                       c0lo, static_cast<const H16*>(nullptr), plane)));
     net_mark(c, mk);  // 1
     if (stop == 1) { set_debug(nw, Y1, 0, m, hs[1], ws[1], 30, cp[1]); return ORCAI_OK; }
     ORCAI_CHECK(run_precise_block(c, 1, Y1, TA, TB, TC, Y2, m, hs[1], ws[1], cp[1], cp[2]));
@@ -586,7 +588,9 @@ int forward_precise_tall(Ctx* c, const float* d_raw, int64_t first, int64_t n, f
   ORCAI_CHECK(ensure_device_buffer(c, &nw->tc_ws, &nw->tc_ws_cap, off + 256));
   unsigned char* base = static_cast<unsigned char*>(nw->tc_ws);
   auto F = [&](size_t o) { return reinterpret_cast<float*>(base + o); };
-  const size_t c0_row = (size_t)ws[0] * 16;        // halfs per row of the entry convolution's output
+  // entry-convolution output, chunk-planar: per (hi | lo) set two planes of (guard + rows + guard, W, 8) halfs
+  const size_t c0_row = (size_t)ws[0] * 8;         // halfs per row of one plane
+  const long long c0_plane_halfs = (long long)(kGuardB + rows_at(M, 0) + kGuardA) * c0_row;
   H16* c0hi = reinterpret_cast<H16*>(base + o_c0hi) + kGuardB * c0_row;
   H16* c0lo = reinterpret_cast<H16*>(base + o_c0lo) + kGuardB * c0_row;
   float* Y[5] = {nullptr, F(o_y[1]), F(o_y[2]), F(o_y[3]), F(o_y[4])};
@@ -603,17 +607,20 @@ int forward_precise_tall(Ctx* c, const float* d_raw, int64_t first, int64_t n, f
     const long long R0 = rows_at(m, 0);
     net_mark(c, mk);
     // entry convolution: the chunk's rows as one image, and the 8-row border images of every snippet (its own zero padding)
-    for (H16* p : {c0hi, c0lo}) {
-      ORCAI_CUDA(c, cudaMemsetAsync(p - kGuardB * c0_row, 0, kGuardB * c0_row * 2, c->stream));
-      ORCAI_CUDA(c, cudaMemsetAsync(p + R0 * c0_row, 0, (size_t)kGuardA * c0_row * 2, c->stream));
-    }
-    ORCAI_CHECK(run_conv0_split(c, d_raw, 0, first + s0, kRawLd, 1, (int)R0, Wf, c0hi, c0lo, 1, 0, (int)R0));
-    ORCAI_CHECK(run_conv0_split(c, d_raw, 0, first + s0, kRawLd, 2 * m, 8, Wf, b0hi, b0lo, m, Himg - 8, Himg));
+    for (H16* p0 : {c0hi, c0lo})
+      for (int pl = 0; pl < 2; ++pl) {
+        H16* p = p0 + (size_t)pl * c0_plane_halfs;
+        ORCAI_CUDA(c, cudaMemsetAsync(p - kGuardB * c0_row, 0, kGuardB * c0_row * 2, c->stream));
+        ORCAI_CUDA(c, cudaMemsetAsync(p + R0 * c0_row, 0, (size_t)kGuardA * c0_row * 2, c->stream));
+      }
+    const long long b0_plane_halfs = (long long)2 * m * 8 * ws[0] * 8;
+    ORCAI_CHECK(run_conv0_split(c, d_raw, 0, first + s0, kRawLd, 1, (int)R0, Wf, c0hi, c0lo, 1, 0, (int)R0, c0_plane_halfs));
+    ORCAI_CHECK(run_conv0_split(c, d_raw, 0, first + s0, kRawLd, 2 * m, 8, Wf, b0hi, b0lo, m, Himg - 8, Himg, b0_plane_halfs));
     net_mark(c, mk);  // 0: conv0
     // block 1: fused kernel over windows of the tall image; border images as independent 8-row images -> ALT (2m, 4, ..)
-    ORCAI_CHECK(run_block1_tall(c, c0hi, c0lo, Y[1], R0, Wf, kWin, kWarm));
+    ORCAI_CHECK(run_block1_tall(c, c0hi, c0lo, c0_plane_halfs, Y[1], R0, Wf, kWin, kWarm));
     ORCAI_CHECK((run_fused_block<FB1P>(c, 0, b0hi, static_cast<const H16*>(nullptr), reinterpret_cast<H16*>(ALT), static_cast<H16*>(nullptr), 2 * m, 8, ws[0],
-                                       b0lo, static_cast<const H16*>(nullptr))));
+                                       b0lo, static_cast<const H16*>(nullptr), b0_plane_halfs)));
     net_mark(c, mk);  // 1
     // blocks 2 - 4: tall image, then the border images gathered from the tall tensor and the previous level's border rows
     for (int l = 1; l <= 3; ++l) {

@@ -334,7 +334,7 @@ template <bool SPLIT>
 __global__ void __launch_bounds__(256)
 conv0_direct_kernel(const float* __restrict__ in, int mode, long long first, int shift, int in_ld, int Himg, int Wimg,
                     const SelectState* __restrict__ st, __half* __restrict__ out, __half* __restrict__ out_sub,
-                    int tiles_w, int tiles_h, __half* __restrict__ out_lo, long long n_snip, int off_bot, int Hfull) {
+                    int tiles_w, int tiles_h, __half* __restrict__ out_lo, long long n_snip, int off_bot, int Hfull, long long plane_halfs) {
   __shared__ float s_x[kC0TH + 2][kC0TW + 2];
   const int tid = threadIdx.x, ty = tid >> 5, tx = tid & 31;
   const int tiles_per = tiles_w * tiles_h;
@@ -378,6 +378,15 @@ conv0_direct_kernel(const float* __restrict__ in, int mode, long long first, int
     uint4 h0, l0, h1, l1;
     fused::split8h(acc, h0, l0);
     fused::split8h(acc + 8, h1, l1);
+    if (plane_halfs > 0) {
+      // chunk-planar: channels 0-7 and 8-15 as two (n, H, W, 8) planes plane_halfs apart - rows of a TMA box are then contiguous
+      const size_t at = (((size_t)b * Himg + hh) * Wimg + ww) * 8;
+      *reinterpret_cast<uint4*>(out + at) = h0;
+      *reinterpret_cast<uint4*>(out + at + plane_halfs) = h1;
+      *reinterpret_cast<uint4*>(out_lo + at) = l0;
+      *reinterpret_cast<uint4*>(out_lo + at + plane_halfs) = l1;
+      return;
+    }
     const size_t at = (((size_t)b * Himg + hh) * Wimg + ww) * 16;
     reinterpret_cast<uint4*>(out + at)[0] = h0;
     reinterpret_cast<uint4*>(out + at)[1] = h1;
@@ -820,9 +829,8 @@ unsigned int* g_trap_host = nullptr;   // mapped host memory behind tc::g_trap_i
 long long* g_trace_dev = nullptr;      // device memory behind fused::g_trace (ORCAI_B200_TRACE=<file>)
 #endif
 
-int prepare_fused(Ctx* c) {
-  NetWeights* nw = c->net;
-  if (nw->fused_ready) return ORCAI_OK;
+// bring-up aids shared by the fused paths (compiled out of the product)
+int prepare_bringup_aids(Ctx* c) {
 #ifdef ORCAI_FUSED_TRACE
   if (g_trace_dev == nullptr && getenv("ORCAI_B200_TRACE") != nullptr) {
     ORCAI_CUDA(c, cudaMalloc(reinterpret_cast<void**>(&g_trace_dev), 8 * 8 * 256));
@@ -839,6 +847,14 @@ int prepare_fused(Ctx* c) {
     ORCAI_CUDA(c, cudaMemcpyToSymbol(tc::g_trap_info, &d, sizeof d));
   }
 #endif
+  (void)c;
+  return ORCAI_OK;
+}
+
+int prepare_fused(Ctx* c) {
+  NetWeights* nw = c->net;
+  if (nw->fused_ready) return ORCAI_OK;
+  ORCAI_CHECK(prepare_bringup_aids(c));
   ORCAI_CHECK(net_tc_prepare(c, 0));   // the final sepconv reuses the fp16 layer-wise operands
   ORCAI_CHECK(build_conv0_mma(c));
   ORCAI_CHECK(build_fused_block<FB1>(c, 0));
@@ -899,9 +915,25 @@ int make_act_map(Ctx* c, CUtensorMap* map, const __half* base, long long n, int 
 }
 
 // PREC blocks take their input tensors as (hi, lo) pairs (xr_lo, xs_lo) and write fp32 tensors (yr, ys point to floats)
+// rank-5 map over a chunk-PLANAR fp16 activation tensor: `planes` planes of (n, h, w, 8) halfs, plane_halfs apart;
+// box = {8 ch, box_w, box_h, 1 image, 1 plane}: every row of a box is one contiguous run of box_w * 16 bytes
+int make_planar_map(Ctx* c, CUtensorMap* map, const __half* base, long long n, int h, int w, int planes, long long plane_halfs, int box_w, int box_h,
+                    int step = 1, long long img_rows = 0) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) ORCAI_FAIL(c, ORCAI_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t dims[5] = {8, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n, (cuuint64_t)planes};
+  const cuuint64_t strides[4] = {16, (cuuint64_t)w * 16, (cuuint64_t)(img_rows > 0 ? img_rows : h) * w * 16, (cuuint64_t)plane_halfs * 2};
+  const cuuint32_t box[5] = {8, (cuuint32_t)(box_w * step), (cuuint32_t)(box_h * step), 1, 1};
+  const cuuint32_t estr[5] = {1, (cuuint32_t)step, (cuuint32_t)step, 1, 1};
+  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 5, const_cast<__half*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) ORCAI_FAIL(c, ORCAI_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for the planar tensor (%lld, %d, %d) x %d", (int)r, n, h, w, planes);
+  return ORCAI_OK;
+}
+
 template <class G>
 int run_fused_block(Ctx* c, int blk, const __half* xr, const __half* xs, __half* yr, __half* ys, long long m, int Himg, int Wimg,
-                    const __half* xr_lo = nullptr, const __half* xs_lo = nullptr) {
+                    const __half* xr_lo = nullptr, const __half* xs_lo = nullptr, long long plane_halfs = 0) {
   NetWeights* nw = c->net;
   const int Ho = Himg / 2, Wo = (Wimg + 1) / 2;
   const int n_strips = (Wo + G::CP - 1) / G::CP;
@@ -914,10 +946,12 @@ int run_fused_block(Ctx* c, int blk, const __half* xr, const __half* xs, __half*
   if (xs) ORCAI_CHECK(make_act_map(c, &tmr, xs, m, Ho, Wo, G::ICP, G::CP, G::S / 2));
   else ORCAI_CHECK(make_act_map(c, &tmr, xr, m, Himg, Wimg, G::ICP, G::CP, G::S / 2, 2));
   tmxl = tmx; tmrl = tmr;
-  if (G::PREC) {
-    ORCAI_CHECK(make_act_map(c, &tmxl, xr_lo, m, Himg, Wimg, G::ICP, G::WP, G::S + 2));
-    if (xs) ORCAI_CHECK(make_act_map(c, &tmrl, xs_lo, m, Ho, Wo, G::ICP, G::CP, G::S / 2));
-    else ORCAI_CHECK(make_act_map(c, &tmrl, xr_lo, m, Himg, Wimg, G::ICP, G::CP, G::S / 2, 2));
+  if (G::PREC) {   // chunk-planar (hi, lo) inputs; the residual convolution walks the same tensors with stride 2
+    (void)xs_lo;
+    ORCAI_CHECK(make_planar_map(c, &tmx, xr, m, Himg, Wimg, G::XG, plane_halfs, G::WP, G::S + 2));
+    ORCAI_CHECK(make_planar_map(c, &tmr, xr, m, Himg, Wimg, G::XG, plane_halfs, G::CP, G::S / 2, 2));
+    ORCAI_CHECK(make_planar_map(c, &tmxl, xr_lo, m, Himg, Wimg, G::XG, plane_halfs, G::WP, G::S + 2));
+    ORCAI_CHECK(make_planar_map(c, &tmrl, xr_lo, m, Himg, Wimg, G::XG, plane_halfs, G::CP, G::S / 2, 2));
   }
   fused::fused_block_kernel<G><<<(unsigned)grid, G::NTHREADS, G::SMEM, c->stream>>>(tmx, tmr, xs ? 1 : 2, yr, ys, Himg, Wimg, n_strips, items,
                                                                                    static_cast<const unsigned char*>(G::PREC ? nw->fbp_w[blk] : nw->fb_w[blk]),
@@ -1063,7 +1097,7 @@ int forward_fused(Ctx* c, const float* d_in, int input_mode, int64_t first, int6
       const float* src = (input_mode == 0) ? d_in : d_in + (size_t)s0 * Himg * Wf;
       conv0_direct_kernel<false><<<(unsigned)(m * tiles_w * tiles_h), 256, 0, c->stream>>>(src, input_mode, first + s0, shift, input_mode == 0 ? kRawLd : Wf,
                                                                                           Himg, Wf, c->d_sel, act[0], static_cast<H*>(nullptr), tiles_w, tiles_h,
-                                                                                          static_cast<H*>(nullptr), m, 0, Himg);
+                                                                                          static_cast<H*>(nullptr), m, 0, Himg, 0);
       c->launches++;
       ORCAI_CUDA(c, cudaGetLastError());
     }

@@ -8,7 +8,8 @@ from orcai_b200.weights import synthetic_weights
 P, S = runtime.bundled_parameters()
 ctx = runtime.get_context(P, S, 0)
 ctx.load_weights(synthetic_weights(P, S, seed=1234))
-ctx.set_option("net_path", 3)
+import os
+ctx.set_option("net_path", int(os.environ.get("ORCAI_TRACE_NET_PATH", "3")))
 pcm = synth_pcm16(600.0, seed=20251018)
 for _ in range(3):
     ctx.predict_pcm(pcm)

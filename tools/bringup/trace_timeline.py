@@ -9,7 +9,7 @@ from collections import defaultdict
 
 NAMES = {1: "issuer: X landed, start conv1", 2: "issuer: conv1 issued", 3: "issuer: start conv2 (waits s1_full)", 4: "issuer: conv2 issued",
          5: "producer: X free, TMA issued", 20: "workers: epi1 done", 21: "workers: pool+store done", 22: "workers: carry S2 done, wait conv2",
-         39: "workers: epi2 drained (warp 0)", 40: "workers: all drained (sync)", 41: "workers: S1 carry done = step end"}
+         19: "workers: epi1 stores done (warp 0), sync", 23: "workers: depthwise -> D2 done (warp 0)", 39: "workers: epi2 drained (warp 0)", 40: "workers: all drained (sync)", 41: "workers: S1 carry done = step end"}
 for t in range(8):
     NAMES[10 + t] = f"workers: conv1 tile {t} complete"
     NAMES[30 + t] = f"workers: conv2 tile {t} complete"
