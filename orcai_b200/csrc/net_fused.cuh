@@ -613,8 +613,10 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     const int quad = warp & 3, team = warp >> 2;
     const int row = quad * 32 + lane;              // accumulator row (TMEM lane) this thread drains
     const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
-    const int g0 = team * 2;                       // first of the (up to) two channel groups of this team
-    const bool has0 = g0 < G::NG, has1 = g0 + 1 < G::NG;
+    // a team drains two channel groups (16 accumulator columns), or one when there are as many teams as groups
+    constexpr int kGPT = G::NT >= G::NG ? 1 : 2;
+    const int g0 = team * kGPT;                    // first of the (up to) two channel groups of this team
+    const bool has0 = g0 < G::NG, has1 = kGPT == 2 && g0 + 1 < G::NG;
     const int q_i = row / G::CP, q_j = row - q_i * G::CP;   // pooled pixel of the pool / residual epilogue
     // tile-invariant pixel coordinates of the accumulator rows this thread drains
     int y1[G::N1], c1[G::N1], y2[G::N2], c2[G::N2];

@@ -101,19 +101,35 @@ def weights_from_h5(h5: H5File, orcai_parameter: dict, shape: dict, config: dict
     if not layers:
         raise Hdf5Error("no Keras layer variables found in the HDF5 file")
     order = sorted(layers, key=_suffix_key)
+    cfg_names: list = []
     if config is not None:
         try:
             cfg_names = [l["name"] if "name" in l else l["config"]["name"] for l in config["config"]["layers"]]
         except (KeyError, TypeError):
             cfg_names = []
-        if cfg_names and all(n in cfg_names for n in layers):
-            order = sorted(layers, key=cfg_names.index)
+    ordered_by_config = bool(cfg_names) and all(n in cfg_names for n in layers)
+    if ordered_by_config:
+        order = sorted(layers, key=cfg_names.index)
     by_kind: dict[str, list[str]] = {"conv": [], "sep": [], "bn": [], "bi": [], "dense": []}
     for name in order:
         k = _kind(layers[name])
         if k is None:
             raise Hdf5Error(f"layer group {name!r}: unrecognised variable structure {sorted(layers[name])}")
         by_kind[k].append(name)
+    if not ordered_by_config:
+        # Without a layer list the only order information is the numeric suffix of auto-generated names (conv2d, conv2d_1, ..: creation
+        # order; this reader does not parse the legacy file's `layer_names` attribute).  Several layers of one kind have identical
+        # shapes (the two BatchNormalizations of a block), so a renamed or re-created layer could be swapped silently: refuse any
+        # family that is not one base name with consecutive suffixes.
+        for kind, names in by_kind.items():
+            keys = [_suffix_key(n) for n in names]
+            bases = {b for b, _ in keys}
+            nums = [k for _, k in keys]
+            if nums and (len(bases) > 1 or nums != list(range(nums[0], nums[0] + len(nums)))):
+                raise Hdf5Error(
+                    f"cannot establish the order of the {kind!r} layers from their names {names}: expected one auto-generated family with "
+                    "consecutive suffixes (e.g. conv2d, conv2d_1, ..). Export the weights with tools/export_keras_weights.py (-> .weights.npz) "
+                    "or provide the .keras archive, whose config.json lists the layers in order.")
     nb = len(orcai_parameter["model"]["filters"])
     want = {"conv": 1 + nb, "sep": 2 * nb + 1, "bn": 2 * nb + 3, "bi": 2, "dense": 2}
     got = {k: len(v) for k, v in by_kind.items()}

@@ -362,3 +362,84 @@ def test_model_rebinds_a_shared_context(monkeypatch):
     assert "precise" in m1.describe() and "calibration" in m2.describe()
     with pytest.raises(ValueError):
         model_mod.OrcaiModel(P, S, W1, precision="bf16")
+
+
+def _spec_read_zarr_v3(root: Path) -> np.ndarray:
+    """A reader written from the Zarr v3 core specification alone (no knowledge of orcai_b200.io): zarr.json -> array.
+    Supports what zarr-python 3.0.8 emits for `zarr.open(mode="w", shape, chunks, dtype="float32")` with the gzip default
+    compressor the reference configures (io.py:320-330): regular chunk grid, default chunk-key encoding, bytes + gzip codecs."""
+    import zlib
+
+    meta = json.loads((root / "zarr.json").read_text())
+    required = {"zarr_format", "node_type", "shape", "data_type", "chunk_grid", "chunk_key_encoding", "fill_value", "codecs"}
+    assert required <= set(meta), sorted(required - set(meta))
+    assert meta["zarr_format"] == 3 and meta["node_type"] == "array"
+    assert set(meta) <= required | {"attributes", "storage_transformers", "dimension_names"}   # nothing a v3 reader would not know
+    assert meta.get("storage_transformers", []) == [] and isinstance(meta.get("attributes", {}), dict)
+    dtype = {"float32": "f4", "float64": "f8", "int16": "i2", "int32": "i4"}[meta["data_type"]]
+    grid = meta["chunk_grid"]
+    assert grid["name"] == "regular"
+    cshape = tuple(grid["configuration"]["chunk_shape"])
+    enc = meta["chunk_key_encoding"]
+    assert enc["name"] in ("default", "v2")
+    sep = enc.get("configuration", {}).get("separator", "/" if enc["name"] == "default" else ".")
+    codecs = meta["codecs"]
+    kinds = [c["name"] for c in codecs]
+    assert kinds.count("bytes") == 1 and kinds.index("bytes") == 0, "exactly one array->bytes codec, first"
+    endian = codecs[0].get("configuration", {}).get("endian", "little")
+    shape = tuple(meta["shape"])
+    out = np.full(shape, meta["fill_value"], dtype=dtype)
+    n_chunks = [-(-s // c) for s, c in zip(shape, cshape)]
+    for idx in np.ndindex(*n_chunks):
+        key = ("c" + sep + sep.join(map(str, idx))) if enc["name"] == "default" else sep.join(map(str, idx))
+        f = root / key
+        if not f.exists():
+            continue                                          # missing chunk = fill value
+        raw = f.read_bytes()
+        for c in reversed(codecs[1:]):                        # bytes -> bytes codecs, undone last to first
+            assert c["name"] == "gzip" and 0 <= c["configuration"].get("level", 5) <= 9
+            raw = zlib.decompress(raw, 31)                    # gzip container (RFC 1952)
+        blk = np.frombuffer(raw, dtype=("<" if endian == "little" else ">") + dtype).reshape(cshape)   # edge chunks are full-sized
+        sl = tuple(slice(i * c, min((i + 1) * c, s)) for i, c, s in zip(idx, cshape, shape))
+        out[sl] = blk[tuple(slice(0, x.stop - x.start) for x in sl)]
+    return out
+
+
+def test_zarr_v3_store_conforms_to_the_specification(tmp_path):
+    """The store `create-spectrograms` writes, read back by a reader derived from the Zarr v3 specification only, and the exact
+    metadata zarr-python 3.0.8 produces for the reference's call (keys, codec chain, gzip level 5, chunk keys c/<i>/0)."""
+    rng = np.random.default_rng(3)
+    a = rng.random((4500, 171), dtype=np.float32)
+    a[2000:4000] = 0.0
+    root = tmp_path / "spectrogram.zarr"
+    io.save_as_zarr(a, root)
+    np.testing.assert_array_equal(_spec_read_zarr_v3(root), a)
+    meta = json.loads((root / "zarr.json").read_text())
+    assert meta == {
+        "shape": [4500, 171], "data_type": "float32",
+        "chunk_grid": {"name": "regular", "configuration": {"chunk_shape": [2000, 171]}},
+        "chunk_key_encoding": {"name": "default", "configuration": {"separator": "/"}},
+        "fill_value": 0.0,
+        "codecs": [{"name": "bytes", "configuration": {"endian": "little"}}, {"name": "gzip", "configuration": {"level": 5}}],
+        "attributes": {}, "zarr_format": 3, "node_type": "array", "storage_transformers": [],
+    }
+    files = sorted(str(f.relative_to(root)) for f in root.rglob("*") if f.is_file())
+    assert files == ["c/0/0", "c/2/0", "zarr.json"]          # the all-zero chunk is not stored (write_empty_chunks=False)
+    assert (root / "c" / "0" / "0").read_bytes()[:3] == b"\x1f\x8b\x08"   # gzip magic + deflate
+    # and the other direction: a store with different but valid choices (big-endian bytes codec, another gzip level, an attribute,
+    # dimension names) is read by orcai_b200's reader
+    alt = tmp_path / "alt.zarr"
+    (alt / "c" / "1").mkdir(parents=True)
+    b = rng.random((2500, 171), dtype=np.float32)
+    (alt / "zarr.json").write_text(json.dumps({
+        "zarr_format": 3, "node_type": "array", "shape": [2500, 171], "data_type": "float32", "fill_value": 0.0,
+        "chunk_grid": {"name": "regular", "configuration": {"chunk_shape": [2000, 171]}},
+        "chunk_key_encoding": {"name": "default", "configuration": {"separator": "/"}},
+        "codecs": [{"name": "bytes", "configuration": {"endian": "little"}}, {"name": "gzip", "configuration": {"level": 1}}],
+        "attributes": {"note": "x"}, "dimension_names": ["time", "frequency"]}))
+    pad = np.zeros((2000, 171), np.float32)
+    pad[:500] = b[2000:]
+    (alt / "c" / "1" / "0").write_bytes(gzip.compress(pad.tobytes(), 1))
+    got = io.read_zarr(alt)
+    assert (got[:2000] == 0).all()
+    np.testing.assert_array_equal(got[2000:], b[2000:])

@@ -1,5 +1,6 @@
 """Keras artefact readers (reference io.py:386-404) on top of the pure-Python HDF5 reader: no keras / h5py in the image."""
 
+import json
 import struct
 import zlib
 from pathlib import Path
@@ -174,3 +175,89 @@ def test_load_orcai_model_prefers_like_the_reference(tmp_path, PSW, monkeypatch)
     write_keras_archive(d / (P["name"] + ".keras"), W2, P)
     oio.load_orcai_model(d)
     np.testing.assert_array_equal(seen["W"]["dense2/kernel"], W2["dense2/kernel"])
+
+
+# ---------------------------------------------------------------------------------------------
+# conformance with the published layouts (files written by the real producers cannot be fetched offline)
+# ---------------------------------------------------------------------------------------------
+def _keras3_arrays(W, P, h5_offset=0):
+    """model.weights.h5 of Keras 3.10 for res_net_LSTM_arch: saving_lib names every layer of a container
+    `<snake_case(class)>[_<k>]` with k counting that class INSIDE the container in `model.layers` order (not the layer's own,
+    session-dependent name), variables under `layers/<entry>/vars/<i>` in `layer.weights` order, Bidirectional's cells under
+    `forward_layer/cell/vars/<i>` / `backward_layer/cell/vars/<i>`, the optimizer's slots under `optimizer/vars/<i>`."""
+    from orcai_b200.keras_weights import _LEGACY_ORDER, _SNAKE, _VARS, _layer_plan
+
+    arrays, counts = {}, {}
+    for cls, prefix in _layer_plan(P):
+        k = counts.get(cls, 0)
+        counts[cls] = k + 1
+        entry = _SNAKE[cls] + (f"_{k + h5_offset}" if k + h5_offset else "")
+        if cls == "Bidirectional":
+            for d in ("forward", "backward"):
+                for i, v in enumerate(_LEGACY_ORDER["lstm"]):
+                    arrays[f"/layers/{entry}/{d}_layer/cell/vars/{i}"] = W[f"{prefix}/{d}/{v}"]
+        else:
+            for i, v in enumerate(_LEGACY_ORDER[_VARS[cls]]):
+                arrays[f"/layers/{entry}/vars/{i}"] = W[f"{prefix}/{v}"]
+    # Adam: iteration counter, learning rate, then two slots per trainable variable (train.py:223 saves with the optimizer)
+    arrays["/optimizer/vars/0"] = np.zeros((), np.int64)
+    arrays["/optimizer/vars/1"] = np.float32(1e-3) * np.ones((), np.float32)
+    for j, (kname, a) in enumerate(sorted(W.items())[:6]):
+        arrays[f"/optimizer/vars/{2 + j}"] = np.zeros_like(a)
+    return arrays
+
+
+def test_keras3_archive_layout_conformance(tmp_path, PSW):
+    """A `.keras` archive laid out as Keras 3.10 writes it: config.json carries the layers' own names (session-dependent
+    suffixes, plus every variable-less layer), model.weights.h5 the per-container class-counter names and the optimizer slots."""
+    import zipfile
+
+    from orcai_b200.hdf5_min import write_h5
+    from orcai_b200.keras_weights import _SNAKE, _layer_plan, load_keras_archive
+
+    P, S, W = PSW
+    h5p = tmp_path / "model.weights.h5"
+    write_h5(h5p, _keras3_arrays(W, P))
+    # the layer list of the functional model: own names with a session offset, interleaved with layers that own no variables
+    cfg_layers = [{"class_name": "InputLayer", "name": "input_layer_3", "config": {"name": "input_layer_3"}}]
+    counts = {}
+    for cls, _prefix in _layer_plan(P):
+        k = counts.get(cls, 0)
+        counts[cls] = k + 1
+        cfg_layers.append({"class_name": cls, "name": f"{_SNAKE[cls]}_{k + 17}", "config": {"name": f"{_SNAKE[cls]}_{k + 17}"}})
+        if cls == "BatchNormalization":
+            cfg_layers.append({"class_name": "ReLU", "name": f"re_lu_{k + 40}", "config": {}})
+        if cls == "Conv2D" and k > 0:
+            cfg_layers += [{"class_name": "MaxPooling2D", "name": f"max_pooling2d_{k}", "config": {}}, {"class_name": "Add", "name": f"add_{k}", "config": {}}]
+    arch = tmp_path / "orcai-v1.keras"
+    with zipfile.ZipFile(arch, "w") as z:
+        z.writestr("metadata.json", json.dumps({"keras_version": "3.10.0", "date_saved": "2025-06-01@12:00:00"}))
+        z.writestr("config.json", json.dumps({"module": "keras", "class_name": "Functional", "config": {"name": "functional_2", "layers": cfg_layers}}))
+        z.write(h5p, "model.weights.h5")
+    got = load_keras_archive(arch, P, S)
+    assert set(got) == set(W)
+    for k in W:
+        np.testing.assert_array_equal(got[k], W[k])
+
+
+def test_ambiguous_layer_order_fails_loudly(tmp_path, PSW):
+    """Legacy model_weights.h5 / bare weight files carry no layer list this reader parses; the numeric name suffix is the only
+    order.  A renamed layer, a gap or a second name family must raise instead of silently swapping same-shaped layers."""
+    from orcai_b200.hdf5_min import Hdf5Error, write_h5
+    from orcai_b200.keras_weights import load_weights_h5
+
+    P, S, W = PSW
+    good = _keras3_arrays(W, P, h5_offset=5)                # an auto-generated family that starts at a session offset is fine
+    write_h5(tmp_path / "ok.h5", good)
+    got = load_weights_h5(tmp_path / "ok.h5", P, S)
+    np.testing.assert_array_equal(got["block1/bn2/gamma"], W["block1/bn2/gamma"])
+
+    def renamed(old, new):
+        return {k.replace(f"/layers/{old}/", f"/layers/{new}/"): v for k, v in good.items()}
+
+    for name, arrays in (("renamed", renamed("batch_normalization_7", "my_norm")),            # a custom layer name
+                         ("gap", renamed("batch_normalization_7", "batch_normalization_99")),  # re-created layer: the suffix jumps
+                         ("swapped-family", renamed("separable_conv2d_6", "sepconv_6"))):
+        write_h5(tmp_path / f"{name}.h5", arrays)
+        with pytest.raises(Hdf5Error, match="order of the"):
+            load_weights_h5(tmp_path / f"{name}.h5", P, S)
