@@ -53,7 +53,10 @@ dw3x3_kernel(const float* __restrict__ x, float* __restrict__ d, const float* __
 
 // MaxPool (3,2)/2 "same" (-inf beyond the image) of s2 (n, H, W, COP)  +  Conv1x1/2 of the block input  ->  y (n, Ho, Wo, COP).
 // The block input at even positions is addressed as xs + b * xs_img + ho * xs_row + wo * xs_px (floats): its own sub-sampled
-// tensor, or the full tensor walked with stride 2.  rw: [CIP][COP] (zero padded), rb: [COP].  One thread per (pixel, 4 channels).
+// tensor, or the full tensor walked with stride 2.  rw: [CIP][COP] (zero padded), rb: [COP].  One thread per (kPoolPx consecutive
+// pooled pixels of a row, 4 channels): every residual weight read from shared memory serves kPoolPx pixels (with one pixel per
+// thread the kernel was bound by those reads: 32 LDS.128 for 128 FMAs).
+constexpr int kPoolPx = 4;
 __global__ void __launch_bounds__(256)
 pool_res_f32_kernel(const float* __restrict__ s2, const float* __restrict__ xs, long long xs_img, long long xs_row, int xs_px,
                     float* __restrict__ y, long long n, int H, int W, int Ho, int Wo, int CIP, int COP,
@@ -63,41 +66,58 @@ pool_res_f32_kernel(const float* __restrict__ s2, const float* __restrict__ xs, 
   for (int i = threadIdx.x; i < COP; i += blockDim.x) s_w[CIP * COP + i] = rb[i];
   __syncthreads();
   const int G4 = COP >> 2;
-  const long long total = n * Ho * Wo * G4;
+  const int WB = (Wo + kPoolPx - 1) / kPoolPx;            // pixel groups per pooled row
+  const long long total = n * Ho * WB * G4;
   for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
     const int g = (int)(idx % G4);
     long long r = idx / G4;
-    const int wo = (int)(r % Wo); r /= Wo;
+    const int wb = (int)(r % WB); r /= WB;
     const int ho = (int)(r % Ho);
     const long long b = r / Ho;
     const float* sb = s2 + (size_t)b * H * W * COP + 4 * g;
-    float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    const float4 bias = *reinterpret_cast<const float4*>(s_w + CIP * COP + 4 * g);
+    float4 m[kPoolPx], a[kPoolPx];
+    const float* xp[kPoolPx];
 #pragma unroll
-    for (int dy = 0; dy < 3; ++dy) {
-      const int hh = 2 * ho + dy;
-      if (hh >= H) continue;
+    for (int p = 0; p < kPoolPx; ++p) {
+      const int wo = wb * kPoolPx + p;
+      m[p] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      a[p] = bias;
+      xp[p] = xs + (size_t)b * xs_img + (size_t)ho * xs_row + (size_t)(wo < Wo ? wo : Wo - 1) * xs_px;
 #pragma unroll
-      for (int dx = 0; dx < 2; ++dx) {
-        const int ww = 2 * wo + dx;
-        if (ww >= W) continue;
-        const float4 v = __ldg(reinterpret_cast<const float4*>(sb + ((size_t)hh * W + ww) * COP));
-        m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+      for (int dy = 0; dy < 3; ++dy) {
+        const int hh = 2 * ho + dy;
+        if (hh >= H) continue;
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          const int ww = 2 * wo + dx;
+          if (ww >= W) continue;
+          const float4 v = __ldg(reinterpret_cast<const float4*>(sb + ((size_t)hh * W + ww) * COP));
+          m[p].x = fmaxf(m[p].x, v.x); m[p].y = fmaxf(m[p].y, v.y); m[p].z = fmaxf(m[p].z, v.z); m[p].w = fmaxf(m[p].w, v.w);
+        }
       }
     }
-    const float* xp = xs + (size_t)b * xs_img + (size_t)ho * xs_row + (size_t)wo * xs_px;
-    float4 a = *reinterpret_cast<const float4*>(s_w + CIP * COP + 4 * g);
     for (int ci = 0; ci < CIP; ci += 4) {
-      const float4 xv = __ldg(reinterpret_cast<const float4*>(xp + ci));
       const float4 w0 = *reinterpret_cast<const float4*>(s_w + (ci + 0) * COP + 4 * g);
       const float4 w1 = *reinterpret_cast<const float4*>(s_w + (ci + 1) * COP + 4 * g);
       const float4 w2 = *reinterpret_cast<const float4*>(s_w + (ci + 2) * COP + 4 * g);
       const float4 w3 = *reinterpret_cast<const float4*>(s_w + (ci + 3) * COP + 4 * g);
-      a.x = fmaf(xv.x, w0.x, a.x); a.y = fmaf(xv.x, w0.y, a.y); a.z = fmaf(xv.x, w0.z, a.z); a.w = fmaf(xv.x, w0.w, a.w);
-      a.x = fmaf(xv.y, w1.x, a.x); a.y = fmaf(xv.y, w1.y, a.y); a.z = fmaf(xv.y, w1.z, a.z); a.w = fmaf(xv.y, w1.w, a.w);
-      a.x = fmaf(xv.z, w2.x, a.x); a.y = fmaf(xv.z, w2.y, a.y); a.z = fmaf(xv.z, w2.z, a.z); a.w = fmaf(xv.z, w2.w, a.w);
-      a.x = fmaf(xv.w, w3.x, a.x); a.y = fmaf(xv.w, w3.y, a.y); a.z = fmaf(xv.w, w3.z, a.z); a.w = fmaf(xv.w, w3.w, a.w);
+#pragma unroll
+      for (int p = 0; p < kPoolPx; ++p) {
+        const float4 xv = __ldg(reinterpret_cast<const float4*>(xp[p] + ci));
+        // per output channel the same FMA order as with one pixel per thread: ci ascending
+        a[p].x = fmaf(xv.x, w0.x, a[p].x); a[p].y = fmaf(xv.x, w0.y, a[p].y); a[p].z = fmaf(xv.x, w0.z, a[p].z); a[p].w = fmaf(xv.x, w0.w, a[p].w);
+        a[p].x = fmaf(xv.y, w1.x, a[p].x); a[p].y = fmaf(xv.y, w1.y, a[p].y); a[p].z = fmaf(xv.y, w1.z, a[p].z); a[p].w = fmaf(xv.y, w1.w, a[p].w);
+        a[p].x = fmaf(xv.z, w2.x, a[p].x); a[p].y = fmaf(xv.z, w2.y, a[p].y); a[p].z = fmaf(xv.z, w2.z, a[p].z); a[p].w = fmaf(xv.z, w2.w, a[p].w);
+        a[p].x = fmaf(xv.w, w3.x, a[p].x); a[p].y = fmaf(xv.w, w3.y, a[p].y); a[p].z = fmaf(xv.w, w3.z, a[p].z); a[p].w = fmaf(xv.w, w3.w, a[p].w);
+      }
     }
-    *reinterpret_cast<float4*>(y + (size_t)idx * 4) = make_float4(m.x + a.x, m.y + a.y, m.z + a.z, m.w + a.w);
+#pragma unroll
+    for (int p = 0; p < kPoolPx; ++p) {
+      const int wo = wb * kPoolPx + p;
+      if (wo < Wo)
+        *reinterpret_cast<float4*>(y + ((((size_t)b * Ho + ho) * Wo + wo) * COP + 4 * g)) = make_float4(m[p].x + a[p].x, m[p].y + a[p].y, m[p].z + a[p].z, m[p].w + a[p].w);
+    }
   }
 }
 
@@ -430,7 +450,7 @@ int run_precise_block(Ctx* c, int blk, const float* x, float* ta, float* tb, flo
   ORCAI_CHECK(run_precise_sep(c, tb, ta, tc, n, h, w, cop, cop, cop, false, false, nw->p_sep2[blk]));
   const long long ho = h / 2;
   const int wo = (w + 1) / 2;
-  const long long total = n * ho * wo * (cop / 4);
+  const long long total = n * ho * ((wo + precise::kPoolPx - 1) / precise::kPoolPx) * (cop / 4);
   if (total <= 0) return ORCAI_OK;
   const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, (long long)c->sm_count * 16);
   const size_t smem = ((size_t)cip * cop + cop) * sizeof(float);
