@@ -179,24 +179,27 @@ assemble_feat_kernel(const float* __restrict__ tall, const float* __restrict__ b
 // Two CTAs per SM overlap each other's phases.  x: (n, H, W, CP), out: (n, H, W, ldc); CP <= 64, ldc <= 64.
 constexpr int kUfTH = 16, kUfTW = 8, kUfHalo = (kUfTH + 2) * (kUfTW + 2);
 constexpr uint32_t kUfLboA = 128 * 16 + 16;                           // A plane pitch (one 8-channel chunk of 128 rows) + pad
+// shared memory sized by the channel count: 56 KB at 32 channels (the register file then allows three CTAs per SM), 95 KB at 64
 struct UfSmem {
-  static constexpr uint32_t OFF_HALO = 0;                              // [18][10][CP] fp32, up to 46 080 B
-  static constexpr uint32_t OFF_A = 46080;                             // 8 hi planes, 8 lo planes
-  static constexpr uint32_t A_HALF = 8 * kUfLboA;
-  static constexpr uint32_t OFF_B = OFF_A + 2 * A_HALF;                // [hi | lo] 64 x 64 fp16 blocks
-  static constexpr uint32_t B_HALF = 64 * 64 * 2;
-  static constexpr uint32_t OFF_BAR = OFF_B + 2 * B_HALF;              // halo_full, halo_free, a_full, acc_full, acc_free, b_full
-  static constexpr uint32_t BYTES = OFF_BAR + 6 * 8 + 16;
+  static constexpr uint32_t B_HALF = 64 * 64 * 2;                      // [hi | lo] 64 x 64 fp16 blocks
+  uint32_t off_a, a_half, off_b, off_bar, bytes;                       // halo [18][10][CP] fp32 at 0; hi planes, lo planes; B; barriers
+  __host__ __device__ explicit UfSmem(int cp) {
+    const uint32_t planes = 2u * (uint32_t)((cp + 15) / 16);           // 8-channel planes the MMAs read (K steps of 16)
+    off_a = (uint32_t)kUfHalo * cp * 4;                                // multiple of 128 (cp is a multiple of 8)
+    a_half = planes * kUfLboA;
+    off_b = (off_a + 2 * a_half + 127) & ~127u;
+    off_bar = off_b + 2 * B_HALF;                                      // halo_full, halo_free, a_full, acc_full, acc_free, b_full
+    bytes = off_bar + 6 * 8 + 16;
+  }
 };
-static_assert(UfSmem::BYTES * 2 + 2048 <= 227 * 1024, "two CTAs per SM");
 
 template <bool RELU_IN, int ACT>
-__global__ void __launch_bounds__(160, 2)
+__global__ void __launch_bounds__(160, 3)
 sep_uf_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__ dw, const __half* __restrict__ Bp, const float* __restrict__ bias,
               float* __restrict__ out, long long n_img, int H, int W, int CP, int ldc, int n_valid, int tiles_w, int tiles_h) {
-  using S = UfSmem;
+  const UfSmem L(CP);
   extern __shared__ __align__(128) unsigned char smem[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::OFF_BAR);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.off_bar);
   uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 6);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int Q = CP >> 2;
@@ -209,7 +212,7 @@ sep_uf_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__
     mbar_init(&bars[5], 1);      // b_full
     fence_mbar_init();
   }
-  for (int i = tid; i < (int)(2 * S::A_HALF / 16); i += 160) reinterpret_cast<uint4*>(smem + S::OFF_A)[i] = make_uint4(0, 0, 0, 0);   // unused K planes stay zero
+  for (int i = tid; i < (int)(2 * L.a_half / 16); i += 160) reinterpret_cast<uint4*>(smem + L.off_a)[i] = make_uint4(0, 0, 0, 0);   // unused K planes stay zero
   __syncwarp();
   if (warp == 0) tmem_alloc<64>(tslot);
   fence_proxy_async();
@@ -225,15 +228,15 @@ sep_uf_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__
   if (warp == 4) {
     // =============================== issuer: TMA + MMA ===============================
     if (fused::elect_one()) {
-      fused::mbar_arrive_expect_tx(&bars[5], 2 * S::B_HALF);
-      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sbase + S::OFF_B), "l"(Bp),
-                   "r"(2 * S::B_HALF), "r"(smem_u32(&bars[5]))
+      fused::mbar_arrive_expect_tx(&bars[5], 2 * UfSmem::B_HALF);
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sbase + L.off_b), "l"(Bp),
+                   "r"(2 * UfSmem::B_HALF), "r"(smem_u32(&bars[5]))
                    : "memory");
     }
     __syncwarp();
     constexpr uint32_t idesc = make_idesc_f16(128, 64, 0);
-    const uint64_t da = make_smem_desc(sbase + S::OFF_A, kUfLboA, 128);
-    const uint64_t db = make_smem_desc(sbase + S::OFF_B, 128, 8 * 128);
+    const uint64_t da = make_smem_desc(sbase + L.off_a, kUfLboA, 128);
+    const uint64_t db = make_smem_desc(sbase + L.off_b, 128, 8 * 128);
     const int ksteps = (CP + 15) >> 4;
     long long it = 0;
     for (long long tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
@@ -243,7 +246,7 @@ sep_uf_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__
       if (it > 0) mbar_wait(&bars[1], (uint32_t)((it - 1) & 1));          // the workers have read the previous halo
       if (fused::elect_one()) {
         fused::mbar_arrive_expect_tx(&bars[0], halo_bytes);
-        fused::tma_load_4d(sbase + S::OFF_HALO, &tmX, &bars[0], 0, w0 - 1, h0 - 1, (int)b);
+        fused::tma_load_4d(sbase, &tmX, &bars[0], 0, w0 - 1, h0 - 1, (int)b);
       }
       __syncwarp();
       if (it == 0) mbar_wait(&bars[5], 0);
@@ -254,8 +257,8 @@ sep_uf_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__
         for (int ks = 0; ks < ksteps; ++ks) {
           const uint64_t a = da + ((2 * ks * kUfLboA) >> 4), bb = db + ((2 * ks * 128) >> 4);
           mma_f16_ss(tmem, a, bb, idesc, ks != 0);
-          mma_f16_ss(tmem, a + (S::A_HALF >> 4), bb, idesc, 1);
-          mma_f16_ss(tmem, a, bb + (S::B_HALF >> 4), idesc, 1);
+          mma_f16_ss(tmem, a + (L.a_half >> 4), bb, idesc, 1);
+          mma_f16_ss(tmem, a, bb + (UfSmem::B_HALF >> 4), idesc, 1);
         }
         mma_commit(&bars[3]);
       }
@@ -271,7 +274,7 @@ sep_uf_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__
     float4 k[9];
 #pragma unroll
     for (int t = 0; t < 9; ++t) k[t] = active ? __ldg(reinterpret_cast<const float4*>(dw + t * CP + 4 * quad)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4* halo = reinterpret_cast<const float4*>(smem + S::OFF_HALO);
+    const float4* halo = reinterpret_cast<const float4*>(smem);
     const int hrow = (kUfTW + 2) * Q;                                       // float4 per halo row
     auto ld = [&](int y, int x) {
       float4 v = halo[y * hrow + x * Q + quad];
@@ -306,12 +309,12 @@ sep_uf_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__
           const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
           const __half2 l01 = __floats2half2_rn(acc.x - f01.x, acc.y - f01.y), l23 = __floats2half2_rn(acc.z - f23.x, acc.w - f23.y);
           const int prow = (r0 + r) * kUfTW + col;
-          unsigned char* dst = smem + S::OFF_A + (quad >> 1) * kUfLboA + prow * 16 + (quad & 1) * 8;
+          unsigned char* dst = smem + L.off_a + (quad >> 1) * kUfLboA + prow * 16 + (quad & 1) * 8;
           uint2 hv, lv;
           hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
           lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
           *reinterpret_cast<uint2*>(dst) = hv;
-          *reinterpret_cast<uint2*>(dst + S::A_HALF) = lv;
+          *reinterpret_cast<uint2*>(dst + L.a_half) = lv;
         }
       }
       fence_proxy_async();
@@ -407,15 +410,17 @@ template <bool RELU_IN, int ACT>
 int launch_sep_uf(Ctx* c, const float* x, float* out, long long n, long long h, int w, int cip, int ldc, int n_valid, const NetWeights::PreciseSep& ps) {
   static std::atomic<unsigned long long> attr_devices{0ull};
   if (!((attr_devices.load() >> (c->device & 63)) & 1ull)) {
-    ORCAI_CUDA(c, cudaFuncSetAttribute(precise::sep_uf_kernel<RELU_IN, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)precise::UfSmem::BYTES));
+    ORCAI_CUDA(c, cudaFuncSetAttribute(precise::sep_uf_kernel<RELU_IN, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)precise::UfSmem(64).bytes));
     attr_devices.fetch_or(1ull << (c->device & 63));
   }
+  const precise::UfSmem L(cip);
+  const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(3, (size_t)(225 * 1024) / (L.bytes + 1024)));
   CUtensorMap tm;
   ORCAI_CHECK(make_uf_map(c, &tm, x, n, h, w, cip));
   const int tiles_w = (w + precise::kUfTW - 1) / precise::kUfTW, tiles_h = (int)((h + precise::kUfTH - 1) / precise::kUfTH);
   const long long total = n * tiles_w * tiles_h;
-  const unsigned grid = (unsigned)std::min<long long>(total, (long long)c->sm_count * 2);
-  precise::sep_uf_kernel<RELU_IN, ACT><<<grid, 160, precise::UfSmem::BYTES, c->stream>>>(tm, ps.dw, ps.pw, ps.bias, out, n, (int)h, w, cip, ldc, n_valid, tiles_w,
+  const unsigned grid = (unsigned)std::min<long long>(total, (long long)c->sm_count * per_sm);
+  precise::sep_uf_kernel<RELU_IN, ACT><<<grid, 160, L.bytes, c->stream>>>(tm, ps.dw, ps.pw, ps.bias, out, n, (int)h, w, cip, ldc, n_valid, tiles_w,
                                                                                         tiles_h);
   c->launches++;
   ORCAI_CUDA(c, cudaGetLastError());
