@@ -808,12 +808,21 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
           if (warp == 0) FB_TRACE(21, g);
           worker_sync<G::NWORK>();   // pooling has finished reading S2
           if (prev_carry) {
-            for (int i = tid; i < G::PL * G::NG * G::WP; i += G::NWORK) {   // the lo plane set follows the hi set
+            // all loads of a thread first, then its stores (one shared-memory round trip instead of one per element)
+            constexpr int kN2 = G::PL * G::NG * G::WP, kIt2 = (kN2 + G::NWORK - 1) / G::NWORK;
+            unsigned char* cp2[kIt2];
+            uint4 cv2[kIt2];
+#pragma unroll
+            for (int it = 0; it < kIt2; ++it) {
+              const int i = tid + it * G::NWORK;                             // the lo plane set follows the hi set
               const int gq = i / G::WP, px = i - gq * G::WP;
               const int hp = px / (G::WP / 2), cc = px - hp * (G::WP / 2);   // half-plane (column parity), column / 2
-              unsigned char* p = smem + G::OFF_S2 + gq * G::LBO_S2 + (hp * G::S2HALF + cc) * 16;
-              *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(p + G::S * (G::WP / 2) * 16);
+              cp2[it] = smem + G::OFF_S2 + gq * G::LBO_S2 + (hp * G::S2HALF + cc) * 16;
+              if (i < kN2) cv2[it] = *reinterpret_cast<const uint4*>(cp2[it] + G::S * (G::WP / 2) * 16);
             }
+#pragma unroll
+            for (int it = 0; it < kIt2; ++it)
+              if (tid + it * G::NWORK < kN2) *reinterpret_cast<uint4*>(cp2[it]) = cv2[it];
             worker_sync<G::NWORK>();  // carried S2 row in place before epilogue 2 overwrites its source row
           }
         }
@@ -860,12 +869,20 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         const bool carry = step + 1 < n_steps;
         if (g + 1 < total_steps) {
           constexpr int kCarryPlanes = G::UF2 ? G::NQ : G::PL * G::NG;
-          for (int i = tid; i < kCarryPlanes * 2 * G::WP; i += G::NWORK) {
+          constexpr int kN1 = kCarryPlanes * 2 * G::WP, kIt1 = (kN1 + G::NWORK - 1) / G::NWORK;
+          unsigned char* cp1[kIt1];
+          uint4 cv1[kIt1];
+#pragma unroll
+          for (int it = 0; it < kIt1; ++it) {
+            const int i = tid + it * G::NWORK;
             const int gs = i / (2 * G::WP), px = i - gs * 2 * G::WP;
             const int gq = G::UF2 ? gs : gs % G::NG + (gs / G::NG) * G::MCH;   // lo planes sit MCH planes after the hi planes
-            unsigned char* p = smem + G::OFF_S1 + gq * G::LBO_S1 + px * 16;
-            *reinterpret_cast<uint4*>(p) = carry ? *reinterpret_cast<const uint4*>(p + G::S * G::WP * 16) : make_uint4(0, 0, 0, 0);
+            cp1[it] = smem + G::OFF_S1 + gq * G::LBO_S1 + px * 16;
+            cv1[it] = (carry && i < kN1) ? *reinterpret_cast<const uint4*>(cp1[it] + G::S * G::WP * 16) : make_uint4(0, 0, 0, 0);
           }
+#pragma unroll
+          for (int it = 0; it < kIt1; ++it)
+            if (tid + it * G::NWORK < kN1) *reinterpret_cast<uint4*>(cp1[it]) = cv1[it];
           worker_sync<G::NWORK>();   // carried rows in place before epilogue 1 overwrites their source rows
         }
         if (warp == 0) FB_TRACE(41, g);
