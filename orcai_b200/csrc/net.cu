@@ -283,7 +283,7 @@ template <int U>
 __global__ void __launch_bounds__(4 * U)
 lstm_rec_kernel(const float* __restrict__ xz, const float* __restrict__ whh, float* __restrict__ out, long long n, int Tn) {
   constexpr int G = 4 * U;
-  __shared__ float s_h[kSN][U];
+  __shared__ __align__(16) float s_h[kSN][U];
   __shared__ float s_z[kSN][G];
   const int dir = blockIdx.y;
   const long long b0 = (long long)blockIdx.x * kSN;
@@ -302,11 +302,20 @@ lstm_rec_kernel(const float* __restrict__ xz, const float* __restrict__ whh, flo
       const long long b = b0 + s;
       acc[s] = (b < n) ? xz[((size_t)b * Tn + t) * (2 * G) + (size_t)dir * G + g] : 0.f;
     }
-#pragma unroll 8
-    for (int j = 0; j < U; ++j) {
-      const float wv = __ldg(w + (size_t)j * G + g);
+    // four hidden units per iteration: one broadcast LDS.128 of h serves four FMAs (the scalar form issued one shared-memory
+    // load per FMA and was bound by the load/store unit); per accumulator the additions stay in ascending j order
+#pragma unroll 2
+    for (int j = 0; j < U; j += 4) {
+      const float w0 = __ldg(w + (size_t)(j + 0) * G + g), w1 = __ldg(w + (size_t)(j + 1) * G + g);
+      const float w2 = __ldg(w + (size_t)(j + 2) * G + g), w3 = __ldg(w + (size_t)(j + 3) * G + g);
 #pragma unroll
-      for (int s = 0; s < kSN; ++s) acc[s] = fmaf(s_h[s][j], wv, acc[s]);
+      for (int s = 0; s < kSN; ++s) {
+        const float4 h4 = *reinterpret_cast<const float4*>(&s_h[s][j]);
+        acc[s] = fmaf(h4.x, w0, acc[s]);
+        acc[s] = fmaf(h4.y, w1, acc[s]);
+        acc[s] = fmaf(h4.z, w2, acc[s]);
+        acc[s] = fmaf(h4.w, w3, acc[s]);
+      }
     }
 #pragma unroll
     for (int s = 0; s < kSN; ++s) s_z[s][g] = acc[s];
