@@ -214,7 +214,7 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--hours", type=float, default=1.0, help="length of the synthetic recording each GPU annotates per step")
-    ap.add_argument("--rows-per-gpu", type=int, default=16, help="e2e arm: recordings per GPU in the table one step annotates")
+    ap.add_argument("--rows-per-gpu", type=int, default=32, help="e2e arm: recordings per GPU in the table one step annotates")
     ap.add_argument("--cpu-sample-seconds", type=float, default=600.0, help="bounded CPU-oracle sample (BASELINE config 0: one 10-min recording)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip BASELINE configs 1, 2, 4 (create-spectrograms, 24-h recording, batch sweep)")
