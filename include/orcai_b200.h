@@ -169,17 +169,22 @@ int orcai_calibrate(orcai_ctx* ctx, int64_t max_snippets);
  *   orcai_chunk_histogram    pass 0/1/2 of the exact radix select over rows [row0, row1): hist_out[2][2048] counts of the
  *                            11/11/10-bit digit, restricted to keys that start with prefix[r] (pass 0: one histogram)
  *   orcai_chunk_select_end   the decided 32-bit keys -> lo / hi; the chunk is then ready for orcai_forward_resident
- * Results are bit-identical to the one-context path (tests/test_gpu_timesplit.py). */
+ * Results are bit-identical to the one-context path (tests/test_timesplit.py). */
 int orcai_chunk_spectrogram(orcai_ctx* ctx, int64_t stat_row0, int64_t stat_row1, float* max_power_out);
 int orcai_chunk_select_begin(orcai_ctx* ctx, float max_power);
 int orcai_chunk_histogram(orcai_ctx* ctx, int32_t pass, int64_t row0, int64_t row1, const uint32_t* prefix, uint64_t* hist_out);
 int orcai_chunk_select_end(orcai_ctx* ctx, const uint32_t* keys, orcai_spec_stats* stats);
 
 /* ---- knobs ---------------------------------------------------------------------------------- */
-/* Options: "net_path"  0 = fp32 CUDA-core path (reference grade, library default), 1 = fp16 / 2 = bf16 layer-wise tcgen05
- *                      path, 3 = fp16 fused tcgen05 path (what orcai_b200's Python layer selects unless
- *                      ORCAI_B200_PRECISION=reference): tensor-core entry convolution, fused residual-block kernels,
- *                      tensor-core LSTM tail; fp32 accumulation everywhere;
+/* Options: "net_path"  4 = split-fp16 tcgen05 path at fp32 grade (what orcai_b200's Python layer selects by default): every
+ *                      GEMM as A_hi*W_hi + A_lo*W_hi + A_hi*W_lo with fp32 accumulation, fp32 CUDA cores elsewhere, within
+ *                      2e-5 of the fp32 graph (model.predict of predict.py:266-268 is compared at 1e-3);
+ *                      0 = fp32 CUDA-core path (the in-library yardstick, library default of a fresh context),
+ *                      1 = fp16 / 2 = bf16 layer-wise tcgen05 path, 3 = single-fp16 fused tcgen05 path (opt-in, outside the
+ *                      1e-3 gate): tensor-core entry convolution, fused residual-block kernels, tensor-core LSTM tail;
+ *          "precise_tall" (net_path 4, resident recordings) 1 = trunk once over the recording as a tall image + per-snippet
+ *          border rows (default; bit-identical to 0 = snippet by snippet); "precise_sep_path" (net_path 4) 1 = depthwise filter
+ *          fused into the split pointwise GEMM (default), 0 = two kernels (bit-identical);
  *          "tail_path" (net_path 3) 1 = tensor-core LSTM/dense tail (default), 0 = fp32 CUDA-core tail;
  *          "conv0_path" (net_path 3) 1 = tensor-core entry convolution (default), 0 = fp32 CUDA-core entry convolution,
  *          2 = entry convolution fused into the first residual block's kernel (measured slower, kept as an option);
