@@ -188,8 +188,8 @@ struct UfSmem {
     off_a = (uint32_t)kUfHalo * cp * 4;                                // multiple of 128 (cp is a multiple of 8)
     a_half = planes * kUfLboA;
     off_b = (off_a + 2 * a_half + 127) & ~127u;
-    off_bar = off_b + 2 * B_HALF;                                      // halo_full, halo_free, a_full, acc_full, acc_free, b_full
-    bytes = off_bar + 6 * 8 + 16;
+    off_bar = off_b + 2 * B_HALF;                                      // halo_full, halo_free, a_full, acc_full, acc_free, b_full; then 64 bias floats
+    bytes = off_bar + 64 + 64 * 4;
   }
 };
 
@@ -201,8 +201,10 @@ sep_uf_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.off_bar);
   uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 6);
+  float* s_bias = reinterpret_cast<float*>(smem + L.off_bar + 64);     // the epilogue's bias reads stay off the global-memory path
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int Q = CP >> 2;
+  if (tid < 64) s_bias[tid] = __ldg(bias + tid);
   if (tid == 0) {
     mbar_init(&bars[0], 1);      // halo_full: TMA complete_tx
     mbar_init(&bars[1], 4);      // halo_free: one arrival per worker warp
@@ -333,7 +335,7 @@ sep_uf_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__
         tmem_ld16(lane_addr + c0, v);
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          v[i] += __ldg(bias + c0 + i);
+          v[i] += s_bias[c0 + i];
           if (ACT == 1) v[i] = fmaxf(v[i], 0.f);
         }
         if (inside) {
