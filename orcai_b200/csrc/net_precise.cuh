@@ -182,36 +182,41 @@ constexpr uint32_t kUfLboA = 128 * 16 + 16;                           // A plane
 // shared memory sized by the channel count: 56 KB at 32 channels (the register file then allows three CTAs per SM), 95 KB at 64
 struct UfSmem {
   static constexpr uint32_t B_HALF = 64 * 64 * 2;                      // [hi | lo] 64 x 64 fp16 blocks
-  uint32_t off_a, a_half, off_b, off_bar, bytes;                       // halo [18][10][CP] fp32 at 0; hi planes, lo planes; B; barriers
-  __host__ __device__ explicit UfSmem(int cp) {
+  uint32_t halo_bytes, off_a, a_half, off_b, off_bar, bytes;           // halo(s) [18][10][CP] fp32 at 0; hi planes, lo planes; B; barriers
+  __host__ __device__ UfSmem(int cp, int n_halo) {
     const uint32_t planes = 2u * (uint32_t)((cp + 15) / 16);           // 8-channel planes the MMAs read (K steps of 16)
-    off_a = (uint32_t)kUfHalo * cp * 4;                                // multiple of 128 (cp is a multiple of 8)
+    halo_bytes = ((uint32_t)kUfHalo * cp * 4 + 127) & ~127u;
+    off_a = halo_bytes * (uint32_t)n_halo;
     a_half = planes * kUfLboA;
     off_b = (off_a + 2 * a_half + 127) & ~127u;
-    off_bar = off_b + 2 * B_HALF;                                      // halo_full, halo_free, a_full, acc_full, acc_free, b_full; then 64 bias floats
-    bytes = off_bar + 64 + 64 * 4;
+    off_bar = off_b + 2 * B_HALF;                                      // halo_full[2], halo_free[2], a_full, acc_full, acc_free, b_full; then 64 bias floats
+    bytes = off_bar + 128 + 64 * 4;
   }
 };
 
 template <bool RELU_IN, int ACT>
 __global__ void __launch_bounds__(160, 3)   // four CTAs per SM (96 registers, spills) measured 9 % slower
 sep_uf_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__ dw, const __half* __restrict__ Bp, const float* __restrict__ bias,
-              float* __restrict__ out, long long n_img, int H, int W, int CP, int ldc, int n_valid, int tiles_w, int tiles_h) {
-  const UfSmem L(CP);
+              float* __restrict__ out, long long n_img, int H, int W, int CP, int ldc, int n_valid, int tiles_w, int tiles_h, int n_halo) {
+  // n_halo = 2: the halo of tile i+1 is in flight while tile i is being filtered (the shared memory of <= 40 channels allows it at
+  // two CTAs per SM); 1: it is fetched once the workers have read the current one
+  const UfSmem L(CP, n_halo);
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.off_bar);
-  uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 6);
-  float* s_bias = reinterpret_cast<float*>(smem + L.off_bar + 64);     // the epilogue's bias reads stay off the global-memory path
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 8);
+  float* s_bias = reinterpret_cast<float*>(smem + L.off_bar + 128);     // the epilogue's bias reads stay off the global-memory path
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int Q = CP >> 2;
   if (tid < 64) s_bias[tid] = __ldg(bias + tid);
   if (tid == 0) {
-    mbar_init(&bars[0], 1);      // halo_full: TMA complete_tx
-    mbar_init(&bars[1], 4);      // halo_free: one arrival per worker warp
+    mbar_init(&bars[0], 1);      // halo_full[0]: TMA complete_tx
+    mbar_init(&bars[1], 4);      // halo_free[0]: one arrival per worker warp
     mbar_init(&bars[2], 4);      // a_full
     mbar_init(&bars[3], 1);      // acc_full: tcgen05.commit
     mbar_init(&bars[4], 4);      // acc_free
     mbar_init(&bars[5], 1);      // b_full
+    mbar_init(&bars[6], 1);      // halo_full[1]
+    mbar_init(&bars[7], 4);      // halo_free[1]
     fence_mbar_init();
   }
   for (int i = tid; i < (int)(2 * L.a_half / 16); i += 160) reinterpret_cast<uint4*>(smem + L.off_a)[i] = make_uint4(0, 0, 0, 0);   // unused K planes stay zero
@@ -240,17 +245,31 @@ sep_uf_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__
     const uint64_t da = make_smem_desc(sbase + L.off_a, kUfLboA, 128);
     const uint64_t db = make_smem_desc(sbase + L.off_b, 128, 8 * 128);
     const int ksteps = (CP + 15) >> 4;
-    long long it = 0;
-    for (long long tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
-      const long long b = tile / tiles_per;
-      const int tr = (int)(tile - b * tiles_per);
-      const int h0 = (tr / tiles_w) * kUfTH, w0 = (tr % tiles_w) * kUfTW;
-      if (it > 0) mbar_wait(&bars[1], (uint32_t)((it - 1) & 1));          // the workers have read the previous halo
+    auto halo_full = [&](long long i) { return &bars[(n_halo == 2 && (i & 1)) ? 6 : 0]; };
+    auto halo_free = [&](long long i) { return &bars[(n_halo == 2 && (i & 1)) ? 7 : 1]; };
+    auto load_halo = [&](long long i, long long tl) {      // tile tl = this CTA's i-th tile
+      const long long b2 = tl / tiles_per;
+      const int tr2 = (int)(tl - b2 * tiles_per);
       if (fused::elect_one()) {
-        fused::mbar_arrive_expect_tx(&bars[0], halo_bytes);
-        fused::tma_load_4d(sbase, &tmX, &bars[0], 0, w0 - 1, h0 - 1, (int)b);
+        fused::mbar_arrive_expect_tx(halo_full(i), (uint32_t)kUfHalo * CP * 4);
+        fused::tma_load_4d(sbase + (n_halo == 2 ? (uint32_t)(i & 1) * L.halo_bytes : 0u), &tmX, halo_full(i), 0, (tr2 % tiles_w) * kUfTW - 1,
+                           (tr2 / tiles_w) * kUfTH - 1, (int)b2);
       }
       __syncwarp();
+    };
+    long long it = 0;
+    if (n_halo == 2 && blockIdx.x < total) load_halo(0, blockIdx.x);
+    for (long long tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+      if (n_halo == 2) {
+        // the next tile's halo goes into the other buffer as soon as the workers have read the tile that used it (tile it - 1)
+        if (tile + gridDim.x < total) {
+          if (it >= 1) mbar_wait(halo_free(it + 1), (uint32_t)(((it - 1) >> 1) & 1));
+          load_halo(it + 1, tile + gridDim.x);
+        }
+      } else {
+        if (it > 0) mbar_wait(&bars[1], (uint32_t)((it - 1) & 1));          // the workers have read the previous halo
+        load_halo(it, tile);
+      }
       if (it == 0) mbar_wait(&bars[5], 0);
       mbar_wait(&bars[2], (uint32_t)(it & 1));                             // A planes of this tile written
       if (it > 0) mbar_wait(&bars[4], (uint32_t)((it - 1) & 1));          // accumulator drained
@@ -276,7 +295,7 @@ sep_uf_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__
     float4 k[9];
 #pragma unroll
     for (int t = 0; t < 9; ++t) k[t] = active ? __ldg(reinterpret_cast<const float4*>(dw + t * CP + 4 * quad)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4* halo = reinterpret_cast<const float4*>(smem);
+    const float4* halo = reinterpret_cast<const float4*>(smem);   // re-pointed per tile
     const int hrow = (kUfTW + 2) * Q;                                       // float4 per halo row
     auto ld = [&](int y, int x) {
       float4 v = halo[y * hrow + x * Q + quad];
@@ -289,7 +308,9 @@ sep_uf_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__
       const long long b = tile / tiles_per;
       const int tr = (int)(tile - b * tiles_per);
       const int h0 = (tr / tiles_w) * kUfTH, w0 = (tr % tiles_w) * kUfTW;
-      mbar_wait(&bars[0], (uint32_t)(it & 1));
+      const int hb = n_halo == 2 ? (int)(it & 1) : 0;                      // halo buffer of this tile
+      halo = reinterpret_cast<const float4*>(smem + hb * L.halo_bytes);
+      mbar_wait(&bars[hb ? 6 : 0], (uint32_t)((n_halo == 2 ? (it >> 1) : it) & 1));
       if (it > 0) mbar_wait(&bars[3], (uint32_t)((it - 1) & 1));          // the MMAs that read the A planes are done ...
       // (... and this thread's epilogue of the previous tile below has run: program order)
       if (active) {
@@ -321,7 +342,7 @@ sep_uf_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__
       }
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) { fused::mbar_arrive(&bars[1]); fused::mbar_arrive(&bars[2]); }
+      if (lane == 0) { fused::mbar_arrive(&bars[hb ? 7 : 1]); fused::mbar_arrive(&bars[2]); }
       // ---- epilogue: accumulator row tid = pixel (tid / 8, tid % 8) ----
       mbar_wait(&bars[3], (uint32_t)(it & 1));
       tc_fence_after();
@@ -412,10 +433,11 @@ template <bool RELU_IN, int ACT>
 int launch_sep_uf(Ctx* c, const float* x, float* out, long long n, long long h, int w, int cip, int ldc, int n_valid, const NetWeights::PreciseSep& ps) {
   static std::atomic<unsigned long long> attr_devices{0ull};
   if (!((attr_devices.load() >> (c->device & 63)) & 1ull)) {
-    ORCAI_CUDA(c, cudaFuncSetAttribute(precise::sep_uf_kernel<RELU_IN, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)precise::UfSmem(64).bytes));
+    ORCAI_CUDA(c, cudaFuncSetAttribute(precise::sep_uf_kernel<RELU_IN, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)precise::UfSmem(64, 1).bytes));
     attr_devices.fetch_or(1ull << (c->device & 63));
   }
-  const precise::UfSmem L(cip);
+  const int n_halo = (c->net->precise_halo2 && cip <= 40) ? 2 : 1;
+  const precise::UfSmem L(cip, n_halo);
   const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(3, (size_t)(225 * 1024) / (L.bytes + 1024)));
   CUtensorMap tm;
   ORCAI_CHECK(make_uf_map(c, &tm, x, n, h, w, cip));
@@ -423,7 +445,7 @@ int launch_sep_uf(Ctx* c, const float* x, float* out, long long n, long long h, 
   const long long total = n * tiles_w * tiles_h;
   const unsigned grid = (unsigned)std::min<long long>(total, (long long)c->sm_count * per_sm);
   precise::sep_uf_kernel<RELU_IN, ACT><<<grid, 160, L.bytes, c->stream>>>(tm, ps.dw, ps.pw, ps.bias, out, n, (int)h, w, cip, ldc, n_valid, tiles_w,
-                                                                                        tiles_h);
+                                                                                        tiles_h, n_halo);
   c->launches++;
   ORCAI_CUDA(c, cudaGetLastError());
   return ORCAI_OK;
