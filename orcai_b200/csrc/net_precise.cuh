@@ -433,7 +433,8 @@ template <bool RELU_IN, int ACT>
 int launch_sep_uf(Ctx* c, const float* x, float* out, long long n, long long h, int w, int cip, int ldc, int n_valid, const NetWeights::PreciseSep& ps) {
   static std::atomic<unsigned long long> attr_devices{0ull};
   if (!((attr_devices.load() >> (c->device & 63)) & 1ull)) {
-    ORCAI_CUDA(c, cudaFuncSetAttribute(precise::sep_uf_kernel<RELU_IN, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)precise::UfSmem(64, 1).bytes));
+    ORCAI_CUDA(c, cudaFuncSetAttribute(precise::sep_uf_kernel<RELU_IN, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)std::max(precise::UfSmem(64, 1).bytes, precise::UfSmem(40, 2).bytes)));
     attr_devices.fetch_or(1ull << (c->device & 63));
   }
   const int n_halo = (c->net->precise_halo2 && cip <= 40) ? 2 : 1;
