@@ -721,8 +721,9 @@ int forward_precise(Ctx* c, const float* d_in, int input_mode, int64_t first, in
     ORCAI_CUDA(c, cudaMemcpyToSymbolAsync(c_conv0, nw->h_conv0_pack.data(), 160 * sizeof(float), 0, cudaMemcpyHostToDevice, c->stream));
   }
   // the shared-interior evaluation needs the geometry it was derived for: 4 blocks, snippets half a length apart, 16-row aligned
+  // (and at least three snippets: the tall image of m snippets has (m + 1) / 2m of their rows plus the border images)
   const bool tall_ok = input_mode == 0 && nw->debug_stop < 0 && nw->precise_tall && nw->n_blocks == 4 && (c->p.snippet_len / 2) % 16 == 0 &&
-                       nw->H >= 128 && nw->H % 16 == 0;
+                       nw->H >= 128 && nw->H % 16 == 0 && n >= 3;
   if (tall_ok) return forward_precise_tall(c, d_in, first, n, d_preds, g);
   return forward_precise_snippets(c, d_in, input_mode, first, n, d_preds, g);
 }

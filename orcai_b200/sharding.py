@@ -27,6 +27,7 @@ def assign_rows(costs: list[float], world: int) -> list[list[int]]:
 
 
 def rows_for_rank(costs: list[float], world: int, rank: int) -> list[int]:
+    """The share of one rank (what `predict._rank_shard` workers take; also used by the gloo test)."""
     return assign_rows(costs, world)[rank]
 
 
@@ -42,7 +43,10 @@ def recording_costs(paths) -> list[float]:
 
 
 def gather_to_rank0(obj, world: int, rank: int):
-    """Host-side gather of python objects (torch.distributed, any backend). Returns the list on rank 0, None elsewhere."""
+    """Host-side gather of python objects (torch.distributed, any backend). Returns the list on rank 0, None elsewhere.
+
+    The product's table run needs no gather at all (every worker writes its own label files); this helper exists for callers that
+    want the per-recording results in one place and is exercised by tests/test_dist_cpu.py only."""
     if world == 1:
         return [obj]
     import torch.distributed as dist
