@@ -68,27 +68,22 @@ __host__ __device__ constexpr int pow2cols(int c) { return c <= 32 ? 32 : c <= 6
 //        3 MMAs per K chunk.  S1 is then no MMA operand any more, hence fp32.
 //        (Un-folding the FIRST convolution the same way was built and measured slower - 3.25 vs 2.98 ms per 10 min of audio,
 //        profiles/r02x_block1_uf1_experiment.log: its depthwise pass lands on the worker warps' critical chain, while the folded
-//        form's 27 MMAs per K chunk run on an otherwise idle tensor pipe.  Git history: eff5589.)
+//        form's 27 MMAs per K chunk run on an otherwise idle tensor pipe; with the pass on four dedicated warps it was still
+//        slower, 9.28 vs 8.90 ms per 1 024 snippets, profiles/r02zd_block1_uf1_dedicated_warps_experiment.log: the workers' chain
+//        does not shorten when the tensor pipe's operand reads go away.  Git history: eff5589 and its successor.)
 template <int CIN_, int COUT_, int CPOOL_, int S_, bool RELU_OUT_, int CTAS_, int NEW_, bool CONV0_ = false, int ISS_ = 1, int XBUF_ = 1, bool PREC_ = false,
-          bool UF2_ = false, bool UF1_ = false>
+          bool UF2_ = false>
 struct FB {
   static constexpr int XBUF = XBUF_;
-  static constexpr bool PREC = PREC_, UF2 = UF2_, UF1 = UF1_;
+  static constexpr bool PREC = PREC_, UF2 = UF2_;
   static_assert(!UF2_ || (PREC_ && ISS_ == 2), "the un-folded second convolution: split-fp16 configuration with two issuer warps");
-  // UF1_ (with UF2_): the FIRST separable convolution un-folded as well.  X arrives as fp32 in quad-planar layout (no MMA reads it
-  //        any more), four dedicated warps run the depthwise filter of step g+1 into the (hi, lo) operand D1 while the workers are busy
-  //        with step g, and the first convolution is 3 MMAs per K chunk instead of 27 (run on the worker warps the pass sat on
-  //        their critical chain and the kernel got slower: profiles/r02x_block1_uf1_experiment.log).  The residual input R (the
-  //        block input at even positions) stays a (hi, lo) fp16 operand loaded from its own tensor.
-  static_assert(!UF1_ || (UF2_ && XBUF_ == 1), "un-folded first convolution: on top of the un-folded second one, one X buffer");
   static constexpr int PL = PREC_ ? 2 : 1;           // operand plane sets: hi (, lo)
   static_assert(!(PREC_ && CONV0_), "the in-kernel entry convolution writes single fp16 operands");
   static_assert(XBUF_ == 1 || (XBUF_ == 2 && ISS_ == 2 && !CONV0_), "two X buffers: two-issuer TMA configuration only");
   static constexpr int CIN = CIN_, COUT = COUT_, CP = CPOOL_, S = S_, CTAS = CTAS_, NEW = NEW_, ISS = ISS_;
   static constexpr bool RELU_OUT = RELU_OUT_, CONV0 = CONV0_;
   static constexpr int NPROD = CONV0 ? 2 : 1;                       // producer warps: one TMA warp, or two entry-convolution warps
-  static constexpr int NDW1 = UF1_ ? 4 : 0;                        // UF1: warps that run the first convolution's depthwise pass
-  static constexpr int NWORK = NEW * 32, NTHREADS = NWORK + 32 * ISS + 32 * NPROD + 32 * NDW1;   // + issuer(s) + producer(s) (+ depthwise warps)
+  static constexpr int NWORK = NEW * 32, NTHREADS = NWORK + 32 * ISS + 32 * NPROD;   // + issuer warp(s) + producer warp(s)
   static_assert(ISS == 1 || ISS == 2, "one or two issuer warps");
   static constexpr int NT = NEW / 4;                 // worker teams per TMEM lane quadrant; a team drains 16 columns
   static constexpr int ICP = cpad8(CIN), OCP = cpad8(COUT);
@@ -103,7 +98,7 @@ struct FB {
   static constexpr int P1_0 = 2 * WP + 1, P2_0 = WP + 2;
   // one buffer: padded so that the last tile's over-read stays inside it; two buffers: packed (the over-read of rows that
   // feed no consumed accumulator row runs into the next plane / buffer, which is finite shared memory of this CTA)
-  static constexpr int XPIX = (XBUF_ == 2 || UF1_) ? round8((S + 2) * WP + 2) : round8(imax((S + 2) * WP, P1_0 + 128 * N1 + 1));
+  static constexpr int XPIX = XBUF_ == 2 ? round8((S + 2) * WP) : round8(imax((S + 2) * WP, P1_0 + 128 * N1 + 1));
   static constexpr int S1PIX = round8(imax((S + 2) * WP, P2_0 + 128 * N2 + WP + 1));
   // S2 is stored de-interleaved: even image columns in the first half of a chunk plane, odd columns in the second half
   // (offset by 64 B modulo 128), so that the pooling epilogue's lanes (one pooled column each) read consecutive 16-byte pieces
@@ -115,7 +110,7 @@ struct FB {
   // chunk alias the next group (finite values times a zero A chunk), missing n-groups only feed unused columns.
   static constexpr uint32_t SBO_W1 = XG * 128, SBO_W2 = NG * 128;
   static constexpr uint32_t TAP_W1 = NG * SBO_W1, TAP_W2 = NG * SBO_W2;
-  static constexpr uint32_t W1_BYTES = (UF1_ ? 1 : 9) * TAP_W1 + 128, W2_BYTES = (UF2_ ? 1 : 9) * TAP_W2 + 128, WR_BYTES = TAP_W1 + 128;
+  static constexpr uint32_t W1_BYTES = 9 * TAP_W1 + 128, W2_BYTES = (UF2_ ? 1 : 9) * TAP_W2 + 128, WR_BYTES = TAP_W1 + 128;
   static constexpr uint32_t WB_BYTES = NG * 128 + 128;   // [bias_hi, bias_lo] rows of one GEMM: n-groups of one k-chunk
   static constexpr uint32_t OFF_W1 = 0, OFF_W2 = OFF_W1 + W1_BYTES, OFF_WR = OFF_W2 + W2_BYTES;
   static constexpr uint32_t WSET = OFF_WR + WR_BYTES;        // one weight set [sep1 | sep2 | residual]; PREC: the lo set follows
@@ -123,34 +118,27 @@ struct FB {
   static constexpr uint32_t OFF_WB1 = WSET * PL, OFF_WB2 = OFF_WB1 + WB_BYTES, OFF_WBR = OFF_WB2 + WB_BYTES;
   static constexpr uint32_t OFF_ONES = OFF_WBR + WB_BYTES;   // two 8x8 core matrices: k = 0,1 are 1.0, the rest 0 (SBO = 0)
   static constexpr uint32_t OFF_DW2 = OFF_ONES + 256;          // UF2: depthwise taps of the second convolution, [9][NP] fp32
-  static constexpr uint32_t OFF_DW1 = OFF_DW2 + (UF2_ ? 9 * NP * 4 : 0);   // UF1: depthwise taps of the first convolution, [9][KP1] fp32
-  static constexpr uint32_t W_BYTES = (OFF_DW1 + (UF1_ ? 9 * KP1 * 4 : 0) + 127) / 128 * 128;   // TMA destinations behind it: 128-byte aligned
+  static constexpr uint32_t W_BYTES = OFF_DW2 + (UF2_ ? 9 * NP * 4 : 0);
   static constexpr uint32_t OFF_R = W_BYTES;
   static constexpr uint32_t R_LO = XCH * LBO_R, X_LO = XCH * LBO_X, S1_LO = MCH * LBO_S1, S2_LO = NG * LBO_S2;   // hi -> lo plane set
   static constexpr int NQ = OCP / 4;                             // UF2: fp32 S1 planes (4-channel quads), LBO_S1 apart
   static constexpr uint32_t S1_BYTES = UF2_ ? NQ * LBO_S1 : PL * MCH * LBO_S1;
   static constexpr int D2PIX = N2 * 128;                         // UF2: A operand of the pointwise GEMM, accumulator-row order
   static constexpr uint32_t LBO_D2 = D2PIX * 16, D2_LO = MCH * LBO_D2, D2_BYTES = UF2_ ? 2 * MCH * LBO_D2 : 0;
-  static constexpr int XQ = ICP / 4;                             // UF1: fp32 X planes (4-channel quads), LBO_X apart
-  static constexpr uint32_t X_BYTES = UF1_ ? XQ * LBO_X : PL * XCH * LBO_X;
-  static constexpr int D1PIX = N1 * 128;                         // UF1: A operand of the first pointwise GEMM, accumulator-row order
-  static constexpr uint32_t LBO_D1 = D1PIX * 16, D1_LO = XCH * LBO_D1, D1_BYTES = UF1_ ? 2 * XCH * LBO_D1 : 0;
   static constexpr uint32_t OFF_X = OFF_R + PL * XCH * LBO_R;
-  static constexpr uint32_t XR_BYTES = PL * XCH * LBO_R + X_BYTES;        // one R + X buffer; buffer b sits b * XR_BYTES further
-  static constexpr uint32_t OFF_S1 = OFF_X + X_BYTES + (XBUF - 1) * XR_BYTES;
+  static constexpr uint32_t XR_BYTES = PL * (XCH * LBO_R + XCH * LBO_X);        // one R + X buffer; buffer b sits b * XR_BYTES further
+  static constexpr uint32_t OFF_S1 = OFF_X + PL * XCH * LBO_X + (XBUF - 1) * XR_BYTES;
   static constexpr uint32_t OFF_S2 = OFF_S1 + S1_BYTES;
   // entry-convolution input: two (S+5) x SPW fp16 tiles of the normalised spectrogram (rows a-1 .. a+S+3, columns cb-1 ..)
   static constexpr int SPW = 64, SPH = S + 5;
   static constexpr uint32_t SPEC_BYTES = CONV0 ? SPH * SPW * 2 : 0;
   static constexpr uint32_t OFF_D2 = OFF_S2 + PL * NG * LBO_S2;
-  static constexpr uint32_t OFF_D1 = OFF_D2 + D2_BYTES;
-  static constexpr uint32_t OFF_SPEC = OFF_D1 + D1_BYTES;
+  static constexpr uint32_t OFF_SPEC = OFF_D2 + D2_BYTES;
   static constexpr uint32_t OFF_BAR = OFF_SPEC + 2 * ((SPEC_BYTES + 127) / 128 * 128);
   // barriers: bar1[N1] bar2[N2] barR[2] s1_full[N1] pool_done x_full[2] x_free[2] spec_full[2]
-  static constexpr int B_1 = 0, B_2 = N1, B_R = N1 + N2, B_S1 = N1 + N2 + 2, B_P = 2 * N1 + N2 + 2, B_X = B_P + 1, B_XF = B_X + 2, B_SP = B_XF + 2, B_D2 = B_SP + 2, B_D1 = B_D2 + 1, B_XW = B_D1 + 1, NBAR = B_XW + 1;
+  static constexpr int B_1 = 0, B_2 = N1, B_R = N1 + N2, B_S1 = N1 + N2 + 2, B_P = 2 * N1 + N2 + 2, B_X = B_P + 1, B_XF = B_X + 2, B_SP = B_XF + 2, B_D2 = B_SP + 2, NBAR = B_D2 + 1;
   static constexpr uint32_t SMEM = OFF_BAR + NBAR * 8 + 16;
-  static constexpr uint32_t TX_BYTES = UF1_ ? (XQ * (S + 2) * WP + PL * XG * (S / 2) * CP) * 16   // fp32 X quads + (hi, lo) R chunks
-                                            : PL * XG * ((S + 2) * WP + (S / 2) * CP) * 16;      // bytes one step's TMA loads deliver
+  static constexpr uint32_t TX_BYTES = PL * XG * ((S + 2) * WP + (S / 2) * CP) * 16;   // bytes one step's TMA loads deliver
   static constexpr int COL_R = 0, COL_1 = 2 * NP, COL_2 = 2 * NP + N1 * NP;
   static constexpr int TM_COLS = pow2cols(NP * (2 + N1 + N2));
   static_assert(NEW == 8 || NEW == 16, "worker warps come in groups of four (one per TMEM lane quadrant)");
@@ -313,8 +301,6 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     }
     mbar_init(&bars[G::B_SP], 1); mbar_init(&bars[G::B_SP + 1], 1);            // spectrogram tiles of the entry convolution
     mbar_init(&bars[G::B_D2], G::NEW);                                         // UF2: D2 written, one arrival per worker warp
-    mbar_init(&bars[G::B_D1], G::NDW1 ? G::NDW1 : 1);                          // UF1: D1 written, one arrival per depthwise warp
-    mbar_init(&bars[G::B_XW], G::NDW1 ? G::NDW1 : 1);                          // UF1: the depthwise warps have read X
     fence_mbar_init();
   }
   __syncwarp();
@@ -329,58 +315,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
   const long long my_items = blockIdx.x < n_items ? (n_items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
   const long long total_steps = my_items * n_steps;
 
-  if (G::NDW1 > 0 && warp >= G::NEW + G::ISS + G::NPROD) {
-    // =============================== UF1: depthwise warps of the first convolution ===============================
-    // Their own warps, so that the pass for step g+1 overlaps the workers' chain of step g instead of lengthening it.
-    // X (fp32 quad planes, rows a+1 .. a+S+2 of the step's tile) -> D1 (hi, lo) in accumulator-row order.  No geometry is needed:
-    // pixels outside the image are zero in X (TMA fill / guard rows) and their S1 values are zeroed by epilogue 1.  The block
-    // input of block 1 is post-ReLU, so no ReLU on load.
-    const int dtid = tid - (G::NEW + G::ISS + G::NPROD) * 32;
-    for (long long gd = 0; gd < total_steps; ++gd) {
-      mbar_wait(&bars[G::B_X], (uint32_t)(gd & 1));
-      if (gd > 0) mbar_wait(&bars[G::B_1 + G::N1 - 1], (uint32_t)((gd - 1) & 1));   // the MMAs that read D1 of the previous step are done
-      for (int u = dtid; u < G::XQ * G::WP; u += G::NDW1 * 32) {
-        const int q = u / G::WP, c = u - q * G::WP;
-        const float4* kw = reinterpret_cast<const float4*>(smem + G::OFF_DW1) + q;
-        float4 k[9];
-#pragma unroll
-        for (int t = 0; t < 9; ++t) k[t] = kw[t * (G::KP1 / 4)];
-        const unsigned char* xq = smem + G::OFF_X + q * G::LBO_X;
-        auto ld = [&](int y, int x) { return *reinterpret_cast<const float4*>(xq + (y * G::WP + x) * 16); };
-        float4 w[3][3];
-#pragma unroll
-        for (int y = 0; y < 2; ++y)
-#pragma unroll
-          for (int x = 0; x < 3; ++x) w[y + 1][x] = ld(y, c - 1 + x);
-#pragma unroll
-        for (int r = 2; r <= G::S + 1; ++r) {                      // S1 row r <- X tile rows r-2 .. r
-#pragma unroll
-          for (int x = 0; x < 3; ++x) { w[0][x] = w[1][x]; w[1][x] = w[2][x]; w[2][x] = ld(r, c - 1 + x); }
-          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-          for (int t = 0; t < 9; ++t) {
-            const float4 a4 = w[t / 3][t % 3];
-            acc.x = fmaf(a4.x, k[t].x, acc.x); acc.y = fmaf(a4.y, k[t].y, acc.y); acc.z = fmaf(a4.z, k[t].z, acc.z); acc.w = fmaf(a4.w, k[t].w, acc.w);
-          }
-          const int m = r * G::WP + c - G::P1_0;                   // accumulator row (all tiles) of this pixel
-          if (m >= 0 && m < G::D1PIX) {
-            const __half2 h01 = __floats2half2_rn(acc.x, acc.y), h23 = __floats2half2_rn(acc.z, acc.w);
-            const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-            const __half2 l01 = __floats2half2_rn(acc.x - f01.x, acc.y - f01.y), l23 = __floats2half2_rn(acc.z - f23.x, acc.w - f23.y);
-            unsigned char* dst = smem + G::OFF_D1 + (q >> 1) * G::LBO_D1 + m * 16 + (q & 1) * 8;
-            uint2 hv, lv;
-            hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
-            lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
-            *reinterpret_cast<uint2*>(dst) = hv;
-            *reinterpret_cast<uint2*>(dst + G::D1_LO) = lv;
-          }
-        }
-      }
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) { mbar_arrive(&bars[G::B_D1]); mbar_arrive(&bars[G::B_XW]); }
-    }
-  } else if (warp >= G::NEW + G::ISS) {
+  if (warp >= G::NEW + G::ISS) {
     if constexpr (G::CONV0) {
       // =============================== entry-convolution producers ===============================
       // Conv2D 3x3 1->16 + folded BatchNorm + ReLU (architectures.py:162-168) on the CUDA cores, straight into the X planes
@@ -479,24 +414,12 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         const int xb = G::XBUF == 2 ? (int)(g & 1) : 0;
         if (G::XBUF == 1) {
           if (g > 0) mbar_wait(&bars[G::B_1 + G::N1 - 1], (uint32_t)((g - 1) & 1));
-          if (G::UF1 && g > 0) mbar_wait(&bars[G::B_XW], (uint32_t)((g - 1) & 1));   // ... and the workers' depthwise pass has read X
         } else if (g >= 2) {
           mbar_wait(&bars[G::B_XF + xb], (uint32_t)(((g >> 1) - 1) & 1));
         }
         FB_TRACE(5, g);
         if (elect_one()) {
           mbar_arrive_expect_tx(&bars[G::B_X + xb], G::TX_BYTES);
-          if constexpr (G::UF1) {
-            // X: fp32 quad planes {4 floats, w, h, image, quad}; R: (hi, lo) chunk planes of the even-position tensor
-#pragma unroll
-            for (int q = 0; q < G::XQ; ++q)
-              tma_load_5d(sbase + G::OFF_X + q * G::LBO_X, &tmX, &bars[G::B_X], 0, cb, a + 1, (int)b, q);
-#pragma unroll
-            for (int c = 0; c < G::XG; ++c) {
-              tma_load_5d(sbase + G::OFF_R + c * G::LBO_R, &tmR, &bars[G::B_X], 0, wo0, a >> 1, (int)b, c);
-              tma_load_5d(sbase + G::OFF_R + G::R_LO + c * G::LBO_R, &tmRl, &bars[G::B_X], 0, wo0, a >> 1, (int)b, c);
-            }
-          } else
 #pragma unroll
           for (int c = 0; c < G::XG; ++c) {
             if constexpr (G::PREC) {
@@ -619,11 +542,6 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
             mma_commit(&bars[G::B_R + (int)(g & 1)]);
           }
           __syncwarp();
-          if constexpr (G::UF1) {
-            // un-folded: the workers have written D1 = depthwise(X) of this step as (hi, lo) rows in accumulator order
-            mbar_wait(&bars[G::B_D1], (uint32_t)(g & 1));
-            tc_fence_after();
-          }
 #pragma unroll
           for (int t = 0; t < G::N1; ++t) {
             if (g > 0) {
@@ -632,12 +550,6 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
             }
             if (elect_one()) {
               mma_f16_ss(tmem + G::COL_1 + t * G::NP, dOnes, dB1, idesc, 0);
-              if constexpr (G::UF1) {
-                const uint64_t dD1 = make_smem_desc(sbase + G::OFF_D1, G::LBO_D1, 128);
-#pragma unroll
-                for (int ks = 0; ks < G::KP1 / 16; ++ks)
-                  mma_x(tmem + G::COL_1 + t * G::NP, dD1 + (uint32_t)(128 * t) + ((2 * ks * G::LBO_D1) >> 4), dW1 + ((2 * ks * 128) >> 4), G::D1_LO >> 4);
-              } else {
 #pragma unroll
               for (int tap = 0; tap < 9; ++tap) {
                 const uint32_t aoff = (uint32_t)(G::P1_0 + 128 * t - 2 * G::WP - 1 + (tap / 3) * G::WP + (tap % 3));   // pixels = 16-byte units
@@ -645,7 +557,6 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                 for (int ks = 0; ks < G::KP1 / 16; ++ks)
                   mma_x(tmem + G::COL_1 + t * G::NP, dXb + aoff + ((2 * ks * G::LBO_X) >> 4),
                         dW1 + ((tap * G::TAP_W1 + 2 * ks * 128) >> 4), G::X_LO >> 4);
-              }
               }
               mma_commit(&bars[G::B_1 + t]);
               if (G::XBUF == 2 && t == G::N1 - 1) mma_commit(&bars[G::B_XF + xb]);   // this step's X / R buffer may be reloaded

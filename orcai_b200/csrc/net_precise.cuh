@@ -379,7 +379,7 @@ sep_uf_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__
 
 // block 1 of the fp32-grade path: one CTA per SM (the (hi, lo) plane sets fill its shared memory), two issuer warps; its output
 // is the un-rectified block output in fp32 (the next block applies the ReLU on load and walks it with stride 2 for its residual)
-using FB1P = fused::FB<16, 30, 29, 4, false, 1, 8, false, 2, 1, true, true, true>;   // both convolutions un-folded; the first one's depthwise pass on its own warps
+using FB1P = fused::FB<16, 30, 29, 4, false, 1, 8, false, 2, 1, true, true>;   // measured alternatives: 16 worker warps 3.40 vs 3.25 ms per 10 min (not issue-bound); strips of 14 columns with two CTAs per SM 11.2 vs 8.9 ms per 1 024 snippets (80 registers, more halo)
 
 inline std::vector<float> pad_matrix(const float* w, int rows, int cols, int rows_p, int cols_p) {
   std::vector<float> out((size_t)rows_p * cols_p, 0.f);
@@ -492,24 +492,21 @@ int run_precise_block(Ctx* c, int blk, const float* x, float* ta, float* tb, flo
   return ORCAI_OK;
 }
 
-// entry convolution for the un-folded block 1: xq = fp32 quad-planar output (4 planes, xq_plane floats apart), r_hi / r_lo = its
-// even positions as (hi, lo) chunk planes (2 planes each, r_plane halfs apart)
-int run_conv0_uf(Ctx* c, const float* src, int input_mode, long long first, int in_ld, long long n_img, int Himg, int Wf, float* xq, long long xq_plane,
-                 __half* r_hi, __half* r_lo, long long r_plane, long long n_snip, int off_bot, int Hfull) {
+int run_conv0_split(Ctx* c, const float* src, int input_mode, long long first, int in_ld, long long n_img, int Himg, int Wf, __half* hi, __half* lo,
+                    long long n_snip, int off_bot, int Hfull, long long plane_halfs) {
   const int tiles_w = (Wf + kC0TW - 1) / kC0TW, tiles_h = (Himg + kC0TH - 1) / kC0TH;
   const long long blocks = n_img * tiles_w * tiles_h;
   if (blocks <= 0) return ORCAI_OK;
-  conv0_direct_kernel<2><<<(unsigned)blocks, 256, 0, c->stream>>>(src, input_mode, first, c->p.snippet_len / 2, in_ld, Himg, Wf, c->d_sel,
-                                                                  reinterpret_cast<__half*>(xq), r_hi, tiles_w, tiles_h, r_lo, n_snip, off_bot, Hfull, xq_plane, r_plane);
+  conv0_direct_kernel<true><<<(unsigned)blocks, 256, 0, c->stream>>>(src, input_mode, first, c->p.snippet_len / 2, in_ld, Himg, Wf, c->d_sel, hi,
+                                                                     static_cast<__half*>(nullptr), tiles_w, tiles_h, lo, n_snip, off_bot, Hfull, plane_halfs);
   c->launches++;
   ORCAI_CUDA(c, cudaGetLastError());
   return ORCAI_OK;
 }
 
-// block 1 over ONE tall image (rows, W): fp32 quad-planar X plus the (hi, lo) even-position tensor, cut into windows of `stride`
-// rows (+ warm-up); guard rows of zeros lie before the tensors (>= warm rows of X, warm / 2 of R) and after them (>= stride + 16)
-int run_block1_tall(Ctx* c, const float* xq, long long xq_plane, const __half* r_hi, const __half* r_lo, long long r_plane, float* y, long long rows,
-                    int Wimg, int stride, int warm) {
+// block 1 over ONE tall image (rows, W) of (hi, lo) fp16 pairs, cut into windows of `stride` rows (+ warm-up); guard rows of
+// zeros lie before x (>= warm rows) and after it (>= stride + 16 rows)
+int run_block1_tall(Ctx* c, const __half* x_hi, const __half* x_lo, long long plane_halfs, float* y, long long rows, int Wimg, int stride, int warm) {
   using G = FB1P;
   NetWeights* nw = c->net;
   const int Wo = (Wimg + 1) / 2;
@@ -518,15 +515,16 @@ int run_block1_tall(Ctx* c, const float* xq, long long xq_plane, const __half* r
   const long long items = n_win * n_strips;
   const long long grid = std::min<long long>(items, (long long)c->sm_count * G::CTAS);
   const int Hloc = warm + stride;
-  CUtensorMap tmx, tmr, tmrl;
-  ORCAI_CHECK(make_quad_map(c, &tmx, xq - (size_t)warm * Wimg * 4, n_win, Hloc + 8, Wimg, G::XQ, xq_plane, G::WP, G::S + 2, stride));
-  const size_t rshift = (size_t)(warm / 2) * Wo * 8;
-  ORCAI_CHECK(make_planar_map(c, &tmr, r_hi - rshift, n_win, (Hloc + 8) / 2, Wo, G::XG, r_plane, G::CP, G::S / 2, 1, stride / 2));
-  ORCAI_CHECK(make_planar_map(c, &tmrl, r_lo - rshift, n_win, (Hloc + 8) / 2, Wo, G::XG, r_plane, G::CP, G::S / 2, 1, stride / 2));
+  const size_t shift = (size_t)warm * Wimg * 8;      // halfs per plane
+  CUtensorMap tmx, tmr, tmxl, tmrl;
+  ORCAI_CHECK(make_planar_map(c, &tmx, x_hi - shift, n_win, Hloc + 8, Wimg, G::XG, plane_halfs, G::WP, G::S + 2, 1, stride));
+  ORCAI_CHECK(make_planar_map(c, &tmr, x_hi - shift, n_win, Hloc + 8, Wimg, G::XG, plane_halfs, G::CP, G::S / 2, 2, stride));
+  ORCAI_CHECK(make_planar_map(c, &tmxl, x_lo - shift, n_win, Hloc + 8, Wimg, G::XG, plane_halfs, G::WP, G::S + 2, 1, stride));
+  ORCAI_CHECK(make_planar_map(c, &tmrl, x_lo - shift, n_win, Hloc + 8, Wimg, G::XG, plane_halfs, G::CP, G::S / 2, 2, stride));
   fused::TallView tv;
   tv.on = 1; tv.stride = stride; tv.warm = warm; tv.rows = rows;
-  fused::fused_block_kernel<G><<<(unsigned)grid, G::NTHREADS, G::SMEM, c->stream>>>(tmx, tmr, 1, reinterpret_cast<__half*>(y), static_cast<__half*>(nullptr), Hloc,
-                                                                                   Wimg, n_strips, items, static_cast<const unsigned char*>(nw->fbp_w[0]), tmx,
+  fused::fused_block_kernel<G><<<(unsigned)grid, G::NTHREADS, G::SMEM, c->stream>>>(tmx, tmr, 2, reinterpret_cast<__half*>(y), static_cast<__half*>(nullptr), Hloc,
+                                                                                   Wimg, n_strips, items, static_cast<const unsigned char*>(nw->fbp_w[0]), tmxl,
                                                                                    tmrl, tv);
   c->launches++;
   ORCAI_CUDA(c, cudaGetLastError());
@@ -544,20 +542,18 @@ int forward_precise_snippets(Ctx* c, const float* d_in, int input_mode, int64_t 
   const int Himg = nw->H, Wf = nw->Wf, U = nw->U, L = nw->L;
   const int Tn = Himg >> nw->n_blocks;
   const int *hs = g.hs, *ws = g.ws, *cp = g.cp;
-  const size_t c0_h = (size_t)hs[0] * ws[0] * 16 * 2;                   // fp32 X (16 channels), counted in halfs
-  const size_t r_h = (size_t)hs[1] * ws[1] * 16;                        // even-position tensor, halfs per (hi | lo) set
+  const size_t c0_h = (size_t)hs[0] * ws[0] * 16;                       // halfs per plane set
   const size_t y1 = (size_t)hs[1] * ws[1] * cp[1], y2 = (size_t)hs[2] * ws[2] * cp[2], y3 = (size_t)hs[3] * ws[3] * cp[3], y4 = (size_t)hs[4] * ws[4] * cp[4];
   const size_t tmp = (size_t)hs[1] * ws[1] * cp[2];
   const size_t feat_f = (size_t)Tn * nw->feat;
   const size_t tail_f = (size_t)Tn * (2 * 4 * U + 2 * U + 2 * U + 128);
-  const size_t per = (c0_h + 2 * r_h) * 2 + (y1 + y2 + y3 + y4 + 3 * tmp + feat_f + tail_f) * 4;
+  const size_t per = c0_h * 2 * 2 + (y1 + y2 + y3 + y4 + 3 * tmp + feat_f + tail_f) * 4;
   const long long chunk = std::min<long long>(std::max(nw->chunk_precise, 1), n);
   if (chunk <= 0) return ORCAI_OK;
   ORCAI_CHECK(ensure_device_buffer(c, &nw->tc_ws, &nw->tc_ws_cap, per * (size_t)chunk + 256));
-  float* XQ = static_cast<float*>(nw->tc_ws);                             // entry-convolution output: fp32 quad planes
-  H16* rhi = reinterpret_cast<H16*>(XQ) + c0_h * chunk;                   // ... and its even positions as (hi, lo) chunk planes
-  H16* rlo = rhi + r_h * chunk;
-  float* Y1 = reinterpret_cast<float*>(rlo + r_h * chunk);
+  H16* c0hi = static_cast<H16*>(nw->tc_ws);
+  H16* c0lo = c0hi + c0_h * chunk;
+  float* Y1 = reinterpret_cast<float*>(c0lo + c0_h * chunk);
   float* Y2 = Y1 + y1 * chunk;
   float* Y3 = Y2 + y2 * chunk;
   float* Y4 = Y3 + y3 * chunk;
@@ -573,13 +569,12 @@ int forward_precise_snippets(Ctx* c, const float* d_in, int input_mode, int64_t 
     if (mk) nw->marked_snippets = m;
     net_mark(c, mk);
     const float* src = (input_mode == 0) ? d_in : d_in + (size_t)s0 * Himg * Wf;
-    const long long xq_plane = (long long)m * hs[0] * ws[0] * 4;   // floats per quad plane
-    const long long r_plane = (long long)m * hs[1] * ws[1] * 8;    // halfs per chunk plane of the even-position tensor
-    ORCAI_CHECK(run_conv0_uf(c, src, input_mode, first + s0, input_mode == 0 ? kRawLd : Wf, m, Himg, Wf, XQ, xq_plane, rhi, rlo, r_plane, m, 0, Himg));
+    const long long plane = (long long)m * hs[0] * ws[0] * 8;   // chunk-planar (hi, lo) output: two planes of 8 channels each
+    ORCAI_CHECK(run_conv0_split(c, src, input_mode, first + s0, input_mode == 0 ? kRawLd : Wf, m, Himg, Wf, c0hi, c0lo, m, 0, Himg, plane));
     net_mark(c, mk);  // 0: conv0
-    if (stop == 0) { set_debug(nw, XQ, 0, m, hs[0], ws[0], 4, 4); return ORCAI_OK; }   // channels 0-3 (first quad plane)
-    ORCAI_CHECK((run_fused_block<FB1P>(c, 0, reinterpret_cast<const H16*>(XQ), rhi, reinterpret_cast<H16*>(Y1), static_cast<H16*>(nullptr), m, hs[0], ws[0],
-                                       static_cast<const H16*>(nullptr), rlo, xq_plane, r_plane)));
+    if (stop == 0) { set_debug(nw, c0hi, 1, m, hs[0], ws[0], 8, 8); return ORCAI_OK; }   // channels 0-7, hi plane
+    ORCAI_CHECK((run_fused_block<FB1P>(c, 0, c0hi, static_cast<const H16*>(nullptr), reinterpret_cast<H16*>(Y1), static_cast<H16*>(nullptr), m, hs[0], ws[0],
+                                       c0lo, static_cast<const H16*>(nullptr), plane)));
     net_mark(c, mk);  // 1
     if (stop == 1) { set_debug(nw, Y1, 0, m, hs[1], ws[1], 30, cp[1]); return ORCAI_OK; }
     ORCAI_CHECK(run_precise_block(c, 1, Y1, TA, TB, TC, Y2, m, hs[1], ws[1], cp[1], cp[2]));
@@ -626,16 +621,15 @@ int forward_precise_tall(Ctx* c, const float* d_raw, int64_t first, int64_t n, f
   const long long M = chunk;
   size_t off = 0;
   auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
-  // entry-convolution output: 4 fp32 quad planes of (guard + rows + guard, W, 4); its even positions: (hi | lo) x 2 chunk planes
-  const long long xq_plane = (long long)(kGuardB + rows_at(M, 0) + kGuardA) * ws[0] * 4;                  // floats
-  const long long r_plane = (long long)(kGuardB / 2 + rows_at(M, 1) + kGuardA / 2) * ws[1] * 8;           // halfs
-  const size_t o_xq = take((size_t)4 * xq_plane * 4), o_rhi = take((size_t)2 * r_plane * 2), o_rlo = take((size_t)2 * r_plane * 2);
+  const size_t c0_plane = (size_t)(kGuardB + rows_at(M, 0) + kGuardA) * ws[0] * 16 * 2;
+  const size_t o_c0hi = take(c0_plane), o_c0lo = take(c0_plane);
   size_t o_y[5] = {};
   for (int l = 1; l <= 4; ++l) o_y[l] = take((size_t)rows_at(M, l) * ws[l] * cp[l] * 4);
   const size_t tmp = (size_t)rows_at(M, 1) * ws[1] * cp[2] * 4;
   const size_t o_ta = take(tmp), o_tb = take(tmp), o_tc = take(tmp);
   const size_t o_featt = take((size_t)rows_at(M, 4) * nw->feat * 4);
-  const size_t o_bxq = take((size_t)2 * M * 8 * ws[0] * 16 * 4), o_brhi = take((size_t)2 * M * 4 * ws[1] * 16 * 2), o_brlo = take((size_t)2 * M * 4 * ws[1] * 16 * 2);
+  const size_t b0_plane = (size_t)2 * M * 8 * ws[0] * 16 * 2;
+  const size_t o_b0hi = take(b0_plane), o_b0lo = take(b0_plane);
   const size_t alt_sz = (size_t)2 * M * 4 * ws[1] * cp[1] * 4, bimg_sz = (size_t)2 * M * 8 * ws[1] * cp[1] * 4, btmp = (size_t)2 * M * 8 * ws[1] * cp[2] * 4;
   const size_t o_alt = take(alt_sz), o_bimg = take(bimg_sz), o_bta = take(btmp), o_btb = take(btmp), o_btc = take(btmp);
   const size_t o_featb = take((size_t)2 * M * 8 * nw->feat * 4);
@@ -644,15 +638,15 @@ int forward_precise_tall(Ctx* c, const float* d_raw, int64_t first, int64_t n, f
   ORCAI_CHECK(ensure_device_buffer(c, &nw->tc_ws, &nw->tc_ws_cap, off + 256));
   unsigned char* base = static_cast<unsigned char*>(nw->tc_ws);
   auto F = [&](size_t o) { return reinterpret_cast<float*>(base + o); };
-  const size_t xq_row = (size_t)ws[0] * 4, r_row = (size_t)ws[1] * 8;     // floats / halfs per row of one plane
-  float* XQ = F(o_xq) + kGuardB * xq_row;
-  H16* rhi = reinterpret_cast<H16*>(base + o_rhi) + (kGuardB / 2) * r_row;
-  H16* rlo = reinterpret_cast<H16*>(base + o_rlo) + (kGuardB / 2) * r_row;
+  // entry-convolution output, chunk-planar: per (hi | lo) set two planes of (guard + rows + guard, W, 8) halfs
+  const size_t c0_row = (size_t)ws[0] * 8;         // halfs per row of one plane
+  const long long c0_plane_halfs = (long long)(kGuardB + rows_at(M, 0) + kGuardA) * c0_row;
+  H16* c0hi = reinterpret_cast<H16*>(base + o_c0hi) + kGuardB * c0_row;
+  H16* c0lo = reinterpret_cast<H16*>(base + o_c0lo) + kGuardB * c0_row;
   float* Y[5] = {nullptr, F(o_y[1]), F(o_y[2]), F(o_y[3]), F(o_y[4])};
   float *TA = F(o_ta), *TB = F(o_tb), *TC = F(o_tc), *FEATT = F(o_featt);
-  float* BXQ = F(o_bxq);
-  H16* brhi = reinterpret_cast<H16*>(base + o_brhi);
-  H16* brlo = reinterpret_cast<H16*>(base + o_brlo);
+  H16* b0hi = reinterpret_cast<H16*>(base + o_b0hi);
+  H16* b0lo = reinterpret_cast<H16*>(base + o_b0lo);
   float *ALT = F(o_alt), *BIMG = F(o_bimg), *BTA = F(o_bta), *BTB = F(o_btb), *BTC = F(o_btc), *FEATB = F(o_featb);
   float *feat = F(o_feat), *scratch = F(o_tail);
 
@@ -663,25 +657,20 @@ int forward_precise_tall(Ctx* c, const float* d_raw, int64_t first, int64_t n, f
     const long long R0 = rows_at(m, 0);
     net_mark(c, mk);
     // entry convolution: the chunk's rows as one image, and the 8-row border images of every snippet (its own zero padding)
-    for (int pl = 0; pl < 4; ++pl) {
-      float* p = XQ + (size_t)pl * xq_plane;
-      ORCAI_CUDA(c, cudaMemsetAsync(p - kGuardB * xq_row, 0, kGuardB * xq_row * 4, c->stream));
-      ORCAI_CUDA(c, cudaMemsetAsync(p + R0 * xq_row, 0, (size_t)kGuardA * xq_row * 4, c->stream));
-    }
-    for (H16* p0 : {rhi, rlo})
+    for (H16* p0 : {c0hi, c0lo})
       for (int pl = 0; pl < 2; ++pl) {
-        H16* p = p0 + (size_t)pl * r_plane;
-        ORCAI_CUDA(c, cudaMemsetAsync(p - (kGuardB / 2) * r_row, 0, (kGuardB / 2) * r_row * 2, c->stream));
-        ORCAI_CUDA(c, cudaMemsetAsync(p + (R0 / 2) * r_row, 0, (size_t)(kGuardA / 2) * r_row * 2, c->stream));
+        H16* p = p0 + (size_t)pl * c0_plane_halfs;
+        ORCAI_CUDA(c, cudaMemsetAsync(p - kGuardB * c0_row, 0, kGuardB * c0_row * 2, c->stream));
+        ORCAI_CUDA(c, cudaMemsetAsync(p + R0 * c0_row, 0, (size_t)kGuardA * c0_row * 2, c->stream));
       }
-    const long long bxq_plane = (long long)2 * m * 8 * ws[0] * 4, br_plane = (long long)2 * m * 4 * ws[1] * 8;
-    ORCAI_CHECK(run_conv0_uf(c, d_raw, 0, first + s0, kRawLd, 1, (int)R0, Wf, XQ, xq_plane, rhi, rlo, r_plane, 1, 0, (int)R0));
-    ORCAI_CHECK(run_conv0_uf(c, d_raw, 0, first + s0, kRawLd, 2 * m, 8, Wf, BXQ, bxq_plane, brhi, brlo, br_plane, m, Himg - 8, Himg));
+    const long long b0_plane_halfs = (long long)2 * m * 8 * ws[0] * 8;
+    ORCAI_CHECK(run_conv0_split(c, d_raw, 0, first + s0, kRawLd, 1, (int)R0, Wf, c0hi, c0lo, 1, 0, (int)R0, c0_plane_halfs));
+    ORCAI_CHECK(run_conv0_split(c, d_raw, 0, first + s0, kRawLd, 2 * m, 8, Wf, b0hi, b0lo, m, Himg - 8, Himg, b0_plane_halfs));
     net_mark(c, mk);  // 0: conv0
     // block 1: fused kernel over windows of the tall image; border images as independent 8-row images -> ALT (2m, 4, ..)
-    ORCAI_CHECK(run_block1_tall(c, XQ, xq_plane, rhi, rlo, r_plane, Y[1], R0, Wf, kWin, kWarm));
-    ORCAI_CHECK((run_fused_block<FB1P>(c, 0, reinterpret_cast<const H16*>(BXQ), brhi, reinterpret_cast<H16*>(ALT), static_cast<H16*>(nullptr), 2 * m, 8, ws[0],
-                                       static_cast<const H16*>(nullptr), brlo, bxq_plane, br_plane)));
+    ORCAI_CHECK(run_block1_tall(c, c0hi, c0lo, c0_plane_halfs, Y[1], R0, Wf, kWin, kWarm));
+    ORCAI_CHECK((run_fused_block<FB1P>(c, 0, b0hi, static_cast<const H16*>(nullptr), reinterpret_cast<H16*>(ALT), static_cast<H16*>(nullptr), 2 * m, 8, ws[0],
+                                       b0lo, static_cast<const H16*>(nullptr), b0_plane_halfs)));
     net_mark(c, mk);  // 1
     // blocks 2 - 4: tall image, then the border images gathered from the tall tensor and the previous level's border rows
     for (int l = 1; l <= 3; ++l) {

@@ -330,16 +330,11 @@ constexpr int kC0TH = 8, kC0TW = 32;
 // Row windows (net_precise.cuh, border images): image b is rows [off, off + Himg) of snippet b % n_snip, off = 0 for b < n_snip
 // and off_bot for the others; zero padding applies outside the snippet's rows [0, Hfull).  Plain use: n_snip = image count,
 // off_bot = 0, Hfull = Himg.
-// OUT: 0 = fp16 NHWC (+ even-position copy), 1 = SPLIT (hi, lo) fp16, 2 = fp32 quad-planar (four planes of (n, H, W, 4) floats,
-// plane_halfs FLOATS apart, at `out`) plus the (hi, lo) chunk-planar tensor of the pixels at even positions (out_sub / out_lo, two
-// planes sub_plane halfs apart): the X and R operands of the fully un-folded block 1
-template <int OUT>
+template <bool SPLIT>
 __global__ void __launch_bounds__(256)
 conv0_direct_kernel(const float* __restrict__ in, int mode, long long first, int shift, int in_ld, int Himg, int Wimg,
                     const SelectState* __restrict__ st, __half* __restrict__ out, __half* __restrict__ out_sub,
-                    int tiles_w, int tiles_h, __half* __restrict__ out_lo, long long n_snip, int off_bot, int Hfull, long long plane_halfs,
-                    long long sub_plane) {
-  constexpr bool SPLIT = OUT == 1;
+                    int tiles_w, int tiles_h, __half* __restrict__ out_lo, long long n_snip, int off_bot, int Hfull, long long plane_halfs) {
   __shared__ float s_x[kC0TH + 2][kC0TW + 2];
   const int tid = threadIdx.x, ty = tid >> 5, tx = tid & 31;
   const int tiles_per = tiles_w * tiles_h;
@@ -379,22 +374,6 @@ conv0_direct_kernel(const float* __restrict__ in, int mode, long long first, int
     for (int c = 0; c < 16; ++c) acc[c] = fmaf(x[t], c_conv0[t * 16 + c], acc[c]);
 #pragma unroll
   for (int c = 0; c < 16; ++c) acc[c] = fmaxf(acc[c], 0.f);
-  if constexpr (OUT == 2) {
-    float* xo = reinterpret_cast<float*>(out) + (((size_t)b * Himg + hh) * Wimg + ww) * 4;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(xo + (size_t)q * plane_halfs) = make_float4(acc[4 * q], acc[4 * q + 1], acc[4 * q + 2], acc[4 * q + 3]);
-    if (!(hh & 1) && !(ww & 1)) {
-      uint4 h0, l0, h1, l1;
-      fused::split8h(acc, h0, l0);
-      fused::split8h(acc + 8, h1, l1);
-      const size_t at = (((size_t)b * (Himg >> 1) + (hh >> 1)) * ((Wimg + 1) >> 1) + (ww >> 1)) * 8;
-      *reinterpret_cast<uint4*>(out_sub + at) = h0;
-      *reinterpret_cast<uint4*>(out_sub + at + sub_plane) = h1;
-      *reinterpret_cast<uint4*>(out_lo + at) = l0;
-      *reinterpret_cast<uint4*>(out_lo + at + sub_plane) = l1;
-    }
-    return;
-  }
   if constexpr (SPLIT) {
     uint4 h0, l0, h1, l1;
     fused::split8h(acc, h0, l0);
@@ -693,11 +672,10 @@ int build_fused_block(Ctx* c, int blk) {
     else *acc += ((double)__half2float(q) - v) * mu;
   };
   for (int t = 0; t < 9; ++t) {
-    if (!G::UF1)
-      for (int k = 0; k < G::CIN; ++k)
-        for (int n = 0; n < G::COUT; ++n)
-          put(at(G::OFF_W1 + t * G::TAP_W1, G::SBO_W1, n, k), (double)(s1.dw[(size_t)t * G::CIN + k] * s1.pw[(size_t)k * G::COUT + n]),
-              cal.valid ? cal.in_relu[blk][k] : 0.0, &d1[n]);
+    for (int k = 0; k < G::CIN; ++k)
+      for (int n = 0; n < G::COUT; ++n)
+        put(at(G::OFF_W1 + t * G::TAP_W1, G::SBO_W1, n, k), (double)(s1.dw[(size_t)t * G::CIN + k] * s1.pw[(size_t)k * G::COUT + n]),
+            cal.valid ? cal.in_relu[blk][k] : 0.0, &d1[n]);
     if (!G::UF2)
       for (int k = 0; k < G::COUT; ++k)
         for (int n = 0; n < G::COUT; ++n)
@@ -710,13 +688,6 @@ int build_fused_block(Ctx* c, int blk) {
     float* taps = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(w.data()) + G::OFF_DW2);
     for (int t = 0; t < 9; ++t)
       for (int k = 0; k < G::COUT; ++k) taps[t * G::NP + k] = s2.dw[(size_t)t * G::COUT + k];
-  }
-  if (G::UF1) {   // the same for the first convolution
-    for (int k = 0; k < G::CIN; ++k)
-      for (int n = 0; n < G::COUT; ++n) put(at(G::OFF_W1, G::SBO_W1, n, k), (double)s1.pw[(size_t)k * G::COUT + n], 0.0, &d1[n]);
-    float* taps = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(w.data()) + G::OFF_DW1);
-    for (int t = 0; t < 9; ++t)
-      for (int k = 0; k < G::CIN; ++k) taps[t * G::KP1 + k] = s1.dw[(size_t)t * G::CIN + k];
   }
   const std::vector<float>& rw = nw->h_res_w[blk];
   for (int k = 0; k < G::CIN; ++k)
@@ -960,47 +931,22 @@ int make_planar_map(Ctx* c, CUtensorMap* map, const __half* base, long long n, i
   return ORCAI_OK;
 }
 
-// rank-5 map over an fp32 quad-PLANAR activation tensor: `quads` planes of (n, h, w, 4) floats, plane_floats apart;
-// box = {4 floats, box_w, box_h, 1 image, 1 quad}
-int make_quad_map(Ctx* c, CUtensorMap* map, const float* base, long long n, int h, int w, int quads, long long plane_floats, int box_w, int box_h,
-                  long long img_rows = 0) {
-  EncodeTiledFn fn = encode_tiled_fn();
-  if (!fn) ORCAI_FAIL(c, ORCAI_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
-  const cuuint64_t dims[5] = {4, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n, (cuuint64_t)quads};
-  const cuuint64_t strides[4] = {16, (cuuint64_t)w * 16, (cuuint64_t)(img_rows > 0 ? img_rows : h) * w * 16, (cuuint64_t)plane_floats * 4};
-  const cuuint32_t box[5] = {4, (cuuint32_t)box_w, (cuuint32_t)box_h, 1, 1};
-  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  const CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) ORCAI_FAIL(c, ORCAI_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for the quad-planar tensor (%lld, %d, %d) x %d", (int)r, n, h, w, quads);
-  return ORCAI_OK;
-}
-
 template <class G>
 int run_fused_block(Ctx* c, int blk, const __half* xr, const __half* xs, __half* yr, __half* ys, long long m, int Himg, int Wimg,
-                    const __half* xr_lo = nullptr, const __half* xs_lo = nullptr, long long plane_halfs = 0, long long sub_plane = 0) {
+                    const __half* xr_lo = nullptr, const __half* xs_lo = nullptr, long long plane_halfs = 0) {
   NetWeights* nw = c->net;
   const int Ho = Himg / 2, Wo = (Wimg + 1) / 2;
   const int n_strips = (Wo + G::CP - 1) / G::CP;
   const long long items = m * n_strips;
   const long long grid = std::min<long long>(items, (long long)c->sm_count * G::CTAS);
   CUtensorMap tmx, tmr, tmxl, tmrl;
-  if (!G::PREC) {
-    ORCAI_CHECK(make_act_map(c, &tmx, xr, m, Himg, Wimg, G::ICP, G::WP, G::S + 2));
-    // residual input = x at even positions: its own tensor, or (xs == nullptr: x is non-negative, ReLU(x) == x) the full tensor
-    // traversed with element stride 2
-    if (xs) ORCAI_CHECK(make_act_map(c, &tmr, xs, m, Ho, Wo, G::ICP, G::CP, G::S / 2));
-    else ORCAI_CHECK(make_act_map(c, &tmr, xr, m, Himg, Wimg, G::ICP, G::CP, G::S / 2, 2));
-  }
+  ORCAI_CHECK(make_act_map(c, &tmx, xr, m, Himg, Wimg, G::ICP, G::WP, G::S + 2));
+  // residual input = x at even positions: its own tensor, or (xs == nullptr: x is non-negative, ReLU(x) == x) the full tensor
+  // traversed with element stride 2
+  if (xs) ORCAI_CHECK(make_act_map(c, &tmr, xs, m, Ho, Wo, G::ICP, G::CP, G::S / 2));
+  else ORCAI_CHECK(make_act_map(c, &tmr, xr, m, Himg, Wimg, G::ICP, G::CP, G::S / 2, 2));
   tmxl = tmx; tmrl = tmr;
-  if (G::UF1) {
-    // xr = fp32 quad-planar block input (planes plane_halfs FLOATS apart), xs / xs_lo = its even positions as (hi, lo) chunk planes
-    // (planes sub_plane halfs apart)
-    ORCAI_CHECK(make_quad_map(c, &tmx, reinterpret_cast<const float*>(xr), m, Himg, Wimg, G::XQ, plane_halfs, G::WP, G::S + 2));
-    ORCAI_CHECK(make_planar_map(c, &tmr, xs, m, Ho, Wo, G::XG, sub_plane, G::CP, G::S / 2));
-    tmxl = tmx;
-    ORCAI_CHECK(make_planar_map(c, &tmrl, xs_lo, m, Ho, Wo, G::XG, sub_plane, G::CP, G::S / 2));
-  } else if (G::PREC) {   // chunk-planar (hi, lo) inputs; the residual convolution walks the same tensors with stride 2
+  if (G::PREC) {   // chunk-planar (hi, lo) inputs; the residual convolution walks the same tensors with stride 2
     (void)xs_lo;
     ORCAI_CHECK(make_planar_map(c, &tmx, xr, m, Himg, Wimg, G::XG, plane_halfs, G::WP, G::S + 2));
     ORCAI_CHECK(make_planar_map(c, &tmr, xr, m, Himg, Wimg, G::XG, plane_halfs, G::CP, G::S / 2, 2));
@@ -1149,9 +1095,9 @@ int forward_fused(Ctx* c, const float* d_in, int input_mode, int64_t first, int6
     } else {
       const int tiles_w = (Wf + kC0TW - 1) / kC0TW, tiles_h = (Himg + kC0TH - 1) / kC0TH;
       const float* src = (input_mode == 0) ? d_in : d_in + (size_t)s0 * Himg * Wf;
-      conv0_direct_kernel<0><<<(unsigned)(m * tiles_w * tiles_h), 256, 0, c->stream>>>(src, input_mode, first + s0, shift, input_mode == 0 ? kRawLd : Wf,
+      conv0_direct_kernel<false><<<(unsigned)(m * tiles_w * tiles_h), 256, 0, c->stream>>>(src, input_mode, first + s0, shift, input_mode == 0 ? kRawLd : Wf,
                                                                                           Himg, Wf, c->d_sel, act[0], static_cast<H*>(nullptr), tiles_w, tiles_h,
-                                                                                          static_cast<H*>(nullptr), m, 0, Himg, 0, 0);
+                                                                                          static_cast<H*>(nullptr), m, 0, Himg, 0);
       c->launches++;
       ORCAI_CUDA(c, cudaGetLastError());
     }

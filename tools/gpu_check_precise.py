@@ -43,7 +43,7 @@ def main() -> int:
     ok = True
     report = {}
     ctx.set_option("net_path", args.path)
-    stages = [(0, "conv0 (ch 0-3, fp32)", nhwc["conv0"][..., :4]), (1, "block1", nhwc["block1"]),
+    stages = [(0, "conv0 (hi, ch 0-7)", nhwc["conv0"][..., :8]), (1, "block1", nhwc["block1"]),
               (2, "block2", nhwc["block2"]), (3, "block3", nhwc["block3"]), (4, "block4", nhwc["block4"]), (5, "final", nhwc["final"])]
     for stage, key, want in ([] if args.only_timing else stages):
         t0 = time.time()
