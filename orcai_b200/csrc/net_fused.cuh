@@ -70,7 +70,9 @@ __host__ __device__ constexpr int pow2cols(int c) { return c <= 32 ? 32 : c <= 6
 //        profiles/r02x_block1_uf1_experiment.log: its depthwise pass lands on the worker warps' critical chain, while the folded
 //        form's 27 MMAs per K chunk run on an otherwise idle tensor pipe; with the pass on four dedicated warps it was still
 //        slower, 9.28 vs 8.90 ms per 1 024 snippets, profiles/r02zd_block1_uf1_dedicated_warps_experiment.log: the workers' chain
-//        does not shorten when the tensor pipe's operand reads go away.  Git history: eff5589 and its successor.)
+//        does not shorten when the tensor pipe's operand reads go away.  Git history: eff5589 and its successor.  Likewise measured
+//        and dropped: a second X buffer (9.0 ms), S1 / S2 as row rings without carry copies and three of the five barriers per step
+//        (9.5 ms, profiles/r02zh_block1_rings_xbuf2_experiment.log), the first convolution queued behind the second one (9.1 ms).)
 template <int CIN_, int COUT_, int CPOOL_, int S_, bool RELU_OUT_, int CTAS_, int NEW_, bool CONV0_ = false, int ISS_ = 1, int XBUF_ = 1, bool PREC_ = false,
           bool UF2_ = false>
 struct FB {
@@ -632,8 +634,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     for (int t = 0; t < G::N2; ++t) { const int p = G::P2_0 + 128 * t + row; y2[t] = p / G::WP; c2[t] = p - y2[t] * G::WP; }
 
     // pooling epilogue of global step gp: max-pool (3,2)/2 + residual add (+ ReLU) -> global
-    // prb2: ring position of S2's row 0 in that step (UF2: S1 / S2 rows live in rings, nothing is carried by copying)
-    auto pool_store = [&](long long gp, long long pb, int pwo0, int pa, int prb2) {
+    auto pool_store = [&](long long gp, long long pb, int pwo0, int pa) {
       mbar_wait(&bars[G::B_R + (int)(gp & 1)], (uint32_t)((gp >> 1) & 1));
       tc_fence_after();
       if (has0) {
@@ -659,14 +660,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
               for (int i = 0; i < 8; ++i) y[i] = -INFINITY;
 #pragma unroll
               for (int q = 0; q < 6; ++q) {
-                int off;                                                        // bytes from s2 (which points at row 2 q_i of the linear layout)
-                if constexpr (G::UF2) {
-                  int rr = prb2 + 2 * q_i + (q >> 1);                           // ring row of S2 row 2 q_i + dy
-                  rr -= rr >= G::S + 1 ? G::S + 1 : 0;
-                  off = ((rr - 2 * q_i) * (G::WP / 2) + (q & 1) * G::S2HALF) * 16;
-                } else {
-                  off = ((q >> 1) * (G::WP / 2) + (q & 1) * G::S2HALF) * 16;
-                }
+                const uint32_t off = (uint32_t)((q >> 1) * (G::WP / 2) + (q & 1) * G::S2HALF) * 16;
                 fmax8_split(y, *reinterpret_cast<const uint4*>(s2 + off), *reinterpret_cast<const uint4*>(s2 + G::S2_LO + off));
               }
 #pragma unroll
@@ -713,7 +707,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
 
     long long g = 0;
     long long prev_b = 0;
-    int prev_wo0 = 0, prev_a = 0, prev_rb2 = 0;
+    int prev_wo0 = 0, prev_a = 0;
     bool prev_carry = false;
     for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
       const long long b = item / n_strips;
@@ -724,17 +718,6 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       for (int step = 0; step < n_steps; ++step, ++g) {
         const int a = step * G::S - 2;
         const uint32_t par = (uint32_t)(g & 1);
-        // UF2: S1 (S + 2 rows) and S2 (S + 1 rows) are row RINGS - the rows a step shares with the next one stay where they are and
-        // the step's row 0 moves on by S; the carry copies and their two barriers (1.4 k + 0.5 k of a 9 k-cycle step) are gone
-        const int rb1 = G::UF2 ? (step * G::S) % (G::S + 2) : 0, rb2 = G::UF2 ? (step * G::S) % (G::S + 1) : 0;
-        if constexpr (G::UF2) {
-          if (step == 0) {   // rows above the image (the two rows before this item's first row) are zero for the second convolution
-            for (int i = tid; i < G::NQ * 2 * G::WP; i += G::NWORK) {
-              const int gq = i / (2 * G::WP), px = i - gq * 2 * G::WP;
-              *reinterpret_cast<uint4*>(smem + G::OFF_S1 + gq * G::LBO_S1 + px * 16) = make_uint4(0, 0, 0, 0);
-            }
-          }
-        }
         // ---- epilogue 1: ReLU, zero outside the image ("same" padding of the second convolution) -> S1 ----
 #pragma unroll
         for (int t = 0; t < G::N1; ++t) {
@@ -754,9 +737,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
               if constexpr (G::UF2) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] = inimg ? fmaxf(v[i], 0.f) : 0.f;
-                int yr = rb1 + y1[t];
-                yr -= yr >= G::S + 2 ? G::S + 2 : 0;
-                unsigned char* dq = smem + G::OFF_S1 + (2 * g0) * G::LBO_S1 + (yr * G::WP + c1[t]) * 16;     // quads 2 g0 .. 2 g0 + 3, ring row
+                unsigned char* dq = smem + G::OFF_S1 + (2 * g0) * G::LBO_S1 + p1 * 16;     // quads 2 g0 .. 2 g0 + 3
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
                   if (q < 2 || has1) *reinterpret_cast<float4*>(dq + q * G::LBO_S1) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
@@ -793,11 +774,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
 #pragma unroll
             for (int t = 0; t < 9; ++t) k[t] = kw[t * (G::NP / 4)];
             const unsigned char* s1q = smem + G::OFF_S1 + q * G::LBO_S1;
-            auto ld = [&](int y, int x) {
-              int yr = rb1 + y;                                      // ring row
-              yr -= yr >= G::S + 2 ? G::S + 2 : 0;
-              return *reinterpret_cast<const float4*>(s1q + (yr * G::WP + x) * 16);
-            };
+            auto ld = [&](int y, int x) { return *reinterpret_cast<const float4*>(s1q + (y * G::WP + x) * 16); };
             float4 w[3][3];
 #pragma unroll
             for (int y = 0; y < 2; ++y)
@@ -835,10 +812,10 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         // ---- previous step: pool + store while the tensor pipe runs this step's second convolution ----
         if (warp == 0) FB_TRACE(20, g);
         if (g > 0) {
-          pool_store(g - 1, prev_b, prev_wo0, prev_a, prev_rb2);
+          pool_store(g - 1, prev_b, prev_wo0, prev_a);
           if (warp == 0) FB_TRACE(21, g);
           worker_sync<G::NWORK>();   // pooling has finished reading S2
-          if (!G::UF2 && prev_carry) {
+          if (prev_carry) {
             // all loads of a thread first, then its stores (one shared-memory round trip instead of one per element)
             constexpr int kN2 = G::PL * G::NG * G::WP, kIt2 = (kN2 + G::NWORK - 1) / G::NWORK;
             unsigned char* cp2[kIt2];
@@ -873,9 +850,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
             const bool inimg = hh >= 0 && hh < img_rows && ww >= 0 && ww < W;
             if (p2 < (G::S + 1) * G::WP) {
               const uint4 ninf = make_uint4(0xFC00FC00u, 0xFC00FC00u, 0xFC00FC00u, 0xFC00FC00u);
-              int yr2 = rb2 + y2[t];                                   // UF2: ring row
-              yr2 -= yr2 >= G::S + 1 ? G::S + 1 : 0;
-              unsigned char* dst = smem + G::OFF_S2 + g0 * G::LBO_S2 + ((c2[t] & 1) * G::S2HALF + (G::UF2 ? yr2 : y2[t]) * (G::WP / 2) + (c2[t] >> 1)) * 16;
+              unsigned char* dst = smem + G::OFF_S2 + g0 * G::LBO_S2 + ((c2[t] & 1) * G::S2HALF + y2[t] * (G::WP / 2) + (c2[t] >> 1)) * 16;
               if constexpr (G::PREC) {
                 const uint4 z = make_uint4(0, 0, 0, 0);
                 uint4 hi, lo;
@@ -896,13 +871,11 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         }
         tc_fence_before();
         if (warp == 0) FB_TRACE(39, g);
-        // UF2: no barrier here - the next step's barrier after epilogue 1 orders these S2 writes before the pooling that reads them,
-        // and every warp has left its depthwise pass (the only reader of S1) before any accumulator of this step completed
-        if constexpr (!G::UF2) worker_sync<G::NWORK>();   // every worker has seen the second convolution complete: S1 is free, S2 is written
+        worker_sync<G::NWORK>();   // every worker has seen the second convolution complete: S1 is free, S2 is written
         if (warp == 0) FB_TRACE(40, g);
         // ---- carry the S1 overlap rows into the next step (rows above the next strip's first row are zero) ----
         const bool carry = step + 1 < n_steps;
-        if (!G::UF2 && g + 1 < total_steps) {
+        if (g + 1 < total_steps) {
           constexpr int kCarryPlanes = G::UF2 ? G::NQ : G::PL * G::NG;
           constexpr int kN1 = kCarryPlanes * 2 * G::WP, kIt1 = (kN1 + G::NWORK - 1) / G::NWORK;
           unsigned char* cp1[kIt1];
@@ -921,11 +894,10 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
           worker_sync<G::NWORK>();   // carried rows in place before epilogue 1 overwrites their source rows
         }
         if (warp == 0) FB_TRACE(41, g);
-        prev_b = b; prev_wo0 = wo0; prev_a = a; prev_carry = carry; prev_rb2 = rb2;
+        prev_b = b; prev_wo0 = wo0; prev_a = a; prev_carry = carry;
       }
     }
-    if constexpr (G::UF2) worker_sync<G::NWORK>();   // the last step's S2 is written
-    if (g > 0) pool_store(g - 1, prev_b, prev_wo0, prev_a, prev_rb2);
+    if (g > 0) pool_store(g - 1, prev_b, prev_wo0, prev_a);
   }
   tc_fence_before();
   __syncthreads();
