@@ -334,11 +334,13 @@ def main() -> None:
         table_step()               # first call: model directory -> weights on the device; later calls reuse the cached model
     barrier()
     le0 = ctx.timings()["kernel_launches"]
+    cpu0 = time.process_time()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         table_step()
     barrier()
     t_e2e = max_over_ranks(time.perf_counter() - t0)
+    host_cpu_s = max_over_ranks(time.process_time() - cpu0)   # user + system CPU time of this rank's process (all its threads)
     launches_e2e = ctx.timings()["kernel_launches"] - le0
     clocks = sampler.stop()   # sampled every 50 ms across both timed regions (and the short warm-up between them)
     rows_total = args.rows_per_gpu * world
@@ -419,6 +421,10 @@ def main() -> None:
                     "what": f"orcai_b200.predict.predict(TABLE.csv, output_path=DIR): {rows_total} rows of 1-h WAV files on disk ({n_files} distinct files) -> "
                             f"{rows_total} label files per step; every rank = one GPU's worker process taking its longest-first share (RANK / WORLD_SIZE)",
                     "recordings_per_step": rows_total, "label_files_written_rank0": label_files,
+                    "host_cpu_ms_per_recording": 1e3 * host_cpu_s / (args.rows_per_gpu * args.steps), "host_cores": len(os.sched_getaffinity(0)),
+                    "host_note": "CPU time of one rank's process per recording it annotates (max over ranks), mostly the read of the 346 MB file into the "
+                                 "page-locked buffer; N ranks need N x that per device-time-per-recording of cores - beyond the host's core count the "
+                                 "e2e arm is host-bound, the device-resident `value` is not",
                     "limiter": "per recording: WAV read + decode on 3 loader threads, one H2D copy of 346 MB overlapped with the previous recording's kernels, "
                                "device time, label table + label file on a writer thread; the slowest of these per recording bounds the rate"},
             "gpu_launches": int(launches), "gpu_launches_e2e": int(launches_e2e),
