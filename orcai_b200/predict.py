@@ -552,14 +552,22 @@ def predict(
     # A table on several devices: one worker PROCESS per GPU (own interpreter: the per-recording host work - WAV decode, label
     # table, label file - does not serialise on one interpreter lock; measured round 1: threads reached 2.1x on 8 GPUs).  The
     # workers live for the whole table, so their start-up (CUDA context, model, page-locked buffers) is paid once; tables too
-    # short to amortise it (fewer than 2 rows per device) and ORCAI_B200_TABLE_PROCESSES=0 use worker THREADS instead.
-    n_rows_hint = None
+    # short to amortise it and ORCAI_B200_TABLE_PROCESSES=0 use worker THREADS instead (ORCAI_B200_TABLE_PROCESSES=1 forces processes).
+    # processes pay ~5 s of start-up each (in parallel): worth it from ~12 s of single-GPU work on, i.e. ~100 GB of WAV files
+    procs_default = "0"
     if is_table and len(devices) > 1 and not _worker:
         try:
-            n_rows_hint = sum(1 for _ in open(recording_path)) - 1
-        except OSError:
-            n_rows_hint = None
-    procs_default = "1" if (n_rows_hint is not None and n_rows_hint >= 2 * len(devices)) else "0"
+            t = pd.read_csv(recording_path, usecols=["base_dir_recording", "rel_recording_path"])
+            base = str(base_dir_recording) if base_dir_recording is not None else None
+            total = 0
+            for b, r in zip(t["base_dir_recording"], t["rel_recording_path"]):
+                try:
+                    total += os.path.getsize(Path(base if base is not None else b).joinpath(r))
+                except OSError:
+                    pass
+            procs_default = "1" if total >= 100e9 else "0"
+        except Exception:  # noqa: BLE001 - an unreadable table fails below, in the normal path
+            procs_default = "0"
     multi = is_table and len(devices) > 1 and not _worker and os.environ.get("ORCAI_B200_TABLE_PROCESSES", procs_default) == "1"
     if not multi:
         devices = list(dict.fromkeys(devices))   # one context per device in this process: a device listed twice counts once
