@@ -443,3 +443,40 @@ def test_zarr_v3_store_conforms_to_the_specification(tmp_path):
     got = io.read_zarr(alt)
     assert (got[:2000] == 0).all()
     np.testing.assert_array_equal(got[2000:], b[2000:])
+
+
+def test_model_directory_is_loaded_once_per_process(tmp_path, monkeypatch):
+    """load_orcai_model keeps a per-process cache keyed by (directory, file sizes / mtimes, device, arithmetic): table after table
+    reuses the bound model, an edited weight file is re-read."""
+    from orcai_b200 import model as model_mod
+    from orcai_b200.weights import save_npz, synthetic_weights
+
+    P, S = runtime.bundled_parameters()
+    d = tmp_path / "orcai-V1"
+    d.mkdir()
+    (d / "orcai_parameter.json").write_text(json.dumps(P))
+    (d / "model_shape.json").write_text(json.dumps(S))
+    save_npz(synthetic_weights(P, S, seed=1), d / "orcai-v1.weights.npz")
+    made = []
+
+    class FakeModel:
+        def __init__(self, orcai_parameter, shape, W, device=None, precision=None):
+            made.append((float(W["dense2/bias"][0]), device))
+
+    monkeypatch.setattr(model_mod, "OrcaiModel", FakeModel)
+    monkeypatch.delenv("ORCAI_B200_PRECISION", raising=False)
+    io._MODEL_CACHE.clear()
+    m1, p1, s1 = io.load_orcai_model(d, device=0)
+    m2, _, _ = io.load_orcai_model(d, device=0)
+    assert m1 is m2 and len(made) == 1 and p1 == P and s1 == S
+    io.load_orcai_model(d, device=1)                                   # another device: its own model
+    monkeypatch.setenv("ORCAI_B200_PRECISION", "reference")            # another arithmetic: its own model
+    io.load_orcai_model(d, device=0)
+    assert len(made) == 3
+    W2 = synthetic_weights(P, S, seed=2)
+    save_npz(W2, d / "orcai-v1.weights.npz")                           # edited weights are re-read
+    import os as _os
+    _os.utime(d / "orcai-v1.weights.npz", ns=(1, 1))
+    io.load_orcai_model(d, device=0)
+    assert len(made) == 4 and made[-1][0] == float(W2["dense2/bias"][0])
+    io._MODEL_CACHE.clear()
