@@ -404,7 +404,12 @@ def main() -> None:
                                         if args.net_path == 4 else "") + "; its bound is the shared-memory operand bandwidth of the tensor pipe, see DESIGN.md"}
         else:
             roofline_main = roofline_net
-        agg_bytes = (T // 16) * (7 + 1) * 8
+        # read back per recording of the table run (no probabilities file asked for -> no aggregates): the segment count, the
+        # statistics and the speculative copy of the first min(capacity, 32768) segments (orcai_predict_resident_begin)
+        seg_cap = max(1024, min(7 * ((T // 16 + 1) // 2), 1 << 22))
+        d2h_per_recording = 8 + 48 + 20 * min(seg_cap, 32768)
+        ts = dict(opredict.TABLE_STATS)
+        per = max(1, ts.get("rows", 0))
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * t_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -417,16 +422,21 @@ def main() -> None:
             "stage_ms": {k: v / args.steps for k, v in stage.items()},
             "net_stage_ms_first_chunk": dict(zip(STAGES, [round(v, 4) for v in net_stage[:11]])) | {"snippets": int(net_stage[15])},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(pcm.nbytes) * rows_total,
-                    "d2h_bytes_per_step": int(agg_bytes + 20 * n_segments) * rows_total, "ms_per_step": 1e3 * t_e2e / args.steps,
+                    "d2h_bytes_per_step": int(d2h_per_recording) * rows_total, "ms_per_step": 1e3 * t_e2e / args.steps,
                     "what": f"orcai_b200.predict.predict(TABLE.csv, output_path=DIR): {rows_total} rows of 1-h WAV files on disk ({n_files} distinct files) -> "
                             f"{rows_total} label files per step; every rank = one GPU's worker process taking its longest-first share (RANK / WORLD_SIZE)",
                     "recordings_per_step": rows_total, "label_files_written_rank0": label_files,
                     "host_cpu_ms_per_recording": 1e3 * host_cpu_s / (args.rows_per_gpu * args.steps), "host_cores": len(os.sched_getaffinity(0)),
+                    "main_thread_ms_per_recording_rank0": {"waiting_for_the_device": 1e3 * ts.get("wait_device_s", 0.0) / per,
+                                                           "waiting_for_a_loader_thread": 1e3 * ts.get("wait_loader_s", 0.0) / per,
+                                                           "file_read_on_a_loader_thread": 1e3 * ts.get("load_s", 0.0) / per,
+                                                           "waiting_for_the_writer_at_table_end_ms": 1e3 * ts.get("wait_writer_s", 0.0)},
                     "host_note": "CPU time of one rank's process per recording it annotates (max over ranks), mostly the read of the 346 MB file into the "
                                  "page-locked buffer; N ranks need N x that per device-time-per-recording of cores - beyond the host's core count the "
                                  "e2e arm is host-bound, the device-resident `value` is not",
                     "limiter": "per recording: WAV read + decode on 3 loader threads, one H2D copy of 346 MB overlapped with the previous recording's kernels, "
-                               "device time, label table + label file on a writer thread; the slowest of these per recording bounds the rate"},
+                               "device time (recording k+1 is enqueued before recording k is collected: orcai_predict_resident_begin / _end), label table + "
+                               "label file on a writer thread; the slowest of these per recording bounds the rate"},
             "gpu_launches": int(launches), "gpu_launches_e2e": int(launches_e2e),
             "parity": parity,
             "clocks": clocks,

@@ -145,6 +145,20 @@ int orcai_threshold_segments(orcai_ctx* ctx, const double* agg_host, const doubl
 int orcai_predict_resident(orcai_ctx* ctx, double threshold, orcai_spec_stats* stats,
                            double* agg_out, double* cnt_out, int32_t* seg_label, int64_t* seg_start,
                            int64_t* seg_stop, int64_t seg_capacity, int64_t* n_segments);
+/* The same call in two halves, for a caller that annotates recording after recording (the table loop, predict.py:733-755):
+ * _begin enqueues everything for the resident recording - kernels and the read-back of the results into page-locked staging
+ * owned by the context - and returns at once; _end waits (the host thread sleeps) for the OLDEST begun call and hands out its
+ * results.  Up to two calls may be in flight, so recording k+1 is queued on the device before the host has collected recording
+ * k and the device never idles while the host thread builds label tables or waits for the interpreter lock.  Between _begin and
+ * its _end only orcai_prefetch_pcm, orcai_swap_pcm and this pair may be called on the context; the stage timings of
+ * orcai_get_timings are not updated.  `want_agg` != 0 makes the aggregates available to _end (agg_out / cnt_out may then be
+ * non-null).  _end returns ORCAI_ERR_CAPACITY (n_segments = the count needed) when either capacity was too small: the
+ * recording has to be annotated again with a larger one. */
+int orcai_predict_resident_begin(orcai_ctx* ctx, double threshold, int32_t want_agg, int64_t seg_capacity);
+int orcai_predict_resident_end(orcai_ctx* ctx, orcai_spec_stats* stats, double* agg_out, double* cnt_out,
+                               int32_t* seg_label, int64_t* seg_start, int64_t* seg_stop,
+                               int64_t seg_capacity, int64_t* n_segments);
+int orcai_predict_in_flight(const orcai_ctx* ctx);   /* begun and not yet collected calls (0..2) */
 /* upload + orcai_predict_resident. */
 int orcai_predict_pcm(orcai_ctx* ctx, const void* pcm_host, int32_t dtype, int64_t n_samples,
                       double threshold, orcai_spec_stats* stats, double* agg_out, double* cnt_out,

@@ -105,6 +105,9 @@ _SIGNATURES = {
     "orcai_postprocess": (C.c_int, [_P, _P, C.c_int64, C.c_int64, C.c_double, _P, _P, _P, _P, _P, C.c_int64, C.POINTER(C.c_int64)]),
     "orcai_threshold_segments": (C.c_int, [_P, _P, _P, C.c_int64, C.c_int32, C.c_double, _P, _P, _P, C.c_int64, C.POINTER(C.c_int64)]),
     "orcai_predict_resident": (C.c_int, [_P, C.c_double, C.POINTER(SpecStats), _P, _P, _P, _P, _P, C.c_int64, C.POINTER(C.c_int64)]),
+    "orcai_predict_resident_begin": (C.c_int, [_P, C.c_double, C.c_int32, C.c_int64]),
+    "orcai_predict_resident_end": (C.c_int, [_P, C.POINTER(SpecStats), _P, _P, _P, _P, _P, C.c_int64, C.POINTER(C.c_int64)]),
+    "orcai_predict_in_flight": (C.c_int, [_P]),
     "orcai_predict_pcm": (C.c_int, [_P, _P, C.c_int32, C.c_int64, C.c_double, C.POINTER(SpecStats), _P, _P, _P, _P, _P, C.c_int64, C.POINTER(C.c_int64)]),
     "orcai_set_option": (C.c_int, [_P, C.c_char_p, C.c_int64]),
     "orcai_calibrate": (C.c_int, [_P, C.c_int64]),
@@ -447,6 +450,33 @@ class Context:
             self._check(rc)
             k = int(n.value)
             return lab[:k], sta[:k], sto[:k]
+
+    def predict_begin(self, n_samples: int, threshold: float = 0.5, want_agg: bool = True):
+        """Enqueue the whole annotation of the resident recording (``swap_pcm`` / ``upload_pcm``) and return at once -> a token for
+        ``predict_end``.  Up to two calls may be in flight; ``predict_end`` collects them oldest first (orcai_predict_resident_begin)."""
+        T = self.lib.orcai_num_frames(int(n_samples), self.params.hop)
+        ds = 1 << self.params.n_blocks
+        S, L = T // ds, self.params.n_labels
+        cap = max(1024, min(L * ((S + 1) // 2), 1 << 22))
+        self._check(self.lib.orcai_predict_resident_begin(self._h, float(threshold), 1 if want_agg else 0, cap))
+        return (S, L, cap, bool(want_agg))
+
+    def predict_end(self, token):
+        """Wait (sleeping) for the oldest begun call -> what ``predict_pcm`` returns."""
+        S, L, cap, want_agg = token
+        agg = np.empty((S, L), np.float64) if want_agg else None
+        cnt = np.empty(S, np.float64) if want_agg else None
+        st = SpecStats()
+        lab = np.empty(cap, np.int32)
+        sta = np.empty(cap, np.int64)
+        sto = np.empty(cap, np.int64)
+        n = C.c_int64(0)
+        self._check(self.lib.orcai_predict_resident_end(self._h, C.byref(st), _ptr(agg), _ptr(cnt), _ptr(lab), _ptr(sta), _ptr(sto), cap, C.byref(n)))
+        k = int(n.value)
+        return st, agg, cnt, lab[:k].copy(), sta[:k].copy(), sto[:k].copy()
+
+    def predict_in_flight(self) -> int:
+        return int(self.lib.orcai_predict_in_flight(self._h))
 
     def postprocess(self, preds: np.ndarray, n_frames: int, threshold: float = 0.5, want_agg: bool = True):
         p = np.ascontiguousarray(preds, dtype=np.float32)

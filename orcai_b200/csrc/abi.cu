@@ -214,6 +214,12 @@ void orcai_destroy(orcai_ctx* c) {
   if (c->d_post) cudaFree(c->d_post);
   if (c->h_pin) cudaFreeHost(c->h_pin);
   if (c->h_small) cudaFreeHost(c->h_small);
+  for (auto& sl : c->slot) {
+    if (sl.d_post) cudaFree(sl.d_post);
+    if (sl.h_pin) cudaFreeHost(sl.h_pin);
+    if (sl.done) cudaEventDestroy(sl.done);
+  }
+  if (c->ev_block) cudaEventDestroy(c->ev_block);
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
   if (c->stream) cudaStreamDestroy(c->stream);
   cudaGetLastError();
@@ -479,6 +485,56 @@ int orcai_predict_resident(orcai_ctx* c, double threshold, orcai_spec_stats* sta
   c->tm.total_ms = elapsed(c, EV_H2D, EV_POST);
   return rc != ORCAI_OK ? rc : rc2;
 }
+
+int orcai_predict_resident_begin(orcai_ctx* c, double threshold, int32_t want_agg, int64_t seg_capacity) {
+  if (!c || seg_capacity < 0) return ORCAI_ERR_ARG;
+  if (c->async_pending >= kAsyncDepth) ORCAI_FAIL(c, ORCAI_ERR_STATE, "%d predict calls already in flight (orcai_predict_resident_end)", kAsyncDepth);
+  ORCAI_CUDA(c, cudaSetDevice(c->device));
+  AsyncSlot* s = &c->slot[(c->async_head + c->async_pending) % kAsyncDepth];
+  if (!s->done) ORCAI_CUDA(c, cudaEventCreateWithFlags(&s->done, cudaEventBlockingSync | cudaEventDisableTiming));
+  ORCAI_CHECK(spectrogram_stages(c, 0));
+  const int64_t N = orcai_num_snippets(c->T, c->p.snippet_len);
+  if (N <= 0) ORCAI_FAIL(c, ORCAI_ERR_TOO_SHORT, "recording has %lld frames, shorter than one snippet of %d", (long long)c->T, c->p.snippet_len);
+  ORCAI_CHECK(ensure_preds(c, N));
+  ORCAI_CHECK(net_forward(c, c->d_raw, 0, 0, N, c->d_preds));
+  ORCAI_CHECK(postprocess_begin(c, c->d_preds, N, c->T, threshold, want_agg != 0, seg_capacity, s));
+  ORCAI_CUDA(c, cudaMemcpyAsync(static_cast<unsigned char*>(s->h_pin) + kStageStatsOff,
+                                reinterpret_cast<const unsigned char*>(c->d_sel) + offsetof(SelectState, rank), sizeof(StatsTail),
+                                cudaMemcpyDeviceToHost, c->stream));
+  ORCAI_CUDA(c, cudaEventRecord(s->done, c->stream));
+  s->busy = true;
+  c->async_pending++;
+  return ORCAI_OK;
+}
+
+int orcai_predict_resident_end(orcai_ctx* c, orcai_spec_stats* stats, double* agg_out, double* cnt_out, int32_t* seg_label,
+                               int64_t* seg_start, int64_t* seg_stop, int64_t seg_capacity, int64_t* n_segments) {
+  if (!c || !n_segments || seg_capacity < 0) return ORCAI_ERR_ARG;
+  if (c->async_pending <= 0) ORCAI_FAIL(c, ORCAI_ERR_STATE, "no predict call in flight (orcai_predict_resident_begin)");
+  ORCAI_CUDA(c, cudaSetDevice(c->device));
+  AsyncSlot* s = &c->slot[c->async_head];
+  // the slot is released whatever happens below: a failed collection must not wedge the ring
+  c->async_head = (c->async_head + 1) % kAsyncDepth;
+  c->async_pending--;
+  s->busy = false;
+  ORCAI_CUDA(c, cudaEventSynchronize(s->done));
+  if (stats) {
+    StatsTail t;
+    memcpy(&t, static_cast<const unsigned char*>(s->h_pin) + kStageStatsOff, sizeof t);
+    const int nb = c->p.band_hi - c->p.band_lo;
+    const unsigned long long n = (unsigned long long)s->T * (unsigned long long)nb;
+    stats->n_frames = s->T;
+    memcpy(&stats->ref_power, &t.pmax_bits, 4);
+    stats->db_ref = t.db_ref;
+    stats->lo = t.lo;
+    stats->hi = t.hi;
+    stats->rank_lo = (int64_t)nearbyint((double)(n - 1) * c->p.q_lo);
+    stats->rank_hi = (int64_t)nearbyint((double)(n - 1) * c->p.q_hi);
+  }
+  return postprocess_end(c, s, agg_out, cnt_out, seg_label, seg_start, seg_stop, seg_capacity, n_segments);
+}
+
+int orcai_predict_in_flight(const orcai_ctx* c) { return c ? c->async_pending : 0; }
 
 /* ---- time chunks of ONE recording (orcai_b200/timesplit.py) ---------------------------------------- */
 int orcai_chunk_spectrogram(orcai_ctx* c, int64_t stat_row0, int64_t stat_row1, float* max_power_out) {

@@ -34,6 +34,22 @@ __device__ __forceinline__ float power_to_db(float p, bool precise) {
 
 struct NetWeights;                   // net.cu
 
+// One begun-but-not-collected predict call (orcai_predict_resident_begin / _end): its own post-processing scratch and
+// page-locked result staging, so that the next recording can be enqueued behind it before the host has read its results.
+struct AsyncSlot {
+  bool busy = false;
+  cudaEvent_t done = nullptr;                 // blocking-sync event: the host thread sleeps, it does not spin
+  void* d_post = nullptr; size_t post_cap = 0;
+  void* h_pin = nullptr;  size_t pin_cap = 0;
+  int64_t T = 0;
+  long long cap = 0, spec = 0, n_agg = 0, n_cnt = 0;
+  bool want_agg = false;
+  size_t o_lab = 0, o_sta = 0, o_sto = 0, o_agg = 0, o_cnt = 0;
+  const int* d_lab = nullptr; const long long* d_sta = nullptr; const long long* d_sto = nullptr;
+};
+constexpr int kAsyncDepth = 2;
+constexpr size_t kStageTotalOff = 0, kStageStatsOff = 64, kStageSegsOff = 256;   // layout of the head of a slot's staging
+
 struct Ctx {
   int device = 0;
   orcai_params p{};
@@ -66,6 +82,10 @@ struct Ctx {
   uint64_t launches = 0;
   int sm_count = 148;
   int stft_f64 = 1;                   // 1: float64 FFT (parity grade, default), 0: float32 FFT (fast variant)
+  // asynchronous predict calls in flight (oldest first: async_head)
+  AsyncSlot slot[kAsyncDepth];
+  int async_head = 0, async_pending = 0;
+  cudaEvent_t ev_block = nullptr;     // blocking-sync event behind wait_stream()
 };
 
 #define ORCAI_CUDA(ctx, call)                                                            \
@@ -132,6 +152,12 @@ int net_forward(Ctx* c, const float* d_in, int input_mode, int64_t first, int64_
 int launch_postprocess(Ctx* c, const float* d_preds, int64_t n_snippets, int64_t T, double threshold,
                        double* h_agg, double* h_cnt, int32_t* h_label, int64_t* h_start, int64_t* h_stop,
                        int64_t cap, int64_t* n_seg);
+// the same in two halves for orcai_predict_resident_begin / _end: everything (kernels and the copies into the slot's page-locked
+// staging) is enqueued by _begin; _end interprets the staging after the slot's `done` event
+int postprocess_begin(Ctx* c, const float* d_preds, int64_t n_snippets, int64_t T, double threshold, bool want_agg, int64_t cap, AsyncSlot* s);
+int postprocess_end(Ctx* c, AsyncSlot* s, double* h_agg, double* h_cnt, int32_t* h_label, int64_t* h_start, int64_t* h_stop,
+                    int64_t cap, int64_t* n_seg);
+int wait_stream(Ctx* c);   // like cudaStreamSynchronize(c->stream), but the host thread sleeps (blocking-sync event)
 int launch_threshold_segments(Ctx* c, const double* h_agg, const double* h_cnt, int64_t S, int L, double threshold,
                               int32_t* h_label, int64_t* h_start, int64_t* h_stop, int64_t cap, int64_t* n_seg);
 

@@ -249,7 +249,7 @@ int copy_out_results(Ctx* c, const PostBuffers& b, long long cap, int32_t* h_lab
   }
   if (h_agg) ORCAI_CUDA(c, cudaMemcpyAsync(pin + o_agg, b.agg, (size_t)n_agg * 8, cudaMemcpyDeviceToHost, c->stream));
   if (h_cnt) ORCAI_CUDA(c, cudaMemcpyAsync(pin + o_cnt, b.cnt, (size_t)n_cnt * 8, cudaMemcpyDeviceToHost, c->stream));
-  ORCAI_CUDA(c, cudaStreamSynchronize(c->stream));
+  ORCAI_CHECK(wait_stream(c));   // the long wait of a predict call: sleep, leave the core to the loader / writer threads
   unsigned long long total = 0;
   memcpy(&total, pin + o_tot, 8);
   if (h_agg) memcpy(h_agg, pin + o_agg, (size_t)n_agg * 8);
@@ -324,6 +324,110 @@ int launch_postprocess(Ctx* c, const float* d_preds, int64_t n_snippets, int64_t
   }
   ORCAI_CUDA(c, cudaGetLastError());
   return copy_out_results(c, b, cap, h_label, h_start, h_stop, n_seg, h_agg, h_cnt, total, g.S);
+}
+
+int postprocess_begin(Ctx* c, const float* d_preds, int64_t n_snippets, int64_t T, double threshold, bool want_agg, int64_t cap, AsyncSlot* s) {
+  const int ds = 1 << c->p.n_blocks;
+  PostGeom g;
+  g.S = T / ds;
+  g.N = n_snippets;
+  g.L = c->p.n_labels;
+  g.P = c->p.snippet_len / ds;
+  g.shift = (c->p.snippet_len / 2) / ds;
+  if (g.N < 1) ORCAI_FAIL(c, ORCAI_ERR_TOO_SHORT, "no snippets to aggregate");
+  if (g.shift < 1) ORCAI_FAIL(c, ORCAI_ERR_ARG, "snippet shift shorter than one output step");
+  long long max_overlap = (g.P + g.shift - 1) / g.shift;
+  if (max_overlap > g.N) max_overlap = g.N;
+  const double thr = threshold / (double)max_overlap;
+  const long long total = g.S * g.L;
+  const long long n_tiles = (total + kTile - 1) / kTile;
+  s->T = T; s->cap = cap; s->want_agg = want_agg; s->n_agg = total; s->n_cnt = g.S;
+  s->spec = std::min<long long>(cap, kSpecSegs);
+  auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  s->o_lab = kStageSegsOff;
+  s->o_sta = s->o_lab + up((size_t)s->spec * 4);
+  s->o_sto = s->o_sta + up((size_t)s->spec * 8);
+  s->o_agg = s->o_sto + up((size_t)s->spec * 8);
+  s->o_cnt = s->o_agg + (want_agg ? up((size_t)total * 8) : 0);
+  const size_t bytes = s->o_cnt + (want_agg ? up((size_t)g.S * 8) : 0);
+  if (bytes > s->pin_cap || !s->h_pin) {
+    if (s->h_pin) { ORCAI_CUDA(c, cudaFreeHost(s->h_pin)); s->h_pin = nullptr; s->pin_cap = 0; }
+    const size_t want = std::max<size_t>(bytes + bytes / 4, (size_t)1 << 20);
+    ORCAI_CUDA(c, cudaMallocHost(&s->h_pin, want));
+    s->pin_cap = want;
+  }
+  unsigned char* pin = static_cast<unsigned char*>(s->h_pin);
+  memset(pin + kStageTotalOff, 0, 8);
+  if (g.S == 0) { s->d_lab = nullptr; return ORCAI_OK; }
+  PostBuffers b;
+  {  // the slot's own scratch: the next recording's post-processing must not overwrite segments that are still to be read
+    std::swap(c->d_post, s->d_post);
+    std::swap(c->post_cap, s->post_cap);
+    const int rc = carve(c, n_tiles, cap, g.S, g.L, 0, want_agg, &b);
+    std::swap(c->d_post, s->d_post);
+    std::swap(c->post_cap, s->post_cap);
+    ORCAI_CHECK(rc);
+  }
+  s->d_lab = b.seg_label; s->d_sta = b.seg_start; s->d_sto = b.seg_stop;
+  MaskFromPreds m{d_preds, g, thr};
+  segments_scan_kernel<MaskFromPreds><<<(unsigned)n_tiles, kThreads, 0, c->stream>>>(
+      m, g.S, g.L, b.tile_state, b.scr, b.seg_label, b.seg_start, b.seg_stop, cap);
+  c->launches++;
+  if (want_agg) {
+    aggregate_kernel<<<c->sm_count * 4, 256, 0, c->stream>>>(d_preds, g, b.agg, b.cnt);
+    c->launches++;
+  }
+  ORCAI_CUDA(c, cudaGetLastError());
+  ORCAI_CUDA(c, cudaMemcpyAsync(pin + kStageTotalOff, &b.scr->total, 8, cudaMemcpyDeviceToHost, c->stream));
+  if (s->spec) {
+    ORCAI_CUDA(c, cudaMemcpyAsync(pin + s->o_lab, b.seg_label, (size_t)s->spec * 4, cudaMemcpyDeviceToHost, c->stream));
+    ORCAI_CUDA(c, cudaMemcpyAsync(pin + s->o_sta, b.seg_start, (size_t)s->spec * 8, cudaMemcpyDeviceToHost, c->stream));
+    ORCAI_CUDA(c, cudaMemcpyAsync(pin + s->o_sto, b.seg_stop, (size_t)s->spec * 8, cudaMemcpyDeviceToHost, c->stream));
+  }
+  if (want_agg) {
+    ORCAI_CUDA(c, cudaMemcpyAsync(pin + s->o_agg, b.agg, (size_t)total * 8, cudaMemcpyDeviceToHost, c->stream));
+    ORCAI_CUDA(c, cudaMemcpyAsync(pin + s->o_cnt, b.cnt, (size_t)g.S * 8, cudaMemcpyDeviceToHost, c->stream));
+  }
+  return ORCAI_OK;
+}
+
+int postprocess_end(Ctx* c, AsyncSlot* s, double* h_agg, double* h_cnt, int32_t* h_label, int64_t* h_start, int64_t* h_stop,
+                    int64_t cap, int64_t* n_seg) {
+  const unsigned char* pin = static_cast<const unsigned char*>(s->h_pin);
+  *n_seg = 0;
+  if ((h_agg || h_cnt) && !s->want_agg) ORCAI_FAIL(c, ORCAI_ERR_ARG, "aggregates requested from a call begun without want_agg");
+  unsigned long long total = 0;
+  memcpy(&total, pin + kStageTotalOff, 8);
+  if (h_agg) memcpy(h_agg, pin + s->o_agg, (size_t)s->n_agg * 8);
+  if (h_cnt) memcpy(h_cnt, pin + s->o_cnt, (size_t)s->n_cnt * 8);
+  const long long n_starts = (long long)(total >> 31), n_stops = (long long)(total & 0x7fffffffull);
+  if (n_starts != n_stops) ORCAI_FAIL(c, ORCAI_ERR_STATE, "segment scan inconsistent: %lld starts vs %lld stops", n_starts, n_stops);
+  *n_seg = n_starts;
+  if (n_starts > s->cap || n_starts > cap)
+    ORCAI_FAIL(c, ORCAI_ERR_CAPACITY, "segment capacity %lld too small, need %lld", (long long)std::min<long long>(s->cap, cap), n_starts);
+  const long long first = std::min(n_starts, s->spec);
+  if (first) {
+    memcpy(h_label, pin + s->o_lab, (size_t)first * 4);
+    memcpy(h_start, pin + s->o_sta, (size_t)first * 8);
+    memcpy(h_stop, pin + s->o_sto, (size_t)first * 8);
+  }
+  if (n_starts > s->spec) {
+    // the rest sits in the slot's own scratch (complete: `done` has passed); fetched on the copy stream, the compute stream may
+    // already hold the next recording
+    const long long rest = n_starts - s->spec;
+    ORCAI_CUDA(c, cudaMemcpyAsync(h_label + s->spec, s->d_lab + s->spec, (size_t)rest * 4, cudaMemcpyDeviceToHost, c->copy_stream));
+    ORCAI_CUDA(c, cudaMemcpyAsync(h_start + s->spec, s->d_sta + s->spec, (size_t)rest * 8, cudaMemcpyDeviceToHost, c->copy_stream));
+    ORCAI_CUDA(c, cudaMemcpyAsync(h_stop + s->spec, s->d_sto + s->spec, (size_t)rest * 8, cudaMemcpyDeviceToHost, c->copy_stream));
+    ORCAI_CUDA(c, cudaStreamSynchronize(c->copy_stream));
+  }
+  return ORCAI_OK;
+}
+
+int wait_stream(Ctx* c) {
+  if (!c->ev_block) ORCAI_CUDA(c, cudaEventCreateWithFlags(&c->ev_block, cudaEventBlockingSync | cudaEventDisableTiming));
+  ORCAI_CUDA(c, cudaEventRecord(c->ev_block, c->stream));
+  ORCAI_CUDA(c, cudaEventSynchronize(c->ev_block));
+  return ORCAI_OK;
 }
 
 int launch_threshold_segments(Ctx* c, const double* h_agg, const double* h_cnt, int64_t S, int L, double threshold,

@@ -16,6 +16,7 @@ from __future__ import annotations
 import gzip
 import os
 import threading
+import time
 from concurrent.futures import ThreadPoolExecutor
 from importlib.resources import files
 from pathlib import Path
@@ -301,6 +302,7 @@ def predict_wav(
 # ---------------------------------------------------------------------------------------------
 # writers (predict.py:343-364, 474-531)
 # ---------------------------------------------------------------------------------------------
+TABLE_STATS: dict = {}   # host-side accounting of this process' last table run (bench.py reports it): where its main thread waited
 _SECONDS_TEXT: dict[float, dict[int, str]] = {}   # delta_t -> {frame index: text of its time in seconds}
 _SECONDS_LOCK = threading.Lock()                  # writer threads of several GPUs share the cache
 
@@ -371,6 +373,35 @@ def save_prediction_probabilities(
 # ---------------------------------------------------------------------------------------------
 # drivers (predict.py:534-757)
 # ---------------------------------------------------------------------------------------------
+def _resolved_output_path(recording_path: Path, channel: int, orcai_parameter: dict, output_path, overwrite: bool, msgr):
+    """Where the label file goes (None: nowhere); an existing file is an error unless ``overwrite`` (predict.py:569-583)."""
+    if output_path is None:
+        return None
+    if output_path == "default":
+        output_path = recording_path.with_name(f"{recording_path.stem}_c{channel}_{orcai_parameter['name']}_predicted.txt")
+    else:
+        output_path = Path(output_path)
+    msgr.info(f"Output file: {output_path}")
+    if output_path.exists():
+        if overwrite:
+            msgr.warning(f"Output file {output_path} already exists. Overwriting.")
+        else:
+            raise FileExistsError(f"Annotation file already exists: {output_path}")
+    return output_path
+
+
+def _host_tail(aggregated_predictions, lab, sta, sto, delta_t, orcai_parameter, output_path, save_probabilities, call_duration_limits,
+               label_suffix, msgr):
+    """Segments of the device scan -> label table -> duration filter -> files (predict.py:585-611)."""
+    predicted_labels = _labels_of(lab, sta, sto, orcai_parameter, label_suffix, msgr)
+    msgr.success("Prediction finished.")
+    if call_duration_limits is not None:
+        predicted_labels = filter_predictions(predicted_labels, delta_t=delta_t, call_duration_limits=call_duration_limits, label_suffix=label_suffix, msgr=msgr)
+    save_predictions(predicted_labels=predicted_labels, output_path=output_path, delta_t=delta_t, msgr=msgr)
+    if save_probabilities:
+        save_prediction_probabilities(aggregated_predictions, orcai_parameter, delta_t, output_path, msgr=msgr)
+
+
 def _predict_and_save(
     recording_path: Path | str,
     channel: int,
@@ -384,41 +415,15 @@ def _predict_and_save(
     label_suffix: str = "*",
     msgr: Messenger = Messenger(verbosity=0),
     progressbar: tqdm = None,
-    _resident_samples=None,
     _time_split: bool = False,
-    _writer=None,
 ):
-    """``_writer`` (table mode): an executor that takes the host-side tail (label table, filter, files) off the thread that
-    drives the GPU; the future is returned so that the caller can report a failure against the right row."""
     recording_path = Path(recording_path)
-    if output_path is not None:
-        if output_path == "default":
-            output_path = recording_path.with_name(f"{recording_path.stem}_c{channel}_{orcai_parameter['name']}_predicted.txt")
-        else:
-            output_path = Path(output_path)
-        msgr.info(f"Output file: {output_path}")
-        if output_path.exists():
-            if overwrite:
-                msgr.warning(f"Output file {output_path} already exists. Overwriting.")
-            else:
-                raise FileExistsError(f"Annotation file already exists: {output_path}")
-
+    output_path = _resolved_output_path(recording_path, channel, orcai_parameter, output_path, overwrite, msgr)
     _stats, aggregated_predictions, lab, sta, sto, delta_t = _device_predict(
-        recording_path, channel, model, orcai_parameter, shape, msgr, progressbar, _resident_samples, _time_split
+        recording_path, channel, model, orcai_parameter, shape, msgr, progressbar, None, _time_split
     )
-
-    def finish():
-        predicted_labels = _labels_of(lab, sta, sto, orcai_parameter, label_suffix, msgr)
-        msgr.success("Prediction finished.")
-        if call_duration_limits is not None:
-            predicted_labels = filter_predictions(predicted_labels, delta_t=delta_t, call_duration_limits=call_duration_limits, label_suffix=label_suffix, msgr=msgr)
-        save_predictions(predicted_labels=predicted_labels, output_path=output_path, delta_t=delta_t, msgr=msgr)
-        if save_probabilities:
-            save_prediction_probabilities(aggregated_predictions, orcai_parameter, delta_t, output_path, msgr=msgr)
-
-    if _writer is not None:
-        return _writer.submit(finish)
-    finish()
+    _host_tail(aggregated_predictions, lab, sta, sto, delta_t, orcai_parameter, output_path, save_probabilities, call_duration_limits,
+               label_suffix, msgr)
     return None
 
 
@@ -636,48 +641,33 @@ def predict(
         else:
             msgr.error(text)
 
-    def run_row(i, mdl, pb, resident=None, writer=None):
-        """-> future of the row's host-side tail (or None); failures are reported per row, like the reference loop (predict.py:752-755)"""
-        try:
-            if isinstance(resident, BaseException):
-                raise resident
-            return _predict_and_save(
-                recording_path=row_path(i),
-                channel=int(recording_table.loc[i, "channel"]),
-                model=mdl,
-                orcai_parameter=orcai_parameter,
-                shape=shape,
-                output_path=out_path_of[i],
-                overwrite=overwrite,
-                save_probabilities=save_probabilities,
-                call_duration_limits=call_duration_limits,
-                label_suffix=label_suffix,
-                msgr=Messenger(verbosity=0),
-                progressbar=pb,
-                _resident_samples=resident,
-                _writer=writer,
-            )
-        except Exception as e:
-            report(i, e)
-            return None
-
     def pipelined(mdl, my_rows, pb, tick):
-        """One GPU's share of the table as a three-stage pipeline around the device:
-        loader threads decode WAV files straight into page-locked buffers (a 1-h file takes ~70 ms to read, three times the
-        device time, hence several loaders) -> this thread uploads recording k+1 (DMA, orcai_prefetch_pcm / orcai_swap_pcm)
-        while the device annotates recording k -> a writer thread builds the label table and writes the files."""
+        """One GPU's share of the table as a pipeline around the device that never lets it idle:
+        loader threads decode WAV files straight into page-locked buffers (a 1-h file takes ~70 ms to read, twice the device time,
+        hence several loaders) -> this thread uploads recording k+1 (DMA on the copy stream: orcai_prefetch_pcm / orcai_swap_pcm)
+        and ENQUEUES its whole annotation (orcai_predict_resident_begin) while the device still works on recording k -> it then
+        sleeps until recording k is done (orcai_predict_resident_end), hands its segments to a writer thread (label table, duration
+        filter, files) and goes on.  Every failure of row k - load, hand-over, annotation, files - is reported against row k, like
+        the reference loop (predict.py:752-755); the rows after it still run."""
+        from collections import deque
+
         from orcai_b200._lib import PinnedPool
 
         ctx = _context_of(mdl, orcai_parameter, shape)
         sp = orcai_parameter["spectrogram"]
+        if ctx.params.n_freq != shape["input_shape"][1]:
+            raise ValueError(f"Spectrogram shape ({ctx.params.n_freq}) not equal to input shape ({shape['input_shape'][1]})")
+        times01 = frames_to_time(2, sp)
+        delta_t = times01[1] - times01[0]
+        quiet = Messenger(verbosity=0)
         n_load = 3
         depth = n_load + 1
         # the pool lives on the context: page-locking 346 MB takes ~0.1 s, a table run must not pay it per call
         pool = ctx.__dict__.get("_pinned_pool")
         if pool is None:
-            pool = ctx.__dict__["_pinned_pool"] = PinnedPool(max_free=depth + 2)
+            pool = ctx.__dict__["_pinned_pool"] = PinnedPool(max_free=depth + 3)
 
-        def load(i):
+        def load(i, read_threads=1):
             taken = []
 
             def alloc(nbytes):
@@ -685,56 +675,103 @@ def predict(
                 taken.append(a)
                 return a
 
+            t0 = time.perf_counter()
             try:
-                return load_recording(row_path(i), int(recording_table.loc[i, "channel"]), sp, Messenger(verbosity=0), alloc=alloc), taken
-            except Exception as e:  # surfaced inside run_row so that the row is reported like any other failure
+                return load_recording(row_path(i), int(recording_table.loc[i, "channel"]), sp, quiet, alloc=alloc, read_threads=read_threads), taken
+            except Exception as e:  # surfaced in the main loop so that the row is reported like any other failure
                 for a in taken:
                     pool.give(a)
                 return e, []
+            finally:
+                with stats_lock:
+                    stats["load_s"] += time.perf_counter() - t0
 
-        pending = []
+        def give(taken):
+            for a in taken:
+                pool.give(a)
+
+        stats = {"rows": 0, "load_s": 0.0, "wait_loader_s": 0.0, "wait_device_s": 0.0, "wait_writer_s": 0.0, "device": getattr(ctx, "device", None)}
+        stats_lock = threading.Lock()
+        pending = []      # (row, future of its host-side tail)
+        in_flight = deque()   # (row, output path, token of predict_begin, page-locked buffers of its samples), oldest first
         with ThreadPoolExecutor(max_workers=n_load) as loaders, ThreadPoolExecutor(max_workers=1) as writer:
-            futs = {k: loaders.submit(load, my_rows[k]) for k in range(min(depth, len(my_rows)))}
+            # nothing overlaps the read of the share's first recording: it is read by four concurrent slices
+            futs = {k: loaders.submit(load, my_rows[k], 4 if k == 0 else 1) for k in range(min(depth, len(my_rows)))}
 
             def fetch(k):
                 """wait for recording k on the host and start its upload"""
+                t0 = time.perf_counter()
                 res, taken = futs.pop(k).result()
+                stats["wait_loader_s"] += time.perf_counter() - t0
                 if not isinstance(res, BaseException):
                     try:
                         ctx.prefetch_pcm(res)
                     except Exception as e:
-                        for a in taken:
-                            pool.give(a)
+                        give(taken)
                         return e, []
                 return res, taken
+
+            def begin(i, res):
+                """hand-over of row i's samples and its whole annotation, enqueued behind whatever the device is doing"""
+                if isinstance(res, BaseException):
+                    raise res
+                rp = row_path(i)
+                out = _resolved_output_path(rp, int(recording_table.loc[i, "channel"]), orcai_parameter, out_path_of[i], overwrite, quiet)
+                ctx.swap_pcm()
+                try:
+                    return out, ctx.predict_begin(res.size, threshold=0.5, want_agg=bool(save_probabilities))
+                except OrcaiError as e:
+                    if e.code == ORCAI_ERR_TOO_SHORT:
+                        raise ValueError(f"{rp.stem}: {e.message}") from e
+                    raise
+
+            def collect():
+                """sleep until the oldest row in flight is done; its host-side tail goes to the writer thread"""
+                i, out, token, taken = in_flight.popleft()
+                try:
+                    t0 = time.perf_counter()
+                    _stats, agg, _cnt, lab, sta, sto = ctx.predict_end(token)
+                    stats["wait_device_s"] += time.perf_counter() - t0
+                    stats["rows"] += 1
+                    pending.append((i, writer.submit(_host_tail, agg, lab, sta, sto, delta_t, orcai_parameter, out, save_probabilities,
+                                                     call_duration_limits, label_suffix, quiet)))
+                except Exception as e:
+                    report(i, e)
+                give(taken)
+                tick()
 
             cur = fetch(0) if my_rows else None
             for k, i in enumerate(my_rows):
                 res, taken = cur
-                # everything of row k - including the hand-over of its samples - fails into row k's report, like the reference
-                # loop (predict.py:752-755); the rows after it still run
+                begun = None
                 try:
-                    if not isinstance(res, BaseException):
-                        ctx.swap_pcm()
+                    begun = begin(i, res)                   # queued behind row k-1, which is still on the device
                 except Exception as e:
-                    res = e
+                    report(i, e)
+                if in_flight:
+                    collect()                               # row k-1: done -> its device PCM buffer is free for row k+1's upload
+                if begun is not None:
+                    in_flight.append((i, begun[0], begun[1], taken))
+                else:
+                    give(taken)
+                    tick()
                 if k + depth < len(my_rows):
                     futs[k + depth] = loaders.submit(load, my_rows[k + depth])
                 try:
-                    cur = fetch(k + 1) if k + 1 < len(my_rows) else None   # its upload overlaps the annotation of recording k
+                    cur = fetch(k + 1) if k + 1 < len(my_rows) else None   # its upload overlaps the annotation of row k
                 except Exception as e:
                     cur = (e, [])
-                fut = run_row(i, mdl, pb, resident=res, writer=writer)
-                if fut is not None:
-                    pending.append((i, fut))
-                for a in taken:
-                    pool.give(a)
-                tick()
+            while in_flight:
+                collect()
+            t0 = time.perf_counter()
             for i, fut in pending:
                 try:
                     fut.result()
                 except Exception as e:
                     report(i, e)
+            stats["wait_writer_s"] = time.perf_counter() - t0
+        TABLE_STATS.clear()
+        TABLE_STATS.update(stats)
 
     if _worker:
         q = _worker["queue"]

@@ -20,13 +20,14 @@ from orcai_b200.runtime import get_context, shape_for
 from orcai_b200.wavio import read_wav
 
 
-def load_recording(wav_file_path: Path | str, channel: int, spectrogram_parameter: dict, msgr: Messenger | None = None, alloc=None) -> np.ndarray:
+def load_recording(wav_file_path: Path | str, channel: int, spectrogram_parameter: dict, msgr: Messenger | None = None, alloc=None,
+                   read_threads: int = 1) -> np.ndarray:
     """Mono samples of the requested channel at the model's sampling rate (int16 or float32).
 
     Stands in for ``librosa.load(path, sr=..., mono=False)`` + channel selection (spectrogram.py:23-31).
     ``alloc``: see ``wavio.read_wav`` (table mode decodes into page-locked buffers).
     """
-    samples, sr, n_ch = read_wav(wav_file_path, channel, alloc=alloc)
+    samples, sr, n_ch = read_wav(wav_file_path, channel, alloc=alloc, read_threads=read_threads)
     if n_ch > 1 and msgr is not None:
         msgr.warning(f"Multiple channels found, using channel {channel}")
     target = int(spectrogram_parameter["sampling_rate"])

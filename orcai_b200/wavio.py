@@ -76,22 +76,52 @@ def read_wav_info(path: Path | str) -> WavInfo:
                 f.seek(1, 1)
 
 
-def read_wav(path: Path | str, channel: int = 1, alloc=None) -> tuple[np.ndarray, int, int]:
+def _read_slices(path, offset: int, out: memoryview, threads: int) -> int:
+    """Fill ``out`` from ``path`` at ``offset`` with ``threads`` concurrent positional reads (the copy out of the page cache runs at
+    ~7 GB/s per core; os.preadv releases the interpreter lock) -> bytes read."""
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+
+    n = len(out)
+    step = -(-n // threads + 4095) // 4096 * 4096 if n else 0
+    fd = os.open(path, os.O_RDONLY)
+    try:
+        def part(k):
+            lo, hi = k * step, min(n, (k + 1) * step)
+            got = 0
+            while lo + got < hi:
+                r = os.preadv(fd, [out[lo + got:hi]], offset + lo + got)
+                if r <= 0:
+                    break
+                got += r
+            return got
+
+        with ThreadPoolExecutor(max_workers=threads) as ex:
+            return sum(ex.map(part, range(-(-n // step) if step else 0)))
+    finally:
+        os.close(fd)
+
+
+def read_wav(path: Path | str, channel: int = 1, alloc=None, read_threads: int = 1) -> tuple[np.ndarray, int, int]:
     """Return (mono samples, sample_rate, n_channels).
 
     ``channel`` is 1-indexed and only used for multi-channel files (reference
     spectrogram.py:29-31).  The result is int16 for PCM16 input, else float32.
     ``alloc(nbytes) -> uint8 ndarray``: where to put the samples (e.g. page-locked memory, ``_lib.PinnedPool.take``); a mono
-    PCM16 file is read straight into it, everything else is decoded first and then copied.
+    PCM16 file is read straight into it (by ``read_threads`` concurrent positional reads when > 1: the first recording of a table,
+    whose read nothing overlaps), everything else is decoded first and then copied.
     """
     info = read_wav_info(path)
     if alloc is not None:
         if info.channels == 1 and info.bits == 16 and not info.is_float:
             n = info.n_frames
             buf = alloc(2 * n)
-            with open(path, "rb") as f:
-                f.seek(info.data_offset)
-                got = f.readinto(memoryview(buf)[: 2 * n])
+            if read_threads > 1 and n > (1 << 22):
+                got = _read_slices(path, info.data_offset, memoryview(buf)[: 2 * n], read_threads)
+            else:
+                with open(path, "rb") as f:
+                    f.seek(info.data_offset)
+                    got = f.readinto(memoryview(buf)[: 2 * n])
             if got != 2 * n:
                 raise ValueError(f"{path}: truncated data chunk ({got} of {2 * n} bytes)")
             return buf[: 2 * n].view("<i2"), info.sample_rate, 1

@@ -172,6 +172,57 @@ def test_prefetch_swap_pipeline(ctx):
         ctx.swap_pcm()
 
 
+def test_two_predict_calls_in_flight(ctx):
+    """orcai_predict_resident_begin / _end: recording k+1 is enqueued before recording k is collected; every result - statistics,
+    aggregates, segments - equals the one-call result bit for bit, for recordings of different lengths (buffers are re-allocated
+    under a call in flight), with and without aggregates, on the fp32 and the default network path; misuse fails loudly."""
+    recs = [synth_pcm16(secs, seed=170 + k, calls_per_minute=40.0) for k, secs in enumerate((9.0, 21.0, 8.0, 30.0, 12.0))]
+    for path in (0, 4):
+        ctx.set_option("net_path", path)
+        try:
+            one = [ctx.predict_pcm(r) for r in recs]
+            got = []
+            tokens = []
+            ctx.prefetch_pcm(recs[0])
+            for k, r in enumerate(recs):
+                ctx.swap_pcm()
+                tokens.append(ctx.predict_begin(r.size, want_agg=(k % 2 == 0)))
+                assert ctx.predict_in_flight() == len(tokens)
+                if len(tokens) == 2:
+                    got.append(ctx.predict_end(tokens.pop(0)))
+                if k + 1 < len(recs):
+                    ctx.prefetch_pcm(recs[k + 1])      # into the buffer of the recording collected above
+            while tokens:
+                got.append(ctx.predict_end(tokens.pop(0)))
+            assert ctx.predict_in_flight() == 0
+            for k, (a, b) in enumerate(zip(one, got)):
+                assert (a[0].n_frames, a[0].lo, a[0].hi, a[0].db_ref, a[0].rank_lo, a[0].rank_hi) == (b[0].n_frames, b[0].lo, b[0].hi, b[0].db_ref, b[0].rank_lo, b[0].rank_hi)
+                if k % 2 == 0:
+                    np.testing.assert_array_equal(a[1], b[1])
+                    np.testing.assert_array_equal(a[2], b[2])
+                else:
+                    assert b[1] is None and b[2] is None
+                for i in (3, 4, 5):
+                    np.testing.assert_array_equal(a[i], b[i])
+                assert len(a[3]) > 0
+        finally:
+            ctx.set_option("net_path", 0)
+    with pytest.raises(Exception, match="no predict call in flight"):
+        ctx.predict_end((1, 7, 1024, False))
+    ctx.upload_pcm(recs[0])
+    t1 = ctx.predict_begin(recs[0].size)
+    t2 = ctx.predict_begin(recs[0].size)
+    with pytest.raises(Exception, match="already in flight"):
+        ctx.predict_begin(recs[0].size)
+    a, b = ctx.predict_end(t1), ctx.predict_end(t2)
+    for i in (1, 2, 3, 4, 5):
+        np.testing.assert_array_equal(a[i], b[i])
+    ctx.upload_pcm(synth_pcm16(1.0, seed=3))
+    with pytest.raises(Exception, match="shorter than one snippet"):
+        ctx.predict_begin(48000)
+    assert ctx.predict_in_flight() == 0
+
+
 def test_calibration_reduces_weight_rounding_error(ctx, params):
     """orcai_calibrate: deterministic, cleared by load_weights, and it shrinks the fast path's deviation on unseen audio."""
     P, S = params

@@ -323,6 +323,11 @@ def test_wav_reader_into_caller_memory(tmp_path):
     cut_plain = wavio.read_wav(tmp_path / "cut.wav", 1)[0]
     cut_alloc = wavio.read_wav(tmp_path / "cut.wav", 1, alloc=alloc)[0]
     np.testing.assert_array_equal(cut_plain, cut_alloc)
+    # the first recording of a table is read by concurrent slices (any slice count, ragged tail): the same samples
+    big = rng.integers(-32768, 32767, (1 << 22) + 12345, dtype=np.int16)
+    wavio.write_wav_pcm16(tmp_path / "big.wav", big)
+    for th in (2, 3, 4, 7):
+        np.testing.assert_array_equal(wavio.read_wav(tmp_path / "big.wav", 1, alloc=alloc, read_threads=th)[0], big)
 
 
 def test_model_rebinds_a_shared_context(monkeypatch):
@@ -480,3 +485,110 @@ def test_model_directory_is_loaded_once_per_process(tmp_path, monkeypatch):
     io.load_orcai_model(d, device=0)
     assert len(made) == 4 and made[-1][0] == float(W2["dense2/bias"][0])
     io._MODEL_CACHE.clear()
+
+
+def test_table_pipeline_keeps_two_recordings_in_flight_and_reports_failures_per_row(tmp_path, monkeypatch):
+    """predict(TABLE.csv) on one device, with a stand-in context that logs the C-ABI calls: recording k+1 is handed over and enqueued
+    (swap, predict_begin) BEFORE recording k is collected (predict_end), its upload starts only after recording k-1 - whose device
+    buffer it takes - has been collected; a missing file, a recording that is too short and an existing label file are reported
+    against their own rows and the rows after them still run (reference loop predict.py:752-755)."""
+    import pandas as pd
+
+    from orcai_b200 import _lib, predict as op, wavio
+    from orcai_b200._lib import ORCAI_ERR_TOO_SHORT, OrcaiError, SpecStats
+
+    P, S = runtime.bundled_parameters()
+    log = []
+
+    class Pool:
+        def __init__(self, max_free=0):
+            self.out = 0
+
+        def take(self, nbytes):
+            self.out += 1
+            return np.zeros(nbytes, np.uint8)
+
+        def give(self, a):
+            self.out -= 1
+
+    pools = []
+    monkeypatch.setattr(_lib, "PinnedPool", lambda max_free=0: pools.append(Pool()) or pools[-1])
+
+    class Ctx:
+        device = 0
+
+        class params:
+            n_freq = S["input_shape"][1]
+
+        def __init__(self):
+            self.next = self.cur = None
+            self.flight = []
+
+        def prefetch_pcm(self, pcm):
+            log.append(("prefetch", int(pcm[0])))
+            self.next = int(pcm[0])
+
+        def swap_pcm(self):
+            assert self.next is not None
+            log.append(("swap", self.next))
+            self.cur, self.next = self.next, None
+
+        def predict_begin(self, n_samples, threshold=0.5, want_agg=True):
+            assert len(self.flight) < 2 and not want_agg
+            if n_samples < 1000:
+                raise OrcaiError(ORCAI_ERR_TOO_SHORT, "recording has 3 frames, shorter than one snippet of 736")
+            log.append(("begin", self.cur))
+            self.flight.append(self.cur)
+            return self.cur
+
+        def predict_end(self, token):
+            assert self.flight.pop(0) == token
+            log.append(("end", token))
+            st = SpecStats()
+            st.n_frames = 1000
+            return st, None, None, np.array([token % 7], np.int32), np.array([token], np.int64), np.array([token + 3], np.int64)
+
+    class Model:
+        ctx = Ctx()
+
+        def bind(self):
+            return self.ctx
+
+        def describe(self):
+            return "stand-in"
+
+    monkeypatch.setattr(op, "load_orcai_model", lambda model_dir, device=None: (Model(), P, S))
+    monkeypatch.delenv("ORCAI_B200_DEVICES", raising=False)
+    monkeypatch.delenv("ORCAI_B200_SHARD", raising=False)
+    for v in ("RANK", "WORLD_SIZE"):
+        monkeypatch.delenv(v, raising=False)
+    monkeypatch.setattr(op, "_table_devices", lambda: [0])
+    rows = []
+    for k in range(7):
+        n = 500 if k == 4 else 5000            # row 4 is too short
+        pcm = np.full(n, k + 1, np.int16)      # the first sample names the recording in the log
+        if k != 2:                             # row 2's file is missing
+            wavio.write_wav_pcm16(tmp_path / f"w{k}.wav", pcm)
+        rows.append({"recording": f"r{k}", "channel": 1, "base_dir_recording": str(tmp_path), "rel_recording_path": f"w{k}.wav"})
+    csv = tmp_path / "t.csv"
+    pd.DataFrame(rows).to_csv(csv, index=False)
+    out = tmp_path / "out"
+    out.mkdir()
+    (out / "r5_orcai-V1_predicted.txt").write_text("old")    # row 5: label file exists, no overwrite
+    errors = []
+
+    class Msgr(op.Messenger):
+        def error(self, text, *a, **k):
+            errors.append(str(text))
+
+    op.predict(csv, model_dir=tmp_path / "orcai-V1", output_path=str(out), msgr=Msgr(verbosity=0))
+    ev = [e for e in log if e[0] in ("begin", "end")]
+    # rows 0, 1 overlap; row 2 (missing) only collects row 1; row 3 runs; row 4 (too short) collects it; row 5 (file exists); row 6
+    assert ev == [("begin", 1), ("begin", 2), ("end", 1), ("end", 2), ("begin", 4), ("end", 4), ("begin", 7), ("end", 7)]
+    # the upload of the row after next starts only when the buffer it takes has been released by predict_end
+    assert log.index(("prefetch", 4)) > log.index(("end", 1)) and log.index(("prefetch", 7)) > log.index(("end", 4))
+    assert sorted(f.name for f in out.iterdir()) == [f"r{k}_orcai-V1_predicted.txt" for k in (0, 1, 3, 5, 6)]
+    assert (out / "r5_orcai-V1_predicted.txt").read_text() == "old"
+    assert (out / "r3_orcai-V1_predicted.txt").read_text().splitlines()[1].split("\t")[2] == P["calls"][4 % 7] + "*"
+    assert len(errors) == 3 and "r2" in errors[0] and "r4" in errors[1] and "shorter than one snippet" in errors[1] and "r5" in errors[2] and "already exists" in errors[2]
+    assert pools and pools[0].out == 0           # every page-locked buffer went back to the pool
