@@ -90,7 +90,6 @@ struct NetWeights {
   float* p_res_w[kMaxBlocks] = {};   // [CIP][COP] fp32, zero padded
   float* p_res_b[kMaxBlocks] = {};   // [COP]
   int chunk_precise = 2048;
-  int precise_halo2 = 0;      // sep_uf_kernel: 1 = double-buffered halo for <= 40 channels (two CTAs per SM); measured 5-10 % slower than three CTAs per SM with one halo
   int precise_sep_path = 1;   // un-folded separable convolutions: 1 = depthwise fused into the split GEMM (sep_uf_kernel), 0 = two kernels
   int precise_tall = 1;       // resident recordings: trunk once over the chunk's rows as one tall image + per-snippet border rows
   int debug_stop = -1;        // stop the forward after this stage (debug reads), -1 = run everything

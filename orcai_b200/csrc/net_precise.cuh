@@ -171,36 +171,49 @@ assemble_feat_kernel(const float* __restrict__ tall, const float* __restrict__ b
 //   tile      16 x 8 pixels = the 128 rows of one tcgen05.mma; its 18 x 10 halo arrives as ONE TMA box of the fp32 NHWC tensor
 //             ([18][10][CP] floats; image borders are zero-filled by the TMA unit = the "same" padding)
 //   workers   4 warps.  Thread t < 8 * Q (Q = CP / 4 channel quads) owns tile column t / Q and channel quad t % Q and walks the
-//             rows with a sliding 3 x 3 window in registers: 3 conflict-free LDS.128 + 36 FFMA per output float4; the results go
-//             to the (hi, lo) A planes (canonical K-major, plane pitch padded by 16 B against bank conflicts)
-//   issuer    1 warp: TMA of the next halo as soon as the workers have read the current one, then 3 MMAs per K step
-//             (A_hi*B_hi + A_lo*B_hi + A_hi*B_lo, N = 64, fp32 accumulation in TMEM)
+//             rows with a sliding 3 x 3 window in registers (eight rows per unrolled trip): 3 conflict-free LDS.128 + 36 FFMA per
+//             output float4; the results go to the (hi, lo) A planes (canonical K-major, plane pitch padded by 16 B against bank
+//             conflicts).  (Dealing the (column, row) pairs out evenly to all lanes at Q = 10 was measured slower: the SM's three
+//             CTAs are bound by the instructions they issue together, and that mapping issues more of them.)
+//   issuer    1 warp: the TMA of the NEXT tile's halo the moment the workers have consumed the current one (before this tile's
+//             MMAs are issued), then 3 MMAs per K step (A_hi*B_hi + A_lo*B_hi + A_hi*B_lo, N = 64, fp32 accumulation in TMEM)
 //   epilogue  the workers drain TMEM (thread = pixel), add the bias, apply the ReLU, store fp32 NHWC rows
-// Two CTAs per SM overlap each other's phases.  x: (n, H, W, CP), out: (n, H, W, ldc); CP <= 64, ldc <= 64.
+// Three CTAs per SM overlap each other's phases.  x: (n, H, W, CP), out: (n, H, W, ldc); CP <= 64, ldc <= 64.
 constexpr int kUfTH = 16, kUfTW = 8, kUfHalo = (kUfTH + 2) * (kUfTW + 2);
 constexpr uint32_t kUfLboA = 128 * 16 + 16;                           // A plane pitch (one 8-channel chunk of 128 rows) + pad
 // shared memory sized by the channel count: 56 KB at 32 channels (the register file then allows three CTAs per SM), 95 KB at 64
 struct UfSmem {
   static constexpr uint32_t B_HALF = 64 * 64 * 2;                      // [hi | lo] 64 x 64 fp16 blocks
-  uint32_t halo_bytes, off_a, a_half, off_b, off_bar, bytes;           // halo(s) [18][10][CP] fp32 at 0; hi planes, lo planes; B; barriers
-  __host__ __device__ UfSmem(int cp, int n_halo) {
+  uint32_t halo_bytes, off_a, a_half, off_b, off_bar, bytes;           // halo [18][10][CP] fp32 at 0; hi planes, lo planes; B; barriers
+  __host__ __device__ explicit UfSmem(int cp) {
     const uint32_t planes = 2u * (uint32_t)((cp + 15) / 16);           // 8-channel planes the MMAs read (K steps of 16)
     halo_bytes = ((uint32_t)kUfHalo * cp * 4 + 127) & ~127u;
-    off_a = halo_bytes * (uint32_t)n_halo;
+    off_a = halo_bytes;
     a_half = planes * kUfLboA;
     off_b = (off_a + 2 * a_half + 127) & ~127u;
-    off_bar = off_b + 2 * B_HALF;                                      // halo_full[2], halo_free[2], a_full, acc_full, acc_free, b_full; then 64 bias floats
+    off_bar = off_b + 2 * B_HALF;                                      // halo_full, a_full, acc_full, acc_free, b_full; then 64 bias floats
     bytes = off_bar + 128 + 64 * 4;
   }
 };
 
+// 256-bit global store (sm_100: STG.E.256): p must be 32-byte aligned
+__device__ __forceinline__ void st_global_v8(float* p, const float* v) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]),
+               "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+
+#ifdef ORCAI_FUSED_TRACE
+#define UF_TRACE(tag, g) do { if (CP == 40 && !RELU_IN && ACT == 0 && tiles_h > 1000) fused::trace_event(70, tag, g); } while (0)
+#else
+#define UF_TRACE(tag, g)
+#endif
+
 template <bool RELU_IN, int ACT>
-__global__ void __launch_bounds__(160, 3)   // four CTAs per SM (96 registers, spills) measured 9 % slower
+__global__ void __launch_bounds__(160, 3)   // four CTAs per SM (96 registers, spills) measured 9 % slower; a second halo buffer (two CTAs per SM) 8 % slower
 sep_uf_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__ dw, const __half* __restrict__ Bp, const float* __restrict__ bias,
-              float* __restrict__ out, long long n_img, int H, int W, int CP, int ldc, int n_valid, int tiles_w, int tiles_h, int n_halo) {
-  // n_halo = 2: the halo of tile i+1 is in flight while tile i is being filtered (the shared memory of <= 40 channels allows it at
-  // two CTAs per SM); 1: it is fetched once the workers have read the current one
-  const UfSmem L(CP, n_halo);
+              float* __restrict__ out, long long n_img, int H, int W, int CP, int ldc, int n_valid, int tiles_w, int tiles_h) {
+  const UfSmem L(CP);
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.off_bar);
   uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 8);
@@ -209,14 +222,11 @@ sep_uf_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__
   const int Q = CP >> 2;
   if (tid < 64) s_bias[tid] = __ldg(bias + tid);
   if (tid == 0) {
-    mbar_init(&bars[0], 1);      // halo_full[0]: TMA complete_tx
-    mbar_init(&bars[1], 4);      // halo_free[0]: one arrival per worker warp
-    mbar_init(&bars[2], 4);      // a_full
+    mbar_init(&bars[0], 1);      // halo_full: TMA complete_tx
+    mbar_init(&bars[2], 4);      // a_full: one arrival per worker warp = A planes written AND halo consumed
     mbar_init(&bars[3], 1);      // acc_full: tcgen05.commit
     mbar_init(&bars[4], 4);      // acc_free
     mbar_init(&bars[5], 1);      // b_full
-    mbar_init(&bars[6], 1);      // halo_full[1]
-    mbar_init(&bars[7], 4);      // halo_free[1]
     fence_mbar_init();
   }
   for (int i = tid; i < (int)(2 * L.a_half / 16); i += 160) reinterpret_cast<uint4*>(smem + L.off_a)[i] = make_uint4(0, 0, 0, 0);   // unused K planes stay zero
@@ -228,9 +238,8 @@ sep_uf_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__
   tc_fence_after();
   const uint32_t tmem = *tslot;
   const uint32_t sbase = smem_u32(smem);
-  const long long tiles_per = (long long)tiles_w * tiles_h;
-  const long long total = n_img * tiles_per;
-  const uint32_t halo_bytes = (uint32_t)kUfHalo * CP * 4;
+  const uint32_t tiles_per = (uint32_t)tiles_w * (uint32_t)tiles_h;
+  const uint32_t total = (uint32_t)n_img * tiles_per;                      // < 2^31 (checked by the launcher)
 
   if (warp == 4) {
     // =============================== issuer: TMA + MMA ===============================
@@ -245,35 +254,27 @@ sep_uf_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__
     const uint64_t da = make_smem_desc(sbase + L.off_a, kUfLboA, 128);
     const uint64_t db = make_smem_desc(sbase + L.off_b, 128, 8 * 128);
     const int ksteps = (CP + 15) >> 4;
-    auto halo_full = [&](long long i) { return &bars[(n_halo == 2 && (i & 1)) ? 6 : 0]; };
-    auto halo_free = [&](long long i) { return &bars[(n_halo == 2 && (i & 1)) ? 7 : 1]; };
-    auto load_halo = [&](long long i, long long tl) {      // tile tl = this CTA's i-th tile
-      const long long b2 = tl / tiles_per;
-      const int tr2 = (int)(tl - b2 * tiles_per);
+    const uint32_t halo_tx = (uint32_t)kUfHalo * CP * 4;
+    auto load_halo = [&](uint32_t tl) {
+      const uint32_t b2 = tl / tiles_per, tr2 = tl - b2 * tiles_per;
+      const uint32_t ty = tr2 / (uint32_t)tiles_w, tx = tr2 - ty * (uint32_t)tiles_w;
       if (fused::elect_one()) {
-        fused::mbar_arrive_expect_tx(halo_full(i), (uint32_t)kUfHalo * CP * 4);
-        fused::tma_load_4d(sbase + (n_halo == 2 ? (uint32_t)(i & 1) * L.halo_bytes : 0u), &tmX, halo_full(i), 0, (tr2 % tiles_w) * kUfTW - 1,
-                           (tr2 / tiles_w) * kUfTH - 1, (int)b2);
+        fused::mbar_arrive_expect_tx(&bars[0], halo_tx);
+        fused::tma_load_4d(sbase, &tmX, &bars[0], 0, (int)tx * kUfTW - 1, (int)ty * kUfTH - 1, (int)b2);
       }
       __syncwarp();
     };
-    long long it = 0;
-    if (n_halo == 2 && blockIdx.x < total) load_halo(0, blockIdx.x);
-    for (long long tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
-      if (n_halo == 2) {
-        // the next tile's halo goes into the other buffer as soon as the workers have read the tile that used it (tile it - 1)
-        if (tile + gridDim.x < total) {
-          if (it >= 1) mbar_wait(halo_free(it + 1), (uint32_t)(((it - 1) >> 1) & 1));
-          load_halo(it + 1, tile + gridDim.x);
-        }
-      } else {
-        if (it > 0) mbar_wait(&bars[1], (uint32_t)((it - 1) & 1));          // the workers have read the previous halo
-        load_halo(it, tile);
-      }
+    uint32_t it = 0;
+    if (blockIdx.x < total) { load_halo(blockIdx.x); UF_TRACE(1, 0); }
+    for (uint32_t tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
       if (it == 0) mbar_wait(&bars[5], 0);
-      mbar_wait(&bars[2], (uint32_t)(it & 1));                             // A planes of this tile written
-      if (it > 0) mbar_wait(&bars[4], (uint32_t)((it - 1) & 1));          // accumulator drained
+      mbar_wait(&bars[2], it & 1);                                         // A planes of this tile written, its halo consumed
+      UF_TRACE(2, it);
+      // the next tile's halo is requested BEFORE this tile's MMAs are issued: it lands while they run and the workers drain them
+      if (tile + gridDim.x < total) { load_halo(tile + gridDim.x); UF_TRACE(1, it + 1); }
+      if (it > 0) mbar_wait(&bars[4], (it - 1) & 1);                       // accumulator drained
       tc_fence_after();
+      UF_TRACE(4, it);
       if (fused::elect_one()) {
         for (int ks = 0; ks < ksteps; ++ks) {
           const uint64_t a = da + ((2 * ks * kUfLboA) >> 4), bb = db + ((2 * ks * 128) >> 4);
@@ -284,6 +285,7 @@ sep_uf_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__
         mma_commit(&bars[3]);
       }
       __syncwarp();
+      UF_TRACE(3, it);
     }
   } else {
     // =============================== workers ===============================
@@ -295,57 +297,66 @@ sep_uf_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__
     float4 k[9];
 #pragma unroll
     for (int t = 0; t < 9; ++t) k[t] = active ? __ldg(reinterpret_cast<const float4*>(dw + t * CP + 4 * quad)) : make_float4(0.f, 0.f, 0.f, 0.f);
-    const float4* halo = reinterpret_cast<const float4*>(smem);   // re-pointed per tile
     const int hrow = (kUfTW + 2) * Q;                                       // float4 per halo row
-    auto ld = [&](int y, int x) {
-      float4 v = halo[y * hrow + x * Q + quad];
-      if (RELU_IN) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-      return v;
+    const float4* const halo0 = reinterpret_cast<const float4*>(smem) + (r0 * hrow + col * Q + quad);   // window origin of this thread
+    auto ldrow = [&](const float4* p, float4 (&v)[3]) {
+#pragma unroll
+      for (int x = 0; x < 3; ++x) {
+        v[x] = p[x * Q];
+        if (RELU_IN) { v[x].x = fmaxf(v[x].x, 0.f); v[x].y = fmaxf(v[x].y, 0.f); v[x].z = fmaxf(v[x].z, 0.f); v[x].w = fmaxf(v[x].w, 0.f); }
+      }
     };
+    unsigned char* const a_dst0 = smem + L.off_a + (quad >> 1) * kUfLboA + (quad & 1) * 8 + (r0 * kUfTW + col) * 16;
     const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
-    long long it = 0;
-    for (long long tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
-      const long long b = tile / tiles_per;
-      const int tr = (int)(tile - b * tiles_per);
-      const int h0 = (tr / tiles_w) * kUfTH, w0 = (tr % tiles_w) * kUfTW;
-      const int hb = n_halo == 2 ? (int)(it & 1) : 0;                      // halo buffer of this tile
-      halo = reinterpret_cast<const float4*>(smem + hb * L.halo_bytes);
-      mbar_wait(&bars[hb ? 6 : 0], (uint32_t)((n_halo == 2 ? (it >> 1) : it) & 1));
-      if (it > 0) mbar_wait(&bars[3], (uint32_t)((it - 1) & 1));          // the MMAs that read the A planes are done ...
-      // (... and this thread's epilogue of the previous tile below has run: program order)
+    const bool wide = (ldc & 7) == 0 && (reinterpret_cast<uintptr_t>(out) & 31) == 0;   // pixel rows start on 32-byte boundaries
+    uint32_t it = 0;
+    for (uint32_t tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+      const uint32_t b = tile / tiles_per, tr = tile - b * tiles_per;
+      const uint32_t ty = tr / (uint32_t)tiles_w, tx = tr - ty * (uint32_t)tiles_w;
+      const int h0 = (int)ty * kUfTH, w0 = (int)tx * kUfTW;
+      mbar_wait(&bars[0], it & 1);
+      // (the MMAs that read the A planes of the previous tile are done: this thread's epilogue below waited for them)
+      if (warp == 0) UF_TRACE(10, it);
       if (active) {
         float4 w[3][3];
+        ldrow(halo0, w[1]);
+        ldrow(halo0 + hrow, w[2]);
+        const float4* hp = halo0 + 2 * hrow;
+        unsigned char* dst = a_dst0;
+        for (int rr = 0; rr < rows; rr += 8) {
+          // eight rows per trip, fully unrolled: the window rotates by register renaming (no moves except once per trip)
 #pragma unroll
-        for (int y = 0; y < 2; ++y)
+          for (int i = 0; i < 8; ++i) {
 #pragma unroll
-          for (int x = 0; x < 3; ++x) w[y + 1][x] = ld(r0 + y, col + x);
-        for (int r = 0; r < rows; ++r) {
+            for (int x = 0; x < 3; ++x) { w[0][x] = w[1][x]; w[1][x] = w[2][x]; }
+            ldrow(hp, w[2]);
+            hp += hrow;
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-          for (int x = 0; x < 3; ++x) { w[0][x] = w[1][x]; w[1][x] = w[2][x]; w[2][x] = ld(r0 + r + 2, col + x); }
-          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-          for (int t = 0; t < 9; ++t) {
-            const float4 v = w[t / 3][t % 3];
-            acc.x = fmaf(v.x, k[t].x, acc.x); acc.y = fmaf(v.y, k[t].y, acc.y); acc.z = fmaf(v.z, k[t].z, acc.z); acc.w = fmaf(v.w, k[t].w, acc.w);
+            for (int t = 0; t < 9; ++t) {
+              const float4 v = w[t / 3][t % 3];
+              acc.x = fmaf(v.x, k[t].x, acc.x); acc.y = fmaf(v.y, k[t].y, acc.y); acc.z = fmaf(v.z, k[t].z, acc.z); acc.w = fmaf(v.w, k[t].w, acc.w);
+            }
+            const __half2 h01 = __floats2half2_rn(acc.x, acc.y), h23 = __floats2half2_rn(acc.z, acc.w);
+            const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+            const __half2 l01 = __floats2half2_rn(acc.x - f01.x, acc.y - f01.y), l23 = __floats2half2_rn(acc.z - f23.x, acc.w - f23.y);
+            uint2 hv, lv;
+            hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
+            lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
+            *reinterpret_cast<uint2*>(dst) = hv;
+            *reinterpret_cast<uint2*>(dst + L.a_half) = lv;
+            dst += kUfTW * 16;
           }
-          const __half2 h01 = __floats2half2_rn(acc.x, acc.y), h23 = __floats2half2_rn(acc.z, acc.w);
-          const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-          const __half2 l01 = __floats2half2_rn(acc.x - f01.x, acc.y - f01.y), l23 = __floats2half2_rn(acc.z - f23.x, acc.w - f23.y);
-          const int prow = (r0 + r) * kUfTW + col;
-          unsigned char* dst = smem + L.off_a + (quad >> 1) * kUfLboA + prow * 16 + (quad & 1) * 8;
-          uint2 hv, lv;
-          hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
-          lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
-          *reinterpret_cast<uint2*>(dst) = hv;
-          *reinterpret_cast<uint2*>(dst + L.a_half) = lv;
         }
       }
       fence_proxy_async();
       __syncwarp();
-      if (lane == 0) { fused::mbar_arrive(&bars[hb ? 7 : 1]); fused::mbar_arrive(&bars[2]); }
+      if (lane == 0) fused::mbar_arrive(&bars[2]);
+      if (warp == 0) UF_TRACE(11, it);
       // ---- epilogue: accumulator row tid = pixel (tid / 8, tid % 8) ----
-      mbar_wait(&bars[3], (uint32_t)(it & 1));
+      mbar_wait(&bars[3], it & 1);
       tc_fence_after();
+      if (warp == 0) UF_TRACE(12, it);
       const int hh = h0 + (tid >> 3), ww = w0 + (tid & 7);
       const bool inside = hh < H && ww < W;
       float* orow = out + (((size_t)b * H + hh) * W + ww) * ldc;
@@ -360,14 +371,23 @@ sep_uf_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__
           if (ACT == 1) v[i] = fmaxf(v[i], 0.f);
         }
         if (inside) {
+          // one whole 32-byte sector per store instruction where the row allows it (a thread owns a pixel: its stores are 4 * ldc
+          // bytes apart from its neighbours', so 16-byte stores would leave every sector half written per instruction)
 #pragma unroll
-          for (int q = 0; q < 4; ++q)
-            if (c0 + 4 * q + 4 <= n_valid) reinterpret_cast<float4*>(orow + c0)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+          for (int q = 0; q < 4; q += 2) {
+            if (wide && c0 + 4 * q + 8 <= n_valid) st_global_v8(orow + c0 + 4 * q, v + 4 * q);
+            else {
+#pragma unroll
+              for (int qq = q; qq < q + 2; ++qq)
+                if (c0 + 4 * qq + 4 <= n_valid) reinterpret_cast<float4*>(orow + c0)[qq] = make_float4(v[4 * qq], v[4 * qq + 1], v[4 * qq + 2], v[4 * qq + 3]);
+            }
+          }
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) fused::mbar_arrive(&bars[4]);
+      if (warp == 0) UF_TRACE(13, it);
     }
   }
   tc_fence_before();
@@ -434,19 +454,19 @@ int launch_sep_uf(Ctx* c, const float* x, float* out, long long n, long long h, 
   static std::atomic<unsigned long long> attr_devices{0ull};
   if (!((attr_devices.load() >> (c->device & 63)) & 1ull)) {
     ORCAI_CUDA(c, cudaFuncSetAttribute(precise::sep_uf_kernel<RELU_IN, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)std::max(precise::UfSmem(64, 1).bytes, precise::UfSmem(40, 2).bytes)));
+                                    (int)precise::UfSmem(64).bytes));
     attr_devices.fetch_or(1ull << (c->device & 63));
   }
-  const int n_halo = (c->net->precise_halo2 && cip <= 40) ? 2 : 1;
-  const precise::UfSmem L(cip, n_halo);
+  const precise::UfSmem L(cip);
   const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(3, (size_t)(225 * 1024) / (L.bytes + 1024)));
   CUtensorMap tm;
   ORCAI_CHECK(make_uf_map(c, &tm, x, n, h, w, cip));
   const int tiles_w = (w + precise::kUfTW - 1) / precise::kUfTW, tiles_h = (int)((h + precise::kUfTH - 1) / precise::kUfTH);
   const long long total = n * tiles_w * tiles_h;
+  if (total >= (1ll << 31)) ORCAI_FAIL(c, ORCAI_ERR_ARG, "sep_uf_kernel: %lld tiles exceed the 32-bit tile index", total);
   const unsigned grid = (unsigned)std::min<long long>(total, (long long)c->sm_count * per_sm);
   precise::sep_uf_kernel<RELU_IN, ACT><<<grid, 160, L.bytes, c->stream>>>(tm, ps.dw, ps.pw, ps.bias, out, n, (int)h, w, cip, ldc, n_valid, tiles_w,
-                                                                                        tiles_h, n_halo);
+                                                                                        tiles_h);
   c->launches++;
   ORCAI_CUDA(c, cudaGetLastError());
   return ORCAI_OK;

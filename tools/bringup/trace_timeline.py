@@ -14,6 +14,10 @@ for t in range(8):
     NAMES[10 + t] = f"workers: conv1 tile {t} complete"
     NAMES[30 + t] = f"workers: conv2 tile {t} complete"
 
+UF = {1: "issuer: halo free, TMA issued", 2: "issuer: A planes full", 4: "issuer: accumulator drained, MMAs start", 3: "issuer: MMAs committed",
+      10: "workers: halo landed, depthwise starts", 11: "workers: depthwise done (A planes written)", 12: "workers: accumulator complete, epilogue starts",
+      13: "workers: epilogue done"}
+
 runs = [[]]
 for line in open(sys.argv[1]):
     a, b = map(int, line.split())
@@ -30,7 +34,7 @@ for k, ev in sorted(by_kernel.items()):
     t0 = ev[0][2]
     print(f"===== block with CIN = {k}: {len(ev)} events, span {ev[-1][2] - t0} cycles =====")
     for g, tag, clk in ev:
-        print(f"  {clk - t0:8d}  step {g:3d}  {NAMES.get(tag, tag)}")
-    ends = [clk for g, tag, clk in ev if tag == 41]
+        print(f"  {clk - t0:8d}  step {g:3d}  {(UF if k == 70 else NAMES).get(tag, tag)}")
+    ends = [clk for g, tag, clk in ev if tag == (13 if k == 70 else 41)]
     if len(ends) > 1:
         print("  step period (cycles):", [b - a for a, b in zip(ends, ends[1:])])
