@@ -78,38 +78,58 @@ pool_res_f32_kernel(const float* __restrict__ s2, const float* __restrict__ xs, 
     const float4 bias = *reinterpret_cast<const float4*>(s_w + CIP * COP + 4 * g);
     float4 m[kPoolPx], a[kPoolPx];
     const float* xp[kPoolPx];
+    // The window loads are branch-free: a row / column beyond the image is clamped onto the image's last one, which the window
+    // holds anyway (the maximum does not change), so all twelve loads of a pixel pair are in flight together.  (With "continue"
+    // on the borders the loads were issued two at a time and the kernel waited on memory latency 57 % of its time.)
+    const int hr0 = 2 * ho, hr1 = min(2 * ho + 1, H - 1), hr2 = min(2 * ho + 2, H - 1);
+    const float* const r0p = sb + (size_t)hr0 * W * COP;
+    const float* const r1p = sb + (size_t)hr1 * W * COP;
+    const float* const r2p = sb + (size_t)hr2 * W * COP;
 #pragma unroll
-    for (int p = 0; p < kPoolPx; ++p) {
-      const int wo = wb * kPoolPx + p;
-      m[p] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-      a[p] = bias;
-      xp[p] = xs + (size_t)b * xs_img + (size_t)ho * xs_row + (size_t)(wo < Wo ? wo : Wo - 1) * xs_px;
+    for (int pp = 0; pp < kPoolPx; pp += 2) {
+      float4 v[2][6];
 #pragma unroll
-      for (int dy = 0; dy < 3; ++dy) {
-        const int hh = 2 * ho + dy;
-        if (hh >= H) continue;
+      for (int q = 0; q < 2; ++q) {
+        const int wo = min(wb * kPoolPx + pp + q, Wo - 1);
+        const int c0 = 2 * wo * COP, c1 = min(2 * wo + 1, W - 1) * COP;
+        v[q][0] = __ldg(reinterpret_cast<const float4*>(r0p + c0));
+        v[q][1] = __ldg(reinterpret_cast<const float4*>(r0p + c1));
+        v[q][2] = __ldg(reinterpret_cast<const float4*>(r1p + c0));
+        v[q][3] = __ldg(reinterpret_cast<const float4*>(r1p + c1));
+        v[q][4] = __ldg(reinterpret_cast<const float4*>(r2p + c0));
+        v[q][5] = __ldg(reinterpret_cast<const float4*>(r2p + c1));
+        xp[pp + q] = xs + (size_t)b * xs_img + (size_t)ho * xs_row + (size_t)wo * xs_px;
+        a[pp + q] = bias;
+      }
 #pragma unroll
-        for (int dx = 0; dx < 2; ++dx) {
-          const int ww = 2 * wo + dx;
-          if (ww >= W) continue;
-          const float4 v = __ldg(reinterpret_cast<const float4*>(sb + ((size_t)hh * W + ww) * COP));
-          m[p].x = fmaxf(m[p].x, v.x); m[p].y = fmaxf(m[p].y, v.y); m[p].z = fmaxf(m[p].z, v.z); m[p].w = fmaxf(m[p].w, v.w);
-        }
+      for (int q = 0; q < 2; ++q) {
+        float4 mm = v[q][0];
+#pragma unroll
+        for (int t = 1; t < 6; ++t) { mm.x = fmaxf(mm.x, v[q][t].x); mm.y = fmaxf(mm.y, v[q][t].y); mm.z = fmaxf(mm.z, v[q][t].z); mm.w = fmaxf(mm.w, v[q][t].w); }
+        m[pp + q] = mm;
       }
     }
+    float4 xv[kPoolPx];
+#pragma unroll
+    for (int p = 0; p < kPoolPx; ++p) xv[p] = __ldg(reinterpret_cast<const float4*>(xp[p]));
     for (int ci = 0; ci < CIP; ci += 4) {
       const float4 w0 = *reinterpret_cast<const float4*>(s_w + (ci + 0) * COP + 4 * g);
       const float4 w1 = *reinterpret_cast<const float4*>(s_w + (ci + 1) * COP + 4 * g);
       const float4 w2 = *reinterpret_cast<const float4*>(s_w + (ci + 2) * COP + 4 * g);
       const float4 w3 = *reinterpret_cast<const float4*>(s_w + (ci + 3) * COP + 4 * g);
+      float4 xn[kPoolPx];
+      const int cn = ci + 4 < CIP ? ci + 4 : ci;           // the next quad of input channels is requested before this one is used
+#pragma unroll
+      for (int p = 0; p < kPoolPx; ++p) xn[p] = __ldg(reinterpret_cast<const float4*>(xp[p] + cn));
 #pragma unroll
       for (int p = 0; p < kPoolPx; ++p) {
-        const float4 xv = __ldg(reinterpret_cast<const float4*>(xp[p] + ci));
+        const float4 x4 = xv[p];
         // per output channel the same FMA order as with one pixel per thread: ci ascending
-        a[p].x = fmaf(xv.x, w0.x, a[p].x); a[p].y = fmaf(xv.x, w0.y, a[p].y); a[p].z = fmaf(xv.x, w0.z, a[p].z); a[p].w = fmaf(xv.x, w0.w, a[p].w);
-        a[p].x = fmaf(xv.y, w1.x, a[p].x); a[p].y = fmaf(xv.y, w1.y, a[p].y); a[p].z = fmaf(xv.y, w1.z, a[p].z); a[p].w = fmaf(xv.y, w1.w, a[p].w);
-        a[p].x = fmaf(xv.z, w2.x, a[p].x); a[p].y = fmaf(xv.z, w2.y, a[p].y); a[p].z = fmaf(xv.z, w2.z, a[p].z); a[p].w = fmaf(xv.z, w2.w, a[p].w);
-        a[p].x = fmaf(xv.w, w3.x, a[p].x); a[p].y = fmaf(xv.w, w3.y, a[p].y); a[p].z = fmaf(xv.w, w3.z, a[p].z); a[p].w = fmaf(xv.w, w3.w, a[p].w);
+        a[p].x = fmaf(x4.x, w0.x, a[p].x); a[p].y = fmaf(x4.x, w0.y, a[p].y); a[p].z = fmaf(x4.x, w0.z, a[p].z); a[p].w = fmaf(x4.x, w0.w, a[p].w);
+        a[p].x = fmaf(x4.y, w1.x, a[p].x); a[p].y = fmaf(x4.y, w1.y, a[p].y); a[p].z = fmaf(x4.y, w1.z, a[p].z); a[p].w = fmaf(x4.y, w1.w, a[p].w);
+        a[p].x = fmaf(x4.z, w2.x, a[p].x); a[p].y = fmaf(x4.z, w2.y, a[p].y); a[p].z = fmaf(x4.z, w2.z, a[p].z); a[p].w = fmaf(x4.z, w2.w, a[p].w);
+        a[p].x = fmaf(x4.w, w3.x, a[p].x); a[p].y = fmaf(x4.w, w3.y, a[p].y); a[p].z = fmaf(x4.w, w3.z, a[p].z); a[p].w = fmaf(x4.w, w3.w, a[p].w);
+        xv[p] = xn[p];
       }
     }
 #pragma unroll
