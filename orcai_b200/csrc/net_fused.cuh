@@ -669,15 +669,13 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
               float* yf = reinterpret_cast<float*>(Yr) + o_full;
               if (sub) {
                 float* ys = reinterpret_cast<float*>(Ysub) + o_sub;
-                reinterpret_cast<float4*>(ys)[0] = make_float4(y[0], y[1], y[2], y[3]);
-                reinterpret_cast<float4*>(ys)[1] = make_float4(y[4], y[5], y[6], y[7]);
+                st_global_v8(ys, y);
               }
               if (G::RELU_OUT) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) y[i] = fmaxf(y[i], 0.f);
               }
-              reinterpret_cast<float4*>(yf)[0] = make_float4(y[0], y[1], y[2], y[3]);
-              reinterpret_cast<float4*>(yf)[1] = make_float4(y[4], y[5], y[6], y[7]);
+              st_global_v8(yf, y);   // the pixel's 8-channel group = one whole 32-byte sector (OCP is a multiple of 8, the tensors 256-byte aligned)
             } else {
             uint4 m = *reinterpret_cast<const uint4*>(s2);
             m = hmax8(m, *reinterpret_cast<const uint4*>(s2 + G::S2HALF * 16));

@@ -194,6 +194,7 @@ gemm_tc_kernel(const TA* __restrict__ A, int lda, const __half* __restrict__ Bp,
     tc_fence_after();
     const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
     float* crow = C + (size_t)(row0 + row) * ldc + (size_t)nt * BN;
+    const bool wide = (ldc & 7) == 0 && (reinterpret_cast<uintptr_t>(C) & 31) == 0;   // rows start on 32-byte boundaries
 #pragma unroll 2
     for (int c0 = 0; c0 < BN; c0 += 16) {
       float v[16];
@@ -205,8 +206,14 @@ gemm_tc_kernel(const TA* __restrict__ A, int lda, const __half* __restrict__ Bp,
       }
       if (row_ok) {
 #pragma unroll
-        for (int q = 0; q < 4; ++q)
-          if (nt * BN + c0 + 4 * q + 4 <= n_valid) reinterpret_cast<float4*>(crow + c0)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        for (int q = 0; q < 4; q += 2) {
+          if (wide && nt * BN + c0 + 4 * q + 8 <= n_valid) st_global_v8(crow + c0 + 4 * q, v + 4 * q);
+          else {
+#pragma unroll
+            for (int qq = q; qq < q + 2; ++qq)
+              if (nt * BN + c0 + 4 * qq + 4 <= n_valid) reinterpret_cast<float4*>(crow + c0)[qq] = make_float4(v[4 * qq], v[4 * qq + 1], v[4 * qq + 2], v[4 * qq + 3]);
+          }
+        }
       }
     }
   }

@@ -216,13 +216,6 @@ struct UfSmem {
   }
 };
 
-// 256-bit global store (sm_100: STG.E.256): p must be 32-byte aligned
-__device__ __forceinline__ void st_global_v8(float* p, const float* v) {
-  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]),
-               "f"(v[6]), "f"(v[7])
-               : "memory");
-}
-
 #ifdef ORCAI_FUSED_TRACE
 #define UF_TRACE(tag, g) do { if (CP == 40 && !RELU_IN && ACT == 0 && tiles_h > 1000) fused::trace_event(70, tag, g); } while (0)
 #else
@@ -534,11 +527,16 @@ int run_precise_block(Ctx* c, int blk, const float* x, float* ta, float* tb, flo
 
 int run_conv0_split(Ctx* c, const float* src, int input_mode, long long first, int in_ld, long long n_img, int Himg, int Wf, __half* hi, __half* lo,
                     long long n_snip, int off_bot, int Hfull, long long plane_halfs) {
-  const int tiles_w = (Wf + kC0TW - 1) / kC0TW, tiles_h = (Himg + kC0TH - 1) / kC0TH;
+  const int rpt = Himg >= 32 ? 4 : 1;                                  // tall images / whole snippets: four rows per thread; 8-row border images: one
+  const int tiles_w = (Wf + kC0TW - 1) / kC0TW, tiles_h = (Himg + c0_tile_rows(rpt) - 1) / c0_tile_rows(rpt);
   const long long blocks = n_img * tiles_w * tiles_h;
   if (blocks <= 0) return ORCAI_OK;
-  conv0_direct_kernel<true><<<(unsigned)blocks, 256, 0, c->stream>>>(src, input_mode, first, c->p.snippet_len / 2, in_ld, Himg, Wf, c->d_sel, hi,
-                                                                     static_cast<__half*>(nullptr), tiles_w, tiles_h, lo, n_snip, off_bot, Hfull, plane_halfs);
+  if (rpt == 4)
+    conv0_direct_kernel<true, 4><<<(unsigned)blocks, 256, 0, c->stream>>>(src, input_mode, first, c->p.snippet_len / 2, in_ld, Himg, Wf, c->d_sel, hi,
+                                                                          static_cast<__half*>(nullptr), tiles_w, tiles_h, lo, n_snip, off_bot, Hfull, plane_halfs);
+  else
+    conv0_direct_kernel<true, 1><<<(unsigned)blocks, 256, 0, c->stream>>>(src, input_mode, first, c->p.snippet_len / 2, in_ld, Himg, Wf, c->d_sel, hi,
+                                                                          static_cast<__half*>(nullptr), tiles_w, tiles_h, lo, n_snip, off_bot, Hfull, plane_halfs);
   c->launches++;
   ORCAI_CUDA(c, cudaGetLastError());
   return ORCAI_OK;

@@ -324,84 +324,106 @@ __constant__ float c_conv0[9 * 16 + 16];   // [tap][16] (BatchNorm folded), then
 // Weights sit in constant memory: every FFMA takes its weight as a constant-bank operand, no load instructions.
 // ------------------------------------------------------------------------------------------------
 
-constexpr int kC0TH = 8, kC0TW = 32;
+constexpr int kC0TW = 32;
+__host__ __device__ constexpr int c0_tile_rows(int rpt) { return 8 * rpt; }
 
 // SPLIT: the result as (hi, lo) fp16 pairs, out_lo = fp16(v - hi) (fp32-grade path, net_precise.cuh)
 // Row windows (net_precise.cuh, border images): image b is rows [off, off + Himg) of snippet b % n_snip, off = 0 for b < n_snip
 // and off_bot for the others; zero padding applies outside the snippet's rows [0, Hfull).  Plain use: n_snip = image count,
 // off_bot = 0, Hfull = Himg.
-template <bool SPLIT>
+// One CTA = 8 warps = a tile of 8 * RPT rows x 32 columns; warp y, lane x owns column x of rows [RPT * y, RPT * y + RPT) and walks
+// them with a sliding 3 x 3 window (RPT = 4 for tall images: the index arithmetic, the halo's normalisation and the barrier - half
+// of the instructions with one pixel per thread - are shared by four pixels; RPT = 1 for the 8-row border images).
+template <bool SPLIT, int RPT>
 __global__ void __launch_bounds__(256)
 conv0_direct_kernel(const float* __restrict__ in, int mode, long long first, int shift, int in_ld, int Himg, int Wimg,
                     const SelectState* __restrict__ st, __half* __restrict__ out, __half* __restrict__ out_sub,
                     int tiles_w, int tiles_h, __half* __restrict__ out_lo, long long n_snip, int off_bot, int Hfull, long long plane_halfs) {
-  __shared__ float s_x[kC0TH + 2][kC0TW + 2];
+  constexpr int TH = c0_tile_rows(RPT);
+  __shared__ float s_x[TH + 2][kC0TW + 2];
   const int tid = threadIdx.x, ty = tid >> 5, tx = tid & 31;
   const int tiles_per = tiles_w * tiles_h;
   const long long b = blockIdx.x / tiles_per;
   const int tr = (int)(blockIdx.x - b * tiles_per);
-  const int h0 = (tr / tiles_w) * kC0TH, w0 = (tr % tiles_w) * kC0TW;
+  const int h0 = (tr / tiles_w) * TH, w0 = (tr % tiles_w) * kC0TW;
   float db_ref = 0.f, lo = 0.f, hi = 1.f, range = 1.f;
   if (mode == 0) { db_ref = st->db_ref; lo = st->lo; hi = st->hi; range = hi - lo; }
   const long long snip = b % n_snip;
   const int off = b < n_snip ? 0 : off_bot;
   const long long row0 = ((mode == 0) ? (first + snip) * shift : snip * (long long)Hfull) + off;
-  for (int i = tid; i < (kC0TH + 2) * (kC0TW + 2); i += 256) {
-    const int r = i / (kC0TW + 2), cc = i - r * (kC0TW + 2);
-    const int hh = h0 + r - 1, ww = w0 + cc - 1;
-    float v = 0.f;
-    if (off + hh >= 0 && off + hh < Hfull && ww >= 0 && ww < Wimg) {
-      v = in[(size_t)(row0 + hh) * in_ld + ww];
-      if (mode == 0) {
-        v = fmaxf(v - db_ref, -kTopDbF);
-        v = __fdiv_rn(fminf(fmaxf(v, lo), hi) - lo, range);
+  // halo: warp y fetches rows y, y + 8, ...: lane x columns x and (x < 2) 32 + x - no divisions, coalesced rows
+  for (int r = ty; r < TH + 2; r += 8) {
+    const int hh = h0 + r - 1;
+    const bool row_in = off + hh >= 0 && off + hh < Hfull;
+    const float* src = in + (size_t)(row0 + hh) * in_ld;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int cc = tx + 32 * k;
+      if (k == 1 && tx >= 2) break;
+      const int ww = w0 + cc - 1;
+      float v = 0.f;
+      if (row_in && ww >= 0 && ww < Wimg) {
+        v = src[ww];
+        if (mode == 0) {
+          v = fmaxf(v - db_ref, -kTopDbF);
+          v = __fdiv_rn(fminf(fmaxf(v, lo), hi) - lo, range);
+        }
       }
+      s_x[r][cc] = v;
     }
-    s_x[r][cc] = v;
   }
   __syncthreads();
-  const int hh = h0 + ty, ww = w0 + tx;
-  if (hh >= Himg || ww >= Wimg) return;
+  const int ww = w0 + tx;
+  if (ww >= Wimg) return;
   float x[9];
 #pragma unroll
-  for (int t = 0; t < 9; ++t) x[t] = s_x[ty + t / 3][tx + t % 3];
-  float acc[16];
+  for (int t = 3; t < 9; ++t) x[t] = s_x[RPT * ty + t / 3 - 1][tx + t % 3];
 #pragma unroll
-  for (int c = 0; c < 16; ++c) acc[c] = c_conv0[144 + c];
+  for (int rr = 0; rr < RPT; ++rr) {
+    const int hh = h0 + RPT * ty + rr;
+    if (hh >= Himg) return;
 #pragma unroll
-  for (int t = 0; t < 9; ++t)
+    for (int t = 0; t < 6; ++t) x[t] = x[t + 3];
 #pragma unroll
-    for (int c = 0; c < 16; ++c) acc[c] = fmaf(x[t], c_conv0[t * 16 + c], acc[c]);
+    for (int t = 6; t < 9; ++t) x[t] = s_x[RPT * ty + rr + 2][tx + t - 6];
+    float acc[16];
 #pragma unroll
-  for (int c = 0; c < 16; ++c) acc[c] = fmaxf(acc[c], 0.f);
-  if constexpr (SPLIT) {
-    uint4 h0, l0, h1, l1;
-    fused::split8h(acc, h0, l0);
-    fused::split8h(acc + 8, h1, l1);
-    if (plane_halfs > 0) {
-      // chunk-planar: channels 0-7 and 8-15 as two (n, H, W, 8) planes plane_halfs apart - rows of a TMA box are then contiguous
-      const size_t at = (((size_t)b * Himg + hh) * Wimg + ww) * 8;
-      *reinterpret_cast<uint4*>(out + at) = h0;
-      *reinterpret_cast<uint4*>(out + at + plane_halfs) = h1;
-      *reinterpret_cast<uint4*>(out_lo + at) = l0;
-      *reinterpret_cast<uint4*>(out_lo + at + plane_halfs) = l1;
-      return;
+    for (int c = 0; c < 16; ++c) acc[c] = c_conv0[144 + c];
+#pragma unroll
+    for (int t = 0; t < 9; ++t)
+#pragma unroll
+      for (int c = 0; c < 16; ++c) acc[c] = fmaf(x[t], c_conv0[t * 16 + c], acc[c]);
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc[c] = fmaxf(acc[c], 0.f);
+    if constexpr (SPLIT) {
+      uint4 h0v, l0v, h1v, l1v;
+      fused::split8h(acc, h0v, l0v);
+      fused::split8h(acc + 8, h1v, l1v);
+      if (plane_halfs > 0) {
+        // chunk-planar: channels 0-7 and 8-15 as two (n, H, W, 8) planes plane_halfs apart - rows of a TMA box are then contiguous
+        const size_t at = (((size_t)b * Himg + hh) * Wimg + ww) * 8;
+        *reinterpret_cast<uint4*>(out + at) = h0v;
+        *reinterpret_cast<uint4*>(out + at + plane_halfs) = h1v;
+        *reinterpret_cast<uint4*>(out_lo + at) = l0v;
+        *reinterpret_cast<uint4*>(out_lo + at + plane_halfs) = l1v;
+      } else {
+        const size_t at = (((size_t)b * Himg + hh) * Wimg + ww) * 16;
+        reinterpret_cast<uint4*>(out + at)[0] = h0v;
+        reinterpret_cast<uint4*>(out + at)[1] = h1v;
+        reinterpret_cast<uint4*>(out_lo + at)[0] = l0v;
+        reinterpret_cast<uint4*>(out_lo + at)[1] = l1v;
+      }
+    } else {
+      const uint4 v0 = fused::pack8h(acc), v1 = fused::pack8h(acc + 8);
+      __half* o = out + (((size_t)b * Himg + hh) * Wimg + ww) * 16;
+      reinterpret_cast<uint4*>(o)[0] = v0;
+      reinterpret_cast<uint4*>(o)[1] = v1;
+      if (out_sub != nullptr && !(hh & 1) && !(ww & 1)) {
+        __half* os = out_sub + (((size_t)b * (Himg >> 1) + (hh >> 1)) * ((Wimg + 1) >> 1) + (ww >> 1)) * 16;
+        reinterpret_cast<uint4*>(os)[0] = v0;
+        reinterpret_cast<uint4*>(os)[1] = v1;
+      }
     }
-    const size_t at = (((size_t)b * Himg + hh) * Wimg + ww) * 16;
-    reinterpret_cast<uint4*>(out + at)[0] = h0;
-    reinterpret_cast<uint4*>(out + at)[1] = h1;
-    reinterpret_cast<uint4*>(out_lo + at)[0] = l0;
-    reinterpret_cast<uint4*>(out_lo + at)[1] = l1;
-    return;
-  }
-  const uint4 v0 = fused::pack8h(acc), v1 = fused::pack8h(acc + 8);
-  __half* o = out + (((size_t)b * Himg + hh) * Wimg + ww) * 16;
-  reinterpret_cast<uint4*>(o)[0] = v0;
-  reinterpret_cast<uint4*>(o)[1] = v1;
-  if (out_sub != nullptr && !(hh & 1) && !(ww & 1)) {
-    __half* os = out_sub + (((size_t)b * (Himg >> 1) + (hh >> 1)) * ((Wimg + 1) >> 1) + (ww >> 1)) * 16;
-    reinterpret_cast<uint4*>(os)[0] = v0;
-    reinterpret_cast<uint4*>(os)[1] = v1;
   }
 }
 
@@ -1093,9 +1115,9 @@ int forward_fused(Ctx* c, const float* d_in, int input_mode, int64_t first, int6
       c->launches++;
       ORCAI_CUDA(c, cudaGetLastError());
     } else {
-      const int tiles_w = (Wf + kC0TW - 1) / kC0TW, tiles_h = (Himg + kC0TH - 1) / kC0TH;
+      const int tiles_w = (Wf + kC0TW - 1) / kC0TW, tiles_h = (Himg + c0_tile_rows(4) - 1) / c0_tile_rows(4);
       const float* src = (input_mode == 0) ? d_in : d_in + (size_t)s0 * Himg * Wf;
-      conv0_direct_kernel<false><<<(unsigned)(m * tiles_w * tiles_h), 256, 0, c->stream>>>(src, input_mode, first + s0, shift, input_mode == 0 ? kRawLd : Wf,
+      conv0_direct_kernel<false, 4><<<(unsigned)(m * tiles_w * tiles_h), 256, 0, c->stream>>>(src, input_mode, first + s0, shift, input_mode == 0 ? kRawLd : Wf,
                                                                                           Himg, Wf, c->d_sel, act[0], static_cast<H*>(nullptr), tiles_w, tiles_h,
                                                                                           static_cast<H*>(nullptr), m, 0, Himg, 0);
       c->launches++;

@@ -131,5 +131,13 @@ template <> struct half_traits<__nv_bfloat16> {
   static __device__ __forceinline__ float to_float(__nv_bfloat16 h) { return __bfloat162float(h); }
 };
 
+// 256-bit global store (sm_100: STG.E.256), p 32-byte aligned.  A thread that owns a row (pixel / GEMM row) whose neighbours' rows
+// are far away fills a whole 32-byte sector per instruction with it; with 16-byte stores every sector is written half at a time.
+__device__ __forceinline__ void st_global_v8(float* p, const float* v) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]),
+               "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+
 }  // namespace tc
 }  // namespace orcai
