@@ -137,8 +137,8 @@ struct FB {
   static constexpr uint32_t OFF_D2 = OFF_S2 + PL * NG * LBO_S2;
   static constexpr uint32_t OFF_SPEC = OFF_D2 + D2_BYTES;
   static constexpr uint32_t OFF_BAR = OFF_SPEC + 2 * ((SPEC_BYTES + 127) / 128 * 128);
-  // barriers: bar1[N1] bar2[N2] barR[2] s1_full[N1] pool_done x_full[2] x_free[2] spec_full[2]
-  static constexpr int B_1 = 0, B_2 = N1, B_R = N1 + N2, B_S1 = N1 + N2 + 2, B_P = 2 * N1 + N2 + 2, B_X = B_P + 1, B_XF = B_X + 2, B_SP = B_XF + 2, B_D2 = B_SP + 2, NBAR = B_D2 + 1;
+  // barriers: bar1[N1] bar2[N2] barR[2] s1_full[N1] pool_done x_full[2] x_free[2] spec_full[2] d2_full carry_s1 carry_s2
+  static constexpr int B_1 = 0, B_2 = N1, B_R = N1 + N2, B_S1 = N1 + N2 + 2, B_P = 2 * N1 + N2 + 2, B_X = B_P + 1, B_XF = B_X + 2, B_SP = B_XF + 2, B_D2 = B_SP + 2, B_C1 = B_D2 + 1, B_C2 = B_D2 + 2, NBAR = B_D2 + 3;
   static constexpr uint32_t SMEM = OFF_BAR + NBAR * 8 + 16;
   static constexpr uint32_t TX_BYTES = PL * XG * ((S + 2) * WP + (S / 2) * CP) * 16;   // bytes one step's TMA loads deliver
   static constexpr int COL_R = 0, COL_1 = 2 * NP, COL_2 = 2 * NP + N1 * NP;
@@ -168,6 +168,19 @@ __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+// Measured and left off (-DORCAI_B1_ACARRY=1 builds it): the carried S1 / S2 rows copied by the TMA unit (shared -> shared bulk copies)
+// instead of through the workers' registers.  The copies queue in the TMA unit behind the next step's X tile (~6 k cycles) and
+// the workers end up waiting for them: block 1 of a 1-h recording 18.75 ms against 16.06 ms, with one X buffer or two.
+#ifndef ORCAI_B1_ACARRY
+#define ORCAI_B1_ACARRY 0
+#endif
+constexpr bool kAsyncCarry = ORCAI_B1_ACARRY != 0;
+// shared -> shared copy inside the CTA through the TMA unit (no thread touches the data), completion counted on an mbarrier
+__device__ __forceinline__ void bulk_copy_s2s(uint32_t dst, uint32_t src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "r"(src), "r"(bytes),
+               "r"(smem_u32(bar))
+               : "memory");
 }
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
@@ -277,7 +290,11 @@ struct TallView {
 };
 
 template <class G>
+#if ORCAI_B1_ACARRY
+__global__ void __cluster_dims__(1, 1, 1) __launch_bounds__(G::NTHREADS, G::CTAS)   // a cluster of one: shared -> shared bulk copies address shared::cluster
+#else
 __global__ void __launch_bounds__(G::NTHREADS, G::CTAS)
+#endif
 fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmR, int r_step, __half* __restrict__ Yr,
                    __half* __restrict__ Ysub, int H, int W, int n_strips, long long n_items,
                    const unsigned char* __restrict__ wpack,
@@ -303,6 +320,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     }
     mbar_init(&bars[G::B_SP], 1); mbar_init(&bars[G::B_SP + 1], 1);            // spectrogram tiles of the entry convolution
     mbar_init(&bars[G::B_D2], G::NEW);                                         // UF2: D2 written, one arrival per worker warp
+    mbar_init(&bars[G::B_C1], 1); mbar_init(&bars[G::B_C2], 1);                // carried S1 / S2 rows copied (bulk copies, complete_tx)
     fence_mbar_init();
   }
   __syncwarp();
@@ -707,6 +725,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     long long prev_b = 0;
     int prev_wo0 = 0, prev_a = 0;
     bool prev_carry = false;
+    uint32_t n_c1 = 0, w_c1 = 0, n_c2 = 0, w_c2 = 0;   // bulk carries issued / awaited (S1, S2): the same count in every worker
     for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
       const long long b = item / n_strips;
       const int strip = (int)(item - b * n_strips);
@@ -721,6 +740,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         for (int t = 0; t < G::N1; ++t) {
           mbar_wait(&bars[G::B_1 + t], par);
           tc_fence_after();
+          if (G::PREC && t == 0 && n_c1 > w_c1) { mbar_wait(&bars[G::B_C1], (uint32_t)(w_c1 & 1)); ++w_c1; }   // carried S1 rows in place
           if (warp == 0) FB_TRACE(10 + t, g);
           if (has0) {
             float v[16];
@@ -813,7 +833,21 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
           pool_store(g - 1, prev_b, prev_wo0, prev_a);
           if (warp == 0) FB_TRACE(21, g);
           worker_sync<G::NWORK>();   // pooling has finished reading S2
-          if (prev_carry) {
+          if (G::PREC && kAsyncCarry && prev_carry) {
+            // as for S1: one row per plane half (even / odd columns), copied by the TMA unit; awaited before epilogue 2 stores
+            if (tid == 0) {
+              fence_proxy_async();
+              mbar_arrive_expect_tx(&bars[G::B_C2], (uint32_t)(G::PL * G::NG * 2 * (G::WP / 2) * 16));
+#pragma unroll
+              for (int gq = 0; gq < G::PL * G::NG; ++gq)
+#pragma unroll
+                for (int hp = 0; hp < 2; ++hp) {
+                  const uint32_t d = sbase + G::OFF_S2 + gq * G::LBO_S2 + hp * G::S2HALF * 16;
+                  bulk_copy_s2s(d, d + G::S * (G::WP / 2) * 16, (G::WP / 2) * 16, &bars[G::B_C2]);
+                }
+            }
+            ++n_c2;
+          } else if (prev_carry) {
             // all loads of a thread first, then its stores (one shared-memory round trip instead of one per element)
             constexpr int kN2 = G::PL * G::NG * G::WP, kIt2 = (kN2 + G::NWORK - 1) / G::NWORK;
             unsigned char* cp2[kIt2];
@@ -838,6 +872,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
           if (warp == 0 && t == 0) FB_TRACE(22, g);
           mbar_wait(&bars[G::B_2 + t], par);
           tc_fence_after();
+          if (G::PREC && t == 0 && n_c2 > w_c2) { mbar_wait(&bars[G::B_C2], (uint32_t)(w_c2 & 1)); ++w_c2; }   // carried S2 row in place
           if (warp == 0) FB_TRACE(30 + t, g);
           if (has0) {
             float v[16];
@@ -868,6 +903,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
           }
         }
         tc_fence_before();
+        if (G::PREC && kAsyncCarry) fence_proxy_async();   // this thread's S1 / S2 accesses are ordered before the bulk copies issued behind the barrier
         if (warp == 0) FB_TRACE(39, g);
         worker_sync<G::NWORK>();   // every worker has seen the second convolution complete: S1 is free, S2 is written
         if (warp == 0) FB_TRACE(40, g);
@@ -875,6 +911,21 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         const bool carry = step + 1 < n_steps;
         if (g + 1 < total_steps) {
           constexpr int kCarryPlanes = G::UF2 ? G::NQ : G::PL * G::NG;
+          if (G::PREC && kAsyncCarry && carry) {
+            // the TMA unit copies the two rows plane by plane while the workers go on; they wait for it (carry_s1) before the
+            // next step's first epilogue overwrites the source rows.  (Copied by the workers - 16 KB through their registers, with
+            // a barrier behind it - this was 12 % of their step.)
+            if (tid == 0) {
+              mbar_arrive_expect_tx(&bars[G::B_C1], (uint32_t)kCarryPlanes * 2 * G::WP * 16);
+#pragma unroll
+              for (int gs = 0; gs < kCarryPlanes; ++gs) {
+                const int gq = G::UF2 ? gs : gs % G::NG + (gs / G::NG) * G::MCH;
+                const uint32_t d = sbase + G::OFF_S1 + gq * G::LBO_S1;
+                bulk_copy_s2s(d, d + G::S * G::WP * 16, 2 * G::WP * 16, &bars[G::B_C1]);
+              }
+            }
+            ++n_c1;
+          } else {
           constexpr int kN1 = kCarryPlanes * 2 * G::WP, kIt1 = (kN1 + G::NWORK - 1) / G::NWORK;
           unsigned char* cp1[kIt1];
           uint4 cv1[kIt1];
@@ -890,6 +941,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
           for (int it = 0; it < kIt1; ++it)
             if (tid + it * G::NWORK < kN1) *reinterpret_cast<uint4*>(cp1[it]) = cv1[it];
           worker_sync<G::NWORK>();   // carried rows in place before epilogue 1 overwrites their source rows
+          }
         }
         if (warp == 0) FB_TRACE(41, g);
         prev_b = b; prev_wo0 = wo0; prev_a = a; prev_carry = carry;
