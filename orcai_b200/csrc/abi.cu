@@ -219,7 +219,6 @@ void orcai_destroy(orcai_ctx* c) {
     if (sl.h_pin) cudaFreeHost(sl.h_pin);
     if (sl.done) cudaEventDestroy(sl.done);
   }
-  if (c->ev_block) cudaEventDestroy(c->ev_block);
   for (auto& ev : c->ev) if (ev) cudaEventDestroy(ev);
   if (c->stream) cudaStreamDestroy(c->stream);
   cudaGetLastError();

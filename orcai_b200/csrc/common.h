@@ -85,7 +85,6 @@ struct Ctx {
   // asynchronous predict calls in flight (oldest first: async_head)
   AsyncSlot slot[kAsyncDepth];
   int async_head = 0, async_pending = 0;
-  cudaEvent_t ev_block = nullptr;     // blocking-sync event behind wait_stream()
 };
 
 #define ORCAI_CUDA(ctx, call)                                                            \
@@ -157,7 +156,6 @@ int launch_postprocess(Ctx* c, const float* d_preds, int64_t n_snippets, int64_t
 int postprocess_begin(Ctx* c, const float* d_preds, int64_t n_snippets, int64_t T, double threshold, bool want_agg, int64_t cap, AsyncSlot* s);
 int postprocess_end(Ctx* c, AsyncSlot* s, double* h_agg, double* h_cnt, int32_t* h_label, int64_t* h_start, int64_t* h_stop,
                     int64_t cap, int64_t* n_seg);
-int wait_stream(Ctx* c);   // like cudaStreamSynchronize(c->stream), but the host thread sleeps (blocking-sync event)
 int launch_threshold_segments(Ctx* c, const double* h_agg, const double* h_cnt, int64_t S, int L, double threshold,
                               int32_t* h_label, int64_t* h_start, int64_t* h_stop, int64_t cap, int64_t* n_seg);
 

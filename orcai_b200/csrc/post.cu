@@ -249,7 +249,9 @@ int copy_out_results(Ctx* c, const PostBuffers& b, long long cap, int32_t* h_lab
   }
   if (h_agg) ORCAI_CUDA(c, cudaMemcpyAsync(pin + o_agg, b.agg, (size_t)n_agg * 8, cudaMemcpyDeviceToHost, c->stream));
   if (h_cnt) ORCAI_CUDA(c, cudaMemcpyAsync(pin + o_cnt, b.cnt, (size_t)n_cnt * 8, cudaMemcpyDeviceToHost, c->stream));
-  ORCAI_CHECK(wait_stream(c));   // the long wait of a predict call: sleep, leave the core to the loader / writer threads
+  // a spinning wait: the synchronous call returns ~0.4 ms sooner than through a blocking-sync event (measured); callers that
+  // annotate recording after recording use orcai_predict_resident_begin / _end, whose wait sleeps
+  ORCAI_CUDA(c, cudaStreamSynchronize(c->stream));
   unsigned long long total = 0;
   memcpy(&total, pin + o_tot, 8);
   if (h_agg) memcpy(h_agg, pin + o_agg, (size_t)n_agg * 8);
@@ -420,13 +422,6 @@ int postprocess_end(Ctx* c, AsyncSlot* s, double* h_agg, double* h_cnt, int32_t*
     ORCAI_CUDA(c, cudaMemcpyAsync(h_stop + s->spec, s->d_sto + s->spec, (size_t)rest * 8, cudaMemcpyDeviceToHost, c->copy_stream));
     ORCAI_CUDA(c, cudaStreamSynchronize(c->copy_stream));
   }
-  return ORCAI_OK;
-}
-
-int wait_stream(Ctx* c) {
-  if (!c->ev_block) ORCAI_CUDA(c, cudaEventCreateWithFlags(&c->ev_block, cudaEventBlockingSync | cudaEventDisableTiming));
-  ORCAI_CUDA(c, cudaEventRecord(c->ev_block, c->stream));
-  ORCAI_CUDA(c, cudaEventSynchronize(c->ev_block));
   return ORCAI_OK;
 }
 
