@@ -137,19 +137,24 @@ struct FB {
   static constexpr uint32_t OFF_D2 = OFF_S2 + PL * NG * LBO_S2;
   static constexpr uint32_t OFF_SPEC = OFF_D2 + D2_BYTES;
   static constexpr uint32_t OFF_BAR = OFF_SPEC + 2 * ((SPEC_BYTES + 127) / 128 * 128);
-  // barriers: bar1[N1] bar2[N2] barR[2] s1_full[N1] pool_done x_full[2] x_free[2] spec_full[2] d2_full carry_s1 carry_s2
-  static constexpr int B_1 = 0, B_2 = N1, B_R = N1 + N2, B_S1 = N1 + N2 + 2, B_P = 2 * N1 + N2 + 2, B_X = B_P + 1, B_XF = B_X + 2, B_SP = B_XF + 2, B_D2 = B_SP + 2, B_C1 = B_D2 + 1, B_C2 = B_D2 + 2, NBAR = B_D2 + 3;
+  // residual accumulators.  Two cover "the pooling epilogue of step g-1 runs inside worker step g".  The un-folded configuration with
+  // two X buffers takes three: the first convolution (and residual MMA) of step g+1 is then issued as soon as the workers have
+  // drained step g's first-convolution accumulators, i.e. it runs on the tensor pipe WHILE the workers' depthwise pass of step g
+  // runs on the CUDA cores - at that point the residuals of steps g-1 (not pooled yet), g and g+1 are all live.
+  static constexpr int RB = (UF2_ && XBUF_ == 2) ? 3 : 2;
+  // barriers: bar1[N1] bar2[N2] barR[RB] s1_full[N1] pool_done[RB] x_full[2] x_free[2] spec_full[2] d2_full carry_s1 carry_s2
+  static constexpr int B_1 = 0, B_2 = N1, B_R = N1 + N2, B_S1 = N1 + N2 + RB, B_P = 2 * N1 + N2 + RB, B_X = B_P + RB, B_XF = B_X + 2, B_SP = B_XF + 2, B_D2 = B_SP + 2, B_C1 = B_D2 + 1, B_C2 = B_D2 + 2, NBAR = B_D2 + 3;
   static constexpr uint32_t SMEM = OFF_BAR + NBAR * 8 + 16;
   static constexpr uint32_t TX_BYTES = PL * XG * ((S + 2) * WP + (S / 2) * CP) * 16;   // bytes one step's TMA loads deliver
-  static constexpr int COL_R = 0, COL_1 = 2 * NP, COL_2 = 2 * NP + N1 * NP;
-  static constexpr int TM_COLS = pow2cols(NP * (2 + N1 + N2));
+  static constexpr int COL_R = 0, COL_1 = RB * NP, COL_2 = RB * NP + N1 * NP;
+  static constexpr int TM_COLS = pow2cols(NP * (RB + N1 + N2));
   static_assert(NEW == 8 || NEW == 16, "worker warps come in groups of four (one per TMEM lane quadrant)");
   static_assert(NT * 2 >= NG, "each worker team drains two channel groups (16 accumulator columns)");
   static_assert(S % 2 == 0 && S >= 2, "steps advance by whole pooled rows");
   static_assert(RQ <= 128, "one residual MMA tile per step");
   static_assert(WP <= 126, "a second-convolution tile may only depend on first-convolution tiles t-1 .. t+1");
   static_assert(!CONV0 || (CIN == 16 && WP + 2 <= SPW && 2 * CP + 3 <= SPW), "entry-convolution tile: 16 channels, WP + 2 spectrogram columns");
-  static_assert(NP * (2 + N1 + N2) <= 512 && TM_COLS * CTAS <= 512, "TMEM columns");
+  static_assert(NP * (RB + N1 + N2) <= 512 && TM_COLS * CTAS <= 512, "TMEM columns");
   static_assert(SMEM <= 227 * 1024 && (SMEM + 1024) * CTAS <= 228 * 1024, "shared memory (per CTA and per SM)");
   static_assert((128 - RPIX) * 16 <= XCH * LBO_X, "residual tile over-read must stay inside the CTA's shared memory");
   static_assert(W_BYTES % 128 == 0 && LBO_X % 128 == 0 && LBO_R % 128 == 0, "TMA destinations are 128-byte aligned");
@@ -176,6 +181,16 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 #define ORCAI_B1_ACARRY 0
 #endif
 constexpr bool kAsyncCarry = ORCAI_B1_ACARRY != 0;
+// timing experiments only (wrong results): fewer taps in block 1's first convolution, no depthwise pass, no pooling epilogue
+#ifndef ORCAI_EXP_TAPS
+#define ORCAI_EXP_TAPS 9
+#endif
+#ifndef ORCAI_EXP_NODW
+#define ORCAI_EXP_NODW 0
+#endif
+#ifndef ORCAI_EXP_NOPOOL
+#define ORCAI_EXP_NOPOOL 0
+#endif
 // shared -> shared copy inside the CTA through the TMA unit (no thread touches the data), completion counted on an mbarrier
 __device__ __forceinline__ void bulk_copy_s2s(uint32_t dst, uint32_t src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "r"(src), "r"(bytes),
@@ -259,6 +274,15 @@ __device__ __forceinline__ void split8h(const float* v, uint4& hi, uint4& lo) {
     r[2 * i + 1] = v[2 * i + 1] - f.y;
   }
   lo = pack8h(r);
+}
+// two fp32 FMAs in one instruction (FFMA2, sm_100): d = a * b + d per lane, each rounded like a scalar fmaf
+__device__ __forceinline__ void fma2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  unsigned long long d, a, b;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "f"(d0), "f"(d1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+  asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
 }
 // elementwise max of m[8] with the values (hi + lo)
 __device__ __forceinline__ void fmax8_split(float (&m)[8], uint4 hi, uint4 lo) {
@@ -488,12 +512,12 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       if constexpr (G::ISS == 1) {
         auto issue_first = [&](long long g) {   // residual 1x1 and first separable convolution of step g
           if (elect_one()) {
-            const uint32_t colr = tmem + G::COL_R + (uint32_t)(g & 1) * G::NP;
+            const uint32_t colr = tmem + G::COL_R + (uint32_t)(g % G::RB) * G::NP;
             mma_f16_ss(colr, dOnes, dBR, idesc, 0);
 #pragma unroll
             for (int ks = 0; ks < G::KP1 / 16; ++ks)
               mma_x(colr, dR + ((2 * ks * G::LBO_R) >> 4), dWR + ((2 * ks * 128) >> 4), G::R_LO >> 4);
-            mma_commit(&bars[G::B_R + (int)(g & 1)]);
+            mma_commit(&bars[G::B_R + (int)(g % G::RB)]);
 #pragma unroll
             for (int t = 0; t < G::N1; ++t) {
               mma_f16_ss(tmem + G::COL_1 + t * G::NP, dOnes, dB1, idesc, 0);
@@ -536,7 +560,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
             __syncwarp();
           }
           if (g + 1 < total_steps) {
-            if (g >= 1) mbar_wait(&bars[G::B_P], par ^ 1);   // pooling of step g-1 has read the residual buffer step g+1 reuses
+            if (g + 1 >= G::RB) mbar_wait(&bars[G::B_P + (int)((g + 1) % G::RB)], (uint32_t)(((g + 1) / G::RB - 1) & 1));   // the pooling epilogue that read the residual buffer step g+1 reuses is done
             mbar_wait(&bars[G::B_X], par ^ 1);
             tc_fence_after();
             issue_first(g + 1);
@@ -547,19 +571,19 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         // Its own stream no longer follows the second convolution of the previous step, so it waits explicitly until the
         // workers have drained the accumulator tile it is about to overwrite (s1_full[t] of step g-1).
         for (long long g = 0; g < total_steps; ++g) {
-          if (g >= 2) mbar_wait(&bars[G::B_P], (uint32_t)(g & 1));   // pooling of step g-2 has read the residual buffer step g reuses
+          if (g >= G::RB) mbar_wait(&bars[G::B_P + (int)(g % G::RB)], (uint32_t)((g / G::RB - 1) & 1));   // pooling of step g-RB has read the residual buffer step g reuses
           const int xb = G::XBUF == 2 ? (int)(g & 1) : 0;
           mbar_wait(&bars[G::B_X + xb], (uint32_t)((G::XBUF == 2 ? (g >> 1) : g) & 1));
           tc_fence_after();
           FB_TRACE(1, g);
           const uint64_t dXb = dX + ((xb * G::XR_BYTES) >> 4), dRb = dR + ((xb * G::XR_BYTES) >> 4);
           if (elect_one()) {
-            const uint32_t colr = tmem + G::COL_R + (uint32_t)(g & 1) * G::NP;
+            const uint32_t colr = tmem + G::COL_R + (uint32_t)(g % G::RB) * G::NP;
             mma_f16_ss(colr, dOnes, dBR, idesc, 0);
 #pragma unroll
             for (int ks = 0; ks < G::KP1 / 16; ++ks)
               mma_x(colr, dRb + ((2 * ks * G::LBO_R) >> 4), dWR + ((2 * ks * 128) >> 4), G::R_LO >> 4);
-            mma_commit(&bars[G::B_R + (int)(g & 1)]);
+            mma_commit(&bars[G::B_R + (int)(g % G::RB)]);
           }
           __syncwarp();
 #pragma unroll
@@ -571,7 +595,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
             if (elect_one()) {
               mma_f16_ss(tmem + G::COL_1 + t * G::NP, dOnes, dB1, idesc, 0);
 #pragma unroll
-              for (int tap = 0; tap < 9; ++tap) {
+              for (int tap = 0; tap < (G::UF2 ? ORCAI_EXP_TAPS : 9); ++tap) {
                 const uint32_t aoff = (uint32_t)(G::P1_0 + 128 * t - 2 * G::WP - 1 + (tap / 3) * G::WP + (tap % 3));   // pixels = 16-byte units
 #pragma unroll
                 for (int ks = 0; ks < G::KP1 / 16; ++ks)
@@ -653,16 +677,16 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
 
     // pooling epilogue of global step gp: max-pool (3,2)/2 + residual add (+ ReLU) -> global
     auto pool_store = [&](long long gp, long long pb, int pwo0, int pa) {
-      mbar_wait(&bars[G::B_R + (int)(gp & 1)], (uint32_t)((gp >> 1) & 1));
+      mbar_wait(&bars[G::B_R + (int)(gp % G::RB)], (uint32_t)((gp / G::RB) & 1));
       tc_fence_after();
       if (has0) {
         float r[16];
-        tmem_ld16f(lane_addr + G::COL_R + (uint32_t)(gp & 1) * G::NP + g0 * 8, r);
+        tmem_ld16f(lane_addr + G::COL_R + (uint32_t)(gp % G::RB) * G::NP + g0 * 8, r);
         const int ho = (pa >> 1) + q_i, wo = pwo0 + q_j;
         // output row in the output tensor: image pb's own rows, or (tall view) the window's rows past its warm-up
         const long long orow = tall.on ? (pb * tall.stride - tall.warm) / 2 + ho : pb * Ho + ho;
         const bool row_ok = tall.on ? (ho >= tall.warm / 2 && ho < Ho && orow < tall.rows / 2) : (ho >= 0 && ho < Ho);
-        if (row < G::RQ && row_ok && wo < Wo) {
+        if (row < G::RQ && row_ok && wo < Wo && !ORCAI_EXP_NOPOOL) {
           const uint32_t p00 = (uint32_t)((2 * q_i) * (G::WP / 2) + 1 + q_j);   // even column 2 + 2j of row 2i; the odd column 3 + 2j sits S2HALF further
 #pragma unroll
           for (int u = 0; u < 2; ++u) {
@@ -679,7 +703,15 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
 #pragma unroll
               for (int q = 0; q < 6; ++q) {
                 const uint32_t off = (uint32_t)((q >> 1) * (G::WP / 2) + (q & 1) * G::S2HALF) * 16;
-                fmax8_split(y, *reinterpret_cast<const uint4*>(s2 + off), *reinterpret_cast<const uint4*>(s2 + G::S2_LO + off));
+                if constexpr (G::UF2) {
+                  // fp32 S2, one plane per channel quad: quads 2 gg, 2 gg + 1
+                  const float4 a = *reinterpret_cast<const float4*>(s2 + (size_t)gg * G::LBO_S2 + off);
+                  const float4 b = *reinterpret_cast<const float4*>(s2 + (size_t)(gg + 1) * G::LBO_S2 + off);
+                  y[0] = fmaxf(y[0], a.x); y[1] = fmaxf(y[1], a.y); y[2] = fmaxf(y[2], a.z); y[3] = fmaxf(y[3], a.w);
+                  y[4] = fmaxf(y[4], b.x); y[5] = fmaxf(y[5], b.y); y[6] = fmaxf(y[6], b.z); y[7] = fmaxf(y[7], b.w);
+                } else {
+                  fmax8_split(y, *reinterpret_cast<const uint4*>(s2 + off), *reinterpret_cast<const uint4*>(s2 + G::S2_LO + off));
+                }
               }
 #pragma unroll
               for (int i = 0; i < 8; ++i) y[i] += r[8 * u + i];
@@ -718,7 +750,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars[G::B_P]);
+      if (lane == 0) mbar_arrive(&bars[G::B_P + (int)(gp % G::RB)]);
     };
 
     long long g = 0;
@@ -785,7 +817,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         if constexpr (G::UF2) {
           // ---- depthwise 3x3 of the second separable convolution on the CUDA cores: S1 (fp32) -> D2 (hi, lo) ----
           worker_sync<G::NWORK>();   // every S1 pixel of this step and the carried rows are in place
-          for (int u = tid; u < G::NQ * G::WP; u += G::NWORK) {
+          for (int u = tid; u < (ORCAI_EXP_NODW ? 0 : G::NQ * G::WP); u += G::NWORK) {
             const int q = u / G::WP, c = u - q * G::WP;             // channel quad, column: consecutive lanes = consecutive pixels
             const float4* kw = reinterpret_cast<const float4*>(smem + G::OFF_DW2) + q;
             float4 k[9];
@@ -806,7 +838,8 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
 #pragma unroll
               for (int t = 0; t < 9; ++t) {
                 const float4 a = w[t / 3][t % 3];
-                acc.x = fmaf(a.x, k[t].x, acc.x); acc.y = fmaf(a.y, k[t].y, acc.y); acc.z = fmaf(a.z, k[t].z, acc.z); acc.w = fmaf(a.w, k[t].w, acc.w);
+                fma2(acc.x, acc.y, a.x, a.y, k[t].x, k[t].y);
+                fma2(acc.z, acc.w, a.z, a.w, k[t].z, k[t].w);
               }
               const int m = r * G::WP + c - G::P2_0;                 // accumulator row (all tiles) of this pixel
               if (m >= 0 && m < G::D2PIX) {
@@ -884,7 +917,15 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
             if (p2 < (G::S + 1) * G::WP) {
               const uint4 ninf = make_uint4(0xFC00FC00u, 0xFC00FC00u, 0xFC00FC00u, 0xFC00FC00u);
               unsigned char* dst = smem + G::OFF_S2 + g0 * G::LBO_S2 + ((c2[t] & 1) * G::S2HALF + y2[t] * (G::WP / 2) + (c2[t] >> 1)) * 16;
-              if constexpr (G::PREC) {
+              if constexpr (G::UF2) {
+                // S2 only feeds the pooling epilogue: fp32, one plane per channel quad (quads 2 g0 .. 2 g0 + 3), same pixel order
+                unsigned char* dq = dst + (size_t)g0 * G::LBO_S2;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                  if (q < 2 || has1)
+                    *reinterpret_cast<float4*>(dq + q * G::LBO_S2) = inimg ? make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3])
+                                                                           : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+              } else if constexpr (G::PREC) {
                 const uint4 z = make_uint4(0, 0, 0, 0);
                 uint4 hi, lo;
                 split8h(v, hi, lo);
