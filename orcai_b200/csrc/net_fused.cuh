@@ -96,7 +96,7 @@ struct FB {
   static constexpr int NG = OCP / 8;               // S1 / S2 chunk planes that carry data
   static constexpr int MCH = NP / 8;               // S1 chunk planes the MMA reads
   static constexpr int WP = 2 * CP + 4;
-  static constexpr int N1 = (S * WP - 2 + 127) / 128, N2 = (S * WP - 4 + 127) / 128;
+  static constexpr int N1 = (S * WP - 2 + 127) / 128, N2 = UF2_ ? 2 : (S * WP - 4 + 127) / 128;
   static constexpr int P1_0 = 2 * WP + 1, P2_0 = WP + 2;
   // one buffer: padded so that the last tile's over-read stays inside it; two buffers: packed (the over-read of rows that
   // feed no consumed accumulator row runs into the next plane / buffer, which is finite shared memory of this CTA)
@@ -123,9 +123,19 @@ struct FB {
   static constexpr uint32_t W_BYTES = OFF_DW2 + (UF2_ ? 9 * NP * 4 : 0);
   static constexpr uint32_t OFF_R = W_BYTES;
   static constexpr uint32_t R_LO = XCH * LBO_R, X_LO = XCH * LBO_X, S1_LO = MCH * LBO_S1, S2_LO = NG * LBO_S2;   // hi -> lo plane set
-  static constexpr int NQ = OCP / 4;                             // UF2: fp32 S1 planes (4-channel quads), LBO_S1 apart
-  static constexpr uint32_t S1_BYTES = UF2_ ? NQ * LBO_S1 : PL * MCH * LBO_S1;
-  static constexpr int D2PIX = N2 * 128;                         // UF2: A operand of the pointwise GEMM, accumulator-row order
+  static constexpr int NQ = OCP / 4;                             // UF2: fp32 S1 planes (4-channel quads), LBO_S1F apart
+  // UF2: an fp32 S1 plane holds the even image columns of all rows, then (S1HALF pixels further) the odd columns: [parity][row][column / 2].
+  // The depthwise pass gives every thread a PAIR of adjacent columns (4 window loads per row instead of 2 x 3) and its lanes then
+  // read consecutive 16-byte pieces of one half.  S1HALF = 5 (mod 8) pixels keeps the first epilogue's stores conflict free (its
+  // lanes alternate odd / even columns starting with an odd one: the two 64-byte runs of a quarter warp land 64 bytes apart modulo 128);
+  // the plane pitch is 64 (mod 128) bytes so that lane pairs working on quads (q, q ^ 1) of the same pixels do not collide either.
+  static constexpr int S1HALF = ((S + 2) * (WP / 2) + 7) / 8 * 8 + 5;
+  static constexpr uint32_t LBO_S1F = S1PIX * 16 + 64;
+  static_assert(!UF2_ || (S1HALF + (S + 2) * (WP / 2) <= S1PIX && WP % 2 == 0), "fp32 S1 plane: two column-parity halves");
+  static constexpr int DWP = CP;                                 // UF2: column pairs the second convolution is evaluated on (columns 2 .. 2 CP + 1)
+  static_assert(!UF2_ || S * DWP <= 128, "UF2: the even and the odd columns of a step are one accumulator tile each");
+  static constexpr uint32_t S1_BYTES = UF2_ ? NQ * LBO_S1F : PL * MCH * LBO_S1;
+  static constexpr int D2PIX = 2 * 128;                          // UF2: A operand of the pointwise GEMM, accumulator-row order: tile 0 = even columns, tile 1 = odd columns, row = (y - 1) * DWP + column pair
   static constexpr uint32_t LBO_D2 = D2PIX * 16, D2_LO = MCH * LBO_D2, D2_BYTES = UF2_ ? 2 * MCH * LBO_D2 : 0;
   static constexpr uint32_t OFF_X = OFF_R + PL * XCH * LBO_R;
   static constexpr uint32_t XR_BYTES = PL * (XCH * LBO_R + XCH * LBO_X);        // one R + X buffer; buffer b sits b * XR_BYTES further
@@ -180,7 +190,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 #ifndef ORCAI_B1_ACARRY
 #define ORCAI_B1_ACARRY 0
 #endif
-constexpr bool kAsyncCarry = ORCAI_B1_ACARRY != 0;
+constexpr bool kAsyncCarry = ORCAI_B1_ACARRY != 0;   // (written for the linear S1 layout of its time; the un-folded configuration's S1 is now split by column parity)
 // timing experiments only (wrong results): fewer taps in block 1's first convolution, no depthwise pass, no pooling epilogue
 #ifndef ORCAI_EXP_TAPS
 #define ORCAI_EXP_TAPS 9
@@ -673,7 +683,13 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
 #pragma unroll
     for (int t = 0; t < G::N1; ++t) { const int p = G::P1_0 + 128 * t + row; y1[t] = p / G::WP; c1[t] = p - y1[t] * G::WP; }
 #pragma unroll
-    for (int t = 0; t < G::N2; ++t) { const int p = G::P2_0 + 128 * t + row; y2[t] = p / G::WP; c2[t] = p - y2[t] * G::WP; }
+    for (int t = 0; t < G::N2; ++t) {
+      if constexpr (G::UF2) {   // tile t = the columns of parity t: accumulator row = (y - 1) * DWP + (column pair - 1)
+        y2[t] = row / G::DWP + 1; c2[t] = 2 * (row - (y2[t] - 1) * G::DWP + 1) + t;
+      } else {
+        const int p = G::P2_0 + 128 * t + row; y2[t] = p / G::WP; c2[t] = p - y2[t] * G::WP;
+      }
+    }
 
     // pooling epilogue of global step gp: max-pool (3,2)/2 + residual add (+ ReLU) -> global
     auto pool_store = [&](long long gp, long long pb, int pwo0, int pa) {
@@ -787,10 +803,10 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
               if constexpr (G::UF2) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] = inimg ? fmaxf(v[i], 0.f) : 0.f;
-                unsigned char* dq = smem + G::OFF_S1 + (2 * g0) * G::LBO_S1 + p1 * 16;     // quads 2 g0 .. 2 g0 + 3
+                unsigned char* dq = smem + G::OFF_S1 + (2 * g0) * G::LBO_S1F + ((c1[t] & 1) * G::S1HALF + y1[t] * (G::WP / 2) + (c1[t] >> 1)) * 16;     // quads 2 g0 .. 2 g0 + 3
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
-                  if (q < 2 || has1) *reinterpret_cast<float4*>(dq + q * G::LBO_S1) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                  if (q < 2 || has1) *reinterpret_cast<float4*>(dq + q * G::LBO_S1F) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
               } else if constexpr (G::PREC) {
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] = inimg ? fmaxf(v[i], 0.f) : 0.f;
@@ -817,36 +833,46 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         if constexpr (G::UF2) {
           // ---- depthwise 3x3 of the second separable convolution on the CUDA cores: S1 (fp32) -> D2 (hi, lo) ----
           worker_sync<G::NWORK>();   // every S1 pixel of this step and the carried rows are in place
-          for (int u = tid; u < (ORCAI_EXP_NODW ? 0 : G::NQ * G::WP); u += G::NWORK) {
-            const int q = u / G::WP, c = u - q * G::WP;             // channel quad, column: consecutive lanes = consecutive pixels
+          // thread = (column pair jj: columns 2 jj, 2 jj + 1; channel quad q); lanes 2 i, 2 i + 1 take quads (q, q ^ 1) of the same pair, so
+          // that their 8-byte D2 stores fill one 16-byte row piece and a warp's stores are contiguous
+          if (tid < (ORCAI_EXP_NODW ? 0 : G::NQ * G::DWP)) {
+            const int pr = tid >> 1, qp = pr / G::DWP, jj = pr - qp * G::DWP + 1, q = 2 * qp + (tid & 1);
             const float4* kw = reinterpret_cast<const float4*>(smem + G::OFF_DW2) + q;
             float4 k[9];
 #pragma unroll
             for (int t = 0; t < 9; ++t) k[t] = kw[t * (G::NP / 4)];
-            const unsigned char* s1q = smem + G::OFF_S1 + q * G::LBO_S1;
-            auto ld = [&](int y, int x) { return *reinterpret_cast<const float4*>(s1q + (y * G::WP + x) * 16); };
-            float4 w[3][3];
-#pragma unroll
-            for (int y = 0; y < 2; ++y)
-#pragma unroll
-              for (int x = 0; x < 3; ++x) w[y + 1][x] = ld(y, c - 1 + x);
+            const unsigned char* s1e = smem + G::OFF_S1 + q * G::LBO_S1F + jj * 16;   // even half: column 2 jj of row 0
+            const unsigned char* s1o = s1e + G::S1HALF * 16;                           // odd half: column 2 jj + 1 of row 0
+            // window columns 2 jj - 1 .. 2 jj + 2 = odd[jj - 1], even[jj], odd[jj], even[jj + 1]
+            float4 w[3][4];
+            auto ld_row = [&](int y, float4 (&d)[4]) {
+              const int o = y * (G::WP / 2) * 16;
+              d[0] = *reinterpret_cast<const float4*>(s1o + o - 16);
+              d[1] = *reinterpret_cast<const float4*>(s1e + o);
+              d[2] = *reinterpret_cast<const float4*>(s1o + o);
+              d[3] = *reinterpret_cast<const float4*>(s1e + o + 16);
+            };
+            ld_row(0, w[1]);
+            ld_row(1, w[2]);
+            unsigned char* d2 = smem + G::OFF_D2 + qp * G::LBO_D2 + (jj - 1) * 16 + (tid & 1) * 8;
 #pragma unroll
             for (int r = 1; r <= G::S; ++r) {                        // S2 row r <- S1 rows r-1 .. r+1 (unrolled: the window rotates by renaming)
 #pragma unroll
-              for (int x = 0; x < 3; ++x) { w[0][x] = w[1][x]; w[1][x] = w[2][x]; w[2][x] = ld(r + 1, c - 1 + x); }
-              float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+              for (int x = 0; x < 4; ++x) { w[0][x] = w[1][x]; w[1][x] = w[2][x]; }
+              ld_row(r + 1, w[2]);
 #pragma unroll
-              for (int t = 0; t < 9; ++t) {
-                const float4 a = w[t / 3][t % 3];
-                fma2(acc.x, acc.y, a.x, a.y, k[t].x, k[t].y);
-                fma2(acc.z, acc.w, a.z, a.w, k[t].z, k[t].w);
-              }
-              const int m = r * G::WP + c - G::P2_0;                 // accumulator row (all tiles) of this pixel
-              if (m >= 0 && m < G::D2PIX) {
+              for (int px = 0; px < 2; ++px) {                       // px = column parity = accumulator tile
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                for (int t = 0; t < 9; ++t) {
+                  const float4 a = w[t / 3][t % 3 + px];
+                  fma2(acc.x, acc.y, a.x, a.y, k[t].x, k[t].y);
+                  fma2(acc.z, acc.w, a.z, a.w, k[t].z, k[t].w);
+                }
                 const __half2 h01 = __floats2half2_rn(acc.x, acc.y), h23 = __floats2half2_rn(acc.z, acc.w);
                 const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
                 const __half2 l01 = __floats2half2_rn(acc.x - f01.x, acc.y - f01.y), l23 = __floats2half2_rn(acc.z - f23.x, acc.w - f23.y);
-                unsigned char* dst = smem + G::OFF_D2 + (q >> 1) * G::LBO_D2 + m * 16 + (q & 1) * 8;
+                unsigned char* dst = d2 + (px * 128 + (r - 1) * G::DWP) * 16;
                 uint2 hv, lv;
                 hv.x = *reinterpret_cast<const uint32_t*>(&h01); hv.y = *reinterpret_cast<const uint32_t*>(&h23);
                 lv.x = *reinterpret_cast<const uint32_t*>(&l01); lv.y = *reinterpret_cast<const uint32_t*>(&l23);
@@ -914,7 +940,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
             const long long hh = img_row0 + a + y2[t];
             const int ww = cb + c2[t];
             const bool inimg = hh >= 0 && hh < img_rows && ww >= 0 && ww < W;
-            if (p2 < (G::S + 1) * G::WP) {
+            if (G::UF2 ? row < G::S * G::DWP : p2 < (G::S + 1) * G::WP) {
               const uint4 ninf = make_uint4(0xFC00FC00u, 0xFC00FC00u, 0xFC00FC00u, 0xFC00FC00u);
               unsigned char* dst = smem + G::OFF_S2 + g0 * G::LBO_S2 + ((c2[t] & 1) * G::S2HALF + y2[t] * (G::WP / 2) + (c2[t] >> 1)) * 16;
               if constexpr (G::UF2) {
@@ -975,6 +1001,12 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
             const int i = tid + it * G::NWORK;
             const int gs = i / (2 * G::WP), px = i - gs * 2 * G::WP;
             const int gq = G::UF2 ? gs : gs % G::NG + (gs / G::NG) * G::MCH;   // lo planes sit MCH planes after the hi planes
+            if constexpr (G::UF2) {   // rows S, S + 1 -> rows 0, 1 of either column-parity half: WP contiguous pixels per half
+              const int hp = px / G::WP;
+              cp1[it] = smem + G::OFF_S1 + gq * G::LBO_S1F + (hp * G::S1HALF + px - hp * G::WP) * 16;
+              cv1[it] = (carry && i < kN1) ? *reinterpret_cast<const uint4*>(cp1[it] + G::S * (G::WP / 2) * 16) : make_uint4(0, 0, 0, 0);
+              continue;
+            }
             cp1[it] = smem + G::OFF_S1 + gq * G::LBO_S1 + px * 16;
             cv1[it] = (carry && i < kN1) ? *reinterpret_cast<const uint4*>(cp1[it] + G::S * G::WP * 16) : make_uint4(0, 0, 0, 0);
           }
