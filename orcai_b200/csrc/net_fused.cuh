@@ -40,6 +40,15 @@
 
 namespace fused {
 
+// block 1 of the fp32-grade path (FB<..., PREC, UF2>): residual accumulators (with two X buffers) and whether the second issuer
+// warp takes half of the first convolution's tiles
+#ifndef ORCAI_B1_RB
+#define ORCAI_B1_RB 3
+#endif
+#ifndef ORCAI_B1_SPLIT1
+#define ORCAI_B1_SPLIT1 0
+#endif
+
 __host__ __device__ constexpr int imax(int a, int b) { return a > b ? a : b; }
 __host__ __device__ constexpr int imin(int a, int b) { return a < b ? a : b; }
 __host__ __device__ constexpr int round8(int a) { return (a + 7) & ~7; }
@@ -151,7 +160,9 @@ struct FB {
   // two X buffers takes three: the first convolution (and residual MMA) of step g+1 is then issued as soon as the workers have
   // drained step g's first-convolution accumulators, i.e. it runs on the tensor pipe WHILE the workers' depthwise pass of step g
   // runs on the CUDA cores - at that point the residuals of steps g-1 (not pooled yet), g and g+1 are all live.
-  static constexpr int RB = (UF2_ && XBUF_ == 2) ? 3 : 2;
+  static constexpr int RB = (UF2_ && XBUF_ == 2) ? ORCAI_B1_RB : 2;
+  // UF2: the tiles of the first convolution split between the two issuer warps (the second one is idle until the depthwise pass is done)
+  static constexpr int N1A = (UF2_ && ORCAI_B1_SPLIT1) ? (N1 + 1) / 2 : N1;
   // barriers: bar1[N1] bar2[N2] barR[RB] s1_full[N1] pool_done[RB] x_full[2] x_free[2] spec_full[2] d2_full carry_s1 carry_s2
   static constexpr int B_1 = 0, B_2 = N1, B_R = N1 + N2, B_S1 = N1 + N2 + RB, B_P = 2 * N1 + N2 + RB, B_X = B_P + RB, B_XF = B_X + 2, B_SP = B_XF + 2, B_D2 = B_SP + 2, B_C1 = B_D2 + 1, B_C2 = B_D2 + 2, NBAR = B_D2 + 3;
   static constexpr uint32_t SMEM = OFF_BAR + NBAR * 8 + 16;
@@ -350,7 +361,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
     for (int i = G::B_S1; i < G::B_X; ++i) mbar_init(&bars[i], G::NEW);        // one arrival per worker warp (s1_full, pool_done)
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars[G::B_X + i], G::CONV0 ? G::NPROD : 1);                   // TMA arrive.expect_tx, or one arrival per entry-conv warp
-      mbar_init(&bars[G::B_XF + i], 1);                                        // tcgen05.commit: the buffer's first convolution is done
+      mbar_init(&bars[G::B_XF + i], G::N1A < G::N1 ? 2 : 1);                   // tcgen05.commit (one per issuing warp): the buffer's first convolution is done
     }
     mbar_init(&bars[G::B_SP], 1); mbar_init(&bars[G::B_SP + 1], 1);            // spectrogram tiles of the entry convolution
     mbar_init(&bars[G::B_D2], G::NEW);                                         // UF2: D2 written, one arrival per worker warp
@@ -467,7 +478,10 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         // X and R are free once the first convolution (and residual MMA) of the step that used the buffer has completed
         const int xb = G::XBUF == 2 ? (int)(g & 1) : 0;
         if (G::XBUF == 1) {
-          if (g > 0) mbar_wait(&bars[G::B_1 + G::N1 - 1], (uint32_t)((g - 1) & 1));
+          if (g > 0) {
+            if (G::N1A < G::N1) mbar_wait(&bars[G::B_1 + G::N1A - 1], (uint32_t)((g - 1) & 1));
+            mbar_wait(&bars[G::B_1 + G::N1 - 1], (uint32_t)((g - 1) & 1));
+          }
         } else if (g >= 2) {
           mbar_wait(&bars[G::B_XF + xb], (uint32_t)(((g >> 1) - 1) & 1));
         }
@@ -581,6 +595,11 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         // Its own stream no longer follows the second convolution of the previous step, so it waits explicitly until the
         // workers have drained the accumulator tile it is about to overwrite (s1_full[t] of step g-1).
         for (long long g = 0; g < total_steps; ++g) {
+          // three residual accumulators (UF2): this step no longer waits for the pooling epilogue of step g-2 (which the workers run
+          // AFTER their depthwise pass of step g-1), only for that depthwise pass - the tensor pipe's operand reads and the pass's
+          // window loads slow each other down when they overlap (measured: 14.9 against 13.3 ms per hour of audio), the pooling
+          // epilogue, the carries and the second epilogue are light on shared memory and run beside this step's MMAs
+          if (G::UF2 && G::RB == 3 && g >= 1) mbar_wait(&bars[G::B_D2], (uint32_t)((g - 1) & 1));
           if (g >= G::RB) mbar_wait(&bars[G::B_P + (int)(g % G::RB)], (uint32_t)((g / G::RB - 1) & 1));   // pooling of step g-RB has read the residual buffer step g reuses
           const int xb = G::XBUF == 2 ? (int)(g & 1) : 0;
           mbar_wait(&bars[G::B_X + xb], (uint32_t)((G::XBUF == 2 ? (g >> 1) : g) & 1));
@@ -597,7 +616,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
           }
           __syncwarp();
 #pragma unroll
-          for (int t = 0; t < G::N1; ++t) {
+          for (int t = 0; t < G::N1A; ++t) {
             if (g > 0) {
               mbar_wait(&bars[G::B_S1 + t], (uint32_t)((g - 1) & 1));
               tc_fence_after();
@@ -613,7 +632,7 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
                         dW1 + ((tap * G::TAP_W1 + 2 * ks * 128) >> 4), G::X_LO >> 4);
               }
               mma_commit(&bars[G::B_1 + t]);
-              if (G::XBUF == 2 && t == G::N1 - 1) mma_commit(&bars[G::B_XF + xb]);   // this step's X / R buffer may be reloaded
+              if (G::XBUF == 2 && t == G::N1A - 1) mma_commit(&bars[G::B_XF + xb]);   // this step's X / R buffer may be reloaded
             }
             __syncwarp();
           }
@@ -624,6 +643,34 @@ fused_block_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constan
         for (long long g = 0; g < total_steps; ++g) {
           const uint32_t par = (uint32_t)(g & 1);
           FB_TRACE(3, g);
+          if constexpr (G::N1A < G::N1) {
+            // this warp's share of the first convolution (it has seen the depthwise pass of step g-1 complete in its last trip)
+            const int xb = G::XBUF == 2 ? (int)(g & 1) : 0;
+            mbar_wait(&bars[G::B_X + xb], (uint32_t)((G::XBUF == 2 ? (g >> 1) : g) & 1));
+            tc_fence_after();
+            const uint64_t dXb = dX + ((xb * G::XR_BYTES) >> 4);
+#pragma unroll
+            for (int t = G::N1A; t < G::N1; ++t) {
+              if (g > 0) {
+                mbar_wait(&bars[G::B_S1 + t], (uint32_t)((g - 1) & 1));
+                tc_fence_after();
+              }
+              if (elect_one()) {
+                mma_f16_ss(tmem + G::COL_1 + t * G::NP, dOnes, dB1, idesc, 0);
+#pragma unroll
+                for (int tap = 0; tap < ORCAI_EXP_TAPS; ++tap) {
+                  const uint32_t aoff = (uint32_t)(G::P1_0 + 128 * t - 2 * G::WP - 1 + (tap / 3) * G::WP + (tap % 3));
+#pragma unroll
+                  for (int ks = 0; ks < G::KP1 / 16; ++ks)
+                    mma_x(tmem + G::COL_1 + t * G::NP, dXb + aoff + ((2 * ks * G::LBO_X) >> 4),
+                          dW1 + ((tap * G::TAP_W1 + 2 * ks * 128) >> 4), G::X_LO >> 4);
+                }
+                mma_commit(&bars[G::B_1 + t]);
+                if (G::XBUF == 2 && t == G::N1 - 1) mma_commit(&bars[G::B_XF + xb]);
+              }
+              __syncwarp();
+            }
+          }
           if constexpr (G::UF2) {
             // un-folded: the workers have written D2 = depthwise(S1) as (hi, lo) rows in accumulator order; pointwise 1x1 only
             const uint64_t dD2 = make_smem_desc(sbase + G::OFF_D2, G::LBO_D2, 128);

@@ -413,7 +413,7 @@ sep_uf_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__
 // block 1 of the fp32-grade path: one CTA per SM (the (hi, lo) plane sets fill its shared memory), two issuer warps; its output
 // is the un-rectified block output in fp32 (the next block applies the ReLU on load and walks it with stride 2 for its residual)
 #ifndef ORCAI_B1_XBUF
-#define ORCAI_B1_XBUF 1
+#define ORCAI_B1_XBUF 2
 #endif
 using FB1P = fused::FB<16, 30, 29, 4, false, 1, 8, false, 2, ORCAI_B1_XBUF, true, true>;   // measured alternatives: 16 worker warps 3.40 vs 3.25 ms per 10 min (not issue-bound); strips of 14 columns with two CTAs per SM 11.2 vs 8.9 ms per 1 024 snippets (80 registers, more halo)
 
