@@ -348,7 +348,8 @@ sep_uf_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__
 #pragma unroll
             for (int t = 0; t < 9; ++t) {
               const float4 v = w[t / 3][t % 3];
-              acc.x = fmaf(v.x, k[t].x, acc.x); acc.y = fmaf(v.y, k[t].y, acc.y); acc.z = fmaf(v.z, k[t].z, acc.z); acc.w = fmaf(v.w, k[t].w, acc.w);
+              fused::fma2(acc.x, acc.y, v.x, v.y, k[t].x, k[t].y);   // FFMA2: two fp32 FMAs per issued instruction, each rounded like fmaf
+              fused::fma2(acc.z, acc.w, v.z, v.w, k[t].z, k[t].w);
             }
             const __half2 h01 = __floats2half2_rn(acc.x, acc.y), h23 = __floats2half2_rn(acc.z, acc.w);
             const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
@@ -379,9 +380,13 @@ sep_uf_kernel(const __grid_constant__ CUtensorMap tmX, const float* __restrict__
         float v[16];
         tmem_ld16(lane_addr + c0, v);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          v[i] += s_bias[c0 + i];
-          if (ACT == 1) v[i] = fmaxf(v[i], 0.f);
+        for (int q = 0; q < 4; ++q) {
+          const float4 bq = *reinterpret_cast<const float4*>(s_bias + c0 + 4 * q);
+          v[4 * q] += bq.x; v[4 * q + 1] += bq.y; v[4 * q + 2] += bq.z; v[4 * q + 3] += bq.w;
+        }
+        if (ACT == 1) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
         }
         if (inside) {
           // one whole 32-byte sector per store instruction where the row allows it (a thread owns a pixel: its stores are 4 * ldc
