@@ -246,6 +246,7 @@ int orcai_set_option(orcai_ctx* c, const char* key, int64_t value) {
   if (!strcmp(key, "block1_path")) return net_set_block1_path(c, (int)value);
   if (!strcmp(key, "precise_tall")) return net_set_precise_tall(c, (int)value);
   if (!strcmp(key, "precise_sep_path")) return net_set_precise_tall(c, value ? 3 : 2);
+  if (!strcmp(key, "precise_lstm_tc")) return net_set_precise_tall(c, value ? 5 : 4);   // net_path 4: split-fp16 tensor-core recurrence (1, default) or the fp32 CUDA-core one (0)
   if (!strcmp(key, "net_path")) {
     if (value < 0 || value > 4)
       ORCAI_FAIL(c, ORCAI_ERR_ARG, "net_path must be 0 (fp32), 1 (fp16 tensor cores), 2 (bf16 tensor cores), 3 (fp16 fused residual blocks) or 4 (split-fp16 tensor cores, fp32 grade)");

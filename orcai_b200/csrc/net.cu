@@ -509,8 +509,9 @@ int net_set_block1_path(Ctx* c, int path) {
   return ORCAI_OK;
 }
 
-int net_set_precise_tall(Ctx* c, int on) {   // 0 / 1: precise_tall; 2 / 3: precise_sep_path 0 / 1
-  if (on >= 2) c->net->precise_sep_path = on - 2;
+int net_set_precise_tall(Ctx* c, int on) {   // 0 / 1: precise_tall; 2 / 3: precise_sep_path 0 / 1; 4 / 5: precise_lstm_tc 0 / 1
+  if (on >= 4) c->net->precise_lstm_tc = on - 4;
+  else if (on >= 2) c->net->precise_sep_path = on - 2;
   else c->net->precise_tall = on ? 1 : 0;
   return ORCAI_OK;
 }

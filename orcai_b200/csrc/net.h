@@ -85,6 +85,8 @@ struct NetWeights {
   bool precise_ready = false, tail_precise_ready = false;
   __half* tp_wih[2] = {};     // split (hi, lo) B blocks of the LSTM input projections
   __half* tp_d1 = nullptr;    // ... of Dense(128)
+  int precise_lstm_tc = 1;    // net_path 4: 1 = split-fp16 tensor-core recurrence on CTA pairs, 0 = fp32 CUDA-core recurrence
+  __half* tp_whh_hi[2] = {}, *tp_whh_lo[2] = {};   // W_hh^T as (hi, lo) fp16, [2 directions][4U x U] canonical K-major (the split recurrence)
   struct PreciseSep { float* dw = nullptr; __half* pw = nullptr; float* bias = nullptr; };   // [9][CIP] fp32, split B blocks [CIP][64], 64 floats
   PreciseSep p_sep1[kMaxBlocks], p_sep2[kMaxBlocks], p_fin;
   float* p_res_w[kMaxBlocks] = {};   // [CIP][COP] fp32, zero padded

@@ -379,6 +379,200 @@ lstm_rec_tc_kernel(const float* __restrict__ xz, const __half* __restrict__ whh_
   if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// The recurrence at fp32 grade on the tensor cores (net_path 4): every product runs as h_hi*W_hi + h_lo*W_hi + h_hi*W_lo.
+// W_hh as (hi, lo) is 256 KB per direction - more than one SM's shared memory - so a CLUSTER OF TWO CTAs owns 64 snippets x one
+// direction: CTA r keeps the recurrent weights of hidden units [64 r, 64 r + 64) (all four gates: 256 B-operand rows, hi + lo =
+// 128 KB) and computes those 256 gate columns (its TMEM) for the 64 snippets; both CTAs hold all of h_{t-1} as the (hi, lo) A
+// operand (64 KB), and the workers of CTA r write the h_t of their units into BOTH copies, the partner's through distributed
+// shared memory.  Hand-offs per step, no cluster-wide barrier:
+//     z_ready  (2 arrivals)   tcgen05.commit of BOTH CTAs' step (multicast): the accumulator is complete AND neither tensor pipe
+//                             reads h_{t-1} any more, so either copy may be overwritten
+//     h_ready  (32 arrivals)  the 16 worker warps of either CTA have written h_t (the remote ones arrive through the cluster)
+// 24 MMAs (M 128, N 256, K 16) per step and CTA; the step is bound by the gate math and the hand-off latencies.
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t kSrW = 256 * kU * 2;              // 64 KB: [n = gate*64 + unit][k] canonical, hi; the lo copy follows
+constexpr uint32_t kSrH = 128 * kU * 2;              // 32 KB: h as [k-chunk][row][8], hi; the lo copy follows
+constexpr uint32_t kSrSmem = 2 * kSrW + 2 * kSrH + 4 * 8 + 16;
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void st_cluster_v2(uint32_t addr, uint2 v) {
+  asm volatile("st.shared::cluster.v2.u32 [%0], {%1, %2};" ::"r"(addr), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {   // release at cluster scope
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {   // acquire at cluster scope
+  const uint32_t a = smem_u32(bar);
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// commit to the same barrier of both CTAs of the pair
+__device__ __forceinline__ void mma_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(1024, 1)
+lstm_rec_split_kernel(const float* __restrict__ xz, const __half* __restrict__ whh_hi, const __half* __restrict__ whh_lo, float* __restrict__ hout,
+                      long long n, int Tn) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  unsigned char* s_h = smem + 2 * kSrW;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * kSrW + 2 * kSrH);   // w_full, z_ready, h_ready
+  uint32_t* tslot = reinterpret_cast<uint32_t*>(bars + 3);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int dir = blockIdx.y;
+  const uint32_t r = cluster_ctarank();
+  const long long s0 = (long long)(blockIdx.x >> 1) * kRecRows;
+  if (tid == 0) {
+    mbar_init(&bars[0], 1);
+    mbar_init(&bars[1], 2);          // both CTAs' commits
+    mbar_init(&bars[2], 32);         // 16 worker warps of either CTA
+    fence_mbar_init();
+  }
+  for (int i = tid; i < (int)(2 * kSrH / 16); i += 1024) reinterpret_cast<uint4*>(s_h)[i] = make_uint4(0, 0, 0, 0);
+  __syncwarp();
+  if (warp == 0) tmem_alloc<256>(tslot);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                // the partner's barriers and h buffers exist before anything is sent there
+  tc_fence_after();
+  const uint32_t tmem = *tslot;
+  const uint32_t sbase = smem_u32(smem);
+
+  if (warp == 3) {
+    if (elect_one()) {
+      mbar_arrive_expect_tx(&bars[0], 2 * kSrW);
+      for (int g = 0; g < 4; ++g) {   // this CTA's units of gate g: 8 row groups of 2 KB out of the gate's 16
+        const size_t src = (size_t)dir * kRecW + (size_t)(g * 16 + 8 * r) * 2048;
+        bulk_copy_g2s(sbase + g * 16384, reinterpret_cast<const unsigned char*>(whh_hi) + src, 16384, &bars[0]);
+        bulk_copy_g2s(sbase + kSrW + g * 16384, reinterpret_cast<const unsigned char*>(whh_lo) + src, 16384, &bars[0]);
+      }
+    }
+    __syncwarp();
+    mbar_wait(&bars[0], 0);
+    constexpr uint32_t idesc = make_idesc_f16(128, 256, 0);
+    const uint64_t dh = make_smem_desc(sbase + 2 * kSrW, 128 * 16, 128);
+    const uint64_t dw = make_smem_desc(sbase, 128, (kU / 8) * 128);
+    for (int ti = 1; ti < Tn; ++ti) {            // step 0 has h = 0: no recurrent term
+      mbar_wait_cluster(&bars[2], (uint32_t)((ti - 1) & 1));
+      fence_proxy_async();                       // the partner's writes into this CTA's h (generic proxy) before the MMAs read it
+      tc_fence_after();
+      if (elect_one()) {
+#pragma unroll
+        for (int ks = 0; ks < kU / 16; ++ks) {
+          const uint64_t a = dh + ((2 * ks * 128 * 16) >> 4), b = dw + ((2 * ks * 128) >> 4);
+          mma_f16_ss(tmem, a, b, idesc, ks != 0);
+          mma_f16_ss(tmem, a + (kSrH >> 4), b, idesc, 1);
+          mma_f16_ss(tmem, a, b + (kSrW >> 4), idesc, 1);
+        }
+        mma_commit_pair(&bars[1]);
+      }
+      __syncwarp();
+    }
+  } else if ((warp & 3) < 2) {
+    const int quad = warp & 3, cg = warp >> 2;     // cg 0..7: 8 of this CTA's 64 hidden units each
+    const int row = quad * 32 + lane;
+    const long long s = s0 + row;
+    const bool ok = s < n;
+    const uint32_t lane_addr = tmem + ((uint32_t)(quad * 32) << 16);
+    const int u0 = cg * 8, ug0 = 64 * (int)r + u0;   // first unit: column inside a gate's 64 columns / hidden unit
+    const uint32_t sh_local = smem_u32(s_h), sh_peer = map_to_cta(sh_local, r ^ 1u);
+    const uint32_t hbar_local = smem_u32(&bars[2]), hbar_peer = map_to_cta(hbar_local, r ^ 1u);
+    float cst[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) cst[i] = 0.f;
+    for (int ti = 0; ti < Tn; ++ti) {
+      const int t = dir ? Tn - 1 - ti : ti;
+      const float* xrow = xz + ((size_t)(ok ? s : 0) * Tn + t) * (2 * kG4) + (size_t)dir * kG4 + ug0;
+      float* hrow = hout + ((size_t)(ok ? s : 0) * Tn + t) * (2 * kU) + (size_t)dir * kU + ug0;
+      if (ti + 2 < Tn) {   // the projected inputs of the step after next: into L2 (they stream from HBM)
+        const int t2 = dir ? Tn - 3 - ti : ti + 2;
+        const float* xn = xz + ((size_t)(ok ? s : 0) * Tn + t2) * (2 * kG4) + (size_t)dir * kG4 + ug0;
+#pragma unroll
+        for (int gte = 0; gte < 4; ++gte) asm volatile("prefetch.global.L2 [%0];" ::"l"(xn + gte * kU));
+      }
+      float4 xa[2][4];
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int gte = 0; gte < 4; ++gte) xa[j][gte] = __ldg(reinterpret_cast<const float4*>(xrow + gte * kU + 4 * j));
+      if (ti > 0) {
+        mbar_wait(&bars[1], (uint32_t)((ti - 1) & 1));
+        tc_fence_after();
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        float z[4][4];
+#pragma unroll
+        for (int gte = 0; gte < 4; ++gte) {
+          if (ti > 0) {
+            tmem_ld4f(lane_addr + gte * 64 + u0 + 4 * j, z[gte]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) z[gte][i] = 0.f;
+          }
+          z[gte][0] += xa[j][gte].x; z[gte][1] += xa[j][gte].y; z[gte][2] += xa[j][gte].z; z[gte][3] += xa[j][gte].w;
+        }
+        float h[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float ig = sigmoid_fast(z[0][i]), fg = sigmoid_fast(z[1][i]), gg = tanh_fast(z[2][i]), og = sigmoid_fast(z[3][i]);
+          const float cn = fg * cst[4 * j + i] + ig * gg;
+          cst[4 * j + i] = cn;
+          h[i] = og * tanh_fast(cn);
+        }
+        const __half2 h01 = __floats2half2_rn(h[0], h[1]), h23 = __floats2half2_rn(h[2], h[3]);
+        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+        const __half2 l01 = __floats2half2_rn(h[0] - f01.x, h[1] - f01.y), l23 = __floats2half2_rn(h[2] - f23.x, h[3] - f23.y);
+        uint2 hp, lp;
+        hp.x = *reinterpret_cast<const uint32_t*>(&h01); hp.y = *reinterpret_cast<const uint32_t*>(&h23);
+        lp.x = *reinterpret_cast<const uint32_t*>(&l01); lp.y = *reinterpret_cast<const uint32_t*>(&l23);
+        const int u = ug0 + 4 * j;
+        const uint32_t off = (uint32_t)(u >> 3) * (128 * 16) + (uint32_t)row * 16 + (uint32_t)(u & 4) * 2;
+        *reinterpret_cast<uint2*>(s_h + off) = hp;
+        *reinterpret_cast<uint2*>(s_h + kSrH + off) = lp;
+        st_cluster_v2(sh_peer + off, hp);
+        st_cluster_v2(sh_peer + kSrH + off, lp);
+        if (ok) *reinterpret_cast<float4*>(hrow + 4 * j) = make_float4(h[0], h[1], h[2], h[3]);
+      }
+      if (ti + 1 < Tn) {
+        fence_proxy_async();
+        tc_fence_before();
+        asm volatile("fence.acq_rel.cluster;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive_cluster(hbar_local);
+          mbar_arrive_cluster(hbar_peer);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                // nobody leaves while the partner may still send
+  if (warp == 0) tmem_dealloc<256>(tmem);
+}
+
 // Dense(7) + sigmoid on the Dense(128)+ReLU activations (BatchNorm folded into the weights): one warp per row
 __global__ void __launch_bounds__(256)
 dense_out_kernel(const float* __restrict__ d1, const float* __restrict__ w2, const float* __restrict__ b2, float* __restrict__ out,
@@ -523,6 +717,24 @@ int net_tail_precise_prepare(Ctx* c) {
     ORCAI_CHECK(net_pack_split_b(c, nw->h_lstm_wih[l].data(), I, 2 * G, 2 * G, &nw->tp_wih[l]));
   }
   ORCAI_CHECK(net_pack_split_b(c, nw->h_d1_w.data(), 2 * U, 128, 128, &nw->tp_d1));
+  if (U == kU) {
+    // W_hh^T per direction as (hi, lo): B operand rows n = gate*128 + unit, K = previous hidden unit; recurrent_kernel is [U][4U]
+    for (int l = 0; l < 2; ++l) {
+      std::vector<__half> whi((size_t)2 * G * U), wlo((size_t)2 * G * U);
+      for (int d = 0; d < 2; ++d)
+        for (int n = 0; n < G; ++n)
+          for (int k = 0; k < U; ++k) {
+            const float w = nw->h_lstm_whh[l][(size_t)d * U * G + (size_t)k * G + n];
+            const __half hi = __float2half_rn(w);
+            const size_t at = (size_t)d * G * U + ((size_t)(n / 8) * (U / 8) * 128 + (size_t)(k / 8) * 128 + (n % 8) * 16 + (k % 8) * 2) / 2;
+            whi[at] = hi;
+            wlo[at] = __float2half_rn(w - __half2float(hi));
+          }
+      ORCAI_CHECK(upload_half(c, whi, &nw->tp_whh_hi[l]));
+      ORCAI_CHECK(upload_half(c, wlo, &nw->tp_whh_lo[l]));
+    }
+    ORCAI_CUDA(c, cudaFuncSetAttribute(lstm_rec_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSrSmem));
+  }
   nw->tail_precise_ready = true;
   return ORCAI_OK;
 }
@@ -541,11 +753,21 @@ int net_tail_precise(Ctx* c, const float* feat, float* scratch, long long m, flo
   float* d1 = h2 + (size_t)rows * 2 * U;        // (rows, 128)
   ORCAI_CHECK(net_gemm_split(c, feat, nw->feat, nw->tp_wih[0], nw->lstm_bih[0], xz, 2 * G, rows, 2 * G, nw->feat, 2 * G, 0));
   net_mark(c, mk);  // 6: lstm1 input projection
-  ORCAI_CHECK(net_lstm_rec_fp32(c, xz, nw->lstm_whh[0], h1, m, Tn));
+  // the recurrence: split-fp16 tensor-core kernel on CTA pairs (lstm_rec 1, default) or the fp32 CUDA-core kernel of the reference-grade path
+  auto recurrence = [&](int l, float* hout) -> int {
+    if (U != kU || !nw->precise_lstm_tc) return net_lstm_rec_fp32(c, xz, nw->lstm_whh[l], hout, m, Tn);
+    if (m <= 0) return ORCAI_OK;
+    const dim3 rgrid((unsigned)(2 * ((m + kRecRows - 1) / kRecRows)), 2);
+    lstm_rec_split_kernel<<<rgrid, 1024, kSrSmem, c->stream>>>(xz, nw->tp_whh_hi[l], nw->tp_whh_lo[l], hout, m, Tn);
+    c->launches++;
+    ORCAI_CUDA(c, cudaGetLastError());
+    return ORCAI_OK;
+  };
+  ORCAI_CHECK(recurrence(0, h1));
   net_mark(c, mk);  // 7: lstm1 recurrence
   ORCAI_CHECK(net_gemm_split(c, h1, 2 * U, nw->tp_wih[1], nw->lstm_bih[1], xz, 2 * G, rows, 2 * G, 2 * U, 2 * G, 0));
   net_mark(c, mk);  // 8: lstm2 input projection
-  ORCAI_CHECK(net_lstm_rec_fp32(c, xz, nw->lstm_whh[1], h2, m, Tn));
+  ORCAI_CHECK(recurrence(1, h2));
   net_mark(c, mk);  // 9: lstm2 recurrence
   ORCAI_CHECK(net_gemm_split(c, h2, 2 * U, nw->tp_d1, nw->d1_b, d1, 128, rows, 128, 2 * U, 128, 1));
   {
