@@ -714,7 +714,8 @@ int net_tail_precise_prepare(Ctx* c) {
   const int U = nw->U, G = 4 * U;
   for (int l = 0; l < 2; ++l) {
     const int I = l == 0 ? nw->feat : 2 * U;
-    ORCAI_CHECK(net_pack_split_b(c, nw->h_lstm_wih[l].data(), I, 2 * G, 2 * G, &nw->tp_wih[l]));
+    // column blocks of 256: every CTA stages (splits) its 128 A rows once per block, so 4 blocks instead of 16 quarter that work
+    ORCAI_CHECK(upload_half(c, pack_gemm_b(nw->h_lstm_wih[l].data(), I, 2 * G, 256, true), &nw->tp_wih[l]));
   }
   ORCAI_CHECK(net_pack_split_b(c, nw->h_d1_w.data(), 2 * U, 128, 128, &nw->tp_d1));
   if (U == kU) {
@@ -751,7 +752,7 @@ int net_tail_precise(Ctx* c, const float* feat, float* scratch, long long m, flo
   float* h1 = xz + (size_t)rows * 2 * G;        // (rows, 2U)
   float* h2 = h1 + (size_t)rows * 2 * U;        // (rows, 2U)
   float* d1 = h2 + (size_t)rows * 2 * U;        // (rows, 128)
-  ORCAI_CHECK(net_gemm_split(c, feat, nw->feat, nw->tp_wih[0], nw->lstm_bih[0], xz, 2 * G, rows, 2 * G, nw->feat, 2 * G, 0));
+  ORCAI_CHECK((run_gemm_tc<float, 256, 0, true>(c, feat, nw->feat, nw->tp_wih[0], nw->lstm_bih[0], xz, 2 * G, rows, 2 * G, nw->feat, 2 * G)));
   net_mark(c, mk);  // 6: lstm1 input projection
   // the recurrence: split-fp16 tensor-core kernel on CTA pairs (lstm_rec 1, default) or the fp32 CUDA-core kernel of the reference-grade path
   auto recurrence = [&](int l, float* hout) -> int {
@@ -765,7 +766,7 @@ int net_tail_precise(Ctx* c, const float* feat, float* scratch, long long m, flo
   };
   ORCAI_CHECK(recurrence(0, h1));
   net_mark(c, mk);  // 7: lstm1 recurrence
-  ORCAI_CHECK(net_gemm_split(c, h1, 2 * U, nw->tp_wih[1], nw->lstm_bih[1], xz, 2 * G, rows, 2 * G, 2 * U, 2 * G, 0));
+  ORCAI_CHECK((run_gemm_tc<float, 256, 0, true>(c, h1, 2 * U, nw->tp_wih[1], nw->lstm_bih[1], xz, 2 * G, rows, 2 * G, 2 * U, 2 * G)));
   net_mark(c, mk);  // 8: lstm2 input projection
   ORCAI_CHECK(recurrence(1, h2));
   net_mark(c, mk);  // 9: lstm2 recurrence
