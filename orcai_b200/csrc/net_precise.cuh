@@ -125,10 +125,11 @@ pool_res_f32_kernel(const float* __restrict__ s2, const float* __restrict__ xs, 
       for (int p = 0; p < kPoolPx; ++p) {
         const float4 x4 = xv[p];
         // per output channel the same FMA order as with one pixel per thread: ci ascending
-        a[p].x = fmaf(x4.x, w0.x, a[p].x); a[p].y = fmaf(x4.x, w0.y, a[p].y); a[p].z = fmaf(x4.x, w0.z, a[p].z); a[p].w = fmaf(x4.x, w0.w, a[p].w);
-        a[p].x = fmaf(x4.y, w1.x, a[p].x); a[p].y = fmaf(x4.y, w1.y, a[p].y); a[p].z = fmaf(x4.y, w1.z, a[p].z); a[p].w = fmaf(x4.y, w1.w, a[p].w);
-        a[p].x = fmaf(x4.z, w2.x, a[p].x); a[p].y = fmaf(x4.z, w2.y, a[p].y); a[p].z = fmaf(x4.z, w2.z, a[p].z); a[p].w = fmaf(x4.z, w2.w, a[p].w);
-        a[p].x = fmaf(x4.w, w3.x, a[p].x); a[p].y = fmaf(x4.w, w3.y, a[p].y); a[p].z = fmaf(x4.w, w3.z, a[p].z); a[p].w = fmaf(x4.w, w3.w, a[p].w);
+        // FFMA2 (two output channels per instruction, the pixel value as the broadcast operand); each lane rounds like fmaf
+        fused::fma2(a[p].x, a[p].y, w0.x, w0.y, x4.x, x4.x); fused::fma2(a[p].z, a[p].w, w0.z, w0.w, x4.x, x4.x);
+        fused::fma2(a[p].x, a[p].y, w1.x, w1.y, x4.y, x4.y); fused::fma2(a[p].z, a[p].w, w1.z, w1.w, x4.y, x4.y);
+        fused::fma2(a[p].x, a[p].y, w2.x, w2.y, x4.z, x4.z); fused::fma2(a[p].z, a[p].w, w2.z, w2.w, x4.z, x4.z);
+        fused::fma2(a[p].x, a[p].y, w3.x, w3.y, x4.w, x4.w); fused::fma2(a[p].z, a[p].w, w3.z, w3.w, x4.w, x4.w);
         xv[p] = xn[p];
       }
     }

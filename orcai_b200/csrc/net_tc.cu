@@ -392,7 +392,7 @@ conv0_direct_kernel(const float* __restrict__ in, int mode, long long first, int
 #pragma unroll
     for (int t = 0; t < 9; ++t)
 #pragma unroll
-      for (int c = 0; c < 16; ++c) acc[c] = fmaf(x[t], c_conv0[t * 16 + c], acc[c]);
+      for (int c = 0; c < 16; c += 2) fused::fma2(acc[c], acc[c + 1], c_conv0[t * 16 + c], c_conv0[t * 16 + c + 1], x[t], x[t]);   // FFMA2: two channels per instruction
 #pragma unroll
     for (int c = 0; c < 16; ++c) acc[c] = fmaxf(acc[c], 0.f);
     if constexpr (SPLIT) {
