@@ -106,6 +106,9 @@ stft_db_kernel(const SampleT* __restrict__ pcm, long long n_samples, long long T
       pmax = fmaxf(pmax, (live && j >= stat_row0 && j < stat_row1) ? pw : 0.0f);   // time chunks: only the rows this chunk owns
       if (live && k >= band_lo && k < band_hi) out[k] = power_to_db(pw, kPrecise);
     });
+    // pad columns of the row (band_hi - band_lo .. ld): +inf, which the radix select counts above every real value (select.cu)
+    if (live)
+      for (int cpad = band_hi + t; cpad < band_lo + ld; cpad += 8) out[cpad] = __int_as_float(0x7f800000);
     __syncwarp();
   }
   unsigned int m = __reduce_max_sync(0xffffffffu, __float_as_uint(pmax));  // non-negative floats order as uints

@@ -45,7 +45,7 @@ int main(int argc, char** argv) {
     for (int k = 0; k < 257; ++k) gmax = std::max(gmax, PD[j * 257 + k]);
   }
   const float floor_p = gmax * 1e-8f;
-  const int NB = 12;  // buckets of -log10(r): [0,1) ... [11,inf)
+  const int NB = 24;  // half-decade buckets of -log10(r)
   double worst[NB] = {0}, worst_fl[NB] = {0};
   long long cnt[NB] = {0};
   auto db = [](float p) { return 10.0 * std::log10((double)std::max(p, 1e-10f)); };
@@ -55,7 +55,7 @@ int main(int argc, char** argv) {
     for (int k = 0; k < 257; ++k) sum += pf[k];
     for (int k = 0; k < 171; ++k) mn = std::min(mn, pf[k]);
     const double mean = sum / 257.0;
-    int b = mean > 0 ? (int)std::floor(-std::log10(std::max((double)mn, 1e-300) / mean)) : 0;
+    int b = mean > 0 ? (int)std::floor(-2.0 * std::log10(std::max((double)mn, 1e-300) / mean)) : 0;
     b = std::min(std::max(b, 0), NB - 1);
     cnt[b]++;
     for (int k = 0; k < 171; ++k) {
@@ -67,6 +67,6 @@ int main(int argc, char** argv) {
     }
   }
   std::printf("frames %lld gmax %.4g\n  -log10(min_inband/mean)   frames   max dB err   max dB err after the -80 dB floor\n", T, gmax);
-  for (int b = 0; b < NB; ++b) std::printf("  [%2d,%2d)  %9lld   %.3e   %.3e\n", b, b + 1, cnt[b], worst[b], worst_fl[b]);
+  for (int b = 0; b < NB; ++b) std::printf("  [%4.1f,%4.1f)  %9lld   %.3e   %.3e\n", b * 0.5, b * 0.5 + 0.5, cnt[b], worst[b], worst_fl[b]);
   return 0;
 }
