@@ -46,8 +46,8 @@ BLOCK1_EXECUTED_MAC_PER_SNIPPET = 123 * 3 * 88 * 128 * 32 * 16
 # kernel (profiles/; the file is named with the number): net_path -> {bytes_per_snippet, source}
 BLOCK1_TRAFFIC = {
     3: {"bytes_per_snippet": (734.0e6 + 425.0e6) / 182, "source": "profiles/r01g_ncu_full_summary.csv (182-snippet launch)"},
-    4: {"bytes_per_snippet": (7.654241e9 + 3.691397e9) / 1833, "source": "profiles/r02r_ncu_full_block1.csv (tall launch over the 1 833 snippets of the 1-h recording; "
-                                                                         "the border-image launch adds 6 %)"},
+    4: {"bytes_per_snippet": (7.654334e9 + 3.691655e9 + 0.321043e9 + 0.137265e9) / 1833,
+        "source": "profiles/r02zv_ncu_full_summary.csv (tall launch over the 1 833 snippets of the 1-h recording + its border-image launch)"},
 }
 SELECT_PASSES = 3   # times the select streams the 704 B/frame dB buffer
 

@@ -143,3 +143,30 @@ def test_one_hour_properties(ctx):
     P = np.abs(S[:171].T) ** 2
     ref = np.maximum(10 * np.log10(np.maximum(1e-10, P)) - st.db_ref, -80.0)
     assert np.abs(db[j0 : j0 + ref.shape[0]].cpu().numpy() - ref).max() <= DB_TOL
+
+
+def test_select_shared_prefixes_and_floor_mass(ctx):
+    """The radix select's corner paths (select.cu): both ranks inside one digit (one histogram serves both), a rank inside the
+    -80 dB floor's digit, and nearly every cell ON the floor (ranks share every prefix; the pass-0 table sees one digit)."""
+    rng = np.random.default_rng(3)
+    n = 48000 * 20
+    t = np.arange(4096)
+    burst = (32000 * np.sin(2 * np.pi * 3000 * t / 48000)).astype(np.int16)
+    # (a) a short full-scale burst in digital silence: > 99.9 % of the cells sit exactly on the floor -> lo = hi = -80
+    pcm = np.zeros(n, np.int16)
+    pcm[100000 : 100000 + 256] = burst[:256]
+    spec, st = ctx.spectrogram(pcm)
+    db = ctx.read_db(0, spec.shape[0])
+    flat = np.sort(db.ravel())
+    assert st.lo == -80.0 and st.hi == -80.0 and flat[st.rank_lo] == st.lo and flat[st.rank_hi] == st.hi
+    assert db.max() == 0.0
+    # (b) faint noise under a longer burst: the low rank ON the floor, the high one at -66 dB - both inside [-80, -64) dB = one 11-bit digit
+    pcm = np.round(40.0 * rng.standard_normal(n)).astype(np.int16)
+    pcm[100000 : 100000 + 4096] += burst
+    _, st = check(ctx, pcm)
+    assert -80.0 <= st.lo < st.hi < -64.0
+    # (c) louder noise: the low rank in the floor's digit, the high one in another
+    pcm = np.round(300.0 * rng.standard_normal(n)).astype(np.int16)
+    pcm[100000 : 100000 + 4096] += burst
+    _, st = check(ctx, pcm)
+    assert st.lo < -64.0 < st.hi
