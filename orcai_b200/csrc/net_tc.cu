@@ -351,26 +351,23 @@ conv0_direct_kernel(const float* __restrict__ in, int mode, long long first, int
   const long long snip = b % n_snip;
   const int off = b < n_snip ? 0 : off_bot;
   const long long row0 = ((mode == 0) ? (first + snip) * shift : snip * (long long)Hfull) + off;
-  // halo: warp y fetches rows y, y + 8, ...: lane x columns x and (x < 2) 32 + x - no divisions, coalesced rows
-  for (int r = ty; r < TH + 2; r += 8) {
-    const int hh = h0 + r - 1;
-    const bool row_in = off + hh >= 0 && off + hh < Hfull;
-    const float* src = in + (size_t)(row0 + hh) * in_ld;
+  // halo: the (TH + 2) x 34 elements are dealt to the 256 threads as one flat list (division by the constant 34 = one multiply
+  // + shift).  Dealing rows to warps and the two extra columns to lanes 0 / 1 ran the whole load + normalise body twice per row for
+  // 34 useful lanes of 64: the halo cost as many instructions as half of the convolution.
+  constexpr int HW = kC0TW + 2;
 #pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      const int cc = tx + 32 * k;
-      if (k == 1 && tx >= 2) break;
-      const int ww = w0 + cc - 1;
-      float v = 0.f;
-      if (row_in && ww >= 0 && ww < Wimg) {
-        v = src[ww];
-        if (mode == 0) {
-          v = fmaxf(v - db_ref, -kTopDbF);
-          v = __fdiv_rn(fminf(fmaxf(v, lo), hi) - lo, range);
-        }
+  for (int e = tid; e < (TH + 2) * HW; e += 256) {
+    const int r = e / HW, cc = e - r * HW;
+    const int hh = h0 + r - 1, ww = w0 + cc - 1;
+    float v = 0.f;
+    if (off + hh >= 0 && off + hh < Hfull && ww >= 0 && ww < Wimg) {
+      v = in[(size_t)(row0 + hh) * in_ld + ww];
+      if (mode == 0) {
+        v = fmaxf(v - db_ref, -kTopDbF);
+        v = __fdiv_rn(fminf(fmaxf(v, lo), hi) - lo, range);
       }
-      s_x[r][cc] = v;
     }
+    s_x[r][cc] = v;
   }
   __syncthreads();
   const int ww = w0 + tx;
