@@ -335,7 +335,7 @@ __host__ __device__ constexpr int c0_tile_rows(int rpt) { return 8 * rpt; }
 // them with a sliding 3 x 3 window (RPT = 4 for tall images: the index arithmetic, the halo's normalisation and the barrier - half
 // of the instructions with one pixel per thread - are shared by four pixels; RPT = 1 for the 8-row border images).
 template <bool SPLIT, int RPT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 6)
 conv0_direct_kernel(const float* __restrict__ in, int mode, long long first, int shift, int in_ld, int Himg, int Wimg,
                     const SelectState* __restrict__ st, __half* __restrict__ out, __half* __restrict__ out_sub,
                     int tiles_w, int tiles_h, __half* __restrict__ out_lo, long long n_snip, int off_bot, int Hfull, long long plane_halfs) {
