@@ -202,6 +202,7 @@ void orcai_destroy(orcai_ctx* c) {
   net_destroy(c);
   for (auto& t : c->d_tables) if (t) cudaFree(t);
   for (auto& t : c->d_tables64) if (t) cudaFree(t);
+  for (auto& t : c->d_tables64_16) if (t) cudaFree(t);
   if (c->d_sel) cudaFree(c->d_sel);
   if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);
   if (c->d_pcm) cudaFree(c->d_pcm);
@@ -254,6 +255,7 @@ int orcai_set_option(orcai_ctx* c, const char* key, int64_t value) {
   }
   if (!strcmp(key, "debug_stop")) return net_set_debug_stop(c, (int)value);
   if (!strcmp(key, "stft_f64")) { c->stft_f64 = value ? 1 : 0; c->have_stats = false; return ORCAI_OK; }
+  if (!strcmp(key, "stft_threads")) { c->stft_threads = value == 8 ? 8 : 16; c->have_stats = false; return ORCAI_OK; }
   ORCAI_FAIL(c, ORCAI_ERR_ARG, "unknown option '%s'", key);
 }
 

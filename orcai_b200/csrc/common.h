@@ -58,6 +58,7 @@ struct Ctx {
   // STFT tables on device: [0]=float input scale, [1]=int16 input scale ; each 768 float2
   float* d_tables[2] = {nullptr, nullptr};
   double* d_tables64[2] = {nullptr, nullptr};
+  double* d_tables64_16[2] = {nullptr, nullptr};   // float64 tables of the 16-threads-per-frame kernel (16 x 16 stage-A twiddles)
   int h_flags[2] = {0, 1};           // stable host source for tiny async H2D copies
   SelectState* d_sel = nullptr;
   // current recording
@@ -82,6 +83,7 @@ struct Ctx {
   uint64_t launches = 0;
   int sm_count = 148;
   int stft_f64 = 1;                   // 1: float64 FFT (parity grade, default), 0: float32 FFT (fast variant)
+  int stft_threads = 16;              // threads per frame of the float64 kernel: 16 (default) or 8 (the round-1 decomposition)
   // asynchronous predict calls in flight (oldest first: async_head)
   AsyncSlot slot[kAsyncDepth];
   int async_head = 0, async_pending = 0;

@@ -13,8 +13,9 @@ struct StftHostTables {
 };
 
 // scale = 0.5 for float input in [-1,1]; 0.5/32768 for raw int16 input (both exact powers of two).
+// rows = 32: the 32 x 8 decomposition of stft_core.cuh (tw at k1*8 + n2); rows = 16: the 16 x 16 one of stft_core16.cuh (k1*16 + n2)
 template <typename T>
-inline StftHostTables<T> make_stft_tables(double scale) {
+inline StftHostTables<T> make_stft_tables(double scale, int rows = 32) {
   const double PI = 3.14159265358979323846;
   StftHostTables<T> t;
   t.win.resize(512);
@@ -27,11 +28,12 @@ inline StftHostTables<T> make_stft_tables(double scale) {
     t.win[2 * m] = static_cast<T>(h0 * scale);
     t.win[2 * m + 1] = static_cast<T>(h1 * scale);
   }
-  for (int k1 = 0; k1 < 32; ++k1)
-    for (int n2 = 0; n2 < 8; ++n2) {
+  const int cols = 256 / rows;
+  for (int k1 = 0; k1 < rows; ++k1)
+    for (int n2 = 0; n2 < cols; ++n2) {
       const double a = -2.0 * PI * ((n2 * k1) % 256) / 256.0;
-      t.tw[2 * (8 * k1 + n2)] = static_cast<T>(std::cos(a));
-      t.tw[2 * (8 * k1 + n2) + 1] = static_cast<T>(std::sin(a));
+      t.tw[2 * (cols * k1 + n2)] = static_cast<T>(std::cos(a));
+      t.tw[2 * (cols * k1 + n2) + 1] = static_cast<T>(std::sin(a));
     }
   for (int k = 0; k < 256; ++k) {
     const double a = -2.0 * PI * k / 512.0;

@@ -170,3 +170,22 @@ def test_select_shared_prefixes_and_floor_mass(ctx):
     pcm[100000 : 100000 + 4096] += burst
     _, st = check(ctx, pcm)
     assert st.lo < -64.0 < st.hi
+
+
+def test_both_float64_decompositions(ctx):
+    """K1 float64: 16 threads per frame (default, stft_core16.cuh) and 8 threads per frame (stft_core.cuh) are two
+    factorisations of the same 256-point FFT: both within the dB gate of the oracle, and within float rounding of each other."""
+    pcm = synth_pcm16(30.0, seed=20251018 + 5, calls_per_minute=30.0)
+    db_ref, _, lo, hi = oracle(pcm16_to_float(pcm))
+    got = {}
+    try:
+        for threads in (16, 8):
+            ctx.set_option("stft_threads", threads)
+            spec, st = ctx.spectrogram(pcm)
+            got[threads] = ctx.read_db(0, spec.shape[0])
+            assert np.abs(got[threads] - db_ref).max() <= DB_TOL
+            assert abs(st.lo - lo) <= DB_TOL and abs(st.hi - hi) <= DB_TOL
+    finally:
+        ctx.set_option("stft_threads", 16)
+    assert np.abs(got[16] - got[8]).max() <= 1e-4
+    # ragged edges through the 16-thread kernel's guarded loads are covered by test_ragged_lengths (it is the default)

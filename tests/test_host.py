@@ -592,3 +592,19 @@ def test_table_pipeline_keeps_two_recordings_in_flight_and_reports_failures_per_
     assert (out / "r3_orcai-V1_predicted.txt").read_text().splitlines()[1].split("\t")[2] == P["calls"][4 % 7] + "*"
     assert len(errors) == 3 and "r2" in errors[0] and "r4" in errors[1] and "shorter than one snippet" in errors[1] and "r5" in errors[2] and "already exists" in errors[2]
     assert pools and pools[0].out == 0           # every page-locked buffer went back to the pool
+
+
+def test_stft_kernel_dataflow_replayed_on_the_cpu(tmp_path):
+    """tests/host_emul/stft_emul.cpp replays K1's per-thread building blocks (stft_core.cuh: 8 threads per frame,
+    stft_core16.cuh: 16 threads per frame) thread by thread on the CPU and checks every bin against a naive float64 DFT."""
+    import shutil
+    import subprocess
+
+    gxx = shutil.which("g++")
+    if gxx is None:
+        pytest.skip("g++ not available")
+    root = Path(__file__).resolve().parent.parent
+    exe = tmp_path / "stft_emul"
+    subprocess.run([gxx, "-O2", "-std=c++17", "-I", str(root / "orcai_b200" / "csrc"), str(root / "tests" / "host_emul" / "stft_emul.cpp"), "-o", str(exe)], check=True)
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout + r.stderr
