@@ -205,6 +205,8 @@ int orcai_chunk_select_end(orcai_ctx* ctx, const uint32_t* keys, orcai_spec_stat
  *          "block1_path" (net_path 3) 0 = one MMA per tap (default), 1 = N-widened MMAs: the three dx taps as column
  *          blocks of one MMA, combined by warp shuffles in the epilogue (correct, measured slower: epilogue-bound);
  *          "stft_f64"  1 = float64 FFT (parity grade, default), 0 = float32 FFT (fast);
+ *          "stft_threads" threads per frame of the float64 FFT kernel: 16 (default: 16 x 16 decomposition, 128 registers) or
+ *          8 (32 x 8 decomposition, 255 registers); the two differ by float rounding only;
  *          "chunk"     snippets per network launch sequence;
  *          "debug_stop" stop the forward after a stage (see orcai_debug_read), -1 = off. */
 int orcai_set_option(orcai_ctx* ctx, const char* key, int64_t value);
