@@ -38,6 +38,7 @@ __global__ void select_init_kernel(SelectState* st, unsigned long long rank_lo, 
     st->rank[1] = rank_hi;
     st->prefix[0] = 0u;
     st->prefix[1] = 0u;
+    st->tile_counter = 0u;   // the passes' last-CTA ticket: a select always starts from zero, whatever an earlier failed call left
   }
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * 2048; i += gridDim.x * blockDim.x)
     (&st->hist[0][0])[i] = 0ull;
