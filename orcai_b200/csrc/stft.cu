@@ -4,6 +4,8 @@
 // reference (the "ref = np.max" shift and the top_db floor are applied by the consumers from the
 // exact global maximum this kernel produces, so no second pass over the 257-bin array exists).
 //
+// Two kernels: stft_db16_kernel (float64 default: 16 threads per frame, 2 frames per warp, stft_core16.cuh; further down) and
+// stft_db_kernel (float32 variant and the round-1 float64 decomposition, option stft_threads = 8), described here.
 // Mapping: 8 threads per frame, 4 frames per warp, 8 warps per CTA; each warp walks groups of 4
 // consecutive frames (the 50% overlap makes the second read of every sample an L1 hit).  All FFT
 // butterflies are register-resident with immediate twiddles (fft_gen.cuh); the only exchange is one
