@@ -224,16 +224,26 @@ normalise_kernel(const float* __restrict__ raw, long long T, int ld, int nb, con
   // a row is at most kRawLd = 176 floats: six coalesced loads per lane, all in flight before the first store (the loop
   // over a run-time column count kept ONE load in flight per thread: 3.4 TB/s)
   constexpr int Q = (kRawLd + 31) / 32;
-  for (long long j = (long long)blockIdx.x * (blockDim.x >> 5) + warp; j < T; j += wstride) {
-    const float* row = raw + (size_t)j * ld;
-    float* o = out + (size_t)j * nb;
-    float x[Q];
+  constexpr int R = 2;   // rows per warp iteration: twelve loads per lane in flight
+  for (long long j = (long long)blockIdx.x * (blockDim.x >> 5) + warp; j < T; j += R * wstride) {
+    float x[R][Q];
 #pragma unroll
-    for (int q = 0; q < Q; ++q) x[q] = lane + 32 * q < nb ? __ldg(row + lane + 32 * q) : 0.0f;
+    for (int r = 0; r < R; ++r) {
+      const long long jr = j + r * wstride;
+      const float* row = raw + (size_t)(jr < T ? jr : j) * ld;
 #pragma unroll
-    for (int q = 0; q < Q; ++q) {
-      const float v = shifted_db(x[q], db_ref);
-      if (lane + 32 * q < nb) o[lane + 32 * q] = (mode == 0) ? __fdiv_rn(fminf(fmaxf(v, lo), hi) - lo, range) : v;
+      for (int q = 0; q < Q; ++q) x[r][q] = lane + 32 * q < nb ? __ldg(row + lane + 32 * q) : 0.0f;
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const long long jr = j + r * wstride;
+      if (jr >= T) break;
+      float* o = out + (size_t)jr * nb;
+#pragma unroll
+      for (int q = 0; q < Q; ++q) {
+        const float v = shifted_db(x[r][q], db_ref);
+        if (lane + 32 * q < nb) o[lane + 32 * q] = (mode == 0) ? __fdiv_rn(fminf(fmaxf(v, lo), hi) - lo, range) : v;
+      }
     }
   }
 }
