@@ -224,7 +224,7 @@ normalise_kernel(const float* __restrict__ raw, long long T, int ld, int nb, con
   // a row is at most kRawLd = 176 floats: six coalesced loads per lane, all in flight before the first store (the loop
   // over a run-time column count kept ONE load in flight per thread: 3.4 TB/s)
   constexpr int Q = (kRawLd + 31) / 32;
-  constexpr int R = 2;   // rows per warp iteration: twelve loads per lane in flight
+  constexpr int R = 4;   // rows per warp iteration: twenty-four loads per lane in flight
   for (long long j = (long long)blockIdx.x * (blockDim.x >> 5) + warp; j < T; j += R * wstride) {
     float x[R][Q];
 #pragma unroll
